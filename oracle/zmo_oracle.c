@@ -110,7 +110,7 @@ static inline u32 jenkins32(u32 key){
 
 /* ------------------------------------------------------------------ parameters (wtzmo.c:1543-1588) */
 typedef struct {
-	int ncpu, n_job, i_job, do_align, min_rdlen, overwrite, skip_contained, refine, debug;
+	int ncpu, n_job, i_job, do_align, min_rdlen, overwrite, skip_contained, write_contained, refine, debug;
 	int hk, hz, ksize, zsize, kwin, kstep, kovl, ksave, n_idx, ztot, zovl, kcut, zcut, kvar;
 	float wnorm, wrep;
 	int ncand, nbest;
@@ -123,7 +123,7 @@ typedef struct {
 
 static void zparams_default(zparams_t *p){
 	memset(p, 0, sizeof(*p));
-	p->ncpu = 1; p->n_job = 1; p->i_job = 0; p->do_align = 1; p->skip_contained = 1;
+	p->ncpu = 1; p->n_job = 1; p->i_job = 0; p->do_align = 1; p->skip_contained = 1; p->write_contained = 1;
 	p->hk = 1; p->hz = 1; p->ksize = 16; p->zsize = 10; p->kwin = 800; p->kovl = 300; p->ksave = 4; p->n_idx = 1;
 	p->wnorm = 20; p->wrep = 100; p->ncand = 500; p->nbest = 100; p->ztot = 300; p->zovl = 200; p->kcut = 0; p->zcut = 64; p->kvar = 2;
 	p->w = 50; p->ew = 800; p->W = 3200; p->M = 2; p->X = -5; p->O = -3; p->E = -1; p->T = -50; p->min_score = 200; p->min_id = 0.5;
@@ -1521,7 +1521,7 @@ int main(int argc, char **argv){
 			case '9': pairoutf = optarg; break;
 			case 'S': par->ksave = atoi(optarg); break;
 			case 'f': par->overwrite = 1; break;
-			case 'C': par->skip_contained = 0; break;
+			case 'C': par->write_contained = 0; break;   /* -C never reaches wt->skip_contained (wtzmo.c:168,1609,1781): it only suppresses the .contained file */
 			case 'H': par->hk = atoi(optarg); par->hz = (par->hk >> 1) & 1; par->hk &= 1; break;
 			case 'k': par->ksize = atoi(optarg); break;
 			case 'K': par->kcut = atoi(optarg); break;
@@ -1625,7 +1625,7 @@ int main(int argc, char **argv){
 	out = strcmp(output, "-")? fopen(output, "w") : stdout;
 	run_overlap(z, out);
 	if(strcmp(output, "-")) fclose(out);
-	if(par->skip_contained && strcmp(output, "-")){
+	if(par->write_contained && strcmp(output, "-")){
 		char *maskf = malloc(strlen(output) + 16); FILE *mf;
 		sprintf(maskf, "%s.contained", output); mf = fopen(maskf, "w");
 		for(i=0;i<z->rs.n_rd;i++) if(z->masked[i]) fprintf(mf, "%s\n", z->rs.reads.a[i].name);
