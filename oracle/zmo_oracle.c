@@ -1644,3 +1644,86 @@ int main(int argc, char **argv){
 	return 0;
 }
 #endif
+
+/* ------------------------------------------------------------------ library exports for the tests (same shapes as ref_shim.c) */
+#ifdef ZMO_ORACLE_LIB
+static void orc_export(aln_t x, int *out){ out[0]=x.score; out[1]=x.tb; out[2]=x.te; out[3]=x.qb; out[4]=x.qe; out[5]=x.aln; out[6]=x.mat; out[7]=x.mis; out[8]=x.ins; out[9]=x.del; }
+static zparams_t orc_par(int zsize, int hz, int zcut, int kvar, int kwin, int kstep, int zovl, int ztot, int W){
+	zparams_t p; zparams_default(&p); p.zsize = zsize; p.hz = hz; p.zcut = zcut; p.kvar = kvar; p.kwin = kwin; p.kstep = kstep; p.zovl = zovl; p.ztot = ztot; p.W = W; return p;
+}
+int orc_extend(int mode, int qlen, u8 *q, int tlen, u8 *t, int strand, int init, int W, int M, int X, int I, int D, int E, int T, int *out, u32 *cigar_out, int cigar_cap){
+	u32v cg; int n, i; aln_t x; vec_init(cg);
+	x = banded_extend(mode, qlen, q, tlen, t, strand, init, W, M, X, I, D, E, T, &cg);
+	orc_export(x, out); n = (int)cg.n;
+	for(i=0;i<n&&i<cigar_cap;i++) cigar_out[i] = cg.a[i];
+	vec_free(cg); return n;
+}
+int orc_global2(int qlen, u8 *q, int tlen, u8 *t, int M, int X, int o_del, int e_del, int o_ins, int e_ins, int w, int *score_out, u32 *cigar_out, int cigar_cap){
+	u32v cg; int n, i; vec_init(cg);
+	*score_out = banded_global(qlen, q, tlen, t, M, X, o_del, e_del, o_ins, e_ins, w, &cg);
+	n = (int)cg.n; for(i=0;i<n&&i<cigar_cap;i++) cigar_out[i] = cg.a[i];
+	vec_free(cg); return n;
+}
+int orc_hz_align(u8 *pb1, u32 len1, u8 *pb2, u32 len2, int M, int I, int D, int E, int *out, u32 *cigar_out, int cigar_cap){
+	u32v cg; int n, i; aln_t x; vec_init(cg);
+	x = runlen_align(pb1, len1, pb2, len2, M, I, D, E, &cg);
+	orc_export(x, out); n = (int)cg.n; for(i=0;i<n&&i<cigar_cap;i++) cigar_out[i] = cg.a[i];
+	vec_free(cg); return n;
+}
+static int gt_u64_asc(const void *a, const void *b, void *c){ (void)c; return *(const u64*)a > *(const u64*)b; }
+static int gt_u64_hi_asc(const void *a, const void *b, void *c){ (void)c; return (*(const u64*)a >> 32) > (*(const u64*)b >> 32); }
+static int gt_u64_hi_desc(const void *a, const void *b, void *c){ (void)c; return (*(const u64*)b >> 32) > (*(const u64*)a >> 32); }
+void orc_sort_u64_asc(u64 *a, size_t n){ ref_sort(a, n, 8, gt_u64_asc, NULL); }
+void orc_sort_u64_lo32_desc(u64 *a, size_t n){ ref_sort(a, n, 8, gt_cand_ol_desc, NULL); }
+void orc_sort_u64_hi32_asc(u64 *a, size_t n){ ref_sort(a, n, 8, gt_u64_hi_asc, NULL); }
+void orc_sort_u64_hi32_desc(u64 *a, size_t n){ ref_sort(a, n, 8, gt_u64_hi_desc, NULL); }
+
+int orc_pair_windows(u8 *pb1, int alen, u8 *pb2, int blen, int zsize, int hz, int zcut, int kvar, int kwin, int kstep, int zovl, int ztot, int W,
+		int *n_hzmp, int *ovl, int *win_out, int win_cap, int *anc_out, int anc_cap, int *n_anc_out){
+	zparams_t par = orc_par(zsize, hz, zcut, kvar, kwin, kstep, zovl, ztot, W);
+	zindex_t zi; zpairv cache; pair_seed_t ps; int d, nw = 0, na = 0; size_t j; u32 k;
+	memset(&zi, 0, sizeof(zi)); vec_init(cache); pair_seed_init(&ps);
+	zindex_build(&zi, pb1, alen, &par);
+	zmatch(&zi, pb2, blen, &par, &cache);
+	/* the shim reports windows of every strand with windows, regardless of ztot; mirror that */
+	*n_hzmp = (int)cache.n; ovl[0] = ovl[1] = 0;
+	if(cache.n * par.zsize >= (u32)par.ztot){
+		ref_sort(cache.a, cache.n, sizeof(zpair_t), gt_zpair_off12, NULL);
+		for(d=0;d<2;d++){
+			winv w2; zpairv a2; vec_init(w2); vec_init(a2);
+			if(pair_windows_strand(cache.a, (u32)cache.n, d, &w2, &a2, &par)){
+				ovl[d] = chain_windows(w2.a, (u32)w2.n, par.W);
+				for(j=0;j<w2.n;j++){
+					win_t *w = &w2.a[j];
+					if(w->closed) continue;
+					if(nw < win_cap){ int *o = win_out + 7 * nw; o[0]=d; o[1]=w->beg[0]; o[2]=w->end[0]; o[3]=w->beg[1]; o[4]=w->end[1]; o[5]=w->ovl; o[6]=w->anc[1]-w->anc[0]; }
+					nw ++;
+					for(k=w->anc[0];k<w->anc[1];k++){
+						zpair_t *p = &a2.a[k];
+						if(na < anc_cap){ int *o = anc_out + 6 * na; o[0]=p->off1; o[1]=p->off2; o[2]=p->len1; o[3]=p->len2; o[4]=p->dir1; o[5]=p->dir2; }
+						na ++;
+					}
+				}
+			}
+			vec_free(w2); vec_free(a2);
+		}
+	}
+	*n_anc_out = na;
+	vec_free(cache); vec_free(zi.seeds); vec_free(zi.slots); pair_seed_free(&ps);
+	return nw;
+}
+int orc_pair_dotmatrix(u8 *pb1, int alen, u8 *pb2, int blen, int zsize, int hz, int zcut, int kvar, int xvar, int yvar, int min_block_len, int max_overhang, float dev_pen, float gap_pen, int *out){
+	zparams_t par = orc_par(zsize, hz, zcut, kvar, 800, 400, 200, 300, 3200);
+	zindex_t zi; zpairv cache; dotres_t r; int n;
+	par.xvar = xvar; par.yvar = yvar; par.min_block_len = min_block_len; par.max_overhang = max_overhang; par.deviation_penalty = dev_pen; par.gap_penalty = gap_pen;
+	memset(&zi, 0, sizeof(zi)); vec_init(cache);
+	zindex_build(&zi, pb1, alen, &par);
+	zmatch(&zi, pb2, blen, &par, &cache);
+	n = (int)cache.n;
+	r = dot_matrix_pair(&cache, alen, blen, &par);
+	out[0]=r.score; out[1]=r.qb; out[2]=r.qe; out[3]=r.tb; out[4]=r.te; out[5]=r.strand;
+	vec_free(cache); vec_free(zi.seeds); vec_free(zi.slots);
+	return n;
+}
+/* full pair alignment on explicit windows/anchors is exercised through the whole-program runs */
+#endif

@@ -1,0 +1,211 @@
+/*
+ * zmo_dp.cu -- DP kernels (persistent executors pulling jobs from a device work counter) and the
+ * stand-alone DP operators of the C ABI.
+ */
+#include "zmo_jobs.cuh"
+
+#define EXT_NT 256
+#define EXT_C  7
+#define EXT_CAP 2048
+#define EXT_SEQW 4096
+#define WRP_C  7
+#define WRP_CAP 256
+#define WRP_SEQW 256
+#define WRP_PER_CTA 4
+
+/* CTA-per-job extension kernel (wide bands: end extensions with ew up to 1022 in shared memory) */
+template<int MODE>
+__global__ void __launch_bounds__(EXT_NT) k_ext_cta(const DPJob *jobs, const uint32_t *order, uint32_t njobs, DevReads R, DPPar P,
+		uint32_t *arena, uint32_t *cig_arena, DPRes *res, unsigned long long *ctr, int ctr_work, int ctr_cells){
+	__shared__ int s_h[3 * EXT_CAP];
+	__shared__ uint32_t s_seq[EXT_SEQW];
+	__shared__ int s_red[2 * (EXT_NT / 32)];
+	__shared__ long long s_redk[EXT_NT / 32];
+	__shared__ int s_misc[16];
+	__shared__ uint32_t s_job;
+	ExecSmem<EXT_NT> X; X.carve(s_h, EXT_CAP, s_seq, EXT_SEQW, s_red, s_redk, s_misc);
+	const int tid = threadIdx.x;
+	while(1){
+		if(tid == 0) s_job = (uint32_t)atomicAdd(ctr + ctr_work, 1ULL);
+		__syncthreads();
+		const uint32_t jn = s_job;
+		__syncthreads();
+		if(jn >= njobs) break;
+		run_ext_job<EXT_NT, EXT_C, MODE>(jobs[order? order[jn] : jn], R, P, X, arena, cig_arena, res, ctr + ctr_cells, tid);
+		__syncthreads();
+	}
+}
+
+/* warp-per-job extension kernel (narrow bands) */
+template<int MODE>
+__global__ void __launch_bounds__(32 * WRP_PER_CTA) k_ext_warp(const DPJob *jobs, const uint32_t *order, uint32_t njobs, DevReads R, DPPar P,
+		uint32_t *arena, uint32_t *cig_arena, DPRes *res, unsigned long long *ctr, int ctr_work, int ctr_cells){
+	__shared__ int s_h[WRP_PER_CTA][3 * WRP_CAP];
+	__shared__ uint32_t s_seq[WRP_PER_CTA][WRP_SEQW];
+	__shared__ int s_misc[WRP_PER_CTA][16];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	ExecSmem<32> X; X.carve(s_h[warp], WRP_CAP, s_seq[warp], WRP_SEQW, nullptr, nullptr, s_misc[warp]);
+	while(1){
+		uint32_t jn = 0;
+		if(lane == 0) jn = (uint32_t)atomicAdd(ctr + ctr_work, 1ULL);
+		jn = __shfl_sync(0xffffffffu, jn, 0);
+		if(jn >= njobs) break;
+		run_ext_job<32, WRP_C, MODE>(jobs[order? order[jn] : jn], R, P, X, arena, cig_arena, res, ctr + ctr_cells, lane);
+		__syncwarp();
+	}
+}
+
+__global__ void __launch_bounds__(32 * WRP_PER_CTA) k_glb_warp(const DPJob *jobs, const uint32_t *order, uint32_t njobs, DevReads R, DPPar P,
+		uint32_t *arena, uint32_t *cig_arena, DPRes *res, unsigned long long *ctr, int ctr_work, int ctr_cells){
+	__shared__ int s_h[WRP_PER_CTA][3 * WRP_CAP];
+	__shared__ uint32_t s_seq[WRP_PER_CTA][WRP_SEQW];
+	__shared__ int s_misc[WRP_PER_CTA][16];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	ExecSmem<32> X; X.carve(s_h[warp], WRP_CAP, s_seq[warp], WRP_SEQW, nullptr, nullptr, s_misc[warp]);
+	while(1){
+		uint32_t jn = 0;
+		if(lane == 0) jn = (uint32_t)atomicAdd(ctr + ctr_work, 1ULL);
+		jn = __shfl_sync(0xffffffffu, jn, 0);
+		if(jn >= njobs) break;
+		run_glb_job<32, WRP_C>(jobs[order? order[jn] : jn], R, P, X, arena, cig_arena, res, ctr + ctr_cells, lane);
+		__syncwarp();
+	}
+}
+
+/* CTA-per-job global kernel for gaps whose band does not fit a warp executor comfortably */
+__global__ void __launch_bounds__(EXT_NT) k_glb_cta(const DPJob *jobs, const uint32_t *order, uint32_t njobs, DevReads R, DPPar P,
+		uint32_t *arena, uint32_t *cig_arena, DPRes *res, unsigned long long *ctr, int ctr_work, int ctr_cells){
+	__shared__ int s_h[3 * EXT_CAP];
+	__shared__ uint32_t s_seq[EXT_SEQW];
+	__shared__ int s_red[2 * (EXT_NT / 32)];
+	__shared__ long long s_redk[EXT_NT / 32];
+	__shared__ int s_misc[16];
+	__shared__ uint32_t s_job;
+	ExecSmem<EXT_NT> X; X.carve(s_h, EXT_CAP, s_seq, EXT_SEQW, s_red, s_redk, s_misc);
+	const int tid = threadIdx.x;
+	while(1){
+		if(tid == 0) s_job = (uint32_t)atomicAdd(ctr + ctr_work, 1ULL);
+		__syncthreads();
+		const uint32_t jn = s_job;
+		__syncthreads();
+		if(jn >= njobs) break;
+		run_glb_job<EXT_NT, EXT_C>(jobs[order? order[jn] : jn], R, P, X, arena, cig_arena, res, ctr + ctr_cells, tid);
+		__syncthreads();
+	}
+}
+
+static DPPar dp_par(const zmo_ctx *c){ DPPar P; P.M = c->par.M; P.X = c->par.X; P.I = c->par.O; P.D = c->par.O; P.E = c->par.E; P.T = c->par.T; return P; }
+
+/* ---- launch helpers used by the API and the pipeline --------------------------------------- */
+int zmo_launch_ext(zmo_ctx *c, int mode, bool wide, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells){
+	if(n == 0) return 0;
+	unsigned long long *ctr = c->d_ctr.as<unsigned long long>();
+	CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORK, 0, 8, c->stream));
+	DevReads R = dev_reads(c); DPPar P = dp_par(c);
+	if(wide){
+		int grid = (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 4);
+		if(mode == 1) k_ext_cta<1><<<grid, EXT_NT, 0, c->stream>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, CTR_WORK, ctr_cells);
+		else k_ext_cta<0><<<grid, EXT_NT, 0, c->stream>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, CTR_WORK, ctr_cells);
+	} else {
+		int grid = (int)std::min<uint64_t>((n + WRP_PER_CTA - 1) / WRP_PER_CTA, (uint64_t)c->n_sm * 8);
+		if(mode == 1) k_ext_warp<1><<<grid, 32 * WRP_PER_CTA, 0, c->stream>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, CTR_WORK, ctr_cells);
+		else k_ext_warp<0><<<grid, 32 * WRP_PER_CTA, 0, c->stream>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, CTR_WORK, ctr_cells);
+	}
+	c->launches++;
+	CUDA_TRY(cudaGetLastError());
+	return 0;
+}
+int zmo_launch_glb(zmo_ctx *c, bool wide, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells){
+	if(n == 0) return 0;
+	unsigned long long *ctr = c->d_ctr.as<unsigned long long>();
+	CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORK, 0, 8, c->stream));
+	DevReads R = dev_reads(c); DPPar P = dp_par(c);
+	if(wide){
+		int grid = (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 4);
+		k_glb_cta<<<grid, EXT_NT, 0, c->stream>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, CTR_WORK, ctr_cells);
+	} else {
+		int grid = (int)std::min<uint64_t>((n + WRP_PER_CTA - 1) / WRP_PER_CTA, (uint64_t)c->n_sm * 8);
+		k_glb_warp<<<grid, 32 * WRP_PER_CTA, 0, c->stream>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, CTR_WORK, ctr_cells);
+	}
+	c->launches++;
+	CUDA_TRY(cudaGetLastError());
+	return 0;
+}
+
+/* ---- stand-alone operators ------------------------------------------------------------------ */
+static int dp_batch(zmo_ctx *c, int kind /*0 ext mode0, 1 ext mode1, 2 global*/, const zmo_dp_problem_t *probs, const int32_t *wv, uint32_t n,
+		zmo_dp_result_t *res, uint32_t *cigars, uint64_t cigar_cap, uint64_t *cigar_needed){
+	if(!c || (n && (!probs || !res))) return zmo_set_err(ZMO_ERR_ARG, "null argument");
+	if(n == 0){ if(cigar_needed) *cigar_needed = 0; return 0; }
+	DPPar P = dp_par(c);
+	std::vector<DPJob> jw, jn; std::vector<uint32_t> iw, in_;
+	uint64_t scratch = 0, cig = 0;
+	for(uint32_t i = 0; i < n; i++){
+		const zmo_dp_problem_t &p = probs[i]; DPJob J; memset(&J, 0, sizeof(J));
+		if(p.q_rid >= c->n_reads || p.t_rid >= c->n_reads) return zmo_set_err(ZMO_ERR_ARG, "problem %u: read id out of range", i);
+		J.q_rid = p.q_rid; J.t_rid = p.t_rid; J.q_start = p.q_start; J.q_step = p.q_step; J.q_comp = p.q_comp; J.qlen = p.qlen;
+		J.t_start = p.t_start; J.t_step = p.t_step; J.t_comp = p.t_comp; J.tlen = p.tlen; J.init = p.init_score; J.Wp = p.W; J.Wmax = 0;
+		J.out_idx = i; J.cig_off = cig; J.cig_cap = (uint32_t)((p.qlen > 0? p.qlen : 0) + (p.tlen > 0? p.tlen : 0) + 4);
+		cig += J.cig_cap;
+		bool wide;
+		if(kind == 2){
+			J.Wp = wv[i];
+			int w = J.Wp, dl = abs(p.qlen - p.tlen); while(w < dl) w <<= 1;
+			int bw = std::min(p.qlen, 2 * w + 1);
+			wide = bw > 32 * WRP_C * 2;
+			J.scratch = scratch;
+			scratch += wide? glb_scratch_words<EXT_NT, EXT_C>(p.qlen, p.tlen, EXT_CAP) : glb_scratch_words<32, WRP_C>(p.qlen, p.tlen, WRP_CAP);
+		} else {
+			int init = p.init_score < 0? 0 : p.init_score;
+			BandDims d; d.W = 0; d.ql = d.tl = d.ncol = 0;
+			if(p.qlen > 0 && p.tlen > 0) d = band_dims(p.qlen, p.tlen, init, p.W, P);
+			wide = d.ncol > 32 * WRP_C;
+			J.scratch = scratch;
+			scratch += wide? ext_scratch_words<EXT_NT, EXT_C>(d, EXT_CAP) : ext_scratch_words<32, WRP_C>(d, WRP_CAP);
+		}
+		if(wide){ jw.push_back(J); } else { jn.push_back(J); }
+	}
+	if(cigar_needed) *cigar_needed = cig;
+	if(cig > cigar_cap) return zmo_set_err(ZMO_ERR_CAPACITY, "cigar buffer too small: need %llu", (unsigned long long)cig);
+	if(c->arena.reserve((scratch + 64) * 4)) return ZMO_ERR_CUDA;
+	if(c->s0.reserve((jw.size() + jn.size() + 1) * sizeof(DPJob))) return ZMO_ERR_CUDA;
+	if(c->s1.reserve((size_t)(n + 1) * sizeof(DPRes))) return ZMO_ERR_CUDA;
+	if(c->s2.reserve((cig + 16) * 4)) return ZMO_ERR_CUDA;
+	DPJob *dj = c->s0.as<DPJob>();
+	if(jw.size()) CUDA_TRY(cudaMemcpyAsync(dj, jw.data(), jw.size() * sizeof(DPJob), cudaMemcpyHostToDevice, c->stream));
+	if(jn.size()) CUDA_TRY(cudaMemcpyAsync(dj + jw.size(), jn.data(), jn.size() * sizeof(DPJob), cudaMemcpyHostToDevice, c->stream));
+	{
+		StageTimer t(c, kind == 2? ST_GAP : (kind == 1? ST_EXT : ST_WINALN));
+		int cc = kind == 2? CTR_CELLS_GAP : (kind == 1? CTR_CELLS_EXT : CTR_CELLS_WIN);
+		if(kind == 2){
+			if(zmo_launch_glb(c, true, dj, nullptr, (uint32_t)jw.size(), c->arena.as<uint32_t>(), c->s2.as<uint32_t>(), c->s1.as<DPRes>(), cc)) return ZMO_ERR_CUDA;
+			if(zmo_launch_glb(c, false, dj + jw.size(), nullptr, (uint32_t)jn.size(), c->arena.as<uint32_t>(), c->s2.as<uint32_t>(), c->s1.as<DPRes>(), cc)) return ZMO_ERR_CUDA;
+		} else {
+			if(zmo_launch_ext(c, kind, true, dj, nullptr, (uint32_t)jw.size(), c->arena.as<uint32_t>(), c->s2.as<uint32_t>(), c->s1.as<DPRes>(), cc)) return ZMO_ERR_CUDA;
+			if(zmo_launch_ext(c, kind, false, dj + jw.size(), nullptr, (uint32_t)jn.size(), c->arena.as<uint32_t>(), c->s2.as<uint32_t>(), c->s1.as<DPRes>(), cc)) return ZMO_ERR_CUDA;
+		}
+	}
+	std::vector<DPRes> hr(n);
+	CUDA_TRY(cudaMemcpyAsync(hr.data(), c->s1.p, (size_t)n * sizeof(DPRes), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(cigars, c->s2.p, cig * 4, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	/* CIGARs come back in walk order (end -> start); flip each to alignment order like the reference's reverse_u32list */
+	std::vector<const DPJob*> all; for(auto &j : jw) all.push_back(&j); for(auto &j : jn) all.push_back(&j);
+	for(const DPJob *j : all){
+		const DPRes &r = hr[j->out_idx]; zmo_dp_result_t &o = res[j->out_idx];
+		o.score = r.score; o.qe = r.qe; o.te = r.te; o.mat = r.mat; o.mis = r.mis; o.ins = r.ins; o.del = r.del; o.aln = r.mat + r.mis + r.ins + r.del;
+		o.cigar_off = j->cig_off; o.n_cigar = (uint32_t)r.ncig; o.cells = (uint64_t)r.w_used;
+		uint32_t *cg = cigars + j->cig_off;
+		for(int a = 0, b = r.ncig - 1; a < b; a++, b--){ uint32_t t = cg[a]; cg[a] = cg[b]; cg[b] = t; }
+	}
+	return 0;
+}
+
+extern "C" int zmo_dp_extend(zmo_ctx *ctx, int mode, const zmo_dp_problem_t *probs, uint32_t n, zmo_dp_result_t *res, uint32_t *cigars, uint64_t cigar_cap, uint64_t *cigar_needed){
+	if(mode != 0 && mode != 1) return zmo_set_err(ZMO_ERR_ARG, "mode must be 0 or 1");
+	return dp_batch(ctx, mode, probs, nullptr, n, res, cigars, cigar_cap, cigar_needed);
+}
+extern "C" int zmo_dp_global(zmo_ctx *ctx, const zmo_dp_problem_t *probs, const int32_t *w, uint32_t n, zmo_dp_result_t *res, uint32_t *cigars, uint64_t cigar_cap, uint64_t *cigar_needed){
+	if(n && !w) return zmo_set_err(ZMO_ERR_ARG, "null band array");
+	return dp_batch(ctx, 2, probs, w, n, res, cigars, cigar_cap, cigar_needed);
+}
