@@ -1,0 +1,907 @@
+/*
+ * wtzmo_main.c -- B200 build of SMARTdenovo's `wtzmo` overlapper: same command line, same
+ * .ovl / .dmo.ovl / .contained / -9 outputs (wtzmo.c:1422-1812), so smartdenovo.pl, run_zmo.sh and
+ * run_dmo.sh work unchanged.
+ *
+ * The host keeps what is inherently sequential in the reference -- option parsing, FASTA/FASTQ
+ * loading into the 2-bit bank, the length sort, and the read-by-read STATE REPLAY (masked reads, tried
+ * pairs, per-read overlap counters, candidate heap quirks, repeat weighting, nbest/containment
+ * breaks, wtzmo.c:803-1134,1170-1357) -- and calls libzmo_b200.so (include/zmo_b200.h) for every
+ * numeric stage.  The pthread worker pool of thread.h is replaced by batch dispatch onto the GPU:
+ * reads are processed in id order in speculative batches; the device computes the pure per-read /
+ * per-pair results for a superset of what the state machine will consume, and the replay then walks
+ * the reads exactly in `-t 1` order, so the output is byte-identical to `wtzmo -t 1`.
+ * There is no CPU implementation of the numeric stages in this program: without a usable GPU it
+ * stops with an error.
+ */
+#define _GNU_SOURCE
+#include <stdio.h>
+#include <stdlib.h>
+#include <stdint.h>
+#include <string.h>
+#include <getopt.h>
+#include <math.h>
+#include <time.h>
+#include <sys/stat.h>
+#include <sys/time.h>
+#include "../../../include/zmo_b200.h"
+
+
+typedef uint8_t u8; typedef uint16_t u16; typedef uint32_t u32; typedef uint64_t u64; typedef int32_t i32; typedef int64_t i64;
+
+/* ------------------------------------------------------------------ growable array */
+#define VEC(T) struct { T *a; size_t n, m; }
+#define vec_init(v) ((v).a = NULL, (v).n = (v).m = 0)
+#define vec_free(v) (free((v).a), (v).a = NULL, (v).n = (v).m = 0)
+#define vec_reserve(v, need) do { size_t _nd = (need); if(_nd > (v).m){ size_t _m = (v).m? (v).m : 16; while(_m < _nd) _m <<= 1; (v).a = realloc((v).a, _m * sizeof(*(v).a)); (v).m = _m; } } while(0)
+#define vec_push(v, x) do { vec_reserve(v, (v).n + 1); (v).a[(v).n++] = (x); } while(0)
+#define vec_clear(v) ((v).n = 0)
+typedef VEC(u32) u32v; typedef VEC(u64) u64v; typedef VEC(u8) u8v; typedef VEC(i32) i32v;
+
+#define imin(a,b) ((a) < (b)? (a) : (b))
+#define imax(a,b) ((a) > (b)? (a) : (b))
+#define idiff(a,b) ((a) > (b)? (a) - (b) : (b) - (a))
+
+/* ------------------------------------------------------------------ sort_array emulation (sort.h:104-155)
+ * Median-of-3 quicksort with an explicit stack that leaves partitions of <=5 elements to a final
+ * bubble pass.  Deterministic but not stable: the permutation of equal keys is part of the contract
+ * at several call sites, so the exact sequence of swaps is reproduced. */
+typedef int (*gt_fn)(const void *a, const void *b, void *ctx);
+#define SORT_MAX_ES 64
+static void ref_sort(void *base, size_t n, size_t es, gt_fn gt, void *ctx){
+	u8 *rs = (u8*)base, piv[SORT_MAX_ES], tmp[SORT_MAX_ES];
+	size_t stack[64][2], x = 0, s, e, i, j, m;
+#define EL(k) (rs + (k) * es)
+#define SWAP(p, q) do { memcpy(tmp, EL(p), es); memcpy(EL(p), EL(q), es); memcpy(EL(q), tmp, es); } while(0)
+	if(n < 2) return;
+	stack[0][0] = 0; stack[0][1] = n - 1; x = 1;
+	while(x){
+		x --; s = stack[x][0]; e = stack[x][1];
+		m = s + (e - s) / 2;
+		if(gt(EL(s), EL(m), ctx) > 0) SWAP(s, m);
+		if(gt(EL(m), EL(e), ctx) > 0){
+			SWAP(e, m);
+			if(gt(EL(s), EL(m), ctx) > 0) SWAP(s, m);
+		}
+		memcpy(piv, EL(m), es);
+		i = s + 1; j = e - 1;
+		while(1){
+			while(gt(piv, EL(i), ctx) > 0) i ++;
+			while(gt(EL(j), piv, ctx) > 0) j --;
+			if(i < j){ SWAP(i, j); i ++; j --; }
+			else break;
+		}
+		if(i == j){ i ++; j --; }
+		if(j - s > e - i){
+			if(s + 4 < j){ stack[x][0] = s; stack[x][1] = j; x ++; }
+			if(i + 4 < e){ stack[x][0] = i; stack[x][1] = e; x ++; }
+		} else {
+			if(i + 4 < e){ stack[x][0] = i; stack[x][1] = e; x ++; }
+			if(s + 4 < j){ stack[x][0] = s; stack[x][1] = j; x ++; }
+		}
+	}
+	for(i=0;i<n;i++){
+		int swapped = 0;
+		for(j=n-1;j>i;j--){
+			if(gt(EL(j - 1), EL(j), ctx) > 0){ SWAP(j - 1, j); swapped = 1; }
+		}
+		if(!swapped) break;
+	}
+#undef EL
+#undef SWAP
+}
+
+
+
+
+/* ------------------------------------------------------------------ 2-bit read store (dna.h:78,263,397-471) */
+static inline u32 bank_get(const u64 *bits, u64 off){ return (bits[off >> 5] >> (((~off) & 31) << 1)) & 3; }
+static inline void bank_put(u64 *bits, u64 off, u64 b){ if((off & 31) == 0) bits[off >> 5] = 0; bits[off >> 5] |= b << (((~off) & 31) << 1); }
+
+
+
+/* ------------------------------------------------------------------ parameters (wtzmo.c:1543-1588) */
+typedef struct {
+	int ncpu, n_job, i_job, do_align, min_rdlen, overwrite, skip_contained, write_contained, refine, debug;
+	int hk, hz, ksize, zsize, kwin, kstep, kovl, ksave, n_idx, ztot, zovl, kcut, zcut, kvar;
+	float wnorm, wrep;
+	int ncand, nbest;
+	int w, ew, W, M, X, O, E, T, min_score;
+	float min_id;
+	int dot_matrix, xvar, yvar, min_block_len, max_overhang;
+	float deviation_penalty, gap_penalty;
+	u32 max_unalign_in_contained, max_unalign_in_dovetail;
+} zparams_t;
+
+static void zparams_default(zparams_t *p){
+	memset(p, 0, sizeof(*p));
+	p->ncpu = 1; p->n_job = 1; p->i_job = 0; p->do_align = 1; p->skip_contained = 1; p->write_contained = 1;
+	p->hk = 1; p->hz = 1; p->ksize = 16; p->zsize = 10; p->kwin = 800; p->kovl = 300; p->ksave = 4; p->n_idx = 1;
+	p->wnorm = 20; p->wrep = 100; p->ncand = 500; p->nbest = 100; p->ztot = 300; p->zovl = 200; p->kcut = 0; p->zcut = 64; p->kvar = 2;
+	p->w = 50; p->ew = 800; p->W = 3200; p->M = 2; p->X = -5; p->O = -3; p->E = -1; p->T = -50; p->min_score = 200; p->min_id = 0.5;
+	p->dot_matrix = 0; p->xvar = 128; p->yvar = 64; p->min_block_len = 160; p->max_overhang = 256;
+	p->deviation_penalty = 1.0; p->gap_penalty = 0.05;
+	p->max_unalign_in_contained = 0; p->max_unalign_in_dovetail = 200; /* wtzmo.c:174-175, not settable */
+}
+
+
+
+/* ------------------------------------------------------------------ read set + FASTA/FASTQ reader
+ * Behaviour of file_reader.c:296-424 as used by wtzmo.c:1691-1703: type guessed from the first
+ * non-empty, non-'#' line; FASTA name = header up to first blank; multi-line sequences are
+ * concatenated; FASTQ = 4-line records; "*.gz" through `gzip -dc`; several files are chained. */
+typedef struct { u64 off; u32 len; char *name; } read_t;
+typedef struct {
+	u64 *bits; u64 nbases, cap_words;
+	VEC(read_t) reads;
+	u32 n_rd, n_qr;
+} readset_t;
+
+static void rs_add_read(readset_t *rs, const char *name, int name_len, const char *seq, u32 len){
+	read_t r; u32 i;
+	u64 need = (rs->nbases + len + 31) / 32 + 2;
+	if(need > rs->cap_words){ u64 m = rs->cap_words? rs->cap_words : 1024; while(m < need) m <<= 1; rs->bits = realloc(rs->bits, m * 8); memset(rs->bits + rs->cap_words, 0, (m - rs->cap_words) * 8); rs->cap_words = m; }
+	r.off = rs->nbases; r.len = len; r.name = malloc(name_len + 1); memcpy(r.name, name, name_len); r.name[name_len] = 0;
+	for(i=0;i<len;i++){
+		u64 c;
+		switch(seq[i]){ case 'A': case 'a': c = 0; break; case 'C': case 'c': c = 1; break; case 'G': case 'g': c = 2; break; case 'T': case 't': c = 3; break;
+			default: c = lrand48() & 3; }                    /* dna.h:405: unseeded lrand48 on non-ACGT */
+		bank_put(rs->bits, rs->nbases, c); rs->nbases ++;
+	}
+	vec_push(rs->reads, r);
+}
+
+typedef struct { char **files; int nfiles, fidx; FILE *fp; int is_proc; char *line; size_t cap; ssize_t n; int have_line; int type; } seqreader_t;
+
+static int sr_open_next(seqreader_t *sr){
+	while(sr->fidx < sr->nfiles){
+		const char *fn = sr->files[sr->fidx ++]; size_t l = strlen(fn);
+		if(!strcmp(fn, "-")){ sr->fp = stdin; sr->is_proc = 0; return 1; }
+		if(l > 3 && !strcmp(fn + l - 3, ".gz")){ char *cmd = malloc(l + 20); sprintf(cmd, "gzip -dc %s", fn); sr->fp = popen(cmd, "r"); free(cmd); sr->is_proc = 1; if(sr->fp) return 1; continue; }
+		sr->fp = fopen(fn, "r"); sr->is_proc = 0;
+		if(sr->fp) return 1;
+		fprintf(stderr, " -- Cannot open %s --\n", fn); exit(1);
+	}
+	return 0;
+}
+static int sr_getline(seqreader_t *sr){
+	if(sr->have_line){ sr->have_line = 0; return 1; }
+	while(1){
+		if(sr->fp == NULL && !sr_open_next(sr)) return 0;
+		sr->n = getline(&sr->line, &sr->cap, sr->fp);
+		if(sr->n >= 0){
+			while(sr->n && (sr->line[sr->n-1] == '\n')) sr->line[--sr->n] = 0;
+			return 1;
+		}
+		if(sr->is_proc) pclose(sr->fp); else if(sr->fp != stdin) fclose(sr->fp);
+		sr->fp = NULL;
+	}
+}
+/* returns 1 and fills name/seq (growable) or 0 at end */
+static int sr_next(seqreader_t *sr, u8v *name, u8v *seq){
+	size_t i;
+	if(sr->type == 0){
+		while(sr_getline(sr)){
+			if(sr->n == 0 || sr->line[0] == '#') continue;
+			sr->type = sr->line[0] == '>'? 1 : (sr->line[0] == '@'? 2 : 3);
+			sr->have_line = 1; break;
+		}
+		if(sr->type == 0) return 0;
+	}
+	vec_clear(*name); vec_clear(*seq);
+	if(sr->type == 1){
+		int flag = 0;
+		while(sr_getline(sr)){
+			if(sr->n && sr->line[0] == '>'){
+				if(flag){ sr->have_line = 1; break; }
+				flag = 1;
+				for(i=1;i<(size_t)sr->n;i++){ char ch = sr->line[i]; if(ch == ' ' || ch == '\t' || ch == '\r' || ch == '\n') break; }
+				vec_reserve(*name, i); memcpy(name->a, sr->line + 1, i - 1); name->n = i - 1;
+			} else if(flag){
+				vec_reserve(*seq, seq->n + sr->n + 1); memcpy(seq->a + seq->n, sr->line, sr->n); seq->n += sr->n;
+			}
+		}
+		return flag != 0;
+	} else if(sr->type == 2){
+		int flag = 0;
+		while(flag != 4 && sr_getline(sr)){
+			switch(flag){
+				case 0: if(sr->line[0] != '@') break; flag = 1;
+					for(i=1;i<(size_t)sr->n;i++){ char ch = sr->line[i]; if(ch == ' ' || ch == '\t' || ch == '\n') break; }
+					vec_reserve(*name, i); memcpy(name->a, sr->line + 1, i - 1); name->n = i - 1; break;
+				case 1: flag = 2; vec_reserve(*seq, sr->n + 1); memcpy(seq->a, sr->line, sr->n); seq->n = sr->n; break;
+				case 2: if(sr->line[0] != '+') break; flag = 3; break;
+				case 3: flag = 4; break;
+			}
+		}
+		return flag == 4;
+	}
+	return 0;
+}
+
+static int gt_read_len_desc(const void *a, const void *b, void *ctx){ (void)ctx; return ((const read_t*)b)->len > ((const read_t*)a)->len; }
+
+static void rs_load(readset_t *rs, char **files, int nfiles, int min_rdlen, int as_query){
+	seqreader_t sr; u8v name, seq;
+	memset(&sr, 0, sizeof(sr)); sr.files = files; sr.nfiles = nfiles;
+	vec_init(name); vec_init(seq);
+	while(sr_next(&sr, &name, &seq)){
+		if((int)seq.n < min_rdlen) continue;
+		rs_add_read(rs, (char*)name.a, (int)name.n, (char*)seq.a, (u32)seq.n);
+		if(as_query) rs->n_qr ++; else rs->n_rd ++;
+	}
+	free(sr.line); vec_free(name); vec_free(seq);
+}
+
+static u32 rs_find(const readset_t *rs, u32 n, const char *name){   /* linear/bsearch-free name lookup via a tiny hash built lazily */
+	static u32 *tab = NULL; static u32 tabsz = 0; static const readset_t *owner = NULL;
+	u32 i, h;
+	if(owner != rs){
+		free(tab); tabsz = 16; while(tabsz < 2 * n + 1) tabsz <<= 1; tab = malloc(tabsz * 4); memset(tab, 0xFF, tabsz * 4); owner = rs;
+		for(i=0;i<n;i++){ const char *s = rs->reads.a[i].name; h = 2166136261u; while(*s){ h = (h ^ (u8)*s++) * 16777619u; } h &= tabsz - 1; while(tab[h] != 0xFFFFFFFFU) h = (h + 1) & (tabsz - 1); tab[h] = i; }
+	}
+	{ const char *s = name; h = 2166136261u; while(*s){ h = (h ^ (u8)*s++) * 16777619u; } h &= tabsz - 1; }
+	while(tab[h] != 0xFFFFFFFFU){ if(!strcmp(rs->reads.a[tab[h]].name, name)) return tab[h]; h = (h + 1) & (tabsz - 1); }
+	return 0xFFFFFFFFU;
+}
+
+
+
+/* ------------------------------------------------------------------ heap macros behaviour (list.h:78-144) on u64 keyed by low 32 bits */
+static inline int cand_cmp(u64 a, u64 b){ u32 x = (u32)a, y = (u32)b; return x > y? 1 : (x < y? -1 : 0); }
+static void cheap_push(u64v *h, u64 v){
+	size_t i = h->n, j;
+	vec_push(*h, v);
+	while(i){ j = (i - 1) >> 1; if(cand_cmp(h->a[i], h->a[j]) >= 0) break; { u64 t = h->a[i]; h->a[i] = h->a[j]; h->a[j] = t; } i = j; }
+}
+static void cheap_replace0(u64v *h, u64 v){
+	size_t idx = 0, sw;
+	h->a[0] = v;
+	while((idx << 1) + 1 < h->n){
+		sw = idx;
+		if(cand_cmp(h->a[sw], h->a[(idx << 1) + 1]) > 0) sw = (idx << 1) + 1;
+		if((idx << 1) + 2 < h->n && cand_cmp(h->a[sw], h->a[(idx << 1) + 2]) > 0) sw = (idx << 1) + 2;
+		if(sw == idx) break;
+		{ u64 t = h->a[idx]; h->a[idx] = h->a[sw]; h->a[sw] = t; }
+		idx = sw;
+	}
+}
+
+/* Turn the ordered event stream of one index partition (already filtered to ol >= kovl on the
+ * device) into the candidate array (wtzmo.c:494-571).  `cands` may hold entries carried over from
+ * earlier index partitions (-G).  Quirks kept: the heap-full test looks at the CURRENT ol but inserts
+ * the PREVIOUS pending candidate; the final flush compares against ol==0; an empty stream pushes the
+ * sentinel 0xFFFFFFFF00000000. */
+static void candidates_from_events(const zmo_event_t *ev, size_t n, const zparams_t *par, u64v *cands){
+	u64 x1 = 0xFFFFFFFF00000000ULL, x2; size_t i; u32 ol = 0;
+	for(i=0;i<n;i++){
+		ol = ev[i].ol;
+		x2 = ((u64)(ev[i].tkey >> 1) << 32) | ol;
+		if((x1 >> 32) == (x2 >> 32)){ x1 = (u32)x1 > (u32)x2? x1 : x2; }
+		else if(x1 == 0xFFFFFFFF00000000ULL){ x1 = x2; }
+		else {
+			if(cands->n >= (size_t)par->ncand){ if((u32)cands->a[0] < ol) cheap_replace0(cands, x1); }
+			else cheap_push(cands, x1);
+			x1 = x2;
+		}
+	}
+	ol = 0;
+	if(cands->n >= (size_t)par->ncand){ if((u32)cands->a[0] < ol) cheap_replace0(cands, x1); }
+	else cheap_push(cands, x1);
+}
+
+/* ------------------------------------------------------------------ u64 hash set (closed pairs) */
+typedef struct { u64 *tab; size_t cap, n; } u64set_t;
+static void u64set_init(u64set_t *s){ s->cap = 1024; s->n = 0; s->tab = malloc(s->cap * 8); memset(s->tab, 0xFF, s->cap * 8); }
+static inline size_t u64set_slot(const u64set_t *s, u64 k){ u64 h = k * 0x9E3779B97F4A7C15ULL; size_t i = (h >> 20) & (s->cap - 1); while(s->tab[i] != ~0ULL && s->tab[i] != k) i = (i + 1) & (s->cap - 1); return i; }
+static int u64set_has(const u64set_t *s, u64 k){ return s->tab[u64set_slot(s, k)] == k; }
+static void u64set_add(u64set_t *s, u64 k){
+	size_t i = u64set_slot(s, k);
+	if(s->tab[i] == k) return;
+	s->tab[i] = k; s->n ++;
+	if(s->n * 2 > s->cap){
+		u64 *old = s->tab; size_t oc = s->cap, j;
+		s->cap <<= 1; s->tab = malloc(s->cap * 8); memset(s->tab, 0xFF, s->cap * 8);
+		for(j=0;j<oc;j++) if(old[j] != ~0ULL) s->tab[u64set_slot(s, old[j])] = old[j];
+		free(old);
+	}
+}
+static inline u64 pair_key(u32 a, u32 b){ return a < b? (((u64)a << 33) | ((u64)b << 1)) : (((u64)b << 33) | ((u64)a << 1)); }  /* wtzmo.c:84-85 */
+
+
+/* ------------------------------------------------------------------ records + output (wtzmo.c:1170-1249) */
+typedef struct { u32 pb1, pb2; u8 dir2; int qb, qe, tb, te, score, mat, mis, ins, del, aln; const u32 *cigar; u32 n_cigar; int has_cigar; } hit_t;
+typedef VEC(hit_t) hitv;
+typedef struct { u32 pb2; u32 ovl; u8 dir, closed; u32 cand_idx; } seed_t;
+typedef VEC(seed_t) seedv;
+#define WIN_OVL_MASK 0x1FFFFFFFU
+
+typedef struct {
+	readset_t rs; zparams_t par; zmo_ctx *ctx;
+	u8 *masked; u32 *rdcovs; u64set_t closed; u32 avg_rdlen; u32 kcut;
+	u64v *rdhits;                       /* per-read candidate carry-over, only with -G > 1 */
+	u64 n_records, aln_cols, n_tasks, n_tasks_used, n_pairs_seeded, n_batches;
+	FILE *out; char *obuf; size_t obuf_n, obuf_cap;
+	double t_dev, t_replay, t_write;
+	int batch_reads, batch_pairs;
+} wz_t;
+
+static double now_s(void){ struct timeval tv; gettimeofday(&tv, NULL); return tv.tv_sec + 1e-6 * tv.tv_usec; }
+static void die_zmo(const char *what){ fprintf(stderr, "wtzmo(b200): %s: %s\n", what, zmo_last_error()); exit(3); }
+
+static inline void ob_reserve(wz_t *z, size_t more){
+	if(z->obuf_n + more > z->obuf_cap){
+		if(z->obuf_n){ fwrite(z->obuf, 1, z->obuf_n, z->out); z->obuf_n = 0; }
+		if(more > z->obuf_cap){ z->obuf_cap = more + (1u << 20); z->obuf = realloc(z->obuf, z->obuf_cap); }
+	}
+}
+static inline void ob_flush(wz_t *z){ if(z->obuf_n){ fwrite(z->obuf, 1, z->obuf_n, z->out); z->obuf_n = 0; } }
+static inline char* put_u32(char *p, u32 v){ char t[12]; int n = 0; do { t[n++] = '0' + v % 10; v /= 10; } while(v); while(n) *p++ = t[--n]; return p; }
+
+typedef struct { hitv hits; u32v masks; u64v closed; seedv seeds; u32 rd_id; } readout_t;
+
+/* defer_masks: print the hits and merge rdcovs/closed now, but keep the read's masks pending; used at a
+ * batch boundary, because the reference tests masked[next read] BEFORE merging the previous read's
+ * masks (wtzmo.c:1315 vs 1322) */
+static void flush_read(wz_t *z, readout_t *ro, int defer_masks){
+	size_t i, k; const readset_t *rs = &z->rs;
+	if(!z->par.do_align){   /* -N: seed lines only (wtzmo.c:1176-1181) */
+		for(i=0;i<ro->seeds.n;i++){
+			seed_t *s = &ro->seeds.a[i];
+			if(s->closed) continue;
+			ob_reserve(z, 1024 + strlen(rs->reads.a[ro->rd_id].name) + strlen(rs->reads.a[s->pb2].name));
+			z->obuf_n += sprintf(z->obuf + z->obuf_n, "# %s\t%c\t%d\t%s\t%c\t%d\t%d\n", rs->reads.a[ro->rd_id].name, '+', rs->reads.a[ro->rd_id].len, rs->reads.a[s->pb2].name, "+-"[s->dir], rs->reads.a[s->pb2].len, s->ovl);
+		}
+	}
+	for(i=0;i<ro->hits.n;i++){
+		hit_t *h = &ro->hits.a[i]; u32 x1, x2; int l1 = rs->reads.a[h->pb1].len, l2 = rs->reads.a[h->pb2].len; char *p;
+		if(h->aln == 0) h->aln = 1;
+		x1 = imin(h->tb, h->qb); x2 = imin(l1 - h->te, l2 - h->qe);
+		if(x1 + x2 <= z->par.max_unalign_in_dovetail){ z->rdcovs[h->pb1] ++; z->rdcovs[h->pb2] ++; }
+		ob_reserve(z, 512 + strlen(rs->reads.a[h->pb1].name) + strlen(rs->reads.a[h->pb2].name) + (size_t)h->n_cigar * 11);
+		z->obuf_n += sprintf(z->obuf + z->obuf_n, "%s\t%c\t%d\t%d\t%d\t%s\t%c\t%d\t%d\t%d\t%d\t%0.3f\t%d\t%d\t%d\t%d\t", rs->reads.a[h->pb1].name, '+', l1, h->tb, h->te,
+			rs->reads.a[h->pb2].name, "+-"[h->dir2], l2, h->qb, h->qe, h->score, 1.0 * h->mat / h->aln, h->mat, h->mis, h->ins, h->del);
+		p = z->obuf + z->obuf_n;
+		if(h->has_cigar){          /* kswx_cigar2string (kswx.h:1093-1120) */
+			for(k=0;k<h->n_cigar;k++){
+				u32 op = h->cigar[k] & 0xF, len = h->cigar[k] >> 4;
+				if(len == 0) continue;
+				if(op > 2){ fprintf(stderr, " -- CIGAR only support M(0),I(1),D(2) cigar, but met ?(%d) --\n", op); exit(1); }
+				p = put_u32(p, len); *p++ = "MIDX"[op];
+			}
+		} else { *p++ = '0'; *p++ = 'M'; }
+		*p++ = '\n';
+		z->obuf_n = p - z->obuf;
+		z->n_records ++;
+		z->aln_cols += z->par.dot_matrix? (u64)h->aln : (u64)(h->mat + h->mis + h->ins + h->del);
+	}
+	vec_clear(ro->hits); vec_clear(ro->seeds);
+	if(!defer_masks){ for(i=0;i<ro->masks.n;i++) z->masked[ro->masks.a[i]] = 1; vec_clear(ro->masks); }
+	for(i=0;i<ro->closed.n;i++) u64set_add(&z->closed, ro->closed.a[i]);
+	vec_clear(ro->closed);
+}
+static void masks_put(u32v *m, u32 id){ size_t i; for(i=0;i<m->n;i++) if(m->a[i] == id) return; vec_push(*m, id); }
+
+static int gt_cand_ol_desc(const void *a, const void *b, void *ctx){ (void)ctx; return (u32)(*(const u64*)b) > (u32)(*(const u64*)a); }
+static int gt_seed_ovl_desc(const void *a, const void *b, void *ctx){ (void)ctx; return ((const seed_t*)b)->ovl > ((const seed_t*)a)->ovl; }
+
+/* ------------------------------------------------------------------ batch engine
+ * One batch = a run of consecutive eligible reads.  Device phases:
+ *   A  zmo_candidates      -> ordered (target,strand,ol) events per read           (pure)
+ *   B  zmo_pair_windows    -> z-matches, windows, chain weights per (read,cand)    (pure)
+ *   C  zmo_pair_align      -> alignment record + CIGAR per (read,cand,strand)      (pure)
+ * followed by the sequential replay of the reference state machine, which only CONSUMES results. */
+typedef struct {
+	u32 rd_id; int skip;                /* skip: bcov >= nbest at batch build time (nothing to compute) */
+	u64v cands_raw;                     /* candidate array in heap order after this partition's events */
+	u32v cand_pair;                     /* per raw candidate: pair index in the batch, 0xFFFFFFFF = none */
+} bread_t;
+typedef struct {
+	VEC(bread_t) reads;
+	VEC(zmo_pair_t) pairs;
+	zmo_pairseed_t *seeds; zmo_window_t *wins; size_t wins_cap;
+	VEC(zmo_task_t) tasks; u32 *task_of_pair;   /* pair -> task index (dir = chosen strand) or 0xFFFFFFFF */
+	zmo_record_t *recs; u32 *cigars; size_t cig_cap;
+	zmo_dotres_t *dots;
+} batch_t;
+
+static u32 read_nbest(const wz_t *z, u32 pbid){
+	u32 nbest = (u32)(((size_t)z->par.nbest) * z->rs.reads.a[pbid].len / z->avg_rdlen);
+	if(nbest < (u32)z->par.nbest) nbest = z->par.nbest;
+	return nbest;
+}
+
+/* phase A for a list of reads: events -> raw candidate arrays (appended to `carry` arrays when -G) */
+static void batch_candidates(wz_t *z, batch_t *b){
+	size_t i, nq = 0; u32 *qids = malloc((b->reads.n + 1) * 4); u64 *off = malloc((b->reads.n + 2) * 8); u32 *qmap = malloc((b->reads.n + 1) * 4);
+	zmo_event_t *ev = NULL; u64 cap = 0, need = 0; int rc;
+	for(i=0;i<b->reads.n;i++) if(!b->reads.a[i].skip){ qmap[nq] = (u32)i; qids[nq++] = b->reads.a[i].rd_id; }
+	if(nq){
+		cap = 4096 + 512 * nq; ev = malloc(cap * sizeof(zmo_event_t));
+		rc = zmo_candidates(z->ctx, qids, (u32)nq, off, ev, cap, &need);
+		if(rc == ZMO_ERR_CAPACITY){ cap = need + 16; ev = realloc(ev, cap * sizeof(zmo_event_t)); rc = zmo_candidates(z->ctx, qids, (u32)nq, off, ev, cap, &need); }
+		if(rc) die_zmo("zmo_candidates");
+		for(i=0;i<nq;i++){
+			bread_t *r = &b->reads.a[qmap[i]];
+			if(z->rdhits){ u64v *h = &z->rdhits[r->rd_id]; vec_clear(r->cands_raw); vec_reserve(r->cands_raw, h->n + 1); memcpy(r->cands_raw.a, h->a, h->n * 8); r->cands_raw.n = h->n; }
+			candidates_from_events(ev + off[i], (size_t)(off[i + 1] - off[i]), &z->par, &r->cands_raw);
+		}
+	}
+	free(qids); free(off); free(qmap); free(ev);
+}
+
+/* candidate post-filter with the CURRENT state (wtzmo.c:813-822); keeps cand_pair aligned with cands */
+static void filter_sort_candidates(wz_t *z, u32 pbid, u64v *c, u32v *cp){
+	size_t i, n = c->n; u64 *tmp;
+	for(i=0;i<n;i++) if(u64set_has(&z->closed, pair_key(pbid, (u32)(c->a[i] >> 32)))) c->a[i] &= 0xFFFFFFFF00000000ULL;
+	if(cp){
+		/* sort (value, original index) records with the reference permutation: the comparator only
+		 * looks at the low 32 bits of the value, so carrying the index along does not change it */
+		typedef struct { u64 v; u32 idx; u32 pad; } rec_t;
+		rec_t *r = malloc((n + 1) * sizeof(rec_t)); u32 *np = malloc((n + 1) * 4);
+		for(i=0;i<n;i++){ r[i].v = c->a[i]; r[i].idx = (u32)i; r[i].pad = 0; }
+		ref_sort(r, n, sizeof(rec_t), gt_cand_ol_desc, NULL);
+		for(i=0;i<n;i++){ c->a[i] = r[i].v; np[i] = cp->a[r[i].idx]; }
+		memcpy(cp->a, np, n * 4);
+		free(r); free(np);
+	} else ref_sort(c->a, n, 8, gt_cand_ol_desc, NULL);
+	while(c->n && (u32)c->a[c->n - 1] == 0) c->n --;
+	if(cp) cp->n = c->n;
+	(void)tmp;
+}
+
+/* replay of one read in SW / -N mode (wtzmo.c:803-1134) using the batch's device results */
+static void replay_read(wz_t *z, batch_t *b, bread_t *br, u32 bcov, readout_t *ro){
+	const zparams_t *par = &z->par; const readset_t *rs = &z->rs; u32 pbid = br->rd_id;
+	u32 alen = rs->reads.a[pbid].len, nbest, i, j, k, ncand; u16 *windeps; float *weights;
+	ro->rd_id = pbid;
+	nbest = read_nbest(z, pbid);
+	if(bcov >= nbest) return;
+	if(br->skip){ fprintf(stderr, "wtzmo(b200): internal error: read %u needed but was skipped at batch build\n", pbid); exit(4); }
+	filter_sort_candidates(z, pbid, &br->cands_raw, &br->cand_pair);
+	if(z->rdhits){ u64v *h = &z->rdhits[pbid]; vec_clear(*h); vec_reserve(*h, br->cands_raw.n + 1); memcpy(h->a, br->cands_raw.a, br->cands_raw.n * 8); h->n = br->cands_raw.n; }
+	windeps = calloc(alen + 1, sizeof(u16)); weights = malloc((alen + 1) * sizeof(float));
+	for(i=0;i<br->cands_raw.n;i++){
+		u32 id2 = (u32)(br->cands_raw.a[i] >> 32), pi = br->cand_pair.a[i]; const zmo_pairseed_t *ps; int dir;
+		if(pi == 0xFFFFFFFFU){ fprintf(stderr, "wtzmo(b200): internal error: pair (%u,%u) was not seeded\n", pbid, id2); exit(4); }
+		ps = &b->seeds[pi];
+		if(ps->n_zpair * (u32)par->zsize < (u32)par->ztot) continue;
+		if(par->dot_matrix){
+			const zmo_dotres_t *r = &b->dots[pi]; u32 ol;
+			vec_push(ro->closed, pair_key(id2, pbid));
+			ol = imax(r->qe - r->qb, r->te - r->tb);
+			if(r->score >= par->min_score && r->score >= (int)(par->min_id * ol)){
+				hit_t h; memset(&h, 0, sizeof(h));
+				h.pb1 = pbid; h.pb2 = id2; h.dir2 = r->strand; h.score = r->score; h.tb = r->tb; h.te = r->te; h.qb = r->qb; h.qe = r->qe;
+				h.mat = r->score; h.aln = ol; h.has_cigar = 0;
+				vec_push(ro->hits, h);
+			}
+			continue;
+		}
+		for(dir=0;dir<2;dir++) for(j=0;j<ps->n_win[dir];j++){
+			const zmo_window_t *w = &b->wins[ps->win_off[dir] + j];
+			for(k=w->beg[0];(int)k<w->end[0];k++) windeps[k] ++;
+		}
+		dir = ((u32)ps->ovl[0] & WIN_OVL_MASK) < ((u32)ps->ovl[1] & WIN_OVL_MASK);
+		if(((u32)ps->ovl[dir] & WIN_OVL_MASK) >= (u32)par->ztot){
+			seed_t s; s.pb2 = id2; s.dir = dir; s.ovl = (u32)ps->ovl[dir] & WIN_OVL_MASK; s.closed = 0; s.cand_idx = pi;
+			vec_push(ro->seeds, s);
+		}
+	}
+	if(!par->dot_matrix){
+		/* repeat weighting (wtzmo.c:933-980); float/double expression shapes kept */
+		for(i=0;i<alen;i++)
+			weights[i] = (windeps[i] <= par->wnorm)? 1.0 : ((windeps[i] >= par->wrep)? 0.0 : par->wnorm / (float)windeps[i]);
+		for(i=0;i<alen;i++) weights[i] = weights[i] * (0.3 + 0.7 * (idiff(((int)i), (int)alen / 2) / ((int)alen / 2.0)));
+		for(i=0;i<ro->seeds.n;i++){
+			seed_t *s = &ro->seeds.a[i]; const zmo_pairseed_t *ps = &b->seeds[s->cand_idx]; int blen = rs->reads.a[s->pb2].len; u32 ol = 0; double avg;
+			for(j=0;j<ps->n_win[s->dir];j++){
+				const zmo_window_t *w = &b->wins[ps->win_off[s->dir] + j];
+				avg = (w->end[0] - w->beg[0]) * weights[(w->beg[0] + w->end[0]) / 2];
+				avg = avg * (0.3 + 0.7 * (idiff(((int)((w->beg[1] + w->end[1]) / 2)), blen / 2) / (blen / 2.0)));
+				ol += avg;
+			}
+			s->ovl = ol & WIN_OVL_MASK;
+			if(ol * par->wrep < par->ztot * par->wnorm) s->closed = 1;
+		}
+		ref_sort(ro->seeds.a, ro->seeds.n, sizeof(seed_t), gt_seed_ovl_desc, NULL);
+		if(par->do_align){
+			ncand = par->ncand;
+			for(i=0;i<ro->seeds.n&&i<ncand;i++){
+				seed_t *s = &ro->seeds.a[i]; int blen = rs->reads.a[s->pb2].len; hit_t h; u32 x1, x2, x3, x4, ti; int l1 = alen, l2 = blen; const zmo_record_t *x;
+				if(s->closed){ ncand ++; continue; }
+				vec_push(ro->closed, pair_key(s->pb2, pbid));
+				ti = b->task_of_pair[s->cand_idx];
+				if(ti == 0xFFFFFFFFU || b->tasks.a[ti].dir != s->dir){ fprintf(stderr, "wtzmo(b200): internal error: pair (%u,%u) was not aligned\n", pbid, s->pb2); exit(4); }
+				x = &b->recs[ti]; z->n_tasks_used ++;
+				if(!x->ok){ s->closed = 1; ncand ++; continue; }
+				if(x->score < par->min_score || x->mat < x->aln * par->min_id) continue;
+				memset(&h, 0, sizeof(h));
+				h.pb1 = pbid; h.pb2 = s->pb2; h.dir2 = s->dir; h.score = x->score; h.tb = x->tb; h.te = x->te; h.qb = x->qb; h.qe = x->qe;
+				h.mat = x->mat; h.mis = x->mis; h.ins = x->ins; h.del = x->del; h.aln = x->aln; h.cigar = b->cigars + x->cigar_off; h.n_cigar = x->n_cigar; h.has_cigar = 1;
+				vec_push(ro->hits, h);
+				x1 = imin(h.tb, h.qb); x2 = imin(l1 - h.te, l2 - h.qe);
+				if(x1 + x2 <= par->max_unalign_in_dovetail){
+					/* wt->skip_contained is always 1: -C never reaches it (wtzmo.c:168,1609) */
+					x3 = ((h.tb == 0 && h.qb) || (h.te == l1 && h.qe < l2));
+					x4 = ((h.qb == 0 && h.tb) || (h.qe == l2 && h.te < l1));
+					x1 = l2 + h.qb - h.qe; x2 = l1 + h.tb - h.te;
+					if(x1 <= par->max_unalign_in_contained && x3 == 0){
+						if(x2 <= par->max_unalign_in_contained && x4 == 0){
+							if(l1 > l2){ masks_put(&ro->masks, h.pb2); }
+							else if(l1 < l2){ masks_put(&ro->masks, h.pb1); break; }
+							else if(h.pb2 > h.pb1){ masks_put(&ro->masks, h.pb2); continue; }
+							else { masks_put(&ro->masks, h.pb1); break; }
+						} else { masks_put(&ro->masks, h.pb2); continue; }
+						ncand ++;
+					} else if(x2 <= par->max_unalign_in_contained && x4 == 0){ masks_put(&ro->masks, h.pb1); break; }
+					bcov ++;
+					if(bcov >= nbest) break;
+				}
+			}
+		}
+	}
+	free(windeps); free(weights);
+}
+
+static void batch_free(batch_t *b){
+	size_t i;
+	for(i=0;i<b->reads.n;i++){ vec_free(b->reads.a[i].cands_raw); vec_free(b->reads.a[i].cand_pair); }
+	vec_free(b->reads); vec_free(b->pairs); vec_free(b->tasks);
+	free(b->seeds); free(b->wins); free(b->task_of_pair); free(b->recs); free(b->cigars); free(b->dots);
+	memset(b, 0, sizeof(*b));
+}
+
+/* device phases B + C for the batch */
+static void batch_compute(wz_t *z, batch_t *b){
+	const zparams_t *par = &z->par; size_t i, k; int rc; u64 need = 0;
+	/* pairs = candidates not closed as of now (the closed set only grows, so this is a superset of what the replay will ask for) */
+	for(i=0;i<b->reads.n;i++){
+		bread_t *r = &b->reads.a[i];
+		vec_reserve(r->cand_pair, r->cands_raw.n + 1); r->cand_pair.n = r->cands_raw.n;
+		for(k=0;k<r->cands_raw.n;k++){
+			u32 id2 = (u32)(r->cands_raw.a[k] >> 32), ol = (u32)r->cands_raw.a[k];
+			r->cand_pair.a[k] = 0xFFFFFFFFU;
+			if(r->skip || ol == 0 || id2 >= z->rs.n_rd + z->rs.n_qr) continue;
+			if(u64set_has(&z->closed, pair_key(r->rd_id, id2))) continue;
+			{ zmo_pair_t p; p.qid = r->rd_id; p.cid = id2; r->cand_pair.a[k] = (u32)b->pairs.n; vec_push(b->pairs, p); }
+		}
+	}
+	if(b->pairs.n == 0) return;
+	z->n_pairs_seeded += b->pairs.n;
+	if(par->dot_matrix){
+		b->dots = malloc(b->pairs.n * sizeof(zmo_dotres_t)); b->seeds = calloc(b->pairs.n, sizeof(zmo_pairseed_t));
+		if(zmo_pair_dotmatrix(z->ctx, b->pairs.a, (u32)b->pairs.n, b->dots)) die_zmo("zmo_pair_dotmatrix");
+		for(i=0;i<b->pairs.n;i++) b->seeds[i].n_zpair = b->dots[i].n_zpair;
+		return;
+	}
+	b->seeds = malloc(b->pairs.n * sizeof(zmo_pairseed_t));
+	b->wins_cap = 64 * b->pairs.n + 1024; b->wins = malloc(b->wins_cap * sizeof(zmo_window_t));
+	rc = zmo_pair_windows(z->ctx, 0, b->pairs.a, (u32)b->pairs.n, b->seeds, b->wins, b->wins_cap, &need);
+	if(rc == ZMO_ERR_CAPACITY && need > b->wins_cap){ b->wins_cap = need + 16; b->wins = realloc(b->wins, b->wins_cap * sizeof(zmo_window_t)); rc = zmo_pair_windows(z->ctx, 0, b->pairs.a, (u32)b->pairs.n, b->seeds, b->wins, b->wins_cap, &need); }
+	if(rc) die_zmo("zmo_pair_windows");
+	if(!par->do_align) return;
+	/* tasks: every pair whose better strand passes ztot (the replay decides which ones it consumes) */
+	b->task_of_pair = malloc(b->pairs.n * 4);
+	for(i=0;i<b->pairs.n;i++){
+		const zmo_pairseed_t *ps = &b->seeds[i]; int dir;
+		b->task_of_pair[i] = 0xFFFFFFFFU;
+		if(ps->n_zpair * (u32)par->zsize < (u32)par->ztot) continue;
+		dir = ((u32)ps->ovl[0] & WIN_OVL_MASK) < ((u32)ps->ovl[1] & WIN_OVL_MASK);
+		if(((u32)ps->ovl[dir] & WIN_OVL_MASK) < (u32)par->ztot) continue;
+		{ zmo_task_t t; t.pair_idx = (u32)i; t.dir = dir; b->task_of_pair[i] = (u32)b->tasks.n; vec_push(b->tasks, t); }
+	}
+	if(b->tasks.n == 0) return;
+	z->n_tasks += b->tasks.n;
+	b->recs = malloc(b->tasks.n * sizeof(zmo_record_t));
+	b->cig_cap = 4096 * b->tasks.n + (1u << 16); b->cigars = malloc(b->cig_cap * 4);
+	rc = zmo_pair_align(z->ctx, 0, b->tasks.a, (u32)b->tasks.n, b->recs, b->cigars, b->cig_cap, &need);
+	if(rc == ZMO_ERR_CAPACITY && need > b->cig_cap){ b->cig_cap = need + 16; b->cigars = realloc(b->cigars, b->cig_cap * 4); rc = zmo_pair_align(z->ctx, 0, b->tasks.a, (u32)b->tasks.n, b->recs, b->cigars, b->cig_cap, &need); }
+	if(rc) die_zmo("zmo_pair_align");
+}
+
+static void run_overlap(wz_t *z){
+	const zparams_t *par = &z->par; readset_t *rs = &z->rs; u32 j, beg, end, pbbeg = 0, pbend = 0, i_idx; u64 tot = 0; readout_t ro; zmo_index_stats_t st;
+	memset(&ro, 0, sizeof(ro)); ro.rd_id = 0xFFFFFFFFU;
+	if(rs->n_qr == 0 && rs->n_rd){ for(j=0;j<rs->n_rd;j++) tot += rs->reads.a[j].len; z->avg_rdlen = (u32)(tot / rs->n_rd); }
+	else if(rs->n_qr){ for(j=0;j<rs->n_qr;j++) tot += rs->reads.a[j + rs->n_rd].len; z->avg_rdlen = (u32)(tot / rs->n_qr); }
+	else z->avg_rdlen = 10000;
+	if(z->avg_rdlen == 0) z->avg_rdlen = 1;
+	if(par->n_idx > 1) z->rdhits = calloc(rs->n_rd + rs->n_qr, sizeof(u64v));
+	z->kcut = par->kcut;
+	if(rs->n_qr == 0){ beg = 0; end = rs->n_rd; } else { beg = rs->n_rd; end = beg + rs->n_qr; }
+	for(i_idx=0;i_idx<(u32)par->n_idx;i_idx++){
+		double t0 = now_s();
+		pbbeg = pbend; pbend = pbbeg + (rs->n_rd + par->n_idx - 1) / par->n_idx;
+		fprintf(stderr, "[wtzmo-b200] indexing %u/%u\n", i_idx + 1, par->n_idx);
+		if(zmo_index_build(z->ctx, pbbeg, pbend, &z->kcut, &st)) die_zmo("zmo_index_build");
+		fprintf(stderr, "[wtzmo-b200] - average kmer depth = %u\n[wtzmo-b200] - %llu high frequency kmers (>=%u)\n[wtzmo-b200] - indexing %llu kmers, %llu postings (%.3f s)\n", st.kavg,
+			(unsigned long long)st.n_filtered_high, st.kcut, (unsigned long long)st.n_indexed, (unsigned long long)st.n_postings, now_s() - t0);
+		if(i_idx + 1 >= (u32)par->n_idx) break;
+		/* just_query passes (wtzmo.c:1289-1301): candidates of every eligible read against this partition; bcov is 0 there */
+		for(j=0;j<rs->n_rd;){
+			batch_t b; size_t i; memset(&b, 0, sizeof(b));
+			for(;j<rs->n_rd&&b.reads.n<(size_t)z->batch_reads*8;j++){
+				bread_t r; memset(&r, 0, sizeof(r));
+				if((j % par->n_job) != (u32)par->i_job) continue;
+				if(z->masked[j]) continue;
+				r.rd_id = j; vec_push(b.reads, r);
+			}
+			batch_candidates(z, &b);
+			for(i=0;i<b.reads.n;i++){ bread_t *r = &b.reads.a[i]; filter_sort_candidates(z, r->rd_id, &r->cands_raw, NULL); { u64v *h = &z->rdhits[r->rd_id]; vec_clear(*h); vec_reserve(*h, r->cands_raw.n + 1); memcpy(h->a, r->cands_raw.a, r->cands_raw.n * 8); h->n = r->cands_raw.n; } }
+			batch_free(&b);
+		}
+	}
+	for(j=beg;j<end;){
+		batch_t b; size_t i, est_pairs = 0; double t0, t1, t2; memset(&b, 0, sizeof(b));
+		/* collect the next run of reads; masked / job filters are re-checked at replay time */
+		for(;j<end&&b.reads.n<(size_t)z->batch_reads&&est_pairs<(size_t)z->batch_pairs;j++){
+			bread_t r; memset(&r, 0, sizeof(r));
+			if((j % par->n_job) != (u32)par->i_job) continue;
+			if(z->masked[j]) continue;
+			r.rd_id = j; r.skip = z->rdcovs[j] >= read_nbest(z, j);
+			vec_push(b.reads, r);
+			if(!r.skip) est_pairs += 40;
+		}
+		if(b.reads.n == 0) break;
+		t0 = now_s();
+		batch_candidates(z, &b);
+		batch_compute(z, &b);
+		t1 = now_s();
+		for(i=0;i<b.reads.n;i++){
+			bread_t *br = &b.reads.a[i];
+			if(z->masked[br->rd_id]) continue;       /* checked BEFORE the previous read's masks are merged (wtzmo.c:1315 vs 1322) */
+			flush_read(z, &ro, 0);
+			replay_read(z, &b, br, z->rdcovs[br->rd_id], &ro);
+		}
+		flush_read(z, &ro, 1);  /* hits point into this batch's CIGAR buffer: print them before it is freed; masks stay pending */
+		t2 = now_s();
+		z->t_dev += t1 - t0; z->t_replay += t2 - t1; z->n_batches ++;
+		batch_free(&b);
+	}
+	flush_read(z, &ro, 0);
+	ob_flush(z);
+	vec_free(ro.hits); vec_free(ro.masks); vec_free(ro.closed); vec_free(ro.seeds);
+}
+
+/* ------------------------------------------------------------------ command line (wtzmo.c:1422-1812) */
+static int file_exists(const char *f){ struct stat st; return stat(f, &st) == 0; }
+static int usage(void){
+	printf(
+	"WTZMO: Overlaper of long reads using homopolymer compressed k-mer seeding\n"
+	"SMARTdenovo: Ultra-fast de novo assembler for high noisy long reads\n"
+	"B200 build: hot path on NVIDIA Blackwell (sm_100a); output identical to the reference `wtzmo -t 1`\n"
+	"Usage: wtzmo [options]\n"
+	"Options:\n"
+	" -t <int>    Number of threads, [1] (accepted for compatibility; the GPU replaces the worker pool)\n"
+	" -P <int>    Total parallel jobs, [1]\n"
+	" -p <int>    Index of current job (0-based), [0]\n"
+	" -i <string> Long reads sequences file, + *\n"
+	" -I <string> Long reads sequence file, DON'T build index on them, +\n"
+	" -b <string> Long reads retained region, often from wtobt/wtcyc, +\n"
+	" -J <int>    Jack knife of original read length, [0]\n"
+	" -L <string> Load pairs of read name from file, will avoid to calculate overlap them again, + [NULL]\n"
+	" -o <string> Output file of alignments, *\n"
+	" -9 <string> Record pairs of sequences have beed aligned regardless of successful, including pairs from '-L'\n"
+	" -f          Force overwrite\n"
+	" -H <int>    Option of homopolymer compression, [3]\n"
+	" -k <int>    Kmer size, 5 <= <-k> <= 32, [16]\n"
+	" -K <int>    Filter high frequency kmers, maybe repetitive, [0]\n"
+	" -d <int>    Minimum size of total seeding region for kmer windows, [300]\n"
+	" -S <int>    Subsampling kmers, 1/<-S> kmers are indexed, [4]\n"
+	" -G <int>    Build kmer index in multiple iterations to save memory, 1: once, [1]\n"
+	" -z <int>    Smaller kmer size (z-mer), 5 <= <-z> <= 16, [10]\n"
+	" -Z <int>    Filter high frequency z-mers, maybe repetitive, [64]\n"
+	" -U <float>  Ultra-fast dot matrix alignment (five values, or -U -1 for the defaults 128 64 160 1.0 0.05)\n"
+	" -y <int>    Zmer window, [800]\n"
+	" -R <int>    Minimum size of seeding region within zmer window, [200]\n"
+	" -r <int>    Minimum size of total seeding region for zmer windows, [300]\n"
+	" -l <int>    Maximum variant of uncompressed sizes between two matched hz-kmer, [2]\n"
+	" -q <int>    THreshold of seed-window coverage along query, [100]\n"
+	" -A <int>    Limit number of best candidates per read, [500]\n"
+	" -B <int>    Limit number of best overlaps per read, [100]\n"
+	" -C          Don't write the <output>.contained file\n"
+	" -F <string> Reads from this file(s) are to be exclued, one line for one read name, + [NULL]\n"
+	" -M <int>    Alignment penalty: match, [2]\n"
+	" -X <int>    Alignment penalty: mismatch, [-5]\n"
+	" -O <int>    Alignment penalty: insertion or deletion, [-3]\n"
+	" -E <int>    Alignment penalty: gap extension, [-1]\n"
+	" -T <int>    Alignment penalty: read end clipping, [-50]\n"
+	" -w <int>    Minimum bandwidth, iteratively doubled to maximum [50]\n"
+	" -W <int>    Maximum bandwidth, [3200]\n"
+	" -e <int>    Maximum bandwidth at ending extension, [800]\n"
+	" -s <int>    Minimum alignment score, [200]\n"
+	" -m <float>  Minimum alignment identity, [0.5]\n"
+	" -n          Refine the alignment (not available in the B200 build)\n"
+	" -v          Verbose (accepted, ignored)\n"
+	"Environment: ZMO_DEVICE (GPU ordinal, default 0; under torchrun LOCAL_RANK), ZMO_BATCH_READS, ZMO_BATCH_PAIRS, ZMO_STATS=file\n"
+	"\n");
+	return 1;
+}
+
+int main(int argc, char **argv){
+	wz_t Z, *z = &Z; zparams_t *par = &Z.par; int c, device = 0; float optval; zmo_params_t zp;
+	char *output = NULL, *pairoutf = NULL, *env; double t_start = now_s(), t_ovl0, t_ovl1;
+	VEC(char*) pbs, flts, ovls, obts, tbas; u32 i;
+	memset(z, 0, sizeof(*z)); zparams_default(par);
+	vec_init(pbs); vec_init(flts); vec_init(ovls); vec_init(obts); vec_init(tbas);
+	while((c = getopt(argc, argv, "ht:P:p:Ni:b:J:I:o:9:S:fCH:k:G:z:Z:U:y:d:r:q:l:K:A:B:r:R:L:F:W:w:e:M:X:O:E:T:s:m:nv")) != -1){
+		switch(c){
+			case 'h': return usage();
+			case 't': par->ncpu = atoi(optarg); break;
+			case 'P': par->n_job = atoi(optarg); break;
+			case 'p': par->i_job = atoi(optarg); break;
+			case 'N': par->do_align = 0; break;
+			case 'i': vec_push(pbs, optarg); break;
+			case 'b': vec_push(obts, optarg); break;
+			case 'J': par->min_rdlen = atoi(optarg); break;
+			case 'I': vec_push(tbas, optarg); break;
+			case 'o': output = optarg; break;
+			case '9': pairoutf = optarg; break;
+			case 'S': par->ksave = atoi(optarg); break;
+			case 'f': par->overwrite = 1; break;
+			case 'C': par->write_contained = 0; break;   /* -C never reaches wt->skip_contained (wtzmo.c:168,1609,1781) */
+			case 'H': par->hk = atoi(optarg); par->hz = (par->hk >> 1) & 1; par->hk &= 1; break;
+			case 'k': par->ksize = atoi(optarg); break;
+			case 'K': par->kcut = atoi(optarg); break;
+			case 'z': par->zsize = atoi(optarg); break;
+			case 'Z': par->zcut = atoi(optarg); break;
+			case 'U': optval = atof(optarg);
+				if(optval < 0){ par->dot_matrix = 5; break; }
+				switch(par->dot_matrix){
+					case 0: par->xvar = optval; break;
+					case 1: par->yvar = optval; break;
+					case 2: par->min_block_len = optval; break;
+					case 3: par->deviation_penalty = optval; break;
+					case 4: par->gap_penalty = optval; break;
+					default: par->dot_matrix = 5;
+				}
+				par->dot_matrix ++;
+				break;
+			case 'y': par->kwin = atoi(optarg); break;
+			case 'l': par->kvar = atoi(optarg); break;
+			case 'd': par->kovl = atof(optarg); break;
+			case 'G': par->n_idx = atoi(optarg); break;
+			case 'r': par->ztot = atof(optarg); break;
+			case 'R': par->zovl = atof(optarg); break;
+			case 'q': par->wrep = atoi(optarg); break;
+			case 'A': par->ncand = atoi(optarg); break;
+			case 'B': par->nbest = atoi(optarg); break;
+			case 'w': par->w = atoi(optarg); break;
+			case 'e': par->ew = atoi(optarg); break;
+			case 'W': par->W = atoi(optarg); break;
+			case 'M': par->M = atoi(optarg); break;
+			case 'X': par->X = atoi(optarg); break;
+			case 'O': par->O = atoi(optarg); break;
+			case 'E': par->E = atoi(optarg); break;
+			case 'T': par->T = atoi(optarg); break;
+			case 'L': vec_push(ovls, optarg); break;
+			case 'F': vec_push(flts, optarg); break;
+			case 's': par->min_score = atoi(optarg); break;
+			case 'm': par->min_id = atof(optarg); break;
+			case 'n': par->refine = 1; break;
+			case 'v': par->debug ++; break;
+			default: return usage();
+		}
+	}
+	if(output == NULL) return usage();
+	if(!par->overwrite && strcmp(output, "-") && file_exists(output)){ fprintf(stderr, "File exists! '%s'\n\n", output); return usage(); }
+	if(pbs.n == 0) return usage();
+	if(par->ksize > 32 || par->ksize < 5) return usage();
+	if(par->zsize > 16 || par->zsize < 5) return usage();
+	if(par->ksave < 1) return usage();
+	if(par->refine){ fprintf(stderr, "wtzmo(b200): -n (kswx_refine_alignment) is not available in this build\n"); return 2; }
+	if(par->n_job < 1 || par->n_idx < 1){ fprintf(stderr, "wtzmo(b200): -P and -G must be >= 1\n"); return 2; }
+	par->max_overhang = 2 * par->xvar;
+	par->kstep = par->kwin / 2;
+	if((env = getenv("ZMO_DEVICE"))) device = atoi(env); else if((env = getenv("LOCAL_RANK"))) device = atoi(env);
+	z->batch_reads = (env = getenv("ZMO_BATCH_READS"))? atoi(env) : 256;
+	z->batch_pairs = (env = getenv("ZMO_BATCH_PAIRS"))? atoi(env) : 16384;
+	if(z->batch_reads < 1) z->batch_reads = 1;
+	fprintf(stderr, "[wtzmo-b200] loading long reads\n");
+	rs_load(&z->rs, pbs.a, (int)pbs.n, par->min_rdlen, 0);
+	ref_sort(z->rs.reads.a, z->rs.reads.n, sizeof(read_t), gt_read_len_desc, NULL);      /* wtzmo.c:1708 */
+	if(tbas.n) rs_load(&z->rs, tbas.a, (int)tbas.n, par->min_rdlen, 1);
+	fprintf(stderr, "[wtzmo-b200] Done, %u reads (+%u query-only), %.3f s\n", z->rs.n_rd, z->rs.n_qr, now_s() - t_start);
+	if(z->rs.n_rd == 0){ fprintf(stderr, "wtzmo(b200): no reads\n"); return 1; }
+	z->masked = calloc(z->rs.n_rd + z->rs.n_qr + 1, 1);
+	z->rdcovs = calloc(z->rs.n_rd + z->rs.n_qr + 1, sizeof(u32));
+	u64set_init(&z->closed);
+	{	/* side inputs: tab tables / name lists, '#' lines skipped (wtzmo.c:1732-1773) */
+		char *line = NULL; size_t cap = 0; FILE *fp;
+		for(i=0;i<obts.n;i++){
+			if((fp = fopen(obts.a[i], "r")) == NULL) exit(1);
+			while(getline(&line, &cap, fp) >= 0){
+				char *nm, *a, *b, *sv; u32 id; int coff, clen;
+				if(line[0] == '#') continue;
+				nm = strtok_r(line, "\t\n", &sv); a = strtok_r(NULL, "\t\n", &sv); b = strtok_r(NULL, "\t\n", &sv);
+				if(!nm || !a || !b) continue;
+				if((id = rs_find(&z->rs, z->rs.n_rd, nm)) == 0xFFFFFFFFU) continue;
+				coff = atoi(a); clen = atoi(b);
+				if(coff < 0 || coff + clen > (int)z->rs.reads.a[id].len) continue;
+				z->rs.reads.a[id].off += coff; z->rs.reads.a[id].len = clen;
+			}
+			fclose(fp);
+		}
+		for(i=0;i<flts.n;i++){
+			if((fp = fopen(flts.a[i], "r")) == NULL) exit(1);
+			while(getline(&line, &cap, fp) >= 0){
+				u32 id; size_t l = strlen(line);
+				while(l && line[l-1] == '\n') line[--l] = 0;
+				if(line[0] == '#') continue;
+				if((id = rs_find(&z->rs, z->rs.n_rd, line)) == 0xFFFFFFFFU) continue;
+				z->masked[id] = 1;
+			}
+			fclose(fp);
+		}
+		for(i=0;i<ovls.n;i++){
+			if((fp = fopen(ovls.a[i], "r")) == NULL) exit(1);
+			while(getline(&line, &cap, fp) >= 0){
+				char *a, *b, *sv; u32 p1, p2;
+				if(line[0] == '#') continue;
+				a = strtok_r(line, "\t\n", &sv); b = strtok_r(NULL, "\t\n", &sv);
+				if(!a || !b) continue;
+				if((p1 = rs_find(&z->rs, z->rs.n_rd, a)) == 0xFFFFFFFFU) continue;
+				if((p2 = rs_find(&z->rs, z->rs.n_rd, b)) == 0xFFFFFFFFU) continue;
+				u64set_add(&z->closed, pair_key(p1, p2));
+			}
+			fclose(fp);
+		}
+		free(line);
+	}
+	/* device context + read upload */
+	memset(&zp, 0, sizeof(zp));
+	zp.hk = par->hk; zp.hz = par->hz; zp.ksize = par->ksize; zp.zsize = par->zsize; zp.ksave = par->ksave; zp.kovl = par->kovl; zp.zcut = par->zcut; zp.kvar = par->kvar;
+	zp.kwin = par->kwin; zp.kstep = par->kstep; zp.zovl = par->zovl; zp.ztot = par->ztot; zp.w = par->w; zp.ew = par->ew; zp.W = par->W;
+	zp.M = par->M; zp.X = par->X; zp.O = par->O; zp.E = par->E; zp.T = par->T; zp.min_id = par->min_id;
+	zp.xvar = par->xvar; zp.yvar = par->yvar; zp.min_block_len = par->min_block_len; zp.max_overhang = par->max_overhang; zp.deviation_penalty = par->deviation_penalty; zp.gap_penalty = par->gap_penalty;
+	if(zmo_ctx_create(&z->ctx, device, &zp)) die_zmo("zmo_ctx_create");
+	{
+		u32 n = z->rs.n_rd + z->rs.n_qr; u64 *off = malloc((size_t)n * 8); u32 *len = malloc((size_t)n * 4);
+		for(i=0;i<n;i++){ off[i] = z->rs.reads.a[i].off; len[i] = z->rs.reads.a[i].len; }
+		if(zmo_reads_upload(z->ctx, z->rs.bits, z->rs.nbases, off, len, n)) die_zmo("zmo_reads_upload");
+		free(off); free(len);
+	}
+	z->out = strcmp(output, "-")? fopen(output, "w") : stdout;
+	if(z->out == NULL){ fprintf(stderr, "wtzmo(b200): cannot open %s\n", output); return 1; }
+	z->obuf_cap = 8u << 20; z->obuf = malloc(z->obuf_cap);
+	fprintf(stderr, "[wtzmo-b200] calculating overlaps on GPU %d\n", device);
+	t_ovl0 = now_s();
+	run_overlap(z);
+	if(strcmp(output, "-")) fclose(z->out); else fflush(stdout);
+	t_ovl1 = now_s();
+	fprintf(stderr, "[wtzmo-b200] Done, %llu records, %llu aligned columns, %.3f s (device calls %.3f s, replay+format %.3f s, %llu batches, %llu pairs seeded, %llu aligned, %llu consumed)\n",
+		(unsigned long long)z->n_records, (unsigned long long)z->aln_cols, t_ovl1 - t_ovl0, z->t_dev, z->t_replay, (unsigned long long)z->n_batches,
+		(unsigned long long)z->n_pairs_seeded, (unsigned long long)z->n_tasks, (unsigned long long)z->n_tasks_used);
+	if(par->write_contained && strcmp(output, "-")){
+		char *maskf = malloc(strlen(output) + 16); FILE *mf;
+		sprintf(maskf, "%s.contained", output); mf = fopen(maskf, "w");
+		for(i=0;i<z->rs.n_rd;i++) if(z->masked[i]) fprintf(mf, "%s\n", z->rs.reads.a[i].name);
+		fclose(mf); free(maskf);
+	}
+	if(pairoutf){
+		FILE *pf = fopen(pairoutf, "w"); size_t k;
+		for(k=0;k<z->closed.cap;k++){
+			u64 v = z->closed.tab[k];
+			if(v == ~0ULL) continue;
+			fprintf(pf, "%s\t%s\n", z->rs.reads.a[v >> 33].name, z->rs.reads.a[(v & 0xFFFFFFFFU) >> 1].name);
+		}
+		fclose(pf);
+	}
+	if((env = getenv("ZMO_STATS"))){
+		FILE *sf = fopen(env, "w"); double ms[8]; uint64_t ct[8];
+		zmo_stage_ms(z->ctx, ms); zmo_counters(z->ctx, ct);
+		if(sf){
+			fprintf(sf, "{\"records\": %llu, \"aligned_cols\": %llu, \"overlap_s\": %.6f, \"total_s\": %.6f, \"device_call_s\": %.6f, \"replay_s\": %.6f, \"batches\": %llu, \"pairs_seeded\": %llu, \"tasks\": %llu, \"tasks_used\": %llu, \"launches\": %llu,",
+				(unsigned long long)z->n_records, (unsigned long long)z->aln_cols, t_ovl1 - t_ovl0, now_s() - t_start, z->t_dev, z->t_replay, (unsigned long long)z->n_batches,
+				(unsigned long long)z->n_pairs_seeded, (unsigned long long)z->n_tasks, (unsigned long long)z->n_tasks_used, (unsigned long long)zmo_kernel_launches(z->ctx));
+			fprintf(sf, " \"stage_ms\": {\"index\": %.3f, \"candidates\": %.3f, \"pair_windows\": %.3f, \"window_align\": %.3f, \"gap_global\": %.3f, \"end_extend\": %.3f, \"dotmatrix\": %.3f, \"copy\": %.3f},", ms[0], ms[1], ms[2], ms[3], ms[4], ms[5], ms[6], ms[7]);
+			fprintf(sf, " \"counters\": {\"cells_ext\": %llu, \"cells_win\": %llu, \"cells_gap\": %llu, \"zpairs\": %llu, \"postings\": %llu, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu},",
+				(unsigned long long)ct[0], (unsigned long long)ct[1], (unsigned long long)ct[2], (unsigned long long)ct[3], (unsigned long long)ct[4], (unsigned long long)ct[5], (unsigned long long)ct[6]);
+			fprintf(sf, " \"n_reads\": %u, \"n_bases\": %llu}\n", z->rs.n_rd + z->rs.n_qr, (unsigned long long)z->rs.nbases);
+			fclose(sf);
+		}
+	}
+	zmo_ctx_destroy(z->ctx);
+	return 0;
+}

@@ -1,0 +1,450 @@
+/*
+ * zmo_align.cu -- pair alignment pipeline on the device (replaces wtzmo.c:1017-1030:
+ * fast_seeds_align_hzmo per window + global_align_regs_hzmo).
+ *
+ *   k_window_align  one warp per (task, window): walk the window's anchors, bridge each gap with the
+ *                   fixed-band extension DP, pad, run-length-align the anchor (hzm_aln.h:1247-1302)
+ *   k_plan          one thread per task: region filter (wtzmo.c:1026), left end-extension job and
+ *                   gap-filling jobs, scratch bump-allocated from the device arena
+ *   k_ext_* / k_glb_*   persistent DP executors (zmo_dp.cu)
+ *   k_plan2         accumulate left + regions + gaps, create the right end-extension job
+ *   k_finish_size / k_finish   final record and stitched CIGAR (hzm_aln.h:1345-1486)
+ */
+#include <cub/cub.cuh>
+#include "zmo_jobs.cuh"
+#include "zmo_seed_core.cuh"
+
+int zmo_launch_ext(zmo_ctx *c, int mode, bool wide, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells);
+int zmo_launch_glb(zmo_ctx *c, bool wide, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells);
+
+#define CUB_CALL(c, call_expr) do { size_t _tb = 0; void *_tp = nullptr; { auto d_temp = _tp; size_t &temp_bytes = _tb; CUDA_TRY(call_expr); } \
+	if((c)->cubtmp.reserve(_tb + 256)) return ZMO_ERR_CUDA; { void *d_temp = (c)->cubtmp.p; size_t &temp_bytes = _tb; CUDA_TRY(call_expr); } (c)->launches++; } while(0)
+
+#define WA_C 7
+#define WA_CAP 256
+#define WA_SEQW 192
+#define WA_WARPS 4
+
+struct WItem { uint32_t task, win; };
+struct DevReg { int score, tb, te, qb, qe, aln, mat, mis, ins, del; unsigned long long cig_off; uint32_t cig_len, kept; };
+struct AlnTask { uint32_t pair_idx, dir, item_off, n_item; };
+struct AlnPar { int w, ew, W, zovl; float min_id; DPPar P; };
+
+/* views of the two reads of a task: pb1 = q forward, pb2 = c on strand dir (hzm_aln.h naming) */
+__device__ __forceinline__ SeqView view_pb1(const DevReads &R, uint32_t qid, int start, int step){ SeqView v; v.w = R.words + R.woff[qid]; v.start = start; v.step = step; v.comp = 0; return v; }
+__device__ __forceinline__ SeqView view_pb2(const DevReads &R, uint32_t cid, uint32_t dir, int start, int step){
+	SeqView v; v.w = R.words + R.woff[cid];
+	if(dir){ v.start = (int)R.len[cid] - 1 - start; v.step = -step; v.comp = 3u; } else { v.start = start; v.step = step; v.comp = 0; }
+	return v;
+}
+
+__device__ __forceinline__ void cig_put(uint32_t *c, uint32_t &n, uint32_t op, uint32_t len){         /* kswx.h:39-44 */
+	if(len == 0) return;
+	if(n && (c[n - 1] & 0xFu) == op) c[n - 1] += len << 4; else c[n++] = (len << 4) | op;
+}
+__device__ __forceinline__ void cig_cat(uint32_t *c, uint32_t &n, const uint32_t *src, uint32_t len, bool reversed){   /* kswx.h:46-52 */
+	if(len == 0) return;
+	uint32_t i = 0; const uint32_t first = reversed? src[len - 1] : src[0];
+	if(n && (c[n - 1] & 0xFu) == (first & 0xFu)){ c[n - 1] += first & 0xFFFFFFF0u; i = 1; }
+	if(reversed) for(; i < len; i++) c[n++] = src[len - 1 - i];
+	else for(; i < len; i++) c[n++] = src[i];
+}
+
+/* warp-per-window executor */
+__global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *items, uint32_t nitems, const AlnTask *tasks, const zmo_pair_t *pairs,
+		const DevWin *wins, const DevZPair *anchors, DevReads R, AlnPar A, uint32_t *arena, unsigned long long slab_words, int max_rows,
+		uint32_t *cig_arena, const unsigned long long *item_cig_off, DevReg *regs, unsigned long long *ctr, int ctr_work, int ctr_cells){
+	__shared__ int s_h[WA_WARPS][3 * WA_CAP];
+	__shared__ uint32_t s_seq[WA_WARPS][WA_SEQW];
+	__shared__ int s_misc[WA_WARPS][16];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const unsigned gw = blockIdx.x * WA_WARPS + warp;
+	uint32_t *slab = arena + (unsigned long long)gw * slab_words;
+	BandSmem S; S.H0 = s_h[warp]; S.H1 = S.H0 + WA_CAP; S.Ev = S.H1 + WA_CAP; S.cap_mask = WA_CAP - 1; S.sred = nullptr; S.sredk = nullptr; S.smisc = s_misc[warp];
+	const DPPar P = A.P;
+	while(1){
+		uint32_t it = 0;
+		if(lane == 0) it = (uint32_t)atomicAdd(ctr + ctr_work, 1ULL);
+		it = __shfl_sync(0xffffffffu, it, 0);
+		if(it >= nitems) break;
+		const WItem I = items[it]; const AlnTask T = tasks[I.task]; const zmo_pair_t pr = pairs[T.pair_idx]; const DevWin W = wins[I.win];
+		uint32_t *cig = cig_arena + item_cig_off[it]; uint32_t ncig = 0;
+		int x_score = 0, x_tb = 0, x_te = 0, x_qb = 0, x_qe = 0, x_aln = 0, x_mat = 0, x_mis = 0, x_ins = 0, x_del = 0;
+		for(uint32_t ai = W.anc0; ai < W.anc1; ai++){
+			const DevZPair p = anchors[ai];
+			if(x_aln == 0){ x_tb = x_te = (int)p.off1; x_qb = x_qe = (int)p.off2; }
+			if((int)p.off1 < x_te) continue;
+			if((int)p.off2 < x_qe) continue;
+			const int qlen = (int)p.off2 - x_qe, tlen = (int)p.off1 - x_te;
+			const int init = x_score < 0? 0 : x_score;
+			DPOut o; o.score = init; o.qe = o.te = o.mat = o.mis = o.ins = o.del = o.ncig = 0;
+			uint32_t *tmpc = nullptr;
+			if(qlen > 0 && tlen > 0){
+				const BandDims d = band_dims(qlen, tlen, init, A.w, P);
+				const int rw = band_row_words<32, WA_C>(d.ncol);
+				uint32_t *scr = slab;
+				uint32_t *z = scr; scr += (size_t)max_rows * rw;
+				int *zb = (int*)scr; scr += max_rows;
+				tmpc = scr; scr += 2 * (size_t)max_rows + 2 * (size_t)A.w + 16;
+				const int qw = (d.ql + 15) >> 4, tw = (d.tl + 15) >> 4;
+				uint32_t *qpk, *tpk;
+				if(qw + tw <= WA_SEQW){ qpk = s_seq[warp]; tpk = qpk + qw; } else { qpk = scr; tpk = scr + qw; }
+				scr += ((size_t)max_rows >> 3) + ((size_t)A.w >> 3) + 8;
+				BandSmem S2 = S;
+				if(2 * d.W + 3 > WA_CAP){ int cap = 1; while(cap < 2 * d.W + 3) cap <<= 1; S2.H0 = (int*)scr; S2.H1 = S2.H0 + cap; S2.Ev = S2.H1 + cap; S2.cap_mask = cap - 1; }
+				stage_packed<32>(view_pb2(R, pr.cid, T.dir, x_qe, 1), d.ql, qpk, lane);
+				stage_packed<32>(view_pb1(R, pr.qid, x_te, 1), d.tl, tpk, lane);
+				__syncwarp();
+				band_extend<32, WA_C, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, zb, tmpc, 2 * max_rows + 2 * A.w + 16, o, ctr + ctr_cells, lane);
+			}
+			x_score = o.score;
+			x_aln += o.mat + o.mis + o.ins + o.del; x_mat += o.mat; x_mis += o.mis; x_ins += o.ins; x_del += o.del;
+			x_te += o.te; x_qe += o.qe;
+			/* the reference merges [extension cigar + D pad + I pad] into the window cigar as ONE block
+			 * (kswx_push_cigars merges only its first op with the previous last op) */
+			uint32_t padD = 0, padI = 0;
+			if(x_te < (int)p.off1){ padD = p.off1 - x_te; x_del += padD; x_aln += padD; x_te = p.off1; }
+			if(x_qe < (int)p.off2){ padI = p.off2 - x_qe; x_ins += padI; x_aln += padI; x_qe = p.off2; }
+			int ok = 1;
+			if(lane == 0){
+				/* block = reverse(walk-order ops) ++ D pad ++ I pad with run merging inside the block */
+				const uint32_t base = ncig; uint32_t nb = ncig;   /* build the block in place after position base, merging only within the block */
+				uint32_t *blk = cig + base; uint32_t bn = 0;
+				for(int k = o.ncig - 1; k >= 0; k--) blk[bn++] = tmpc[k];
+				if(padD){ if(bn && (blk[bn - 1] & 0xFu) == 2u) blk[bn - 1] += padD << 4; else blk[bn++] = (padD << 4) | 2u; }
+				if(padI){ if(bn && (blk[bn - 1] & 0xFu) == 1u) blk[bn - 1] += padI << 4; else blk[bn++] = (padI << 4) | 1u; }
+				/* now splice: merge first op of the block with the previous op if equal */
+				if(bn){
+					if(base && (cig[base - 1] & 0xFu) == (blk[0] & 0xFu)){
+						cig[base - 1] += blk[0] & 0xFFFFFFF0u;
+						for(uint32_t k = 1; k < bn; k++) cig[base + k - 1] = blk[k];
+						nb = base + bn - 1;
+					} else nb = base + bn;
+				}
+				ncig = nb;
+				/* run-length alignment of the anchor itself (hzm_aln.h:278-314) */
+				const SeqView a = view_pb1(R, pr.qid, (int)p.off1, 1), b = view_pb2(R, pr.cid, T.dir, (int)p.off2, 1);
+				const uint32_t la = p.len1, lb = p.len2; uint32_t sa = 0, sb = 0;
+				int y_score = 0, y_aln = 0, y_mat = 0, y_ins = 0, y_del = 0;
+				uint32_t blk2[96]; uint32_t n2 = 0; bool bad = false;
+				while(sa < la || sb < lb){
+					const uint32_t ca = sa < la? sv_base(a, sa) : 4u, cb = sb < lb? sv_base(b, sb) : 5u;
+					if(ca != cb){ bad = true; break; }
+					uint32_t ea = sa + 1; while(ea < la && sv_base(a, ea) == ca) ea++;
+					uint32_t eb = sb + 1; while(eb < lb && sv_base(b, eb) == cb) eb++;
+					const uint32_t na = ea - sa, nbb = eb - sb;
+					if(na < nbb){ y_aln += nbb; y_mat += na; y_ins += nbb - na; y_score += na * P.M + P.I + (int)(nbb - na) * P.E; if(n2 < 94){ cig_put(blk2, n2, 0, na); cig_put(blk2, n2, 1, nbb - na); } }
+					else if(na == nbb){ y_aln += na; y_mat += na; y_score += na * P.M; if(n2 < 94) cig_put(blk2, n2, 0, na); }
+					else { y_aln += na; y_mat += nbb; y_del += na - nbb; y_score += nbb * P.M + P.D + (int)(na - nbb) * P.E; if(n2 < 94){ cig_put(blk2, n2, 0, nbb); cig_put(blk2, n2, 2, na - nbb); } }
+					sa = ea; sb = eb;
+				}
+				if(bad || y_aln == 0) ok = 0;
+				else {
+					s_misc[warp][9] = y_score; s_misc[warp][10] = y_aln; s_misc[warp][11] = y_mat; s_misc[warp][12] = y_ins; s_misc[warp][13] = y_del;
+					cig_cat(cig, ncig, blk2, n2, false);
+				}
+			}
+			ok = __shfl_sync(0xffffffffu, ok, 0);
+			__syncwarp();
+			if(!ok) break;               /* "should never happen": window truncated (hzm_aln.h:1288-1291) */
+			x_score += s_misc[warp][9]; x_aln += s_misc[warp][10]; x_mat += s_misc[warp][11]; x_ins += s_misc[warp][12]; x_del += s_misc[warp][13];
+			x_te += s_misc[warp][11] + s_misc[warp][13]; x_qe += s_misc[warp][11] + s_misc[warp][12];
+			__syncwarp();
+		}
+		if(lane == 0){
+			DevReg r; r.score = x_score; r.tb = x_tb; r.te = x_te; r.qb = x_qb; r.qe = x_qe; r.aln = x_aln; r.mat = x_mat; r.mis = x_mis; r.ins = x_ins; r.del = x_del;
+			r.cig_off = item_cig_off[it]; r.cig_len = ncig;
+			r.kept = !(x_aln * 2 < A.zovl || (float)x_mat < (float)x_aln * A.min_id);       /* wtzmo.c:1026 */
+			regs[it] = r;
+		}
+		__syncwarp();
+	}
+}
+
+/* per-task bookkeeping shared by the plan/finish kernels */
+struct TaskState { int ok; int first, last; int left_job, right_job; int gap0, ngap; int score, tb, te, qb, qe, aln, mat, mis, ins, del; unsigned long long cig_need; };
+struct JobLists { DPJob *ext_w, *ext_n, *glb_w, *glb_n; unsigned long long *n_ext_w, *n_ext_n, *n_glb_w, *n_glb_n; uint32_t cap; unsigned long long *arena_cur, arena_cap, *cig_cur, cig_cap, *overflow; uint32_t res_ext_w, res_ext_n, res_glb_w, res_glb_n; };
+
+__device__ inline int push_job(DPJob *list, unsigned long long *cnt, uint32_t cap, uint32_t res_base, DPJob &J, unsigned long long scratch_words, JobLists &L){
+	const unsigned long long s0 = atomicAdd(L.arena_cur, scratch_words), c0 = atomicAdd(L.cig_cur, (unsigned long long)J.cig_cap);
+	const unsigned long long k = atomicAdd(cnt, 1ULL);
+	if(s0 + scratch_words > L.arena_cap || c0 + J.cig_cap > L.cig_cap || k >= cap){ atomicAdd(L.overflow, 1ULL); return -1; }
+	J.scratch = s0; J.cig_off = c0; J.out_idx = res_base + (uint32_t)k;
+	list[k] = J;
+	return (int)J.out_idx;
+}
+
+__global__ void k_plan(const AlnTask *tasks, uint32_t nt, const zmo_pair_t *pairs, const DevReg *regs, DevReads R, AlnPar A, JobLists L, TaskState *ts, unsigned long long arena_base){
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if(t >= nt) return;
+	const AlnTask T = tasks[t]; const zmo_pair_t pr = pairs[T.pair_idx];
+	TaskState S; memset(&S, 0, sizeof(S)); S.left_job = S.right_job = -1; S.first = S.last = -1; S.gap0 = -1;
+	int prev = -1;
+	for(uint32_t k = 0; k < T.n_item; k++){
+		const DevReg &r = regs[T.item_off + k];
+		if(!r.kept) continue;
+		if(S.first < 0) S.first = (int)(T.item_off + k);
+		if(prev >= 0){
+			/* gap between regions prev and this one (hzm_aln.h:1395-1407) */
+			const DevReg &r1 = regs[prev];
+			DPJob J; memset(&J, 0, sizeof(J));
+			int gq = r.qb - r1.qe, gt = r.tb - r1.te; if(gq < 0) gq = 0; if(gt < 0) gt = 0;
+			const SeqView q = view_pb2(R, pr.cid, T.dir, r1.qe, 1), tv = view_pb1(R, pr.qid, r1.te, 1);
+			J.q_rid = pr.cid; J.q_start = q.start; J.q_step = q.step; J.q_comp = q.comp? 1 : 0; J.qlen = gq;
+			J.t_rid = pr.qid; J.t_start = tv.start; J.t_step = tv.step; J.t_comp = 0; J.tlen = gt;
+			J.init = 0; J.Wp = A.w; J.Wmax = A.W; J.cig_cap = (uint32_t)(gq + gt + 4);
+			int w = A.w; const int dl = gq > gt? gq - gt : gt - gq; while(w < dl) w <<= 1;
+			const int bw = gq < 2 * w + 1? gq : 2 * w + 1;
+			const bool wide = bw > 32 * 7 * 2;
+			int id;
+			if(wide) id = push_job(L.glb_w, L.n_glb_w, L.cap, L.res_glb_w, J, glb_scratch_words<256, 7>(gq, gt, 2048), L);
+			else id = push_job(L.glb_n, L.n_glb_n, L.cap, L.res_glb_n, J, glb_scratch_words<32, 7>(gq, gt, 256), L);
+			/* gap job ids of one task are not contiguous across classes: remember them in the region record slot */
+			((DevReg*)regs)[T.item_off + k].kept = 2u + (uint32_t)(id < 0? 0 : id);
+			S.ngap++;
+		}
+		prev = (int)(T.item_off + k); S.last = prev;
+	}
+	S.ok = S.first >= 0;
+	if(S.ok){
+		const DevReg &r0 = regs[S.first];
+		if(r0.qb && r0.tb){
+			DPJob J; memset(&J, 0, sizeof(J));
+			const SeqView q = view_pb2(R, pr.cid, T.dir, r0.qb - 1, -1), tv = view_pb1(R, pr.qid, r0.tb - 1, -1);
+			J.q_rid = pr.cid; J.q_start = q.start; J.q_step = q.step; J.q_comp = q.comp? 1 : 0; J.qlen = r0.qb;
+			J.t_rid = pr.qid; J.t_start = tv.start; J.t_step = tv.step; J.t_comp = 0; J.tlen = r0.tb;
+			J.init = r0.score + 100 * A.P.M; J.Wp = -A.ew; J.cig_cap = (uint32_t)(r0.qb + r0.tb + 4);
+			const int init = J.init < 0? 0 : J.init;
+			const BandDims d = band_dims(J.qlen, J.tlen, init, J.Wp, A.P);
+			if(d.ncol > 32 * 7) S.left_job = push_job(L.ext_w, L.n_ext_w, L.cap, L.res_ext_w, J, ext_scratch_words<256, 7>(d, 2048), L);
+			else S.left_job = push_job(L.ext_n, L.n_ext_n, L.cap, L.res_ext_n, J, ext_scratch_words<32, 7>(d, 256), L);
+		}
+	}
+	ts[t] = S;
+}
+
+/* accumulate left extension + regions + gaps (hzm_aln.h:1357-1450) */
+__device__ inline void accumulate(const AlnTask &T, const DevReg *regs, const DPRes *res, const AlnPar &A, TaskState &S){
+	const DevReg &r0 = regs[S.first];
+	S.score = r0.score; S.tb = r0.tb; S.te = r0.te; S.qb = r0.qb; S.qe = r0.qe; S.aln = r0.aln; S.mat = r0.mat; S.mis = r0.mis; S.ins = r0.ins; S.del = r0.del;
+	unsigned long long need = 0;
+	if(S.left_job >= 0){
+		const DPRes &y = res[S.left_job];
+		S.score = y.score - 100 * A.P.M;
+		S.aln += y.mat + y.mis + y.ins + y.del; S.mat += y.mat; S.mis += y.mis; S.ins += y.ins; S.del += y.del;
+		S.qb -= y.qe; S.tb -= y.te;
+		need += y.ncig;
+	}
+	need += r0.cig_len;
+	for(uint32_t k = (uint32_t)S.first + 1 - T.item_off; k < T.n_item; k++){
+		const DevReg &r = regs[T.item_off + k];
+		if(r.kept < 2u) continue;
+		const DPRes &g = res[r.kept - 2u];
+		S.score += g.score;
+		S.aln += g.mat + g.mis + g.ins + g.del; S.mat += g.mat; S.mis += g.mis; S.ins += g.ins; S.del += g.del;
+		S.score += r.score; S.aln += r.aln; S.mat += r.mat; S.mis += r.mis; S.ins += r.ins; S.del += r.del;
+		S.qe = r.qe; S.te = r.te;
+		need += g.ncig + r.cig_len;
+	}
+	S.cig_need = need;
+}
+
+__global__ void k_plan2(const AlnTask *tasks, uint32_t nt, const zmo_pair_t *pairs, const DevReg *regs, const DPRes *res, DevReads R, AlnPar A, JobLists L, TaskState *ts){
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if(t >= nt) return;
+	TaskState S = ts[t];
+	if(!S.ok) return;
+	const AlnTask T = tasks[t]; const zmo_pair_t pr = pairs[T.pair_idx];
+	accumulate(T, regs, res, A, S);
+	const int len1 = (int)R.len[pr.qid], len2 = (int)R.len[pr.cid];
+	S.right_job = -1;
+	if(S.te < len1 && S.qe < len2){
+		DPJob J; memset(&J, 0, sizeof(J));
+		const SeqView q = view_pb2(R, pr.cid, T.dir, S.qe, 1), tv = view_pb1(R, pr.qid, S.te, 1);
+		J.q_rid = pr.cid; J.q_start = q.start; J.q_step = q.step; J.q_comp = q.comp? 1 : 0; J.qlen = len2 - S.qe;
+		J.t_rid = pr.qid; J.t_start = tv.start; J.t_step = tv.step; J.t_comp = 0; J.tlen = len1 - S.te;
+		J.init = S.score; J.Wp = -A.ew; J.cig_cap = (uint32_t)(J.qlen + J.tlen + 4);
+		const int init = J.init < 0? 0 : J.init;
+		const BandDims d = band_dims(J.qlen, J.tlen, init, J.Wp, A.P);
+		if(d.ncol > 32 * 7) S.right_job = push_job(L.ext_w, L.n_ext_w, L.cap, L.res_ext_w, J, ext_scratch_words<256, 7>(d, 2048), L);
+		else S.right_job = push_job(L.ext_n, L.n_ext_n, L.cap, L.res_ext_n, J, ext_scratch_words<32, 7>(d, 256), L);
+	}
+	ts[t] = S;
+}
+
+__global__ void k_finish_size(uint32_t nt, const DPRes *res, TaskState *ts, unsigned long long *need){
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if(t >= nt) return;
+	const TaskState &S = ts[t];
+	unsigned long long n = 0;
+	if(S.ok){ n = S.cig_need; if(S.right_job >= 0) n += res[S.right_job].ncig; }
+	need[t] = n;
+}
+
+__global__ void k_finish(const AlnTask *tasks, uint32_t nt, const DevReg *regs, const DPRes *res, const DPJob *jobs_all,
+		const uint32_t *cig_arena, AlnPar A, const TaskState *ts, const unsigned long long *out_off, uint32_t *out_cig, zmo_record_t *recs){
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if(t >= nt) return;
+	TaskState S = ts[t]; zmo_record_t rec; memset(&rec, 0, sizeof(rec));
+	if(!S.ok){ recs[t] = rec; return; }
+	const AlnTask T = tasks[t];
+	uint32_t *dst = out_cig + out_off[t]; uint32_t n = 0;
+	if(S.left_job >= 0){ const DPRes &y = res[S.left_job]; const DPJob &J = jobs_all[S.left_job]; cig_cat(dst, n, cig_arena + J.cig_off, (uint32_t)y.ncig, false); }
+	{ const DevReg &r0 = regs[S.first]; cig_cat(dst, n, cig_arena + r0.cig_off, r0.cig_len, false); }
+	for(uint32_t k = (uint32_t)S.first + 1 - T.item_off; k < T.n_item; k++){
+		const DevReg &r = regs[T.item_off + k];
+		if(r.kept < 2u) continue;
+		const DPRes &g = res[r.kept - 2u]; const DPJob &J = jobs_all[r.kept - 2u];
+		cig_cat(dst, n, cig_arena + J.cig_off, (uint32_t)g.ncig, true);
+		cig_cat(dst, n, cig_arena + r.cig_off, r.cig_len, false);
+	}
+	if(S.right_job >= 0){
+		const DPRes &y = res[S.right_job]; const DPJob &J = jobs_all[S.right_job];
+		S.score = y.score;
+		S.aln += y.mat + y.mis + y.ins + y.del; S.mat += y.mat; S.mis += y.mis; S.ins += y.ins; S.del += y.del;
+		S.qe += y.qe; S.te += y.te;
+		cig_cat(dst, n, cig_arena + J.cig_off, (uint32_t)y.ncig, true);
+	}
+	rec.ok = 1; rec.score = S.score; rec.tb = S.tb; rec.te = S.te; rec.qb = S.qb; rec.qe = S.qe; rec.aln = S.aln; rec.mat = S.mat; rec.mis = S.mis; rec.ins = S.ins; rec.del = S.del;
+	rec.cigar_off = out_off[t]; rec.n_cigar = n;
+	recs[t] = rec;
+}
+
+/* res index -> position in the concatenated job array [ext_w | ext_n | glb_w | glb_n] is the identity by construction */
+extern "C" int zmo_pair_align(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32_t nt, zmo_record_t *recs, uint32_t *cigars, uint64_t cigar_cap, uint64_t *cigar_needed){
+	if(!c || (nt && (!tasks || !recs))) return zmo_set_err(ZMO_ERR_ARG, "null argument");
+	if(slot < 0 || slot > 1) return zmo_set_err(ZMO_ERR_ARG, "slot must be 0 or 1");
+	if(cigar_needed) *cigar_needed = 0;
+	if(nt == 0) return 0;
+	SeedSlot &SL = c->slot[slot];
+	if(SL.np == 0) return zmo_set_err(ZMO_ERR_STATE, "zmo_pair_windows has not filled slot %d", slot);
+	CUDA_TRY(cudaSetDevice(c->device));
+	/* host: items and per-item cigar regions */
+	std::vector<AlnTask> ht(nt); std::vector<WItem> items; std::vector<unsigned long long> icig;
+	std::vector<DevWin> hw(SL.n_wins);
+	if(SL.n_wins) CUDA_TRY(cudaMemcpy(hw.data(), SL.wins.p, SL.n_wins * sizeof(DevWin), cudaMemcpyDeviceToHost));
+	unsigned long long cig_words = 0; int max_rows = 16;
+	for(uint32_t t = 0; t < nt; t++){
+		if(tasks[t].pair_idx >= SL.np || tasks[t].dir > 1) return zmo_set_err(ZMO_ERR_ARG, "task %u out of range", t);
+		const zmo_pairseed_t &ps = SL.h_seeds[tasks[t].pair_idx]; const uint32_t d = tasks[t].dir;
+		ht[t].pair_idx = tasks[t].pair_idx; ht[t].dir = d; ht[t].item_off = (uint32_t)items.size(); ht[t].n_item = ps.n_win[d];
+		for(uint32_t k = 0; k < ps.n_win[d]; k++){
+			WItem it; it.task = t; it.win = ps.win_off[d] + k; items.push_back(it);
+			const DevWin &w = hw[it.win];
+			const int s0 = w.end[0] - w.beg[0], s1 = w.end[1] - w.beg[1];
+			icig.push_back(cig_words); cig_words += (unsigned long long)(s0 + s1 + 16 + 2 * (w.anc1 - w.anc0));
+			if(s1 + 8 > max_rows) max_rows = s1 + 8;
+			if(s0 + 8 > max_rows) max_rows = s0 + 8;
+		}
+	}
+	const uint32_t nitems = (uint32_t)items.size();
+	AlnPar A; A.w = c->par.w; A.ew = c->par.ew; A.W = c->par.W; A.zovl = c->par.zovl; A.min_id = c->par.min_id;
+	A.P.M = c->par.M; A.P.X = c->par.X; A.P.I = c->par.O; A.P.D = c->par.O; A.P.E = c->par.E; A.P.T = c->par.T;
+	DevReads R = dev_reads(c);
+	unsigned long long *ctr = c->d_ctr.as<unsigned long long>();
+	/* window-align executors and their slabs */
+	const int wgrid = (int)std::min<uint64_t>((nitems + WA_WARPS - 1) / WA_WARPS + 1, (uint64_t)c->n_sm * 8);
+	const int wcol = std::min(max_rows + c->par.w, 2 * c->par.w + 1);
+	unsigned long long slab = (unsigned long long)max_rows * band_row_words<32, WA_C>(wcol) + max_rows + (2ull * max_rows + 2ull * c->par.w + 16) + ((unsigned long long)max_rows >> 3) + (c->par.w >> 3) + 8;
+	if(2 * c->par.w + 3 > WA_CAP){ unsigned long long cap = 1; while(cap < (unsigned long long)(2 * c->par.w + 3)) cap <<= 1; slab += 3 * cap; }
+	slab = (slab + 63) & ~63ull;
+	const unsigned long long slabs_total = slab * (unsigned long long)wgrid * WA_WARPS;
+	const uint32_t jcap = nitems + 2 * nt + 8;
+	/* device buffers: s0 tasks|items|icig, s1 regs, s2 task state, s3 jobs (4 lists), s4 results, s6 cig arena, s7 out offsets */
+	if(c->s0.reserve((size_t)nt * sizeof(AlnTask) + (size_t)nitems * (sizeof(WItem) + 8) + 64) || c->s1.reserve(((size_t)nitems + 1) * sizeof(DevReg)) || c->s2.reserve(((size_t)nt + 1) * sizeof(TaskState))
+		|| c->s3.reserve((size_t)jcap * 4 * sizeof(DPJob)) || c->s4.reserve((size_t)jcap * 4 * sizeof(DPRes)) || c->s7.reserve(((size_t)nt + 2) * 16)) return ZMO_ERR_CUDA;
+	AlnTask *d_tasks = c->s0.as<AlnTask>(); WItem *d_items = (WItem*)(d_tasks + nt); unsigned long long *d_icig = (unsigned long long*)(((uintptr_t)(d_items + nitems) + 7) & ~(uintptr_t)7);
+	DevReg *d_regs = c->s1.as<DevReg>(); TaskState *d_ts = c->s2.as<TaskState>();
+	DPJob *d_jobs = c->s3.as<DPJob>(); DPRes *d_res = c->s4.as<DPRes>();
+	CUDA_TRY(cudaMemcpyAsync(d_tasks, ht.data(), (size_t)nt * sizeof(AlnTask), cudaMemcpyHostToDevice, c->stream));
+	if(nitems){
+		CUDA_TRY(cudaMemcpyAsync(d_items, items.data(), (size_t)nitems * sizeof(WItem), cudaMemcpyHostToDevice, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(d_icig, icig.data(), (size_t)nitems * 8, cudaMemcpyHostToDevice, c->stream));
+	}
+	c->counters[5] += (size_t)nt * sizeof(AlnTask) + (size_t)nitems * 16;
+	unsigned long long arena_words = std::max<unsigned long long>(c->arena.cap / 4, slabs_total + (64ull << 20));
+	unsigned long long cig_cap_words = cig_words + (unsigned long long)nt * 4096 + (1ull << 20);
+	for(int attempt = 0; ; attempt++){
+		if(c->arena.reserve(arena_words * 4) || c->s6.reserve(cig_cap_words * 4)) return ZMO_ERR_CUDA;
+		arena_words = c->arena.cap / 4; cig_cap_words = c->s6.cap / 4;
+		uint32_t *arena = c->arena.as<uint32_t>(), *cig_arena = c->s6.as<uint32_t>();
+		if(nitems){
+			StageTimer tm(c, ST_WINALN);
+			CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORK, 0, 8, c->stream));
+			k_window_align<<<wgrid, 32 * WA_WARPS, 0, c->stream>>>(d_items, nitems, d_tasks, SL.pairs.as<zmo_pair_t>(), SL.wins.as<DevWin>(), SL.anchors.as<DevZPair>(), R, A,
+				arena, slab, max_rows, cig_arena, d_icig, d_regs, ctr, CTR_WORK, CTR_CELLS_WIN);
+			c->launches++;
+			CUDA_TRY(cudaGetLastError());
+		}
+		/* plan: left extensions + gaps */
+		JobLists L; L.cap = jcap; L.ext_w = d_jobs; L.ext_n = d_jobs + jcap; L.glb_w = d_jobs + 2 * (size_t)jcap; L.glb_n = d_jobs + 3 * (size_t)jcap;
+		L.n_ext_w = ctr + CTR_N1; L.n_ext_n = ctr + CTR_N2; L.n_glb_w = ctr + CTR_N3; L.n_glb_n = ctr + CTR_N4;
+		L.arena_cur = ctr + CTR_ARENA; L.arena_cap = arena_words; L.cig_cur = ctr + CTR_N5; L.cig_cap = cig_cap_words; L.overflow = ctr + CTR_OVERFLOW;
+		L.res_ext_w = 0; L.res_ext_n = jcap; L.res_glb_w = 2 * jcap; L.res_glb_n = 3 * jcap;
+		unsigned long long init_ctr[8] = {0};
+		CUDA_TRY(cudaMemsetAsync(ctr + CTR_N1, 0, 5 * 8, c->stream));
+		CUDA_TRY(cudaMemsetAsync(ctr + CTR_OVERFLOW, 0, 8, c->stream));
+		init_ctr[0] = slabs_total; init_ctr[1] = cig_words;
+		CUDA_TRY(cudaMemcpyAsync(ctr + CTR_ARENA, &init_ctr[0], 8, cudaMemcpyHostToDevice, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(ctr + CTR_N5, &init_ctr[1], 8, cudaMemcpyHostToDevice, c->stream));
+		k_plan<<<(nt + 63) / 64, 64, 0, c->stream>>>(d_tasks, nt, SL.pairs.as<zmo_pair_t>(), d_regs, R, A, L, d_ts, 0); c->launches++;
+		unsigned long long h[8];
+		CUDA_TRY(cudaMemcpyAsync(h, ctr + CTR_ARENA, 8 * 8, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		/* h: [0]=arena cursor [1]=work [2]=overflow [3..6]=n_ext_w,n_ext_n,n_glb_w,n_glb_n [7]=cig cursor */
+		if(h[2]){
+			if(attempt >= 6) return zmo_set_err(ZMO_ERR_CAPACITY, "DP arena overflow after %d attempts", attempt);
+			arena_words = std::max(arena_words * 2, h[0] + (64ull << 20)); cig_cap_words = std::max(cig_cap_words * 2, h[7] + (1ull << 20));
+			continue;
+		}
+		const uint32_t n_ew = (uint32_t)h[3], n_en = (uint32_t)h[4], n_gw = (uint32_t)h[5], n_gn = (uint32_t)h[6];
+		{
+			StageTimer tm(c, ST_EXT);
+			if(zmo_launch_ext(c, 1, true, L.ext_w, nullptr, n_ew, arena, cig_arena, d_res, CTR_CELLS_EXT)) return ZMO_ERR_CUDA;
+			if(zmo_launch_ext(c, 1, false, L.ext_n, nullptr, n_en, arena, cig_arena, d_res, CTR_CELLS_EXT)) return ZMO_ERR_CUDA;
+		}
+		{
+			StageTimer tm(c, ST_GAP);
+			if(zmo_launch_glb(c, true, L.glb_w, nullptr, n_gw, arena, cig_arena, d_res, CTR_CELLS_GAP)) return ZMO_ERR_CUDA;
+			if(zmo_launch_glb(c, false, L.glb_n, nullptr, n_gn, arena, cig_arena, d_res, CTR_CELLS_GAP)) return ZMO_ERR_CUDA;
+		}
+		/* plan2: right extensions appended to the same ext lists */
+		k_plan2<<<(nt + 63) / 64, 64, 0, c->stream>>>(d_tasks, nt, SL.pairs.as<zmo_pair_t>(), d_regs, d_res, R, A, L, d_ts); c->launches++;
+		CUDA_TRY(cudaMemcpyAsync(h, ctr + CTR_ARENA, 8 * 8, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		if(h[2]){
+			if(attempt >= 6) return zmo_set_err(ZMO_ERR_CAPACITY, "DP arena overflow after %d attempts", attempt);
+			arena_words = std::max(arena_words * 2, h[0] + (64ull << 20)); cig_cap_words = std::max(cig_cap_words * 2, h[7] + (1ull << 20));
+			continue;
+		}
+		const uint32_t n_ew2 = (uint32_t)h[3], n_en2 = (uint32_t)h[4];
+		{
+			StageTimer tm(c, ST_EXT);
+			if(zmo_launch_ext(c, 1, true, L.ext_w + n_ew, nullptr, n_ew2 - n_ew, arena, cig_arena, d_res, CTR_CELLS_EXT)) return ZMO_ERR_CUDA;
+			if(zmo_launch_ext(c, 1, false, L.ext_n + n_en, nullptr, n_en2 - n_en, arena, cig_arena, d_res, CTR_CELLS_EXT)) return ZMO_ERR_CUDA;
+		}
+		/* final sizes, offsets, stitched CIGARs */
+		unsigned long long *d_need = c->s7.as<unsigned long long>(), *d_ooff = d_need + nt + 1;
+		k_finish_size<<<(nt + 127) / 128, 128, 0, c->stream>>>(nt, d_res, d_ts, d_need); c->launches++;
+		CUDA_TRY(cudaMemsetAsync(d_need + nt, 0, 8, c->stream));
+		CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_need, d_ooff, nt + 1, c->stream));
+		unsigned long long total = 0;
+		CUDA_TRY(cudaMemcpyAsync(&total, d_ooff + nt, 8, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		if(cigar_needed) *cigar_needed = total;
+		if(total > cigar_cap) return zmo_set_err(ZMO_ERR_CAPACITY, "cigar buffer too small: need %llu", total);
+		if(c->s5.reserve((total + 16) * 4) || c->cubtmp.reserve((size_t)nt * sizeof(zmo_record_t) + 256)) return ZMO_ERR_CUDA;
+		/* a job's index in [ext_w | ext_n | glb_w | glb_n] equals its result index by construction */
+		zmo_record_t *d_recs = c->cubtmp.as<zmo_record_t>();
+		k_finish<<<(nt + 63) / 64, 64, 0, c->stream>>>(d_tasks, nt, d_regs, d_res, d_jobs, cig_arena, A, d_ts, d_ooff, c->s5.as<uint32_t>(), d_recs); c->launches++;
+		CUDA_TRY(cudaGetLastError());
+		{
+			StageTimer tm(c, ST_COPY);
+			CUDA_TRY(cudaMemcpyAsync(recs, d_recs, (size_t)nt * sizeof(zmo_record_t), cudaMemcpyDeviceToHost, c->stream));
+			if(total) CUDA_TRY(cudaMemcpyAsync(cigars, c->s5.p, total * 4, cudaMemcpyDeviceToHost, c->stream));
+		}
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		c->counters[6] += (size_t)nt * sizeof(zmo_record_t) + total * 4;
+		return 0;
+	}
+}

@@ -54,8 +54,8 @@ extern "C" void zmo_counters(const zmo_ctx *c, uint64_t out[8]){
 	unsigned long long h[8];
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
-	if(cudaMemcpy(h, c->d_ctr.p, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess){ for(int i = 0; i < 5; i++) out[i] = h[i]; }
-	out[5] = c->counters[5]; out[6] = c->counters[6];
+	if(cudaMemcpy(h, c->d_ctr.p, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess){ for(int i = 0; i < 3; i++) out[i] = h[i]; }
+	out[3] = c->counters[3]; out[4] = c->counters[4]; out[5] = c->counters[5]; out[6] = c->counters[6];
 }
 
 /* re-pack the reference BaseBank layout (dna.h:78,263: 32 bases per uint64, MSB first, reads

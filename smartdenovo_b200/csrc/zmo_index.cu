@@ -1,0 +1,256 @@
+/*
+ * zmo_index.cu -- global k-mer index build and candidate-event query on the device.
+ *
+ * Index (replaces index_wtzmo / midx / msrt, wtzmo.c:227-430): scan the homopolymer-compressed
+ * canonical k-mers of reads [beg,end), keep the sampled ones (Jenkins hash of the low 32 bits,
+ * wtzmo.c:270-271), radix-sort (k-mer) with the posting (rd_id<<1|dir) as payload, run-length encode
+ * into distinct k-mers with 16-bit-saturating counts (wtzmo.c:276), derive K (wtzmo.c:380-393), and
+ * keep the postings of k-mers with 1 < count <= K (wtzmo.c:401-406).  The reference's 1024 sharded
+ * hash tables are replaced by one sorted array of distinct k-mers (binary search); only posting-list
+ * CONTENT is observable, not table layout.
+ *
+ * Candidate events (replaces the heap merge of query_wtzmo, wtzmo.c:433-562): gather
+ * (query, target<<1|strand, query offset, span) tuples of a batch of query reads, stable radix sort by
+ * (query, target<<1|strand) -- tuples are emitted in ascending query offset, so each group stays
+ * offset-ordered -- then per group ol = sum_i(off_i >= end_{i-1} ? len_i : end_i - end_{i-1}) with
+ * uint32 wrap (wtzmo.c:558-560).  Groups with ol >= kovl are returned in ascending key order; the
+ * host replays the top-ncand heap quirks (wtzmo.c:521-571).
+ *
+ * Device-wide sort/scan/run-length primitives come from CUB (shipped with the CUDA toolkit).
+ */
+#include <cub/cub.cuh>
+#include "zmo_ctx.cuh"
+#include "zmo_seed_core.cuh"
+
+/* ---------------------------------------------------------------- index build */
+__global__ void k_idx_count(DevReads R, uint32_t beg, uint32_t end, int ksize, int hk, uint32_t ksave, unsigned long long *cnt){
+	uint32_t rid = beg + blockIdx.x * blockDim.x + threadIdx.x;
+	if(rid >= end) return;
+	unsigned long long n = 0;
+	zmo_scan_kmers(R.words + R.woff[rid], R.len[rid], ksize, hk, [&](uint64_t mer, uint32_t, uint32_t, uint32_t){ if(zmo_kmer_sampled(mer, ksave)) n++; });
+	cnt[rid - beg] = n;
+}
+__global__ void k_idx_fill(DevReads R, uint32_t beg, uint32_t end, int ksize, int hk, uint32_t ksave, const unsigned long long *off, unsigned long long *keys, uint32_t *vals){
+	uint32_t rid = beg + blockIdx.x * blockDim.x + threadIdx.x;
+	if(rid >= end) return;
+	unsigned long long p = off[rid - beg];
+	zmo_scan_kmers(R.words + R.woff[rid], R.len[rid], ksize, hk, [&](uint64_t mer, uint32_t dir, uint32_t, uint32_t){
+		if(zmo_kmer_sampled(mer, ksave)){ keys[p] = mer; vals[p] = (rid << 1) | dir; p++; }
+	});
+}
+__global__ void k_idx_heads(const unsigned long long *keys, unsigned long long n, uint32_t *flag){
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i < n) flag[i] = (i == 0 || keys[i] != keys[i - 1]);
+}
+__global__ void k_idx_runs(const unsigned long long *keys, const uint32_t *flag, const uint32_t *pos, unsigned long long n, unsigned long long *mer, unsigned long long *run_start){
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i < n && flag[i]){ mer[pos[i]] = keys[i]; run_start[pos[i]] = i; }
+}
+__global__ void k_idx_counts(const unsigned long long *run_start, unsigned long long ne, unsigned long long n, uint32_t *cnt){
+	unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if(r < ne){ unsigned long long c = (r + 1 < ne? run_start[r + 1] : n) - run_start[r]; cnt[r] = c > 0xFFFFFFFFull? 0xFFFFFFFFu : (uint32_t)c; }
+}
+struct SatCount { __host__ __device__ unsigned long long operator()(uint32_t c) const { return c > 0xFFFFu? 0xFFFFull : (unsigned long long)c; } };
+__global__ void k_idx_flags(const uint32_t *cnt, uint64_t n, uint32_t K, uint8_t *flt, unsigned long long *kept, unsigned long long *stats){
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	uint32_t c = cnt[i];
+	bool high = c > 0xFFFFu || c > K, f = high || c <= 1;
+	flt[i] = f; kept[i] = f? 0 : c;
+	if(high) atomicAdd(stats + 0, 1ULL);
+	if(!f) atomicAdd(stats + 1, 1ULL);
+}
+__global__ void k_idx_gather(const unsigned long long *run_start, const unsigned long long *kept_off, const uint8_t *flt, const uint32_t *cnt, uint64_t n, const uint32_t *vals, uint32_t *post){
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n || flt[i]) return;
+	const unsigned long long s = run_start[i], d = kept_off[i]; const uint32_t c = cnt[i];
+	for(uint32_t k = 0; k < c; k++) post[d + k] = vals[s + k];
+}
+
+#define CUB_CALL(c, call_expr) do { size_t _tb = 0; void *_tp = nullptr; { auto d_temp = _tp; size_t &temp_bytes = _tb; CUDA_TRY(call_expr); } \
+	if((c)->cubtmp.reserve(_tb + 256)) return ZMO_ERR_CUDA; { void *d_temp = (c)->cubtmp.p; size_t &temp_bytes = _tb; CUDA_TRY(call_expr); } (c)->launches++; } while(0)
+
+extern "C" int zmo_index_build(zmo_ctx *c, uint32_t beg, uint32_t end, uint32_t *kcut_io, zmo_index_stats_t *stats){
+	if(!c || !kcut_io) return zmo_set_err(ZMO_ERR_ARG, "null argument");
+	if(c->n_reads == 0) return zmo_set_err(ZMO_ERR_STATE, "no reads uploaded");
+	if(end > c->n_reads) end = c->n_reads;     /* the reference reads past the table here when n_rd % n_idx != 0 (wtzmo.c:1283) */
+	if(beg >= end) return zmo_set_err(ZMO_ERR_ARG, "empty read range");
+	CUDA_TRY(cudaSetDevice(c->device));
+	StageTimer tm(c, ST_INDEX);
+	const uint32_t nr = end - beg; const int bs = 64; DevReads R = dev_reads(c);
+	if(c->s0.reserve(((size_t)nr + 1) * 8) || c->s1.reserve(((size_t)nr + 1) * 8)) return ZMO_ERR_CUDA;
+	unsigned long long *d_cnt = c->s0.as<unsigned long long>(), *d_off = c->s1.as<unsigned long long>();
+	k_idx_count<<<(nr + bs - 1) / bs, bs, 0, c->stream>>>(R, beg, end, c->par.ksize, c->par.hk, (uint32_t)c->par.ksave, d_cnt); c->launches++;
+	CUDA_TRY(cudaMemsetAsync(d_cnt + nr, 0, 8, c->stream));
+	CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_cnt, d_off, nr + 1, c->stream));
+	unsigned long long N = 0;
+	CUDA_TRY(cudaMemcpyAsync(&N, d_off + nr, 8, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	if(N == 0){ c->n_ent = 0; c->n_post = 0; c->have_index = true; if(*kcut_io < 2) *kcut_io = 100; c->kcut = *kcut_io; if(stats) memset(stats, 0, sizeof(*stats)); return 0; }
+	if(c->s2.reserve(N * 8) || c->s3.reserve(N * 8) || c->s4.reserve(N * 4) || c->s5.reserve(N * 4)) return ZMO_ERR_CUDA;
+	unsigned long long *k_in = c->s2.as<unsigned long long>(), *k_out = c->s3.as<unsigned long long>();
+	uint32_t *v_in = c->s4.as<uint32_t>(), *v_out = c->s5.as<uint32_t>();
+	k_idx_fill<<<(nr + bs - 1) / bs, bs, 0, c->stream>>>(R, beg, end, c->par.ksize, c->par.hk, (uint32_t)c->par.ksave, d_off, k_in, v_in); c->launches++;
+	CUB_CALL(c, cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, k_in, k_out, v_in, v_out, (uint64_t)N, 0, 2 * c->par.ksize, c->stream));
+	/* run-length encode (hand-rolled, 64-bit safe): head flags -> exclusive scan -> scatter of
+	 * distinct k-mers (ix_mer) and run starts; counts = difference of consecutive run starts */
+	if(N >= 0xFFFFFFF0ull) return zmo_set_err(ZMO_ERR_CAPACITY, "index partition too large (%llu sampled k-mers); split it with -G", N);
+	if(c->ix_mer.reserve(N * 8) || c->s0.reserve((N + 2) * 8) || c->s6.reserve(N * 4 + 16) || c->s7.reserve(N * 4 + 16)) return ZMO_ERR_CUDA;
+	unsigned long long *ctr = c->d_ctr.as<unsigned long long>();
+	uint32_t *d_hflag = c->s6.as<uint32_t>(), *d_hpos = c->s7.as<uint32_t>();
+	unsigned long long *run_start = c->s0.as<unsigned long long>();
+	k_idx_heads<<<(unsigned)((N + 255) / 256), 256, 0, c->stream>>>(k_out, N, d_hflag); c->launches++;
+	CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_hflag, d_hpos, (uint64_t)N, c->stream));
+	uint32_t lp = 0, lf = 0;
+	CUDA_TRY(cudaMemcpyAsync(&lp, d_hpos + (N - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(&lf, d_hflag + (N - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	const unsigned long long ne = (unsigned long long)lp + lf;
+	k_idx_runs<<<(unsigned)((N + 255) / 256), 256, 0, c->stream>>>(k_out, d_hflag, d_hpos, N, c->ix_mer.as<unsigned long long>(), run_start); c->launches++;
+	uint32_t *d_rc = v_in;       /* v_in is free after the sort */
+	k_idx_counts<<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(run_start, ne, N, d_rc); c->launches++;
+	/* K (wtzmo.c:380-393): ktot = sum of saturated counts over all distinct k-mers */
+	uint32_t K = *kcut_io, kavg = 0;
+	{
+		cub::TransformInputIterator<unsigned long long, SatCount, const uint32_t*> it(d_rc, SatCount());
+		CUB_CALL(c, cub::DeviceReduce::Sum(d_temp, temp_bytes, it, ctr + CTR_N2, (uint64_t)ne, c->stream));
+		unsigned long long ktot = 0;
+		CUDA_TRY(cudaMemcpyAsync(&ktot, ctr + CTR_N2, 8, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		kavg = (uint32_t)(ktot / (ne + 1));
+		if(K < 2){ uint32_t ka = kavg < 20? 20 : kavg; K = ka * 5; }
+	}
+	*kcut_io = K; c->kcut = K;
+	/* filter flags, kept offsets, postings */
+	if(c->s1.reserve((ne + 1) * 8) || c->ix_off.reserve((ne + 2) * 8) || c->ix_flt.reserve(ne + 8)) return ZMO_ERR_CUDA;
+	unsigned long long *kept = c->s1.as<unsigned long long>();
+	CUDA_TRY(cudaMemsetAsync(ctr + CTR_N3, 0, 16, c->stream));
+	k_idx_flags<<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(d_rc, ne, K, c->ix_flt.as<uint8_t>(), kept, ctr + CTR_N3); c->launches++;
+	CUDA_TRY(cudaMemsetAsync(kept + ne, 0, 8, c->stream));
+	CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, kept, c->ix_off.as<unsigned long long>(), (uint64_t)ne + 1, c->stream));
+	unsigned long long np = 0, st2[2] = {0, 0};
+	CUDA_TRY(cudaMemcpyAsync(&np, c->ix_off.as<unsigned long long>() + ne, 8, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(st2, ctr + CTR_N3, 16, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	if(c->ix_post.reserve((np + 4) * 4)) return ZMO_ERR_CUDA;
+	k_idx_gather<<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(run_start, c->ix_off.as<unsigned long long>(), c->ix_flt.as<uint8_t>(), d_rc, ne, v_out, c->ix_post.as<uint32_t>()); c->launches++;
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	c->n_ent = ne; c->n_post = np; c->have_index = true;
+	if(stats){ stats->n_kmers = ne; stats->n_postings = np; stats->n_filtered_high = st2[0]; stats->n_indexed = st2[1]; stats->kcut = K; stats->kavg = kavg; }
+	return 0;
+}
+
+/* ---------------------------------------------------------------- candidate events */
+struct IdxView { const unsigned long long *mer; const unsigned long long *off; const uint8_t *flt; const uint32_t *post; unsigned long long n; };
+__device__ __forceinline__ long long idx_find(const IdxView &I, unsigned long long mer){
+	unsigned long long lo = 0, hi = I.n;
+	while(lo < hi){ unsigned long long mid = (lo + hi) >> 1; if(I.mer[mid] < mer) lo = mid + 1; else hi = mid; }
+	return (lo < I.n && I.mer[lo] == mer)? (long long)lo : -1;
+}
+/* PASS 0 counts, PASS 1 fills.  key = qlocal<<32 | tkey ; val = off<<16 | len */
+template<int PASS>
+__global__ void k_cand_scan(DevReads R, IdxView I, const uint32_t *qids, uint32_t nq, int ksize, int hk, uint32_t ksave,
+		unsigned long long *cnt_or_off, unsigned long long *keys, unsigned long long *vals){
+	uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+	if(q >= nq) return;
+	const uint32_t qid = qids[q], qlen = R.len[qid], up = (uint32_t)((double)qlen * 1.2);
+	unsigned long long n = PASS? cnt_or_off[q] : 0;
+	zmo_scan_kmers(R.words + R.woff[qid], qlen, ksize, hk, [&](uint64_t mer, uint32_t, uint32_t off, uint32_t ln){
+		if(!zmo_kmer_sampled(mer, ksave)) return;
+		const long long e = idx_find(I, mer);
+		if(e < 0 || I.flt[e]) return;
+		const unsigned long long b0 = I.off[e], b1 = I.off[e + 1];
+		for(unsigned long long b = b0; b < b1; b++){
+			const uint32_t tk = I.post[b], tid = tk >> 1;
+			if(tid == qid) continue;
+			if(R.len[tid] > up) continue;
+			if(PASS){ keys[n] = ((unsigned long long)q << 32) | tk; vals[n] = ((unsigned long long)off << 16) | ln; }
+			n++;
+		}
+	});
+	if(!PASS) cnt_or_off[q] = n;
+}
+/* one thread per sorted tuple; group heads accumulate the union length of their group */
+__global__ void k_cand_union(const unsigned long long *keys, const unsigned long long *vals, unsigned long long n, uint32_t kovl, uint32_t *flag, uint32_t *ol_out){
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	const unsigned long long key = keys[i];
+	if(i && keys[i - 1] == key){ flag[i] = 0; return; }
+	uint32_t ol = 0, lst = 0;
+	for(unsigned long long j = i; j < n && keys[j] == key; j++){
+		const uint32_t off = (uint32_t)(vals[j] >> 16), ln = (uint32_t)(vals[j] & 0xFFFFu);
+		if(off >= lst) ol += ln; else ol += off + ln - lst;
+		lst = off + ln;
+	}
+	flag[i] = ol >= kovl; ol_out[i] = ol;
+}
+__global__ void k_cand_emit(const unsigned long long *keys, const uint32_t *flag, const uint32_t *pos, const uint32_t *ol, unsigned long long n, zmo_event_t *ev, uint32_t *ev_q){
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n || !flag[i]) return;
+	zmo_event_t e; e.tkey = (uint32_t)keys[i]; e.ol = ol[i];
+	ev[pos[i]] = e; ev_q[pos[i]] = (uint32_t)(keys[i] >> 32);
+}
+__global__ void k_cand_offsets(const uint32_t *ev_q, uint32_t nev, uint32_t nq, unsigned long long *ev_off){
+	uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+	if(q > nq) return;
+	uint32_t lo = 0, hi = nev;     /* first event with query index >= q */
+	while(lo < hi){ uint32_t mid = (lo + hi) >> 1; if(ev_q[mid] < q) lo = mid + 1; else hi = mid; }
+	ev_off[q] = lo;
+}
+
+extern "C" int zmo_candidates(zmo_ctx *c, const uint32_t *qids, uint32_t nq, uint64_t *ev_off, zmo_event_t *events, uint64_t ev_cap, uint64_t *ev_needed){
+	if(!c || !qids || !ev_off) return zmo_set_err(ZMO_ERR_ARG, "null argument");
+	if(!c->have_index) return zmo_set_err(ZMO_ERR_STATE, "zmo_index_build has not been called");
+	if(ev_needed) *ev_needed = 0;
+	if(nq == 0){ ev_off[0] = 0; return 0; }
+	for(uint32_t i = 0; i < nq; i++) if(qids[i] >= c->n_reads) return zmo_set_err(ZMO_ERR_ARG, "query id out of range");
+	CUDA_TRY(cudaSetDevice(c->device));
+	StageTimer tm(c, ST_CAND);
+	DevReads R = dev_reads(c);
+	IdxView I; I.mer = c->ix_mer.as<unsigned long long>(); I.off = c->ix_off.as<unsigned long long>(); I.flt = c->ix_flt.as<uint8_t>(); I.post = c->ix_post.as<uint32_t>(); I.n = c->n_ent;
+	if(c->s0.reserve((size_t)nq * 4) || c->s1.reserve(((size_t)nq + 2) * 8) || c->s2.reserve(((size_t)nq + 2) * 8)) return ZMO_ERR_CUDA;
+	uint32_t *d_q = c->s0.as<uint32_t>(); unsigned long long *d_cnt = c->s1.as<unsigned long long>(), *d_off = c->s2.as<unsigned long long>();
+	CUDA_TRY(cudaMemcpyAsync(d_q, qids, (size_t)nq * 4, cudaMemcpyHostToDevice, c->stream));
+	c->counters[5] += (uint64_t)nq * 4;
+	const int bs = 32;
+	k_cand_scan<0><<<(nq + bs - 1) / bs, bs, 0, c->stream>>>(R, I, d_q, nq, c->par.ksize, c->par.hk, (uint32_t)c->par.ksave, d_cnt, nullptr, nullptr); c->launches++;
+	CUDA_TRY(cudaMemsetAsync(d_cnt + nq, 0, 8, c->stream));
+	CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_cnt, d_off, nq + 1, c->stream));
+	unsigned long long N = 0;
+	CUDA_TRY(cudaMemcpyAsync(&N, d_off + nq, 8, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	uint32_t nev = 0;
+	if(N){
+		if(N >= 0xFFFFFFFFull) return zmo_set_err(ZMO_ERR_CAPACITY, "candidate batch too large (%llu tuples); use a smaller query batch", N);
+		if(c->s3.reserve(N * 8) || c->s4.reserve(N * 8) || c->s5.reserve(N * 8) || c->s6.reserve(N * 8) || c->s7.reserve(N * 12 + 64)) return ZMO_ERR_CUDA;
+		unsigned long long *k_in = c->s3.as<unsigned long long>(), *k_out = c->s4.as<unsigned long long>(), *v_in = c->s5.as<unsigned long long>(), *v_out = c->s6.as<unsigned long long>();
+		k_cand_scan<1><<<(nq + bs - 1) / bs, bs, 0, c->stream>>>(R, I, d_q, nq, c->par.ksize, c->par.hk, (uint32_t)c->par.ksave, d_off, k_in, v_in); c->launches++;
+		int qbits = 1; while((1ull << qbits) < nq) qbits++;
+		CUB_CALL(c, cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, k_in, k_out, v_in, v_out, (uint64_t)N, 0, 32 + qbits, c->stream));
+		uint32_t *d_flag = c->s7.as<uint32_t>(), *d_ol = d_flag + N, *d_pos = d_ol + N;
+		k_cand_union<<<(unsigned)((N + 255) / 256), 256, 0, c->stream>>>(k_out, v_out, N, (uint32_t)c->par.kovl, d_flag, d_ol); c->launches++;
+		CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_flag, d_pos, (uint64_t)N, c->stream));
+		uint32_t lastpos = 0, lastflag = 0;
+		CUDA_TRY(cudaMemcpyAsync(&lastpos, d_pos + (N - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(&lastflag, d_flag + (N - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		nev = lastpos + lastflag;
+		/* events + their query index reuse k_in / v_in (free after the sort) */
+		zmo_event_t *d_ev = (zmo_event_t*)k_in; uint32_t *d_evq = (uint32_t*)v_in;
+		k_cand_emit<<<(unsigned)((N + 255) / 256), 256, 0, c->stream>>>(k_out, d_flag, d_pos, d_ol, N, d_ev, d_evq); c->launches++;
+		k_cand_offsets<<<(nq + 1 + 127) / 128, 128, 0, c->stream>>>(d_evq, nev, nq, d_off); c->launches++;
+		CUDA_TRY(cudaGetLastError());
+		if(ev_needed) *ev_needed = nev;
+		if(nev > ev_cap){ CUDA_TRY(cudaStreamSynchronize(c->stream)); return zmo_set_err(ZMO_ERR_CAPACITY, "event buffer too small: need %u", nev); }
+		if(nev && !events) return zmo_set_err(ZMO_ERR_ARG, "null event buffer");
+		CUDA_TRY(cudaMemcpyAsync(ev_off, d_off, ((size_t)nq + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+		if(nev) CUDA_TRY(cudaMemcpyAsync(events, d_ev, (size_t)nev * sizeof(zmo_event_t), cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		c->counters[6] += ((size_t)nq + 1) * 8 + (size_t)nev * sizeof(zmo_event_t);
+		c->counters[4] += N;
+	} else {
+		for(uint32_t i = 0; i <= nq; i++) ev_off[i] = 0;
+	}
+	return 0;
+}

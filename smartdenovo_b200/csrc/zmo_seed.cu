@@ -1,0 +1,231 @@
+/*
+ * zmo_seed.cu -- pair seeding on the device: z-index of every query read of the batch, z-mer
+ * matching of every (query, candidate) pair, and (one thread per pair, order-exact serial logic from
+ * zmo_seed_core.cuh) the (off1,off2) sort, window finding and window chaining of both strands.
+ * Replaces wtzmo.c:845-914 minus the windeps side effect, which stays in the host replay.
+ *
+ * z-index layout: all z-mers of the batch's distinct query reads are emitted as
+ * key = qlocal<<32 | mer, payload = (off,len,dir), stable-radix-sorted by key (emission is in offset
+ * order, so each mer run stays offset-sorted like hzm_aln.h:101).  Runs shorter than -Z become slots
+ * (the reference's bit-vector + rank, hzm_aln.h:107-114,152, is replaced by a binary search over the
+ * read's sorted slot list).
+ */
+#include <cub/cub.cuh>
+#include <unordered_map>
+#include "zmo_ctx.cuh"
+#include "zmo_seed_core.cuh"
+
+#define CUB_CALL(c, call_expr) do { size_t _tb = 0; void *_tp = nullptr; { auto d_temp = _tp; size_t &temp_bytes = _tb; CUDA_TRY(call_expr); } \
+	if((c)->cubtmp.reserve(_tb + 256)) return ZMO_ERR_CUDA; { void *d_temp = (c)->cubtmp.p; size_t &temp_bytes = _tb; CUDA_TRY(call_expr); } (c)->launches++; } while(0)
+
+template<int PASS>
+__global__ void k_z_scan(DevReads R, const uint32_t *uq, uint32_t nuq, int zsize, int hz, unsigned long long *cnt_or_off, unsigned long long *keys, unsigned long long *vals){
+	uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+	if(u >= nuq) return;
+	const uint32_t rid = uq[u];
+	unsigned long long n = PASS? cnt_or_off[u] : 0;
+	zmo_scan_kmers(R.words + R.woff[rid], R.len[rid], zsize, hz, [&](uint64_t mer, uint32_t dir, uint32_t off, uint32_t ln){
+		if(PASS){ keys[n] = ((unsigned long long)u << 32) | (uint32_t)mer; vals[n] = ((unsigned long long)off << 17) | ((unsigned long long)ln << 1) | dir; }
+		n++;
+	});
+	if(!PASS) cnt_or_off[u] = n;
+}
+/* per sorted z-seed: unpack payload; run heads count their run and flag it as a slot if shorter than zcut */
+__global__ void k_z_heads(const unsigned long long *keys, const unsigned long long *vals, unsigned long long n, uint32_t zcut, uint32_t *flag, uint32_t *runlen, DevZSeed *zs){
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	const unsigned long long v = vals[i]; DevZSeed s; s.off = (uint32_t)(v >> 17); s.len = (uint16_t)((v >> 1) & 0xFFFFu); s.dir = (uint8_t)(v & 1u); s.pad = 0;
+	zs[i] = s;
+	const unsigned long long key = keys[i];
+	if(i && keys[i - 1] == key){ flag[i] = 0; return; }
+	uint32_t c = 1;
+	for(unsigned long long j = i + 1; j < n && keys[j] == key && c <= zcut; j++) c++;
+	flag[i] = c < zcut; runlen[i] = c;
+}
+__global__ void k_z_slots(const unsigned long long *keys, const uint32_t *flag, const uint32_t *pos, const uint32_t *runlen, unsigned long long n, const unsigned long long *zoff, DevSlot *slots){
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n || !flag[i]) return;
+	const uint32_t u = (uint32_t)(keys[i] >> 32);
+	DevSlot s; s.mer = (uint32_t)keys[i]; s.off = (uint32_t)(i - zoff[u]); s.cnt = runlen[i];
+	slots[pos[i]] = s;
+}
+__global__ void k_z_ranges(const unsigned long long *zoff, const uint32_t *pos, uint32_t nuq, unsigned long long Z, uint32_t NS, uint32_t *slot_beg){
+	uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+	if(u > nuq) return;
+	slot_beg[u] = (u < nuq && zoff[u] < Z)? pos[zoff[u]] : NS;
+}
+__global__ void k_p_ns(const uint32_t *pq, uint32_t np, const uint32_t *slot_beg, unsigned long long *ns){
+	uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if(p < np) ns[p] = slot_beg[pq[p] + 1] - slot_beg[pq[p]];
+}
+struct ZIdxView { const DevSlot *slots; const uint32_t *slot_beg; const DevZSeed *zs; const unsigned long long *zoff; };
+template<int PASS>
+__global__ void k_p_match(DevReads R, ZIdxView Z, const uint32_t *pq, const uint32_t *pc, uint32_t np, const unsigned long long *kc_off, uint8_t *kcnts,
+		int zsize, int hz, uint32_t zcut, uint32_t kvar, unsigned long long *nz_or_off, DevZPair *cache){
+	uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if(p >= np) return;
+	const uint32_t u = pq[p], cid = pc[p];
+	const uint32_t sb = Z.slot_beg[u], ns = Z.slot_beg[u + 1] - sb;
+	const uint32_t n = zmo_zmatch(R.words + R.woff[cid], R.len[cid], Z.slots + sb, ns, Z.zs + Z.zoff[u], kcnts + kc_off[p], zsize, hz, zcut, kvar, PASS? cache + nz_or_off[p] : nullptr);
+	if(!PASS) nz_or_off[p] = n;
+}
+
+struct SeedOut { DevWin *wins; DevZPair *anc; unsigned long long cap_wins, cap_anc; unsigned long long *cur_wins, *cur_anc, *overflow; };
+__global__ void k_p_seed(const unsigned long long *cache_off, uint32_t np, DevZPair *cache, uint8_t *scratch, size_t per, SeedPar par, SeedOut O, zmo_pairseed_t *seeds){
+	uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if(p >= np) return;
+	const unsigned long long c0 = cache_off[p]; const uint32_t n = (uint32_t)(cache_off[p + 1] - c0);
+	zmo_pairseed_t S; S.n_zpair = n; S.ovl[0] = S.ovl[1] = 0; S.win_off[0] = S.win_off[1] = 0; S.n_win[0] = S.n_win[1] = 0;
+	if((unsigned long long)n * par.zsize >= par.ztot){
+		DevZPair *rs = cache + c0;
+		zmo_ref_sort(rs, (size_t)n, GtZPairOff12());
+		uint8_t *scr = scratch + c0 * per + (size_t)64 * p;
+		for(int d = 0; d < 2; d++){
+			PairScratch P = zmo_pair_scratch_carve(scr, n); uint32_t nwin = 0; int ovf = 0;
+			const int ovl = zmo_pair_seed_strand(rs, n, d, par, P, &nwin, &ovf);
+			if(ovf){ atomicAdd(O.overflow, 1ULL); break; }
+			S.ovl[d] = ovl;
+			if((uint32_t)ovl >= par.ztot){
+				uint32_t kw = 0, ka = 0;
+				for(uint32_t j = 0; j < nwin; j++) if(!P.w2[j].closed){ kw++; ka += P.w2[j].anc1 - P.w2[j].anc0; }
+				const unsigned long long w0 = atomicAdd(O.cur_wins, (unsigned long long)kw), a0 = atomicAdd(O.cur_anc, (unsigned long long)ka);
+				if(w0 + kw > O.cap_wins || a0 + ka > O.cap_anc){ atomicAdd(O.overflow, 1ULL); break; }
+				unsigned long long wi = w0, ai = a0;
+				for(uint32_t j = 0; j < nwin; j++){
+					DevWin w = P.w2[j];
+					if(w.closed) continue;
+					const uint32_t na = w.anc1 - w.anc0;
+					for(uint32_t k = 0; k < na; k++) O.anc[ai + k] = P.a2[w.anc0 + k];
+					w.anc0 = (uint32_t)ai; w.anc1 = (uint32_t)(ai + na); ai += na;
+					O.wins[wi++] = w;
+				}
+				S.win_off[d] = (uint32_t)w0; S.n_win[d] = kw;
+			}
+		}
+	}
+	seeds[p] = S;
+}
+
+/* steps shared by the SW and dot-matrix paths: z-index of the batch's query reads + match lists */
+struct SeedWork { uint32_t np, nuq; unsigned long long T; unsigned long long *cache_off; DevZPair *cache; };
+static int seed_prepare(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, SeedWork &W, DevBuf &cache_buf){
+	DevReads R = dev_reads(c);
+	std::vector<uint32_t> uq, pq(np), pc(np); std::unordered_map<uint32_t, uint32_t> qmap;
+	for(uint32_t i = 0; i < np; i++){
+		if(pairs[i].qid >= c->n_reads || pairs[i].cid >= c->n_reads) return zmo_set_err(ZMO_ERR_ARG, "pair %u: read id out of range", i);
+		auto it = qmap.find(pairs[i].qid);
+		if(it == qmap.end()){ it = qmap.emplace(pairs[i].qid, (uint32_t)uq.size()).first; uq.push_back(pairs[i].qid); }
+		pq[i] = it->second; pc[i] = pairs[i].cid;
+	}
+	const uint32_t nuq = (uint32_t)uq.size();
+	W.np = np; W.nuq = nuq;
+	/* layout of small per-batch arrays in s0: uq | pq | pc | slot_beg ; s1: zcnt/zoff ; */
+	if(c->s0.reserve(((size_t)nuq + 2 + 2 * (size_t)np + nuq + 4) * 4) || c->s1.reserve(((size_t)nuq + 2) * 16)) return ZMO_ERR_CUDA;
+	uint32_t *d_uq = c->s0.as<uint32_t>(), *d_pq = d_uq + nuq + 1, *d_pc = d_pq + np, *d_slot_beg = d_pc + np;
+	unsigned long long *d_zcnt = c->s1.as<unsigned long long>(), *d_zoff = d_zcnt + nuq + 1;
+	CUDA_TRY(cudaMemcpyAsync(d_uq, uq.data(), (size_t)nuq * 4, cudaMemcpyHostToDevice, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(d_pq, pq.data(), (size_t)np * 4, cudaMemcpyHostToDevice, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(d_pc, pc.data(), (size_t)np * 4, cudaMemcpyHostToDevice, c->stream));
+	c->counters[5] += ((size_t)nuq + 2 * (size_t)np) * 4;
+	const int bs = 32;
+	k_z_scan<0><<<(nuq + bs - 1) / bs, bs, 0, c->stream>>>(R, d_uq, nuq, c->par.zsize, c->par.hz, d_zcnt, nullptr, nullptr); c->launches++;
+	CUDA_TRY(cudaMemsetAsync(d_zcnt + nuq, 0, 8, c->stream));
+	CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_zcnt, d_zoff, nuq + 1, c->stream));
+	unsigned long long Z = 0;
+	CUDA_TRY(cudaMemcpyAsync(&Z, d_zoff + nuq, 8, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	if(Z >= 0xFFFFFFF0ull) return zmo_set_err(ZMO_ERR_CAPACITY, "pair batch too large (%llu z-mers)", Z);
+	/* s2 keys_in, s3 keys_out, s4 vals_in, s5 vals_out, s6 flag|pos|runlen, s7 zs|slots */
+	const unsigned long long Zp = Z + 4;
+	if(c->s2.reserve(Zp * 8) || c->s3.reserve(Zp * 8) || c->s4.reserve(Zp * 8) || c->s5.reserve(Zp * 8) || c->s6.reserve(Zp * 12) || c->s7.reserve(Zp * (sizeof(DevZSeed) + sizeof(DevSlot)))) return ZMO_ERR_CUDA;
+	unsigned long long *k_in = c->s2.as<unsigned long long>(), *k_out = c->s3.as<unsigned long long>(), *v_in = c->s4.as<unsigned long long>(), *v_out = c->s5.as<unsigned long long>();
+	uint32_t *d_flag = c->s6.as<uint32_t>(), *d_pos = d_flag + Zp, *d_run = d_pos + Zp;
+	DevZSeed *d_zs = c->s7.as<DevZSeed>(); DevSlot *d_slots = (DevSlot*)(d_zs + Zp);
+	uint32_t NS = 0;
+	if(Z){
+		k_z_scan<1><<<(nuq + bs - 1) / bs, bs, 0, c->stream>>>(R, d_uq, nuq, c->par.zsize, c->par.hz, d_zoff, k_in, v_in); c->launches++;
+		int qbits = 1; while((1ull << qbits) < nuq) qbits++;
+		CUB_CALL(c, cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, k_in, k_out, v_in, v_out, (uint64_t)Z, 0, 32 + qbits, c->stream));
+		k_z_heads<<<(unsigned)((Z + 255) / 256), 256, 0, c->stream>>>(k_out, v_out, Z, (uint32_t)c->par.zcut, d_flag, d_run, d_zs); c->launches++;
+		CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_flag, d_pos, (uint64_t)Z, c->stream));
+		uint32_t lp = 0, lf = 0;
+		CUDA_TRY(cudaMemcpyAsync(&lp, d_pos + (Z - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(&lf, d_flag + (Z - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		NS = lp + lf;
+		k_z_slots<<<(unsigned)((Z + 255) / 256), 256, 0, c->stream>>>(k_out, d_flag, d_pos, d_run, Z, d_zoff, d_slots); c->launches++;
+	}
+	k_z_ranges<<<(nuq + 1 + 127) / 128, 128, 0, c->stream>>>(d_zoff, d_pos, nuq, Z, NS, d_slot_beg); c->launches++;
+	/* per-pair slot counters: kc_off (s2 is free again after the sort), counts, match lists */
+	if(c->s2.reserve(((size_t)np + 2) * 32)) return ZMO_ERR_CUDA;
+	unsigned long long *d_ns = c->s2.as<unsigned long long>(), *d_kcoff = d_ns + np + 1, *d_nz = d_kcoff + np + 1, *d_coff = d_nz + np + 1;
+	k_p_ns<<<(np + 127) / 128, 128, 0, c->stream>>>(d_pq, np, d_slot_beg, d_ns); c->launches++;
+	CUDA_TRY(cudaMemsetAsync(d_ns + np, 0, 8, c->stream));
+	CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_ns, d_kcoff, np + 1, c->stream));
+	unsigned long long KC = 0;
+	CUDA_TRY(cudaMemcpyAsync(&KC, d_kcoff + np, 8, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	if(c->s4.reserve(KC + 64)) return ZMO_ERR_CUDA;     /* s4 (vals_in) is free after the sort */
+	uint8_t *d_kc = c->s4.as<uint8_t>();
+	ZIdxView ZV; ZV.slots = d_slots; ZV.slot_beg = d_slot_beg; ZV.zs = d_zs; ZV.zoff = d_zoff;
+	CUDA_TRY(cudaMemsetAsync(d_kc, 0, KC + 1, c->stream));
+	k_p_match<0><<<(np + bs - 1) / bs, bs, 0, c->stream>>>(R, ZV, d_pq, d_pc, np, d_kcoff, d_kc, c->par.zsize, c->par.hz, (uint32_t)c->par.zcut, (uint32_t)c->par.kvar, d_nz, nullptr); c->launches++;
+	CUDA_TRY(cudaMemsetAsync(d_nz + np, 0, 8, c->stream));
+	CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_nz, d_coff, np + 1, c->stream));
+	unsigned long long T = 0;
+	CUDA_TRY(cudaMemcpyAsync(&T, d_coff + np, 8, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	if(T >= 0xFFFFFFF0ull) return zmo_set_err(ZMO_ERR_CAPACITY, "pair batch too large (%llu z-mer matches)", T);
+	if(cache_buf.reserve((T + 4) * sizeof(DevZPair))) return ZMO_ERR_CUDA;
+	CUDA_TRY(cudaMemsetAsync(d_kc, 0, KC + 1, c->stream));
+	k_p_match<1><<<(np + bs - 1) / bs, bs, 0, c->stream>>>(R, ZV, d_pq, d_pc, np, d_kcoff, d_kc, c->par.zsize, c->par.hz, (uint32_t)c->par.zcut, (uint32_t)c->par.kvar, d_coff, cache_buf.as<DevZPair>()); c->launches++;
+	CUDA_TRY(cudaGetLastError());
+	W.T = T; W.cache_off = d_coff; W.cache = cache_buf.as<DevZPair>();
+	c->counters[3] += T;
+	return 0;
+}
+
+extern "C" int zmo_pair_windows(zmo_ctx *c, int slot, const zmo_pair_t *pairs, uint32_t np, zmo_pairseed_t *seeds, zmo_window_t *wins, uint64_t win_cap, uint64_t *win_needed){
+	if(!c || (np && (!pairs || !seeds))) return zmo_set_err(ZMO_ERR_ARG, "null argument");
+	if(slot < 0 || slot > 1) return zmo_set_err(ZMO_ERR_ARG, "slot must be 0 or 1");
+	if(c->n_reads == 0) return zmo_set_err(ZMO_ERR_STATE, "no reads uploaded");
+	if(win_needed) *win_needed = 0;
+	SeedSlot &SL = c->slot[slot];
+	SL.np = 0; SL.n_wins = SL.n_anchors = 0;
+	if(np == 0) return 0;
+	CUDA_TRY(cudaSetDevice(c->device));
+	StageTimer tm(c, ST_SEED);
+	const size_t per = 5 * 4 + sizeof(DevWin) + sizeof(DevZPair);
+	SeedPar par; par.zsize = c->par.zsize; par.kwin = c->par.kwin; par.kstep = c->par.kstep; par.zovl = c->par.zovl; par.ztot = c->par.ztot; par.W = c->par.W;
+	unsigned long long *ctr = c->d_ctr.as<unsigned long long>();
+	unsigned long long nw = 0, na = 0;
+	for(int attempt = 0; attempt < 2; attempt++){
+		SeedWork W;
+		if(int rc = seed_prepare(c, pairs, np, W, c->s5)) return rc;      /* match lists live in s5 */
+		const unsigned long long T = W.T;
+		const unsigned long long cap_w = attempt? 2 * T + 64 : T / 2 + 64, cap_a = 2 * T + 64;
+		if(c->s3.reserve(T * per + (size_t)64 * np + 256) || SL.wins.reserve(cap_w * sizeof(DevWin)) || SL.anchors.reserve(cap_a * sizeof(DevZPair)) || SL.seeds.reserve((size_t)np * sizeof(zmo_pairseed_t)) || SL.pairs.reserve((size_t)np * sizeof(zmo_pair_t))) return ZMO_ERR_CUDA;
+		CUDA_TRY(cudaMemsetAsync(ctr + CTR_N1, 0, 24, c->stream));
+		SeedOut O; O.wins = SL.wins.as<DevWin>(); O.anc = SL.anchors.as<DevZPair>(); O.cap_wins = cap_w; O.cap_anc = cap_a; O.cur_wins = ctr + CTR_N1; O.cur_anc = ctr + CTR_N2; O.overflow = ctr + CTR_N3;
+		k_p_seed<<<(np + 31) / 32, 32, 0, c->stream>>>(W.cache_off, np, W.cache, c->s3.as<uint8_t>(), per, par, O, SL.seeds.as<zmo_pairseed_t>()); c->launches++;
+		CUDA_TRY(cudaGetLastError());
+		unsigned long long h[3];
+		CUDA_TRY(cudaMemcpyAsync(h, ctr + CTR_N1, 24, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		if(h[2] == 0){ nw = h[0]; na = h[1]; break; }
+		if(attempt) return zmo_set_err(ZMO_ERR_CAPACITY, "window arena overflow");
+	}
+	if(win_needed) *win_needed = nw;
+	if(nw > win_cap) return zmo_set_err(ZMO_ERR_CAPACITY, "window buffer too small: need %llu", nw);
+	CUDA_TRY(cudaMemcpyAsync(SL.pairs.p, pairs, (size_t)np * sizeof(zmo_pair_t), cudaMemcpyHostToDevice, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(seeds, SL.seeds.p, (size_t)np * sizeof(zmo_pairseed_t), cudaMemcpyDeviceToHost, c->stream));
+	std::vector<DevWin> hw(nw);
+	if(nw) CUDA_TRY(cudaMemcpyAsync(hw.data(), SL.wins.p, nw * sizeof(DevWin), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	for(unsigned long long i = 0; i < nw; i++){ wins[i].beg[0] = hw[i].beg[0]; wins[i].beg[1] = hw[i].beg[1]; wins[i].end[0] = hw[i].end[0]; wins[i].end[1] = hw[i].end[1]; }
+	SL.np = np; SL.n_wins = nw; SL.n_anchors = na;
+	SL.h_seeds.assign(seeds, seeds + np);
+	c->counters[5] += (size_t)np * sizeof(zmo_pair_t);
+	c->counters[6] += (size_t)np * sizeof(zmo_pairseed_t) + nw * sizeof(DevWin);
+	return 0;
+}
