@@ -14,6 +14,7 @@
 #include <unordered_map>
 #include "zmo_ctx.cuh"
 #include "zmo_seed_core.cuh"
+#include "zmo_seed.cuh"
 
 #define CUB_CALL(c, call_expr) do { size_t _tb = 0; void *_tp = nullptr; { auto d_temp = _tp; size_t &temp_bytes = _tb; CUDA_TRY(call_expr); } \
 	if((c)->cubtmp.reserve(_tb + 256)) return ZMO_ERR_CUDA; { void *d_temp = (c)->cubtmp.p; size_t &temp_bytes = _tb; CUDA_TRY(call_expr); } (c)->launches++; } while(0)
@@ -107,8 +108,7 @@ __global__ void k_p_seed(const unsigned long long *cache_off, uint32_t np, DevZP
 }
 
 /* steps shared by the SW and dot-matrix paths: z-index of the batch's query reads + match lists */
-struct SeedWork { uint32_t np, nuq; unsigned long long T; unsigned long long *cache_off; DevZPair *cache; };
-static int seed_prepare(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, SeedWork &W, DevBuf &cache_buf){
+int seed_prepare(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, SeedWork &W, DevBuf &cache_buf){
 	DevReads R = dev_reads(c);
 	std::vector<uint32_t> uq, pq(np), pc(np); std::unordered_map<uint32_t, uint32_t> qmap;
 	for(uint32_t i = 0; i < np; i++){

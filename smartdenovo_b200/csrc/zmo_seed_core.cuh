@@ -17,7 +17,7 @@
 #include <stddef.h>
 #ifdef __CUDACC__
 #define ZMO_HD __host__ __device__ __forceinline__
-#define ZMO_HDN __host__ __device__
+#define ZMO_HDN __host__ __device__ inline
 #define ZMO_HDM __host__ __device__ __forceinline__
 #else
 #define ZMO_HD static inline

@@ -59,3 +59,29 @@ extern "C" int sim_pair_windows(const uint8_t *pb1, int alen, const uint8_t *pb2
 	*n_anc_out = na;
 	return nw;
 }
+
+#include "../../smartdenovo_b200/csrc/zmo_dot_core.cuh"
+extern "C" int sim_pair_dotmatrix(const uint8_t *pb1, int alen, const uint8_t *pb2, int blen, int zsize, int hz, int zcut, int kvar,
+		int xvar, int yvar, int min_block_len, int max_overhang, float dev_pen, float gap_pen, int *out){
+	std::vector<uint32_t> qw = pack(pb1, alen), cw = pack(pb2, blen);
+	struct ZE { uint32_t mer; DevZSeed s; };
+	std::vector<ZE> ze;
+	zmo_scan_kmers(qw.data(), (uint32_t)alen, zsize, hz, [&](uint64_t mer, uint32_t dir, uint32_t off, uint32_t ln){ ZE e; e.mer = (uint32_t)mer; e.s.off = off; e.s.len = (uint16_t)ln; e.s.dir = (uint8_t)dir; e.s.pad = 0; ze.push_back(e); });
+	std::stable_sort(ze.begin(), ze.end(), [](const ZE &a, const ZE &b){ return a.mer < b.mer; });
+	std::vector<DevZSeed> zs(ze.size()); std::vector<DevSlot> slots;
+	for(size_t i = 0; i < ze.size(); i++) zs[i] = ze[i].s;
+	for(size_t i = 0, j; i < ze.size(); i = j){
+		for(j = i + 1; j < ze.size() && ze[j].mer == ze[i].mer; j++);
+		if(j - i < (size_t)zcut){ DevSlot s; s.mer = ze[i].mer; s.off = (uint32_t)i; s.cnt = (uint32_t)(j - i); slots.push_back(s); }
+	}
+	std::vector<uint8_t> kc(slots.size() + 1, 0);
+	uint32_t n = zmo_zmatch(cw.data(), (uint32_t)blen, slots.data(), (uint32_t)slots.size(), zs.data(), kc.data(), zsize, hz, (uint32_t)zcut, (uint32_t)kvar, nullptr);
+	std::vector<DevZPair> cache(n + 1);
+	std::fill(kc.begin(), kc.end(), 0);
+	zmo_zmatch(cw.data(), (uint32_t)blen, slots.data(), (uint32_t)slots.size(), zs.data(), kc.data(), zsize, hz, (uint32_t)zcut, (uint32_t)kvar, cache.data());
+	DotPar par; par.xvar = xvar; par.yvar = yvar; par.min_block_len = min_block_len; par.max_overhang = max_overhang; par.deviation_penalty = dev_pen; par.gap_penalty = gap_pen;
+	std::vector<uint8_t> scr(zmo_dot_scratch_bytes(n));
+	DotRes r = zmo_dot_pair(cache.data(), n, alen, blen, par, scr.data());
+	out[0] = r.score; out[1] = r.qb; out[2] = r.qe; out[3] = r.tb; out[4] = r.te; out[5] = r.strand;
+	return (int)n;
+}

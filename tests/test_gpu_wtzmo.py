@@ -73,3 +73,84 @@ def test_seed_only_mode(tmp_path, gen_reads, oracle_bin):
 def test_nondefault_parameters(tmp_path, gen_reads, oracle_bin):
     _compare(tmp_path, gen_reads, oracle_bin, ["-n", "200", "-L", "5000", "-G", "60000", "-s", "9"],
              ["-k", "15", "-S", "2", "-z", "12", "-Z", "32", "-y", "600", "-R", "150", "-r", "250", "-w", "30", "-e", "300", "-W", "800", "-m", "0.55", "-s", "150", "-A", "50", "-B", "20"])
+
+
+def test_dot_matrix_mode(tmp_path, gen_reads, oracle_bin):
+    """smartdenovo.pl:48 / run_dmo.sh flags: -z 10 -Z 16 -U -1 -m 0.1 -A 1000 (records end with 0M)"""
+    n = _compare(tmp_path, gen_reads, oracle_bin, ["-n", "400", "-L", "5000", "-G", "80000", "-s", "7", "-m", "ont"], ["-k", "16", "-z", "10", "-Z", "16", "-U", "-1", "-m", "0.1", "-A", "1000"])
+    assert n > 300
+    _compare(tmp_path, gen_reads, oracle_bin, ["-n", "200", "-L", "6000", "-G", "60000", "-s", "1"], ["-k", "16", "-U", "256", "-U", "32", "-U", "300", "-U", "0.5", "-U", "0.02", "-m", "0.1"])
+
+
+def test_side_inputs(tmp_path, gen_reads, oracle_bin):
+    """-L tried pairs, -F excluded reads, -b clipping, -I query-only reads, -J minimum length"""
+    fa = str(tmp_path / "base.fa")
+    subprocess.run([gen_reads, "-n", "250", "-L", "5000", "-G", "70000", "-s", "21", "-o", fa], check=True)
+    names = [l[1:].strip() for l in open(fa) if l.startswith(">")]
+    seqs = [l.strip() for l in open(fa) if not l.startswith(">")]
+    with open(tmp_path / "L.pairs", "w") as f:
+        for i in range(0, 60, 2):
+            f.write("%s\t%s\n" % (names[i], names[i + 1]))
+    with open(tmp_path / "F.names", "w") as f:
+        f.write("# comment\n" + "\n".join(names[5:25]) + "\n")
+    with open(tmp_path / "B.clip", "w") as f:
+        for i in range(0, 250, 9):
+            f.write("%s\t%d\t%d\t%d\n" % (names[i], 100, len(seqs[i]) - 300, len(seqs[i])))
+    q = str(tmp_path / "q.fa")
+    subprocess.run([gen_reads, "-n", "30", "-L", "4000", "-G", "70000", "-s", "21", "-o", q], check=True)
+    base = ["-k", "16", "-s", "200", "-m", "0.6"]
+    for extra in (["-L", str(tmp_path / "L.pairs")], ["-F", str(tmp_path / "F.names")], ["-b", str(tmp_path / "B.clip")], ["-I", q], ["-J", "4500"], ["-C"]):
+        for f in ("ref.ovl", "gpu.ovl", "ref.ovl.contained", "gpu.ovl.contained"):
+            if os.path.exists(tmp_path / f):
+                os.remove(tmp_path / f)
+        _run(_checker(oracle_bin), fa, str(tmp_path / "ref.ovl"), base + extra)
+        _run(EXE, fa, str(tmp_path / "gpu.ovl"), base + extra)
+        assert open(tmp_path / "ref.ovl", "rb").read() == open(tmp_path / "gpu.ovl", "rb").read(), extra
+        assert os.path.exists(tmp_path / "ref.ovl.contained") == os.path.exists(tmp_path / "gpu.ovl.contained"), extra
+        if os.path.exists(tmp_path / "ref.ovl.contained"):
+            assert open(tmp_path / "ref.ovl.contained", "rb").read() == open(tmp_path / "gpu.ovl.contained", "rb").read(), extra
+        assert sorted(open(tmp_path / "ref.ovl.pairs").read().split("\n")) == sorted(open(tmp_path / "gpu.ovl.pairs").read().split("\n")), extra
+
+
+def test_edge_reads(tmp_path, oracle_bin):
+    """reads shorter than k / z, equal-length reads (sort ties), multi-line FASTA with header comments, FASTQ input"""
+    import random
+    random.seed(5)
+    g = "".join(random.choice("ACGT") for _ in range(30000))
+
+    def mut(s):
+        o = []
+        for ch in s:
+            r = random.random()
+            if r < 0.05:
+                continue
+            o.append(random.choice("ACGT") if r < 0.08 else ch)
+            if random.random() < 0.06:
+                o.append(random.choice("ACGT"))
+        return "".join(o)
+    recs = []
+    for i in range(150):
+        st = random.randrange(0, 27000)
+        s = mut(g[st:st + 3000])[:random.choice([2000, 2500, 2500, 2500, 3000])]
+        if random.random() < 0.5:
+            s = s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+        recs.append(s)
+    for L in (3, 9, 10, 15, 16, 17, 40):
+        recs.append(g[100:100 + L])
+    fa = tmp_path / "ties.fa"
+    with open(fa, "w") as f:
+        for n, s in enumerate(recs):
+            f.write(">t%d some comment\n" % n)
+            for k in range(0, len(s), 70):
+                f.write(s[k:k + 70] + "\n")
+    fq = tmp_path / "ties.fq"
+    with open(fq, "w") as f:
+        for n, s in enumerate(recs):
+            f.write("@t%d x\n%s\n+\n%s\n" % (n, s, "I" * len(s)))
+    extra = ["-k", "16", "-s", "100", "-m", "0.5", "-r", "200", "-R", "100", "-d", "100"]
+    for src in (fa, fq):
+        _run(_checker(oracle_bin), str(src), str(tmp_path / "ref.ovl"), extra)
+        _run(EXE, str(src), str(tmp_path / "gpu.ovl"), extra)
+        ref = open(tmp_path / "ref.ovl", "rb").read()
+        assert ref == open(tmp_path / "gpu.ovl", "rb").read() and ref.count(b"\n") > 200
+        assert open(tmp_path / "ref.ovl.contained", "rb").read() == open(tmp_path / "gpu.ovl.contained", "rb").read()

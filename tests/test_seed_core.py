@@ -85,12 +85,29 @@ def test_device_seed_core_matches_oracle(oracle_lib, sim_lib):
         assert run_pw(oracle_lib, "orc_pair_windows", x, y) == run_pw(sim_lib, "sim_pair_windows", x, y)
 
 
+def run_dot(lib, name, a, b, zcut=16, xvar=128, yvar=64, mbl=160, dev=1.0, gap=0.05):
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    out = (C.c_int * 6)()
+    n = getattr(lib, name)(a.ctypes.data_as(C.c_void_p), len(a), b.ctypes.data_as(C.c_void_p), len(b), 10, 1, zcut, 2, xvar, yvar, mbl, 2 * xvar,
+                           C.c_float(dev), C.c_float(gap), out)
+    return n, list(out)
+
+
+def test_device_dot_core_matches_oracle(oracle_lib, sim_lib):
+    hits = 0
+    for a, b in pairs(400, 60):
+        exp = run_dot(oracle_lib, "orc_pair_dotmatrix", a, b)
+        assert exp == run_dot(sim_lib, "sim_pair_dotmatrix", a, b)
+        hits += exp[1][0] > 0
+    assert hits > 15
+    for a, b in pairs(401, 10):
+        kw = dict(zcut=64, xvar=256, yvar=32, mbl=300, dev=0.1, gap=0.01)
+        assert run_dot(oracle_lib, "orc_pair_dotmatrix", a, b, **kw) == run_dot(sim_lib, "sim_pair_dotmatrix", a, b, **kw)
+
+
 def test_dotmatrix_oracle_matches_reference(ref_lib, oracle_lib):
-    def run(lib, name, a, b):
-        out = (C.c_int * 6)()
-        n = getattr(lib, name)(a.ctypes.data_as(C.c_void_p), len(a), b.ctypes.data_as(C.c_void_p), len(b), 10, 1, 16, 2, 128, 64, 160, 256,
-                               C.c_float(1.0), C.c_float(0.05), out)
-        return n, list(out)
+    run = run_dot
     hits = 0
     for a, b in pairs(300, 40):
         a = np.ascontiguousarray(a)
