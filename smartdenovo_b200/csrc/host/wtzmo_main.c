@@ -719,15 +719,26 @@ static int usage(void){
 	return 1;
 }
 
-int main(int argc, char **argv){
-	wz_t Z, *z = &Z; zparams_t *par = &Z.par; int c, device = 0; float optval; zmo_params_t zp;
-	char *output = NULL, *pairoutf = NULL, *env; double t_start = now_s(), t_ovl0, t_ovl1;
-	VEC(char*) pbs, flts, ovls, obts, tbas; u32 i;
-	memset(z, 0, sizeof(*z)); zparams_default(par);
+/* ------------------------------------------------------------------ session API (used by main() and, through ctypes, by bench.py)
+ * wz_open   parse the wtzmo command line, load + sort reads, side inputs, create the device context
+ * wz_upload pack-upload the reads to the device (zmo_reads_upload)
+ * wz_run    one complete overlap job `-P n_job -p i_job` from a clean state (index build included), .ovl to out_path
+ * wz_stats  numbers of the last wz_run */
+typedef struct {
+	wz_t z; char *output, *pairoutf; int device, uploaded; u8 *masked0; u64v closed0;
+	double t_open, last_overlap_s, last_upload_s; u64 upload_bytes;
+} wz_session_t;
+
+wz_session_t* wz_open(int argc, char **argv, int *rc_out){
+	wz_session_t *S = calloc(1, sizeof(wz_session_t)); wz_t *z = &S->z; zparams_t *par = &z->par; int c; float optval; zmo_params_t zp;
+	char *env; double t_start = now_s();
+	VEC(char*) pbs, flts, ovls, obts, tbas; u32 i; size_t k;
+	zparams_default(par);
 	vec_init(pbs); vec_init(flts); vec_init(ovls); vec_init(obts); vec_init(tbas);
+	*rc_out = 0; optind = 1;
 	while((c = getopt(argc, argv, "ht:P:p:Ni:b:J:I:o:9:S:fCH:k:G:z:Z:U:y:d:r:q:l:K:A:B:r:R:L:F:W:w:e:M:X:O:E:T:s:m:nv")) != -1){
 		switch(c){
-			case 'h': return usage();
+			case 'h': *rc_out = usage(); return NULL;
 			case 't': par->ncpu = atoi(optarg); break;
 			case 'P': par->n_job = atoi(optarg); break;
 			case 'p': par->i_job = atoi(optarg); break;
@@ -736,8 +747,8 @@ int main(int argc, char **argv){
 			case 'b': vec_push(obts, optarg); break;
 			case 'J': par->min_rdlen = atoi(optarg); break;
 			case 'I': vec_push(tbas, optarg); break;
-			case 'o': output = optarg; break;
-			case '9': pairoutf = optarg; break;
+			case 'o': S->output = optarg; break;
+			case '9': S->pairoutf = optarg; break;
 			case 'S': par->ksave = atoi(optarg); break;
 			case 'f': par->overwrite = 1; break;
 			case 'C': par->write_contained = 0; break;   /* -C never reaches wt->skip_contained (wtzmo.c:168,1609,1781) */
@@ -781,20 +792,17 @@ int main(int argc, char **argv){
 			case 'm': par->min_id = atof(optarg); break;
 			case 'n': par->refine = 1; break;
 			case 'v': par->debug ++; break;
-			default: return usage();
+			default: *rc_out = usage(); return NULL;
 		}
 	}
-	if(output == NULL) return usage();
-	if(!par->overwrite && strcmp(output, "-") && file_exists(output)){ fprintf(stderr, "File exists! '%s'\n\n", output); return usage(); }
-	if(pbs.n == 0) return usage();
-	if(par->ksize > 32 || par->ksize < 5) return usage();
-	if(par->zsize > 16 || par->zsize < 5) return usage();
-	if(par->ksave < 1) return usage();
-	if(par->refine){ fprintf(stderr, "wtzmo(b200): -n (kswx_refine_alignment) is not available in this build\n"); return 2; }
-	if(par->n_job < 1 || par->n_idx < 1){ fprintf(stderr, "wtzmo(b200): -P and -G must be >= 1\n"); return 2; }
+	if(S->output == NULL){ *rc_out = usage(); return NULL; }
+	if(!par->overwrite && strcmp(S->output, "-") && file_exists(S->output)){ fprintf(stderr, "File exists! '%s'\n\n", S->output); *rc_out = usage(); return NULL; }
+	if(pbs.n == 0 || par->ksize > 32 || par->ksize < 5 || par->zsize > 16 || par->zsize < 5 || par->ksave < 1){ *rc_out = usage(); return NULL; }
+	if(par->refine){ fprintf(stderr, "wtzmo(b200): -n (kswx_refine_alignment) is not available in this build\n"); *rc_out = 2; return NULL; }
+	if(par->n_job < 1 || par->n_idx < 1){ fprintf(stderr, "wtzmo(b200): -P and -G must be >= 1\n"); *rc_out = 2; return NULL; }
 	par->max_overhang = 2 * par->xvar;
 	par->kstep = par->kwin / 2;
-	if((env = getenv("ZMO_DEVICE"))) device = atoi(env); else if((env = getenv("LOCAL_RANK"))) device = atoi(env);
+	if((env = getenv("ZMO_DEVICE"))) S->device = atoi(env); else if((env = getenv("LOCAL_RANK"))) S->device = atoi(env);
 	z->batch_reads = (env = getenv("ZMO_BATCH_READS"))? atoi(env) : 256;
 	z->batch_pairs = (env = getenv("ZMO_BATCH_PAIRS"))? atoi(env) : 16384;
 	if(z->batch_reads < 1) z->batch_reads = 1;
@@ -803,7 +811,7 @@ int main(int argc, char **argv){
 	ref_sort(z->rs.reads.a, z->rs.reads.n, sizeof(read_t), gt_read_len_desc, NULL);      /* wtzmo.c:1708 */
 	if(tbas.n) rs_load(&z->rs, tbas.a, (int)tbas.n, par->min_rdlen, 1);
 	fprintf(stderr, "[wtzmo-b200] Done, %u reads (+%u query-only), %.3f s\n", z->rs.n_rd, z->rs.n_qr, now_s() - t_start);
-	if(z->rs.n_rd == 0){ fprintf(stderr, "wtzmo(b200): no reads\n"); return 1; }
+	if(z->rs.n_rd == 0){ fprintf(stderr, "wtzmo(b200): no reads\n"); *rc_out = 1; return NULL; }
 	z->masked = calloc(z->rs.n_rd + z->rs.n_qr + 1, 1);
 	z->rdcovs = calloc(z->rs.n_rd + z->rs.n_qr + 1, sizeof(u32));
 	u64set_init(&z->closed);
@@ -849,38 +857,86 @@ int main(int argc, char **argv){
 		}
 		free(line);
 	}
-	/* device context + read upload */
+	/* remember the initial state so that wz_run can start every job from it */
+	S->masked0 = malloc(z->rs.n_rd + z->rs.n_qr + 1); memcpy(S->masked0, z->masked, z->rs.n_rd + z->rs.n_qr + 1);
+	vec_init(S->closed0);
+	for(k=0;k<z->closed.cap;k++) if(z->closed.tab[k] != ~0ULL) vec_push(S->closed0, z->closed.tab[k]);
 	memset(&zp, 0, sizeof(zp));
 	zp.hk = par->hk; zp.hz = par->hz; zp.ksize = par->ksize; zp.zsize = par->zsize; zp.ksave = par->ksave; zp.kovl = par->kovl; zp.zcut = par->zcut; zp.kvar = par->kvar;
 	zp.kwin = par->kwin; zp.kstep = par->kstep; zp.zovl = par->zovl; zp.ztot = par->ztot; zp.w = par->w; zp.ew = par->ew; zp.W = par->W;
 	zp.M = par->M; zp.X = par->X; zp.O = par->O; zp.E = par->E; zp.T = par->T; zp.min_id = par->min_id;
 	zp.xvar = par->xvar; zp.yvar = par->yvar; zp.min_block_len = par->min_block_len; zp.max_overhang = par->max_overhang; zp.deviation_penalty = par->deviation_penalty; zp.gap_penalty = par->gap_penalty;
-	if(zmo_ctx_create(&z->ctx, device, &zp)) die_zmo("zmo_ctx_create");
-	{
-		u32 n = z->rs.n_rd + z->rs.n_qr; u64 *off = malloc((size_t)n * 8); u32 *len = malloc((size_t)n * 4);
-		for(i=0;i<n;i++){ off[i] = z->rs.reads.a[i].off; len[i] = z->rs.reads.a[i].len; }
-		if(zmo_reads_upload(z->ctx, z->rs.bits, z->rs.nbases, off, len, n)) die_zmo("zmo_reads_upload");
-		free(off); free(len);
-	}
-	z->out = strcmp(output, "-")? fopen(output, "w") : stdout;
-	if(z->out == NULL){ fprintf(stderr, "wtzmo(b200): cannot open %s\n", output); return 1; }
-	z->obuf_cap = 8u << 20; z->obuf = malloc(z->obuf_cap);
-	fprintf(stderr, "[wtzmo-b200] calculating overlaps on GPU %d\n", device);
-	t_ovl0 = now_s();
+	if(zmo_ctx_create(&z->ctx, S->device, &zp)){ fprintf(stderr, "wtzmo(b200): zmo_ctx_create: %s\n", zmo_last_error()); *rc_out = 3; return NULL; }
+	S->t_open = now_s() - t_start;
+	vec_free(pbs); vec_free(flts); vec_free(ovls); vec_free(obts); vec_free(tbas);
+	return S;
+}
+
+int wz_upload(wz_session_t *S){
+	wz_t *z = &S->z; u32 i, n = z->rs.n_rd + z->rs.n_qr; u64 *off = malloc((size_t)n * 8); u32 *len = malloc((size_t)n * 4); double t0 = now_s(); int rc;
+	for(i=0;i<n;i++){ off[i] = z->rs.reads.a[i].off; len[i] = z->rs.reads.a[i].len; }
+	rc = zmo_reads_upload(z->ctx, z->rs.bits, z->rs.nbases, off, len, n);
+	free(off); free(len);
+	if(rc){ fprintf(stderr, "wtzmo(b200): zmo_reads_upload: %s\n", zmo_last_error()); return 3; }
+	S->uploaded = 1; S->last_upload_s = now_s() - t0; S->upload_bytes = ((z->rs.nbases + 31) / 32) * 8 + (u64)n * 12;
+	return 0;
+}
+
+int wz_run(wz_session_t *S, int n_job, int i_job, const char *out_path){
+	wz_t *z = &S->z; size_t k, n = z->rs.n_rd + z->rs.n_qr; double t0;
+	if(!S->uploaded){ int rc = wz_upload(S); if(rc) return rc; }
+	if(n_job < 1 || i_job < 0 || i_job >= n_job) return 2;
+	z->par.n_job = n_job; z->par.i_job = i_job;
+	memcpy(z->masked, S->masked0, n + 1); memset(z->rdcovs, 0, (n + 1) * sizeof(u32));
+	free(z->closed.tab); u64set_init(&z->closed);
+	for(k=0;k<S->closed0.n;k++) u64set_add(&z->closed, S->closed0.a[k]);
+	if(z->rdhits){ for(k=0;k<n;k++) vec_free(z->rdhits[k]); free(z->rdhits); z->rdhits = NULL; }
+	z->n_records = z->aln_cols = z->n_tasks = z->n_tasks_used = z->n_pairs_seeded = z->n_batches = 0; z->t_dev = z->t_replay = 0;
+	z->out = strcmp(out_path, "-")? fopen(out_path, "w") : stdout;
+	if(z->out == NULL){ fprintf(stderr, "wtzmo(b200): cannot open %s\n", out_path); return 1; }
+	if(z->obuf == NULL){ z->obuf_cap = 8u << 20; z->obuf = malloc(z->obuf_cap); }
+	t0 = now_s();
 	run_overlap(z);
-	if(strcmp(output, "-")) fclose(z->out); else fflush(stdout);
-	t_ovl1 = now_s();
+	if(strcmp(out_path, "-")) fclose(z->out); else fflush(stdout);
+	S->last_overlap_s = now_s() - t0;
+	return 0;
+}
+
+/* out[0]=records [1]=aligned columns [2]=overlap wall s [3]=device-call s [4]=replay+format s [5]=batches [6]=pairs seeded
+ * [7]=tasks aligned [8]=tasks consumed [9]=kernel launches (cumulative) [10..17]=stage ms (cumulative) [18..24]=counters (cumulative)
+ * [25]=reads [26]=bases [27]=last upload s [28]=upload bytes */
+void wz_stats(wz_session_t *S, double *out){
+	wz_t *z = &S->z; double ms[8]; uint64_t ct[8]; int i;
+	zmo_stage_ms(z->ctx, ms); zmo_counters(z->ctx, ct);
+	out[0] = (double)z->n_records; out[1] = (double)z->aln_cols; out[2] = S->last_overlap_s; out[3] = z->t_dev; out[4] = z->t_replay; out[5] = (double)z->n_batches;
+	out[6] = (double)z->n_pairs_seeded; out[7] = (double)z->n_tasks; out[8] = (double)z->n_tasks_used; out[9] = (double)zmo_kernel_launches(z->ctx);
+	for(i=0;i<8;i++) out[10 + i] = ms[i];
+	for(i=0;i<7;i++) out[18 + i] = (double)ct[i];
+	out[25] = (double)(z->rs.n_rd + z->rs.n_qr); out[26] = (double)z->rs.nbases; out[27] = S->last_upload_s; out[28] = (double)S->upload_bytes;
+}
+
+void wz_close(wz_session_t *S){ if(S){ if(S->z.ctx) zmo_ctx_destroy(S->z.ctx); free(S); } }
+
+#ifndef WTZMO_LIB
+int main(int argc, char **argv){
+	int rc = 0; double t_start = now_s(); char *env; u32 i;
+	wz_session_t *S = wz_open(argc, argv, &rc); wz_t *z;
+	if(S == NULL) return rc;
+	z = &S->z;
+	if((rc = wz_upload(S))) return rc;
+	fprintf(stderr, "[wtzmo-b200] calculating overlaps on GPU %d\n", S->device);
+	if((rc = wz_run(S, z->par.n_job, z->par.i_job, S->output))) return rc;
 	fprintf(stderr, "[wtzmo-b200] Done, %llu records, %llu aligned columns, %.3f s (device calls %.3f s, replay+format %.3f s, %llu batches, %llu pairs seeded, %llu aligned, %llu consumed)\n",
-		(unsigned long long)z->n_records, (unsigned long long)z->aln_cols, t_ovl1 - t_ovl0, z->t_dev, z->t_replay, (unsigned long long)z->n_batches,
+		(unsigned long long)z->n_records, (unsigned long long)z->aln_cols, S->last_overlap_s, z->t_dev, z->t_replay, (unsigned long long)z->n_batches,
 		(unsigned long long)z->n_pairs_seeded, (unsigned long long)z->n_tasks, (unsigned long long)z->n_tasks_used);
-	if(par->write_contained && strcmp(output, "-")){
-		char *maskf = malloc(strlen(output) + 16); FILE *mf;
-		sprintf(maskf, "%s.contained", output); mf = fopen(maskf, "w");
+	if(z->par.write_contained && strcmp(S->output, "-")){
+		char *maskf = malloc(strlen(S->output) + 16); FILE *mf;
+		sprintf(maskf, "%s.contained", S->output); mf = fopen(maskf, "w");
 		for(i=0;i<z->rs.n_rd;i++) if(z->masked[i]) fprintf(mf, "%s\n", z->rs.reads.a[i].name);
 		fclose(mf); free(maskf);
 	}
-	if(pairoutf){
-		FILE *pf = fopen(pairoutf, "w"); size_t k;
+	if(S->pairoutf){
+		FILE *pf = fopen(S->pairoutf, "w"); size_t k;
 		for(k=0;k<z->closed.cap;k++){
 			u64 v = z->closed.tab[k];
 			if(v == ~0ULL) continue;
@@ -889,19 +945,20 @@ int main(int argc, char **argv){
 		fclose(pf);
 	}
 	if((env = getenv("ZMO_STATS"))){
-		FILE *sf = fopen(env, "w"); double ms[8]; uint64_t ct[8];
-		zmo_stage_ms(z->ctx, ms); zmo_counters(z->ctx, ct);
+		FILE *sf = fopen(env, "w"); double st[32]; const char *nm[8] = {"index", "candidates", "pair_windows", "window_align", "gap_global", "end_extend", "dotmatrix", "copy"};
+		const char *cn[7] = {"cells_ext", "cells_win", "cells_gap", "zpairs", "postings", "h2d_bytes", "d2h_bytes"}; int k;
+		wz_stats(S, st);
 		if(sf){
-			fprintf(sf, "{\"records\": %llu, \"aligned_cols\": %llu, \"overlap_s\": %.6f, \"total_s\": %.6f, \"device_call_s\": %.6f, \"replay_s\": %.6f, \"batches\": %llu, \"pairs_seeded\": %llu, \"tasks\": %llu, \"tasks_used\": %llu, \"launches\": %llu,",
-				(unsigned long long)z->n_records, (unsigned long long)z->aln_cols, t_ovl1 - t_ovl0, now_s() - t_start, z->t_dev, z->t_replay, (unsigned long long)z->n_batches,
-				(unsigned long long)z->n_pairs_seeded, (unsigned long long)z->n_tasks, (unsigned long long)z->n_tasks_used, (unsigned long long)zmo_kernel_launches(z->ctx));
-			fprintf(sf, " \"stage_ms\": {\"index\": %.3f, \"candidates\": %.3f, \"pair_windows\": %.3f, \"window_align\": %.3f, \"gap_global\": %.3f, \"end_extend\": %.3f, \"dotmatrix\": %.3f, \"copy\": %.3f},", ms[0], ms[1], ms[2], ms[3], ms[4], ms[5], ms[6], ms[7]);
-			fprintf(sf, " \"counters\": {\"cells_ext\": %llu, \"cells_win\": %llu, \"cells_gap\": %llu, \"zpairs\": %llu, \"postings\": %llu, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu},",
-				(unsigned long long)ct[0], (unsigned long long)ct[1], (unsigned long long)ct[2], (unsigned long long)ct[3], (unsigned long long)ct[4], (unsigned long long)ct[5], (unsigned long long)ct[6]);
-			fprintf(sf, " \"n_reads\": %u, \"n_bases\": %llu}\n", z->rs.n_rd + z->rs.n_qr, (unsigned long long)z->rs.nbases);
+			fprintf(sf, "{\"records\": %.0f, \"aligned_cols\": %.0f, \"overlap_s\": %.6f, \"total_s\": %.6f, \"device_call_s\": %.6f, \"replay_s\": %.6f, \"batches\": %.0f, \"pairs_seeded\": %.0f, \"tasks\": %.0f, \"tasks_used\": %.0f, \"launches\": %.0f, \"stage_ms\": {",
+				st[0], st[1], st[2], now_s() - t_start, st[3], st[4], st[5], st[6], st[7], st[8], st[9]);
+			for(k=0;k<8;k++) fprintf(sf, "%s\"%s\": %.3f", k? ", " : "", nm[k], st[10 + k]);
+			fprintf(sf, "}, \"counters\": {");
+			for(k=0;k<7;k++) fprintf(sf, "%s\"%s\": %.0f", k? ", " : "", cn[k], st[18 + k]);
+			fprintf(sf, "}, \"n_reads\": %.0f, \"n_bases\": %.0f}\n", st[25], st[26]);
 			fclose(sf);
 		}
 	}
-	zmo_ctx_destroy(z->ctx);
+	wz_close(S);
 	return 0;
 }
+#endif

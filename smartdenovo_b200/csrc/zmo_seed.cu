@@ -72,7 +72,7 @@ __global__ void k_p_match(DevReads R, ZIdxView Z, const uint32_t *pq, const uint
 }
 
 struct SeedOut { DevWin *wins; DevZPair *anc; unsigned long long cap_wins, cap_anc; unsigned long long *cur_wins, *cur_anc, *overflow; };
-__global__ void k_p_seed(const unsigned long long *cache_off, uint32_t np, DevZPair *cache, uint8_t *scratch, size_t per, SeedPar par, SeedOut O, zmo_pairseed_t *seeds){
+__global__ void k_p_seed(const unsigned long long *cache_off, uint32_t np, DevZPair *cache, uint8_t *scratch, size_t per, uint32_t F, SeedPar par, SeedOut O, zmo_pairseed_t *seeds){
 	uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	if(p >= np) return;
 	const unsigned long long c0 = cache_off[p]; const uint32_t n = (uint32_t)(cache_off[p + 1] - c0);
@@ -82,7 +82,7 @@ __global__ void k_p_seed(const unsigned long long *cache_off, uint32_t np, DevZP
 		zmo_ref_sort(rs, (size_t)n, GtZPairOff12());
 		uint8_t *scr = scratch + c0 * per + (size_t)64 * p;
 		for(int d = 0; d < 2; d++){
-			PairScratch P = zmo_pair_scratch_carve(scr, n); uint32_t nwin = 0; int ovf = 0;
+			PairScratch P = zmo_pair_scratch_carve(scr, n, F); uint32_t nwin = 0; int ovf = 0;
 			const int ovl = zmo_pair_seed_strand(rs, n, d, par, P, &nwin, &ovf);
 			if(ovf){ atomicAdd(O.overflow, 1ULL); break; }
 			S.ovl[d] = ovl;
@@ -195,25 +195,24 @@ extern "C" int zmo_pair_windows(zmo_ctx *c, int slot, const zmo_pair_t *pairs, u
 	if(np == 0) return 0;
 	CUDA_TRY(cudaSetDevice(c->device));
 	StageTimer tm(c, ST_SEED);
-	const size_t per = 5 * 4 + sizeof(DevWin) + sizeof(DevZPair);
 	SeedPar par; par.zsize = c->par.zsize; par.kwin = c->par.kwin; par.kstep = c->par.kstep; par.zovl = c->par.zovl; par.ztot = c->par.ztot; par.W = c->par.W;
 	unsigned long long *ctr = c->d_ctr.as<unsigned long long>();
 	unsigned long long nw = 0, na = 0;
-	for(int attempt = 0; attempt < 2; attempt++){
-		SeedWork W;
+	for(int attempt = 0; attempt < 4; attempt++){
+		SeedWork W; const uint32_t F = 2u << (2 * attempt); const size_t per = zmo_pair_scratch_per(F);     /* 2, 8, 32, 128 */
 		if(int rc = seed_prepare(c, pairs, np, W, c->s5)) return rc;      /* match lists live in s5 */
 		const unsigned long long T = W.T;
-		const unsigned long long cap_w = attempt? 2 * T + 64 : T / 2 + 64, cap_a = 2 * T + 64;
+		const unsigned long long cap_w = (attempt? 2 * T * F : T / 2) + 64, cap_a = 2 * T * F + 64;
 		if(c->s3.reserve(T * per + (size_t)64 * np + 256) || SL.wins.reserve(cap_w * sizeof(DevWin)) || SL.anchors.reserve(cap_a * sizeof(DevZPair)) || SL.seeds.reserve((size_t)np * sizeof(zmo_pairseed_t)) || SL.pairs.reserve((size_t)np * sizeof(zmo_pair_t))) return ZMO_ERR_CUDA;
 		CUDA_TRY(cudaMemsetAsync(ctr + CTR_N1, 0, 24, c->stream));
 		SeedOut O; O.wins = SL.wins.as<DevWin>(); O.anc = SL.anchors.as<DevZPair>(); O.cap_wins = cap_w; O.cap_anc = cap_a; O.cur_wins = ctr + CTR_N1; O.cur_anc = ctr + CTR_N2; O.overflow = ctr + CTR_N3;
-		k_p_seed<<<(np + 31) / 32, 32, 0, c->stream>>>(W.cache_off, np, W.cache, c->s3.as<uint8_t>(), per, par, O, SL.seeds.as<zmo_pairseed_t>()); c->launches++;
+		k_p_seed<<<(np + 31) / 32, 32, 0, c->stream>>>(W.cache_off, np, W.cache, c->s3.as<uint8_t>(), per, F, par, O, SL.seeds.as<zmo_pairseed_t>()); c->launches++;
 		CUDA_TRY(cudaGetLastError());
 		unsigned long long h[3];
 		CUDA_TRY(cudaMemcpyAsync(h, ctr + CTR_N1, 24, cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
 		if(h[2] == 0){ nw = h[0]; na = h[1]; break; }
-		if(attempt) return zmo_set_err(ZMO_ERR_CAPACITY, "window arena overflow");
+		if(attempt == 3) return zmo_set_err(ZMO_ERR_CAPACITY, "window arena overflow");
 	}
 	if(win_needed) *win_needed = nw;
 	if(nw > win_cap) return zmo_set_err(ZMO_ERR_CAPACITY, "window buffer too small: need %llu", nw);

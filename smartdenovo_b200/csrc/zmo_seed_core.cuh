@@ -319,17 +319,20 @@ ZMO_HDN int zmo_chain_windows(DevWin *w, uint32_t n, int W, int *nodes){
  * call the strand's windows (with closed flags set by the chain) are in S.w2[0..nwin) and their
  * anchors in S.a2; the caller copies the kept ones out. */
 struct PairScratch { WinScratch ws; DevWin *w2; DevZPair *a2; uint32_t cap; };
-ZMO_HD size_t zmo_pair_scratch_bytes(uint32_t n){ return (size_t)n * (5 * 4 + sizeof(DevWin) + sizeof(DevZPair)) + 64; }
-ZMO_HD PairScratch zmo_pair_scratch_carve(uint8_t *base, uint32_t n){
+/* F = capacity factor for windows/anchors (an anchor can belong to several overlapping sub-windows,
+ * hzm_aln.h:483-514, so the anchor list of a strand may exceed the match count) */
+ZMO_HD size_t zmo_pair_scratch_per(uint32_t F){ return 5 * 4 + (size_t)F * (sizeof(DevWin) + sizeof(DevZPair)); }
+ZMO_HD size_t zmo_pair_scratch_bytes(uint32_t n, uint32_t F){ return (size_t)n * zmo_pair_scratch_per(F) + 64; }
+ZMO_HD PairScratch zmo_pair_scratch_carve(uint8_t *base, uint32_t n, uint32_t F){
 	PairScratch P; uint8_t *p = base;
-	P.a2 = (DevZPair*)p; p += (size_t)n * sizeof(DevZPair);
-	P.w2 = (DevWin*)p; p += (size_t)n * sizeof(DevWin);
+	P.a2 = (DevZPair*)p; p += (size_t)n * F * sizeof(DevZPair);
+	P.w2 = (DevWin*)p; p += (size_t)n * F * sizeof(DevWin);
 	P.ws.ts = (uint32_t*)p; p += (size_t)n * 4;
 	P.ws.as = (int32_t*)p; p += (size_t)n * 4;
 	P.ws.wb = (uint32_t*)p; p += (size_t)n * 4;
 	P.ws.we = (uint32_t*)p; p += (size_t)n * 4;
 	P.ws.wo = (uint32_t*)p;
-	P.cap = n;
+	P.cap = n * F;
 	return P;
 }
 /* returns the chain weight (0 when the strand has no window); nwin/nanc = all windows found */

@@ -38,9 +38,9 @@ extern "C" int sim_pair_windows(const uint8_t *pb1, int alen, const uint8_t *pb2
 	if(n * (uint32_t)zsize >= (uint32_t)ztot){
 		SeedPar par; par.zsize = zsize; par.kwin = kwin; par.kstep = kstep; par.zovl = zovl; par.ztot = ztot; par.W = W;
 		zmo_ref_sort(cache.data(), (size_t)n, GtZPairOff12());
-		std::vector<uint8_t> scr(zmo_pair_scratch_bytes(n));
+		std::vector<uint8_t> scr(zmo_pair_scratch_bytes(n, 8));
 		for(int d = 0; d < 2; d++){
-			PairScratch P = zmo_pair_scratch_carve(scr.data(), n); uint32_t nwin = 0; int ovf = 0;
+			PairScratch P = zmo_pair_scratch_carve(scr.data(), n, 8); uint32_t nwin = 0; int ovf = 0;
 			ovl[d] = zmo_pair_seed_strand(cache.data(), n, d, par, P, &nwin, &ovf);
 			if(ovf) return -1;
 			for(uint32_t j = 0; j < nwin; j++){
