@@ -269,7 +269,7 @@ def main():
             "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": r_e2e["h2d"], "d2h_bytes_per_step": r_e2e["d2h"], "ms_per_step": 1e3 * r_e2e["wall"] / args.steps},
             "gpu_launches": int(launches), "roofline": roof,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
-            "host_ms_per_step": {"device_calls": 1e3 * (st1[3]) , "replay_format": 1e3 * st1[4]},
+            "last_step_host_ms": {"device_calls": 1e3 * st1[3], "replay_format": 1e3 * st1[4]},
             "records_per_step": r_val["rec"] / args.steps, "aligned_bp_per_step": r_val["bp"] / args.steps}
     if world > 1:
         line["gathered_bytes"] = r_e2e["gathered"]
