@@ -148,28 +148,62 @@ __device__ __forceinline__ long long idx_find(const IdxView &I, unsigned long lo
 	while(lo < hi){ unsigned long long mid = (lo + hi) >> 1; if(I.mer[mid] < mer) lo = mid + 1; else hi = mid; }
 	return (lo < I.n && I.mer[lo] == mer)? (long long)lo : -1;
 }
-/* PASS 0 counts, PASS 1 fills.  key = qlocal<<32 | tkey ; val = off<<16 | len */
-template<int PASS>
-__global__ void k_cand_scan(DevReads R, IdxView I, const uint32_t *qids, uint32_t nq, int ksize, int hk, uint32_t ksave,
-		unsigned long long *cnt_or_off, unsigned long long *keys, unsigned long long *vals){
+/* Candidate query, parallel form: (1) chunk-parallel hp-k-mer scan of the query reads (one thread per
+ * 128-base chunk) emits the sampled k-mers in (query, position) order; (2) one thread per k-mer looks it up
+ * in the index and counts the postings that survive the self / length filters (wtzmo.c:488-489,509-510);
+ * (3) one thread per k-mer writes its tuples key = qlocal<<32 | tkey, val = off<<16 | len at the scanned
+ * offset, so tuples of one query stay in ascending query-offset order for the stable sort. */
+#define SCAN_CH 128
+__global__ void k_q_nchunks(DevReads R, const uint32_t *qids, uint32_t nq, unsigned long long *nch){
 	uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-	if(q >= nq) return;
-	const uint32_t qid = qids[q], qlen = R.len[qid], up = (uint32_t)((double)qlen * 1.2);
-	unsigned long long n = PASS? cnt_or_off[q] : 0;
-	zmo_scan_kmers(R.words + R.woff[qid], qlen, ksize, hk, [&](uint64_t mer, uint32_t, uint32_t off, uint32_t ln){
+	if(q < nq) nch[q] = (R.len[qids[q]] + SCAN_CH - 1) / SCAN_CH;
+}
+template<int PASS>
+__global__ void k_qk_scan(DevReads R, const uint32_t *qids, uint32_t nq, const unsigned long long *choff, unsigned long long NC, int ksize, int hk, uint32_t ksave,
+		unsigned long long *cnt_or_off, unsigned long long *km_mer, unsigned long long *km_info){
+	unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if(c >= NC) return;
+	uint32_t lo = 0, hi = nq;
+	while(lo + 1 < hi){ uint32_t mid = (lo + hi) >> 1; if(choff[mid] <= c) lo = mid; else hi = mid; }
+	const uint32_t q = lo, qid = qids[q], s = (uint32_t)(c - choff[q]) * SCAN_CH;
+	unsigned long long n = PASS? cnt_or_off[c] : 0;
+	zmo_scan_kmers_chunk(R.words + R.woff[qid], R.len[qid], ksize, hk, s, s + SCAN_CH, [&](uint64_t mer, uint32_t, uint32_t off, uint32_t ln){
 		if(!zmo_kmer_sampled(mer, ksave)) return;
-		const long long e = idx_find(I, mer);
-		if(e < 0 || I.flt[e]) return;
+		if(PASS){ km_mer[n] = mer; km_info[n] = ((unsigned long long)q << 48) | ((unsigned long long)off << 16) | ln; }
+		n++;
+	});
+	if(!PASS) cnt_or_off[c] = n;
+}
+#define ENT_NONE 0xFFFFFFFFu
+__global__ void k_qk_lookup(IdxView I, DevReads R, const uint32_t *qids, const unsigned long long *km_mer, const unsigned long long *km_info, unsigned long long NK, uint32_t *ent, unsigned long long *cnt){
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= NK) return;
+	const long long e = idx_find(I, km_mer[i]);
+	unsigned long long n = 0;
+	if(e >= 0 && !I.flt[e]){
+		const uint32_t qid = qids[(uint32_t)(km_info[i] >> 48)], up = (uint32_t)((double)R.len[qid] * 1.2);
 		const unsigned long long b0 = I.off[e], b1 = I.off[e + 1];
 		for(unsigned long long b = b0; b < b1; b++){
-			const uint32_t tk = I.post[b], tid = tk >> 1;
-			if(tid == qid) continue;
-			if(R.len[tid] > up) continue;
-			if(PASS){ keys[n] = ((unsigned long long)q << 32) | tk; vals[n] = ((unsigned long long)off << 16) | ln; }
+			const uint32_t tid = I.post[b] >> 1;
+			if(tid == qid || R.len[tid] > up) continue;
 			n++;
 		}
-	});
-	if(!PASS) cnt_or_off[q] = n;
+		ent[i] = (uint32_t)e;
+	} else ent[i] = ENT_NONE;
+	cnt[i] = n;
+}
+__global__ void k_qk_expand(IdxView I, DevReads R, const uint32_t *qids, const unsigned long long *km_info, const uint32_t *ent, const unsigned long long *toff, unsigned long long NK,
+		unsigned long long *keys, unsigned long long *vals){
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= NK || ent[i] == ENT_NONE) return;
+	const unsigned long long info = km_info[i]; const uint32_t q = (uint32_t)(info >> 48), qid = qids[q], up = (uint32_t)((double)R.len[qid] * 1.2);
+	const unsigned long long val = info & 0xFFFFFFFFFFFFull;       /* off<<16 | len */
+	unsigned long long n = toff[i]; const unsigned long long b0 = I.off[ent[i]], b1 = I.off[ent[i] + 1];
+	for(unsigned long long b = b0; b < b1; b++){
+		const uint32_t tk = I.post[b], tid = tk >> 1;
+		if(tid == qid || R.len[tid] > up) continue;
+		keys[n] = ((unsigned long long)q << 32) | tk; vals[n] = val; n++;
+	}
 }
 /* one thread per sorted tuple; group heads accumulate the union length of their group */
 __global__ void k_cand_union(const unsigned long long *keys, const unsigned long long *vals, unsigned long long n, uint32_t kovl, uint32_t *flag, uint32_t *ol_out){
@@ -209,26 +243,54 @@ extern "C" int zmo_candidates(zmo_ctx *c, const uint32_t *qids, uint32_t nq, uin
 	StageTimer tm(c, ST_CAND);
 	DevReads R = dev_reads(c);
 	IdxView I; I.mer = c->ix_mer.as<unsigned long long>(); I.off = c->ix_off.as<unsigned long long>(); I.flt = c->ix_flt.as<uint8_t>(); I.post = c->ix_post.as<uint32_t>(); I.n = c->n_ent;
+	if(nq > 65535) return zmo_set_err(ZMO_ERR_ARG, "at most 65535 query reads per zmo_candidates call");
 	if(c->s0.reserve((size_t)nq * 4) || c->s1.reserve(((size_t)nq + 2) * 8) || c->s2.reserve(((size_t)nq + 2) * 8)) return ZMO_ERR_CUDA;
-	uint32_t *d_q = c->s0.as<uint32_t>(); unsigned long long *d_cnt = c->s1.as<unsigned long long>(), *d_off = c->s2.as<unsigned long long>();
+	uint32_t *d_q = c->s0.as<uint32_t>(); unsigned long long *d_nch = c->s1.as<unsigned long long>(), *d_off = c->s2.as<unsigned long long>();
 	CUDA_TRY(cudaMemcpyAsync(d_q, qids, (size_t)nq * 4, cudaMemcpyHostToDevice, c->stream));
 	c->counters[5] += (uint64_t)nq * 4;
-	const int bs = 32;
-	k_cand_scan<0><<<(nq + bs - 1) / bs, bs, 0, c->stream>>>(R, I, d_q, nq, c->par.ksize, c->par.hk, (uint32_t)c->par.ksave, d_cnt, nullptr, nullptr); c->launches++;
-	CUDA_TRY(cudaMemsetAsync(d_cnt + nq, 0, 8, c->stream));
-	CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_cnt, d_off, nq + 1, c->stream));
-	unsigned long long N = 0;
-	CUDA_TRY(cudaMemcpyAsync(&N, d_off + nq, 8, cudaMemcpyDeviceToHost, c->stream));
+	/* chunk table */
+	k_q_nchunks<<<(nq + 127) / 128, 128, 0, c->stream>>>(R, d_q, nq, d_nch); c->launches++;
+	CUDA_TRY(cudaMemsetAsync(d_nch + nq, 0, 8, c->stream));
+	CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_nch, d_off, nq + 1, c->stream));
+	unsigned long long NC = 0;
+	CUDA_TRY(cudaMemcpyAsync(&NC, d_off + nq, 8, cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	/* sampled k-mers of the queries: count per chunk, scan, fill (s3: chunk counts | chunk offsets) */
+	if(c->s3.reserve((NC + 2) * 16)) return ZMO_ERR_CUDA;
+	unsigned long long *d_ccnt = c->s3.as<unsigned long long>(), *d_coff = d_ccnt + NC + 1;
+	k_qk_scan<0><<<(unsigned)((NC + 127) / 128), 128, 0, c->stream>>>(R, d_q, nq, d_off, NC, c->par.ksize, c->par.hk, (uint32_t)c->par.ksave, d_ccnt, nullptr, nullptr); c->launches++;
+	CUDA_TRY(cudaMemsetAsync(d_ccnt + NC, 0, 8, c->stream));
+	CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_ccnt, d_coff, (uint64_t)NC + 1, c->stream));
+	unsigned long long NK = 0;
+	CUDA_TRY(cudaMemcpyAsync(&NK, d_coff + NC, 8, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	unsigned long long N = 0;
+	unsigned long long *d_kmer = nullptr, *d_kinfo = nullptr, *d_kcnt = nullptr, *d_koff = nullptr; uint32_t *d_ent = nullptr;
+	if(NK){
+		/* s4: km_mer | km_info ; s5: per-k-mer counts | offsets ; s6: entries */
+		if(c->s4.reserve((NK + 2) * 16) || c->s5.reserve((NK + 2) * 16) || c->s6.reserve((NK + 2) * 4)) return ZMO_ERR_CUDA;
+		d_kmer = c->s4.as<unsigned long long>(); d_kinfo = d_kmer + NK + 1; d_kcnt = c->s5.as<unsigned long long>(); d_koff = d_kcnt + NK + 1; d_ent = c->s6.as<uint32_t>();
+		k_qk_scan<1><<<(unsigned)((NC + 127) / 128), 128, 0, c->stream>>>(R, d_q, nq, d_off, NC, c->par.ksize, c->par.hk, (uint32_t)c->par.ksave, d_coff, d_kmer, d_kinfo); c->launches++;
+		k_qk_lookup<<<(unsigned)((NK + 127) / 128), 128, 0, c->stream>>>(I, R, d_q, d_kmer, d_kinfo, NK, d_ent, d_kcnt); c->launches++;
+		CUDA_TRY(cudaMemsetAsync(d_kcnt + NK, 0, 8, c->stream));
+		CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_kcnt, d_koff, (uint64_t)NK + 1, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(&N, d_koff + NK, 8, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+	}
 	uint32_t nev = 0;
 	if(N){
 		if(N >= 0xFFFFFFFFull) return zmo_set_err(ZMO_ERR_CAPACITY, "candidate batch too large (%llu tuples); use a smaller query batch", N);
-		if(c->s3.reserve(N * 8) || c->s4.reserve(N * 8) || c->s5.reserve(N * 8) || c->s6.reserve(N * 8) || c->s7.reserve(N * 12 + 64)) return ZMO_ERR_CUDA;
-		unsigned long long *k_in = c->s3.as<unsigned long long>(), *k_out = c->s4.as<unsigned long long>(), *v_in = c->s5.as<unsigned long long>(), *v_out = c->s6.as<unsigned long long>();
-		k_cand_scan<1><<<(nq + bs - 1) / bs, bs, 0, c->stream>>>(R, I, d_q, nq, c->par.ksize, c->par.hk, (uint32_t)c->par.ksave, d_off, k_in, v_in); c->launches++;
+		/* tuple arrays: keys_in in s3 (the chunk tables there are dead); k_out | v_in | v_out | flag,ol,pos carved from
+		 * the DP arena, which is idle during the candidate stage */
+		if(c->s3.reserve(N * 8 + 64)) return ZMO_ERR_CUDA;
+		unsigned long long *k_in = c->s3.as<unsigned long long>();
+		DevBuf &bk = c->arena;
+		if(bk.reserve(N * (8 + 8 + 8 + 12) + 256)) return ZMO_ERR_CUDA;
+		unsigned long long *k_out = bk.as<unsigned long long>(), *v_in = k_out + N, *v_out = v_in + N;
+		uint32_t *d_flag = (uint32_t*)(v_out + N), *d_ol = d_flag + N, *d_pos = d_ol + N;
+		k_qk_expand<<<(unsigned)((NK + 127) / 128), 128, 0, c->stream>>>(I, R, d_q, d_kinfo, d_ent, d_koff, NK, k_in, v_in); c->launches++;
 		int qbits = 1; while((1ull << qbits) < nq) qbits++;
 		CUB_CALL(c, cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, k_in, k_out, v_in, v_out, (uint64_t)N, 0, 32 + qbits, c->stream));
-		uint32_t *d_flag = c->s7.as<uint32_t>(), *d_ol = d_flag + N, *d_pos = d_ol + N;
 		k_cand_union<<<(unsigned)((N + 255) / 256), 256, 0, c->stream>>>(k_out, v_out, N, (uint32_t)c->par.kovl, d_flag, d_ol); c->launches++;
 		CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_flag, d_pos, (uint64_t)N, c->stream));
 		uint32_t lastpos = 0, lastflag = 0;

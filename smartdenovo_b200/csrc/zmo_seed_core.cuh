@@ -68,6 +68,34 @@ template<class F> ZMO_HD void zmo_scan_kmers(const uint32_t *words, uint32_t len
 	}
 }
 
+/* Chunk-parallel form of zmo_scan_kmers: emits exactly the k-mers whose current (last) kept base lies in
+ * [s, e), so that disjoint chunks of one read can be scanned by independent threads.  The state at s
+ * is recovered by walking back until k-1 kept bases are collected (a base is kept iff it differs from
+ * its predecessor, which is a local rule). */
+template<class F> ZMO_HD void zmo_scan_kmers_chunk(const uint32_t *words, uint32_t len, int k, int hp, uint32_t s, uint32_t e, F f){
+	const uint64_t kmask = 0xFFFFFFFFFFFFFFFFULL >> ((32 - k) << 1);
+	uint64_t kmer = 0; uint32_t ring[32]; uint32_t kept = 0, b = 4, p = s; int need = k - 1;
+	if(e > len) e = len;
+	if(s >= e) return;
+	while(p > 0 && need > 0){
+		p--;
+		if(!hp || p == 0 || rd_base(words, p) != rd_base(words, p - 1)) need--;
+	}
+	/* p is a kept position (or 0), so starting with "no previous base" reproduces the global scan */
+	for(uint32_t j = p; j < e; j++){
+		const uint32_t c = rd_base(words, j);
+		if(hp && c == b) continue;
+		b = c; ring[kept & 31] = j; kept++;
+		kmer = ((kmer << 2) | b) & kmask;
+		if(j < s || kept < (uint32_t)k) continue;
+		const uint64_t krev = zmo_kmer_revcomp(kmer, k);
+		if(krev == kmer) continue;
+		const uint32_t off = ring[(kept - k) & 31];
+		const uint32_t ln = (j + 1 - off > 0xFFFFu)? 0xFFFFu : j + 1 - off;
+		f(krev > kmer? kmer : krev, (uint32_t)(krev > kmer? 0 : 1), off, ln);
+	}
+}
+
 /* ---- sort_array-exact sort (sort.h:104-155): median-of-3 quicksort, <=5-element partitions left to
  * a final bubble pass; the resulting permutation of equal keys is part of the contract. */
 template<class T, class GT> ZMO_HDN void zmo_ref_sort(T *rs, size_t n, GT gt){

@@ -85,3 +85,14 @@ extern "C" int sim_pair_dotmatrix(const uint8_t *pb1, int alen, const uint8_t *p
 	out[0] = r.score; out[1] = r.qb; out[2] = r.qe; out[3] = r.tb; out[4] = r.te; out[5] = r.strand;
 	return (int)n;
 }
+
+/* whole-read scan vs chunk-parallel scan: returns 1 if the concatenation of chunk emissions equals the full scan */
+extern "C" int sim_scan_chunks_equal(const uint8_t *seq, int len, int k, int hp, int chunk){
+	std::vector<uint32_t> w = pack(seq, len);
+	struct E { uint64_t mer; uint32_t dir, off, ln; bool operator==(const E &o) const { return mer == o.mer && dir == o.dir && off == o.off && ln == o.ln; } };
+	std::vector<E> a, b;
+	zmo_scan_kmers(w.data(), (uint32_t)len, k, hp, [&](uint64_t mer, uint32_t dir, uint32_t off, uint32_t ln){ a.push_back(E{mer, dir, off, ln}); });
+	for(int s = 0; s < len; s += chunk)
+		zmo_scan_kmers_chunk(w.data(), (uint32_t)len, k, hp, (uint32_t)s, (uint32_t)(s + chunk), [&](uint64_t mer, uint32_t dir, uint32_t off, uint32_t ln){ b.push_back(E{mer, dir, off, ln}); });
+	return a.size() == b.size() && std::equal(a.begin(), a.end(), b.begin());
+}

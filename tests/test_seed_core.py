@@ -116,3 +116,17 @@ def test_dotmatrix_oracle_matches_reference(ref_lib, oracle_lib):
         assert exp == run(oracle_lib, "orc_pair_dotmatrix", a, b)
         hits += exp[1][0] > 0
     assert hits > 10
+
+
+def test_chunk_scan_equals_full_scan(sim_lib):
+    """zmo_scan_kmers_chunk over disjoint chunks == zmo_scan_kmers over the read (used by the parallel scans)"""
+    rng = np.random.default_rng(77)
+    for trial in range(60):
+        n = int(rng.integers(1, 3000))
+        s = rng.integers(0, 4, n).astype(np.uint8)
+        if trial % 3 == 0:     # long homopolymers and dinucleotide repeats
+            s = np.repeat(rng.integers(0, 4, max(1, n // 7)), rng.integers(1, 15, max(1, n // 7))).astype(np.uint8)[:n]
+        s = np.ascontiguousarray(s)
+        for k, hp in ((16, 1), (10, 1), (5, 1), (32, 1), (16, 0), (10, 0)):
+            for chunk in (1, 7, 64, 128, 1000):
+                assert sim_lib.sim_scan_chunks_equal(s.ctypes.data_as(C.c_void_p), len(s), k, hp, chunk) == 1, (trial, len(s), k, hp, chunk)
