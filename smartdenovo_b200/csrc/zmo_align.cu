@@ -14,7 +14,7 @@
 #include "zmo_jobs.cuh"
 #include "zmo_seed_core.cuh"
 
-int zmo_launch_ext(zmo_ctx *c, int mode, bool wide, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells);
+int zmo_launch_ext(zmo_ctx *c, int mode, int cls, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells);
 int zmo_launch_glb(zmo_ctx *c, bool wide, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells);
 
 #define CUB_CALL(c, call_expr) do { size_t _tb = 0; void *_tp = nullptr; { auto d_temp = _tp; size_t &temp_bytes = _tb; CUDA_TRY(call_expr); } \
@@ -163,7 +163,9 @@ __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *ite
 
 /* per-task bookkeeping shared by the plan/finish kernels */
 struct TaskState { int ok; int first, last; int left_job, right_job; int gap0, ngap; int score, tb, te, qb, qe, aln, mat, mis, ins, del; unsigned long long cig_need; };
-struct JobLists { DPJob *ext_w, *ext_n, *glb_w, *glb_n; unsigned long long *n_ext_w, *n_ext_n, *n_glb_w, *n_glb_n; uint32_t cap; unsigned long long *arena_cur, arena_cap, *cig_cur, cig_cap, *overflow; uint32_t res_ext_w, res_ext_n, res_glb_w, res_glb_n; };
+/* six job lists: extension classes 0..3 (warp, CTA 64/128/256), gap-fill warp (4) and CTA (5); a job's index in the
+ * concatenated array equals its result index */
+struct JobLists { DPJob *list[6]; unsigned long long *cnt[6]; uint32_t res_base[6]; uint32_t cap; unsigned long long *arena_cur, arena_cap, *cig_cur, cig_cap, *overflow; };
 
 __device__ inline int push_job(DPJob *list, unsigned long long *cnt, uint32_t cap, uint32_t res_base, DPJob &J, unsigned long long scratch_words, JobLists &L){
 	const unsigned long long s0 = atomicAdd(L.arena_cur, scratch_words), c0 = atomicAdd(L.cig_cur, (unsigned long long)J.cig_cap);
@@ -197,8 +199,8 @@ __global__ void k_plan(const AlnTask *tasks, uint32_t nt, const zmo_pair_t *pair
 			const int bw = gq < 2 * w + 1? gq : 2 * w + 1;
 			const bool wide = bw > 32 * 7 * 2;
 			int id;
-			if(wide) id = push_job(L.glb_w, L.n_glb_w, L.cap, L.res_glb_w, J, glb_scratch_words<256, 7>(gq, gt, 2048), L);
-			else id = push_job(L.glb_n, L.n_glb_n, L.cap, L.res_glb_n, J, glb_scratch_words<32, 7>(gq, gt, 256), L);
+			if(wide) id = push_job(L.list[5], L.cnt[5], L.cap, L.res_base[5], J, glb_scratch_words<256, 7>(gq, gt, 2048), L);
+			else id = push_job(L.list[4], L.cnt[4], L.cap, L.res_base[4], J, glb_scratch_words<32, 7>(gq, gt, 256), L);
 			/* gap job ids of one task are not contiguous across classes: remember them in the region record slot */
 			((DevReg*)regs)[T.item_off + k].kept = 2u + (uint32_t)(id < 0? 0 : id);
 			S.ngap++;
@@ -216,8 +218,7 @@ __global__ void k_plan(const AlnTask *tasks, uint32_t nt, const zmo_pair_t *pair
 			J.init = r0.score + 100 * A.P.M; J.Wp = -A.ew; J.cig_cap = (uint32_t)(r0.qb + r0.tb + 4);
 			const int init = J.init < 0? 0 : J.init;
 			const BandDims d = band_dims(J.qlen, J.tlen, init, J.Wp, A.P);
-			if(d.ncol > 32 * 7) S.left_job = push_job(L.ext_w, L.n_ext_w, L.cap, L.res_ext_w, J, ext_scratch_words<256, 7>(d, 2048), L);
-			else S.left_job = push_job(L.ext_n, L.n_ext_n, L.cap, L.res_ext_n, J, ext_scratch_words<32, 7>(d, 256), L);
+			{ const int cls = ext_class(d.ncol); S.left_job = push_job(L.list[cls], L.cnt[cls], L.cap, L.res_base[cls], J, ext_scratch_words_cls(d, cls), L); }
 		}
 	}
 	ts[t] = S;
@@ -266,8 +267,7 @@ __global__ void k_plan2(const AlnTask *tasks, uint32_t nt, const zmo_pair_t *pai
 		J.init = S.score; J.Wp = -A.ew; J.cig_cap = (uint32_t)(J.qlen + J.tlen + 4);
 		const int init = J.init < 0? 0 : J.init;
 		const BandDims d = band_dims(J.qlen, J.tlen, init, J.Wp, A.P);
-		if(d.ncol > 32 * 7) S.right_job = push_job(L.ext_w, L.n_ext_w, L.cap, L.res_ext_w, J, ext_scratch_words<256, 7>(d, 2048), L);
-		else S.right_job = push_job(L.ext_n, L.n_ext_n, L.cap, L.res_ext_n, J, ext_scratch_words<32, 7>(d, 256), L);
+		{ const int cls = ext_class(d.ncol); S.right_job = push_job(L.list[cls], L.cnt[cls], L.cap, L.res_base[cls], J, ext_scratch_words_cls(d, cls), L); }
 	}
 	ts[t] = S;
 }
@@ -352,7 +352,7 @@ extern "C" int zmo_pair_align(zmo_ctx *c, int slot, const zmo_task_t *tasks, uin
 	const uint32_t jcap = nitems + 2 * nt + 8;
 	/* device buffers: s0 tasks|items|icig, s1 regs, s2 task state, s3 jobs (4 lists), s4 results, s6 cig arena, s7 out offsets */
 	if(c->s0.reserve((size_t)nt * sizeof(AlnTask) + (size_t)nitems * (sizeof(WItem) + 8) + 64) || c->s1.reserve(((size_t)nitems + 1) * sizeof(DevReg)) || c->s2.reserve(((size_t)nt + 1) * sizeof(TaskState))
-		|| c->s3.reserve((size_t)jcap * 4 * sizeof(DPJob)) || c->s4.reserve((size_t)jcap * 4 * sizeof(DPRes)) || c->s7.reserve(((size_t)nt + 2) * 16)) return ZMO_ERR_CUDA;
+		|| c->s3.reserve((size_t)jcap * 6 * sizeof(DPJob)) || c->s4.reserve((size_t)jcap * 6 * sizeof(DPRes)) || c->s7.reserve(((size_t)nt + 2) * 16)) return ZMO_ERR_CUDA;
 	AlnTask *d_tasks = c->s0.as<AlnTask>(); WItem *d_items = (WItem*)(d_tasks + nt); unsigned long long *d_icig = (unsigned long long*)(((uintptr_t)(d_items + nitems) + 7) & ~(uintptr_t)7);
 	DevReg *d_regs = c->s1.as<DevReg>(); TaskState *d_ts = c->s2.as<TaskState>();
 	DPJob *d_jobs = c->s3.as<DPJob>(); DPRes *d_res = c->s4.as<DPRes>();
@@ -377,51 +377,45 @@ extern "C" int zmo_pair_align(zmo_ctx *c, int slot, const zmo_task_t *tasks, uin
 			CUDA_TRY(cudaGetLastError());
 		}
 		/* plan: left extensions + gaps */
-		JobLists L; L.cap = jcap; L.ext_w = d_jobs; L.ext_n = d_jobs + jcap; L.glb_w = d_jobs + 2 * (size_t)jcap; L.glb_n = d_jobs + 3 * (size_t)jcap;
-		L.n_ext_w = ctr + CTR_N1; L.n_ext_n = ctr + CTR_N2; L.n_glb_w = ctr + CTR_N3; L.n_glb_n = ctr + CTR_N4;
-		L.arena_cur = ctr + CTR_ARENA; L.arena_cap = arena_words; L.cig_cur = ctr + CTR_N5; L.cig_cap = cig_cap_words; L.overflow = ctr + CTR_OVERFLOW;
-		L.res_ext_w = 0; L.res_ext_n = jcap; L.res_glb_w = 2 * jcap; L.res_glb_n = 3 * jcap;
-		unsigned long long init_ctr[8] = {0};
-		CUDA_TRY(cudaMemsetAsync(ctr + CTR_N1, 0, 5 * 8, c->stream));
+		JobLists L; L.cap = jcap;
+		for(int k = 0; k < 6; k++){ L.list[k] = d_jobs + (size_t)k * jcap; L.cnt[k] = ctr + CTR_JOBS + k; L.res_base[k] = (uint32_t)k * jcap; }
+		L.arena_cur = ctr + CTR_ARENA; L.arena_cap = arena_words; L.cig_cur = ctr + CTR_CIG; L.cig_cap = cig_cap_words; L.overflow = ctr + CTR_OVERFLOW;
+		unsigned long long init_ctr[2] = {slabs_total, cig_words};
+		CUDA_TRY(cudaMemsetAsync(ctr + CTR_JOBS, 0, 6 * 8, c->stream));
 		CUDA_TRY(cudaMemsetAsync(ctr + CTR_OVERFLOW, 0, 8, c->stream));
-		init_ctr[0] = slabs_total; init_ctr[1] = cig_words;
 		CUDA_TRY(cudaMemcpyAsync(ctr + CTR_ARENA, &init_ctr[0], 8, cudaMemcpyHostToDevice, c->stream));
-		CUDA_TRY(cudaMemcpyAsync(ctr + CTR_N5, &init_ctr[1], 8, cudaMemcpyHostToDevice, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(ctr + CTR_CIG, &init_ctr[1], 8, cudaMemcpyHostToDevice, c->stream));
 		k_plan<<<(nt + 63) / 64, 64, 0, c->stream>>>(d_tasks, nt, SL.pairs.as<zmo_pair_t>(), d_regs, R, A, L, d_ts, 0); c->launches++;
-		unsigned long long h[8];
-		CUDA_TRY(cudaMemcpyAsync(h, ctr + CTR_ARENA, 8 * 8, cudaMemcpyDeviceToHost, c->stream));
+		unsigned long long h[CTR_TOTAL];
+		CUDA_TRY(cudaMemcpyAsync(h, ctr, CTR_TOTAL * 8, cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
-		/* h: [0]=arena cursor [1]=work [2]=overflow [3..6]=n_ext_w,n_ext_n,n_glb_w,n_glb_n [7]=cig cursor */
-		if(h[2]){
+		if(h[CTR_OVERFLOW]){
 			if(attempt >= 6) return zmo_set_err(ZMO_ERR_CAPACITY, "DP arena overflow after %d attempts", attempt);
-			arena_words = std::max(arena_words * 2, h[0] + (64ull << 20)); cig_cap_words = std::max(cig_cap_words * 2, h[7] + (1ull << 20));
+			arena_words = std::max(arena_words * 2, h[CTR_ARENA] + (64ull << 20)); cig_cap_words = std::max(cig_cap_words * 2, h[CTR_CIG] + (1ull << 20));
 			continue;
 		}
-		const uint32_t n_ew = (uint32_t)h[3], n_en = (uint32_t)h[4], n_gw = (uint32_t)h[5], n_gn = (uint32_t)h[6];
+		uint32_t n1[6]; for(int k = 0; k < 6; k++) n1[k] = (uint32_t)h[CTR_JOBS + k];
 		{
 			StageTimer tm(c, ST_EXT);
-			if(zmo_launch_ext(c, 1, true, L.ext_w, nullptr, n_ew, arena, cig_arena, d_res, CTR_CELLS_EXT)) return ZMO_ERR_CUDA;
-			if(zmo_launch_ext(c, 1, false, L.ext_n, nullptr, n_en, arena, cig_arena, d_res, CTR_CELLS_EXT)) return ZMO_ERR_CUDA;
+			for(int k = 3; k >= 0; k--) if(zmo_launch_ext(c, 1, k, L.list[k], nullptr, n1[k], arena, cig_arena, d_res, CTR_CELLS_EXT)) return ZMO_ERR_CUDA;
 		}
 		{
 			StageTimer tm(c, ST_GAP);
-			if(zmo_launch_glb(c, true, L.glb_w, nullptr, n_gw, arena, cig_arena, d_res, CTR_CELLS_GAP)) return ZMO_ERR_CUDA;
-			if(zmo_launch_glb(c, false, L.glb_n, nullptr, n_gn, arena, cig_arena, d_res, CTR_CELLS_GAP)) return ZMO_ERR_CUDA;
+			if(zmo_launch_glb(c, true, L.list[5], nullptr, n1[5], arena, cig_arena, d_res, CTR_CELLS_GAP)) return ZMO_ERR_CUDA;
+			if(zmo_launch_glb(c, false, L.list[4], nullptr, n1[4], arena, cig_arena, d_res, CTR_CELLS_GAP)) return ZMO_ERR_CUDA;
 		}
-		/* plan2: right extensions appended to the same ext lists */
+		/* plan2: right extensions appended to the same extension lists */
 		k_plan2<<<(nt + 63) / 64, 64, 0, c->stream>>>(d_tasks, nt, SL.pairs.as<zmo_pair_t>(), d_regs, d_res, R, A, L, d_ts); c->launches++;
-		CUDA_TRY(cudaMemcpyAsync(h, ctr + CTR_ARENA, 8 * 8, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(h, ctr, CTR_TOTAL * 8, cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
-		if(h[2]){
+		if(h[CTR_OVERFLOW]){
 			if(attempt >= 6) return zmo_set_err(ZMO_ERR_CAPACITY, "DP arena overflow after %d attempts", attempt);
-			arena_words = std::max(arena_words * 2, h[0] + (64ull << 20)); cig_cap_words = std::max(cig_cap_words * 2, h[7] + (1ull << 20));
+			arena_words = std::max(arena_words * 2, h[CTR_ARENA] + (64ull << 20)); cig_cap_words = std::max(cig_cap_words * 2, h[CTR_CIG] + (1ull << 20));
 			continue;
 		}
-		const uint32_t n_ew2 = (uint32_t)h[3], n_en2 = (uint32_t)h[4];
 		{
 			StageTimer tm(c, ST_EXT);
-			if(zmo_launch_ext(c, 1, true, L.ext_w + n_ew, nullptr, n_ew2 - n_ew, arena, cig_arena, d_res, CTR_CELLS_EXT)) return ZMO_ERR_CUDA;
-			if(zmo_launch_ext(c, 1, false, L.ext_n + n_en, nullptr, n_en2 - n_en, arena, cig_arena, d_res, CTR_CELLS_EXT)) return ZMO_ERR_CUDA;
+			for(int k = 3; k >= 0; k--){ const uint32_t n2 = (uint32_t)h[CTR_JOBS + k]; if(zmo_launch_ext(c, 1, k, L.list[k] + n1[k], nullptr, n2 - n1[k], arena, cig_arena, d_res, CTR_CELLS_EXT)) return ZMO_ERR_CUDA; }
 		}
 		/* final sizes, offsets, stitched CIGARs */
 		unsigned long long *d_need = c->s7.as<unsigned long long>(), *d_ooff = d_need + nt + 1;

@@ -7,13 +7,13 @@
 #include "zmo_seed.cuh"
 #include "zmo_dot_core.cuh"
 
-__global__ void k_p_dot(const unsigned long long *cache_off, const zmo_pair_t *pairs, uint32_t np, DevZPair *cache, uint8_t *scratch, size_t per, DevReads R, DotPar par, uint32_t zsize, uint32_t ztot, zmo_dotres_t *out){
+__global__ void k_p_dot(const unsigned long long *cache_off, const zmo_pair_t *pairs, uint32_t np, DevZPair *cache, const uint8_t *tie, uint8_t *scratch, size_t per, DevReads R, DotPar par, uint32_t zsize, uint32_t ztot, zmo_dotres_t *out){
 	uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	if(p >= np) return;
 	const unsigned long long c0 = cache_off[p]; const uint32_t n = (uint32_t)(cache_off[p + 1] - c0);
 	zmo_dotres_t o; o.n_zpair = n; o.score = 0; o.qb = o.tb = 0x7FFFFFFF; o.qe = o.te = 0; o.strand = 0;
 	if((unsigned long long)n * zsize >= ztot){
-		const DotRes r = zmo_dot_pair(cache + c0, n, (int)R.len[pairs[p].qid], (int)R.len[pairs[p].cid], par, scratch + c0 * per + (size_t)(2 * per + 64) * p);
+		const DotRes r = zmo_dot_pair(cache + c0, n, (int)R.len[pairs[p].qid], (int)R.len[pairs[p].cid], par, scratch + c0 * per + (size_t)(2 * per + 64) * p, tie[p]? 2 : 1);
 		o.score = r.score; o.qb = r.qb; o.qe = r.qe; o.tb = r.tb; o.te = r.te; o.strand = r.strand;
 	}
 	out[p] = o;
@@ -26,16 +26,18 @@ extern "C" int zmo_pair_dotmatrix(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t 
 	CUDA_TRY(cudaSetDevice(c->device));
 	StageTimer tm(c, ST_DOT);
 	SeedWork W;
-	if(int rc = seed_prepare(c, pairs, np, W, c->s5)) return rc;
+	if(int rc = seed_prepare(c, pairs, np, 1, W, c->s5)) return rc;
 	const size_t per = 4 + sizeof(DevDiag) + 4 + 4 + sizeof(DevZPairG) + sizeof(DevWin) + 16;     /* zmo_dot_scratch_bytes(n) = (n+2)*per + 64 */
-	if(c->s3.reserve(W.T * per + (size_t)(2 * per + 64) * np + 256) || c->s6.reserve((size_t)np * sizeof(zmo_pair_t) + 64) || c->s7.reserve((size_t)np * sizeof(zmo_dotres_t) + 64)) return ZMO_ERR_CUDA;
-	CUDA_TRY(cudaMemcpyAsync(c->s6.p, pairs, (size_t)np * sizeof(zmo_pair_t), cudaMemcpyHostToDevice, c->stream));
+	/* scratch in s6; pairs + results in s1 (the per-read z counters there are dead) */
+	if(c->s6.reserve(W.T * per + (size_t)(2 * per + 64) * np + 256) || c->s1.reserve((size_t)np * (sizeof(zmo_pair_t) + sizeof(zmo_dotres_t)) + 128)) return ZMO_ERR_CUDA;
+	zmo_pair_t *d_pairs = c->s1.as<zmo_pair_t>(); zmo_dotres_t *d_out = (zmo_dotres_t*)(d_pairs + np + 1);
+	CUDA_TRY(cudaMemcpyAsync(d_pairs, pairs, (size_t)np * sizeof(zmo_pair_t), cudaMemcpyHostToDevice, c->stream));
 	DotPar par; par.xvar = c->par.xvar; par.yvar = c->par.yvar; par.min_block_len = c->par.min_block_len; par.max_overhang = c->par.max_overhang;
 	par.deviation_penalty = c->par.deviation_penalty; par.gap_penalty = c->par.gap_penalty;
-	k_p_dot<<<(np + 31) / 32, 32, 0, c->stream>>>(W.cache_off, c->s6.as<zmo_pair_t>(), np, W.cache, c->s3.as<uint8_t>(), per, dev_reads(c), par, (uint32_t)c->par.zsize, (uint32_t)c->par.ztot, c->s7.as<zmo_dotres_t>());
+	k_p_dot<<<(np + 31) / 32, 32, 0, c->stream>>>(W.cache_off, d_pairs, np, W.cache, W.tie, c->s6.as<uint8_t>(), per, dev_reads(c), par, (uint32_t)c->par.zsize, (uint32_t)c->par.ztot, d_out);
 	c->launches++;
 	CUDA_TRY(cudaGetLastError());
-	CUDA_TRY(cudaMemcpyAsync(out, c->s7.p, (size_t)np * sizeof(zmo_dotres_t), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(out, d_out, (size_t)np * sizeof(zmo_dotres_t), cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	c->counters[5] += (size_t)np * sizeof(zmo_pair_t); c->counters[6] += (size_t)np * sizeof(zmo_dotres_t);
 	return 0;

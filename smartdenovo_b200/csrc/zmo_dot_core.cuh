@@ -235,11 +235,14 @@ ZMO_HDN int zmo_chain_blocks(int len1, int len2, DevWin *r, uint32_t n, int tail
 	return mw;
 }
 
-/* hzm_aln.h:1134-1181 for one pair; cache is sorted in place, gid must hold >= n words */
-ZMO_HDN DotRes zmo_dot_pair(DevZPair *cache, uint32_t n, int alen, int blen, const DotPar &par, uint8_t *scratch){
+/* hzm_aln.h:1134-1181 for one pair.  presorted: 0 = cache is in the reference emission order (sort it here),
+ * 1 = already sorted by (diagonal, off1) with no tied keys, 2 = sorted but with tied keys: rebuild the emission order
+ * and run the exact sort so that the tie permutation equals the reference's */
+ZMO_HDN DotRes zmo_dot_pair(DevZPair *cache, uint32_t n, int alen, int blen, const DotPar &par, uint8_t *scratch, int presorted){
 	DotScratch S = zmo_dot_scratch_carve(scratch, n);
 	DotRes best[2]; int weight[2];
-	zmo_ref_sort(cache, (size_t)n, GtZPairDiag());
+	if(presorted == 2){ GtZPairEmit g; g.clen = (uint32_t)blen; zmo_ref_sort(cache, (size_t)n, g); }
+	if(presorted != 1) zmo_ref_sort(cache, (size_t)n, GtZPairDiag());
 	for(uint32_t i = 0; i < n; i++) S.gid[i] = 0;
 	for(int d = 0; d < 2; d++){
 		uint32_t nreg = zmo_denoise_strand(cache, n, d, par, S);

@@ -8,22 +8,27 @@
 #define EXT_C  7
 #define EXT_CAP 2048
 #define EXT_SEQW 4096
+/* executor class of an extension band: host and device must agree (scratch sizing depends on it) */
 #define WRP_C  7
 #define WRP_CAP 256
 #define WRP_SEQW 256
 #define WRP_PER_CTA 4
 
-/* CTA-per-job extension kernel (wide bands: end extensions with ew up to 1022 in shared memory) */
-template<int MODE>
-__global__ void __launch_bounds__(EXT_NT) k_ext_cta(const DPJob *jobs, const uint32_t *order, uint32_t njobs, DevReads R, DPPar P,
+/* CTA-per-job extension kernels: NT threads x 7 columns per row chunk.  NT = 64 / 128 / 256 serve bands up to
+ * 448 / 896 / 1792 columns in one chunk (wider bands loop over chunks), so that mid-size bands do not idle most
+ * of a 256-thread CTA or write 1 KB traceback rows. */
+template<int NT, int MODE>
+__global__ void __launch_bounds__(NT, (NT == 256? 3 : (NT == 128? 6 : 10))) k_ext_cta(const DPJob *jobs, const uint32_t *order, uint32_t njobs, DevReads R, DPPar P,
 		uint32_t *arena, uint32_t *cig_arena, DPRes *res, unsigned long long *ctr, int ctr_work, int ctr_cells){
-	__shared__ int s_h[3 * EXT_CAP];
-	__shared__ uint32_t s_seq[EXT_SEQW];
-	__shared__ int s_red[2 * (EXT_NT / 32)];
-	__shared__ long long s_redk[EXT_NT / 32];
+	constexpr int CAP = NT * 8;                /* 512 / 1024 / 2048 >= NT*7 + 2 */
+	constexpr int SEQW = NT == 256? 4096 : 2048;
+	__shared__ int s_h[3 * CAP];
+	__shared__ uint32_t s_seq[SEQW];
+	__shared__ int s_red[2 * (NT / 32)];
+	__shared__ long long s_redk[NT / 32];
 	__shared__ int s_misc[16];
 	__shared__ uint32_t s_job;
-	ExecSmem<EXT_NT> X; X.carve(s_h, EXT_CAP, s_seq, EXT_SEQW, s_red, s_redk, s_misc);
+	ExecSmem<NT> X; X.carve(s_h, CAP, s_seq, SEQW, s_red, s_redk, s_misc);
 	const int tid = threadIdx.x;
 	while(1){
 		if(tid == 0) s_job = (uint32_t)atomicAdd(ctr + ctr_work, 1ULL);
@@ -31,7 +36,7 @@ __global__ void __launch_bounds__(EXT_NT) k_ext_cta(const DPJob *jobs, const uin
 		const uint32_t jn = s_job;
 		__syncthreads();
 		if(jn >= njobs) break;
-		run_ext_job<EXT_NT, EXT_C, MODE>(jobs[order? order[jn] : jn], R, P, X, arena, cig_arena, res, ctr + ctr_cells, tid);
+		run_ext_job<NT, EXT_C, MODE>(jobs[order? order[jn] : jn], R, P, X, arena, cig_arena, res, ctr + ctr_cells, tid);
 		__syncthreads();
 	}
 }
@@ -97,20 +102,23 @@ __global__ void __launch_bounds__(EXT_NT) k_glb_cta(const DPJob *jobs, const uin
 static DPPar dp_par(const zmo_ctx *c){ DPPar P; P.M = c->par.M; P.X = c->par.X; P.I = c->par.O; P.D = c->par.O; P.E = c->par.E; P.T = c->par.T; return P; }
 
 /* ---- launch helpers used by the API and the pipeline --------------------------------------- */
-int zmo_launch_ext(zmo_ctx *c, int mode, bool wide, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells){
+template<int NT> static void launch_ext_cta(zmo_ctx *c, int mode, int grid, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, DevReads R, DPPar P, uint32_t *arena, uint32_t *cig, DPRes *d_res, unsigned long long *ctr, int ctr_cells){
+	if(mode == 1) k_ext_cta<NT, 1><<<grid, NT, 0, c->stream>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, CTR_WORK, ctr_cells);
+	else k_ext_cta<NT, 0><<<grid, NT, 0, c->stream>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, CTR_WORK, ctr_cells);
+}
+/* cls: 0 = warp executor (band <= 224), 1/2/3 = CTA of 64/128/256 threads */
+int zmo_launch_ext(zmo_ctx *c, int mode, int cls, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells){
 	if(n == 0) return 0;
 	unsigned long long *ctr = c->d_ctr.as<unsigned long long>();
 	CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORK, 0, 8, c->stream));
 	DevReads R = dev_reads(c); DPPar P = dp_par(c);
-	if(wide){
-		int grid = (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 4);
-		if(mode == 1) k_ext_cta<1><<<grid, EXT_NT, 0, c->stream>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, CTR_WORK, ctr_cells);
-		else k_ext_cta<0><<<grid, EXT_NT, 0, c->stream>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, CTR_WORK, ctr_cells);
-	} else {
+	if(cls == 0){
 		int grid = (int)std::min<uint64_t>((n + WRP_PER_CTA - 1) / WRP_PER_CTA, (uint64_t)c->n_sm * 8);
 		if(mode == 1) k_ext_warp<1><<<grid, 32 * WRP_PER_CTA, 0, c->stream>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, CTR_WORK, ctr_cells);
 		else k_ext_warp<0><<<grid, 32 * WRP_PER_CTA, 0, c->stream>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, CTR_WORK, ctr_cells);
-	}
+	} else if(cls == 1) launch_ext_cta<64>(c, mode, (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 10), d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, ctr_cells);
+	else if(cls == 2) launch_ext_cta<128>(c, mode, (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 6), d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, ctr_cells);
+	else launch_ext_cta<256>(c, mode, (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 3), d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, ctr_cells);
 	c->launches++;
 	CUDA_TRY(cudaGetLastError());
 	return 0;
@@ -138,7 +146,7 @@ static int dp_batch(zmo_ctx *c, int kind /*0 ext mode0, 1 ext mode1, 2 global*/,
 	if(!c || (n && (!probs || !res))) return zmo_set_err(ZMO_ERR_ARG, "null argument");
 	if(n == 0){ if(cigar_needed) *cigar_needed = 0; return 0; }
 	DPPar P = dp_par(c);
-	std::vector<DPJob> jw, jn; std::vector<uint32_t> iw, in_;
+	std::vector<DPJob> jl[4];       /* per executor class (global: class 3 = CTA, class 0 = warp) */
 	uint64_t scratch = 0, cig = 0;
 	for(uint32_t i = 0; i < n; i++){
 		const zmo_dp_problem_t &p = probs[i]; DPJob J; memset(&J, 0, sizeof(J));
@@ -147,42 +155,41 @@ static int dp_batch(zmo_ctx *c, int kind /*0 ext mode0, 1 ext mode1, 2 global*/,
 		J.t_start = p.t_start; J.t_step = p.t_step; J.t_comp = p.t_comp; J.tlen = p.tlen; J.init = p.init_score; J.Wp = p.W; J.Wmax = 0;
 		J.out_idx = i; J.cig_off = cig; J.cig_cap = (uint32_t)((p.qlen > 0? p.qlen : 0) + (p.tlen > 0? p.tlen : 0) + 4);
 		cig += J.cig_cap;
-		bool wide;
+		int cls;
 		if(kind == 2){
 			J.Wp = wv[i];
 			int w = J.Wp, dl = abs(p.qlen - p.tlen); while(w < dl) w <<= 1;
 			int bw = std::min(p.qlen, 2 * w + 1);
-			wide = bw > 32 * WRP_C * 2;
+			cls = bw > 32 * WRP_C * 2? 3 : 0;
 			J.scratch = scratch;
-			scratch += wide? glb_scratch_words<EXT_NT, EXT_C>(p.qlen, p.tlen, EXT_CAP) : glb_scratch_words<32, WRP_C>(p.qlen, p.tlen, WRP_CAP);
+			scratch += cls? glb_scratch_words<EXT_NT, EXT_C>(p.qlen, p.tlen, EXT_CAP) : glb_scratch_words<32, WRP_C>(p.qlen, p.tlen, WRP_CAP);
 		} else {
 			int init = p.init_score < 0? 0 : p.init_score;
 			BandDims d; d.W = 0; d.ql = d.tl = d.ncol = 0;
 			if(p.qlen > 0 && p.tlen > 0) d = band_dims(p.qlen, p.tlen, init, p.W, P);
-			wide = d.ncol > 32 * WRP_C;
+			cls = ext_class(d.ncol);
 			J.scratch = scratch;
-			scratch += wide? ext_scratch_words<EXT_NT, EXT_C>(d, EXT_CAP) : ext_scratch_words<32, WRP_C>(d, WRP_CAP);
+			scratch += ext_scratch_words_cls(d, cls);
 		}
-		if(wide){ jw.push_back(J); } else { jn.push_back(J); }
+		jl[cls].push_back(J);
 	}
 	if(cigar_needed) *cigar_needed = cig;
 	if(cig > cigar_cap) return zmo_set_err(ZMO_ERR_CAPACITY, "cigar buffer too small: need %llu", (unsigned long long)cig);
 	if(c->arena.reserve((scratch + 64) * 4)) return ZMO_ERR_CUDA;
-	if(c->s0.reserve((jw.size() + jn.size() + 1) * sizeof(DPJob))) return ZMO_ERR_CUDA;
+	if(c->s0.reserve(((size_t)n + 1) * sizeof(DPJob))) return ZMO_ERR_CUDA;
 	if(c->s1.reserve((size_t)(n + 1) * sizeof(DPRes))) return ZMO_ERR_CUDA;
 	if(c->s2.reserve((cig + 16) * 4)) return ZMO_ERR_CUDA;
-	DPJob *dj = c->s0.as<DPJob>();
-	if(jw.size()) CUDA_TRY(cudaMemcpyAsync(dj, jw.data(), jw.size() * sizeof(DPJob), cudaMemcpyHostToDevice, c->stream));
-	if(jn.size()) CUDA_TRY(cudaMemcpyAsync(dj + jw.size(), jn.data(), jn.size() * sizeof(DPJob), cudaMemcpyHostToDevice, c->stream));
+	DPJob *dj = c->s0.as<DPJob>(); size_t joff[5] = {0, 0, 0, 0, 0};
+	for(int k = 0; k < 4; k++){
+		joff[k + 1] = joff[k] + jl[k].size();
+		if(jl[k].size()) CUDA_TRY(cudaMemcpyAsync(dj + joff[k], jl[k].data(), jl[k].size() * sizeof(DPJob), cudaMemcpyHostToDevice, c->stream));
+	}
 	{
 		StageTimer t(c, kind == 2? ST_GAP : (kind == 1? ST_EXT : ST_WINALN));
 		int cc = kind == 2? CTR_CELLS_GAP : (kind == 1? CTR_CELLS_EXT : CTR_CELLS_WIN);
-		if(kind == 2){
-			if(zmo_launch_glb(c, true, dj, nullptr, (uint32_t)jw.size(), c->arena.as<uint32_t>(), c->s2.as<uint32_t>(), c->s1.as<DPRes>(), cc)) return ZMO_ERR_CUDA;
-			if(zmo_launch_glb(c, false, dj + jw.size(), nullptr, (uint32_t)jn.size(), c->arena.as<uint32_t>(), c->s2.as<uint32_t>(), c->s1.as<DPRes>(), cc)) return ZMO_ERR_CUDA;
-		} else {
-			if(zmo_launch_ext(c, kind, true, dj, nullptr, (uint32_t)jw.size(), c->arena.as<uint32_t>(), c->s2.as<uint32_t>(), c->s1.as<DPRes>(), cc)) return ZMO_ERR_CUDA;
-			if(zmo_launch_ext(c, kind, false, dj + jw.size(), nullptr, (uint32_t)jn.size(), c->arena.as<uint32_t>(), c->s2.as<uint32_t>(), c->s1.as<DPRes>(), cc)) return ZMO_ERR_CUDA;
+		for(int k = 0; k < 4; k++){
+			if(kind == 2){ if(zmo_launch_glb(c, k != 0, dj + joff[k], nullptr, (uint32_t)jl[k].size(), c->arena.as<uint32_t>(), c->s2.as<uint32_t>(), c->s1.as<DPRes>(), cc)) return ZMO_ERR_CUDA; }
+			else { if(zmo_launch_ext(c, kind, k, dj + joff[k], nullptr, (uint32_t)jl[k].size(), c->arena.as<uint32_t>(), c->s2.as<uint32_t>(), c->s1.as<DPRes>(), cc)) return ZMO_ERR_CUDA; }
 		}
 	}
 	std::vector<DPRes> hr(n);
@@ -190,7 +197,7 @@ static int dp_batch(zmo_ctx *c, int kind /*0 ext mode0, 1 ext mode1, 2 global*/,
 	CUDA_TRY(cudaMemcpyAsync(cigars, c->s2.p, cig * 4, cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	/* CIGARs come back in walk order (end -> start); flip each to alignment order like the reference's reverse_u32list */
-	std::vector<const DPJob*> all; for(auto &j : jw) all.push_back(&j); for(auto &j : jn) all.push_back(&j);
+	std::vector<const DPJob*> all; for(int k = 0; k < 4; k++) for(auto &j : jl[k]) all.push_back(&j);
 	for(const DPJob *j : all){
 		const DPRes &r = hr[j->out_idx]; zmo_dp_result_t &o = res[j->out_idx];
 		o.score = r.score; o.qe = r.qe; o.te = r.te; o.mat = r.mat; o.mis = r.mis; o.ins = r.ins; o.del = r.del; o.aln = r.mat + r.mis + r.ins + r.del;

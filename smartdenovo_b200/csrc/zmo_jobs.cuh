@@ -24,9 +24,14 @@ template<int NT, int C> __host__ __device__ inline unsigned long long ext_scratc
 	unsigned long long zw = (unsigned long long)d.ql * band_row_words<NT, C>(d.ncol);
 	unsigned long long seq = (unsigned long long)((d.ql + 15) >> 4) + ((d.tl + 15) >> 4) + 2;
 	unsigned long long hb = 0;
-	int need = 2 * d.W + 3;
+	int need = 2 * d.W + 3 < d.tl + 2? 2 * d.W + 3 : d.tl + 2;       /* columns that can be live in the H/E rows */
 	if(need > sm_cap){ unsigned long long cap = 1; while(cap < (unsigned long long)need) cap <<= 1; hb = 3 * cap; }
 	return zw + (unsigned long long)d.ql + seq + hb + 8;
+}
+/* executor class of an extension band: 0 = warp (<= 224 columns), 1/2/3 = CTA of 64/128/256 threads */
+__host__ __device__ inline int ext_class(int ncol){ return ncol <= 224? 0 : (ncol <= 448? 1 : (ncol <= 896? 2 : 3)); }
+__host__ __device__ inline unsigned long long ext_scratch_words_cls(const BandDims &d, int cls){
+	return cls == 0? ext_scratch_words<32, 7>(d, 256) : (cls == 1? ext_scratch_words<64, 7>(d, 512) : (cls == 2? ext_scratch_words<128, 7>(d, 1024) : ext_scratch_words<256, 7>(d, 2048)));
 }
 /* scratch for a global job sized for the widest band the retry loop can reach (ncol <= qlen) */
 template<int NT, int C> __host__ __device__ inline unsigned long long glb_scratch_words(int qlen, int tlen, int sm_cap){
@@ -68,7 +73,10 @@ __device__ void run_ext_job(const DPJob &J, const DevReads &R, const DPPar &P, E
 		else { qpk = scr; tpk = scr + qw; }
 		scr += qw + tw + 2;
 		BandSmem S = X.B;
-		if(2 * d.W + 3 > X.cap){ int cap = 1; while(cap < 2 * d.W + 3) cap <<= 1; S.H0 = (int*)scr; S.H1 = S.H0 + cap; S.Ev = S.H1 + cap; S.cap_mask = cap - 1; }
+		{
+			const int need = 2 * d.W + 3 < d.tl + 2? 2 * d.W + 3 : d.tl + 2;
+			if(need > X.cap){ int cap = 1; while(cap < need) cap <<= 1; S.H0 = (int*)scr; S.H1 = S.H0 + cap; S.Ev = S.H1 + cap; S.cap_mask = cap - 1; }
+		}
 		stage_packed<NT>(job_view(R, J.q_rid, J.q_start, J.q_step, J.q_comp), d.ql, qpk, tid);
 		stage_packed<NT>(job_view(R, J.t_rid, J.t_start, J.t_step, J.t_comp), d.tl, tpk, tid);
 		ex_sync<NT>();

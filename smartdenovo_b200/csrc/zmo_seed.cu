@@ -55,31 +55,103 @@ __global__ void k_z_ranges(const unsigned long long *zoff, const uint32_t *pos, 
 	if(u > nuq) return;
 	slot_beg[u] = (u < nuq && zoff[u] < Z)? pos[zoff[u]] : NS;
 }
-__global__ void k_p_ns(const uint32_t *pq, uint32_t np, const uint32_t *slot_beg, unsigned long long *ns){
-	uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-	if(p < np) ns[p] = slot_beg[pq[p] + 1] - slot_beg[pq[p]];
-}
 struct ZIdxView { const DevSlot *slots; const uint32_t *slot_beg; const DevZSeed *zs; const unsigned long long *zoff; };
-template<int PASS>
-__global__ void k_p_match(DevReads R, ZIdxView Z, const uint32_t *pq, const uint32_t *pc, uint32_t np, const unsigned long long *kc_off, uint8_t *kcnts,
-		int zsize, int hz, uint32_t zcut, uint32_t kvar, unsigned long long *nz_or_off, DevZPair *cache){
+#define SEED_CH 128
+/* chunk table of the candidate reads: one thread per pair */
+__global__ void k_c_nchunks(DevReads R, const uint32_t *pc, uint32_t np, unsigned long long *nch){
 	uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-	if(p >= np) return;
-	const uint32_t u = pq[p], cid = pc[p];
-	const uint32_t sb = Z.slot_beg[u], ns = Z.slot_beg[u + 1] - sb;
-	const uint32_t n = zmo_zmatch(R.words + R.woff[cid], R.len[cid], Z.slots + sb, ns, Z.zs + Z.zoff[u], kcnts + kc_off[p], zsize, hz, zcut, kvar, PASS? cache + nz_or_off[p] : nullptr);
-	if(!PASS) nz_or_off[p] = n;
+	if(p < np) nch[p] = (R.len[pc[p]] + SEED_CH - 1) / SEED_CH;
+}
+/* one thread per (pair, 128-base chunk of c): z-mers of the chunk that hit an indexed slot of q (hzm_aln.h:189-207).
+ * key = pair<<32 | slot (slot index inside q's list), val = off<<17 | len<<1 | dir of the c z-mer.  Threads write in
+ * (pair, chunk, position) order, so a stable sort by key keeps the hits of one slot in c-position order. */
+template<int PASS>
+__global__ void k_hit(DevReads R, ZIdxView Z, const uint32_t *pq, const uint32_t *pc, uint32_t np, const unsigned long long *choff, unsigned long long NC,
+		int zsize, int hz, unsigned long long *cnt_or_off, unsigned long long *hkey, unsigned long long *hval){
+	unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if(c >= NC) return;
+	uint32_t lo = 0, hi = np;
+	while(lo + 1 < hi){ uint32_t mid = (lo + hi) >> 1; if(choff[mid] <= c) lo = mid; else hi = mid; }
+	const uint32_t p = lo, u = pq[p], cid = pc[p], s = (uint32_t)(c - choff[p]) * SEED_CH;
+	const uint32_t sb = Z.slot_beg[u], ns = Z.slot_beg[u + 1] - sb; const DevSlot *slots = Z.slots + sb;
+	unsigned long long n = PASS? cnt_or_off[c] : 0;
+	zmo_scan_kmers_chunk(R.words + R.woff[cid], R.len[cid], zsize, hz, s, s + SEED_CH, [&](uint64_t mer64, uint32_t dir, uint32_t off, uint32_t ln){
+		const uint32_t mer = (uint32_t)mer64;
+		uint32_t a = 0, b = ns;
+		while(a < b){ uint32_t mid = (a + b) >> 1; if(slots[mid].mer < mer) a = mid + 1; else b = mid; }
+		if(a >= ns || slots[a].mer != mer) return;
+		if(PASS){ hkey[n] = ((unsigned long long)p << 32) | a; hval[n] = ((unsigned long long)off << 17) | ((unsigned long long)ln << 1) | dir; }
+		n++;
+	});
+	if(!PASS) cnt_or_off[c] = n;
+}
+/* one thread per sorted hit: rank among the hits of the same (pair, slot) = number of earlier c positions that hit
+ * the slot; the reference's uint8 per-slot counter admits the first Z positions (hzm_aln.h:208-211; with Z > 255 the
+ * counter wraps and never blocks).  Surviving hits expand into one match per q occurrence whose span length differs by
+ * <= kvar (hzm_aln.h:212-220).  MODE 0: key = pair<<48 | off1<<24 | off2 (SW path, process_hzmps order);
+ * MODE 1: key = pair<<49 | (off1-off2+2^24)<<24 | off1 (dot-matrix path, denoising_hzmps order).  val = len1<<18|len2<<2|dir1<<1|dir2. */
+template<int PASS, int MODE>
+__global__ void k_expand(DevReads R, ZIdxView Z, const uint32_t *pq, const uint32_t *pc, const unsigned long long *hkey, const unsigned long long *hval, unsigned long long NH,
+		uint32_t zcut, uint32_t kvar, unsigned long long *cnt_or_off, unsigned long long *zkey, unsigned long long *zval){
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= NH) return;
+	const unsigned long long key = hkey[i];
+	unsigned long long n = PASS? cnt_or_off[i] : 0;
+	uint32_t rank = 0;
+	if(zcut <= 255u){ for(unsigned long long j = i; j > 0 && hkey[j - 1] == key && rank < zcut; j--) rank++; }
+	if(zcut > 255u || rank < zcut){
+		const uint32_t p = (uint32_t)(key >> 32), u = pq[p]; const DevSlot s = Z.slots[Z.slot_beg[u] + (uint32_t)key];
+		const DevZSeed *zs = Z.zs + Z.zoff[u] + s.off;
+		const unsigned long long v = hval[i]; const uint32_t coff = (uint32_t)(v >> 17), ln = (uint32_t)((v >> 1) & 0xFFFFu), dir = (uint32_t)(v & 1u);
+		const uint32_t clen = R.len[pc[p]];
+		for(uint32_t k = 0; k < s.cnt; k++){
+			const DevZSeed p1 = zs[k];
+			const uint32_t dl = p1.len > ln? p1.len - ln : ln - p1.len;
+			if(dl > kvar) continue;
+			if(PASS){
+				const uint32_t off2 = (p1.dir ^ dir)? clen - (coff + ln) : coff;
+				if(MODE == 0) zkey[n] = ((unsigned long long)p << 48) | ((unsigned long long)p1.off << 24) | off2;
+				else zkey[n] = ((unsigned long long)p << 49) | ((unsigned long long)(p1.off + 0x1000000u - off2) << 24) | p1.off;
+				zval[n] = ((unsigned long long)p1.len << 18) | ((unsigned long long)ln << 2) | ((unsigned long long)p1.dir << 1) | dir;
+			}
+			n++;
+		}
+	}
+	if(!PASS) cnt_or_off[i] = n;
+}
+/* sorted (key,val) -> DevZPair list; equal adjacent keys (same q occurrence and same c coordinate on the two strands)
+ * are the only ties of the reference's unstable sorts: flag the pair so that k_p_seed / k_p_dot re-creates the reference
+ * emission order and runs the exact sort_array emulation for it */
+template<int MODE>
+__global__ void k_unpack(const unsigned long long *zkey, const unsigned long long *zval, unsigned long long T, DevZPair *cache, uint8_t *tie){
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= T) return;
+	const unsigned long long key = zkey[i], v = zval[i]; DevZPair z;
+	if(MODE == 0){ z.off1 = (uint32_t)((key >> 24) & 0xFFFFFFu); z.off2 = (uint32_t)(key & 0xFFFFFFu); }
+	else { z.off1 = (uint32_t)(key & 0xFFFFFFu); z.off2 = z.off1 + 0x1000000u - (uint32_t)((key >> 24) & 0x1FFFFFFu); }
+	z.len1 = (uint16_t)(v >> 18); z.len2 = (uint16_t)((v >> 2) & 0xFFFFu); z.dir1 = (uint8_t)((v >> 1) & 1u); z.dir2 = (uint8_t)(v & 1u); z.pad = 0;
+	cache[i] = z;
+	if(i && zkey[i - 1] == key) tie[(uint32_t)(key >> (MODE == 0? 48 : 49))] = 1;
+}
+template<int MODE>
+__global__ void k_pair_offsets(const unsigned long long *zkey, unsigned long long T, uint32_t np, unsigned long long *cache_off){
+	uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if(p > np) return;
+	unsigned long long lo = 0, hi = T;
+	while(lo < hi){ unsigned long long mid = (lo + hi) >> 1; if((uint32_t)(zkey[mid] >> (MODE == 0? 48 : 49)) < p) lo = mid + 1; else hi = mid; }
+	cache_off[p] = lo;
 }
 
 struct SeedOut { DevWin *wins; DevZPair *anc; unsigned long long cap_wins, cap_anc; unsigned long long *cur_wins, *cur_anc, *overflow; };
-__global__ void k_p_seed(const unsigned long long *cache_off, uint32_t np, DevZPair *cache, uint8_t *scratch, size_t per, uint32_t F, SeedPar par, SeedOut O, zmo_pairseed_t *seeds){
+__global__ void k_p_seed(const unsigned long long *cache_off, uint32_t np, DevZPair *cache, const uint8_t *tie, const uint32_t *pc, DevReads R, uint8_t *scratch, size_t per, uint32_t F, SeedPar par, SeedOut O, zmo_pairseed_t *seeds){
 	uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	if(p >= np) return;
 	const unsigned long long c0 = cache_off[p]; const uint32_t n = (uint32_t)(cache_off[p + 1] - c0);
 	zmo_pairseed_t S; S.n_zpair = n; S.ovl[0] = S.ovl[1] = 0; S.win_off[0] = S.win_off[1] = 0; S.n_win[0] = S.n_win[1] = 0;
 	if((unsigned long long)n * par.zsize >= par.ztot){
 		DevZPair *rs = cache + c0;
-		zmo_ref_sort(rs, (size_t)n, GtZPairOff12());
+		/* the list arrives sorted by (off1,off2); only pairs with tied keys need the reference's exact permutation */
+		if(tie[p]){ GtZPairEmit g; g.clen = R.len[pc[p]]; zmo_ref_sort(rs, (size_t)n, g); zmo_ref_sort(rs, (size_t)n, GtZPairOff12()); }
 		uint8_t *scr = scratch + c0 * per + (size_t)64 * p;
 		for(int d = 0; d < 2; d++){
 			PairScratch P = zmo_pair_scratch_carve(scr, n, F); uint32_t nwin = 0; int ovf = 0;
@@ -108,7 +180,7 @@ __global__ void k_p_seed(const unsigned long long *cache_off, uint32_t np, DevZP
 }
 
 /* steps shared by the SW and dot-matrix paths: z-index of the batch's query reads + match lists */
-int seed_prepare(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, SeedWork &W, DevBuf &cache_buf){
+int seed_prepare(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, int mode, SeedWork &W, DevBuf &cache_buf){
 	DevReads R = dev_reads(c);
 	std::vector<uint32_t> uq, pq(np), pc(np); std::unordered_map<uint32_t, uint32_t> qmap;
 	for(uint32_t i = 0; i < np; i++){
@@ -156,30 +228,69 @@ int seed_prepare(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, SeedWork &W, 
 		k_z_slots<<<(unsigned)((Z + 255) / 256), 256, 0, c->stream>>>(k_out, d_flag, d_pos, d_run, Z, d_zoff, d_slots); c->launches++;
 	}
 	k_z_ranges<<<(nuq + 1 + 127) / 128, 128, 0, c->stream>>>(d_zoff, d_pos, nuq, Z, NS, d_slot_beg); c->launches++;
-	/* per-pair slot counters: kc_off (s2 is free again after the sort), counts, match lists */
-	if(c->s2.reserve(((size_t)np + 2) * 32)) return ZMO_ERR_CUDA;
-	unsigned long long *d_ns = c->s2.as<unsigned long long>(), *d_kcoff = d_ns + np + 1, *d_nz = d_kcoff + np + 1, *d_coff = d_nz + np + 1;
-	k_p_ns<<<(np + 127) / 128, 128, 0, c->stream>>>(d_pq, np, d_slot_beg, d_ns); c->launches++;
-	CUDA_TRY(cudaMemsetAsync(d_ns + np, 0, 8, c->stream));
-	CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_ns, d_kcoff, np + 1, c->stream));
-	unsigned long long KC = 0;
-	CUDA_TRY(cudaMemcpyAsync(&KC, d_kcoff + np, 8, cudaMemcpyDeviceToHost, c->stream));
-	CUDA_TRY(cudaStreamSynchronize(c->stream));
-	if(c->s4.reserve(KC + 64)) return ZMO_ERR_CUDA;     /* s4 (vals_in) is free after the sort */
-	uint8_t *d_kc = c->s4.as<uint8_t>();
+	/* ---- match lists, fully parallel: hits per (pair, c-chunk) -> stable sort by (pair, slot) -> rank cap + expansion
+	 * -> sort by the key of the consumer's first sort -> DevZPair lists.  s2: pair chunk table | tie flags,
+	 * s3/s4: keys, s6/arena: values + per-item counters (s7 keeps the z-index). */
+	if(np > (mode? 32768u : 65536u)) return zmo_set_err(ZMO_ERR_ARG, "at most %u pairs per call", mode? 32768u : 65536u);
+	if(c->max_rdlen >= (1u << 24)) return zmo_set_err(ZMO_ERR_ARG, "reads of 2^24 bases or more are not supported (reference limit rdlen:24, wtzmo.c:88)");
+	if(c->s2.reserve(((size_t)np + 2) * 24 + np + 64)) return ZMO_ERR_CUDA;
+	unsigned long long *d_pnch = c->s2.as<unsigned long long>(), *d_pchoff = d_pnch + np + 1, *d_coff = d_pchoff + np + 1; uint8_t *d_tie = (uint8_t*)(d_coff + np + 2);
 	ZIdxView ZV; ZV.slots = d_slots; ZV.slot_beg = d_slot_beg; ZV.zs = d_zs; ZV.zoff = d_zoff;
-	CUDA_TRY(cudaMemsetAsync(d_kc, 0, KC + 1, c->stream));
-	k_p_match<0><<<(np + bs - 1) / bs, bs, 0, c->stream>>>(R, ZV, d_pq, d_pc, np, d_kcoff, d_kc, c->par.zsize, c->par.hz, (uint32_t)c->par.zcut, (uint32_t)c->par.kvar, d_nz, nullptr); c->launches++;
-	CUDA_TRY(cudaMemsetAsync(d_nz + np, 0, 8, c->stream));
-	CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_nz, d_coff, np + 1, c->stream));
-	unsigned long long T = 0;
-	CUDA_TRY(cudaMemcpyAsync(&T, d_coff + np, 8, cudaMemcpyDeviceToHost, c->stream));
+	k_c_nchunks<<<(np + 127) / 128, 128, 0, c->stream>>>(R, d_pc, np, d_pnch); c->launches++;
+	CUDA_TRY(cudaMemsetAsync(d_pnch + np, 0, 8, c->stream));
+	CUDA_TRY(cudaMemsetAsync(d_tie, 0, np, c->stream));
+	CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_pnch, d_pchoff, np + 1, c->stream));
+	unsigned long long NC = 0;
+	CUDA_TRY(cudaMemcpyAsync(&NC, d_pchoff + np, 8, cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
-	if(T >= 0xFFFFFFF0ull) return zmo_set_err(ZMO_ERR_CAPACITY, "pair batch too large (%llu z-mer matches)", T);
-	if(cache_buf.reserve((T + 4) * sizeof(DevZPair))) return ZMO_ERR_CUDA;
-	CUDA_TRY(cudaMemsetAsync(d_kc, 0, KC + 1, c->stream));
-	k_p_match<1><<<(np + bs - 1) / bs, bs, 0, c->stream>>>(R, ZV, d_pq, d_pc, np, d_kcoff, d_kc, c->par.zsize, c->par.hz, (uint32_t)c->par.zcut, (uint32_t)c->par.kvar, d_coff, cache_buf.as<DevZPair>()); c->launches++;
+	if(c->s3.reserve((NC + 2) * 16)) return ZMO_ERR_CUDA;
+	unsigned long long *d_ccnt = c->s3.as<unsigned long long>(), *d_choff = d_ccnt + NC + 1;
+	k_hit<0><<<(unsigned)((NC + 127) / 128), 128, 0, c->stream>>>(R, ZV, d_pq, d_pc, np, d_pchoff, NC, c->par.zsize, c->par.hz, d_ccnt, nullptr, nullptr); c->launches++;
+	CUDA_TRY(cudaMemsetAsync(d_ccnt + NC, 0, 8, c->stream));
+	CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_ccnt, d_choff, (uint64_t)NC + 1, c->stream));
+	unsigned long long NH = 0;
+	CUDA_TRY(cudaMemcpyAsync(&NH, d_choff + NC, 8, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	unsigned long long T = 0;
+	if(NH >= 0xFFFFFFF0ull) return zmo_set_err(ZMO_ERR_CAPACITY, "pair batch too large (%llu z-mer hits)", NH);
+	if(NH){
+		/* hit arrays in the DP arena (idle during seeding): hkey_in | hkey_out | hval_in | hval_out | counts | offsets */
+		if(c->arena.reserve((NH + 2) * 48 + 256)) return ZMO_ERR_CUDA;
+		unsigned long long *hk_in = c->arena.as<unsigned long long>(), *hk_out = hk_in + NH + 1, *hv_in = hk_out + NH + 1, *hv_out = hv_in + NH + 1, *d_hcnt = hv_out + NH + 1, *d_hoff = d_hcnt + NH + 1;
+		k_hit<1><<<(unsigned)((NC + 127) / 128), 128, 0, c->stream>>>(R, ZV, d_pq, d_pc, np, d_pchoff, NC, c->par.zsize, c->par.hz, d_choff, hk_in, hv_in); c->launches++;
+		int pbits = 1; while((1ull << pbits) < np) pbits++;
+		CUB_CALL(c, cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, hk_in, hk_out, hv_in, hv_out, (uint64_t)NH, 0, 32 + pbits, c->stream));
+		/* hk_in / hv_in are free now: expansion counters live there */
+		d_hcnt = hk_in; d_hoff = hv_in;
+		if(mode == 0) k_expand<0, 0><<<(unsigned)((NH + 127) / 128), 128, 0, c->stream>>>(R, ZV, d_pq, d_pc, hk_out, hv_out, NH, (uint32_t)c->par.zcut, (uint32_t)c->par.kvar, d_hcnt, nullptr, nullptr);
+		else k_expand<0, 1><<<(unsigned)((NH + 127) / 128), 128, 0, c->stream>>>(R, ZV, d_pq, d_pc, hk_out, hv_out, NH, (uint32_t)c->par.zcut, (uint32_t)c->par.kvar, d_hcnt, nullptr, nullptr);
+		c->launches++;
+		CUDA_TRY(cudaMemsetAsync(d_hcnt + NH, 0, 8, c->stream));
+		CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_hcnt, d_hoff, (uint64_t)NH + 1, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(&T, d_hoff + NH, 8, cudaMemcpyDeviceToHost, c->stream));
+		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		if(T >= 0xFFFFFFF0ull) return zmo_set_err(ZMO_ERR_CAPACITY, "pair batch too large (%llu z-mer matches)", T);
+		if(T){
+			/* match keys/values: s3 (chunk tables dead) zk_in | zk_out ; s4 zv_in | zv_out */
+			if(c->s3.reserve((T + 2) * 16) || c->s4.reserve((T + 2) * 16) || cache_buf.reserve((T + 4) * sizeof(DevZPair))) return ZMO_ERR_CUDA;
+			unsigned long long *zk_in = c->s3.as<unsigned long long>(), *zk_out = zk_in + T + 1, *zv_in = c->s4.as<unsigned long long>(), *zv_out = zv_in + T + 1;
+			if(mode == 0) k_expand<1, 0><<<(unsigned)((NH + 127) / 128), 128, 0, c->stream>>>(R, ZV, d_pq, d_pc, hk_out, hv_out, NH, (uint32_t)c->par.zcut, (uint32_t)c->par.kvar, d_hoff, zk_in, zv_in);
+			else k_expand<1, 1><<<(unsigned)((NH + 127) / 128), 128, 0, c->stream>>>(R, ZV, d_pq, d_pc, hk_out, hv_out, NH, (uint32_t)c->par.zcut, (uint32_t)c->par.kvar, d_hoff, zk_in, zv_in);
+			c->launches++;
+			CUB_CALL(c, cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, zk_in, zk_out, zv_in, zv_out, (uint64_t)T, 0, (mode? 49 : 48) + pbits, c->stream));
+			if(mode == 0){
+				k_unpack<0><<<(unsigned)((T + 255) / 256), 256, 0, c->stream>>>(zk_out, zv_out, T, cache_buf.as<DevZPair>(), d_tie);
+				k_pair_offsets<0><<<(np + 1 + 127) / 128, 128, 0, c->stream>>>(zk_out, T, np, d_coff);
+			} else {
+				k_unpack<1><<<(unsigned)((T + 255) / 256), 256, 0, c->stream>>>(zk_out, zv_out, T, cache_buf.as<DevZPair>(), d_tie);
+				k_pair_offsets<1><<<(np + 1 + 127) / 128, 128, 0, c->stream>>>(zk_out, T, np, d_coff);
+			}
+			c->launches += 2;
+		}
+	}
+	if(T == 0){ if(cache_buf.reserve(64)) return ZMO_ERR_CUDA; CUDA_TRY(cudaMemsetAsync(d_coff, 0, ((size_t)np + 1) * 8, c->stream)); }
 	CUDA_TRY(cudaGetLastError());
+	W.tie = d_tie; W.pc = d_pc;
 	W.T = T; W.cache_off = d_coff; W.cache = cache_buf.as<DevZPair>();
 	c->counters[3] += T;
 	return 0;
@@ -200,13 +311,13 @@ extern "C" int zmo_pair_windows(zmo_ctx *c, int slot, const zmo_pair_t *pairs, u
 	unsigned long long nw = 0, na = 0;
 	for(int attempt = 0; attempt < 4; attempt++){
 		SeedWork W; const uint32_t F = 2u << (2 * attempt); const size_t per = zmo_pair_scratch_per(F);     /* 2, 8, 32, 128 */
-		if(int rc = seed_prepare(c, pairs, np, W, c->s5)) return rc;      /* match lists live in s5 */
+		if(int rc = seed_prepare(c, pairs, np, 0, W, c->s5)) return rc;      /* match lists live in s5 */
 		const unsigned long long T = W.T;
 		const unsigned long long cap_w = (attempt? 2 * T * F : T / 2) + 64, cap_a = 2 * T * F + 64;
-		if(c->s3.reserve(T * per + (size_t)64 * np + 256) || SL.wins.reserve(cap_w * sizeof(DevWin)) || SL.anchors.reserve(cap_a * sizeof(DevZPair)) || SL.seeds.reserve((size_t)np * sizeof(zmo_pairseed_t)) || SL.pairs.reserve((size_t)np * sizeof(zmo_pair_t))) return ZMO_ERR_CUDA;
+		if(c->s6.reserve(T * per + (size_t)64 * np + 256) || SL.wins.reserve(cap_w * sizeof(DevWin)) || SL.anchors.reserve(cap_a * sizeof(DevZPair)) || SL.seeds.reserve((size_t)np * sizeof(zmo_pairseed_t)) || SL.pairs.reserve((size_t)np * sizeof(zmo_pair_t))) return ZMO_ERR_CUDA;
 		CUDA_TRY(cudaMemsetAsync(ctr + CTR_N1, 0, 24, c->stream));
 		SeedOut O; O.wins = SL.wins.as<DevWin>(); O.anc = SL.anchors.as<DevZPair>(); O.cap_wins = cap_w; O.cap_anc = cap_a; O.cur_wins = ctr + CTR_N1; O.cur_anc = ctr + CTR_N2; O.overflow = ctr + CTR_N3;
-		k_p_seed<<<(np + 31) / 32, 32, 0, c->stream>>>(W.cache_off, np, W.cache, c->s3.as<uint8_t>(), per, F, par, O, SL.seeds.as<zmo_pairseed_t>()); c->launches++;
+		k_p_seed<<<(np + 31) / 32, 32, 0, c->stream>>>(W.cache_off, np, W.cache, W.tie, W.pc, dev_reads(c), c->s6.as<uint8_t>(), per, F, par, O, SL.seeds.as<zmo_pairseed_t>()); c->launches++;
 		CUDA_TRY(cudaGetLastError());
 		unsigned long long h[3];
 		CUDA_TRY(cudaMemcpyAsync(h, ctr + CTR_N1, 24, cudaMemcpyDeviceToHost, c->stream));

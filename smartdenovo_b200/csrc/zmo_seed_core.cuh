@@ -137,6 +137,10 @@ template<class T, class GT> ZMO_HDN void zmo_ref_sort(T *rs, size_t n, GT gt){
 }
 
 struct GtZPairOff12 { ZMO_HDM bool operator()(const DevZPair &a, const DevZPair &b) const { return (((int64_t)a.off1 << 32) | a.off2) > (((int64_t)b.off1 << 32) | b.off2); } };
+/* reference emission order of the match list (c position major, then q occurrence): used to rebuild the input of
+ * the exact sort for lists with tied keys.  c position = off2 on the same strand, clen-off2-len2 on the other. */
+struct GtZPairEmit { uint32_t clen; ZMO_HDM uint64_t k(const DevZPair &a) const { const uint32_t cp = (a.dir1 ^ a.dir2)? clen - a.off2 - a.len2 : a.off2; return ((uint64_t)cp << 32) | a.off1; }
+	ZMO_HDM bool operator()(const DevZPair &a, const DevZPair &b) const { return k(a) > k(b); } };
 struct GtZPairOff1 { ZMO_HDM bool operator()(const DevZPair &a, const DevZPair &b) const { return a.off1 > b.off1; } };
 struct GtIdxOff2 { const DevZPair *rs; ZMO_HDM bool operator()(uint32_t a, uint32_t b) const { return rs[a].off2 > rs[b].off2; } };
 

@@ -81,7 +81,7 @@ extern "C" int sim_pair_dotmatrix(const uint8_t *pb1, int alen, const uint8_t *p
 	zmo_zmatch(cw.data(), (uint32_t)blen, slots.data(), (uint32_t)slots.size(), zs.data(), kc.data(), zsize, hz, (uint32_t)zcut, (uint32_t)kvar, cache.data());
 	DotPar par; par.xvar = xvar; par.yvar = yvar; par.min_block_len = min_block_len; par.max_overhang = max_overhang; par.deviation_penalty = dev_pen; par.gap_penalty = gap_pen;
 	std::vector<uint8_t> scr(zmo_dot_scratch_bytes(n));
-	DotRes r = zmo_dot_pair(cache.data(), n, alen, blen, par, scr.data());
+	DotRes r = zmo_dot_pair(cache.data(), n, alen, blen, par, scr.data(), 0);
 	out[0] = r.score; out[1] = r.qb; out[2] = r.qe; out[3] = r.tb; out[4] = r.te; out[5] = r.strand;
 	return (int)n;
 }
