@@ -62,6 +62,10 @@ void zmo_stage_ms(const zmo_ctx *ctx, double out[8]);
  * [2]=cells gap global, [3]=z-mer match pairs, [4]=postings visited, [5]=bytes H2D, [6]=bytes D2H */
 void zmo_counters(const zmo_ctx *ctx, uint64_t out[8]);
 
+/* page-locked host memory for result buffers (records, CIGARs): lets the D2H copies run at PCIe speed */
+void *zmo_host_alloc(size_t bytes);
+void  zmo_host_free(void *p);
+
 /* ---- read store: replaces BaseBank + pbread_t (dna.h:318-410, wtzmo.c:87-90,207-215) -------- */
 /* bank: the reference's packed layout, 32 bases per uint64, base i of the bank at bits
  * ((~i)&31)*2 of word i>>5.  rdoff/rdlen in bases (after -b clipping).  Reads are re-packed on the

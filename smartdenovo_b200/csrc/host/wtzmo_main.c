@@ -324,6 +324,8 @@ typedef struct {
 	FILE *out; char *obuf; size_t obuf_n, obuf_cap;
 	double t_dev, t_replay, t_write;
 	int batch_reads, batch_pairs;
+	/* page-locked result buffers reused across batches */
+	zmo_record_t *pin_recs; size_t pin_recs_cap; u32 *pin_cig; size_t pin_cig_cap;
 } wz_t;
 
 static double now_s(void){ struct timeval tv; gettimeofday(&tv, NULL); return tv.tv_sec + 1e-6 * tv.tv_usec; }
@@ -548,7 +550,7 @@ static void batch_free(batch_t *b){
 	size_t i;
 	for(i=0;i<b->reads.n;i++){ vec_free(b->reads.a[i].cands_raw); vec_free(b->reads.a[i].cand_pair); }
 	vec_free(b->reads); vec_free(b->pairs); vec_free(b->tasks);
-	free(b->seeds); free(b->wins); free(b->task_of_pair); free(b->recs); free(b->cigars); free(b->dots);
+	free(b->seeds); free(b->wins); free(b->task_of_pair); free(b->dots);     /* recs / cigars live in the session's pinned buffers */
 	memset(b, 0, sizeof(*b));
 }
 
@@ -593,10 +595,15 @@ static void batch_compute(wz_t *z, batch_t *b){
 	}
 	if(b->tasks.n == 0) return;
 	z->n_tasks += b->tasks.n;
-	b->recs = malloc(b->tasks.n * sizeof(zmo_record_t));
-	b->cig_cap = 4096 * b->tasks.n + (1u << 16); b->cigars = malloc(b->cig_cap * 4);
+	if(b->tasks.n > z->pin_recs_cap){ zmo_host_free(z->pin_recs); z->pin_recs_cap = b->tasks.n * 2 + 1024; z->pin_recs = zmo_host_alloc(z->pin_recs_cap * sizeof(zmo_record_t)); if(!z->pin_recs) die_zmo("zmo_host_alloc"); }
+	if(z->pin_cig_cap < 4096 * b->tasks.n + (1u << 16)){ zmo_host_free(z->pin_cig); z->pin_cig_cap = 4096 * b->tasks.n * 2 + (1u << 20); z->pin_cig = zmo_host_alloc(z->pin_cig_cap * 4); if(!z->pin_cig) die_zmo("zmo_host_alloc"); }
+	b->recs = z->pin_recs; b->cigars = z->pin_cig; b->cig_cap = z->pin_cig_cap;
 	rc = zmo_pair_align(z->ctx, 0, b->tasks.a, (u32)b->tasks.n, b->recs, b->cigars, b->cig_cap, &need);
-	if(rc == ZMO_ERR_CAPACITY && need > b->cig_cap){ b->cig_cap = need + 16; b->cigars = realloc(b->cigars, b->cig_cap * 4); rc = zmo_pair_align(z->ctx, 0, b->tasks.a, (u32)b->tasks.n, b->recs, b->cigars, b->cig_cap, &need); }
+	if(rc == ZMO_ERR_CAPACITY && need > b->cig_cap){
+		zmo_host_free(z->pin_cig); z->pin_cig_cap = need + need / 4 + 16; z->pin_cig = zmo_host_alloc(z->pin_cig_cap * 4); if(!z->pin_cig) die_zmo("zmo_host_alloc");
+		b->cigars = z->pin_cig; b->cig_cap = z->pin_cig_cap;
+		rc = zmo_pair_align(z->ctx, 0, b->tasks.a, (u32)b->tasks.n, b->recs, b->cigars, b->cig_cap, &need);
+	}
 	if(rc) die_zmo("zmo_pair_align");
 }
 

@@ -16,6 +16,8 @@
 
 int zmo_launch_ext(zmo_ctx *c, int mode, int cls, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells);
 int zmo_launch_glb(zmo_ctx *c, bool wide, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells);
+int zmo_launch_ext_on(zmo_ctx *c, cudaStream_t st, int wk, int mode, int cls, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells);
+int zmo_launch_glb_on(zmo_ctx *c, cudaStream_t st, int wk, bool wide, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells);
 
 #define CUB_CALL(c, call_expr) do { size_t _tb = 0; void *_tp = nullptr; { auto d_temp = _tp; size_t &temp_bytes = _tb; CUDA_TRY(call_expr); } \
 	if((c)->cubtmp.reserve(_tb + 256)) return ZMO_ERR_CUDA; { void *d_temp = (c)->cubtmp.p; size_t &temp_bytes = _tb; CUDA_TRY(call_expr); } (c)->launches++; } while(0)
@@ -161,6 +163,11 @@ __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *ite
 	}
 }
 
+__global__ void k_job_keys(const DPJob *jobs, uint32_t n, uint32_t *keys, uint32_t *idx){
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i < n){ keys[i] = jobs[i].est; idx[i] = i; }
+}
+
 /* per-task bookkeeping shared by the plan/finish kernels */
 struct TaskState { int ok; int first, last; int left_job, right_job; int gap0, ngap; int score, tb, te, qb, qe, aln, mat, mis, ins, del; unsigned long long cig_need; };
 /* six job lists: extension classes 0..3 (warp, CTA 64/128/256), gap-fill warp (4) and CTA (5); a job's index in the
@@ -195,6 +202,7 @@ __global__ void k_plan(const AlnTask *tasks, uint32_t nt, const zmo_pair_t *pair
 			J.q_rid = pr.cid; J.q_start = q.start; J.q_step = q.step; J.q_comp = q.comp? 1 : 0; J.qlen = gq;
 			J.t_rid = pr.qid; J.t_start = tv.start; J.t_step = tv.step; J.t_comp = 0; J.tlen = gt;
 			J.init = 0; J.Wp = A.w; J.Wmax = A.W; J.cig_cap = (uint32_t)(gq + gt + 4);
+			{ const unsigned long long e = ((unsigned long long)gt * (unsigned long long)(gq < 2 * A.w + 1? gq : 2 * A.w + 1)) >> 8; J.est = e > 0xFFFFFFFFull? 0xFFFFFFFFu : (uint32_t)e; }
 			int w = A.w; const int dl = gq > gt? gq - gt : gt - gq; while(w < dl) w <<= 1;
 			const int bw = gq < 2 * w + 1? gq : 2 * w + 1;
 			const bool wide = bw > 32 * 7 * 2;
@@ -218,6 +226,7 @@ __global__ void k_plan(const AlnTask *tasks, uint32_t nt, const zmo_pair_t *pair
 			J.init = r0.score + 100 * A.P.M; J.Wp = -A.ew; J.cig_cap = (uint32_t)(r0.qb + r0.tb + 4);
 			const int init = J.init < 0? 0 : J.init;
 			const BandDims d = band_dims(J.qlen, J.tlen, init, J.Wp, A.P);
+			{ const unsigned long long e = ((unsigned long long)d.ql * (unsigned long long)d.ncol) >> 8; J.est = e > 0xFFFFFFFFull? 0xFFFFFFFFu : (uint32_t)e; }
 			{ const int cls = ext_class(d.ncol); S.left_job = push_job(L.list[cls], L.cnt[cls], L.cap, L.res_base[cls], J, ext_scratch_words_cls(d, cls), L); }
 		}
 	}
@@ -267,6 +276,7 @@ __global__ void k_plan2(const AlnTask *tasks, uint32_t nt, const zmo_pair_t *pai
 		J.init = S.score; J.Wp = -A.ew; J.cig_cap = (uint32_t)(J.qlen + J.tlen + 4);
 		const int init = J.init < 0? 0 : J.init;
 		const BandDims d = band_dims(J.qlen, J.tlen, init, J.Wp, A.P);
+		{ const unsigned long long e = ((unsigned long long)d.ql * (unsigned long long)d.ncol) >> 8; J.est = e > 0xFFFFFFFFull? 0xFFFFFFFFu : (uint32_t)e; }
 		{ const int cls = ext_class(d.ncol); S.right_job = push_job(L.list[cls], L.cnt[cls], L.cap, L.res_base[cls], J, ext_scratch_words_cls(d, cls), L); }
 	}
 	ts[t] = S;
@@ -308,6 +318,45 @@ __global__ void k_finish(const AlnTask *tasks, uint32_t nt, const DevReg *regs, 
 	rec.ok = 1; rec.score = S.score; rec.tb = S.tb; rec.te = S.te; rec.qb = S.qb; rec.qe = S.qe; rec.aln = S.aln; rec.mat = S.mat; rec.mis = S.mis; rec.ins = S.ins; rec.del = S.del;
 	rec.cigar_off = out_off[t]; rec.n_cigar = n;
 	recs[t] = rec;
+}
+
+/* Run the job lists [first[k], n[k]) of all six executor classes CONCURRENTLY (one auxiliary stream per class, forked from
+ * and joined back to the context stream), each work queue ordered longest-job-first to cut the tail. */
+static int run_dp_lists(zmo_ctx *c, const JobLists &L, const uint32_t *n, const uint32_t *first, uint32_t *arena, uint32_t *cig_arena, DPRes *d_res){
+	uint32_t tot = 0, cnt[6], off[6];
+	for(int k = 0; k < 6; k++){ off[k] = first? first[k] : 0; cnt[k] = n[k] - off[k]; tot += cnt[k]; }
+	if(tot == 0) return 0;
+	/* order arrays: keys | idx | sorted keys | sorted idx per class, in s0's tail is not safe -> dedicated buffer h-less: reuse cubtmp after sizing */
+	DevBuf &ob = c->s5;      /* s5 is free until k_finish */
+	if(ob.reserve((size_t)tot * 16 + 256)) return ZMO_ERR_CUDA;
+	uint32_t *base = ob.as<uint32_t>(); uint32_t *order[6]; size_t pos = 0;
+	for(int k = 0; k < 6; k++){
+		order[k] = nullptr;
+		if(cnt[k] < 2){ continue; }
+		uint32_t *keys = base + pos, *idx = keys + cnt[k], *skeys = idx + cnt[k], *sidx = skeys + cnt[k]; pos += (size_t)cnt[k] * 4;
+		k_job_keys<<<(cnt[k] + 255) / 256, 256, 0, c->stream>>>(L.list[k] + off[k], cnt[k], keys, idx); c->launches++;
+		CUB_CALL(c, cub::DeviceRadixSort::SortPairsDescending(d_temp, temp_bytes, keys, skeys, idx, sidx, (int)cnt[k], 0, 32, c->stream));
+		order[k] = sidx;
+	}
+	CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
+	for(int k = 0; k < 6; k++){
+		if(cnt[k] == 0) continue;
+		CUDA_TRY(cudaStreamWaitEvent(c->aux[k], c->ev_fork, 0));
+		CUDA_TRY(cudaEventRecord(c->ev_a0[k], c->aux[k]));
+		int rc;
+		if(k < 4) rc = zmo_launch_ext_on(c, c->aux[k], CTR_WORKK + k, 1, k, L.list[k] + off[k], order[k], cnt[k], arena, cig_arena, d_res, CTR_CELLS_EXT);
+		else rc = zmo_launch_glb_on(c, c->aux[k], CTR_WORKK + k, k == 5, L.list[k] + off[k], order[k], cnt[k], arena, cig_arena, d_res, CTR_CELLS_GAP);
+		if(rc) return rc;
+		CUDA_TRY(cudaEventRecord(c->ev_a1[k], c->aux[k]));
+		CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_a1[k], 0));
+	}
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	for(int k = 0; k < 6; k++){
+		if(cnt[k] == 0) continue;
+		float ms = 0; cudaEventElapsedTime(&ms, c->ev_a0[k], c->ev_a1[k]);
+		c->stage_ms[k < 4? ST_EXT : ST_GAP] += ms;
+	}
+	return 0;
 }
 
 /* res index -> position in the concatenated job array [ext_w | ext_n | glb_w | glb_n] is the identity by construction */
@@ -395,15 +444,7 @@ extern "C" int zmo_pair_align(zmo_ctx *c, int slot, const zmo_task_t *tasks, uin
 			continue;
 		}
 		uint32_t n1[6]; for(int k = 0; k < 6; k++) n1[k] = (uint32_t)h[CTR_JOBS + k];
-		{
-			StageTimer tm(c, ST_EXT);
-			for(int k = 3; k >= 0; k--) if(zmo_launch_ext(c, 1, k, L.list[k], nullptr, n1[k], arena, cig_arena, d_res, CTR_CELLS_EXT)) return ZMO_ERR_CUDA;
-		}
-		{
-			StageTimer tm(c, ST_GAP);
-			if(zmo_launch_glb(c, true, L.list[5], nullptr, n1[5], arena, cig_arena, d_res, CTR_CELLS_GAP)) return ZMO_ERR_CUDA;
-			if(zmo_launch_glb(c, false, L.list[4], nullptr, n1[4], arena, cig_arena, d_res, CTR_CELLS_GAP)) return ZMO_ERR_CUDA;
-		}
+		if(int rc = run_dp_lists(c, L, n1, nullptr, arena, cig_arena, d_res)) return rc;
 		/* plan2: right extensions appended to the same extension lists */
 		k_plan2<<<(nt + 63) / 64, 64, 0, c->stream>>>(d_tasks, nt, SL.pairs.as<zmo_pair_t>(), d_regs, d_res, R, A, L, d_ts); c->launches++;
 		CUDA_TRY(cudaMemcpyAsync(h, ctr, CTR_TOTAL * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -414,8 +455,9 @@ extern "C" int zmo_pair_align(zmo_ctx *c, int slot, const zmo_task_t *tasks, uin
 			continue;
 		}
 		{
-			StageTimer tm(c, ST_EXT);
-			for(int k = 3; k >= 0; k--){ const uint32_t n2 = (uint32_t)h[CTR_JOBS + k]; if(zmo_launch_ext(c, 1, k, L.list[k] + n1[k], nullptr, n2 - n1[k], arena, cig_arena, d_res, CTR_CELLS_EXT)) return ZMO_ERR_CUDA; }
+			uint32_t n2[6]; for(int k = 0; k < 6; k++) n2[k] = (uint32_t)h[CTR_JOBS + k];
+			n2[4] = n1[4]; n2[5] = n1[5];      /* no new gap jobs in the second phase */
+			if(int rc = run_dp_lists(c, L, n2, n1, arena, cig_arena, d_res)) return rc;
 		}
 		/* final sizes, offsets, stitched CIGARs */
 		unsigned long long *d_need = c->s7.as<unsigned long long>(), *d_ooff = d_need + nt + 1;

@@ -26,7 +26,8 @@ extern "C" int zmo_ctx_create(zmo_ctx **out, int device, const zmo_params_t *par
 	zmo_ctx *c = new zmo_ctx();
 	c->device = device; c->n_sm = prop.multiProcessorCount; c->par = *par;
 	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-	CUDA_TRY(cudaEventCreate(&c->ev0)); CUDA_TRY(cudaEventCreate(&c->ev1));
+	CUDA_TRY(cudaEventCreate(&c->ev0)); CUDA_TRY(cudaEventCreate(&c->ev1)); CUDA_TRY(cudaEventCreate(&c->ev_fork));
+	for(int k = 0; k < 6; k++){ CUDA_TRY(cudaStreamCreateWithFlags(&c->aux[k], cudaStreamNonBlocking)); CUDA_TRY(cudaEventCreate(&c->ev_a0[k])); CUDA_TRY(cudaEventCreate(&c->ev_a1[k])); }
 	if(c->d_ctr.reserve(CTR_TOTAL * 8)) { delete c; return ZMO_ERR_CUDA; }
 	CUDA_TRY(cudaMemsetAsync(c->d_ctr.p, 0, CTR_TOTAL * 8, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -42,9 +43,13 @@ extern "C" void zmo_ctx_destroy(zmo_ctx *c){
 	for(DevBuf *b : bufs) b->release();
 	for(int s = 0; s < 2; s++){ c->slot[s].pairs.release(); c->slot[s].seeds.release(); c->slot[s].wins.release(); c->slot[s].anchors.release(); }
 	c->h0.release(); c->h1.release(); c->h2.release();
-	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream);
+	for(int k = 0; k < 6; k++){ if(c->aux[k]) cudaStreamDestroy(c->aux[k]); if(c->ev_a0[k]) cudaEventDestroy(c->ev_a0[k]); if(c->ev_a1[k]) cudaEventDestroy(c->ev_a1[k]); }
+	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_fork); cudaStreamDestroy(c->stream);
 	delete c;
 }
+
+extern "C" void *zmo_host_alloc(size_t bytes){ void *p = nullptr; if(cudaHostAlloc(&p, bytes? bytes : 1, cudaHostAllocDefault) != cudaSuccess){ zmo_set_err(ZMO_ERR_CUDA, "cudaHostAlloc(%zu) failed", bytes); return nullptr; } return p; }
+extern "C" void zmo_host_free(void *p){ if(p) cudaFreeHost(p); }
 
 extern "C" uint64_t zmo_kernel_launches(const zmo_ctx *c){ return c? c->launches : 0; }
 extern "C" void zmo_stage_ms(const zmo_ctx *c, double out[8]){ for(int i = 0; i < 8; i++) out[i] = c? c->stage_ms[i] : 0; }

@@ -68,6 +68,8 @@ struct zmo_ctx {
 	zmo_params_t par;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaStream_t aux[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};     /* concurrent DP executor classes */
+	cudaEvent_t ev_fork = nullptr, ev_a0[6] = {nullptr}, ev_a1[6] = {nullptr};
 	double stage_ms[ST_N] = {0};
 	uint64_t launches = 0;
 	uint64_t counters[8] = {0};
@@ -104,4 +106,4 @@ struct DevReads { const uint32_t *words; const uint64_t *woff; const uint32_t *l
 static inline DevReads dev_reads(const zmo_ctx *c){ DevReads r; r.words = c->rd_words.as<uint32_t>(); r.woff = c->rd_woff.as<uint64_t>(); r.len = c->rd_len.as<uint32_t>(); r.n = c->n_reads; return r; }
 
 /* indices into the device counter block d_ctr (uint64 each) */
-enum { CTR_CELLS_EXT = 0, CTR_CELLS_WIN, CTR_CELLS_GAP, CTR_ZPAIRS, CTR_POSTINGS, CTR_ARENA = 8, CTR_WORK = 9, CTR_OVERFLOW = 10, CTR_N1 = 11, CTR_N2 = 12, CTR_N3 = 13, CTR_N4 = 14, CTR_N5 = 15, CTR_CIG = 16, CTR_JOBS = 17 /* ..22 */, CTR_TOTAL = 32 };
+enum { CTR_CELLS_EXT = 0, CTR_CELLS_WIN, CTR_CELLS_GAP, CTR_ZPAIRS, CTR_POSTINGS, CTR_ARENA = 8, CTR_WORK = 9, CTR_OVERFLOW = 10, CTR_N1 = 11, CTR_N2 = 12, CTR_N3 = 13, CTR_N4 = 14, CTR_N5 = 15, CTR_CIG = 16, CTR_JOBS = 17 /* ..22 */, CTR_WORKK = 23 /* ..28 */, CTR_TOTAL = 32 };

@@ -102,42 +102,48 @@ __global__ void __launch_bounds__(EXT_NT) k_glb_cta(const DPJob *jobs, const uin
 static DPPar dp_par(const zmo_ctx *c){ DPPar P; P.M = c->par.M; P.X = c->par.X; P.I = c->par.O; P.D = c->par.O; P.E = c->par.E; P.T = c->par.T; return P; }
 
 /* ---- launch helpers used by the API and the pipeline --------------------------------------- */
-template<int NT> static void launch_ext_cta(zmo_ctx *c, int mode, int grid, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, DevReads R, DPPar P, uint32_t *arena, uint32_t *cig, DPRes *d_res, unsigned long long *ctr, int ctr_cells){
-	if(mode == 1) k_ext_cta<NT, 1><<<grid, NT, 0, c->stream>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, CTR_WORK, ctr_cells);
-	else k_ext_cta<NT, 0><<<grid, NT, 0, c->stream>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, CTR_WORK, ctr_cells);
+template<int NT> static void launch_ext_cta(cudaStream_t st, int wk, int mode, int grid, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, DevReads R, DPPar P, uint32_t *arena, uint32_t *cig, DPRes *d_res, unsigned long long *ctr, int ctr_cells){
+	if(mode == 1) k_ext_cta<NT, 1><<<grid, NT, 0, st>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, wk, ctr_cells);
+	else k_ext_cta<NT, 0><<<grid, NT, 0, st>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, wk, ctr_cells);
 }
 /* cls: 0 = warp executor (band <= 224), 1/2/3 = CTA of 64/128/256 threads */
-int zmo_launch_ext(zmo_ctx *c, int mode, int cls, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells){
+int zmo_launch_ext_on(zmo_ctx *c, cudaStream_t st, int wk, int mode, int cls, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells){
 	if(n == 0) return 0;
 	unsigned long long *ctr = c->d_ctr.as<unsigned long long>();
-	CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORK, 0, 8, c->stream));
+	CUDA_TRY(cudaMemsetAsync(ctr + wk, 0, 8, st));
 	DevReads R = dev_reads(c); DPPar P = dp_par(c);
 	if(cls == 0){
 		int grid = (int)std::min<uint64_t>((n + WRP_PER_CTA - 1) / WRP_PER_CTA, (uint64_t)c->n_sm * 8);
-		if(mode == 1) k_ext_warp<1><<<grid, 32 * WRP_PER_CTA, 0, c->stream>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, CTR_WORK, ctr_cells);
-		else k_ext_warp<0><<<grid, 32 * WRP_PER_CTA, 0, c->stream>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, CTR_WORK, ctr_cells);
-	} else if(cls == 1) launch_ext_cta<64>(c, mode, (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 10), d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, ctr_cells);
-	else if(cls == 2) launch_ext_cta<128>(c, mode, (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 6), d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, ctr_cells);
-	else launch_ext_cta<256>(c, mode, (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 3), d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, ctr_cells);
+		if(mode == 1) k_ext_warp<1><<<grid, 32 * WRP_PER_CTA, 0, st>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, wk, ctr_cells);
+		else k_ext_warp<0><<<grid, 32 * WRP_PER_CTA, 0, st>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, wk, ctr_cells);
+	} else if(cls == 1) launch_ext_cta<64>(st, wk, mode, (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 10), d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, ctr_cells);
+	else if(cls == 2) launch_ext_cta<128>(st, wk, mode, (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 6), d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, ctr_cells);
+	else launch_ext_cta<256>(st, wk, mode, (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 3), d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, ctr_cells);
+	c->launches++;
+	CUDA_TRY(cudaGetLastError());
+	return 0;
+}
+int zmo_launch_ext(zmo_ctx *c, int mode, int cls, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells){
+	return zmo_launch_ext_on(c, c->stream, CTR_WORK, mode, cls, d_jobs, d_order, n, arena, cig, d_res, ctr_cells);
+}
+int zmo_launch_glb_on(zmo_ctx *c, cudaStream_t st, int wk, bool wide, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells){
+	if(n == 0) return 0;
+	unsigned long long *ctr = c->d_ctr.as<unsigned long long>();
+	CUDA_TRY(cudaMemsetAsync(ctr + wk, 0, 8, st));
+	DevReads R = dev_reads(c); DPPar P = dp_par(c);
+	if(wide){
+		int grid = (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 4);
+		k_glb_cta<<<grid, EXT_NT, 0, st>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, wk, ctr_cells);
+	} else {
+		int grid = (int)std::min<uint64_t>((n + WRP_PER_CTA - 1) / WRP_PER_CTA, (uint64_t)c->n_sm * 8);
+		k_glb_warp<<<grid, 32 * WRP_PER_CTA, 0, st>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, wk, ctr_cells);
+	}
 	c->launches++;
 	CUDA_TRY(cudaGetLastError());
 	return 0;
 }
 int zmo_launch_glb(zmo_ctx *c, bool wide, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells){
-	if(n == 0) return 0;
-	unsigned long long *ctr = c->d_ctr.as<unsigned long long>();
-	CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORK, 0, 8, c->stream));
-	DevReads R = dev_reads(c); DPPar P = dp_par(c);
-	if(wide){
-		int grid = (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 4);
-		k_glb_cta<<<grid, EXT_NT, 0, c->stream>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, CTR_WORK, ctr_cells);
-	} else {
-		int grid = (int)std::min<uint64_t>((n + WRP_PER_CTA - 1) / WRP_PER_CTA, (uint64_t)c->n_sm * 8);
-		k_glb_warp<<<grid, 32 * WRP_PER_CTA, 0, c->stream>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, CTR_WORK, ctr_cells);
-	}
-	c->launches++;
-	CUDA_TRY(cudaGetLastError());
-	return 0;
+	return zmo_launch_glb_on(c, c->stream, CTR_WORK, wide, d_jobs, d_order, n, arena, cig, d_res, ctr_cells);
 }
 
 /* ---- stand-alone operators ------------------------------------------------------------------ */

@@ -16,6 +16,7 @@ struct DPJob {
 	unsigned long long cig_off;   /* word offset in the cigar arena */
 	uint32_t cig_cap;
 	uint32_t out_idx;
+	uint32_t est, pad;            /* estimated DP cells / 256 (saturating): longest-job-first ordering of the work queue */
 };
 struct DPRes { int score, qe, te, mat, mis, ins, del, ncig, w_used, pad; };
 

@@ -143,40 +143,78 @@ __global__ void k_pair_offsets(const unsigned long long *zkey, unsigned long lon
 }
 
 struct SeedOut { DevWin *wins; DevZPair *anc; unsigned long long cap_wins, cap_anc; unsigned long long *cur_wins, *cur_anc, *overflow; };
-__global__ void k_p_seed(const unsigned long long *cache_off, uint32_t np, DevZPair *cache, const uint8_t *tie, const uint32_t *pc, DevReads R, uint8_t *scratch, size_t per, uint32_t F, SeedPar par, SeedOut O, zmo_pairseed_t *seeds){
-	uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-	if(p >= np) return;
-	const unsigned long long c0 = cache_off[p]; const uint32_t n = (uint32_t)(cache_off[p + 1] - c0);
-	zmo_pairseed_t S; S.n_zpair = n; S.ovl[0] = S.ovl[1] = 0; S.win_off[0] = S.win_off[1] = 0; S.n_win[0] = S.n_win[1] = 0;
-	if((unsigned long long)n * par.zsize >= par.ztot){
-		DevZPair *rs = cache + c0;
-		/* the list arrives sorted by (off1,off2); only pairs with tied keys need the reference's exact permutation */
-		if(tie[p]){ GtZPairEmit g; g.clen = R.len[pc[p]]; zmo_ref_sort(rs, (size_t)n, g); zmo_ref_sort(rs, (size_t)n, GtZPairOff12()); }
-		uint8_t *scr = scratch + c0 * per + (size_t)64 * p;
-		for(int d = 0; d < 2; d++){
-			PairScratch P = zmo_pair_scratch_carve(scr, n, F); uint32_t nwin = 0; int ovf = 0;
-			const int ovl = zmo_pair_seed_strand(rs, n, d, par, P, &nwin, &ovf);
-			if(ovf){ atomicAdd(O.overflow, 1ULL); break; }
-			S.ovl[d] = ovl;
-			if((uint32_t)ovl >= par.ztot){
-				uint32_t kw = 0, ka = 0;
-				for(uint32_t j = 0; j < nwin; j++) if(!P.w2[j].closed){ kw++; ka += P.w2[j].anc1 - P.w2[j].anc0; }
-				const unsigned long long w0 = atomicAdd(O.cur_wins, (unsigned long long)kw), a0 = atomicAdd(O.cur_anc, (unsigned long long)ka);
-				if(w0 + kw > O.cap_wins || a0 + ka > O.cap_anc){ atomicAdd(O.overflow, 1ULL); break; }
-				unsigned long long wi = w0, ai = a0;
-				for(uint32_t j = 0; j < nwin; j++){
-					DevWin w = P.w2[j];
-					if(w.closed) continue;
-					const uint32_t na = w.anc1 - w.anc0;
-					for(uint32_t k = 0; k < na; k++) O.anc[ai + k] = P.a2[w.anc0 + k];
-					w.anc0 = (uint32_t)ai; w.anc1 = (uint32_t)(ai + na); ai += na;
-					O.wins[wi++] = w;
+/* Window finding + chaining, one WARP per pair: the lanes stage the pair's match list in shared memory, lane 0 runs the
+ * order-exact serial logic of zmo_seed_core.cuh on it (shared-memory latency instead of global), the lanes copy the
+ * kept windows/anchors out.  Lists that do not fit the shared-memory budget run from global memory. */
+#define PS_WARPS 4
+#define PS_MAXN 2048
+#define PS_MAXW 512
+struct PSSmem { DevZPair rs[PS_MAXN]; uint32_t ts[PS_MAXN]; int32_t as[PS_MAXN]; uint32_t wb[PS_MAXW], we[PS_MAXW], wo[PS_MAXW]; int bc[8]; };
+__global__ void __launch_bounds__(32 * PS_WARPS) k_p_seed(const unsigned long long *cache_off, uint32_t np, DevZPair *cache, const uint8_t *tie, const uint32_t *pc, DevReads R,
+		uint8_t *scratch, size_t per, uint32_t F, SeedPar par, SeedOut O, zmo_pairseed_t *seeds, unsigned long long *work){
+	extern __shared__ __align__(16) uint8_t ps_raw[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	PSSmem &M = ((PSSmem*)ps_raw)[warp];
+	while(1){
+		uint32_t p = 0;
+		if(lane == 0) p = (uint32_t)atomicAdd(work, 1ULL);
+		p = __shfl_sync(0xffffffffu, p, 0);
+		if(p >= np) break;
+		const unsigned long long c0 = cache_off[p]; const uint32_t n = (uint32_t)(cache_off[p + 1] - c0);
+		zmo_pairseed_t S; S.n_zpair = n; S.ovl[0] = S.ovl[1] = 0; S.win_off[0] = S.win_off[1] = 0; S.n_win[0] = S.n_win[1] = 0;
+		if((unsigned long long)n * par.zsize >= par.ztot){
+			DevZPair *rs = cache + c0;
+			/* the list arrives sorted by (off1,off2); only pairs with tied keys need the reference's exact permutation */
+			if(tie[p] && lane == 0){ GtZPairEmit g; g.clen = R.len[pc[p]]; zmo_ref_sort(rs, (size_t)n, g); zmo_ref_sort(rs, (size_t)n, GtZPairOff12()); }
+			__syncwarp();
+			uint8_t *scr = scratch + c0 * per + (size_t)64 * p;
+			const bool in_smem = n <= PS_MAXN;
+			if(in_smem){
+				const uint4 *src = (const uint4*)rs; uint4 *dst = (uint4*)M.rs;
+				for(uint32_t k = lane; k < n; k += 32) dst[k] = src[k];
+			}
+			__syncwarp();
+			for(int d = 0; d < 2; d++){
+				PairScratch P = zmo_pair_scratch_carve(scr, n, F);
+				if(lane == 0){
+					uint32_t nwin = 0; int ovf = 0, ovl = 0;
+					if(in_smem){
+						PairScratch Q = P; Q.ws.ts = M.ts; Q.ws.as = M.as; Q.ws.wb = M.wb; Q.ws.we = M.we; Q.ws.wo = M.wo; Q.ws.capt = PS_MAXN; Q.ws.capw = PS_MAXW;
+						ovl = zmo_pair_seed_strand(M.rs, n, d, par, Q, &nwin, &ovf);
+					}
+					if(!in_smem || ovf == 2) ovl = zmo_pair_seed_strand(rs, n, d, par, P, &nwin, &ovf);      /* global-memory path */
+					M.bc[0] = ovl; M.bc[1] = (int)nwin; M.bc[2] = ovf;
 				}
-				S.win_off[d] = (uint32_t)w0; S.n_win[d] = kw;
+				__syncwarp();
+				const int ovl = M.bc[0]; const uint32_t nwin = (uint32_t)M.bc[1]; const int ovf = M.bc[2];
+				__syncwarp();
+				if(ovf){ if(lane == 0) atomicAdd(O.overflow, 1ULL); break; }
+				S.ovl[d] = ovl;
+				if((uint32_t)ovl >= par.ztot){
+					uint32_t kw = 0, ka = 0;
+					for(uint32_t j = 0; j < nwin; j++) if(!P.w2[j].closed){ kw++; ka += P.w2[j].anc1 - P.w2[j].anc0; }
+					unsigned long long w0 = 0, a0 = 0;
+					if(lane == 0){ w0 = atomicAdd(O.cur_wins, (unsigned long long)kw); a0 = atomicAdd(O.cur_anc, (unsigned long long)ka); }
+					w0 = __shfl_sync(0xffffffffu, w0, 0); a0 = __shfl_sync(0xffffffffu, a0, 0);
+					if(w0 + kw > O.cap_wins || a0 + ka > O.cap_anc){ if(lane == 0) atomicAdd(O.overflow, 1ULL); break; }
+					unsigned long long wi = w0, ai = a0;
+					for(uint32_t j = 0; j < nwin; j++){
+						DevWin w = P.w2[j];
+						if(w.closed) continue;
+						const uint32_t na = w.anc1 - w.anc0;
+						for(uint32_t k = lane; k < na; k += 32) O.anc[ai + k] = P.a2[w.anc0 + k];
+						w.anc0 = (uint32_t)ai; w.anc1 = (uint32_t)(ai + na); ai += na;
+						if(lane == 0) O.wins[wi] = w;
+						wi++;
+					}
+					S.win_off[d] = (uint32_t)w0; S.n_win[d] = kw;
+				}
+				__syncwarp();
 			}
 		}
+		if(lane == 0) seeds[p] = S;
+		__syncwarp();
 	}
-	seeds[p] = S;
 }
 
 /* steps shared by the SW and dot-matrix paths: z-index of the batch's query reads + match lists */
@@ -317,7 +355,13 @@ extern "C" int zmo_pair_windows(zmo_ctx *c, int slot, const zmo_pair_t *pairs, u
 		if(c->s6.reserve(T * per + (size_t)64 * np + 256) || SL.wins.reserve(cap_w * sizeof(DevWin)) || SL.anchors.reserve(cap_a * sizeof(DevZPair)) || SL.seeds.reserve((size_t)np * sizeof(zmo_pairseed_t)) || SL.pairs.reserve((size_t)np * sizeof(zmo_pair_t))) return ZMO_ERR_CUDA;
 		CUDA_TRY(cudaMemsetAsync(ctr + CTR_N1, 0, 24, c->stream));
 		SeedOut O; O.wins = SL.wins.as<DevWin>(); O.anc = SL.anchors.as<DevZPair>(); O.cap_wins = cap_w; O.cap_anc = cap_a; O.cur_wins = ctr + CTR_N1; O.cur_anc = ctr + CTR_N2; O.overflow = ctr + CTR_N3;
-		k_p_seed<<<(np + 31) / 32, 32, 0, c->stream>>>(W.cache_off, np, W.cache, W.tie, W.pc, dev_reads(c), c->s6.as<uint8_t>(), per, F, par, O, SL.seeds.as<zmo_pairseed_t>()); c->launches++;
+		CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORK, 0, 8, c->stream));
+		{
+			static bool attr_set = false;
+			if(!attr_set){ CUDA_TRY(cudaFuncSetAttribute(k_p_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PS_WARPS * sizeof(PSSmem)))); attr_set = true; }
+			const int grid = (int)std::min<uint64_t>((np + PS_WARPS - 1) / PS_WARPS, (uint64_t)c->n_sm);
+			k_p_seed<<<grid, 32 * PS_WARPS, PS_WARPS * sizeof(PSSmem), c->stream>>>(W.cache_off, np, W.cache, W.tie, W.pc, dev_reads(c), c->s6.as<uint8_t>(), per, F, par, O, SL.seeds.as<zmo_pairseed_t>(), ctr + CTR_WORK); c->launches++;
+		}
 		CUDA_TRY(cudaGetLastError());
 		unsigned long long h[3];
 		CUDA_TRY(cudaMemcpyAsync(h, ctr + CTR_N1, 24, cudaMemcpyDeviceToHost, c->stream));

@@ -197,7 +197,7 @@ ZMO_HDN int32_t zmo_median_select(int32_t *rs, int32_t size){
 }
 
 struct SeedPar { uint32_t zsize, kwin, kstep, zovl, ztot; int W; };
-struct WinScratch { uint32_t *ts; int32_t *as; uint32_t *wb, *we, *wo; };     /* each >= n entries */
+struct WinScratch { uint32_t *ts; int32_t *as; uint32_t *wb, *we, *wo; uint32_t capt, capw; };     /* ts/as hold capt entries, wb/we/wo capw */
 struct WinOut { DevWin *wins; uint32_t nwin, capwin; DevZPair *anc; uint32_t nanc, capanc; int overflow; };
 
 #define ZMO_KWIN_MAX_OFFSET_DEV 50
@@ -213,6 +213,7 @@ ZMO_HDN uint32_t zmo_windows_in_span(const DevZPair *rs, int dir, uint32_t beg, 
 	}
 	for(i = beg; i < end; i++) if(!(rs[i].dir1 ^ rs[i].dir2 ^ dir)) n++;
 	if(n * zsize < zovl) return 0;
+	if(n > S.capt){ O.overflow = 2; return 0; }
 	n = 0;
 	for(i = beg; i < end; i++) if(!(rs[i].dir1 ^ rs[i].dir2 ^ dir)) S.ts[n++] = i;
 	{ GtIdxOff2 g; g.rs = rs; zmo_ref_sort(S.ts, (size_t)n, g); }
@@ -230,7 +231,7 @@ ZMO_HDN uint32_t zmo_windows_in_span(const DevZPair *rs, int dir, uint32_t beg, 
 		if(ol >= zovl){
 			if(n2 && ( rs[S.ts[i]].off2 <= rs[S.ts[S.we[n2-1]]].off2 + kwin / 3 || rs[S.ts[j]].off2 <= rs[S.ts[S.wb[n2-1]]].off2 + kwin / 3 )){
 				if(ol > S.wo[n2-1]){ S.wb[n2-1] = j; S.we[n2-1] = i; S.wo[n2-1] = ol; }
-			} else { S.wb[n2] = j; S.we[n2] = i; S.wo[n2] = ol; n2++; }
+			} else { if(n2 >= S.capw){ O.overflow = 2; return 0; } S.wb[n2] = j; S.we[n2] = i; S.wo[n2] = ol; n2++; }
 		}
 	}
 	for(i = 0; i < n2; i++){
@@ -364,6 +365,7 @@ ZMO_HD PairScratch zmo_pair_scratch_carve(uint8_t *base, uint32_t n, uint32_t F)
 	P.ws.wb = (uint32_t*)p; p += (size_t)n * 4;
 	P.ws.we = (uint32_t*)p; p += (size_t)n * 4;
 	P.ws.wo = (uint32_t*)p;
+	P.ws.capt = n; P.ws.capw = n;
 	P.cap = n * F;
 	return P;
 }
