@@ -148,6 +148,7 @@ def main():
 
     import torch
     import torch.distributed as dist
+    from smartdenovo_b200 import dist as zdist
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()        # rank 0 finished build()
@@ -182,7 +183,7 @@ def main():
     def step(idx, reupload):
         if reupload and host.wz_upload(S):
             raise RuntimeError("upload failed")
-        shard = (idx * world + rank) % n_job
+        shard = zdist.shard_of(idx, rank, world, n_job)
         if host.wz_run(S, n_job, shard, out_path.encode()):
             raise RuntimeError("wz_run failed")
         return stats()
@@ -207,28 +208,17 @@ def main():
             rec += st[0]
         gathered = None
         if world > 1:
-            data = torch.frombuffer(bytearray(open(out_path, "rb").read() or b"\n"), dtype=torch.uint8).cuda()
-            sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-            dist.all_gather(sizes, torch.tensor([data.numel()], dtype=torch.int64, device="cuda"))
-            mx = int(max(int(s.item()) for s in sizes))
-            pad = torch.zeros(mx, dtype=torch.uint8, device="cuda")
-            pad[: data.numel()] = data
-            outs = [torch.empty(mx, dtype=torch.uint8, device="cuda") for _ in range(world)]
-            dist.all_gather(outs, pad)
-            gathered = sum(int(s.item()) for s in sizes)
+            parts = zdist.gather_records(open(out_path, "rb").read(), device="cuda")     # one NCCL all-gather of sizes + one of records
+            gathered = sum(len(p) for p in parts)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         wall = time.perf_counter() - t0
         st1 = stats()
-        t = torch.tensor([wall, float(bp), float(rec)], dtype=torch.float64, device="cuda")
         if world > 1:
-            tmax = t.clone()
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            tsum = t.clone()
-            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-            wall, bp, rec = float(tmax[0]), float(tsum[1]), float(tsum[2])
+            wall = zdist.max_over_ranks([wall], device="cuda")[0]
+            bp, rec = zdist.sum_over_ranks([float(bp), float(rec)], device="cuda")
         return dict(wall=wall, bp=bp, rec=rec, st0=st0, st1=st1, h2d=(st1[23] - h2d0) / nsteps, d2h=(st1[24] - d2h0) / nsteps, gathered=gathered)
 
     for w in range(args.warmup):
@@ -270,7 +260,8 @@ def main():
             "gpu_launches": int(launches), "roofline": roof,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
             "last_step_host_ms": {"device_calls": 1e3 * st1[3], "replay_format": 1e3 * st1[4]},
-            "records_per_step": r_val["rec"] / args.steps, "aligned_bp_per_step": r_val["bp"] / args.steps}
+            "records_per_step": r_val["rec"] / args.steps, "aligned_bp_per_step": r_val["bp"] / args.steps,
+            "last_step_work": {"batches": st1[5], "pairs_seeded": st1[6], "pairs_aligned": st1[7], "alignments_consumed": st1[8]}}
     if world > 1:
         line["gathered_bytes"] = r_e2e["gathered"]
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(REPO, "oracle", "_ref", "wtzmo")):

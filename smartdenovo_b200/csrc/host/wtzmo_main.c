@@ -24,6 +24,7 @@
 #include <time.h>
 #include <sys/stat.h>
 #include <sys/time.h>
+#include <pthread.h>
 #include "../../../include/zmo_b200.h"
 
 
@@ -325,7 +326,7 @@ typedef struct {
 	double t_dev, t_replay, t_write;
 	int batch_reads, batch_pairs;
 	/* page-locked result buffers reused across batches */
-	zmo_record_t *pin_recs; size_t pin_recs_cap; u32 *pin_cig; size_t pin_cig_cap;
+	zmo_record_t *pin_recs[2]; size_t pin_recs_cap[2]; u32 *pin_cig[2]; size_t pin_cig_cap[2]; int pin_sel, pipeline;
 } wz_t;
 
 static double now_s(void){ struct timeval tv; gettimeofday(&tv, NULL); return tv.tv_sec + 1e-6 * tv.tv_usec; }
@@ -405,6 +406,7 @@ typedef struct {
 	VEC(zmo_task_t) tasks; u32 *task_of_pair;   /* pair -> task index (dir = chosen strand) or 0xFFFFFFFF */
 	zmo_record_t *recs; u32 *cigars; size_t cig_cap;
 	zmo_dotres_t *dots;
+	int pin_sel;                        /* which pinned result buffer set this batch uses */
 } batch_t;
 
 static u32 read_nbest(const wz_t *z, u32 pbid){
@@ -462,7 +464,7 @@ static void replay_read(wz_t *z, batch_t *b, bread_t *br, u32 bcov, readout_t *r
 	if(br->skip){ fprintf(stderr, "wtzmo(b200): internal error: read %u needed but was skipped at batch build\n", pbid); exit(4); }
 	filter_sort_candidates(z, pbid, &br->cands_raw, &br->cand_pair);
 	if(z->rdhits){ u64v *h = &z->rdhits[pbid]; vec_clear(*h); vec_reserve(*h, br->cands_raw.n + 1); memcpy(h->a, br->cands_raw.a, br->cands_raw.n * 8); h->n = br->cands_raw.n; }
-	windeps = calloc(alen + 1, sizeof(u16)); weights = malloc((alen + 1) * sizeof(float));
+	windeps = calloc(alen + 2, sizeof(u16)); weights = malloc((alen + 1) * sizeof(float));
 	for(i=0;i<br->cands_raw.n;i++){
 		u32 id2 = (u32)(br->cands_raw.a[i] >> 32), pi = br->cand_pair.a[i]; const zmo_pairseed_t *ps; int dir;
 		if(pi == 0xFFFFFFFFU){ fprintf(stderr, "wtzmo(b200): internal error: pair (%u,%u) was not seeded\n", pbid, id2); exit(4); }
@@ -480,9 +482,11 @@ static void replay_read(wz_t *z, batch_t *b, bread_t *br, u32 bcov, readout_t *r
 			}
 			continue;
 		}
+		/* windeps[k]++ over every kept window (wtzmo.c:908) as a difference array; the uint16 wrap of the
+		 * reference counter is reproduced by the mod-2^16 prefix sum below */
 		for(dir=0;dir<2;dir++) for(j=0;j<ps->n_win[dir];j++){
 			const zmo_window_t *w = &b->wins[ps->win_off[dir] + j];
-			for(k=w->beg[0];(int)k<w->end[0];k++) windeps[k] ++;
+			if(w->beg[0] < w->end[0]){ windeps[w->beg[0]] ++; windeps[w->end[0]] --; }
 		}
 		dir = ((u32)ps->ovl[0] & WIN_OVL_MASK) < ((u32)ps->ovl[1] & WIN_OVL_MASK);
 		if(((u32)ps->ovl[dir] & WIN_OVL_MASK) >= (u32)par->ztot){
@@ -491,6 +495,7 @@ static void replay_read(wz_t *z, batch_t *b, bread_t *br, u32 bcov, readout_t *r
 		}
 	}
 	if(!par->dot_matrix){
+		{ u16 acc = 0; for(i=0;i<alen;i++){ acc = (u16)(acc + windeps[i]); windeps[i] = acc; } }
 		/* repeat weighting (wtzmo.c:933-980); float/double expression shapes kept */
 		for(i=0;i<alen;i++)
 			weights[i] = (windeps[i] <= par->wnorm)? 1.0 : ((windeps[i] >= par->wrep)? 0.0 : par->wnorm / (float)windeps[i]);
@@ -554,9 +559,9 @@ static void batch_free(batch_t *b){
 	memset(b, 0, sizeof(*b));
 }
 
-/* device phases B + C for the batch */
-static void batch_compute(wz_t *z, batch_t *b){
-	const zparams_t *par = &z->par; size_t i, k; int rc; u64 need = 0;
+/* pair list of the batch: state dependent, runs on the main thread */
+static void batch_pairs(wz_t *z, batch_t *b){
+	size_t i, k;
 	/* pairs = candidates not closed as of now (the closed set only grows, so this is a superset of what the replay will ask for) */
 	for(i=0;i<b->reads.n;i++){
 		bread_t *r = &b->reads.a[i];
@@ -569,6 +574,11 @@ static void batch_compute(wz_t *z, batch_t *b){
 			{ zmo_pair_t p; p.qid = r->rd_id; p.cid = id2; r->cand_pair.a[k] = (u32)b->pairs.n; vec_push(b->pairs, p); }
 		}
 	}
+}
+
+/* device phases B + C for the batch (touches only the batch and the device context: may run on the worker thread) */
+static void batch_compute(wz_t *z, batch_t *b){
+	const zparams_t *par = &z->par; size_t i; int rc; u64 need = 0;
 	if(b->pairs.n == 0) return;
 	z->n_pairs_seeded += b->pairs.n;
 	if(par->dot_matrix){
@@ -595,17 +605,23 @@ static void batch_compute(wz_t *z, batch_t *b){
 	}
 	if(b->tasks.n == 0) return;
 	z->n_tasks += b->tasks.n;
-	if(b->tasks.n > z->pin_recs_cap){ zmo_host_free(z->pin_recs); z->pin_recs_cap = b->tasks.n * 2 + 1024; z->pin_recs = zmo_host_alloc(z->pin_recs_cap * sizeof(zmo_record_t)); if(!z->pin_recs) die_zmo("zmo_host_alloc"); }
-	if(z->pin_cig_cap < 4096 * b->tasks.n + (1u << 16)){ zmo_host_free(z->pin_cig); z->pin_cig_cap = 4096 * b->tasks.n * 2 + (1u << 20); z->pin_cig = zmo_host_alloc(z->pin_cig_cap * 4); if(!z->pin_cig) die_zmo("zmo_host_alloc"); }
-	b->recs = z->pin_recs; b->cigars = z->pin_cig; b->cig_cap = z->pin_cig_cap;
-	rc = zmo_pair_align(z->ctx, 0, b->tasks.a, (u32)b->tasks.n, b->recs, b->cigars, b->cig_cap, &need);
-	if(rc == ZMO_ERR_CAPACITY && need > b->cig_cap){
-		zmo_host_free(z->pin_cig); z->pin_cig_cap = need + need / 4 + 16; z->pin_cig = zmo_host_alloc(z->pin_cig_cap * 4); if(!z->pin_cig) die_zmo("zmo_host_alloc");
-		b->cigars = z->pin_cig; b->cig_cap = z->pin_cig_cap;
+	{
+		const int ps = b->pin_sel;
+		if(b->tasks.n > z->pin_recs_cap[ps]){ zmo_host_free(z->pin_recs[ps]); z->pin_recs_cap[ps] = b->tasks.n * 2 + 1024; z->pin_recs[ps] = zmo_host_alloc(z->pin_recs_cap[ps] * sizeof(zmo_record_t)); if(!z->pin_recs[ps]) die_zmo("zmo_host_alloc"); }
+		if(z->pin_cig_cap[ps] < 4096 * b->tasks.n + (1u << 16)){ zmo_host_free(z->pin_cig[ps]); z->pin_cig_cap[ps] = 4096 * b->tasks.n * 2 + (1u << 20); z->pin_cig[ps] = zmo_host_alloc(z->pin_cig_cap[ps] * 4); if(!z->pin_cig[ps]) die_zmo("zmo_host_alloc"); }
+		b->recs = z->pin_recs[ps]; b->cigars = z->pin_cig[ps]; b->cig_cap = z->pin_cig_cap[ps];
 		rc = zmo_pair_align(z->ctx, 0, b->tasks.a, (u32)b->tasks.n, b->recs, b->cigars, b->cig_cap, &need);
+		if(rc == ZMO_ERR_CAPACITY && need > b->cig_cap){
+			zmo_host_free(z->pin_cig[ps]); z->pin_cig_cap[ps] = need + need / 4 + 16; z->pin_cig[ps] = zmo_host_alloc(z->pin_cig_cap[ps] * 4); if(!z->pin_cig[ps]) die_zmo("zmo_host_alloc");
+			b->cigars = z->pin_cig[ps]; b->cig_cap = z->pin_cig_cap[ps];
+			rc = zmo_pair_align(z->ctx, 0, b->tasks.a, (u32)b->tasks.n, b->recs, b->cigars, b->cig_cap, &need);
+		}
 	}
 	if(rc) die_zmo("zmo_pair_align");
 }
+
+typedef struct { wz_t *z; batch_t *b; } wk_arg_t;
+static void* batch_compute_thread(void *arg){ wk_arg_t *wa = arg; batch_compute(wa->z, wa->b); free(wa); return NULL; }
 
 static void run_overlap(wz_t *z){
 	const zparams_t *par = &z->par; readset_t *rs = &z->rs; u32 j, beg, end, pbbeg = 0, pbend = 0, i_idx; u64 tot = 0; readout_t ro; zmo_index_stats_t st;
@@ -639,32 +655,51 @@ static void run_overlap(wz_t *z){
 			batch_free(&b);
 		}
 	}
-	for(j=beg;j<end;){
-		batch_t b; size_t i, est_pairs = 0; double t0, t1, t2; memset(&b, 0, sizeof(b));
-		/* collect the next run of reads; masked / job filters are re-checked at replay time */
-		for(;j<end&&b.reads.n<(size_t)z->batch_reads&&est_pairs<(size_t)z->batch_pairs;j++){
-			bread_t r; memset(&r, 0, sizeof(r));
-			if((j % par->n_job) != (u32)par->i_job) continue;
-			if(z->masked[j]) continue;
-			r.rd_id = j; r.skip = z->rdcovs[j] >= read_nbest(z, j);
-			vec_push(b.reads, r);
-			if(!r.skip) est_pairs += 40;
+	{
+		/* software pipeline: while the host replays batch k, a worker thread runs the device phases of batch k+1.
+		 * Batch k+1 is built from the state as of the end of batch k-1, which only makes the speculation set larger. */
+		batch_t *cur = NULL, *nxt = NULL; int sel = 0; double t0, t1;
+		j = beg;
+		while(1){
+			pthread_t th; int have_thread = 0; size_t i;
+			nxt = NULL;
+			if(j < end){
+				size_t est_pairs = 0;
+				nxt = calloc(1, sizeof(batch_t)); nxt->pin_sel = sel; sel ^= 1;
+				for(;j<end&&nxt->reads.n<(size_t)z->batch_reads&&est_pairs<(size_t)z->batch_pairs;j++){
+					bread_t r; memset(&r, 0, sizeof(r));
+					if((j % par->n_job) != (u32)par->i_job) continue;
+					if(z->masked[j]) continue;
+					r.rd_id = j; r.skip = z->rdcovs[j] >= read_nbest(z, j);
+					vec_push(nxt->reads, r);
+					if(!r.skip) est_pairs += 40;
+				}
+				if(nxt->reads.n == 0){ free(nxt); nxt = NULL; }
+			}
+			if(nxt){
+				t0 = now_s();
+				batch_candidates(z, nxt);
+				batch_pairs(z, nxt);
+				if(cur && z->pipeline){ wk_arg_t *wa = malloc(sizeof(wk_arg_t)); wa->z = z; wa->b = nxt; if(pthread_create(&th, NULL, batch_compute_thread, wa) != 0){ free(wa); batch_compute(z, nxt); } else have_thread = 1; }
+				else batch_compute(z, nxt);
+				z->t_dev += now_s() - t0;
+			}
+			if(cur){
+				t1 = now_s();
+				for(i=0;i<cur->reads.n;i++){
+					bread_t *br = &cur->reads.a[i];
+					if(z->masked[br->rd_id]) continue;       /* checked BEFORE the previous read's masks are merged (wtzmo.c:1315 vs 1322) */
+					flush_read(z, &ro, 0);
+					replay_read(z, cur, br, z->rdcovs[br->rd_id], &ro);
+				}
+				flush_read(z, &ro, 1);  /* hits point into this batch's CIGAR buffer: print them before it is reused; masks stay pending */
+				z->t_replay += now_s() - t1; z->n_batches ++;
+				batch_free(cur); free(cur); cur = NULL;
+			}
+			if(have_thread){ double tj = now_s(); pthread_join(th, NULL); z->t_dev += now_s() - tj; }
+			if(nxt == NULL) break;
+			cur = nxt;
 		}
-		if(b.reads.n == 0) break;
-		t0 = now_s();
-		batch_candidates(z, &b);
-		batch_compute(z, &b);
-		t1 = now_s();
-		for(i=0;i<b.reads.n;i++){
-			bread_t *br = &b.reads.a[i];
-			if(z->masked[br->rd_id]) continue;       /* checked BEFORE the previous read's masks are merged (wtzmo.c:1315 vs 1322) */
-			flush_read(z, &ro, 0);
-			replay_read(z, &b, br, z->rdcovs[br->rd_id], &ro);
-		}
-		flush_read(z, &ro, 1);  /* hits point into this batch's CIGAR buffer: print them before it is freed; masks stay pending */
-		t2 = now_s();
-		z->t_dev += t1 - t0; z->t_replay += t2 - t1; z->n_batches ++;
-		batch_free(&b);
 	}
 	flush_read(z, &ro, 0);
 	ob_flush(z);
@@ -812,6 +847,7 @@ wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	if((env = getenv("ZMO_DEVICE"))) S->device = atoi(env); else if((env = getenv("LOCAL_RANK"))) S->device = atoi(env);
 	z->batch_reads = (env = getenv("ZMO_BATCH_READS"))? atoi(env) : 256;
 	z->batch_pairs = (env = getenv("ZMO_BATCH_PAIRS"))? atoi(env) : 16384;
+	z->pipeline = (env = getenv("ZMO_PIPELINE"))? atoi(env) : 1;
 	if(z->batch_reads < 1) z->batch_reads = 1;
 	fprintf(stderr, "[wtzmo-b200] loading long reads\n");
 	rs_load(&z->rs, pbs.a, (int)pbs.n, par->min_rdlen, 0);

@@ -26,6 +26,7 @@ int zmo_launch_glb_on(zmo_ctx *c, cudaStream_t st, int wk, bool wide, const DPJo
 #define WA_CAP 256
 #define WA_SEQW 192
 #define WA_WARPS 4
+#define WA_ZROWS 64      /* extension problems with <= 64 rows keep their traceback in shared memory */
 
 struct WItem { uint32_t task, win; };
 struct DevReg { int score, tb, te, qb, qe, aln, mat, mis, ins, del; unsigned long long cig_off; uint32_t cig_len, kept; };
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *ite
 	__shared__ int s_h[WA_WARPS][3 * WA_CAP];
 	__shared__ uint32_t s_seq[WA_WARPS][WA_SEQW];
 	__shared__ int s_misc[WA_WARPS][16];
+	__shared__ uint32_t s_z[WA_WARPS][WA_ZROWS * 32];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const unsigned gw = blockIdx.x * WA_WARPS + warp;
 	uint32_t *slab = arena + (unsigned long long)gw * slab_words;
@@ -85,12 +87,12 @@ __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *ite
 				const BandDims d = band_dims(qlen, tlen, init, A.w, P);
 				const int rw = band_row_words<32, WA_C>(d.ncol);
 				uint32_t *scr = slab;
-				uint32_t *z = scr; scr += (size_t)max_rows * rw;
+				uint32_t *z = (d.ql <= WA_ZROWS && rw == 32)? s_z[warp] : scr; scr += (size_t)max_rows * rw;
 				int *zb = (int*)scr; scr += max_rows;
 				tmpc = scr; scr += 2 * (size_t)max_rows + 2 * (size_t)A.w + 16;
 				const int qw = (d.ql + 15) >> 4, tw = (d.tl + 15) >> 4;
 				uint32_t *qpk, *tpk;
-				if(qw + tw <= WA_SEQW){ qpk = s_seq[warp]; tpk = qpk + qw; } else { qpk = scr; tpk = scr + qw; }
+				if(qw + tw + 2 <= WA_SEQW){ qpk = s_seq[warp]; tpk = qpk + qw; } else { qpk = scr; tpk = scr + qw; }
 				scr += ((size_t)max_rows >> 3) + ((size_t)A.w >> 3) + 8;
 				BandSmem S2 = S;
 				if(2 * d.W + 3 > WA_CAP){ int cap = 1; while(cap < 2 * d.W + 3) cap <<= 1; S2.H0 = (int*)scr; S2.H1 = S2.H0 + cap; S2.Ev = S2.H1 + cap; S2.cap_mask = cap - 1; }

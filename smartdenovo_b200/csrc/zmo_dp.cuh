@@ -34,13 +34,25 @@ __device__ __forceinline__ uint32_t pk_base(const uint32_t *pk, int k){ return (
 
 template<int NT> __device__ __forceinline__ void ex_sync(){ if(NT == 32) __syncwarp(); else __syncthreads(); }
 
-/* materialise n logical bases of a view as packed words (logical orientation) */
+/* materialise n logical bases of a view as packed words (logical orientation): every output word is cut out of
+ * two source words with a funnel shift; backward views reverse the sixteen 2-bit fields, complemented views
+ * invert them.  Fields past n are garbage and never read.  (Reads carry spare words after their last base.) */
 template<int NT> __device__ __forceinline__ void stage_packed(const SeqView &s, int n, uint32_t *dst, int tid){
-	int nw = (n + 15) >> 4;
+	const int nw = (n + 15) >> 4;
 	for(int wi = tid; wi < nw; wi += NT){
-		uint32_t v = 0; int base = wi << 4, m = n - base; if(m > 16) m = 16;
-		for(int b = 0; b < m; b++) v |= sv_base(s, base + b) << ((15 - b) << 1);
-		dst[wi] = v;
+		const int t0 = wi << 4; uint32_t v;
+		if(s.step == 1){
+			const int a = s.start + t0, i0 = a >> 4, sh = (a & 15) << 1;
+			const uint32_t hi = __ldg(s.w + i0), lo = __ldg(s.w + i0 + 1);
+			v = sh? (hi << sh) | (lo >> (32 - sh)) : hi;
+		} else {
+			const int a = s.start - t0 - 15, i0 = a >> 4, sh = (a & 15) << 1;      /* a may be negative in the last word */
+			const uint32_t hi = i0 >= 0? __ldg(s.w + i0) : 0u, lo = i0 + 1 >= 0? __ldg(s.w + i0 + 1) : 0u;
+			uint32_t u = sh? (hi << sh) | (lo >> (32 - sh)) : hi;
+			u = __brev(u);
+			v = ((u >> 1) & 0x55555555u) | ((u & 0x55555555u) << 1);
+		}
+		dst[wi] = s.comp? ~v : v;
 	}
 }
 
@@ -105,11 +117,14 @@ __device__ void band_extend(const BandSmem &S, const uint32_t *rowpk, int qlen, 
 		const uint32_t qb = pk_base(rowpk, i);
 		int lmax = 0, larg = -1;
 		int chunk = 0;
-		if(tid == 0) zb[i] = jb;
+		if(MODE == 1 && tid == 0) zb[i] = jb;          /* the fixed band start is recomputed by the walker */
 		cells += (unsigned long long)(je > jb? je - jb : 0);
 		for(int cb = jb; cb < je; cb += PC, chunk++){
 			const int j0 = cb + tid * C;
 			int m[C], e[C];
+			/* the thread's C column bases in one 64-bit window (2 shared loads), XORed with the row base: a 2-bit field is 0 on a match */
+			unsigned long long xw = 0; const int xs = 62 - ((j0 & 15) << 1);
+			if(j0 < je){ const int w0 = j0 >> 4; xw = (((unsigned long long)colpk[w0] << 32) | colpk[w0 + 1]) ^ (0x5555555555555555ull * qb); }
 			#pragma unroll
 			for(int k = 0; k < C; k++){
 				const int j = j0 + k;
@@ -121,7 +136,7 @@ __device__ void band_extend(const BandSmem &S, const uint32_t *rowpk, int qlen, 
 						else hd = (j - 1 >= pjb && j - 1 < pje)? Hp[(j - 1) & mask] : ZMO_NEG;
 						ee = (j >= pjb && j < pje)? S.Ev[j & mask] : ZMO_NEG;
 					}
-					m[k] = hd + (pk_base(colpk, j) == qb? P.M : P.X);
+					m[k] = hd + (((xw >> (xs - 2 * k)) & 3ull)? P.X : P.M);
 					e[k] = ee;
 				} else { m[k] = ZMO_BIGNEG; e[k] = ZMO_BIGNEG; }
 			}
@@ -166,18 +181,22 @@ __device__ void band_extend(const BandSmem &S, const uint32_t *rowpk, int qlen, 
 			z[(size_t)i * rw + chunk * NT + tid] = zw;
 			if(tid == NT - 1) S.smisc[1 + ((chunk + 1) & 1)] = f;
 		}
-		/* row arg-max: key = (max h, first/last column) */
-		long long key = ((long long)lmax << 32) | (unsigned)(MODE == 1? (larg < 0? 0 : 0x7FFFFFFF - larg) : larg + 1);
-		#pragma unroll
-		for(int d = 16; d > 0; d >>= 1){ long long o = __shfl_xor_sync(0xffffffffu, key, d); if(o > key) key = o; }
+		/* row arg-max: max h over the row, then the first (shifting band) / last (fixed band) column reaching it */
+		int rowmax = __reduce_max_sync(0xffffffffu, lmax), rowarg;
+		if(MODE == 1){ const int cand = (lmax == rowmax && larg >= 0)? larg : 0x7FFFFFFF; rowarg = __reduce_min_sync(0xffffffffu, cand); }
+		else { const int cand = (lmax == rowmax)? larg : -1; rowarg = __reduce_max_sync(0xffffffffu, cand); }
 		if(NW > 1){
-			if(lane == 0) S.sredk[warp] = key;
+			if(lane == 0) S.sredk[warp] = ((long long)rowmax << 32) | (unsigned)rowarg;
 			__syncthreads();
+			rowmax = (int)(S.sredk[0] >> 32); rowarg = (int)(unsigned)(S.sredk[0] & 0xffffffffu);
 			#pragma unroll
-			for(int w2 = 0; w2 < NW; w2++){ long long o = S.sredk[w2]; if(o > key) key = o; }
+			for(int w2 = 1; w2 < NW; w2++){
+				const int hm = (int)(S.sredk[w2] >> 32), ha = (int)(unsigned)(S.sredk[w2] & 0xffffffffu);
+				if(MODE == 1){ if(hm > rowmax || (hm == rowmax && ha < rowarg)){ rowmax = hm; rowarg = ha; } }
+				else { if(hm > rowmax || (hm == rowmax && ha > rowarg)){ rowmax = hm; rowarg = ha; } }
+			}
 		} else __syncwarp();
-		const int rowmax = (int)(key >> 32);
-		int rowarg; { unsigned lo = (unsigned)(key & 0xffffffffu); rowarg = MODE == 1? (lo == 0? -1 : 0x7FFFFFFF - (int)lo) : (int)lo - 1; }
+		if(MODE == 1 && rowarg == 0x7FFFFFFF) rowarg = -1;
 		const int hlast = (je > jb)? S.smisc[0] : (jb == 0? init + P.I + E * (i + 1) : ZMO_NEG);
 		if(je == tlen && gbest < hlast){ gbest = hlast; gi = i; gj = je - 1; }
 		if(i + 1 == qlen && gbest < rowmax){ gbest = rowmax; gi = i; gj = rowarg; }
@@ -195,7 +214,7 @@ __device__ void band_extend(const BandSmem &S, const uint32_t *rowpk, int qlen, 
 		int ii = out.qe, jj = out.te, st = 0, mat = 0, mis = 0, ins = 0, del = 0, n = 0;
 		uint32_t cur_op = 0xF, cur_len = 0;
 		while(ii >= 0 && jj >= 0){
-			const int rel = jj - zb[ii];
+			const int rel = jj - (MODE == 1? zb[ii] : (ii > W? ii - W : 0));
 			const int ch = rel / PC, r2 = rel - ch * PC;
 			const uint32_t nib = (z[(size_t)ii * rw + ch * NT + r2 / C] >> ((r2 % C) << 2)) & 0xFu;
 			if(st == 0) st = nib & 3u; else if(st == 1) st = (nib & 4u)? 1 : 0; else st = (nib & 8u)? 2 : 0;
@@ -253,6 +272,8 @@ __device__ void band_global(const BandSmem &S, const uint32_t *colpk /*query*/, 
 		for(int cb = beg; cb < end; cb += PC, chunk++){
 			const int j0 = cb + tid * C;
 			int m[C], e[C];
+			unsigned long long xw = 0; const int xs = 62 - ((j0 & 15) << 1);
+			if(j0 < end){ const int w0 = j0 >> 4; xw = (((unsigned long long)colpk[w0] << 32) | colpk[w0 + 1]) ^ (0x5555555555555555ull * tb); }
 			#pragma unroll
 			for(int k = 0; k < C; k++){
 				const int j = j0 + k;
@@ -264,7 +285,7 @@ __device__ void band_global(const BandSmem &S, const uint32_t *colpk /*query*/, 
 						else hd = (j - 1 >= pbeg && j - 1 < pend)? Hp[(j - 1) & mask] : ZMO_GNEG;
 						ee = (j >= pbeg && j < pend)? S.Ev[j & mask] : ZMO_GNEG;
 					}
-					m[k] = hd + (pk_base(colpk, j) == tb? P.M : P.X);
+					m[k] = hd + (((xw >> (xs - 2 * k)) & 3ull)? P.X : P.M);
 					e[k] = ee;
 				} else { m[k] = ZMO_BIGNEG; e[k] = ZMO_BIGNEG; }
 			}

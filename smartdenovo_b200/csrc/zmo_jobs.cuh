@@ -70,7 +70,7 @@ __device__ void run_ext_job(const DPJob &J, const DevReads &R, const DPPar &P, E
 		int *zb = (int*)scr; scr += d.ql;
 		const int qw = (d.ql + 15) >> 4, tw = (d.tl + 15) >> 4;
 		uint32_t *qpk, *tpk;
-		if(qw + tw <= X.seq_words){ qpk = X.seq; tpk = X.seq + qw; }
+		if(qw + tw + 2 <= X.seq_words){ qpk = X.seq; tpk = X.seq + qw; }
 		else { qpk = scr; tpk = scr + qw; }
 		scr += qw + tw + 2;
 		BandSmem S = X.B;
@@ -96,7 +96,7 @@ __device__ void run_glb_job(const DPJob &J, const DevReads &R, const DPPar &P, E
 	uint32_t *z = scr; scr += (size_t)(tlen > 0? tlen : 0) * rwmax;
 	const int qw = (qlen + 15) >> 4, tw = (tlen + 15) >> 4;
 	uint32_t *qpk, *tpk;
-	if(qw + tw <= X.seq_words){ qpk = X.seq; tpk = X.seq + qw; }
+	if(qw + tw + 2 <= X.seq_words){ qpk = X.seq; tpk = X.seq + qw; }
 	else { qpk = scr; tpk = scr + qw; }
 	scr += qw + tw + 2;
 	BandSmem Sg = X.B;      /* global-memory H/E rows for bands wider than the shared-memory capacity */
