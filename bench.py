@@ -235,6 +235,7 @@ def main():
     names = ["index", "candidates", "pair_windows", "window_align", "gap_global", "end_extend", "dotmatrix", "copy"]
     st0, st1 = r_val["st0"], r_val["st1"]
     stage_ms = {n: st1[10 + i] - st0[10 + i] for i, n in enumerate(names)}
+    stage_ms["dp_phase_wall"] = st1[31] - st0[31]
     cells = {"end_extend": st1[18] - st0[18], "window_align": st1[19] - st0[19], "gap_global": st1[20] - st0[20]}
     dom = max(("end_extend", "window_align", "gap_global"), key=lambda k: stage_ms[k])
     peaks = {}
@@ -261,7 +262,7 @@ def main():
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
             "last_step_host_ms": {"device_calls": 1e3 * st1[3], "replay_format": 1e3 * st1[4]},
             "records_per_step": r_val["rec"] / args.steps, "aligned_bp_per_step": r_val["bp"] / args.steps,
-            "last_step_work": {"batches": st1[5], "pairs_seeded": st1[6], "pairs_aligned": st1[7], "alignments_consumed": st1[8]}}
+            "last_step_work": {"batches": st1[5], "pairs_seeded": st1[6], "pairs_aligned": st1[7], "alignments_consumed": st1[8], "demand_waves": st1[29], "demand_wave_tasks": st1[30]}}
     if world > 1:
         line["gathered_bytes"] = r_e2e["gathered"]
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(REPO, "oracle", "_ref", "wtzmo")):

@@ -56,8 +56,9 @@ const char *zmo_last_error(void);
 uint64_t zmo_kernel_launches(const zmo_ctx *ctx);
 /* cumulative device time (ms) spent per stage, measured with CUDA events on the context stream:
  * out[0]=index, [1]=candidates, [2]=pair_windows, [3]=window_align, [4]=gap_global, [5]=end_extend,
- * [6]=dotmatrix, [7]=h2d/d2h copies */
-void zmo_stage_ms(const zmo_ctx *ctx, double out[8]);
+ * [6]=dotmatrix, [7]=h2d/d2h copies, [8]=wall time of the concurrent end-extension + gap phase (the per-class kernel
+ * times in [4],[5] overlap each other), [9..11] reserved */
+void zmo_stage_ms(const zmo_ctx *ctx, double out[12]);
 /* cumulative work counters: out[0]=DP cells end-extension, [1]=cells window extension,
  * [2]=cells gap global, [3]=z-mer match pairs, [4]=postings visited, [5]=bytes H2D, [6]=bytes D2H */
 void zmo_counters(const zmo_ctx *ctx, uint64_t out[8]);

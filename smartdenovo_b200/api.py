@@ -158,9 +158,9 @@ class Zmo:
         return int(self.lib.zmo_kernel_launches(self._h))
 
     def stage_ms(self):
-        a = (C.c_double * 8)()
+        a = (C.c_double * 12)()
         self.lib.zmo_stage_ms(self._h, a)
-        return dict(zip(["index", "candidates", "pair_windows", "window_align", "gap_global", "end_extend", "dotmatrix", "copy"], list(a)))
+        return dict(zip(["index", "candidates", "pair_windows", "window_align", "gap_global", "end_extend", "dotmatrix", "copy", "dp_phase_wall"], list(a)))
 
     def counters(self):
         a = (C.c_uint64 * 8)()

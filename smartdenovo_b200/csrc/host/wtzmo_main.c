@@ -327,6 +327,8 @@ typedef struct {
 	int batch_reads, batch_pairs;
 	/* page-locked result buffers reused across batches */
 	zmo_record_t *pin_recs[2]; size_t pin_recs_cap[2]; u32 *pin_cig[2]; size_t pin_cig_cap[2]; int pin_sel, pipeline;
+	pthread_mutex_t dev_mu;             /* one device call at a time (worker thread vs on-demand waves of the replay) */
+	u64 n_waves, n_wave_tasks; int wave_margin;
 } wz_t;
 
 static double now_s(void){ struct timeval tv; gettimeofday(&tv, NULL); return tv.tv_sec + 1e-6 * tv.tv_usec; }
@@ -398,13 +400,19 @@ typedef struct {
 	u32 rd_id; int skip;                /* skip: bcov >= nbest at batch build time (nothing to compute) */
 	u64v cands_raw;                     /* candidate array in heap order after this partition's events */
 	u32v cand_pair;                     /* per raw candidate: pair index in the batch, 0xFFFFFFFF = none */
+	u32 bcov0;                          /* rdcovs[rd_id] when the batch was built (lower bound of the replay-time value) */
+	/* resumable seed walk (wtzmo.c:1005-1120): position and counters survive a pause for an on-demand DP wave */
+	int walking; u32 wi, ncand, bcov, nbest;
 } bread_t;
 typedef struct {
 	VEC(bread_t) reads;
 	VEC(zmo_pair_t) pairs;
 	zmo_pairseed_t *seeds; zmo_window_t *wins; size_t wins_cap;
-	VEC(zmo_task_t) tasks; u32 *task_of_pair;   /* pair -> task index (dir = chosen strand) or 0xFFFFFFFF */
-	zmo_record_t *recs; u32 *cigars; size_t cig_cap;
+	VEC(zmo_task_t) tasks;
+	zmo_record_t *recs; u32 *cigars; size_t cig_cap;   /* first wave, in the session's pinned buffers */
+	const zmo_record_t **pres; const u32 **pcig; u8 *pdir;   /* per pair: alignment of the chosen strand (NULL = not computed yet) */
+	VEC(void*) extra;                   /* result buffers of on-demand waves */
+	int slot;                           /* device batch slot holding this batch's windows/anchors */
 	zmo_dotres_t *dots;
 	int pin_sel;                        /* which pinned result buffer set this batch uses */
 } batch_t;
@@ -422,8 +430,10 @@ static void batch_candidates(wz_t *z, batch_t *b){
 	for(i=0;i<b->reads.n;i++) if(!b->reads.a[i].skip){ qmap[nq] = (u32)i; qids[nq++] = b->reads.a[i].rd_id; }
 	if(nq){
 		cap = 4096 + 512 * nq; ev = malloc(cap * sizeof(zmo_event_t));
+		pthread_mutex_lock(&z->dev_mu);
 		rc = zmo_candidates(z->ctx, qids, (u32)nq, off, ev, cap, &need);
 		if(rc == ZMO_ERR_CAPACITY){ cap = need + 16; ev = realloc(ev, cap * sizeof(zmo_event_t)); rc = zmo_candidates(z->ctx, qids, (u32)nq, off, ev, cap, &need); }
+		pthread_mutex_unlock(&z->dev_mu);
 		if(rc) die_zmo("zmo_candidates");
 		for(i=0;i<nq;i++){
 			bread_t *r = &b->reads.a[qmap[i]];
@@ -454,108 +464,170 @@ static void filter_sort_candidates(wz_t *z, u32 pbid, u64v *c, u32v *cp){
 	(void)tmp;
 }
 
-/* replay of one read in SW / -N mode (wtzmo.c:803-1134) using the batch's device results */
-static void replay_read(wz_t *z, batch_t *b, bread_t *br, u32 bcov, readout_t *ro){
-	const zparams_t *par = &z->par; const readset_t *rs = &z->rs; u32 pbid = br->rd_id;
-	u32 alen = rs->reads.a[pbid].len, nbest, i, j, k, ncand; u16 *windeps; float *weights;
-	ro->rd_id = pbid;
-	nbest = read_nbest(z, pbid);
-	if(bcov >= nbest) return;
-	if(br->skip){ fprintf(stderr, "wtzmo(b200): internal error: read %u needed but was skipped at batch build\n", pbid); exit(4); }
-	filter_sort_candidates(z, pbid, &br->cands_raw, &br->cand_pair);
-	if(z->rdhits){ u64v *h = &z->rdhits[pbid]; vec_clear(*h); vec_reserve(*h, br->cands_raw.n + 1); memcpy(h->a, br->cands_raw.a, br->cands_raw.n * 8); h->n = br->cands_raw.n; }
+/* chosen strand of a seeded pair, or -1 (wtzmo.c:913-914) */
+static inline int pair_dir(const zparams_t *par, const zmo_pairseed_t *ps){
+	int dir;
+	if(ps->n_zpair * (u32)par->zsize < (u32)par->ztot) return -1;
+	dir = ((u32)ps->ovl[0] & WIN_OVL_MASK) < ((u32)ps->ovl[1] & WIN_OVL_MASK);
+	return (((u32)ps->ovl[dir] & WIN_OVL_MASK) >= (u32)par->ztot)? dir : -1;
+}
+
+/* seeds of a read from its (already state-filtered and sorted) candidates: windeps, repeat weights, re-scoring and
+ * the unstable sort by score (wtzmo.c:846-986).  Pure function of the candidate list and the batch's device results;
+ * used by the replay and, on the un-filtered list, to PREDICT the alignment order for the first DP wave. */
+static void build_seeds(const wz_t *z, const batch_t *b, u32 pbid, const u64 *cands, const u32 *cand_pair, size_t ncands, seedv *seeds){
+	const zparams_t *par = &z->par; const readset_t *rs = &z->rs; u32 alen = rs->reads.a[pbid].len, i, j; u16 *windeps; float *weights;
+	vec_clear(*seeds);
 	windeps = calloc(alen + 2, sizeof(u16)); weights = malloc((alen + 1) * sizeof(float));
-	for(i=0;i<br->cands_raw.n;i++){
-		u32 id2 = (u32)(br->cands_raw.a[i] >> 32), pi = br->cand_pair.a[i]; const zmo_pairseed_t *ps; int dir;
+	for(i=0;i<ncands;i++){
+		u32 id2 = (u32)(cands[i] >> 32), pi = cand_pair[i]; const zmo_pairseed_t *ps; int dir;
 		if(pi == 0xFFFFFFFFU){ fprintf(stderr, "wtzmo(b200): internal error: pair (%u,%u) was not seeded\n", pbid, id2); exit(4); }
 		ps = &b->seeds[pi];
 		if(ps->n_zpair * (u32)par->zsize < (u32)par->ztot) continue;
-		if(par->dot_matrix){
-			const zmo_dotres_t *r = &b->dots[pi]; u32 ol;
-			vec_push(ro->closed, pair_key(id2, pbid));
-			ol = imax(r->qe - r->qb, r->te - r->tb);
-			if(r->score >= par->min_score && r->score >= (int)(par->min_id * ol)){
-				hit_t h; memset(&h, 0, sizeof(h));
-				h.pb1 = pbid; h.pb2 = id2; h.dir2 = r->strand; h.score = r->score; h.tb = r->tb; h.te = r->te; h.qb = r->qb; h.qe = r->qe;
-				h.mat = r->score; h.aln = ol; h.has_cigar = 0;
-				vec_push(ro->hits, h);
-			}
-			continue;
-		}
 		/* windeps[k]++ over every kept window (wtzmo.c:908) as a difference array; the uint16 wrap of the
 		 * reference counter is reproduced by the mod-2^16 prefix sum below */
 		for(dir=0;dir<2;dir++) for(j=0;j<ps->n_win[dir];j++){
 			const zmo_window_t *w = &b->wins[ps->win_off[dir] + j];
 			if(w->beg[0] < w->end[0]){ windeps[w->beg[0]] ++; windeps[w->end[0]] --; }
 		}
-		dir = ((u32)ps->ovl[0] & WIN_OVL_MASK) < ((u32)ps->ovl[1] & WIN_OVL_MASK);
-		if(((u32)ps->ovl[dir] & WIN_OVL_MASK) >= (u32)par->ztot){
-			seed_t s; s.pb2 = id2; s.dir = dir; s.ovl = (u32)ps->ovl[dir] & WIN_OVL_MASK; s.closed = 0; s.cand_idx = pi;
-			vec_push(ro->seeds, s);
+		dir = pair_dir(par, ps);
+		if(dir >= 0){
+			seed_t sd; sd.pb2 = id2; sd.dir = dir; sd.ovl = (u32)ps->ovl[dir] & WIN_OVL_MASK; sd.closed = 0; sd.cand_idx = pi;
+			vec_push(*seeds, sd);
 		}
 	}
-	if(!par->dot_matrix){
-		{ u16 acc = 0; for(i=0;i<alen;i++){ acc = (u16)(acc + windeps[i]); windeps[i] = acc; } }
-		/* repeat weighting (wtzmo.c:933-980); float/double expression shapes kept */
-		for(i=0;i<alen;i++)
-			weights[i] = (windeps[i] <= par->wnorm)? 1.0 : ((windeps[i] >= par->wrep)? 0.0 : par->wnorm / (float)windeps[i]);
-		for(i=0;i<alen;i++) weights[i] = weights[i] * (0.3 + 0.7 * (idiff(((int)i), (int)alen / 2) / ((int)alen / 2.0)));
-		for(i=0;i<ro->seeds.n;i++){
-			seed_t *s = &ro->seeds.a[i]; const zmo_pairseed_t *ps = &b->seeds[s->cand_idx]; int blen = rs->reads.a[s->pb2].len; u32 ol = 0; double avg;
-			for(j=0;j<ps->n_win[s->dir];j++){
-				const zmo_window_t *w = &b->wins[ps->win_off[s->dir] + j];
-				avg = (w->end[0] - w->beg[0]) * weights[(w->beg[0] + w->end[0]) / 2];
-				avg = avg * (0.3 + 0.7 * (idiff(((int)((w->beg[1] + w->end[1]) / 2)), blen / 2) / (blen / 2.0)));
-				ol += avg;
-			}
-			s->ovl = ol & WIN_OVL_MASK;
-			if(ol * par->wrep < par->ztot * par->wnorm) s->closed = 1;
+	{ u16 acc = 0; for(i=0;i<alen;i++){ acc = (u16)(acc + windeps[i]); windeps[i] = acc; } }
+	/* repeat weighting (wtzmo.c:933-980); float/double expression shapes kept */
+	for(i=0;i<alen;i++)
+		weights[i] = (windeps[i] <= par->wnorm)? 1.0 : ((windeps[i] >= par->wrep)? 0.0 : par->wnorm / (float)windeps[i]);
+	for(i=0;i<alen;i++) weights[i] = weights[i] * (0.3 + 0.7 * (idiff(((int)i), (int)alen / 2) / ((int)alen / 2.0)));
+	for(i=0;i<seeds->n;i++){
+		seed_t *sd = &seeds->a[i]; const zmo_pairseed_t *ps = &b->seeds[sd->cand_idx]; int blen = rs->reads.a[sd->pb2].len; u32 ol = 0; double avg;
+		for(j=0;j<ps->n_win[sd->dir];j++){
+			const zmo_window_t *w = &b->wins[ps->win_off[sd->dir] + j];
+			avg = (w->end[0] - w->beg[0]) * weights[(w->beg[0] + w->end[0]) / 2];
+			avg = avg * (0.3 + 0.7 * (idiff(((int)((w->beg[1] + w->end[1]) / 2)), blen / 2) / (blen / 2.0)));
+			ol += avg;
 		}
-		ref_sort(ro->seeds.a, ro->seeds.n, sizeof(seed_t), gt_seed_ovl_desc, NULL);
-		if(par->do_align){
-			ncand = par->ncand;
-			for(i=0;i<ro->seeds.n&&i<ncand;i++){
-				seed_t *s = &ro->seeds.a[i]; int blen = rs->reads.a[s->pb2].len; hit_t h; u32 x1, x2, x3, x4, ti; int l1 = alen, l2 = blen; const zmo_record_t *x;
-				if(s->closed){ ncand ++; continue; }
-				vec_push(ro->closed, pair_key(s->pb2, pbid));
-				ti = b->task_of_pair[s->cand_idx];
-				if(ti == 0xFFFFFFFFU || b->tasks.a[ti].dir != s->dir){ fprintf(stderr, "wtzmo(b200): internal error: pair (%u,%u) was not aligned\n", pbid, s->pb2); exit(4); }
-				x = &b->recs[ti]; z->n_tasks_used ++;
-				if(!x->ok){ s->closed = 1; ncand ++; continue; }
-				if(x->score < par->min_score || x->mat < x->aln * par->min_id) continue;
-				memset(&h, 0, sizeof(h));
-				h.pb1 = pbid; h.pb2 = s->pb2; h.dir2 = s->dir; h.score = x->score; h.tb = x->tb; h.te = x->te; h.qb = x->qb; h.qe = x->qe;
-				h.mat = x->mat; h.mis = x->mis; h.ins = x->ins; h.del = x->del; h.aln = x->aln; h.cigar = b->cigars + x->cigar_off; h.n_cigar = x->n_cigar; h.has_cigar = 1;
-				vec_push(ro->hits, h);
-				x1 = imin(h.tb, h.qb); x2 = imin(l1 - h.te, l2 - h.qe);
-				if(x1 + x2 <= par->max_unalign_in_dovetail){
-					/* wt->skip_contained is always 1: -C never reaches it (wtzmo.c:168,1609) */
-					x3 = ((h.tb == 0 && h.qb) || (h.te == l1 && h.qe < l2));
-					x4 = ((h.qb == 0 && h.tb) || (h.qe == l2 && h.te < l1));
-					x1 = l2 + h.qb - h.qe; x2 = l1 + h.tb - h.te;
-					if(x1 <= par->max_unalign_in_contained && x3 == 0){
-						if(x2 <= par->max_unalign_in_contained && x4 == 0){
-							if(l1 > l2){ masks_put(&ro->masks, h.pb2); }
-							else if(l1 < l2){ masks_put(&ro->masks, h.pb1); break; }
-							else if(h.pb2 > h.pb1){ masks_put(&ro->masks, h.pb2); continue; }
-							else { masks_put(&ro->masks, h.pb1); break; }
-						} else { masks_put(&ro->masks, h.pb2); continue; }
-						ncand ++;
-					} else if(x2 <= par->max_unalign_in_contained && x4 == 0){ masks_put(&ro->masks, h.pb1); break; }
-					bcov ++;
-					if(bcov >= nbest) break;
+		sd->ovl = ol & WIN_OVL_MASK;
+		if(ol * par->wrep < par->ztot * par->wnorm) sd->closed = 1;
+	}
+	ref_sort(seeds->a, seeds->n, sizeof(seed_t), gt_seed_ovl_desc, NULL);
+	free(windeps); free(weights);
+}
+
+/* containment / dovetail bookkeeping for one accepted hit (wtzmo.c:1064-1100).  Returns 0 = next seed, 2 = stop the
+ * walk.  masks may be NULL (dry walk).  wt->skip_contained is always 1: -C never reaches it (wtzmo.c:168,1609). */
+static int hit_rules(const zparams_t *par, int l1, int l2, u32 pb1, u32 pb2, const zmo_record_t *h, u32 *bcov, u32 nbest, u32 *ncand, u32v *masks){
+	u32 x1, x2, x3, x4;
+	x1 = imin(h->tb, h->qb); x2 = imin(l1 - h->te, l2 - h->qe);
+	if(x1 + x2 <= par->max_unalign_in_dovetail){
+		x3 = ((h->tb == 0 && h->qb) || (h->te == l1 && h->qe < l2));
+		x4 = ((h->qb == 0 && h->tb) || (h->qe == l2 && h->te < l1));
+		x1 = l2 + h->qb - h->qe; x2 = l1 + h->tb - h->te;
+		if(x1 <= par->max_unalign_in_contained && x3 == 0){
+			if(x2 <= par->max_unalign_in_contained && x4 == 0){
+				if(l1 > l2){ if(masks) masks_put(masks, pb2); }
+				else if(l1 < l2){ if(masks) masks_put(masks, pb1); return 2; }
+				else if(pb2 > pb1){ if(masks) masks_put(masks, pb2); return 0; }
+				else { if(masks) masks_put(masks, pb1); return 2; }
+			} else { if(masks) masks_put(masks, pb2); return 0; }
+			(*ncand) ++;
+		} else if(x2 <= par->max_unalign_in_contained && x4 == 0){ if(masks) masks_put(masks, pb1); return 2; }
+		(*bcov) ++;
+		if(*bcov >= nbest) return 2;
+	}
+	return 0;
+}
+
+/* dry walk of a predicted seed list with the results computed so far: index of the first seed whose alignment is
+ * needed but missing, or -1 if the walk would finish.  No state is touched; cross-read effects are ignored. */
+static long dry_walk(const wz_t *z, const batch_t *b, const bread_t *r, const seedv *sv){
+	const zparams_t *par = &z->par; const readset_t *rs = &z->rs; u32 ncand = par->ncand, bcov = r->bcov0, nbest = read_nbest(z, r->rd_id); size_t i;
+	int alen = rs->reads.a[r->rd_id].len;
+	if(bcov >= nbest) return -1;
+	for(i=0;i<sv->n&&i<ncand;i++){
+		const seed_t *s = &sv->a[i]; const zmo_record_t *x;
+		if(s->closed){ ncand ++; continue; }
+		x = b->pres[s->cand_idx];
+		if(x == NULL) return (long)i;
+		if(!x->ok){ ncand ++; continue; }
+		if(x->score < par->min_score || x->mat < x->aln * par->min_id) continue;
+		if(hit_rules(par, alen, rs->reads.a[s->pb2].len, r->rd_id, s->pb2, x, &bcov, nbest, &ncand, NULL) == 2) return -1;
+	}
+	return -1;
+}
+
+/* sort (candidate, pair) records by ol descending with the reference permutation (the payload rides along) */
+static void ref_sort_pairs_desc(u64 *c, u32 *cp, size_t n){
+	typedef struct { u64 v; u32 idx; u32 pad; } rec_t; size_t i;
+	rec_t *r = malloc((n + 1) * sizeof(rec_t)); u32 *np = malloc((n + 1) * 4);
+	for(i=0;i<n;i++){ r[i].v = c[i]; r[i].idx = (u32)i; r[i].pad = 0; }
+	ref_sort(r, n, sizeof(rec_t), gt_cand_ol_desc, NULL);
+	for(i=0;i<n;i++){ c[i] = r[i].v; np[i] = cp[r[i].idx]; }
+	memcpy(cp, np, n * 4);
+	free(r); free(np);
+}
+
+/* replay of one read (wtzmo.c:803-1134) using the batch's device results.  Returns 0 when the read is finished, 1 when
+ * the walk needs an alignment that has not been computed yet (the caller runs an on-demand wave and calls again). */
+static int replay_read(wz_t *z, batch_t *b, bread_t *br, u32 bcov_in, readout_t *ro){
+	const zparams_t *par = &z->par; const readset_t *rs = &z->rs; u32 pbid = br->rd_id;
+	u32 alen = rs->reads.a[pbid].len, i;
+	if(!br->walking){
+		ro->rd_id = pbid;
+		br->nbest = read_nbest(z, pbid); br->bcov = bcov_in;
+		if(br->bcov >= br->nbest) return 0;
+		if(br->skip){ fprintf(stderr, "wtzmo(b200): internal error: read %u needed but was skipped at batch build\n", pbid); exit(4); }
+		filter_sort_candidates(z, pbid, &br->cands_raw, &br->cand_pair);
+		if(z->rdhits){ u64v *h = &z->rdhits[pbid]; vec_clear(*h); vec_reserve(*h, br->cands_raw.n + 1); memcpy(h->a, br->cands_raw.a, br->cands_raw.n * 8); h->n = br->cands_raw.n; }
+		if(par->dot_matrix){
+			for(i=0;i<br->cands_raw.n;i++){
+				u32 id2 = (u32)(br->cands_raw.a[i] >> 32), pi = br->cand_pair.a[i]; const zmo_dotres_t *r; u32 ol;
+				if(pi == 0xFFFFFFFFU){ fprintf(stderr, "wtzmo(b200): internal error: pair (%u,%u) was not seeded\n", pbid, id2); exit(4); }
+				if(b->seeds[pi].n_zpair * (u32)par->zsize < (u32)par->ztot) continue;
+				r = &b->dots[pi];
+				vec_push(ro->closed, pair_key(id2, pbid));
+				ol = imax(r->qe - r->qb, r->te - r->tb);
+				if(r->score >= par->min_score && r->score >= (int)(par->min_id * ol)){
+					hit_t h; memset(&h, 0, sizeof(h));
+					h.pb1 = pbid; h.pb2 = id2; h.dir2 = r->strand; h.score = r->score; h.tb = r->tb; h.te = r->te; h.qb = r->qb; h.qe = r->qe;
+					h.mat = r->score; h.aln = ol; h.has_cigar = 0;
+					vec_push(ro->hits, h);
 				}
 			}
+			return 0;
 		}
+		build_seeds(z, b, pbid, br->cands_raw.a, br->cand_pair.a, br->cands_raw.n, &ro->seeds);
+		if(!par->do_align) return 0;
+		br->walking = 1; br->wi = 0; br->ncand = par->ncand;
 	}
-	free(windeps); free(weights);
+	for(i=br->wi;i<ro->seeds.n&&i<br->ncand;i++){
+		seed_t *s = &ro->seeds.a[i]; hit_t h; const zmo_record_t *x; int act;
+		if(s->closed){ br->ncand ++; continue; }
+		x = b->pres[s->cand_idx];
+		if(x == NULL || b->pdir[s->cand_idx] != s->dir){ br->wi = i; return 1; }      /* not aligned yet: ask for a wave */
+		vec_push(ro->closed, pair_key(s->pb2, pbid));
+		z->n_tasks_used ++;
+		if(!x->ok){ s->closed = 1; br->ncand ++; continue; }
+		if(x->score < par->min_score || x->mat < x->aln * par->min_id) continue;
+		memset(&h, 0, sizeof(h));
+		h.pb1 = pbid; h.pb2 = s->pb2; h.dir2 = s->dir; h.score = x->score; h.tb = x->tb; h.te = x->te; h.qb = x->qb; h.qe = x->qe;
+		h.mat = x->mat; h.mis = x->mis; h.ins = x->ins; h.del = x->del; h.aln = x->aln; h.cigar = b->pcig[s->cand_idx] + x->cigar_off; h.n_cigar = x->n_cigar; h.has_cigar = 1;
+		vec_push(ro->hits, h);
+		act = hit_rules(par, alen, rs->reads.a[s->pb2].len, pbid, s->pb2, x, &br->bcov, br->nbest, &br->ncand, &ro->masks);
+		if(act == 2) break;
+	}
+	br->walking = 0;
+	return 0;
 }
 
 static void batch_free(batch_t *b){
 	size_t i;
 	for(i=0;i<b->reads.n;i++){ vec_free(b->reads.a[i].cands_raw); vec_free(b->reads.a[i].cand_pair); }
 	vec_free(b->reads); vec_free(b->pairs); vec_free(b->tasks);
-	free(b->seeds); free(b->wins); free(b->task_of_pair); free(b->dots);     /* recs / cigars live in the session's pinned buffers */
+	free(b->seeds); free(b->wins); free(b->pres); free(b->pcig); free(b->pdir); free(b->dots);     /* first-wave recs / cigars live in the session's pinned buffers */
+	{ size_t k; for(k=0;k<b->extra.n;k++) free(b->extra.a[k]); vec_free(b->extra); }
 	memset(b, 0, sizeof(*b));
 }
 
@@ -583,41 +655,104 @@ static void batch_compute(wz_t *z, batch_t *b){
 	z->n_pairs_seeded += b->pairs.n;
 	if(par->dot_matrix){
 		b->dots = malloc(b->pairs.n * sizeof(zmo_dotres_t)); b->seeds = calloc(b->pairs.n, sizeof(zmo_pairseed_t));
-		if(zmo_pair_dotmatrix(z->ctx, b->pairs.a, (u32)b->pairs.n, b->dots)) die_zmo("zmo_pair_dotmatrix");
+		pthread_mutex_lock(&z->dev_mu);
+		rc = zmo_pair_dotmatrix(z->ctx, b->pairs.a, (u32)b->pairs.n, b->dots);
+		pthread_mutex_unlock(&z->dev_mu);
+		if(rc) die_zmo("zmo_pair_dotmatrix");
 		for(i=0;i<b->pairs.n;i++) b->seeds[i].n_zpair = b->dots[i].n_zpair;
 		return;
 	}
 	b->seeds = malloc(b->pairs.n * sizeof(zmo_pairseed_t));
 	b->wins_cap = 64 * b->pairs.n + 1024; b->wins = malloc(b->wins_cap * sizeof(zmo_window_t));
-	rc = zmo_pair_windows(z->ctx, 0, b->pairs.a, (u32)b->pairs.n, b->seeds, b->wins, b->wins_cap, &need);
-	if(rc == ZMO_ERR_CAPACITY && need > b->wins_cap){ b->wins_cap = need + 16; b->wins = realloc(b->wins, b->wins_cap * sizeof(zmo_window_t)); rc = zmo_pair_windows(z->ctx, 0, b->pairs.a, (u32)b->pairs.n, b->seeds, b->wins, b->wins_cap, &need); }
+	pthread_mutex_lock(&z->dev_mu);
+	rc = zmo_pair_windows(z->ctx, b->slot, b->pairs.a, (u32)b->pairs.n, b->seeds, b->wins, b->wins_cap, &need);
+	if(rc == ZMO_ERR_CAPACITY && need > b->wins_cap){ b->wins_cap = need + 16; b->wins = realloc(b->wins, b->wins_cap * sizeof(zmo_window_t)); rc = zmo_pair_windows(z->ctx, b->slot, b->pairs.a, (u32)b->pairs.n, b->seeds, b->wins, b->wins_cap, &need); }
+	pthread_mutex_unlock(&z->dev_mu);
 	if(rc) die_zmo("zmo_pair_windows");
 	if(!par->do_align) return;
-	/* tasks: every pair whose better strand passes ztot (the replay decides which ones it consumes) */
-	b->task_of_pair = malloc(b->pairs.n * 4);
-	for(i=0;i<b->pairs.n;i++){
-		const zmo_pairseed_t *ps = &b->seeds[i]; int dir;
-		b->task_of_pair[i] = 0xFFFFFFFFU;
-		if(ps->n_zpair * (u32)par->zsize < (u32)par->ztot) continue;
-		dir = ((u32)ps->ovl[0] & WIN_OVL_MASK) < ((u32)ps->ovl[1] & WIN_OVL_MASK);
-		if(((u32)ps->ovl[dir] & WIN_OVL_MASK) < (u32)par->ztot) continue;
-		{ zmo_task_t t; t.pair_idx = (u32)i; t.dir = dir; b->task_of_pair[i] = (u32)b->tasks.n; vec_push(b->tasks, t); }
-	}
-	if(b->tasks.n == 0) return;
-	z->n_tasks += b->tasks.n;
+	b->pres = calloc(b->pairs.n, sizeof(*b->pres)); b->pcig = calloc(b->pairs.n, sizeof(*b->pcig)); b->pdir = calloc(b->pairs.n, 1);
+	/* DP waves: every read's seeds in the order the replay is predicted to walk them (build_seeds on the candidate list
+	 * as it was at batch build time); wave k aligns the next chunk (16, 32, 64, ... seeds) of every read whose DRY walk
+	 * over the results so far still stops at a missing alignment.  Most reads finish early (the first containing
+	 * candidate masks them, wtzmo.c:1079-1090), so this skips most of the speculative DP.  Whatever the real replay
+	 * still misses is computed on demand (demand_wave). */
 	{
-		const int ps = b->pin_sel;
-		if(b->tasks.n > z->pin_recs_cap[ps]){ zmo_host_free(z->pin_recs[ps]); z->pin_recs_cap[ps] = b->tasks.n * 2 + 1024; z->pin_recs[ps] = zmo_host_alloc(z->pin_recs_cap[ps] * sizeof(zmo_record_t)); if(!z->pin_recs[ps]) die_zmo("zmo_host_alloc"); }
-		if(z->pin_cig_cap[ps] < 4096 * b->tasks.n + (1u << 16)){ zmo_host_free(z->pin_cig[ps]); z->pin_cig_cap[ps] = 4096 * b->tasks.n * 2 + (1u << 20); z->pin_cig[ps] = zmo_host_alloc(z->pin_cig_cap[ps] * 4); if(!z->pin_cig[ps]) die_zmo("zmo_host_alloc"); }
-		b->recs = z->pin_recs[ps]; b->cigars = z->pin_cig[ps]; b->cig_cap = z->pin_cig_cap[ps];
-		rc = zmo_pair_align(z->ctx, 0, b->tasks.a, (u32)b->tasks.n, b->recs, b->cigars, b->cig_cap, &need);
-		if(rc == ZMO_ERR_CAPACITY && need > b->cig_cap){
-			zmo_host_free(z->pin_cig[ps]); z->pin_cig_cap[ps] = need + need / 4 + 16; z->pin_cig[ps] = zmo_host_alloc(z->pin_cig_cap[ps] * 4); if(!z->pin_cig[ps]) die_zmo("zmo_host_alloc");
-			b->cigars = z->pin_cig[ps]; b->cig_cap = z->pin_cig_cap[ps];
-			rc = zmo_pair_align(z->ctx, 0, b->tasks.a, (u32)b->tasks.n, b->recs, b->cigars, b->cig_cap, &need);
+		size_t nr = b->reads.n, k, chunk = z->wave_margin < 0? (size_t)1 << 30 : (size_t)(z->wave_margin > 0? z->wave_margin : 16); int wave = 0;
+		seedv *sv = calloc(nr + 1, sizeof(seedv)); long *pos = calloc(nr + 1, sizeof(long));
+		for(i=0;i<nr;i++){
+			bread_t *r = &b->reads.a[i]; u64v cc; u32v cp;
+			pos[i] = -1;
+			if(r->skip || r->cands_raw.n == 0) continue;
+			vec_init(cc); vec_init(cp);
+			for(k=0;k<r->cands_raw.n;k++) if(r->cand_pair.a[k] != 0xFFFFFFFFU){ vec_push(cc, r->cands_raw.a[k]); vec_push(cp, r->cand_pair.a[k]); }
+			ref_sort_pairs_desc(cc.a, cp.a, cc.n);
+			build_seeds(z, b, r->rd_id, cc.a, cp.a, cc.n, &sv[i]);
+			pos[i] = dry_walk(z, b, r, &sv[i]);
+			vec_free(cc); vec_free(cp);
 		}
+		while(1){
+			VEC(zmo_task_t) tk; zmo_record_t *recs; u32 *cig; size_t cap;
+			vec_init(tk);
+			for(i=0;i<nr;i++){
+				size_t got = 0;
+				if(pos[i] < 0) continue;
+				for(k=(size_t)pos[i];k<sv[i].n&&got<chunk;k++){
+					const seed_t *sd = &sv[i].a[k]; zmo_task_t t;
+					if(sd->closed || b->pres[sd->cand_idx]) continue;
+					t.pair_idx = sd->cand_idx; t.dir = sd->dir; vec_push(tk, t); got ++;
+				}
+			}
+			if(tk.n == 0){ vec_free(tk); break; }
+			z->n_tasks += tk.n;
+			if(wave == 0){
+				const int ps = b->pin_sel;
+				if(tk.n > z->pin_recs_cap[ps]){ zmo_host_free(z->pin_recs[ps]); z->pin_recs_cap[ps] = tk.n * 2 + 1024; z->pin_recs[ps] = zmo_host_alloc(z->pin_recs_cap[ps] * sizeof(zmo_record_t)); if(!z->pin_recs[ps]) die_zmo("zmo_host_alloc"); }
+				if(z->pin_cig_cap[ps] < 4096 * tk.n + (1u << 16)){ zmo_host_free(z->pin_cig[ps]); z->pin_cig_cap[ps] = 4096 * tk.n * 2 + (1u << 20); z->pin_cig[ps] = zmo_host_alloc(z->pin_cig_cap[ps] * 4); if(!z->pin_cig[ps]) die_zmo("zmo_host_alloc"); }
+				recs = z->pin_recs[ps]; cig = z->pin_cig[ps]; cap = z->pin_cig_cap[ps];
+			} else { recs = malloc(tk.n * sizeof(zmo_record_t)); cap = 4096 * tk.n + 65536; cig = malloc(cap * 4); }
+			pthread_mutex_lock(&z->dev_mu);
+			rc = zmo_pair_align(z->ctx, b->slot, tk.a, (u32)tk.n, recs, cig, cap, &need);
+			if(rc == ZMO_ERR_CAPACITY && need > cap){
+				cap = need + need / 4 + 16;
+				if(wave == 0){ const int ps = b->pin_sel; zmo_host_free(z->pin_cig[ps]); z->pin_cig_cap[ps] = cap; z->pin_cig[ps] = zmo_host_alloc(cap * 4); if(!z->pin_cig[ps]) die_zmo("zmo_host_alloc"); cig = z->pin_cig[ps]; }
+				else cig = realloc(cig, cap * 4);
+				rc = zmo_pair_align(z->ctx, b->slot, tk.a, (u32)tk.n, recs, cig, cap, &need);
+			}
+			pthread_mutex_unlock(&z->dev_mu);
+			if(rc) die_zmo("zmo_pair_align");
+			for(i=0;i<tk.n;i++){ b->pres[tk.a[i].pair_idx] = &recs[i]; b->pcig[tk.a[i].pair_idx] = cig; b->pdir[tk.a[i].pair_idx] = (u8)tk.a[i].dir; }
+			if(wave){ vec_push(b->extra, (void*)recs); vec_push(b->extra, (void*)cig); }
+			vec_free(tk);
+			for(i=0;i<nr;i++) if(pos[i] >= 0) pos[i] = dry_walk(z, b, &b->reads.a[i], &sv[i]);
+			wave ++; if(chunk < ((size_t)1 << 20)) chunk *= 2;
+		}
+		for(i=0;i<nr;i++) vec_free(sv[i]);
+		free(sv); free(pos);
 	}
-	if(rc) die_zmo("zmo_pair_align");
+}
+
+/* on-demand DP wave for the read being replayed: every not-yet-aligned seed from the current walk position on */
+static void demand_wave(wz_t *z, batch_t *b, bread_t *br, readout_t *ro){
+	VEC(zmo_task_t) tk; size_t i, cap; u64 need = 0; int rc; zmo_record_t *recs; u32 *cig;
+	vec_init(tk);
+	for(i=br->wi;i<ro->seeds.n;i++){
+		seed_t *s = &ro->seeds.a[i]; zmo_task_t t;
+		if(s->closed) continue;
+		if(b->pres[s->cand_idx] && b->pdir[s->cand_idx] == s->dir) continue;
+		t.pair_idx = s->cand_idx; t.dir = s->dir; vec_push(tk, t);
+		if(tk.n >= (size_t)(br->nbest - br->bcov) + (br->nbest - br->bcov) / 4 + 8) break;
+	}
+	if(tk.n == 0){ fprintf(stderr, "wtzmo(b200): internal error: empty demand wave\n"); exit(4); }
+	recs = malloc(tk.n * sizeof(zmo_record_t)); cap = 4096 * tk.n + 65536; cig = malloc(cap * 4);
+	pthread_mutex_lock(&z->dev_mu);
+	rc = zmo_pair_align(z->ctx, b->slot, tk.a, (u32)tk.n, recs, cig, cap, &need);
+	if(rc == ZMO_ERR_CAPACITY && need > cap){ cap = need + 16; cig = realloc(cig, cap * 4); rc = zmo_pair_align(z->ctx, b->slot, tk.a, (u32)tk.n, recs, cig, cap, &need); }
+	pthread_mutex_unlock(&z->dev_mu);
+	if(rc) die_zmo("zmo_pair_align (demand wave)");
+	for(i=0;i<tk.n;i++){ b->pres[tk.a[i].pair_idx] = &recs[i]; b->pcig[tk.a[i].pair_idx] = cig; b->pdir[tk.a[i].pair_idx] = (u8)tk.a[i].dir; }
+	vec_push(b->extra, (void*)recs); vec_push(b->extra, (void*)cig);
+	z->n_waves ++; z->n_wave_tasks += tk.n; z->n_tasks += tk.n;
+	vec_free(tk);
 }
 
 typedef struct { wz_t *z; batch_t *b; } wk_arg_t;
@@ -665,12 +800,12 @@ static void run_overlap(wz_t *z){
 			nxt = NULL;
 			if(j < end){
 				size_t est_pairs = 0;
-				nxt = calloc(1, sizeof(batch_t)); nxt->pin_sel = sel; sel ^= 1;
+				nxt = calloc(1, sizeof(batch_t)); nxt->pin_sel = sel; nxt->slot = sel; sel ^= 1;
 				for(;j<end&&nxt->reads.n<(size_t)z->batch_reads&&est_pairs<(size_t)z->batch_pairs;j++){
 					bread_t r; memset(&r, 0, sizeof(r));
 					if((j % par->n_job) != (u32)par->i_job) continue;
 					if(z->masked[j]) continue;
-					r.rd_id = j; r.skip = z->rdcovs[j] >= read_nbest(z, j);
+					r.rd_id = j; r.bcov0 = z->rdcovs[j]; r.skip = r.bcov0 >= read_nbest(z, j);
 					vec_push(nxt->reads, r);
 					if(!r.skip) est_pairs += 40;
 				}
@@ -690,7 +825,7 @@ static void run_overlap(wz_t *z){
 					bread_t *br = &cur->reads.a[i];
 					if(z->masked[br->rd_id]) continue;       /* checked BEFORE the previous read's masks are merged (wtzmo.c:1315 vs 1322) */
 					flush_read(z, &ro, 0);
-					replay_read(z, cur, br, z->rdcovs[br->rd_id], &ro);
+					while(replay_read(z, cur, br, z->rdcovs[br->rd_id], &ro)) demand_wave(z, cur, br, &ro);
 				}
 				flush_read(z, &ro, 1);  /* hits point into this batch's CIGAR buffer: print them before it is reused; masks stay pending */
 				z->t_replay += now_s() - t1; z->n_batches ++;
@@ -848,6 +983,8 @@ wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	z->batch_reads = (env = getenv("ZMO_BATCH_READS"))? atoi(env) : 256;
 	z->batch_pairs = (env = getenv("ZMO_BATCH_PAIRS"))? atoi(env) : 16384;
 	z->pipeline = (env = getenv("ZMO_PIPELINE"))? atoi(env) : 1;
+	z->wave_margin = (env = getenv("ZMO_WAVE0"))? atoi(env) : 16;       /* seeds per read in the first DP wave (doubles per wave); < 0: align every seed up front */
+	pthread_mutex_init(&z->dev_mu, NULL);
 	if(z->batch_reads < 1) z->batch_reads = 1;
 	fprintf(stderr, "[wtzmo-b200] loading long reads\n");
 	rs_load(&z->rs, pbs.a, (int)pbs.n, par->min_rdlen, 0);
@@ -934,7 +1071,7 @@ int wz_run(wz_session_t *S, int n_job, int i_job, const char *out_path){
 	free(z->closed.tab); u64set_init(&z->closed);
 	for(k=0;k<S->closed0.n;k++) u64set_add(&z->closed, S->closed0.a[k]);
 	if(z->rdhits){ for(k=0;k<n;k++) vec_free(z->rdhits[k]); free(z->rdhits); z->rdhits = NULL; }
-	z->n_records = z->aln_cols = z->n_tasks = z->n_tasks_used = z->n_pairs_seeded = z->n_batches = 0; z->t_dev = z->t_replay = 0;
+	z->n_records = z->aln_cols = z->n_tasks = z->n_tasks_used = z->n_pairs_seeded = z->n_batches = z->n_waves = z->n_wave_tasks = 0; z->t_dev = z->t_replay = 0;
 	z->out = strcmp(out_path, "-")? fopen(out_path, "w") : stdout;
 	if(z->out == NULL){ fprintf(stderr, "wtzmo(b200): cannot open %s\n", out_path); return 1; }
 	if(z->obuf == NULL){ z->obuf_cap = 8u << 20; z->obuf = malloc(z->obuf_cap); }
@@ -949,13 +1086,14 @@ int wz_run(wz_session_t *S, int n_job, int i_job, const char *out_path){
  * [7]=tasks aligned [8]=tasks consumed [9]=kernel launches (cumulative) [10..17]=stage ms (cumulative) [18..24]=counters (cumulative)
  * [25]=reads [26]=bases [27]=last upload s [28]=upload bytes */
 void wz_stats(wz_session_t *S, double *out){
-	wz_t *z = &S->z; double ms[8]; uint64_t ct[8]; int i;
+	wz_t *z = &S->z; double ms[12]; uint64_t ct[8]; int i;
 	zmo_stage_ms(z->ctx, ms); zmo_counters(z->ctx, ct);
 	out[0] = (double)z->n_records; out[1] = (double)z->aln_cols; out[2] = S->last_overlap_s; out[3] = z->t_dev; out[4] = z->t_replay; out[5] = (double)z->n_batches;
 	out[6] = (double)z->n_pairs_seeded; out[7] = (double)z->n_tasks; out[8] = (double)z->n_tasks_used; out[9] = (double)zmo_kernel_launches(z->ctx);
 	for(i=0;i<8;i++) out[10 + i] = ms[i];
 	for(i=0;i<7;i++) out[18 + i] = (double)ct[i];
 	out[25] = (double)(z->rs.n_rd + z->rs.n_qr); out[26] = (double)z->rs.nbases; out[27] = S->last_upload_s; out[28] = (double)S->upload_bytes;
+	out[29] = (double)z->n_waves; out[30] = (double)z->n_wave_tasks; out[31] = ms[8];
 }
 
 void wz_close(wz_session_t *S){ if(S){ if(S->z.ctx) zmo_ctx_destroy(S->z.ctx); free(S); } }

@@ -341,6 +341,7 @@ static int run_dp_lists(zmo_ctx *c, const JobLists &L, const uint32_t *n, const 
 		order[k] = sidx;
 	}
 	CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
+	CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
 	for(int k = 0; k < 6; k++){
 		if(cnt[k] == 0) continue;
 		CUDA_TRY(cudaStreamWaitEvent(c->aux[k], c->ev_fork, 0));
@@ -352,7 +353,9 @@ static int run_dp_lists(zmo_ctx *c, const JobLists &L, const uint32_t *n, const 
 		CUDA_TRY(cudaEventRecord(c->ev_a1[k], c->aux[k]));
 		CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_a1[k], 0));
 	}
+	CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	{ float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->stage_ms[ST_DPWALL] += ms; }
 	for(int k = 0; k < 6; k++){
 		if(cnt[k] == 0) continue;
 		float ms = 0; cudaEventElapsedTime(&ms, c->ev_a0[k], c->ev_a1[k]);
@@ -372,8 +375,6 @@ extern "C" int zmo_pair_align(zmo_ctx *c, int slot, const zmo_task_t *tasks, uin
 	CUDA_TRY(cudaSetDevice(c->device));
 	/* host: items and per-item cigar regions */
 	std::vector<AlnTask> ht(nt); std::vector<WItem> items; std::vector<unsigned long long> icig;
-	std::vector<DevWin> hw(SL.n_wins);
-	if(SL.n_wins) CUDA_TRY(cudaMemcpy(hw.data(), SL.wins.p, SL.n_wins * sizeof(DevWin), cudaMemcpyDeviceToHost));
 	unsigned long long cig_words = 0; int max_rows = 16;
 	for(uint32_t t = 0; t < nt; t++){
 		if(tasks[t].pair_idx >= SL.np || tasks[t].dir > 1) return zmo_set_err(ZMO_ERR_ARG, "task %u out of range", t);
@@ -381,9 +382,8 @@ extern "C" int zmo_pair_align(zmo_ctx *c, int slot, const zmo_task_t *tasks, uin
 		ht[t].pair_idx = tasks[t].pair_idx; ht[t].dir = d; ht[t].item_off = (uint32_t)items.size(); ht[t].n_item = ps.n_win[d];
 		for(uint32_t k = 0; k < ps.n_win[d]; k++){
 			WItem it; it.task = t; it.win = ps.win_off[d] + k; items.push_back(it);
-			const DevWin &w = hw[it.win];
-			const int s0 = w.end[0] - w.beg[0], s1 = w.end[1] - w.beg[1];
-			icig.push_back(cig_words); cig_words += (unsigned long long)(s0 + s1 + 16 + 2 * (w.anc1 - w.anc0));
+			const int s0 = SL.h_wspan[3 * (size_t)it.win], s1 = SL.h_wspan[3 * (size_t)it.win + 1], na = SL.h_wspan[3 * (size_t)it.win + 2];
+			icig.push_back(cig_words); cig_words += (unsigned long long)(s0 + s1 + 16 + 2 * na);
 			if(s1 + 8 > max_rows) max_rows = s1 + 8;
 			if(s0 + 8 > max_rows) max_rows = s0 + 8;
 		}

@@ -52,7 +52,7 @@ extern "C" void *zmo_host_alloc(size_t bytes){ void *p = nullptr; if(cudaHostAll
 extern "C" void zmo_host_free(void *p){ if(p) cudaFreeHost(p); }
 
 extern "C" uint64_t zmo_kernel_launches(const zmo_ctx *c){ return c? c->launches : 0; }
-extern "C" void zmo_stage_ms(const zmo_ctx *c, double out[8]){ for(int i = 0; i < 8; i++) out[i] = c? c->stage_ms[i] : 0; }
+extern "C" void zmo_stage_ms(const zmo_ctx *c, double out[12]){ for(int i = 0; i < 12; i++) out[i] = c? c->stage_ms[i] : 0; }
 extern "C" void zmo_counters(const zmo_ctx *c, uint64_t out[8]){
 	for(int i = 0; i < 8; i++) out[i] = 0;
 	if(!c) return;

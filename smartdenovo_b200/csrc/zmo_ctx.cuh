@@ -50,7 +50,7 @@ struct PinBuf {
 	template<class T> T* as() const { return (T*)p; }
 };
 
-enum { ST_INDEX = 0, ST_CAND, ST_SEED, ST_WINALN, ST_GAP, ST_EXT, ST_DOT, ST_COPY, ST_N };
+enum { ST_INDEX = 0, ST_CAND, ST_SEED, ST_WINALN, ST_GAP, ST_EXT, ST_DOT, ST_COPY, ST_DPWALL, ST_N = 12 };
 
 /* one batch slot of the pair-seed stage (results stay on the device for zmo_pair_align) */
 struct SeedSlot {
@@ -61,6 +61,7 @@ struct SeedSlot {
 	DevBuf anchors;     /* DevZPair[] anchors of kept windows */
 	uint64_t n_wins = 0, n_anchors = 0;
 	std::vector<zmo_pairseed_t> h_seeds;
+	std::vector<int32_t> h_wspan;       /* per kept window: q span, c span, #anchors (host copy for job sizing) */
 };
 
 struct zmo_ctx {

@@ -376,7 +376,11 @@ extern "C" int zmo_pair_windows(zmo_ctx *c, int slot, const zmo_pair_t *pairs, u
 	std::vector<DevWin> hw(nw);
 	if(nw) CUDA_TRY(cudaMemcpyAsync(hw.data(), SL.wins.p, nw * sizeof(DevWin), cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
-	for(unsigned long long i = 0; i < nw; i++){ wins[i].beg[0] = hw[i].beg[0]; wins[i].beg[1] = hw[i].beg[1]; wins[i].end[0] = hw[i].end[0]; wins[i].end[1] = hw[i].end[1]; }
+	SL.h_wspan.resize(nw * 3);
+	for(unsigned long long i = 0; i < nw; i++){
+		wins[i].beg[0] = hw[i].beg[0]; wins[i].beg[1] = hw[i].beg[1]; wins[i].end[0] = hw[i].end[0]; wins[i].end[1] = hw[i].end[1];
+		SL.h_wspan[3 * i] = hw[i].end[0] - hw[i].beg[0]; SL.h_wspan[3 * i + 1] = hw[i].end[1] - hw[i].beg[1]; SL.h_wspan[3 * i + 2] = (int32_t)(hw[i].anc1 - hw[i].anc0);
+	}
 	SL.np = np; SL.n_wins = nw; SL.n_anchors = na;
 	SL.h_seeds.assign(seeds, seeds + np);
 	c->counters[5] += (size_t)np * sizeof(zmo_pair_t);
