@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *ite
 			uint32_t *tmpc = nullptr;
 			if(qlen > 0 && tlen > 0){
 				const BandDims d = band_dims(qlen, tlen, init, A.w, P);
-				const int rw = band_row_words<32, WA_C>(d.ncol);
+				const int rw = band_row_words<32, WA_C>(d.ncol);      /* >= the row words of the narrower variants (32) */
 				uint32_t *scr = slab;
 				uint32_t *z = (d.ql <= WA_ZROWS && rw == 32)? s_z[warp] : scr; scr += (size_t)max_rows * rw;
 				int *zb = (int*)scr; scr += max_rows;
@@ -99,7 +99,13 @@ __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *ite
 				stage_packed<32>(view_pb2(R, pr.cid, T.dir, x_qe, 1), d.ql, qpk, lane);
 				stage_packed<32>(view_pb1(R, pr.qid, x_te, 1), d.tl, tpk, lane);
 				__syncwarp();
-				band_extend<32, WA_C, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, zb, tmpc, 2 * max_rows + 2 * A.w + 16, o, ctr + ctr_cells, lane);
+				/* columns per lane chosen by band width: narrow bridges (the common case, ~50 columns) run 1-2 cells per lane
+				 * instead of 7 mostly idle ones, which cuts the per-row instruction count several-fold */
+				const int ccap = 2 * max_rows + 2 * A.w + 16;
+				if(d.ncol <= 32) band_extend<32, 1, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, zb, tmpc, ccap, o, ctr + ctr_cells, lane);
+				else if(d.ncol <= 64) band_extend<32, 2, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, zb, tmpc, ccap, o, ctr + ctr_cells, lane);
+				else if(d.ncol <= 128) band_extend<32, 4, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, zb, tmpc, ccap, o, ctr + ctr_cells, lane);
+				else band_extend<32, WA_C, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, zb, tmpc, ccap, o, ctr + ctr_cells, lane);
 			}
 			x_score = o.score;
 			x_aln += o.mat + o.mis + o.ins + o.del; x_mat += o.mat; x_mis += o.mis; x_ins += o.ins; x_del += o.del;

@@ -109,8 +109,12 @@ __device__ void run_glb_job(const DPJob &J, const DevReads &R, const DPPar &P, E
 	while(1){
 		if(w < dl){ w <<= 1; continue; }
 		{
-			const int bw = (qlen < 2 * w + 1? qlen : 2 * w + 1) + 3;
-			band_global<NT, C>(bw <= X.cap? X.B : Sg, qpk, qlen, tpk, tlen, w, P, z, cig_arena + J.cig_off, (int)J.cig_cap, o, cells, tid);
+			const int nc = qlen < 2 * w + 1? qlen : 2 * w + 1, bw = nc + 3;
+			const BandSmem &SS = bw <= X.cap? X.B : Sg;
+			if(NT == 32 && nc <= 32) band_global<NT, 1>(SS, qpk, qlen, tpk, tlen, w, P, z, cig_arena + J.cig_off, (int)J.cig_cap, o, cells, tid);
+			else if(NT == 32 && nc <= 64) band_global<NT, 2>(SS, qpk, qlen, tpk, tlen, w, P, z, cig_arena + J.cig_off, (int)J.cig_cap, o, cells, tid);
+			else if(NT == 32 && nc <= 128) band_global<NT, 4>(SS, qpk, qlen, tpk, tlen, w, P, z, cig_arena + J.cig_off, (int)J.cig_cap, o, cells, tid);
+			else band_global<NT, C>(SS, qpk, qlen, tpk, tlen, w, P, z, cig_arena + J.cig_off, (int)J.cig_cap, o, cells, tid);
 		}
 		if(J.Wmax > 0 && o.score < 0 && w < J.Wmax && w < mxl) w <<= 1; else break;
 	}

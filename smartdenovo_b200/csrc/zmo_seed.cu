@@ -147,9 +147,12 @@ struct SeedOut { DevWin *wins; DevZPair *anc; unsigned long long cap_wins, cap_a
  * order-exact serial logic of zmo_seed_core.cuh on it (shared-memory latency instead of global), the lanes copy the
  * kept windows/anchors out.  Lists that do not fit the shared-memory budget run from global memory. */
 #define PS_WARPS 4
-#define PS_MAXN 2048
-#define PS_MAXW 512
-struct PSSmem { DevZPair rs[PS_MAXN]; uint32_t ts[PS_MAXN]; int32_t as[PS_MAXN]; uint32_t wb[PS_MAXW], we[PS_MAXW], wo[PS_MAXW]; int bc[8]; };
+#define PS_MAXN 2048      /* match list entries staged per pair */
+#define PS_MAXT 1024      /* strand entries of one sliding span */
+#define PS_MAXW 256       /* sub-windows of one span */
+#define PS_STAGE 256      /* anchors of one window */
+#define PS_MAXWIN 112     /* windows of one strand */
+struct PSSmem { DevZPair rs[PS_MAXN]; DevZPair stage[PS_STAGE]; DevWin w2[PS_MAXWIN]; uint32_t ts[PS_MAXT]; int32_t as[PS_MAXT]; uint32_t wb[PS_MAXW], we[PS_MAXW], wo[PS_MAXW]; int bc[8]; };
 __global__ void __launch_bounds__(32 * PS_WARPS) k_p_seed(const unsigned long long *cache_off, uint32_t np, DevZPair *cache, const uint8_t *tie, const uint32_t *pc, DevReads R,
 		uint8_t *scratch, size_t per, uint32_t F, SeedPar par, SeedOut O, zmo_pairseed_t *seeds, unsigned long long *work){
 	extern __shared__ __align__(16) uint8_t ps_raw[];
@@ -177,29 +180,31 @@ __global__ void __launch_bounds__(32 * PS_WARPS) k_p_seed(const unsigned long lo
 			for(int d = 0; d < 2; d++){
 				PairScratch P = zmo_pair_scratch_carve(scr, n, F);
 				if(lane == 0){
-					uint32_t nwin = 0; int ovf = 0, ovl = 0;
+					uint32_t nwin = 0; int ovf = 0, ovl = 0, fast = 0;
 					if(in_smem){
-						PairScratch Q = P; Q.ws.ts = M.ts; Q.ws.as = M.as; Q.ws.wb = M.wb; Q.ws.we = M.we; Q.ws.wo = M.wo; Q.ws.capt = PS_MAXN; Q.ws.capw = PS_MAXW;
+						PairScratch Q = P; Q.ws.ts = M.ts; Q.ws.as = M.as; Q.ws.wb = M.wb; Q.ws.we = M.we; Q.ws.wo = M.wo; Q.ws.capt = PS_MAXT; Q.ws.capw = PS_MAXW;
+						Q.w2 = M.w2; Q.capw2 = PS_MAXWIN; Q.w2_ovf = 2; Q.stage = M.stage; Q.capstage = PS_STAGE;
 						ovl = zmo_pair_seed_strand(M.rs, n, d, par, Q, &nwin, &ovf);
+						fast = ovf != 2;
 					}
-					if(!in_smem || ovf == 2) ovl = zmo_pair_seed_strand(rs, n, d, par, P, &nwin, &ovf);      /* global-memory path */
-					M.bc[0] = ovl; M.bc[1] = (int)nwin; M.bc[2] = ovf;
+					if(!fast) ovl = zmo_pair_seed_strand(rs, n, d, par, P, &nwin, &ovf);      /* global-memory path */
+					M.bc[0] = ovl; M.bc[1] = (int)nwin; M.bc[2] = ovf; M.bc[3] = fast;
 				}
 				__syncwarp();
-				const int ovl = M.bc[0]; const uint32_t nwin = (uint32_t)M.bc[1]; const int ovf = M.bc[2];
+				const int ovl = M.bc[0]; const uint32_t nwin = (uint32_t)M.bc[1]; const int ovf = M.bc[2]; const DevWin *W2 = M.bc[3]? M.w2 : P.w2;
 				__syncwarp();
 				if(ovf){ if(lane == 0) atomicAdd(O.overflow, 1ULL); break; }
 				S.ovl[d] = ovl;
 				if((uint32_t)ovl >= par.ztot){
 					uint32_t kw = 0, ka = 0;
-					for(uint32_t j = 0; j < nwin; j++) if(!P.w2[j].closed){ kw++; ka += P.w2[j].anc1 - P.w2[j].anc0; }
+					for(uint32_t j = 0; j < nwin; j++) if(!W2[j].closed){ kw++; ka += W2[j].anc1 - W2[j].anc0; }
 					unsigned long long w0 = 0, a0 = 0;
 					if(lane == 0){ w0 = atomicAdd(O.cur_wins, (unsigned long long)kw); a0 = atomicAdd(O.cur_anc, (unsigned long long)ka); }
 					w0 = __shfl_sync(0xffffffffu, w0, 0); a0 = __shfl_sync(0xffffffffu, a0, 0);
 					if(w0 + kw > O.cap_wins || a0 + ka > O.cap_anc){ if(lane == 0) atomicAdd(O.overflow, 1ULL); break; }
 					unsigned long long wi = w0, ai = a0;
 					for(uint32_t j = 0; j < nwin; j++){
-						DevWin w = P.w2[j];
+						DevWin w = W2[j];
 						if(w.closed) continue;
 						const uint32_t na = w.anc1 - w.anc0;
 						for(uint32_t k = lane; k < na; k += 32) O.anc[ai + k] = P.a2[w.anc0 + k];

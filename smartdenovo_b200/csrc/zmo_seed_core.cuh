@@ -198,7 +198,9 @@ ZMO_HDN int32_t zmo_median_select(int32_t *rs, int32_t size){
 
 struct SeedPar { uint32_t zsize, kwin, kstep, zovl, ztot; int W; };
 struct WinScratch { uint32_t *ts; int32_t *as; uint32_t *wb, *we, *wo; uint32_t capt, capw; };     /* ts/as hold capt entries, wb/we/wo capw */
-struct WinOut { DevWin *wins; uint32_t nwin, capwin; DevZPair *anc; uint32_t nanc, capanc; int overflow; };
+/* stage: optional fast scratch (shared memory) where a window's anchors are gathered, sorted and measured before the
+ * accepted ones are appended to anc; capwin_ovf: overflow code when wins is full (1 = grow arenas, 2 = retry in global) */
+struct WinOut { DevWin *wins; uint32_t nwin, capwin; DevZPair *anc; uint32_t nanc, capanc; int overflow; DevZPair *stage; uint32_t capstage; int capwin_ovf; };
 
 #define ZMO_KWIN_MAX_OFFSET_DEV 50
 #define ZMO_WIN_OVL_MASK 0x1FFFFFFFu
@@ -238,18 +240,28 @@ ZMO_HDN uint32_t zmo_windows_in_span(const DevZPair *rs, int dir, uint32_t beg, 
 		const uint32_t size = O.nanc; int32_t offset, offn = 0; DevWin W0;
 		for(j = S.wb[i]; j <= S.we[i]; j++) S.as[offn++] = (int32_t)rs[S.ts[j]].off1 - (int32_t)rs[S.ts[j]].off2;
 		offset = zmo_median_select(S.as, offn);
+		/* anchors within +-50 of the median diagonal: gathered into the staging buffer when they fit (so that the sort
+		 * and the measurements run in fast memory and rejected windows never touch the anchor arena) */
+		uint32_t na = 0;
 		for(j = S.wb[i]; j <= S.we[i]; j++){
 			const DevZPair &p = rs[S.ts[j]]; const int32_t off = (int32_t)p.off1 - (int32_t)p.off2;
 			if(off < offset - ZMO_KWIN_MAX_OFFSET_DEV || off > offset + ZMO_KWIN_MAX_OFFSET_DEV) continue;
-			if(O.nanc >= O.capanc){ O.overflow = 1; return ret; }
-			O.anc[O.nanc++] = p;
+			na++;
 		}
-		if(O.nanc == size) continue;
-		zmo_ref_sort(O.anc + size, (size_t)(O.nanc - size), GtZPairOff1());
+		if(na == 0) continue;
+		if(size + na > O.capanc){ O.overflow = 1; return ret; }
+		DevZPair *A = (O.stage && na <= O.capstage)? O.stage : O.anc + size;
+		na = 0;
+		for(j = S.wb[i]; j <= S.we[i]; j++){
+			const DevZPair &p = rs[S.ts[j]]; const int32_t off = (int32_t)p.off1 - (int32_t)p.off2;
+			if(off < offset - ZMO_KWIN_MAX_OFFSET_DEV || off > offset + ZMO_KWIN_MAX_OFFSET_DEV) continue;
+			A[na++] = p;
+		}
+		zmo_ref_sort(A, (size_t)na, GtZPairOff1());
 		W0.closed = 0; W0.dir = (uint8_t)dir; W0.pad = 0; W0.pb2 = 0; W0.anc0 = size; W0.beg[0] = W0.beg[1] = 0x7FFFFFFF; W0.end[0] = W0.end[1] = 0;
 		ol = lst = 0;
-		for(j = size; j < O.nanc; j++){
-			const DevZPair &p = O.anc[j];
+		for(j = 0; j < na; j++){
+			const DevZPair &p = A[j];
 			ol += (p.off1 > lst)? (uint32_t)p.len1 : p.off1 + p.len1 - lst;
 			lst = p.off1 + p.len1;
 			if((int)p.off1 < W0.beg[0]) W0.beg[0] = p.off1;
@@ -257,12 +269,14 @@ ZMO_HDN uint32_t zmo_windows_in_span(const DevZPair *rs, int dir, uint32_t beg, 
 			if((int)p.off2 < W0.beg[1]) W0.beg[1] = p.off2;
 			if((int)(p.off2 + p.len2) > W0.end[1]) W0.end[1] = p.off2 + p.len2;
 		}
-		if(ol * 2 < zovl){ O.nanc = size; continue; }
+		if(ol * 2 < zovl) continue;
 		if(ret){
 			const DevWin &w = O.wins[O.nwin - 1];
-			if(W0.end[1] <= (int)(w.end[1] + kwin / 3) && ol <= w.ovl){ O.nanc = size; continue; }
+			if(W0.end[1] <= (int)(w.end[1] + kwin / 3) && ol <= w.ovl) continue;
 		}
-		if(O.nwin >= O.capwin){ O.overflow = 1; return ret; }
+		if(O.nwin >= O.capwin){ O.overflow = O.capwin_ovf; return ret; }
+		if(A != O.anc + size) for(j = 0; j < na; j++) O.anc[size + j] = A[j];
+		O.nanc = size + na;
 		ret++;
 		W0.ovl = ol & ZMO_WIN_OVL_MASK; W0.anc1 = O.nanc;
 		O.wins[O.nwin++] = W0;
@@ -351,7 +365,7 @@ ZMO_HDN int zmo_chain_windows(DevWin *w, uint32_t n, int W, int *nodes){
  * Scratch layout for a pair with n z-mer matches (bytes): see zmo_pair_scratch_bytes().  After the
  * call the strand's windows (with closed flags set by the chain) are in S.w2[0..nwin) and their
  * anchors in S.a2; the caller copies the kept ones out. */
-struct PairScratch { WinScratch ws; DevWin *w2; DevZPair *a2; uint32_t cap; };
+struct PairScratch { WinScratch ws; DevWin *w2; DevZPair *a2; uint32_t cap, capw2; DevZPair *stage; uint32_t capstage; int w2_ovf; };
 /* F = capacity factor for windows/anchors (an anchor can belong to several overlapping sub-windows,
  * hzm_aln.h:483-514, so the anchor list of a strand may exceed the match count) */
 ZMO_HD size_t zmo_pair_scratch_per(uint32_t F){ return 5 * 4 + (size_t)F * (sizeof(DevWin) + sizeof(DevZPair)); }
@@ -366,12 +380,12 @@ ZMO_HD PairScratch zmo_pair_scratch_carve(uint8_t *base, uint32_t n, uint32_t F)
 	P.ws.we = (uint32_t*)p; p += (size_t)n * 4;
 	P.ws.wo = (uint32_t*)p;
 	P.ws.capt = n; P.ws.capw = n;
-	P.cap = n * F;
+	P.cap = n * F; P.capw2 = n * F; P.stage = nullptr; P.capstage = 0; P.w2_ovf = 1;
 	return P;
 }
 /* returns the chain weight (0 when the strand has no window); nwin/nanc = all windows found */
 ZMO_HDN int zmo_pair_seed_strand(const DevZPair *cache, uint32_t n, int dir, const SeedPar &par, PairScratch &P, uint32_t *nwin, int *overflow){
-	WinOut O; O.wins = P.w2; O.nwin = 0; O.capwin = P.cap; O.anc = P.a2; O.nanc = 0; O.capanc = P.cap; O.overflow = 0;
+	WinOut O; O.wins = P.w2; O.nwin = 0; O.capwin = P.capw2; O.anc = P.a2; O.nanc = 0; O.capanc = P.cap; O.overflow = 0; O.stage = P.stage; O.capstage = P.capstage; O.capwin_ovf = P.w2_ovf;
 	int ovl = 0;
 	if(zmo_pair_windows_strand(cache, n, dir, O, P.ws, par) && !O.overflow){
 		/* ts/as (8 bytes per match) are free again: reuse as chain nodes (8 bytes per window) */
