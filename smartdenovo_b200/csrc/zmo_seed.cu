@@ -146,13 +146,13 @@ struct SeedOut { DevWin *wins; DevZPair *anc; unsigned long long cap_wins, cap_a
 /* Window finding + chaining, one WARP per pair: the lanes stage the pair's match list in shared memory, lane 0 runs the
  * order-exact serial logic of zmo_seed_core.cuh on it (shared-memory latency instead of global), the lanes copy the
  * kept windows/anchors out.  Lists that do not fit the shared-memory budget run from global memory. */
-#define PS_WARPS 4
-#define PS_MAXN 2048      /* match list entries staged per pair */
+#define PS_WARPS 8
 #define PS_MAXT 1024      /* strand entries of one sliding span */
 #define PS_MAXW 256       /* sub-windows of one span */
 #define PS_STAGE 256      /* anchors of one window */
 #define PS_MAXWIN 112     /* windows of one strand */
-struct PSSmem { DevZPair rs[PS_MAXN]; DevZPair stage[PS_STAGE]; DevWin w2[PS_MAXWIN]; uint32_t ts[PS_MAXT]; int32_t as[PS_MAXT]; uint32_t wb[PS_MAXW], we[PS_MAXW], wo[PS_MAXW]; int bc[8]; };
+/* per-warp scratch in shared memory (~25 KB, 8 warps per SM); the read-only match list itself is read through L1 */
+struct PSSmem { uint64_t ts[PS_MAXT]; uint64_t ak[PS_STAGE]; DevZPair stage[PS_STAGE]; DevWin w2[PS_MAXWIN]; int32_t as[PS_MAXT]; uint32_t wb[PS_MAXW], we[PS_MAXW], wo[PS_MAXW]; int bc[8]; };
 __global__ void __launch_bounds__(32 * PS_WARPS) k_p_seed(const unsigned long long *cache_off, uint32_t np, DevZPair *cache, const uint8_t *tie, const uint32_t *pc, DevReads R,
 		uint8_t *scratch, size_t per, uint32_t F, SeedPar par, SeedOut O, zmo_pairseed_t *seeds, unsigned long long *work){
 	extern __shared__ __align__(16) uint8_t ps_raw[];
@@ -171,20 +171,15 @@ __global__ void __launch_bounds__(32 * PS_WARPS) k_p_seed(const unsigned long lo
 			if(tie[p] && lane == 0){ GtZPairEmit g; g.clen = R.len[pc[p]]; zmo_ref_sort(rs, (size_t)n, g); zmo_ref_sort(rs, (size_t)n, GtZPairOff12()); }
 			__syncwarp();
 			uint8_t *scr = scratch + c0 * per + (size_t)64 * p;
-			const bool in_smem = n <= PS_MAXN;
-			if(in_smem){
-				const uint4 *src = (const uint4*)rs; uint4 *dst = (uint4*)M.rs;
-				for(uint32_t k = lane; k < n; k += 32) dst[k] = src[k];
-			}
-			__syncwarp();
+			const bool in_smem = true;
 			for(int d = 0; d < 2; d++){
 				PairScratch P = zmo_pair_scratch_carve(scr, n, F);
 				if(lane == 0){
 					uint32_t nwin = 0; int ovf = 0, ovl = 0, fast = 0;
 					if(in_smem){
-						PairScratch Q = P; Q.ws.ts = M.ts; Q.ws.as = M.as; Q.ws.wb = M.wb; Q.ws.we = M.we; Q.ws.wo = M.wo; Q.ws.capt = PS_MAXT; Q.ws.capw = PS_MAXW;
+						PairScratch Q = P; Q.ws.ts = M.ts; Q.ws.ak = M.ak; Q.ws.as = M.as; Q.ws.wb = M.wb; Q.ws.we = M.we; Q.ws.wo = M.wo; Q.ws.capt = PS_MAXT; Q.ws.capw = PS_MAXW;
 						Q.w2 = M.w2; Q.capw2 = PS_MAXWIN; Q.w2_ovf = 2; Q.stage = M.stage; Q.capstage = PS_STAGE;
-						ovl = zmo_pair_seed_strand(M.rs, n, d, par, Q, &nwin, &ovf);
+						ovl = zmo_pair_seed_strand(rs, n, d, par, Q, &nwin, &ovf);
 						fast = ovf != 2;
 					}
 					if(!fast) ovl = zmo_pair_seed_strand(rs, n, d, par, P, &nwin, &ovf);      /* global-memory path */
@@ -364,7 +359,7 @@ extern "C" int zmo_pair_windows(zmo_ctx *c, int slot, const zmo_pair_t *pairs, u
 		{
 			static bool attr_set = false;
 			if(!attr_set){ CUDA_TRY(cudaFuncSetAttribute(k_p_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PS_WARPS * sizeof(PSSmem)))); attr_set = true; }
-			const int grid = (int)std::min<uint64_t>((np + PS_WARPS - 1) / PS_WARPS, (uint64_t)c->n_sm);
+			const int grid = (int)std::min<uint64_t>((np + PS_WARPS - 1) / PS_WARPS, (uint64_t)c->n_sm);      /* one CTA of 8 warps per SM (shared-memory bound) */
 			k_p_seed<<<grid, 32 * PS_WARPS, PS_WARPS * sizeof(PSSmem), c->stream>>>(W.cache_off, np, W.cache, W.tie, W.pc, dev_reads(c), c->s6.as<uint8_t>(), per, F, par, O, SL.seeds.as<zmo_pairseed_t>(), ctr + CTR_WORK); c->launches++;
 		}
 		CUDA_TRY(cudaGetLastError());

@@ -197,13 +197,23 @@ ZMO_HDN int32_t zmo_median_select(int32_t *rs, int32_t size){
 }
 
 struct SeedPar { uint32_t zsize, kwin, kstep, zovl, ztot; int W; };
-struct WinScratch { uint32_t *ts; int32_t *as; uint32_t *wb, *we, *wo; uint32_t capt, capw; };     /* ts/as hold capt entries, wb/we/wo capw */
+struct WinScratch { uint64_t *ts, *ak; int32_t *as; uint32_t *wb, *we, *wo; uint32_t capt, capw; };     /* ts/ak/as hold capt entries, wb/we/wo capw */
 /* stage: optional fast scratch (shared memory) where a window's anchors are gathered, sorted and measured before the
  * accepted ones are appended to anc; capwin_ovf: overflow code when wins is full (1 = grow arenas, 2 = retry in global) */
 struct WinOut { DevWin *wins; uint32_t nwin, capwin; DevZPair *anc; uint32_t nanc, capanc; int overflow; DevZPair *stage; uint32_t capstage; int capwin_ovf; };
 
 #define ZMO_KWIN_MAX_OFFSET_DEV 50
 #define ZMO_WIN_OVL_MASK 0x1FFFFFFFu
+
+/* hzm_aln.h:410-578 (fast-chaining branch) */
+/* sort keys: the comparators of the reference look at one field only (off2 at hzm_aln.h:449, off1 at :519), so the
+ * sorts run on packed 64-bit (key | payload) words instead of 16-byte structs reached through an index: same comparison
+ * outcomes, hence the same sort_array permutation, with a fraction of the memory traffic. */
+struct GtTsKey { ZMO_HDM bool operator()(uint64_t a, uint64_t b) const { return (a >> 40) > (b >> 40); } };     /* off2:24 | len2:16 | idx:24 */
+struct GtHi32 { ZMO_HDM bool operator()(uint64_t a, uint64_t b) const { return (a >> 32) > (b >> 32); } };       /* key:32 | payload:32 */
+#define ZMO_TS_OFF2(k) ((uint32_t)((k) >> 40))
+#define ZMO_TS_LEN2(k) ((uint32_t)(((k) >> 24) & 0xFFFFu))
+#define ZMO_TS_IDX(k)  ((uint32_t)((k) & 0xFFFFFFu))
 
 /* hzm_aln.h:410-578 (fast-chaining branch) */
 ZMO_HDN uint32_t zmo_windows_in_span(const DevZPair *rs, int dir, uint32_t beg, uint32_t end, int bound, WinOut &O, const WinScratch &S, const SeedPar &par){
@@ -215,53 +225,56 @@ ZMO_HDN uint32_t zmo_windows_in_span(const DevZPair *rs, int dir, uint32_t beg, 
 	}
 	for(i = beg; i < end; i++) if(!(rs[i].dir1 ^ rs[i].dir2 ^ dir)) n++;
 	if(n * zsize < zovl) return 0;
-	if(n > S.capt){ O.overflow = 2; return 0; }
+	if(n > S.capt || end - beg >= (1u << 24)){ O.overflow = 2; return 0; }
 	n = 0;
-	for(i = beg; i < end; i++) if(!(rs[i].dir1 ^ rs[i].dir2 ^ dir)) S.ts[n++] = i;
-	{ GtIdxOff2 g; g.rs = rs; zmo_ref_sort(S.ts, (size_t)n, g); }
+	for(i = beg; i < end; i++){ const DevZPair &p = rs[i]; if(!(p.dir1 ^ p.dir2 ^ dir)) S.ts[n++] = ((uint64_t)p.off2 << 40) | ((uint64_t)p.len2 << 24) | (i - beg); }
+	zmo_ref_sort(S.ts, (size_t)n, GtTsKey());
 	ol = 0; lst = 0;
 	for(i = j = 0; i < n; i++){
-		const DevZPair &p = rs[S.ts[i]];
-		while((uint32_t)p.off2 + p.len2 > rs[S.ts[j]].off2 + kwin && j + 1 < n){
-			const DevZPair &p0 = rs[S.ts[j++]]; const DevZPair &p1 = rs[S.ts[j]];
-			const uint32_t s = p1.off2, t = p0.off2 + p0.len2;
+		const uint64_t pk = S.ts[i]; const uint32_t p_off2 = ZMO_TS_OFF2(pk), p_len2 = ZMO_TS_LEN2(pk);
+		while(p_off2 + p_len2 > ZMO_TS_OFF2(S.ts[j]) + kwin && j + 1 < n){
+			const uint64_t k0 = S.ts[j++], k1 = S.ts[j];
+			const uint32_t s = ZMO_TS_OFF2(k1), t = ZMO_TS_OFF2(k0) + ZMO_TS_LEN2(k0);
 			ol2 = s < t? t - s : 0;
-			ol = ol + ol2 - p0.len2;
+			ol = ol + ol2 - ZMO_TS_LEN2(k0);
 		}
-		ol += (p.off2 > lst)? (uint32_t)p.len2 : p.off2 + p.len2 - lst;
-		lst = p.off2 + p.len2;
+		ol += (p_off2 > lst)? p_len2 : p_off2 + p_len2 - lst;
+		lst = p_off2 + p_len2;
 		if(ol >= zovl){
-			if(n2 && ( rs[S.ts[i]].off2 <= rs[S.ts[S.we[n2-1]]].off2 + kwin / 3 || rs[S.ts[j]].off2 <= rs[S.ts[S.wb[n2-1]]].off2 + kwin / 3 )){
+			if(n2 && ( p_off2 <= ZMO_TS_OFF2(S.ts[S.we[n2-1]]) + kwin / 3 || ZMO_TS_OFF2(S.ts[j]) <= ZMO_TS_OFF2(S.ts[S.wb[n2-1]]) + kwin / 3 )){
 				if(ol > S.wo[n2-1]){ S.wb[n2-1] = j; S.we[n2-1] = i; S.wo[n2-1] = ol; }
 			} else { if(n2 >= S.capw){ O.overflow = 2; return 0; } S.wb[n2] = j; S.we[n2] = i; S.wo[n2] = ol; n2++; }
 		}
 	}
 	for(i = 0; i < n2; i++){
 		const uint32_t size = O.nanc; int32_t offset, offn = 0; DevWin W0;
-		for(j = S.wb[i]; j <= S.we[i]; j++) S.as[offn++] = (int32_t)rs[S.ts[j]].off1 - (int32_t)rs[S.ts[j]].off2;
+		for(j = S.wb[i]; j <= S.we[i]; j++){ const DevZPair &p = rs[beg + ZMO_TS_IDX(S.ts[j])]; S.as[offn++] = (int32_t)p.off1 - (int32_t)p.off2; }
 		offset = zmo_median_select(S.as, offn);
-		/* anchors within +-50 of the median diagonal: gathered into the staging buffer when they fit (so that the sort
-		 * and the measurements run in fast memory and rejected windows never touch the anchor arena) */
+		/* anchors within +-50 of the median diagonal */
 		uint32_t na = 0;
 		for(j = S.wb[i]; j <= S.we[i]; j++){
-			const DevZPair &p = rs[S.ts[j]]; const int32_t off = (int32_t)p.off1 - (int32_t)p.off2;
+			const DevZPair &p = rs[beg + ZMO_TS_IDX(S.ts[j])]; const int32_t off = (int32_t)p.off1 - (int32_t)p.off2;
 			if(off < offset - ZMO_KWIN_MAX_OFFSET_DEV || off > offset + ZMO_KWIN_MAX_OFFSET_DEV) continue;
 			na++;
 		}
 		if(na == 0) continue;
 		if(size + na > O.capanc){ O.overflow = 1; return ret; }
-		DevZPair *A = (O.stage && na <= O.capstage)? O.stage : O.anc + size;
+		/* staged path: gather into fast memory, sort (off1 | slot) keys, measure through the keys, copy accepted windows out in
+		 * sorted order; otherwise gather straight into the arena and sort the structs there */
+		const bool staged = O.stage && na <= O.capstage;
+		DevZPair *A = staged? O.stage : O.anc + size;
 		na = 0;
 		for(j = S.wb[i]; j <= S.we[i]; j++){
-			const DevZPair &p = rs[S.ts[j]]; const int32_t off = (int32_t)p.off1 - (int32_t)p.off2;
+			const DevZPair &p = rs[beg + ZMO_TS_IDX(S.ts[j])]; const int32_t off = (int32_t)p.off1 - (int32_t)p.off2;
 			if(off < offset - ZMO_KWIN_MAX_OFFSET_DEV || off > offset + ZMO_KWIN_MAX_OFFSET_DEV) continue;
+			if(staged) S.ak[na] = ((uint64_t)p.off1 << 32) | na;
 			A[na++] = p;
 		}
-		zmo_ref_sort(A, (size_t)na, GtZPairOff1());
+		if(staged) zmo_ref_sort(S.ak, (size_t)na, GtHi32()); else zmo_ref_sort(A, (size_t)na, GtZPairOff1());
 		W0.closed = 0; W0.dir = (uint8_t)dir; W0.pad = 0; W0.pb2 = 0; W0.anc0 = size; W0.beg[0] = W0.beg[1] = 0x7FFFFFFF; W0.end[0] = W0.end[1] = 0;
 		ol = lst = 0;
 		for(j = 0; j < na; j++){
-			const DevZPair &p = A[j];
+			const DevZPair &p = staged? A[(uint32_t)S.ak[j]] : A[j];
 			ol += (p.off1 > lst)? (uint32_t)p.len1 : p.off1 + p.len1 - lst;
 			lst = p.off1 + p.len1;
 			if((int)p.off1 < W0.beg[0]) W0.beg[0] = p.off1;
@@ -275,7 +288,7 @@ ZMO_HDN uint32_t zmo_windows_in_span(const DevZPair *rs, int dir, uint32_t beg, 
 			if(W0.end[1] <= (int)(w.end[1] + kwin / 3) && ol <= w.ovl) continue;
 		}
 		if(O.nwin >= O.capwin){ O.overflow = O.capwin_ovf; return ret; }
-		if(A != O.anc + size) for(j = 0; j < na; j++) O.anc[size + j] = A[j];
+		if(staged) for(j = 0; j < na; j++) O.anc[size + j] = A[(uint32_t)S.ak[j]];
 		O.nanc = size + na;
 		ret++;
 		W0.ovl = ol & ZMO_WIN_OVL_MASK; W0.anc1 = O.nanc;
@@ -368,13 +381,14 @@ ZMO_HDN int zmo_chain_windows(DevWin *w, uint32_t n, int W, int *nodes){
 struct PairScratch { WinScratch ws; DevWin *w2; DevZPair *a2; uint32_t cap, capw2; DevZPair *stage; uint32_t capstage; int w2_ovf; };
 /* F = capacity factor for windows/anchors (an anchor can belong to several overlapping sub-windows,
  * hzm_aln.h:483-514, so the anchor list of a strand may exceed the match count) */
-ZMO_HD size_t zmo_pair_scratch_per(uint32_t F){ return 5 * 4 + (size_t)F * (sizeof(DevWin) + sizeof(DevZPair)); }
+ZMO_HD size_t zmo_pair_scratch_per(uint32_t F){ return 8 + 8 + 4 * 4 + (size_t)F * (sizeof(DevWin) + sizeof(DevZPair)); }
 ZMO_HD size_t zmo_pair_scratch_bytes(uint32_t n, uint32_t F){ return (size_t)n * zmo_pair_scratch_per(F) + 64; }
 ZMO_HD PairScratch zmo_pair_scratch_carve(uint8_t *base, uint32_t n, uint32_t F){
 	PairScratch P; uint8_t *p = base;
 	P.a2 = (DevZPair*)p; p += (size_t)n * F * sizeof(DevZPair);
 	P.w2 = (DevWin*)p; p += (size_t)n * F * sizeof(DevWin);
-	P.ws.ts = (uint32_t*)p; p += (size_t)n * 4;
+	P.ws.ts = (uint64_t*)p; p += (size_t)n * 8;
+	P.ws.ak = (uint64_t*)p; p += (size_t)n * 8;
 	P.ws.as = (int32_t*)p; p += (size_t)n * 4;
 	P.ws.wb = (uint32_t*)p; p += (size_t)n * 4;
 	P.ws.we = (uint32_t*)p; p += (size_t)n * 4;
