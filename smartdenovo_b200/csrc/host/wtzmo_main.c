@@ -980,10 +980,10 @@ wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	par->max_overhang = 2 * par->xvar;
 	par->kstep = par->kwin / 2;
 	if((env = getenv("ZMO_DEVICE"))) S->device = atoi(env); else if((env = getenv("LOCAL_RANK"))) S->device = atoi(env);
-	z->batch_reads = (env = getenv("ZMO_BATCH_READS"))? atoi(env) : 256;
-	z->batch_pairs = (env = getenv("ZMO_BATCH_PAIRS"))? atoi(env) : 16384;
+	z->batch_reads = (env = getenv("ZMO_BATCH_READS"))? atoi(env) : 512;
+	z->batch_pairs = (env = getenv("ZMO_BATCH_PAIRS"))? atoi(env) : 40000;
 	z->pipeline = (env = getenv("ZMO_PIPELINE"))? atoi(env) : 1;
-	z->wave_margin = (env = getenv("ZMO_WAVE0"))? atoi(env) : 16;       /* seeds per read in the first DP wave (doubles per wave); < 0: align every seed up front */
+	z->wave_margin = (env = getenv("ZMO_WAVE0"))? atoi(env) : 8;       /* seeds per read in the first DP wave (doubles per wave); < 0: align every seed up front */
 	pthread_mutex_init(&z->dev_mu, NULL);
 	if(z->batch_reads < 1) z->batch_reads = 1;
 	fprintf(stderr, "[wtzmo-b200] loading long reads\n");
