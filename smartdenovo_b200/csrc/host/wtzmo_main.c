@@ -328,7 +328,7 @@ typedef struct {
 	/* page-locked result buffers reused across batches */
 	zmo_record_t *pin_recs[2]; size_t pin_recs_cap[2]; u32 *pin_cig[2]; size_t pin_cig_cap[2]; int pin_sel, pipeline;
 	pthread_mutex_t dev_mu;             /* one device call at a time (worker thread vs on-demand waves of the replay) */
-	u64 n_waves, n_wave_tasks; int wave_margin;
+	u64 n_waves, n_wave_tasks; int wave_margin, wave_growth;
 } wz_t;
 
 static double now_s(void){ struct timeval tv; gettimeofday(&tv, NULL); return tv.tv_sec + 1e-6 * tv.tv_usec; }
@@ -724,7 +724,7 @@ static void batch_compute(wz_t *z, batch_t *b){
 			if(wave){ vec_push(b->extra, (void*)recs); vec_push(b->extra, (void*)cig); }
 			vec_free(tk);
 			for(i=0;i<nr;i++) if(pos[i] >= 0) pos[i] = dry_walk(z, b, &b->reads.a[i], &sv[i]);
-			wave ++; if(chunk < ((size_t)1 << 20)) chunk *= 2;
+			wave ++; if(chunk < ((size_t)1 << 20)) chunk *= (size_t)z->wave_growth;
 		}
 		for(i=0;i<nr;i++) vec_free(sv[i]);
 		free(sv); free(pos);
@@ -980,10 +980,11 @@ wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	par->max_overhang = 2 * par->xvar;
 	par->kstep = par->kwin / 2;
 	if((env = getenv("ZMO_DEVICE"))) S->device = atoi(env); else if((env = getenv("LOCAL_RANK"))) S->device = atoi(env);
-	z->batch_reads = (env = getenv("ZMO_BATCH_READS"))? atoi(env) : 512;
+	z->batch_reads = (env = getenv("ZMO_BATCH_READS"))? atoi(env) : 384;
 	z->batch_pairs = (env = getenv("ZMO_BATCH_PAIRS"))? atoi(env) : 40000;
 	z->pipeline = (env = getenv("ZMO_PIPELINE"))? atoi(env) : 1;
 	z->wave_margin = (env = getenv("ZMO_WAVE0"))? atoi(env) : 8;       /* seeds per read in the first DP wave (doubles per wave); < 0: align every seed up front */
+	z->wave_growth = (env = getenv("ZMO_WAVE_GROWTH"))? atoi(env) : 4; if(z->wave_growth < 2) z->wave_growth = 2;
 	pthread_mutex_init(&z->dev_mu, NULL);
 	if(z->batch_reads < 1) z->batch_reads = 1;
 	fprintf(stderr, "[wtzmo-b200] loading long reads\n");

@@ -146,12 +146,13 @@ struct SeedOut { DevWin *wins; DevZPair *anc; unsigned long long cap_wins, cap_a
 /* Window finding + chaining, one WARP per pair: the lanes stage the pair's match list in shared memory, lane 0 runs the
  * order-exact serial logic of zmo_seed_core.cuh on it (shared-memory latency instead of global), the lanes copy the
  * kept windows/anchors out.  Lists that do not fit the shared-memory budget run from global memory. */
-#define PS_WARPS 8
-#define PS_MAXT 1024      /* strand entries of one sliding span */
-#define PS_MAXW 256       /* sub-windows of one span */
-#define PS_STAGE 256      /* anchors of one window */
-#define PS_MAXWIN 112     /* windows of one strand */
-/* per-warp scratch in shared memory (~25 KB, 8 warps per SM); the read-only match list itself is read through L1 */
+#define PS_WARPS 14
+#define PS_MAXT 512       /* strand entries of one sliding span */
+#define PS_MAXW 128       /* sub-windows of one span */
+#define PS_STAGE 192      /* anchors of one window */
+#define PS_MAXWIN 64      /* windows of one strand */
+/* per-warp scratch in shared memory (~14.6 KB, 14 warps per SM: the serial lane is latency bound, so occupancy is what
+ * buys throughput); larger spans / windows fall back to the global-memory scratch; the read-only match list is read through L1 */
 struct PSSmem { uint64_t ts[PS_MAXT]; uint64_t ak[PS_STAGE]; DevZPair stage[PS_STAGE]; DevWin w2[PS_MAXWIN]; int32_t as[PS_MAXT]; uint32_t wb[PS_MAXW], we[PS_MAXW], wo[PS_MAXW]; int bc[8]; };
 __global__ void __launch_bounds__(32 * PS_WARPS) k_p_seed(const unsigned long long *cache_off, uint32_t np, DevZPair *cache, const uint8_t *tie, const uint32_t *pc, DevReads R,
 		uint8_t *scratch, size_t per, uint32_t F, SeedPar par, SeedOut O, zmo_pairseed_t *seeds, unsigned long long *work){
