@@ -15,6 +15,7 @@
 #include "zmo_ctx.cuh"
 #include "zmo_seed_core.cuh"
 #include "zmo_seed.cuh"
+#include "zmo_seed_warp.cuh"
 
 #define CUB_CALL(c, call_expr) do { size_t _tb = 0; void *_tp = nullptr; { auto d_temp = _tp; size_t &temp_bytes = _tb; CUDA_TRY(call_expr); } \
 	if((c)->cubtmp.reserve(_tb + 256)) return ZMO_ERR_CUDA; { void *d_temp = (c)->cubtmp.p; size_t &temp_bytes = _tb; CUDA_TRY(call_expr); } (c)->launches++; } while(0)
@@ -153,7 +154,7 @@ struct SeedOut { DevWin *wins; DevZPair *anc; unsigned long long cap_wins, cap_a
 #define PS_MAXWIN 64      /* windows of one strand */
 /* per-warp scratch in shared memory (~14.6 KB, 14 warps per SM: the serial lane is latency bound, so occupancy is what
  * buys throughput); larger spans / windows fall back to the global-memory scratch; the read-only match list is read through L1 */
-struct PSSmem { uint64_t ts[PS_MAXT]; uint64_t ak[PS_STAGE]; DevZPair stage[PS_STAGE]; DevWin w2[PS_MAXWIN]; int32_t as[PS_MAXT]; uint32_t wb[PS_MAXW], we[PS_MAXW], wo[PS_MAXW]; int bc[8]; };
+struct PSSmem { uint64_t ts[PS_MAXT]; uint64_t ak[256]; DevZPair stage[PS_STAGE]; DevWin w2[PS_MAXWIN]; int32_t as[PS_MAXT]; uint32_t wb[PS_MAXW], we[PS_MAXW], wo[PS_MAXW]; int bc[8]; };
 __global__ void __launch_bounds__(32 * PS_WARPS) k_p_seed(const unsigned long long *cache_off, uint32_t np, DevZPair *cache, const uint8_t *tie, const uint32_t *pc, DevReads R,
 		uint8_t *scratch, size_t per, uint32_t F, SeedPar par, SeedOut O, zmo_pairseed_t *seeds, unsigned long long *work){
 	extern __shared__ __align__(16) uint8_t ps_raw[];
@@ -175,20 +176,22 @@ __global__ void __launch_bounds__(32 * PS_WARPS) k_p_seed(const unsigned long lo
 			const bool in_smem = true;
 			for(int d = 0; d < 2; d++){
 				PairScratch P = zmo_pair_scratch_carve(scr, n, F);
-				if(lane == 0){
-					uint32_t nwin = 0; int ovf = 0, ovl = 0, fast = 0;
-					if(in_smem){
-						PairScratch Q = P; Q.ws.ts = M.ts; Q.ws.ak = M.ak; Q.ws.as = M.as; Q.ws.wb = M.wb; Q.ws.we = M.we; Q.ws.wo = M.wo; Q.ws.capt = PS_MAXT; Q.ws.capw = PS_MAXW;
-						Q.w2 = M.w2; Q.capw2 = PS_MAXWIN; Q.w2_ovf = 2; Q.stage = M.stage; Q.capstage = PS_STAGE;
-						ovl = zmo_pair_seed_strand(rs, n, d, par, Q, &nwin, &ovf);
-						fast = ovf != 2;
-					}
-					if(!fast) ovl = zmo_pair_seed_strand(rs, n, d, par, P, &nwin, &ovf);      /* global-memory path */
-					M.bc[0] = ovl; M.bc[1] = (int)nwin; M.bc[2] = ovf; M.bc[3] = fast;
+				uint32_t nwin = 0; int ovf = 0, ovl = 0;
+				{
+					/* cooperative path: scratch in shared memory, all lanes */
+					PairScratch Q = P; Q.ws.ts = M.ts; Q.ws.ak = M.ak; Q.ws.as = M.as; Q.ws.wb = M.wb; Q.ws.we = M.we; Q.ws.wo = M.wo; Q.ws.capt = PS_MAXT; Q.ws.capw = PS_MAXW;
+					Q.w2 = M.w2; Q.capw2 = PS_MAXWIN; Q.w2_ovf = 2; Q.stage = M.stage; Q.capstage = PS_STAGE;
+					ovl = zmo_pair_seed_strand_w(rs, n, d, par, Q, &nwin, &ovf, lane);
 				}
-				__syncwarp();
-				const int ovl = M.bc[0]; const uint32_t nwin = (uint32_t)M.bc[1]; const int ovf = M.bc[2]; const DevWin *W2 = M.bc[3]? M.w2 : P.w2;
-				__syncwarp();
+				const bool fast = ovf != 2;
+				if(!fast){
+					/* a span / window / strand exceeded the shared-memory scratch: serial exact path on global scratch */
+					if(lane == 0){ ovl = zmo_pair_seed_strand(rs, n, d, par, P, &nwin, &ovf); M.bc[0] = ovl; M.bc[1] = (int)nwin; M.bc[2] = ovf; }
+					__syncwarp();
+					ovl = M.bc[0]; nwin = (uint32_t)M.bc[1]; ovf = M.bc[2];
+					__syncwarp();
+				}
+				const DevWin *W2 = fast? M.w2 : P.w2;
 				if(ovf){ if(lane == 0) atomicAdd(O.overflow, 1ULL); break; }
 				S.ovl[d] = ovl;
 				if((uint32_t)ovl >= par.ztot){
