@@ -14,21 +14,19 @@
 #define WRP_SEQW 256
 #define WRP_PER_CTA 4
 
-/* CTA-per-job extension kernels: NT threads x 7 columns per row chunk.  NT = 64 / 128 / 256 serve bands up to
- * 448 / 896 / 1792 columns in one chunk (wider bands loop over chunks), so that mid-size bands do not idle most
- * of a 256-thread CTA or write 1 KB traceback rows. */
-template<int NT, int MODE>
-__global__ void __launch_bounds__(NT, (NT == 256? 3 : (NT == 128? 6 : 10))) k_ext_cta(const DPJob *jobs, const uint32_t *order, uint32_t njobs, DevReads R, DPPar P,
+/* CTA-per-job extension kernels (register-resident sweep): NT threads x C columns per block; classes 1/2/3 =
+ * 64x7 / 128x7 / CL3_NT x CL3_C serve bands up to 435 / 883 / 1639 columns.  The class-3 kernel also takes the
+ * bands beyond that (chunked sweep with rows in global memory). */
+template<int NT, int C, int MODE>
+__global__ void __launch_bounds__(NT, (NT == 256? 2 : (NT == 128? (C > 7? 3 : 5) : 8))) k_ext_cta(const DPJob *jobs, const uint32_t *order, uint32_t njobs, DevReads R, DPPar P,
 		uint32_t *arena, uint32_t *cig_arena, DPRes *res, unsigned long long *ctr, int ctr_work, int ctr_cells){
-	constexpr int CAP = NT * 8;                /* 512 / 1024 / 2048 >= NT*7 + 2 */
-	constexpr int SEQW = NT == 256? 4096 : 2048;
-	__shared__ int s_h[3 * CAP];
+	constexpr int SEQW = (NT == 256 || C > 7)? 4096 : 2048;
 	__shared__ uint32_t s_seq[SEQW];
 	__shared__ int s_red[2 * (NT / 32)];
 	__shared__ long long s_redk[NT / 32];
 	__shared__ int s_misc[16];
 	__shared__ uint32_t s_job;
-	ExecSmem<NT> X; X.carve(s_h, CAP, s_seq, SEQW, s_red, s_redk, s_misc);
+	ExecSmem<NT> X; X.carve(nullptr, 0, s_seq, SEQW, s_red, s_redk, s_misc);
 	const int tid = threadIdx.x;
 	while(1){
 		if(tid == 0) s_job = (uint32_t)atomicAdd(ctr + ctr_work, 1ULL);
@@ -36,20 +34,19 @@ __global__ void __launch_bounds__(NT, (NT == 256? 3 : (NT == 128? 6 : 10))) k_ex
 		const uint32_t jn = s_job;
 		__syncthreads();
 		if(jn >= njobs) break;
-		run_ext_job<NT, EXT_C, MODE>(jobs[order? order[jn] : jn], R, P, X, arena, cig_arena, res, ctr + ctr_cells, tid);
+		run_ext_job<NT, C, MODE>(jobs[order? order[jn] : jn], R, P, X, arena, cig_arena, res, ctr + ctr_cells, tid);
 		__syncthreads();
 	}
 }
 
-/* warp-per-job extension kernel (narrow bands) */
+/* warp-per-job extension kernel (bands up to 211 columns) */
 template<int MODE>
 __global__ void __launch_bounds__(32 * WRP_PER_CTA) k_ext_warp(const DPJob *jobs, const uint32_t *order, uint32_t njobs, DevReads R, DPPar P,
 		uint32_t *arena, uint32_t *cig_arena, DPRes *res, unsigned long long *ctr, int ctr_work, int ctr_cells){
-	__shared__ int s_h[WRP_PER_CTA][3 * WRP_CAP];
 	__shared__ uint32_t s_seq[WRP_PER_CTA][WRP_SEQW];
 	__shared__ int s_misc[WRP_PER_CTA][16];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	ExecSmem<32> X; X.carve(s_h[warp], WRP_CAP, s_seq[warp], WRP_SEQW, nullptr, nullptr, s_misc[warp]);
+	ExecSmem<32> X; X.carve(nullptr, 0, s_seq[warp], WRP_SEQW, nullptr, nullptr, s_misc[warp]);
 	while(1){
 		uint32_t jn = 0;
 		if(lane == 0) jn = (uint32_t)atomicAdd(ctr + ctr_work, 1ULL);
@@ -102,11 +99,11 @@ __global__ void __launch_bounds__(EXT_NT) k_glb_cta(const DPJob *jobs, const uin
 static DPPar dp_par(const zmo_ctx *c){ DPPar P; P.M = c->par.M; P.X = c->par.X; P.I = c->par.O; P.D = c->par.O; P.E = c->par.E; P.T = c->par.T; return P; }
 
 /* ---- launch helpers used by the API and the pipeline --------------------------------------- */
-template<int NT> static void launch_ext_cta(cudaStream_t st, int wk, int mode, int grid, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, DevReads R, DPPar P, uint32_t *arena, uint32_t *cig, DPRes *d_res, unsigned long long *ctr, int ctr_cells){
-	if(mode == 1) k_ext_cta<NT, 1><<<grid, NT, 0, st>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, wk, ctr_cells);
-	else k_ext_cta<NT, 0><<<grid, NT, 0, st>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, wk, ctr_cells);
+template<int NT, int C> static void launch_ext_cta(cudaStream_t st, int wk, int mode, int grid, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, DevReads R, DPPar P, uint32_t *arena, uint32_t *cig, DPRes *d_res, unsigned long long *ctr, int ctr_cells){
+	if(mode == 1) k_ext_cta<NT, C, 1><<<grid, NT, 0, st>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, wk, ctr_cells);
+	else k_ext_cta<NT, C, 0><<<grid, NT, 0, st>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, wk, ctr_cells);
 }
-/* cls: 0 = warp executor (band <= 224), 1/2/3 = CTA of 64/128/256 threads */
+/* cls: 0 = warp executor, 1/2/3 = CTA executors (see ext_class) */
 int zmo_launch_ext_on(zmo_ctx *c, cudaStream_t st, int wk, int mode, int cls, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells){
 	if(n == 0) return 0;
 	unsigned long long *ctr = c->d_ctr.as<unsigned long long>();
@@ -116,9 +113,9 @@ int zmo_launch_ext_on(zmo_ctx *c, cudaStream_t st, int wk, int mode, int cls, co
 		int grid = (int)std::min<uint64_t>((n + WRP_PER_CTA - 1) / WRP_PER_CTA, (uint64_t)c->n_sm * 8);
 		if(mode == 1) k_ext_warp<1><<<grid, 32 * WRP_PER_CTA, 0, st>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, wk, ctr_cells);
 		else k_ext_warp<0><<<grid, 32 * WRP_PER_CTA, 0, st>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, wk, ctr_cells);
-	} else if(cls == 1) launch_ext_cta<64>(st, wk, mode, (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 10), d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, ctr_cells);
-	else if(cls == 2) launch_ext_cta<128>(st, wk, mode, (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 6), d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, ctr_cells);
-	else launch_ext_cta<256>(st, wk, mode, (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 3), d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, ctr_cells);
+	} else if(cls == 1) launch_ext_cta<64, 7>(st, wk, mode, (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 8), d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, ctr_cells);
+	else if(cls == 2) launch_ext_cta<128, 7>(st, wk, mode, (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 5), d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, ctr_cells);
+	else launch_ext_cta<CL3_NT, CL3_C>(st, wk, mode, (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * (CL3_NT == 256? 2 : 3)), d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, ctr_cells);
 	c->launches++;
 	CUDA_TRY(cudaGetLastError());
 	return 0;

@@ -5,6 +5,7 @@
 #pragma once
 #include "zmo_ctx.cuh"
 #include "zmo_dp.cuh"
+#include "zmo_dpr.cuh"
 
 struct DPJob {
 	uint32_t q_rid, t_rid;
@@ -29,10 +30,19 @@ template<int NT, int C> __host__ __device__ inline unsigned long long ext_scratc
 	if(need > sm_cap){ unsigned long long cap = 1; while(cap < (unsigned long long)need) cap <<= 1; hb = 3 * cap; }
 	return zw + (unsigned long long)d.ql + seq + hb + 8;
 }
-/* executor class of an extension band: 0 = warp (<= 224 columns), 1/2/3 = CTA of 64/128/256 threads */
-__host__ __device__ inline int ext_class(int ncol){ return ncol <= 224? 0 : (ncol <= 448? 1 : (ncol <= 896? 2 : 3)); }
+/* executor classes of an extension band (register-resident sweeps, zmo_dpr.cuh): 0 = warp x 7 columns per lane,
+ * 1/2 = CTA of 64/128 threads x 7, 3 = CTA of CL3_NT threads x CL3_C columns; bands beyond class 3's capacity run the
+ * chunked shared/global-memory sweep of zmo_dp.cuh inside the class-3 kernel */
+#define CL3_NT 128
+#define CL3_C 13
+__host__ __device__ inline int ext_class(int ncol){ return ncol <= RegCap<32, 7>::ncol? 0 : (ncol <= RegCap<64, 7>::ncol? 1 : (ncol <= RegCap<128, 7>::ncol? 2 : 3)); }
 __host__ __device__ inline unsigned long long ext_scratch_words_cls(const BandDims &d, int cls){
-	return cls == 0? ext_scratch_words<32, 7>(d, 256) : (cls == 1? ext_scratch_words<64, 7>(d, 512) : (cls == 2? ext_scratch_words<128, 7>(d, 1024) : ext_scratch_words<256, 7>(d, 2048)));
+	const unsigned long long seq = (unsigned long long)((d.ql + 15) >> 4) + ((d.tl + 15) >> 4) + 2;
+	if(cls == 0) return (unsigned long long)d.ql * 32 + seq + 8;
+	if(cls == 1) return (unsigned long long)d.ql * 64 + seq + 8;
+	if(cls == 2) return (unsigned long long)d.ql * 128 + seq + 8;
+	if(d.ncol <= RegCap<CL3_NT, CL3_C>::ncol) return (unsigned long long)d.ql * CL3_NT * RegCap<CL3_NT, CL3_C>::WPT + seq + 8;
+	return ext_scratch_words<CL3_NT, 7>(d, 0);
 }
 /* scratch for a global job sized for the widest band the retry loop can reach (ncol <= qlen) */
 template<int NT, int C> __host__ __device__ inline unsigned long long glb_scratch_words(int qlen, int tlen, int sm_cap){
@@ -65,23 +75,26 @@ __device__ void run_ext_job(const DPJob &J, const DevReads &R, const DPPar &P, E
 	if(J.qlen > 0 && J.tlen > 0){
 		BandDims d = band_dims(J.qlen, J.tlen, init, J.Wp, P);
 		uint32_t *scr = arena + J.scratch;
-		const int rw = band_row_words<NT, C>(d.ncol);
+		const bool reg = d.ncol <= RegCap<NT, C>::ncol;
+		const int rw = reg? NT * RegCap<NT, C>::WPT : band_row_words<NT, 7>(d.ncol);
 		uint32_t *z = scr; scr += (size_t)d.ql * rw;
-		int *zb = (int*)scr; scr += d.ql;
+		int *zb = (int*)scr; if(!reg) scr += d.ql;
 		const int qw = (d.ql + 15) >> 4, tw = (d.tl + 15) >> 4;
 		uint32_t *qpk, *tpk;
 		if(qw + tw + 2 <= X.seq_words){ qpk = X.seq; tpk = X.seq + qw; }
 		else { qpk = scr; tpk = scr + qw; }
 		scr += qw + tw + 2;
-		BandSmem S = X.B;
-		{
-			const int need = 2 * d.W + 3 < d.tl + 2? 2 * d.W + 3 : d.tl + 2;
-			if(need > X.cap){ int cap = 1; while(cap < need) cap <<= 1; S.H0 = (int*)scr; S.H1 = S.H0 + cap; S.Ev = S.H1 + cap; S.cap_mask = cap - 1; }
-		}
 		stage_packed<NT>(job_view(R, J.q_rid, J.q_start, J.q_step, J.q_comp), d.ql, qpk, tid);
 		stage_packed<NT>(job_view(R, J.t_rid, J.t_start, J.t_step, J.t_comp), d.tl, tpk, tid);
 		ex_sync<NT>();
-		band_extend<NT, C, MODE>(S, qpk, J.qlen, tpk, J.tlen, init, d, P, z, zb, cig_arena + J.cig_off, (int)J.cig_cap, o, cells, tid);
+		if(reg) reg_extend<NT, C, MODE>(X.B, qpk, J.qlen, tpk, J.tlen, init, d, P, z, cig_arena + J.cig_off, (int)J.cig_cap, o, cells, tid);
+		else {
+			/* band wider than the register executor: chunked sweep with H/E rows in shared (if they fit) or global memory */
+			BandSmem S = X.B;
+			const int need = 2 * d.W + 3 < d.tl + 2? 2 * d.W + 3 : d.tl + 2;
+			if(need > X.cap){ int cap = 1; while(cap < need) cap <<= 1; S.H0 = (int*)scr; S.H1 = S.H0 + cap; S.Ev = S.H1 + cap; S.cap_mask = cap - 1; }
+			band_extend<NT, 7, MODE>(S, qpk, J.qlen, tpk, J.tlen, init, d, P, z, zb, cig_arena + J.cig_off, (int)J.cig_cap, o, cells, tid);
+		}
 	}
 	if(tid == 0){ DPRes r; r.score = o.score; r.qe = o.qe; r.te = o.te; r.mat = o.mat; r.mis = o.mis; r.ins = o.ins; r.del = o.del; r.ncig = o.ncig; r.w_used = 0; r.pad = 0; res[J.out_idx] = r; }
 }
@@ -110,11 +123,12 @@ __device__ void run_glb_job(const DPJob &J, const DevReads &R, const DPPar &P, E
 		if(w < dl){ w <<= 1; continue; }
 		{
 			const int nc = qlen < 2 * w + 1? qlen : 2 * w + 1, bw = nc + 3;
-			const BandSmem &SS = bw <= X.cap? X.B : Sg;
-			if(NT == 32 && nc <= 32) band_global<NT, 1>(SS, qpk, qlen, tpk, tlen, w, P, z, cig_arena + J.cig_off, (int)J.cig_cap, o, cells, tid);
-			else if(NT == 32 && nc <= 64) band_global<NT, 2>(SS, qpk, qlen, tpk, tlen, w, P, z, cig_arena + J.cig_off, (int)J.cig_cap, o, cells, tid);
-			else if(NT == 32 && nc <= 128) band_global<NT, 4>(SS, qpk, qlen, tpk, tlen, w, P, z, cig_arena + J.cig_off, (int)J.cig_cap, o, cells, tid);
-			else band_global<NT, C>(SS, qpk, qlen, tpk, tlen, w, P, z, cig_arena + J.cig_off, (int)J.cig_cap, o, cells, tid);
+			uint32_t *cg = cig_arena + J.cig_off; const int cc = (int)J.cig_cap;
+			if(NT == 32 && nc <= RegCap<32, 1>::ncol) reg_global<NT, 1>(X.B, qpk, qlen, tpk, tlen, w, P, z, cg, cc, o, cells, tid);
+			else if(NT == 32 && nc <= RegCap<32, 2>::ncol) reg_global<NT, 2>(X.B, qpk, qlen, tpk, tlen, w, P, z, cg, cc, o, cells, tid);
+			else if(NT == 32 && nc <= RegCap<32, 4>::ncol) reg_global<NT, 4>(X.B, qpk, qlen, tpk, tlen, w, P, z, cg, cc, o, cells, tid);
+			else if(nc <= RegCap<NT, C>::ncol) reg_global<NT, C>(X.B, qpk, qlen, tpk, tlen, w, P, z, cg, cc, o, cells, tid);
+			else { const BandSmem &SS = bw <= X.cap? X.B : Sg; band_global<NT, C>(SS, qpk, qlen, tpk, tlen, w, P, z, cg, cc, o, cells, tid); }
 		}
 		if(J.Wmax > 0 && o.score < 0 && w < J.Wmax && w < mxl) w <<= 1; else break;
 	}
