@@ -34,7 +34,7 @@ sys.path.insert(0, REPO)
 # configs[1] of BASELINE.json: 50k PacBio-like reads x 10 kb over a 4.6 Mb genome (108x), -k 16 -s 200 -m 0.6
 WORKLOADS = {
     "cfg1": dict(n=2000, L=8000, G=500000, model="pacbio", seed=20240602, flags=["-k", "16", "-s", "200", "-m", "0.6"], shards=1),
-    "cfg2": dict(n=50000, L=10000, G=4600000, model="pacbio", seed=20240603, flags=["-k", "16", "-s", "200", "-m", "0.6"], shards=50),
+    "cfg2": dict(n=50000, L=10000, G=4600000, model="pacbio", seed=20240603, flags=["-k", "16", "-s", "200", "-m", "0.6"], shards=int(os.environ.get("ZMO_BENCH_SHARDS", "10"))),
     "cfg2s": dict(n=5000, L=10000, G=460000, model="pacbio", seed=20240603, flags=["-k", "16", "-s", "200", "-m", "0.6"], shards=5),
 }
 
@@ -128,7 +128,7 @@ def main():
             return 0
         fa = ensure_reads(wl, tmpdir)
         # bounded sample: a sub-shard of one step's shard so that K+W steps finish within minutes
-        sub = int(os.environ.get("ZMO_REF_SUBSHARD", "1"))       # 1 = exactly the shard a step of our arm processes
+        sub = int(os.environ.get("ZMO_REF_SUBSHARD", "2"))       # 1 = exactly the shard a step of our arm processes
         n_job = wl["shards"] * sub
         times, bp = [], 0
         for s in range(args.warmup + args.steps):
@@ -270,7 +270,7 @@ def main():
     if world > 1:
         line["gathered_bytes"] = r_e2e["gathered"]
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(REPO, "oracle", "_ref", "wtzmo")):
-        sub = int(os.environ.get("ZMO_REF_SUBSHARD", "4"))
+        sub = int(os.environ.get("ZMO_REF_SUBSHARD", "16"))
         try:
             cols, wall = run_reference(fa, wl["flags"], n_job * sub, 0, cores, tmpdir, "cpu")
             line["cpu_baseline"] = {"value": cols / wall / 1e9, "unit": "Gbp/s", "cores": cores, "kind": "reference",

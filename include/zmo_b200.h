@@ -50,6 +50,10 @@ typedef struct {
 
 /* ---- context ------------------------------------------------------------------------------- */
 int  zmo_ctx_create(zmo_ctx **ctx, int device, const zmo_params_t *par);
+/* A clone shares the root's read store and k-mer index (read-only) and has its own streams, scratch and batch slots,
+ * so that independent batches can be in flight concurrently (one host thread per context).  Reads are uploaded and
+ * the index is built through the root, while no clone is executing; clones are destroyed before the root. */
+int  zmo_ctx_clone(zmo_ctx *root, zmo_ctx **clone);
 void zmo_ctx_destroy(zmo_ctx *ctx);
 const char *zmo_last_error(void);
 /* number of kernels launched by this context so far (bench.py's gpu_launches claim) */
@@ -107,6 +111,10 @@ typedef struct {
 } zmo_record_t;
 int zmo_pair_align(zmo_ctx *ctx, int slot, const zmo_task_t *tasks, uint32_t nt,
                    zmo_record_t *recs, uint32_t *cigars, uint64_t cigar_cap, uint64_t *cigar_needed);
+/* Same, but the CIGARs come back as the text `print_hits_wtzmo` prints (kswx_cigar2string, kswx.h:1093-1120: "<len><M|I|D>"
+ * per op), formatted on the device: recs[i].cigar_off / n_cigar are the byte offset / byte length in cigar_text, sizes in bytes. */
+int zmo_pair_align_text(zmo_ctx *ctx, int slot, const zmo_task_t *tasks, uint32_t nt,
+                        zmo_record_t *recs, char *cigar_text, uint64_t text_cap, uint64_t *text_needed);
 
 /* ---- dot-matrix mode: replaces dot_matrix_align_hzmps for one pair (wtzmo.c:853-863) --------- */
 typedef struct { uint32_t n_zpair; int32_t score, qb, qe, tb, te, strand; } zmo_dotres_t;

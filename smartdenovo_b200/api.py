@@ -94,6 +94,8 @@ def load_lib(path=None):
     lib.zmo_candidates.argtypes = [vp, vp, C.c_uint32, vp, vp, C.c_uint64, u64p]
     lib.zmo_pair_windows.argtypes = [vp, C.c_int, vp, C.c_uint32, vp, vp, C.c_uint64, u64p]
     lib.zmo_pair_align.argtypes = [vp, C.c_int, vp, C.c_uint32, vp, vp, C.c_uint64, u64p]
+    lib.zmo_pair_align_text.argtypes = [vp, C.c_int, vp, C.c_uint32, vp, vp, C.c_uint64, u64p]
+    lib.zmo_ctx_clone.argtypes = [vp, C.POINTER(vp)]
     lib.zmo_pair_dotmatrix.argtypes = [vp, vp, C.c_uint32, vp]
     lib.zmo_dp_extend.argtypes = [vp, C.c_int, vp, C.c_uint32, vp, vp, C.c_uint64, u64p]
     lib.zmo_dp_global.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, u64p]
@@ -132,11 +134,20 @@ def pack_reads(seqs):
 class Zmo:
     """One device context (zmo_ctx).  All methods raise ZmoError on failure."""
 
-    def __init__(self, params=None, device=0, lib=None):
+    def __init__(self, params=None, device=0, lib=None, _clone_of=None):
         self.lib = lib or load_lib()
-        self.params = params or default_params()
         self._h = C.c_void_p()
+        if _clone_of is not None:
+            self.params = _clone_of.params
+            self._chk(self.lib.zmo_ctx_clone(_clone_of._h, C.byref(self._h)))
+            self.n_reads, self.lens = _clone_of.n_reads, _clone_of.lens
+            return
+        self.params = params or default_params()
         self._chk(self.lib.zmo_ctx_create(C.byref(self._h), device, C.byref(self.params)))
+
+    def clone(self):
+        """zmo_ctx_clone: a context with its own streams / scratch that shares this one's reads and index."""
+        return Zmo(lib=self.lib, _clone_of=self)
 
     def _chk(self, rc):
         if rc != 0:
@@ -227,6 +238,21 @@ class Zmo:
                 continue
             self._chk(rc)
             return recs, cig
+
+    def pair_align_text(self, tasks, slot=0, text_cap=1 << 20):
+        """zmo_pair_align_text: records whose cigar_off / n_cigar index the returned bytes (CIGAR text formatted on the device)."""
+        tasks = np.ascontiguousarray(tasks, TASK)
+        recs = np.zeros(len(tasks), RECORD)
+        cap = text_cap
+        while True:
+            txt = np.zeros(cap, np.uint8)
+            need = C.c_uint64(0)
+            rc = self.lib.zmo_pair_align_text(self._h, slot, tasks.ctypes.data, len(tasks), recs.ctypes.data, txt.ctypes.data, cap, C.byref(need))
+            if rc == -3:
+                cap = int(need.value) + 16
+                continue
+            self._chk(rc)
+            return recs, txt
 
     def pair_dotmatrix(self, pairs):
         pairs = np.ascontiguousarray(pairs, PAIR)

@@ -311,14 +311,17 @@ static inline u64 pair_key(u32 a, u32 b){ return a < b? (((u64)a << 33) | ((u64)
 
 
 /* ------------------------------------------------------------------ records + output (wtzmo.c:1170-1249) */
-typedef struct { u32 pb1, pb2; u8 dir2; int qb, qe, tb, te, score, mat, mis, ins, del, aln; const u32 *cigar; u32 n_cigar; int has_cigar; } hit_t;
+typedef struct { u32 pb1, pb2; u8 dir2; int qb, qe, tb, te, score, mat, mis, ins, del, aln; const char *cigar; u32 n_cigar; int has_cigar; } hit_t;   /* cigar = device-formatted text, n_cigar bytes */
 typedef VEC(hit_t) hitv;
 typedef struct { u32 pb2; u32 ovl; u8 dir, closed; u32 cand_idx; } seed_t;
 typedef VEC(seed_t) seedv;
 #define WIN_OVL_MASK 0x1FFFFFFFU
 
+#define WZ_MAX_CTX 8
+#define WZ_PIN_WAVES 6
 typedef struct {
-	readset_t rs; zparams_t par; zmo_ctx *ctx;
+	readset_t rs; zparams_t par; zmo_ctx *ctx;      /* ctx = root context (reads + index); ctxs[0] == ctx, ctxs[1..] = clones */
+	zmo_ctx *ctxs[WZ_MAX_CTX]; int n_ctx, depth; u8 ctx_busy[WZ_MAX_CTX];
 	u8 *masked; u32 *rdcovs; u64set_t closed; u32 avg_rdlen; u32 kcut;
 	u64v *rdhits;                       /* per-read candidate carry-over, only with -G > 1 */
 	u64 n_records, aln_cols, n_tasks, n_tasks_used, n_pairs_seeded, n_batches;
@@ -326,8 +329,9 @@ typedef struct {
 	double t_dev, t_replay, t_write;
 	int batch_reads, batch_pairs;
 	/* page-locked result buffers reused across batches */
-	zmo_record_t *pin_recs[2]; size_t pin_recs_cap[2]; u32 *pin_cig[2]; size_t pin_cig_cap[2]; int pin_sel, pipeline;
-	pthread_mutex_t dev_mu;             /* one device call at a time (worker thread vs on-demand waves of the replay) */
+	zmo_record_t *pin_recs[WZ_MAX_CTX][WZ_PIN_WAVES]; size_t pin_recs_cap[WZ_MAX_CTX][WZ_PIN_WAVES]; u32 *pin_cig[WZ_MAX_CTX][WZ_PIN_WAVES]; size_t pin_cig_cap[WZ_MAX_CTX][WZ_PIN_WAVES];
+	pthread_mutex_t dev_mu[WZ_MAX_CTX];  /* one device call at a time per context */
+	pthread_mutex_t stat_mu;
 	u64 n_waves, n_wave_tasks; int wave_margin, wave_growth;
 } wz_t;
 
@@ -363,18 +367,12 @@ static void flush_read(wz_t *z, readout_t *ro, int defer_masks){
 		if(h->aln == 0) h->aln = 1;
 		x1 = imin(h->tb, h->qb); x2 = imin(l1 - h->te, l2 - h->qe);
 		if(x1 + x2 <= z->par.max_unalign_in_dovetail){ z->rdcovs[h->pb1] ++; z->rdcovs[h->pb2] ++; }
-		ob_reserve(z, 512 + strlen(rs->reads.a[h->pb1].name) + strlen(rs->reads.a[h->pb2].name) + (size_t)h->n_cigar * 11);
+		ob_reserve(z, 512 + strlen(rs->reads.a[h->pb1].name) + strlen(rs->reads.a[h->pb2].name) + (size_t)h->n_cigar + 16);
 		z->obuf_n += sprintf(z->obuf + z->obuf_n, "%s\t%c\t%d\t%d\t%d\t%s\t%c\t%d\t%d\t%d\t%d\t%0.3f\t%d\t%d\t%d\t%d\t", rs->reads.a[h->pb1].name, '+', l1, h->tb, h->te,
 			rs->reads.a[h->pb2].name, "+-"[h->dir2], l2, h->qb, h->qe, h->score, 1.0 * h->mat / h->aln, h->mat, h->mis, h->ins, h->del);
 		p = z->obuf + z->obuf_n;
-		if(h->has_cigar){          /* kswx_cigar2string (kswx.h:1093-1120) */
-			for(k=0;k<h->n_cigar;k++){
-				u32 op = h->cigar[k] & 0xF, len = h->cigar[k] >> 4;
-				if(len == 0) continue;
-				if(op > 2){ fprintf(stderr, " -- CIGAR only support M(0),I(1),D(2) cigar, but met ?(%d) --\n", op); exit(1); }
-				p = put_u32(p, len); *p++ = "MIDX"[op];
-			}
-		} else { *p++ = '0'; *p++ = 'M'; }
+		if(h->has_cigar){ memcpy(p, h->cigar, h->n_cigar); p += h->n_cigar; }      /* kswx_cigar2string (kswx.h:1093-1120), formatted by k_cig_text */
+		else { *p++ = '0'; *p++ = 'M'; }
 		*p++ = '\n';
 		z->obuf_n = p - z->obuf;
 		z->n_records ++;
@@ -414,7 +412,8 @@ typedef struct {
 	VEC(void*) extra;                   /* result buffers of on-demand waves */
 	int slot;                           /* device batch slot holding this batch's windows/anchors */
 	zmo_dotres_t *dots;
-	int pin_sel;                        /* which pinned result buffer set this batch uses */
+	int ci;                             /* device context (and pinned result buffer set) owned by this batch from build to the end of its replay */
+	pthread_t th; int have_thread;
 } batch_t;
 
 static u32 read_nbest(const wz_t *z, u32 pbid){
@@ -430,10 +429,10 @@ static void batch_candidates(wz_t *z, batch_t *b){
 	for(i=0;i<b->reads.n;i++) if(!b->reads.a[i].skip){ qmap[nq] = (u32)i; qids[nq++] = b->reads.a[i].rd_id; }
 	if(nq){
 		cap = 4096 + 512 * nq; ev = malloc(cap * sizeof(zmo_event_t));
-		pthread_mutex_lock(&z->dev_mu);
-		rc = zmo_candidates(z->ctx, qids, (u32)nq, off, ev, cap, &need);
-		if(rc == ZMO_ERR_CAPACITY){ cap = need + 16; ev = realloc(ev, cap * sizeof(zmo_event_t)); rc = zmo_candidates(z->ctx, qids, (u32)nq, off, ev, cap, &need); }
-		pthread_mutex_unlock(&z->dev_mu);
+		pthread_mutex_lock(&z->dev_mu[b->ci]);
+		rc = zmo_candidates(z->ctxs[b->ci], qids, (u32)nq, off, ev, cap, &need);
+		if(rc == ZMO_ERR_CAPACITY){ cap = need + 16; ev = realloc(ev, cap * sizeof(zmo_event_t)); rc = zmo_candidates(z->ctxs[b->ci], qids, (u32)nq, off, ev, cap, &need); }
+		pthread_mutex_unlock(&z->dev_mu[b->ci]);
 		if(rc) die_zmo("zmo_candidates");
 		for(i=0;i<nq;i++){
 			bread_t *r = &b->reads.a[qmap[i]];
@@ -613,7 +612,7 @@ static int replay_read(wz_t *z, batch_t *b, bread_t *br, u32 bcov_in, readout_t 
 		if(x->score < par->min_score || x->mat < x->aln * par->min_id) continue;
 		memset(&h, 0, sizeof(h));
 		h.pb1 = pbid; h.pb2 = s->pb2; h.dir2 = s->dir; h.score = x->score; h.tb = x->tb; h.te = x->te; h.qb = x->qb; h.qe = x->qe;
-		h.mat = x->mat; h.mis = x->mis; h.ins = x->ins; h.del = x->del; h.aln = x->aln; h.cigar = b->pcig[s->cand_idx] + x->cigar_off; h.n_cigar = x->n_cigar; h.has_cigar = 1;
+		h.mat = x->mat; h.mis = x->mis; h.ins = x->ins; h.del = x->del; h.aln = x->aln; h.cigar = (const char*)b->pcig[s->cand_idx] + x->cigar_off; h.n_cigar = x->n_cigar; h.has_cigar = 1;
 		vec_push(ro->hits, h);
 		act = hit_rules(par, alen, rs->reads.a[s->pb2].len, pbid, s->pb2, x, &br->bcov, br->nbest, &br->ncand, &ro->masks);
 		if(act == 2) break;
@@ -651,23 +650,24 @@ static void batch_pairs(wz_t *z, batch_t *b){
 /* device phases B + C for the batch (touches only the batch and the device context: may run on the worker thread) */
 static void batch_compute(wz_t *z, batch_t *b){
 	const zparams_t *par = &z->par; size_t i; int rc; u64 need = 0;
+	zmo_ctx *ctx = z->ctxs[b->ci]; pthread_mutex_t *mu = &z->dev_mu[b->ci];
 	if(b->pairs.n == 0) return;
-	z->n_pairs_seeded += b->pairs.n;
+	pthread_mutex_lock(&z->stat_mu); z->n_pairs_seeded += b->pairs.n; pthread_mutex_unlock(&z->stat_mu);
 	if(par->dot_matrix){
 		b->dots = malloc(b->pairs.n * sizeof(zmo_dotres_t)); b->seeds = calloc(b->pairs.n, sizeof(zmo_pairseed_t));
-		pthread_mutex_lock(&z->dev_mu);
-		rc = zmo_pair_dotmatrix(z->ctx, b->pairs.a, (u32)b->pairs.n, b->dots);
-		pthread_mutex_unlock(&z->dev_mu);
+		pthread_mutex_lock(mu);
+		rc = zmo_pair_dotmatrix(ctx, b->pairs.a, (u32)b->pairs.n, b->dots);
+		pthread_mutex_unlock(mu);
 		if(rc) die_zmo("zmo_pair_dotmatrix");
 		for(i=0;i<b->pairs.n;i++) b->seeds[i].n_zpair = b->dots[i].n_zpair;
 		return;
 	}
 	b->seeds = malloc(b->pairs.n * sizeof(zmo_pairseed_t));
 	b->wins_cap = 64 * b->pairs.n + 1024; b->wins = malloc(b->wins_cap * sizeof(zmo_window_t));
-	pthread_mutex_lock(&z->dev_mu);
-	rc = zmo_pair_windows(z->ctx, b->slot, b->pairs.a, (u32)b->pairs.n, b->seeds, b->wins, b->wins_cap, &need);
-	if(rc == ZMO_ERR_CAPACITY && need > b->wins_cap){ b->wins_cap = need + 16; b->wins = realloc(b->wins, b->wins_cap * sizeof(zmo_window_t)); rc = zmo_pair_windows(z->ctx, b->slot, b->pairs.a, (u32)b->pairs.n, b->seeds, b->wins, b->wins_cap, &need); }
-	pthread_mutex_unlock(&z->dev_mu);
+	pthread_mutex_lock(mu);
+	rc = zmo_pair_windows(ctx, b->slot, b->pairs.a, (u32)b->pairs.n, b->seeds, b->wins, b->wins_cap, &need);
+	if(rc == ZMO_ERR_CAPACITY && need > b->wins_cap){ b->wins_cap = need + 16; b->wins = realloc(b->wins, b->wins_cap * sizeof(zmo_window_t)); rc = zmo_pair_windows(ctx, b->slot, b->pairs.a, (u32)b->pairs.n, b->seeds, b->wins, b->wins_cap, &need); }
+	pthread_mutex_unlock(mu);
 	if(rc) die_zmo("zmo_pair_windows");
 	if(!par->do_align) return;
 	b->pres = calloc(b->pairs.n, sizeof(*b->pres)); b->pcig = calloc(b->pairs.n, sizeof(*b->pcig)); b->pdir = calloc(b->pairs.n, 1);
@@ -703,25 +703,28 @@ static void batch_compute(wz_t *z, batch_t *b){
 				}
 			}
 			if(tk.n == 0){ vec_free(tk); break; }
-			z->n_tasks += tk.n;
-			if(wave == 0){
-				const int ps = b->pin_sel;
-				if(tk.n > z->pin_recs_cap[ps]){ zmo_host_free(z->pin_recs[ps]); z->pin_recs_cap[ps] = tk.n * 2 + 1024; z->pin_recs[ps] = zmo_host_alloc(z->pin_recs_cap[ps] * sizeof(zmo_record_t)); if(!z->pin_recs[ps]) die_zmo("zmo_host_alloc"); }
-				if(z->pin_cig_cap[ps] < 4096 * tk.n + (1u << 16)){ zmo_host_free(z->pin_cig[ps]); z->pin_cig_cap[ps] = 4096 * tk.n * 2 + (1u << 20); z->pin_cig[ps] = zmo_host_alloc(z->pin_cig_cap[ps] * 4); if(!z->pin_cig[ps]) die_zmo("zmo_host_alloc"); }
-				recs = z->pin_recs[ps]; cig = z->pin_cig[ps]; cap = z->pin_cig_cap[ps];
-			} else { recs = malloc(tk.n * sizeof(zmo_record_t)); cap = 4096 * tk.n + 65536; cig = malloc(cap * 4); }
-			pthread_mutex_lock(&z->dev_mu);
-			rc = zmo_pair_align(z->ctx, b->slot, tk.a, (u32)tk.n, recs, cig, cap, &need);
-			if(rc == ZMO_ERR_CAPACITY && need > cap){
-				cap = need + need / 4 + 16;
-				if(wave == 0){ const int ps = b->pin_sel; zmo_host_free(z->pin_cig[ps]); z->pin_cig_cap[ps] = cap; z->pin_cig[ps] = zmo_host_alloc(cap * 4); if(!z->pin_cig[ps]) die_zmo("zmo_host_alloc"); cig = z->pin_cig[ps]; }
-				else cig = realloc(cig, cap * 4);
-				rc = zmo_pair_align(z->ctx, b->slot, tk.a, (u32)tk.n, recs, cig, cap, &need);
+			pthread_mutex_lock(&z->stat_mu); z->n_tasks += tk.n; pthread_mutex_unlock(&z->stat_mu);
+			{
+				/* results land in page-locked buffers owned by (context, wave): they stay valid until the batch has been replayed */
+				const int ps = b->ci, pinned = wave < WZ_PIN_WAVES;
+				if(pinned){
+					if(tk.n > z->pin_recs_cap[ps][wave]){ zmo_host_free(z->pin_recs[ps][wave]); z->pin_recs_cap[ps][wave] = tk.n * 2 + 1024; z->pin_recs[ps][wave] = zmo_host_alloc(z->pin_recs_cap[ps][wave] * sizeof(zmo_record_t)); if(!z->pin_recs[ps][wave]) die_zmo("zmo_host_alloc"); }
+					if(z->pin_cig_cap[ps][wave] < 4096 * tk.n + (1u << 16)){ zmo_host_free(z->pin_cig[ps][wave]); z->pin_cig_cap[ps][wave] = 4096 * tk.n * 2 + (1u << 20); z->pin_cig[ps][wave] = zmo_host_alloc(z->pin_cig_cap[ps][wave] * 4); if(!z->pin_cig[ps][wave]) die_zmo("zmo_host_alloc"); }
+					recs = z->pin_recs[ps][wave]; cig = z->pin_cig[ps][wave]; cap = z->pin_cig_cap[ps][wave];
+				} else { recs = malloc(tk.n * sizeof(zmo_record_t)); cap = 4096 * tk.n + 65536; cig = malloc(cap * 4); }
+				pthread_mutex_lock(mu);
+				rc = zmo_pair_align_text(ctx, b->slot, tk.a, (u32)tk.n, recs, (char*)cig, cap * 4, &need);
+				if(rc == ZMO_ERR_CAPACITY && need > cap * 4){
+					cap = (need + need / 4) / 4 + 16;
+					if(pinned){ zmo_host_free(z->pin_cig[ps][wave]); z->pin_cig_cap[ps][wave] = cap; z->pin_cig[ps][wave] = zmo_host_alloc(cap * 4); if(!z->pin_cig[ps][wave]) die_zmo("zmo_host_alloc"); cig = z->pin_cig[ps][wave]; }
+					else cig = realloc(cig, cap * 4);
+					rc = zmo_pair_align_text(ctx, b->slot, tk.a, (u32)tk.n, recs, (char*)cig, cap * 4, &need);
+				}
+				pthread_mutex_unlock(mu);
 			}
-			pthread_mutex_unlock(&z->dev_mu);
 			if(rc) die_zmo("zmo_pair_align");
 			for(i=0;i<tk.n;i++){ b->pres[tk.a[i].pair_idx] = &recs[i]; b->pcig[tk.a[i].pair_idx] = cig; b->pdir[tk.a[i].pair_idx] = (u8)tk.a[i].dir; }
-			if(wave){ vec_push(b->extra, (void*)recs); vec_push(b->extra, (void*)cig); }
+			if(wave >= WZ_PIN_WAVES){ vec_push(b->extra, (void*)recs); vec_push(b->extra, (void*)cig); }
 			vec_free(tk);
 			for(i=0;i<nr;i++) if(pos[i] >= 0) pos[i] = dry_walk(z, b, &b->reads.a[i], &sv[i]);
 			wave ++; if(chunk < ((size_t)1 << 20)) chunk *= (size_t)z->wave_growth;
@@ -744,10 +747,10 @@ static void demand_wave(wz_t *z, batch_t *b, bread_t *br, readout_t *ro){
 	}
 	if(tk.n == 0){ fprintf(stderr, "wtzmo(b200): internal error: empty demand wave\n"); exit(4); }
 	recs = malloc(tk.n * sizeof(zmo_record_t)); cap = 4096 * tk.n + 65536; cig = malloc(cap * 4);
-	pthread_mutex_lock(&z->dev_mu);
-	rc = zmo_pair_align(z->ctx, b->slot, tk.a, (u32)tk.n, recs, cig, cap, &need);
-	if(rc == ZMO_ERR_CAPACITY && need > cap){ cap = need + 16; cig = realloc(cig, cap * 4); rc = zmo_pair_align(z->ctx, b->slot, tk.a, (u32)tk.n, recs, cig, cap, &need); }
-	pthread_mutex_unlock(&z->dev_mu);
+	pthread_mutex_lock(&z->dev_mu[b->ci]);
+	rc = zmo_pair_align_text(z->ctxs[b->ci], b->slot, tk.a, (u32)tk.n, recs, (char*)cig, cap * 4, &need);
+	if(rc == ZMO_ERR_CAPACITY && need > cap * 4){ cap = need / 4 + 16; cig = realloc(cig, cap * 4); rc = zmo_pair_align_text(z->ctxs[b->ci], b->slot, tk.a, (u32)tk.n, recs, (char*)cig, cap * 4, &need); }
+	pthread_mutex_unlock(&z->dev_mu[b->ci]);
 	if(rc) die_zmo("zmo_pair_align (demand wave)");
 	for(i=0;i<tk.n;i++){ b->pres[tk.a[i].pair_idx] = &recs[i]; b->pcig[tk.a[i].pair_idx] = cig; b->pdir[tk.a[i].pair_idx] = (u8)tk.a[i].dir; }
 	vec_push(b->extra, (void*)recs); vec_push(b->extra, (void*)cig);
@@ -791,16 +794,19 @@ static void run_overlap(wz_t *z){
 		}
 	}
 	{
-		/* software pipeline: while the host replays batch k, a worker thread runs the device phases of batch k+1.
-		 * Batch k+1 is built from the state as of the end of batch k-1, which only makes the speculation set larger. */
-		batch_t *cur = NULL, *nxt = NULL; int sel = 0; double t0, t1;
+		/* software pipeline: up to `depth` batches are in flight on their own device contexts (one worker thread each)
+		 * while the host replays the oldest one.  A batch is built from the state as of its build time, i.e. batch k+depth
+		 * from the state at the end of batch k-1, which only makes the speculation set larger (results are pure). */
+		batch_t *q[WZ_MAX_CTX]; int qh = 0, qn = 0, ci; double t0, t1;
+		memset(z->ctx_busy, 0, sizeof(z->ctx_busy));
 		j = beg;
 		while(1){
-			pthread_t th; int have_thread = 0; size_t i;
-			nxt = NULL;
-			if(j < end){
-				size_t est_pairs = 0;
-				nxt = calloc(1, sizeof(batch_t)); nxt->pin_sel = sel; nxt->slot = sel; sel ^= 1;
+			size_t i; batch_t *cur;
+			while(qn < z->depth && j < end){
+				size_t est_pairs = 0; batch_t *nxt = calloc(1, sizeof(batch_t));
+				for(ci=0;ci<z->n_ctx;ci++) if(!z->ctx_busy[ci]) break;
+				if(ci == z->n_ctx){ fprintf(stderr, "wtzmo(b200): internal error: no free device context\n"); exit(4); }
+				nxt->ci = ci; nxt->slot = 0;
 				for(;j<end&&nxt->reads.n<(size_t)z->batch_reads&&est_pairs<(size_t)z->batch_pairs;j++){
 					bread_t r; memset(&r, 0, sizeof(r));
 					if((j % par->n_job) != (u32)par->i_job) continue;
@@ -809,31 +815,32 @@ static void run_overlap(wz_t *z){
 					vec_push(nxt->reads, r);
 					if(!r.skip) est_pairs += 40;
 				}
-				if(nxt->reads.n == 0){ free(nxt); nxt = NULL; }
-			}
-			if(nxt){
+				if(nxt->reads.n == 0){ free(nxt); break; }
+				z->ctx_busy[ci] = 1;
 				t0 = now_s();
 				batch_candidates(z, nxt);
 				batch_pairs(z, nxt);
-				if(cur && z->pipeline){ wk_arg_t *wa = malloc(sizeof(wk_arg_t)); wa->z = z; wa->b = nxt; if(pthread_create(&th, NULL, batch_compute_thread, wa) != 0){ free(wa); batch_compute(z, nxt); } else have_thread = 1; }
-				else batch_compute(z, nxt);
+				if(z->depth > 1){
+					wk_arg_t *wa = malloc(sizeof(wk_arg_t)); wa->z = z; wa->b = nxt;
+					if(pthread_create(&nxt->th, NULL, batch_compute_thread, wa) != 0){ free(wa); batch_compute(z, nxt); } else nxt->have_thread = 1;
+				} else batch_compute(z, nxt);
 				z->t_dev += now_s() - t0;
+				q[(qh + qn) % WZ_MAX_CTX] = nxt; qn ++;
 			}
-			if(cur){
-				t1 = now_s();
-				for(i=0;i<cur->reads.n;i++){
-					bread_t *br = &cur->reads.a[i];
-					if(z->masked[br->rd_id]) continue;       /* checked BEFORE the previous read's masks are merged (wtzmo.c:1315 vs 1322) */
-					flush_read(z, &ro, 0);
-					while(replay_read(z, cur, br, z->rdcovs[br->rd_id], &ro)) demand_wave(z, cur, br, &ro);
-				}
-				flush_read(z, &ro, 1);  /* hits point into this batch's CIGAR buffer: print them before it is reused; masks stay pending */
-				z->t_replay += now_s() - t1; z->n_batches ++;
-				batch_free(cur); free(cur); cur = NULL;
+			if(qn == 0) break;
+			cur = q[qh]; qh = (qh + 1) % WZ_MAX_CTX; qn --;
+			if(cur->have_thread){ double tj = now_s(); pthread_join(cur->th, NULL); z->t_dev += now_s() - tj; }
+			t1 = now_s();
+			for(i=0;i<cur->reads.n;i++){
+				bread_t *br = &cur->reads.a[i];
+				if(z->masked[br->rd_id]) continue;       /* checked BEFORE the previous read's masks are merged (wtzmo.c:1315 vs 1322) */
+				flush_read(z, &ro, 0);
+				while(replay_read(z, cur, br, z->rdcovs[br->rd_id], &ro)) demand_wave(z, cur, br, &ro);
 			}
-			if(have_thread){ double tj = now_s(); pthread_join(th, NULL); z->t_dev += now_s() - tj; }
-			if(nxt == NULL) break;
-			cur = nxt;
+			flush_read(z, &ro, 1);  /* hits point into this batch's CIGAR buffers: print them before they are reused; masks stay pending */
+			z->t_replay += now_s() - t1; z->n_batches ++;
+			z->ctx_busy[cur->ci] = 0;
+			batch_free(cur); free(cur);
 		}
 	}
 	flush_read(z, &ro, 0);
@@ -982,10 +989,13 @@ wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	if((env = getenv("ZMO_DEVICE"))) S->device = atoi(env); else if((env = getenv("LOCAL_RANK"))) S->device = atoi(env);
 	z->batch_reads = (env = getenv("ZMO_BATCH_READS"))? atoi(env) : 384;
 	z->batch_pairs = (env = getenv("ZMO_BATCH_PAIRS"))? atoi(env) : 40000;
-	z->pipeline = (env = getenv("ZMO_PIPELINE"))? atoi(env) : 1;
+	z->depth = 1 + ((env = getenv("ZMO_DEPTH"))? atoi(env) : 2);      /* ZMO_DEPTH = batches in flight on the device while the host replays the oldest */
+	if((env = getenv("ZMO_PIPELINE")) && atoi(env) == 0) z->depth = 1;  /* no pipeline: one batch at a time, one context */
+	if(z->depth < 1) z->depth = 1;
+	if(z->depth > WZ_MAX_CTX) z->depth = WZ_MAX_CTX;
 	z->wave_margin = (env = getenv("ZMO_WAVE0"))? atoi(env) : 8;       /* seeds per read in the first DP wave (doubles per wave); < 0: align every seed up front */
 	z->wave_growth = (env = getenv("ZMO_WAVE_GROWTH"))? atoi(env) : 4; if(z->wave_growth < 2) z->wave_growth = 2;
-	pthread_mutex_init(&z->dev_mu, NULL);
+	{ int q; for(q=0;q<WZ_MAX_CTX;q++) pthread_mutex_init(&z->dev_mu[q], NULL); pthread_mutex_init(&z->stat_mu, NULL); }
 	if(z->batch_reads < 1) z->batch_reads = 1;
 	fprintf(stderr, "[wtzmo-b200] loading long reads\n");
 	rs_load(&z->rs, pbs.a, (int)pbs.n, par->min_rdlen, 0);
@@ -1048,6 +1058,9 @@ wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	zp.M = par->M; zp.X = par->X; zp.O = par->O; zp.E = par->E; zp.T = par->T; zp.min_id = par->min_id;
 	zp.xvar = par->xvar; zp.yvar = par->yvar; zp.min_block_len = par->min_block_len; zp.max_overhang = par->max_overhang; zp.deviation_penalty = par->deviation_penalty; zp.gap_penalty = par->gap_penalty;
 	if(zmo_ctx_create(&z->ctx, S->device, &zp)){ fprintf(stderr, "wtzmo(b200): zmo_ctx_create: %s\n", zmo_last_error()); *rc_out = 3; return NULL; }
+	/* one context per queued batch: those in flight + the one being replayed (which may still ask for on-demand waves) */
+	z->ctxs[0] = z->ctx; z->n_ctx = 1;
+	{ int q; for(q=1;q<z->depth;q++){ if(zmo_ctx_clone(z->ctx, &z->ctxs[z->n_ctx])){ fprintf(stderr, "wtzmo(b200): zmo_ctx_clone: %s\n", zmo_last_error()); *rc_out = 3; return NULL; } z->n_ctx ++; } }
 	S->t_open = now_s() - t_start;
 	vec_free(pbs); vec_free(flts); vec_free(ovls); vec_free(obts); vec_free(tbas);
 	return S;
@@ -1087,17 +1100,18 @@ int wz_run(wz_session_t *S, int n_job, int i_job, const char *out_path){
  * [7]=tasks aligned [8]=tasks consumed [9]=kernel launches (cumulative) [10..17]=stage ms (cumulative) [18..24]=counters (cumulative)
  * [25]=reads [26]=bases [27]=last upload s [28]=upload bytes */
 void wz_stats(wz_session_t *S, double *out){
-	wz_t *z = &S->z; double ms[12]; uint64_t ct[8]; int i;
-	zmo_stage_ms(z->ctx, ms); zmo_counters(z->ctx, ct);
+	wz_t *z = &S->z; double ms[12], m1[12]; uint64_t ct[8], c1[8]; int i, q; u64 nl = 0;
+	memset(ms, 0, sizeof(ms)); memset(ct, 0, sizeof(ct));
+	for(q=0;q<z->n_ctx;q++){ zmo_stage_ms(z->ctxs[q], m1); zmo_counters(z->ctxs[q], c1); for(i=0;i<12;i++) ms[i] += m1[i]; for(i=0;i<8;i++) ct[i] += c1[i]; nl += zmo_kernel_launches(z->ctxs[q]); }
 	out[0] = (double)z->n_records; out[1] = (double)z->aln_cols; out[2] = S->last_overlap_s; out[3] = z->t_dev; out[4] = z->t_replay; out[5] = (double)z->n_batches;
-	out[6] = (double)z->n_pairs_seeded; out[7] = (double)z->n_tasks; out[8] = (double)z->n_tasks_used; out[9] = (double)zmo_kernel_launches(z->ctx);
+	out[6] = (double)z->n_pairs_seeded; out[7] = (double)z->n_tasks; out[8] = (double)z->n_tasks_used; out[9] = (double)nl;
 	for(i=0;i<8;i++) out[10 + i] = ms[i];
 	for(i=0;i<7;i++) out[18 + i] = (double)ct[i];
 	out[25] = (double)(z->rs.n_rd + z->rs.n_qr); out[26] = (double)z->rs.nbases; out[27] = S->last_upload_s; out[28] = (double)S->upload_bytes;
 	out[29] = (double)z->n_waves; out[30] = (double)z->n_wave_tasks; out[31] = ms[8];
 }
 
-void wz_close(wz_session_t *S){ if(S){ if(S->z.ctx) zmo_ctx_destroy(S->z.ctx); free(S); } }
+void wz_close(wz_session_t *S){ if(S){ int q; for(q=S->z.n_ctx-1;q>=0;q--) if(S->z.ctxs[q]) zmo_ctx_destroy(S->z.ctxs[q]); free(S); } }
 
 #ifndef WTZMO_LIB
 int main(int argc, char **argv){

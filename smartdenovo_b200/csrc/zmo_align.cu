@@ -329,6 +329,48 @@ __global__ void k_finish(const AlnTask *tasks, uint32_t nt, const DevReg *regs, 
 	recs[t] = rec;
 }
 
+/* ---- CIGAR text on the device (kswx_cigar2string, kswx.h:1093-1120: "%d%c" per op with len > 0, ops M/I/D) ---- */
+__device__ __forceinline__ uint32_t cig_op_chars(uint32_t op){
+	const uint32_t len = op >> 4;
+	if(len == 0) return 0;
+	return 2u + (len >= 10u) + (len >= 100u) + (len >= 1000u) + (len >= 10000u) + (len >= 100000u) + (len >= 1000000u) + (len >= 10000000u) + (len >= 100000000u);
+}
+/* one warp per task: text length of its stitched CIGAR */
+__global__ void k_cig_textlen(const zmo_record_t *recs, uint32_t nt, const uint32_t *ops, unsigned long long *tlen){
+	const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if(t >= nt) return;
+	const zmo_record_t r = recs[t];
+	unsigned long long n = 0;
+	if(r.ok){ const uint32_t *o = ops + r.cigar_off; for(uint32_t k = lane; k < r.n_cigar; k += 32) n += cig_op_chars(o[k]); }
+	#pragma unroll
+	for(int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
+	if(lane == 0) tlen[t] = n;
+}
+/* one warp per task: write the text, re-point the record at it (cigar_off / n_cigar become byte offset / byte length) */
+__global__ void k_cig_text(zmo_record_t *recs, uint32_t nt, const uint32_t *ops, const unsigned long long *toff, char *text){
+	const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if(t >= nt) return;
+	const zmo_record_t r = recs[t];
+	const unsigned long long t0 = toff[t], t1 = toff[t + 1];
+	if(r.ok){
+		const uint32_t *o = ops + r.cigar_off; char *dst = text + t0; unsigned long long cur = 0;
+		for(uint32_t base = 0; base < r.n_cigar; base += 32){
+			const uint32_t k = base + lane; const uint32_t op = k < r.n_cigar? o[k] : 0u; const uint32_t nc = cig_op_chars(op);
+			uint32_t incl = nc;
+			#pragma unroll
+			for(int d = 1; d < 32; d <<= 1){ const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if((int)lane >= d) incl += v; }
+			if(nc){
+				char *p = dst + cur + incl - 1;      /* last char of this op */
+				*p-- = "MIDX"[op & 3u];
+				uint32_t len = op >> 4;
+				do { *p-- = (char)('0' + len % 10u); len /= 10u; } while(len);
+			}
+			cur += __shfl_sync(0xffffffffu, incl, 31);
+		}
+	}
+	if(lane == 0){ recs[t].cigar_off = t0; recs[t].n_cigar = (uint32_t)(t1 - t0); }
+}
+
 /* Run the job lists [first[k], n[k]) of all six executor classes CONCURRENTLY (one auxiliary stream per class, forked from
  * and joined back to the context stream), each work queue ordered longest-job-first to cut the tail. */
 static int run_dp_lists(zmo_ctx *c, const JobLists &L, const uint32_t *n, const uint32_t *first, uint32_t *arena, uint32_t *cig_arena, DPRes *d_res){
@@ -372,7 +414,15 @@ static int run_dp_lists(zmo_ctx *c, const JobLists &L, const uint32_t *n, const 
 }
 
 /* res index -> position in the concatenated job array [ext_w | ext_n | glb_w | glb_n] is the identity by construction */
+static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32_t nt, zmo_record_t *recs, uint32_t *cigars, uint64_t cigar_cap, uint64_t *cigar_needed, bool as_text);
 extern "C" int zmo_pair_align(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32_t nt, zmo_record_t *recs, uint32_t *cigars, uint64_t cigar_cap, uint64_t *cigar_needed){
+	return pair_align_impl(c, slot, tasks, nt, recs, cigars, cigar_cap, cigar_needed, false);
+}
+extern "C" int zmo_pair_align_text(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32_t nt, zmo_record_t *recs, char *cigar_text, uint64_t text_cap, uint64_t *text_needed){
+	return pair_align_impl(c, slot, tasks, nt, recs, (uint32_t*)cigar_text, text_cap, text_needed, true);
+}
+/* cigar_cap / *cigar_needed count ops (binary) or bytes (text) */
+static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32_t nt, zmo_record_t *recs, uint32_t *cigars, uint64_t cigar_cap, uint64_t *cigar_needed, bool as_text){
 	if(!c || (nt && (!tasks || !recs))) return zmo_set_err(ZMO_ERR_ARG, "null argument");
 	if(slot < 0 || slot > 1) return zmo_set_err(ZMO_ERR_ARG, "slot must be 0 or 1");
 	if(cigar_needed) *cigar_needed = 0;
@@ -476,13 +526,42 @@ extern "C" int zmo_pair_align(zmo_ctx *c, int slot, const zmo_task_t *tasks, uin
 		unsigned long long total = 0;
 		CUDA_TRY(cudaMemcpyAsync(&total, d_ooff + nt, 8, cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
-		if(cigar_needed) *cigar_needed = total;
-		if(total > cigar_cap) return zmo_set_err(ZMO_ERR_CAPACITY, "cigar buffer too small: need %llu", total);
+		if(!as_text){
+			if(cigar_needed) *cigar_needed = total;
+			if(total > cigar_cap) return zmo_set_err(ZMO_ERR_CAPACITY, "cigar buffer too small: need %llu", total);
+		}
 		if(c->s5.reserve((total + 16) * 4) || c->cubtmp.reserve((size_t)nt * sizeof(zmo_record_t) + 256)) return ZMO_ERR_CUDA;
 		/* a job's index in [ext_w | ext_n | glb_w | glb_n] equals its result index by construction */
 		zmo_record_t *d_recs = c->cubtmp.as<zmo_record_t>();
 		k_finish<<<(nt + 63) / 64, 64, 0, c->stream>>>(d_tasks, nt, d_regs, d_res, d_jobs, cig_arena, A, d_ts, d_ooff, c->s5.as<uint32_t>(), d_recs); c->launches++;
 		CUDA_TRY(cudaGetLastError());
+		if(as_text){
+			/* text lengths -> offsets (d_need / d_ooff are free again) -> text in s3 (the job lists are dead after k_finish) */
+			k_cig_textlen<<<(nt + 3) / 4, 128, 0, c->stream>>>(d_recs, nt, c->s5.as<uint32_t>(), d_need); c->launches++;
+			CUDA_TRY(cudaMemsetAsync(d_need + nt, 0, 8, c->stream));
+			{
+				size_t tb = 0; unsigned long long *d_toff = d_ooff;
+				CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_need, d_toff, nt + 1, c->stream));
+				if(c->s2.reserve(tb + 256)) return ZMO_ERR_CUDA;                      /* scan temp must not alias d_recs (cubtmp); the task state in s2 is dead after k_finish */
+				CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->s2.p, tb, d_need, d_toff, nt + 1, c->stream)); c->launches++;
+			}
+			unsigned long long tbytes = 0;
+			CUDA_TRY(cudaMemcpyAsync(&tbytes, d_ooff + nt, 8, cudaMemcpyDeviceToHost, c->stream));
+			CUDA_TRY(cudaStreamSynchronize(c->stream));
+			if(cigar_needed) *cigar_needed = tbytes;
+			if(tbytes > cigar_cap) return zmo_set_err(ZMO_ERR_CAPACITY, "cigar text buffer too small: need %llu bytes", tbytes);
+			if(c->s3.reserve(tbytes + 64)) return ZMO_ERR_CUDA;
+			k_cig_text<<<(nt + 3) / 4, 128, 0, c->stream>>>(d_recs, nt, c->s5.as<uint32_t>(), d_ooff, c->s3.as<char>()); c->launches++;
+			CUDA_TRY(cudaGetLastError());
+			{
+				StageTimer tm(c, ST_COPY);
+				CUDA_TRY(cudaMemcpyAsync(recs, d_recs, (size_t)nt * sizeof(zmo_record_t), cudaMemcpyDeviceToHost, c->stream));
+				if(tbytes) CUDA_TRY(cudaMemcpyAsync(cigars, c->s3.p, tbytes, cudaMemcpyDeviceToHost, c->stream));
+			}
+			CUDA_TRY(cudaStreamSynchronize(c->stream));
+			c->counters[6] += (size_t)nt * sizeof(zmo_record_t) + tbytes;
+			return 0;
+		}
 		{
 			StageTimer tm(c, ST_COPY);
 			CUDA_TRY(cudaMemcpyAsync(recs, d_recs, (size_t)nt * sizeof(zmo_record_t), cudaMemcpyDeviceToHost, c->stream));

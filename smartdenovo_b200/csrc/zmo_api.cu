@@ -11,6 +11,19 @@ int zmo_set_err(int code, const char *fmt, ...){
 }
 extern "C" const char *zmo_last_error(void){ return g_zmo_err.c_str(); }
 
+static int ctx_init(zmo_ctx *c, int device, const zmo_params_t *par){
+	cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+	if(prop.major < 10) return zmo_set_err(ZMO_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+	c->device = device; c->n_sm = prop.multiProcessorCount; c->par = *par;
+	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CUDA_TRY(cudaEventCreate(&c->ev0)); CUDA_TRY(cudaEventCreate(&c->ev1)); CUDA_TRY(cudaEventCreate(&c->ev_fork));
+	for(int k = 0; k < 6; k++){ CUDA_TRY(cudaStreamCreateWithFlags(&c->aux[k], cudaStreamNonBlocking)); CUDA_TRY(cudaEventCreate(&c->ev_a0[k])); CUDA_TRY(cudaEventCreate(&c->ev_a1[k])); }
+	if(c->d_ctr.reserve(CTR_TOTAL * 8)) return ZMO_ERR_CUDA;
+	CUDA_TRY(cudaMemsetAsync(c->d_ctr.p, 0, CTR_TOTAL * 8, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return ZMO_OK;
+}
+
 extern "C" int zmo_ctx_create(zmo_ctx **out, int device, const zmo_params_t *par){
 	if(!out || !par) return zmo_set_err(ZMO_ERR_ARG, "null argument");
 	*out = nullptr;
@@ -19,18 +32,23 @@ extern "C" int zmo_ctx_create(zmo_ctx **out, int device, const zmo_params_t *par
 	if(e != cudaSuccess || ndev == 0) return zmo_set_err(ZMO_ERR_CUDA, "no CUDA device available (%s); libzmo_b200 has no CPU fallback", e == cudaSuccess? "0 devices" : cudaGetErrorString(e));
 	if(device < 0 || device >= ndev) return zmo_set_err(ZMO_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
 	CUDA_TRY(cudaSetDevice(device));
-	cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-	if(prop.major < 10) return zmo_set_err(ZMO_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
 	if(par->ksize < 5 || par->ksize > 32 || par->zsize < 5 || par->zsize > 16 || par->ksave < 1 || par->E >= 0)
 		return zmo_set_err(ZMO_ERR_ARG, "parameter out of range (k 5..32, z 5..16, S>=1, E<0)");
 	zmo_ctx *c = new zmo_ctx();
-	c->device = device; c->n_sm = prop.multiProcessorCount; c->par = *par;
-	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-	CUDA_TRY(cudaEventCreate(&c->ev0)); CUDA_TRY(cudaEventCreate(&c->ev1)); CUDA_TRY(cudaEventCreate(&c->ev_fork));
-	for(int k = 0; k < 6; k++){ CUDA_TRY(cudaStreamCreateWithFlags(&c->aux[k], cudaStreamNonBlocking)); CUDA_TRY(cudaEventCreate(&c->ev_a0[k])); CUDA_TRY(cudaEventCreate(&c->ev_a1[k])); }
-	if(c->d_ctr.reserve(CTR_TOTAL * 8)) { delete c; return ZMO_ERR_CUDA; }
-	CUDA_TRY(cudaMemsetAsync(c->d_ctr.p, 0, CTR_TOTAL * 8, c->stream));
-	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	c->st = &c->own;
+	if(int rc = ctx_init(c, device, par)){ zmo_ctx_destroy(c); return rc; }
+	*out = c;
+	return ZMO_OK;
+}
+
+extern "C" int zmo_ctx_clone(zmo_ctx *root, zmo_ctx **out){
+	if(!root || !out) return zmo_set_err(ZMO_ERR_ARG, "null argument");
+	*out = nullptr;
+	if(root->is_clone) return zmo_set_err(ZMO_ERR_ARG, "clone of a clone");
+	CUDA_TRY(cudaSetDevice(root->device));
+	zmo_ctx *c = new zmo_ctx();
+	c->st = root->st; c->is_clone = true;
+	if(int rc = ctx_init(c, root->device, &root->par)){ zmo_ctx_destroy(c); return rc; }
 	*out = c;
 	return ZMO_OK;
 }
@@ -38,13 +56,14 @@ extern "C" int zmo_ctx_create(zmo_ctx **out, int device, const zmo_params_t *par
 extern "C" void zmo_ctx_destroy(zmo_ctx *c){
 	if(!c) return;
 	cudaSetDevice(c->device);
-	cudaStreamSynchronize(c->stream);
-	DevBuf *bufs[] = { &c->rd_words, &c->rd_woff, &c->rd_len, &c->ix_mer, &c->ix_off, &c->ix_flt, &c->ix_post, &c->s0, &c->s1, &c->s2, &c->s3, &c->s4, &c->s5, &c->s6, &c->s7, &c->cubtmp, &c->arena, &c->d_ctr };
+	if(c->stream) cudaStreamSynchronize(c->stream);
+	if(!c->is_clone){ DevBuf *sb[] = { &c->own.rd_words, &c->own.rd_woff, &c->own.rd_len, &c->own.ix_mer, &c->own.ix_off, &c->own.ix_flt, &c->own.ix_post }; for(DevBuf *b : sb) b->release(); }
+	DevBuf *bufs[] = { &c->s0, &c->s1, &c->s2, &c->s3, &c->s4, &c->s5, &c->s6, &c->s7, &c->cubtmp, &c->arena, &c->d_ctr };
 	for(DevBuf *b : bufs) b->release();
 	for(int s = 0; s < 2; s++){ c->slot[s].pairs.release(); c->slot[s].seeds.release(); c->slot[s].wins.release(); c->slot[s].anchors.release(); }
 	c->h0.release(); c->h1.release(); c->h2.release();
 	for(int k = 0; k < 6; k++){ if(c->aux[k]) cudaStreamDestroy(c->aux[k]); if(c->ev_a0[k]) cudaEventDestroy(c->ev_a0[k]); if(c->ev_a1[k]) cudaEventDestroy(c->ev_a1[k]); }
-	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_fork); cudaStreamDestroy(c->stream);
+	if(c->ev0) cudaEventDestroy(c->ev0); if(c->ev1) cudaEventDestroy(c->ev1); if(c->ev_fork) cudaEventDestroy(c->ev_fork); if(c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
 
@@ -88,26 +107,27 @@ __global__ void k_repack(const unsigned long long *bank, const unsigned long lon
 
 extern "C" int zmo_reads_upload(zmo_ctx *c, const uint64_t *bank, uint64_t n_bases, const uint64_t *rdoff, const uint32_t *rdlen, uint32_t n_reads){
 	if(!c || !bank || !rdoff || !rdlen || n_reads == 0) return zmo_set_err(ZMO_ERR_ARG, "null/empty argument");
+	if(c->is_clone) return zmo_set_err(ZMO_ERR_STATE, "reads are uploaded through the root context");
 	CUDA_TRY(cudaSetDevice(c->device));
-	c->n_reads = n_reads; c->n_bases = n_bases; c->have_index = false;
-	c->h_rdlen.assign(rdlen, rdlen + n_reads); c->h_woff.resize((size_t)n_reads + 1);
-	uint64_t tw = 0; c->max_rdlen = 0;
+	c->st->n_reads = n_reads; c->st->n_bases = n_bases; c->st->have_index = false;
+	c->st->h_rdlen.assign(rdlen, rdlen + n_reads); c->st->h_woff.resize((size_t)n_reads + 1);
+	uint64_t tw = 0; c->st->max_rdlen = 0;
 	for(uint32_t i = 0; i < n_reads; i++){
 		if(rdoff[i] + rdlen[i] > n_bases) return zmo_set_err(ZMO_ERR_ARG, "read %u exceeds the bank", i);
-		c->h_woff[i] = tw; tw += (((uint64_t)rdlen[i] + 15) / 16 + 3) & ~3ULL; tw += 4;   /* 16-byte aligned, one spare quad */
-		if(rdlen[i] > c->max_rdlen) c->max_rdlen = rdlen[i];
+		c->st->h_woff[i] = tw; tw += (((uint64_t)rdlen[i] + 15) / 16 + 3) & ~3ULL; tw += 4;   /* 16-byte aligned, one spare quad */
+		if(rdlen[i] > c->st->max_rdlen) c->st->max_rdlen = rdlen[i];
 	}
-	c->h_woff[n_reads] = tw;
+	c->st->h_woff[n_reads] = tw;
 	const uint64_t bank_words = (n_bases + 31) / 32 + 1;
-	if(c->s0.reserve(bank_words * 8) || c->s1.reserve((size_t)n_reads * 8) || c->rd_words.reserve(tw * 4 + 64) || c->rd_woff.reserve(((size_t)n_reads + 1) * 8) || c->rd_len.reserve((size_t)n_reads * 4)) return ZMO_ERR_CUDA;
+	if(c->s0.reserve(bank_words * 8) || c->s1.reserve((size_t)n_reads * 8) || c->st->rd_words.reserve(tw * 4 + 64) || c->st->rd_woff.reserve(((size_t)n_reads + 1) * 8) || c->st->rd_len.reserve((size_t)n_reads * 4)) return ZMO_ERR_CUDA;
 	{
 		StageTimer t(c, ST_COPY);
 		CUDA_TRY(cudaMemcpyAsync(c->s0.p, bank, ((n_bases + 31) / 32) * 8, cudaMemcpyHostToDevice, c->stream));
 		CUDA_TRY(cudaMemcpyAsync(c->s1.p, rdoff, (size_t)n_reads * 8, cudaMemcpyHostToDevice, c->stream));
-		CUDA_TRY(cudaMemcpyAsync(c->rd_len.p, rdlen, (size_t)n_reads * 4, cudaMemcpyHostToDevice, c->stream));
-		CUDA_TRY(cudaMemcpyAsync(c->rd_woff.p, c->h_woff.data(), ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(c->st->rd_len.p, rdlen, (size_t)n_reads * 4, cudaMemcpyHostToDevice, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(c->st->rd_woff.p, c->st->h_woff.data(), ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
 		const int bs = 256; const uint64_t nb = (tw + bs - 1) / bs;
-		k_repack<<<(unsigned)nb, bs, 0, c->stream>>>(c->s0.as<unsigned long long>(), c->s1.as<unsigned long long>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<unsigned long long>(), n_reads, c->rd_words.as<uint32_t>(), tw);
+		k_repack<<<(unsigned)nb, bs, 0, c->stream>>>(c->s0.as<unsigned long long>(), c->s1.as<unsigned long long>(), c->st->rd_len.as<uint32_t>(), c->st->rd_woff.as<unsigned long long>(), n_reads, c->st->rd_words.as<uint32_t>(), tw);
 		c->launches++;
 		CUDA_TRY(cudaGetLastError());
 	}

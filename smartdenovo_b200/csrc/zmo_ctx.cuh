@@ -64,17 +64,8 @@ struct SeedSlot {
 	std::vector<int32_t> h_wspan;       /* per kept window: q span, c span, #anchors (host copy for job sizing) */
 };
 
-struct zmo_ctx {
-	int device = 0, n_sm = 0;
-	zmo_params_t par;
-	cudaStream_t stream = nullptr;
-	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-	cudaStream_t aux[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};     /* concurrent DP executor classes */
-	cudaEvent_t ev_fork = nullptr, ev_a0[6] = {nullptr}, ev_a1[6] = {nullptr};
-	double stage_ms[ST_N] = {0};
-	uint64_t launches = 0;
-	uint64_t counters[8] = {0};
-	/* reads */
+/* read store + k-mer index: built by the root context, shared read-only with its clones (zmo_ctx_clone) */
+struct ZStore {
 	uint32_t n_reads = 0; uint64_t n_bases = 0;
 	DevBuf rd_words;     /* uint32 packed, per read 16-byte aligned */
 	DevBuf rd_woff;      /* uint64 word offset per read */
@@ -88,6 +79,21 @@ struct zmo_ctx {
 	DevBuf ix_off;       /* uint64 posting offset (n_ent+1) */
 	DevBuf ix_flt;       /* uint8 filtered flag */
 	DevBuf ix_post;      /* uint32 postings (rd_id<<1|dir) */
+};
+
+struct zmo_ctx {
+	int device = 0, n_sm = 0;
+	zmo_params_t par;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaStream_t aux[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};     /* concurrent DP executor classes */
+	cudaEvent_t ev_fork = nullptr, ev_a0[6] = {nullptr}, ev_a1[6] = {nullptr};
+	double stage_ms[ST_N] = {0};
+	uint64_t launches = 0;
+	uint64_t counters[8] = {0};
+	ZStore *st = nullptr;  /* read store + k-mer index: own (root context) or the root's (clone) */
+	ZStore own;
+	bool is_clone = false;
 	/* scratch */
 	DevBuf s0, s1, s2, s3, s4, s5, s6, s7, cubtmp;
 	DevBuf arena;        /* bump-allocated DP scratch (traceback, staged sequences) */
@@ -104,7 +110,7 @@ struct StageTimer {
 
 /* device-side read accessors */
 struct DevReads { const uint32_t *words; const uint64_t *woff; const uint32_t *len; uint32_t n; };
-static inline DevReads dev_reads(const zmo_ctx *c){ DevReads r; r.words = c->rd_words.as<uint32_t>(); r.woff = c->rd_woff.as<uint64_t>(); r.len = c->rd_len.as<uint32_t>(); r.n = c->n_reads; return r; }
+static inline DevReads dev_reads(const zmo_ctx *c){ DevReads r; r.words = c->st->rd_words.as<uint32_t>(); r.woff = c->st->rd_woff.as<uint64_t>(); r.len = c->st->rd_len.as<uint32_t>(); r.n = c->st->n_reads; return r; }
 
 /* indices into the device counter block d_ctr (uint64 each) */
 enum { CTR_CELLS_EXT = 0, CTR_CELLS_WIN, CTR_CELLS_GAP, CTR_ZPAIRS, CTR_POSTINGS, CTR_ARENA = 8, CTR_WORK = 9, CTR_OVERFLOW = 10, CTR_N1 = 11, CTR_N2 = 12, CTR_N3 = 13, CTR_N4 = 14, CTR_N5 = 15, CTR_CIG = 16, CTR_JOBS = 17 /* ..22 */, CTR_WORKK = 23 /* ..28 */, CTR_TOTAL = 32 };

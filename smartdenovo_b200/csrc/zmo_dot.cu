@@ -21,7 +21,7 @@ __global__ void k_p_dot(const unsigned long long *cache_off, const zmo_pair_t *p
 
 extern "C" int zmo_pair_dotmatrix(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, zmo_dotres_t *out){
 	if(!c || (np && (!pairs || !out))) return zmo_set_err(ZMO_ERR_ARG, "null argument");
-	if(c->n_reads == 0) return zmo_set_err(ZMO_ERR_STATE, "no reads uploaded");
+	if(c->st->n_reads == 0) return zmo_set_err(ZMO_ERR_STATE, "no reads uploaded");
 	if(np == 0) return 0;
 	CUDA_TRY(cudaSetDevice(c->device));
 	StageTimer tm(c, ST_DOT);

@@ -153,7 +153,7 @@ static int dp_batch(zmo_ctx *c, int kind /*0 ext mode0, 1 ext mode1, 2 global*/,
 	uint64_t scratch = 0, cig = 0;
 	for(uint32_t i = 0; i < n; i++){
 		const zmo_dp_problem_t &p = probs[i]; DPJob J; memset(&J, 0, sizeof(J));
-		if(p.q_rid >= c->n_reads || p.t_rid >= c->n_reads) return zmo_set_err(ZMO_ERR_ARG, "problem %u: read id out of range", i);
+		if(p.q_rid >= c->st->n_reads || p.t_rid >= c->st->n_reads) return zmo_set_err(ZMO_ERR_ARG, "problem %u: read id out of range", i);
 		J.q_rid = p.q_rid; J.t_rid = p.t_rid; J.q_start = p.q_start; J.q_step = p.q_step; J.q_comp = p.q_comp; J.qlen = p.qlen;
 		J.t_start = p.t_start; J.t_step = p.t_step; J.t_comp = p.t_comp; J.tlen = p.tlen; J.init = p.init_score; J.Wp = p.W; J.Wmax = 0;
 		J.out_idx = i; J.cig_off = cig; J.cig_cap = (uint32_t)((p.qlen > 0? p.qlen : 0) + (p.tlen > 0? p.tlen : 0) + 4);

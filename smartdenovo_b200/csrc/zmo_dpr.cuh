@@ -155,7 +155,9 @@ __device__ __forceinline__ void reg_sweep(const BandSmem &S, const uint32_t *row
 		const bool act = j0 < je;
 		const int lo = jb - j0, hi = je - j0;
 		const unsigned long long x = xw ^ (0x5555555555555555ull * (unsigned long long)pk_base(rowpk, i));
-		int m[C]; int b = ZMO_BIGNEG;
+		/* m = diagonal move; g[k] = best F value reaching cell k from gaps opened INSIDE this thread's block (no dependence on
+		 * what enters from the left), so that after the scan every cell's F is max(entry + k*E, g[k]) with no serial chain */
+		int m[C], g[C]; int b = ZMO_BIGNEG;
 		if(act){
 			int hd = left;
 			#pragma unroll
@@ -163,12 +165,12 @@ __device__ __forceinline__ void reg_sweep(const BandSmem &S, const uint32_t *row
 				const int mm = hd + (((x >> (62 - 2 * k)) & 3ull)? P.X : P.M);
 				m[k] = (k >= lo && k < hi)? mm : ZMO_BIGNEG;
 				hd = H[k];
+				g[k] = b;
+				const int t2 = m[k] + DE; b += E; if(b < t2) b = t2;
 			}
-			#pragma unroll
-			for(int k = 0; k < C; k++){ const int t2 = m[k] + DE; b += E; if(b < t2) b = t2; }
 		} else {
 			#pragma unroll
-			for(int k = 0; k < C; k++) m[k] = ZMO_BIGNEG;
+			for(int k = 0; k < C; k++){ m[k] = ZMO_BIGNEG; g[k] = ZMO_BIGNEG; }
 		}
 		/* exclusive max-plus prefix over the threads in band order (rank r) */
 		const int t0 = b0 & (NT - 1), w0 = t0 >> 5, l0 = t0 & 31;
@@ -197,13 +199,14 @@ __device__ __forceinline__ void reg_sweep(const BandSmem &S, const uint32_t *row
 			for(int k = 0; k < C; k++){
 				const int j = j0 + k; const int mm = m[k]; int ee = Ev[k]; int h; uint32_t d;
 				const bool inb = k >= lo && k < hi;
+				int fk = f + k * E; if(fk < g[k]) fk = g[k];
 				if(mm >= ee){ d = 0; h = mm; } else { d = 1; h = ee; }
-				if(h < f){ d = 2; h = f; }
+				if(h < fk){ d = 2; h = fk; }
 				const int hn = inb? h : NEGV;
 				if(KIND == 1){ if(hn > lmax){ lmax = hn; larg = j; } }
 				else if(KIND == 0){ if(hn >= lmax){ lmax = hn; larg = j; } }
 				const int t1 = mm + IE; ee += E; if(ee > t1) d |= 4u; else ee = t1;
-				const int t2 = mm + DE; f += E; if(f > t2) d |= 8u; else f = t2;
+				if(fk + E > mm + DE) d |= 8u;
 				H[k] = hn; Ev[k] = inb? ee : NEGV;
 				zw[k >> 3] |= d << ((k & 7) << 2);
 				if(j == je - 1) S.smisc[0] = h;

@@ -72,8 +72,9 @@ __global__ void k_idx_gather(const unsigned long long *run_start, const unsigned
 
 extern "C" int zmo_index_build(zmo_ctx *c, uint32_t beg, uint32_t end, uint32_t *kcut_io, zmo_index_stats_t *stats){
 	if(!c || !kcut_io) return zmo_set_err(ZMO_ERR_ARG, "null argument");
-	if(c->n_reads == 0) return zmo_set_err(ZMO_ERR_STATE, "no reads uploaded");
-	if(end > c->n_reads) end = c->n_reads;     /* the reference reads past the table here when n_rd % n_idx != 0 (wtzmo.c:1283) */
+	if(c->is_clone) return zmo_set_err(ZMO_ERR_STATE, "the index is built through the root context");
+	if(c->st->n_reads == 0) return zmo_set_err(ZMO_ERR_STATE, "no reads uploaded");
+	if(end > c->st->n_reads) end = c->st->n_reads;     /* the reference reads past the table here when n_rd % n_idx != 0 (wtzmo.c:1283) */
 	if(beg >= end) return zmo_set_err(ZMO_ERR_ARG, "empty read range");
 	CUDA_TRY(cudaSetDevice(c->device));
 	StageTimer tm(c, ST_INDEX);
@@ -86,7 +87,7 @@ extern "C" int zmo_index_build(zmo_ctx *c, uint32_t beg, uint32_t end, uint32_t 
 	unsigned long long N = 0;
 	CUDA_TRY(cudaMemcpyAsync(&N, d_off + nr, 8, cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
-	if(N == 0){ c->n_ent = 0; c->n_post = 0; c->have_index = true; if(*kcut_io < 2) *kcut_io = 100; c->kcut = *kcut_io; if(stats) memset(stats, 0, sizeof(*stats)); return 0; }
+	if(N == 0){ c->st->n_ent = 0; c->st->n_post = 0; c->st->have_index = true; if(*kcut_io < 2) *kcut_io = 100; c->st->kcut = *kcut_io; if(stats) memset(stats, 0, sizeof(*stats)); return 0; }
 	if(c->s2.reserve(N * 8) || c->s3.reserve(N * 8) || c->s4.reserve(N * 4) || c->s5.reserve(N * 4)) return ZMO_ERR_CUDA;
 	unsigned long long *k_in = c->s2.as<unsigned long long>(), *k_out = c->s3.as<unsigned long long>();
 	uint32_t *v_in = c->s4.as<uint32_t>(), *v_out = c->s5.as<uint32_t>();
@@ -95,7 +96,7 @@ extern "C" int zmo_index_build(zmo_ctx *c, uint32_t beg, uint32_t end, uint32_t 
 	/* run-length encode (hand-rolled, 64-bit safe): head flags -> exclusive scan -> scatter of
 	 * distinct k-mers (ix_mer) and run starts; counts = difference of consecutive run starts */
 	if(N >= 0xFFFFFFF0ull) return zmo_set_err(ZMO_ERR_CAPACITY, "index partition too large (%llu sampled k-mers); split it with -G", N);
-	if(c->ix_mer.reserve(N * 8) || c->s0.reserve((N + 2) * 8) || c->s6.reserve(N * 4 + 16) || c->s7.reserve(N * 4 + 16)) return ZMO_ERR_CUDA;
+	if(c->st->ix_mer.reserve(N * 8) || c->s0.reserve((N + 2) * 8) || c->s6.reserve(N * 4 + 16) || c->s7.reserve(N * 4 + 16)) return ZMO_ERR_CUDA;
 	unsigned long long *ctr = c->d_ctr.as<unsigned long long>();
 	uint32_t *d_hflag = c->s6.as<uint32_t>(), *d_hpos = c->s7.as<uint32_t>();
 	unsigned long long *run_start = c->s0.as<unsigned long long>();
@@ -106,7 +107,7 @@ extern "C" int zmo_index_build(zmo_ctx *c, uint32_t beg, uint32_t end, uint32_t 
 	CUDA_TRY(cudaMemcpyAsync(&lf, d_hflag + (N - 1), 4, cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	const unsigned long long ne = (unsigned long long)lp + lf;
-	k_idx_runs<<<(unsigned)((N + 255) / 256), 256, 0, c->stream>>>(k_out, d_hflag, d_hpos, N, c->ix_mer.as<unsigned long long>(), run_start); c->launches++;
+	k_idx_runs<<<(unsigned)((N + 255) / 256), 256, 0, c->stream>>>(k_out, d_hflag, d_hpos, N, c->st->ix_mer.as<unsigned long long>(), run_start); c->launches++;
 	uint32_t *d_rc = v_in;       /* v_in is free after the sort */
 	k_idx_counts<<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(run_start, ne, N, d_rc); c->launches++;
 	/* K (wtzmo.c:380-393): ktot = sum of saturated counts over all distinct k-mers */
@@ -120,23 +121,23 @@ extern "C" int zmo_index_build(zmo_ctx *c, uint32_t beg, uint32_t end, uint32_t 
 		kavg = (uint32_t)(ktot / (ne + 1));
 		if(K < 2){ uint32_t ka = kavg < 20? 20 : kavg; K = ka * 5; }
 	}
-	*kcut_io = K; c->kcut = K;
+	*kcut_io = K; c->st->kcut = K;
 	/* filter flags, kept offsets, postings */
-	if(c->s1.reserve((ne + 1) * 8) || c->ix_off.reserve((ne + 2) * 8) || c->ix_flt.reserve(ne + 8)) return ZMO_ERR_CUDA;
+	if(c->s1.reserve((ne + 1) * 8) || c->st->ix_off.reserve((ne + 2) * 8) || c->st->ix_flt.reserve(ne + 8)) return ZMO_ERR_CUDA;
 	unsigned long long *kept = c->s1.as<unsigned long long>();
 	CUDA_TRY(cudaMemsetAsync(ctr + CTR_N3, 0, 16, c->stream));
-	k_idx_flags<<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(d_rc, ne, K, c->ix_flt.as<uint8_t>(), kept, ctr + CTR_N3); c->launches++;
+	k_idx_flags<<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(d_rc, ne, K, c->st->ix_flt.as<uint8_t>(), kept, ctr + CTR_N3); c->launches++;
 	CUDA_TRY(cudaMemsetAsync(kept + ne, 0, 8, c->stream));
-	CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, kept, c->ix_off.as<unsigned long long>(), (uint64_t)ne + 1, c->stream));
+	CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, kept, c->st->ix_off.as<unsigned long long>(), (uint64_t)ne + 1, c->stream));
 	unsigned long long np = 0, st2[2] = {0, 0};
-	CUDA_TRY(cudaMemcpyAsync(&np, c->ix_off.as<unsigned long long>() + ne, 8, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(&np, c->st->ix_off.as<unsigned long long>() + ne, 8, cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaMemcpyAsync(st2, ctr + CTR_N3, 16, cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
-	if(c->ix_post.reserve((np + 4) * 4)) return ZMO_ERR_CUDA;
-	k_idx_gather<<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(run_start, c->ix_off.as<unsigned long long>(), c->ix_flt.as<uint8_t>(), d_rc, ne, v_out, c->ix_post.as<uint32_t>()); c->launches++;
+	if(c->st->ix_post.reserve((np + 4) * 4)) return ZMO_ERR_CUDA;
+	k_idx_gather<<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(run_start, c->st->ix_off.as<unsigned long long>(), c->st->ix_flt.as<uint8_t>(), d_rc, ne, v_out, c->st->ix_post.as<uint32_t>()); c->launches++;
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
-	c->n_ent = ne; c->n_post = np; c->have_index = true;
+	c->st->n_ent = ne; c->st->n_post = np; c->st->have_index = true;
 	if(stats){ stats->n_kmers = ne; stats->n_postings = np; stats->n_filtered_high = st2[0]; stats->n_indexed = st2[1]; stats->kcut = K; stats->kavg = kavg; }
 	return 0;
 }
@@ -235,14 +236,14 @@ __global__ void k_cand_offsets(const uint32_t *ev_q, uint32_t nev, uint32_t nq, 
 
 extern "C" int zmo_candidates(zmo_ctx *c, const uint32_t *qids, uint32_t nq, uint64_t *ev_off, zmo_event_t *events, uint64_t ev_cap, uint64_t *ev_needed){
 	if(!c || !qids || !ev_off) return zmo_set_err(ZMO_ERR_ARG, "null argument");
-	if(!c->have_index) return zmo_set_err(ZMO_ERR_STATE, "zmo_index_build has not been called");
+	if(!c->st->have_index) return zmo_set_err(ZMO_ERR_STATE, "zmo_index_build has not been called");
 	if(ev_needed) *ev_needed = 0;
 	if(nq == 0){ ev_off[0] = 0; return 0; }
-	for(uint32_t i = 0; i < nq; i++) if(qids[i] >= c->n_reads) return zmo_set_err(ZMO_ERR_ARG, "query id out of range");
+	for(uint32_t i = 0; i < nq; i++) if(qids[i] >= c->st->n_reads) return zmo_set_err(ZMO_ERR_ARG, "query id out of range");
 	CUDA_TRY(cudaSetDevice(c->device));
 	StageTimer tm(c, ST_CAND);
 	DevReads R = dev_reads(c);
-	IdxView I; I.mer = c->ix_mer.as<unsigned long long>(); I.off = c->ix_off.as<unsigned long long>(); I.flt = c->ix_flt.as<uint8_t>(); I.post = c->ix_post.as<uint32_t>(); I.n = c->n_ent;
+	IdxView I; I.mer = c->st->ix_mer.as<unsigned long long>(); I.off = c->st->ix_off.as<unsigned long long>(); I.flt = c->st->ix_flt.as<uint8_t>(); I.post = c->st->ix_post.as<uint32_t>(); I.n = c->st->n_ent;
 	if(nq > 65535) return zmo_set_err(ZMO_ERR_ARG, "at most 65535 query reads per zmo_candidates call");
 	if(c->s0.reserve((size_t)nq * 4) || c->s1.reserve(((size_t)nq + 2) * 8) || c->s2.reserve(((size_t)nq + 2) * 8)) return ZMO_ERR_CUDA;
 	uint32_t *d_q = c->s0.as<uint32_t>(); unsigned long long *d_nch = c->s1.as<unsigned long long>(), *d_off = c->s2.as<unsigned long long>();

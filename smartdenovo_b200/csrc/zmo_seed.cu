@@ -226,7 +226,7 @@ int seed_prepare(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, int mode, See
 	DevReads R = dev_reads(c);
 	std::vector<uint32_t> uq, pq(np), pc(np); std::unordered_map<uint32_t, uint32_t> qmap;
 	for(uint32_t i = 0; i < np; i++){
-		if(pairs[i].qid >= c->n_reads || pairs[i].cid >= c->n_reads) return zmo_set_err(ZMO_ERR_ARG, "pair %u: read id out of range", i);
+		if(pairs[i].qid >= c->st->n_reads || pairs[i].cid >= c->st->n_reads) return zmo_set_err(ZMO_ERR_ARG, "pair %u: read id out of range", i);
 		auto it = qmap.find(pairs[i].qid);
 		if(it == qmap.end()){ it = qmap.emplace(pairs[i].qid, (uint32_t)uq.size()).first; uq.push_back(pairs[i].qid); }
 		pq[i] = it->second; pc[i] = pairs[i].cid;
@@ -274,7 +274,7 @@ int seed_prepare(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, int mode, See
 	 * -> sort by the key of the consumer's first sort -> DevZPair lists.  s2: pair chunk table | tie flags,
 	 * s3/s4: keys, s6/arena: values + per-item counters (s7 keeps the z-index). */
 	if(np > (mode? 32768u : 65536u)) return zmo_set_err(ZMO_ERR_ARG, "at most %u pairs per call", mode? 32768u : 65536u);
-	if(c->max_rdlen >= (1u << 24)) return zmo_set_err(ZMO_ERR_ARG, "reads of 2^24 bases or more are not supported (reference limit rdlen:24, wtzmo.c:88)");
+	if(c->st->max_rdlen >= (1u << 24)) return zmo_set_err(ZMO_ERR_ARG, "reads of 2^24 bases or more are not supported (reference limit rdlen:24, wtzmo.c:88)");
 	if(c->s2.reserve(((size_t)np + 2) * 24 + np + 64)) return ZMO_ERR_CUDA;
 	unsigned long long *d_pnch = c->s2.as<unsigned long long>(), *d_pchoff = d_pnch + np + 1, *d_coff = d_pchoff + np + 1; uint8_t *d_tie = (uint8_t*)(d_coff + np + 2);
 	ZIdxView ZV; ZV.slots = d_slots; ZV.slot_beg = d_slot_beg; ZV.zs = d_zs; ZV.zoff = d_zoff;
@@ -341,7 +341,7 @@ int seed_prepare(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, int mode, See
 extern "C" int zmo_pair_windows(zmo_ctx *c, int slot, const zmo_pair_t *pairs, uint32_t np, zmo_pairseed_t *seeds, zmo_window_t *wins, uint64_t win_cap, uint64_t *win_needed){
 	if(!c || (np && (!pairs || !seeds))) return zmo_set_err(ZMO_ERR_ARG, "null argument");
 	if(slot < 0 || slot > 1) return zmo_set_err(ZMO_ERR_ARG, "slot must be 0 or 1");
-	if(c->n_reads == 0) return zmo_set_err(ZMO_ERR_STATE, "no reads uploaded");
+	if(c->st->n_reads == 0) return zmo_set_err(ZMO_ERR_STATE, "no reads uploaded");
 	if(win_needed) *win_needed = 0;
 	SeedSlot &SL = c->slot[slot];
 	SL.np = 0; SL.n_wins = SL.n_anchors = 0;
