@@ -74,12 +74,21 @@ def test_clone_shares_reads_and_index(staged):
         off1, ev1 = c.candidates(np.arange(8, dtype=np.uint32))
         assert np.array_equal(off0, off1) and np.array_equal(ev0, ev1)
         s1, w1 = c.pair_windows(pairs)
-        assert np.array_equal(s1, seeds) and np.array_equal(w1, wins)
+        # kept windows are bump-allocated on the device: win_off (arena order) is not reproducible, the windows of a pair are
+        for f in ("n_zpair", "ovl", "n_win"):
+            assert np.array_equal(s1[f], seeds[f])
+        assert len(w1) == len(wins)
+        for a, b in zip(seeds, s1):
+            for d in (0, 1):
+                n = int(a["n_win"][d])
+                assert np.array_equal(wins[int(a["win_off"][d]):int(a["win_off"][d]) + n], w1[int(b["win_off"][d]):int(b["win_off"][d]) + n])
         r0, t0 = z.pair_align_text(tasks)
         r1, t1 = c.pair_align_text(tasks)
-        assert np.array_equal(r0, r1)
-        n = int(r0["cigar_off"][-1]) + int(r0["n_cigar"][-1])
-        assert np.array_equal(t0[:n], t1[:n])
+        for f in r0.dtype.names:
+            if f != "cigar_off" and not f.startswith("_"):
+                assert np.array_equal(r0[f], r1[f]), f
+        for a, b in zip(r0, r1):
+            assert bytes(t0[int(a["cigar_off"]):int(a["cigar_off"]) + int(a["n_cigar"])]) == bytes(t1[int(b["cigar_off"]):int(b["cigar_off"]) + int(b["n_cigar"])])
         from smartdenovo_b200.api import ZmoError
         with pytest.raises(ZmoError):
             c.index_build()
