@@ -190,19 +190,48 @@ __device__ uint32_t zmo_windows_in_span_w(const DevZPair *rs, int dir, uint32_t 
 	return ret;
 }
 
+/* Sliding cache of the pair's match list for the scalar scan below: the last PS_RING entries the scan has reached, as
+ * (off1 | strand-xor << 31, len1), loaded 128 at a time by all lanes (coalesced 16-byte loads, four in flight per lane)
+ * into shared memory.  The scan then reads its two cursors from shared memory instead of paying one dependent
+ * global-memory round trip per element; an index that has already left the ring is read from global memory. */
+#define PS_RING 512
+struct ZRing { uint32_t *key; uint16_t *len; uint32_t hi; };
+__device__ __forceinline__ void zmo_ring_fill(const DevZPair *rs, uint32_t n, ZRing &G, uint32_t upto, int lane){
+	__syncwarp();
+	while(G.hi <= upto){
+		uint4 v[4];
+		#pragma unroll
+		for(int u = 0; u < 4; u++){ const uint32_t idx = G.hi + u * 32 + lane; if(idx < n) v[u] = *(const uint4*)(rs + idx); }
+		#pragma unroll
+		for(int u = 0; u < 4; u++){
+			const uint32_t idx = G.hi + u * 32 + lane;
+			if(idx < n){ G.key[idx & (PS_RING - 1)] = v[u].x | (((v[u].w ^ (v[u].w >> 8)) & 1u) << 31); G.len[idx & (PS_RING - 1)] = (uint16_t)(v[u].z & 0xFFFFu); }
+		}
+		G.hi += 128;
+	}
+	__syncwarp();
+}
+/* entry idx (< n) as off1 | dirx << 31 and len1; uniform arguments, all 32 lanes call */
+__device__ __forceinline__ void zmo_ring_get(const DevZPair *rs, uint32_t n, ZRing &G, uint32_t idx, int lane, uint32_t &key, uint32_t &len){
+	if(idx >= G.hi) zmo_ring_fill(rs, n, G, idx, lane);
+	if(G.hi > PS_RING && idx < G.hi - PS_RING){ const DevZPair p = rs[idx]; key = p.off1 | ((uint32_t)((p.dir1 ^ p.dir2) & 1) << 31); len = p.len1; }
+	else { key = G.key[idx & (PS_RING - 1)]; len = G.len[idx & (PS_RING - 1)]; }
+}
+
 /* hzm_aln.h:580-656 with every lane running the (cheap) scalar scan redundantly and the span searches done cooperatively */
-__device__ uint32_t zmo_pair_windows_strand_w(const DevZPair *rs, uint32_t n, int dir, WinOut &O, const WinScratch &S, const SeedPar &par, int lane){
-	const uint32_t kwin = par.kwin, kstep = par.kstep, zovl = par.zovl;
+__device__ uint32_t zmo_pair_windows_strand_w(const DevZPair *rs, uint32_t n, int dir, WinOut &O, const WinScratch &S, const SeedPar &par, ZRing &G, int lane){
+	const uint32_t kwin = par.kwin, kstep = par.kstep, zovl = par.zovl, dbit = (uint32_t)dir << 31;
 	uint32_t i, j, a, nw, ol = 0, ol2, lst = 0, wlst = 0, s, t, ret = 0;
-	uint32_t p0_off1, p0_len1, p_off1, p_len1;
-	for(j = 0; j < n; j++) if(!(rs[j].dir1 ^ rs[j].dir2 ^ dir)) break;
+	uint32_t p0_off1, p0_len1, p_off1, p_len1, key, len;
+	G.hi = 0;
+	for(j = 0; j < n; j++){ zmo_ring_get(rs, n, G, j, lane, key, len); if(!((key ^ dbit) >> 31)) break; }
 	if(j == n) return 0;
-	p0_off1 = rs[j].off1; p0_len1 = rs[j].len1;
+	p0_off1 = key & 0x7FFFFFFFu; p0_len1 = len;
 	for(i = j; i <= n; i++){
 		if(i < n){
-			const DevZPair p = rs[i];
-			if(p.dir1 ^ p.dir2 ^ dir) continue;
-			p_off1 = p.off1; p_len1 = p.len1;
+			zmo_ring_get(rs, n, G, i, lane, key, len);
+			if((key ^ dbit) >> 31) continue;
+			p_off1 = key & 0x7FFFFFFFu; p_len1 = len;
 		} else { p_off1 = 0x1FFFFFu; p_len1 = 0x3FFu; }
 		if(p_off1 > p0_off1 + kwin){
 			if(ol >= zovl){
@@ -214,24 +243,26 @@ __device__ uint32_t zmo_pair_windows_strand_w(const DevZPair *rs, uint32_t n, in
 				} else if(i < n){
 					const uint32_t nxt = p0_off1 + kstep;
 					while(p0_off1 < nxt && j < i){
-						const DevZPair p1 = rs[++j];
-						s = p0_off1 > p1.off1? p0_off1 : p1.off1;
-						t = (p0_off1 + p0_len1) < ((uint32_t)p1.off1 + p1.len1)? (p0_off1 + p0_len1) : ((uint32_t)p1.off1 + p1.len1);
+						zmo_ring_get(rs, n, G, ++j, lane, key, len);
+						const uint32_t p1_off1 = key & 0x7FFFFFFFu;
+						s = p0_off1 > p1_off1? p0_off1 : p1_off1;
+						t = (p0_off1 + p0_len1) < (p1_off1 + len)? (p0_off1 + p0_len1) : (p1_off1 + len);
 						ol2 = s < t? t - s : 0;
 						ol = ol + ol2 - p0_len1;
-						p0_off1 = p1.off1; p0_len1 = p1.len1;
+						p0_off1 = p1_off1; p0_len1 = len;
 					}
 				}
 				if(O.overflow) return ret;
 			}
 			if(p_off1 == 0x1FFFFFu) break;
 			while(p_off1 > p0_off1 + kwin){
-				const DevZPair p1 = rs[++j];
-				s = p0_off1 > p1.off1? p0_off1 : p1.off1;
-				t = (p0_off1 + p0_len1) < ((uint32_t)p1.off1 + p1.len1)? (p0_off1 + p0_len1) : ((uint32_t)p1.off1 + p1.len1);
+				zmo_ring_get(rs, n, G, ++j, lane, key, len);
+				const uint32_t p1_off1 = key & 0x7FFFFFFFu;
+				s = p0_off1 > p1_off1? p0_off1 : p1_off1;
+				t = (p0_off1 + p0_len1) < (p1_off1 + len)? (p0_off1 + p0_len1) : (p1_off1 + len);
 				ol2 = s < t? t - s : 0;
 				ol = ol + ol2 - p0_len1;
-				p0_off1 = p1.off1; p0_len1 = p1.len1;
+				p0_off1 = p1_off1; p0_len1 = len;
 			}
 		} else {
 			if(p_off1 >= lst) ol += p_len1;
@@ -244,10 +275,10 @@ __device__ uint32_t zmo_pair_windows_strand_w(const DevZPair *rs, uint32_t n, in
 }
 
 /* strand driver: windows (cooperative) + chain (lane 0); all lanes return the same values */
-__device__ int zmo_pair_seed_strand_w(const DevZPair *rs, uint32_t n, int dir, const SeedPar &par, PairScratch &P, uint32_t *nwin, int *overflow, int lane){
+__device__ int zmo_pair_seed_strand_w(const DevZPair *rs, uint32_t n, int dir, const SeedPar &par, PairScratch &P, ZRing &G, uint32_t *nwin, int *overflow, int lane){
 	WinOut O; O.wins = P.w2; O.nwin = 0; O.capwin = P.capw2; O.anc = P.a2; O.nanc = 0; O.capanc = P.cap; O.overflow = 0; O.stage = P.stage; O.capstage = P.capstage; O.capwin_ovf = P.w2_ovf;
 	int ovl = 0;
-	const uint32_t got = zmo_pair_windows_strand_w(rs, n, dir, O, P.ws, par, lane);
+	const uint32_t got = zmo_pair_windows_strand_w(rs, n, dir, O, P.ws, par, G, lane);
 	__syncwarp();
 	if(got && !O.overflow){
 		if(lane == 0) ovl = zmo_chain_windows(P.w2, O.nwin, par.W, (int*)P.ws.ts);
