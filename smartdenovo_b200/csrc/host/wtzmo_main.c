@@ -324,7 +324,7 @@ typedef struct {
 	zmo_ctx *ctxs[WZ_MAX_CTX]; int n_ctx, depth; u8 ctx_busy[WZ_MAX_CTX];
 	u8 *masked; u32 *rdcovs; u64set_t closed; u32 avg_rdlen; u32 kcut;
 	u64v *rdhits;                       /* per-read candidate carry-over, only with -G > 1 */
-	u64 n_records, aln_cols, n_tasks, n_tasks_used, n_pairs_seeded, n_batches;
+	u64 n_records, aln_cols, n_tasks, n_tasks_used, n_pairs_seeded, n_batches, n_reads_batched, n_reads_late_masked, n_pairs_late_masked;
 	FILE *out; char *obuf; size_t obuf_n, obuf_cap;
 	double t_dev, t_replay, t_write;
 	int batch_reads, batch_pairs;
@@ -831,9 +831,10 @@ static void run_overlap(wz_t *z){
 			cur = q[qh]; qh = (qh + 1) % WZ_MAX_CTX; qn --;
 			if(cur->have_thread){ double tj = now_s(); pthread_join(cur->th, NULL); z->t_dev += now_s() - tj; }
 			t1 = now_s();
+			z->n_reads_batched += cur->reads.n;
 			for(i=0;i<cur->reads.n;i++){
 				bread_t *br = &cur->reads.a[i];
-				if(z->masked[br->rd_id]) continue;       /* checked BEFORE the previous read's masks are merged (wtzmo.c:1315 vs 1322) */
+				if(z->masked[br->rd_id]){ z->n_reads_late_masked ++; z->n_pairs_late_masked += br->cands_raw.n; continue; }       /* checked BEFORE the previous read's masks are merged (wtzmo.c:1315 vs 1322) */
 				flush_read(z, &ro, 0);
 				while(replay_read(z, cur, br, z->rdcovs[br->rd_id], &ro)) demand_wave(z, cur, br, &ro);
 			}
@@ -1085,7 +1086,7 @@ int wz_run(wz_session_t *S, int n_job, int i_job, const char *out_path){
 	free(z->closed.tab); u64set_init(&z->closed);
 	for(k=0;k<S->closed0.n;k++) u64set_add(&z->closed, S->closed0.a[k]);
 	if(z->rdhits){ for(k=0;k<n;k++) vec_free(z->rdhits[k]); free(z->rdhits); z->rdhits = NULL; }
-	z->n_records = z->aln_cols = z->n_tasks = z->n_tasks_used = z->n_pairs_seeded = z->n_batches = z->n_waves = z->n_wave_tasks = 0; z->t_dev = z->t_replay = 0;
+	z->n_records = z->aln_cols = z->n_tasks = z->n_tasks_used = z->n_pairs_seeded = z->n_batches = z->n_reads_batched = z->n_reads_late_masked = z->n_pairs_late_masked = z->n_waves = z->n_wave_tasks = 0; z->t_dev = z->t_replay = 0;
 	z->out = strcmp(out_path, "-")? fopen(out_path, "w") : stdout;
 	if(z->out == NULL){ fprintf(stderr, "wtzmo(b200): cannot open %s\n", out_path); return 1; }
 	if(z->obuf == NULL){ z->obuf_cap = 8u << 20; z->obuf = malloc(z->obuf_cap); }
@@ -1150,7 +1151,7 @@ int main(int argc, char **argv){
 			for(k=0;k<8;k++) fprintf(sf, "%s\"%s\": %.3f", k? ", " : "", nm[k], st[10 + k]);
 			fprintf(sf, "}, \"counters\": {");
 			for(k=0;k<7;k++) fprintf(sf, "%s\"%s\": %.0f", k? ", " : "", cn[k], st[18 + k]);
-			fprintf(sf, "}, \"n_reads\": %.0f, \"n_bases\": %.0f}\n", st[25], st[26]);
+			fprintf(sf, "}, \"n_reads\": %.0f, \"n_bases\": %.0f, \"reads_batched\": %llu, \"reads_late_masked\": %llu, \"cands_late_masked\": %llu}\n", st[25], st[26], (unsigned long long)S->z.n_reads_batched, (unsigned long long)S->z.n_reads_late_masked, (unsigned long long)S->z.n_pairs_late_masked);
 			fclose(sf);
 		}
 	}

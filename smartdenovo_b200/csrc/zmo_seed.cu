@@ -147,14 +147,14 @@ struct SeedOut { DevWin *wins; DevZPair *anc; unsigned long long cap_wins, cap_a
 /* Window finding + chaining, one WARP per pair: the lanes stage the pair's match list in shared memory, lane 0 runs the
  * order-exact serial logic of zmo_seed_core.cuh on it (shared-memory latency instead of global), the lanes copy the
  * kept windows/anchors out.  Lists that do not fit the shared-memory budget run from global memory. */
-#define PS_WARPS 12
+#define PS_WARPS 22
 #define PS_MAXT 512       /* strand entries of one sliding span */
-#define PS_MAXW 128       /* sub-windows of one span */
+#define PS_MAXW 96       /* sub-windows of one span */
 #define PS_STAGE 192      /* anchors of one window */
 #define PS_MAXWIN 64      /* windows of one strand */
 /* per-warp scratch in shared memory (~14.6 KB, 14 warps per SM: the serial lane is latency bound, so occupancy is what
  * buys throughput); larger spans / windows fall back to the global-memory scratch; the read-only match list is read through L1 */
-struct PSSmem { uint64_t ts[PS_MAXT]; uint64_t ak[256]; DevZPair stage[PS_STAGE]; DevWin w2[PS_MAXWIN]; int32_t as[PS_MAXT]; uint32_t wb[PS_MAXW], we[PS_MAXW], wo[PS_MAXW]; uint32_t rkey[PS_RING]; uint16_t rlen[PS_RING]; int bc[8]; };
+struct PSSmem { uint64_t ts[PS_MAXT]; uint64_t ak[256]; DevZPair stage[PS_STAGE]; uint32_t wb[PS_MAXW], we[PS_MAXW], wo[PS_MAXW]; int bc[8]; };     /* as (median scratch) aliases ak: it is dead before the anchors are gathered */
 __global__ void __launch_bounds__(32 * PS_WARPS) k_p_seed(const unsigned long long *cache_off, uint32_t np, DevZPair *cache, const uint8_t *tie, const uint32_t *pc, DevReads R,
 		uint8_t *scratch, size_t per, uint32_t F, SeedPar par, SeedOut O, zmo_pairseed_t *seeds, unsigned long long *work){
 	extern __shared__ __align__(16) uint8_t ps_raw[];
@@ -179,10 +179,9 @@ __global__ void __launch_bounds__(32 * PS_WARPS) k_p_seed(const unsigned long lo
 				uint32_t nwin = 0; int ovf = 0, ovl = 0;
 				{
 					/* cooperative path: scratch in shared memory, all lanes */
-					PairScratch Q = P; Q.ws.ts = M.ts; Q.ws.ak = M.ak; Q.ws.as = M.as; Q.ws.wb = M.wb; Q.ws.we = M.we; Q.ws.wo = M.wo; Q.ws.capt = PS_MAXT; Q.ws.capw = PS_MAXW;
-					Q.w2 = M.w2; Q.capw2 = PS_MAXWIN; Q.w2_ovf = 2; Q.stage = M.stage; Q.capstage = PS_STAGE;
-					ZRing G; G.key = M.rkey; G.len = M.rlen; G.hi = 0;
-					ovl = zmo_pair_seed_strand_w(rs, n, d, par, Q, G, &nwin, &ovf, lane);
+					PairScratch Q = P; Q.ws.ts = M.ts; Q.ws.ak = M.ak; Q.ws.as = (int32_t*)M.ak; Q.ws.wb = M.wb; Q.ws.we = M.we; Q.ws.wo = M.wo; Q.ws.capt = PS_MAXT; Q.ws.capw = PS_MAXW;
+					Q.stage = M.stage; Q.capstage = PS_STAGE;      /* windows go to the pair's global scratch (P.w2) */
+					ovl = zmo_pair_seed_strand_w(rs, n, d, par, Q, &nwin, &ovf, lane);
 				}
 				const bool fast = ovf != 2;
 				if(!fast){
@@ -192,7 +191,7 @@ __global__ void __launch_bounds__(32 * PS_WARPS) k_p_seed(const unsigned long lo
 					ovl = M.bc[0]; nwin = (uint32_t)M.bc[1]; ovf = M.bc[2];
 					__syncwarp();
 				}
-				const DevWin *W2 = fast? M.w2 : P.w2;
+				const DevWin *W2 = P.w2;
 				if(ovf){ if(lane == 0) atomicAdd(O.overflow, 1ULL); break; }
 				S.ovl[d] = ovl;
 				if((uint32_t)ovl >= par.ztot){

@@ -190,46 +190,33 @@ __device__ uint32_t zmo_windows_in_span_w(const DevZPair *rs, int dir, uint32_t 
 	return ret;
 }
 
-/* Sliding cache of the pair's match list for the scalar scan below: the last PS_RING entries the scan has reached, as
- * (off1 | strand-xor << 31, len1), loaded 128 at a time by all lanes (coalesced 16-byte loads, four in flight per lane)
- * into shared memory.  The scan then reads its two cursors from shared memory instead of paying one dependent
- * global-memory round trip per element; an index that has already left the ring is read from global memory. */
-#define PS_RING 512
-struct ZRing { uint32_t *key; uint16_t *len; uint32_t hi; };
-__device__ __forceinline__ void zmo_ring_fill(const DevZPair *rs, uint32_t n, ZRing &G, uint32_t upto, int lane){
-	__syncwarp();
-	while(G.hi <= upto){
-		uint4 v[4];
-		#pragma unroll
-		for(int u = 0; u < 4; u++){ const uint32_t idx = G.hi + u * 32 + lane; if(idx < n) v[u] = *(const uint4*)(rs + idx); }
-		#pragma unroll
-		for(int u = 0; u < 4; u++){
-			const uint32_t idx = G.hi + u * 32 + lane;
-			if(idx < n){ G.key[idx & (PS_RING - 1)] = v[u].x | (((v[u].w ^ (v[u].w >> 8)) & 1u) << 31); G.len[idx & (PS_RING - 1)] = (uint16_t)(v[u].z & 0xFFFFu); }
-		}
-		G.hi += 128;
+/* Register-resident window over the pair's match list for the scalar scan below: every lane keeps one entry of the
+ * current 32-entry chunk as (off1 | strand-xor << 31, len1); the scan reads entry idx by shuffle from lane idx & 31, so
+ * a chunk costs ONE coalesced 16-byte load per lane instead of one dependent global-memory round trip per element.
+ * Two chunks are kept, one per cursor of the two-pointer scan (all arguments are warp-uniform). */
+struct ZChunk { uint32_t base, key, len; };
+__device__ __forceinline__ void zmo_chunk_get(const DevZPair *rs, uint32_t n, ZChunk &C, uint32_t idx, int lane, uint32_t &key, uint32_t &len){
+	if(idx - C.base >= 32u){
+		C.base = idx & ~31u;
+		const uint32_t e = C.base + lane;
+		if(e < n){ const uint4 v = *(const uint4*)(rs + e); C.key = v.x | (((v.w ^ (v.w >> 8)) & 1u) << 31); C.len = v.z & 0xFFFFu; }
 	}
-	__syncwarp();
-}
-/* entry idx (< n) as off1 | dirx << 31 and len1; uniform arguments, all 32 lanes call */
-__device__ __forceinline__ void zmo_ring_get(const DevZPair *rs, uint32_t n, ZRing &G, uint32_t idx, int lane, uint32_t &key, uint32_t &len){
-	if(idx >= G.hi) zmo_ring_fill(rs, n, G, idx, lane);
-	if(G.hi > PS_RING && idx < G.hi - PS_RING){ const DevZPair p = rs[idx]; key = p.off1 | ((uint32_t)((p.dir1 ^ p.dir2) & 1) << 31); len = p.len1; }
-	else { key = G.key[idx & (PS_RING - 1)]; len = G.len[idx & (PS_RING - 1)]; }
+	key = __shfl_sync(0xffffffffu, C.key, idx & 31); len = __shfl_sync(0xffffffffu, C.len, idx & 31);
 }
 
 /* hzm_aln.h:580-656 with every lane running the (cheap) scalar scan redundantly and the span searches done cooperatively */
-__device__ uint32_t zmo_pair_windows_strand_w(const DevZPair *rs, uint32_t n, int dir, WinOut &O, const WinScratch &S, const SeedPar &par, ZRing &G, int lane){
+__device__ uint32_t zmo_pair_windows_strand_w(const DevZPair *rs, uint32_t n, int dir, WinOut &O, const WinScratch &S, const SeedPar &par, int lane){
 	const uint32_t kwin = par.kwin, kstep = par.kstep, zovl = par.zovl, dbit = (uint32_t)dir << 31;
 	uint32_t i, j, a, nw, ol = 0, ol2, lst = 0, wlst = 0, s, t, ret = 0;
 	uint32_t p0_off1, p0_len1, p_off1, p_len1, key, len;
-	G.hi = 0;
-	for(j = 0; j < n; j++){ zmo_ring_get(rs, n, G, j, lane, key, len); if(!((key ^ dbit) >> 31)) break; }
+	ZChunk Ci, Cj; Cj.base = 0xFFFFFF00u; Cj.key = Cj.len = 0;
+	for(j = 0; j < n; j++){ zmo_chunk_get(rs, n, Cj, j, lane, key, len); if(!((key ^ dbit) >> 31)) break; }
 	if(j == n) return 0;
 	p0_off1 = key & 0x7FFFFFFFu; p0_len1 = len;
+	Ci = Cj;
 	for(i = j; i <= n; i++){
 		if(i < n){
-			zmo_ring_get(rs, n, G, i, lane, key, len);
+			zmo_chunk_get(rs, n, Ci, i, lane, key, len);
 			if((key ^ dbit) >> 31) continue;
 			p_off1 = key & 0x7FFFFFFFu; p_len1 = len;
 		} else { p_off1 = 0x1FFFFFu; p_len1 = 0x3FFu; }
@@ -239,11 +226,11 @@ __device__ uint32_t zmo_pair_windows_strand_w(const DevZPair *rs, uint32_t n, in
 					for(a = 0; a < nw; a++){ const int e0 = O.wins[O.nwin + a - nw].end[0] + 20; if((int)wlst < e0) wlst = e0; }
 					ret += nw;
 					p0_off1 = p_off1; p0_len1 = p_len1;
-					ol = p_len1; lst = p_off1 + p_len1; j = i;
+					ol = p_len1; lst = p_off1 + p_len1; j = i; Cj = Ci;
 				} else if(i < n){
 					const uint32_t nxt = p0_off1 + kstep;
 					while(p0_off1 < nxt && j < i){
-						zmo_ring_get(rs, n, G, ++j, lane, key, len);
+						zmo_chunk_get(rs, n, Cj, ++j, lane, key, len);
 						const uint32_t p1_off1 = key & 0x7FFFFFFFu;
 						s = p0_off1 > p1_off1? p0_off1 : p1_off1;
 						t = (p0_off1 + p0_len1) < (p1_off1 + len)? (p0_off1 + p0_len1) : (p1_off1 + len);
@@ -256,7 +243,7 @@ __device__ uint32_t zmo_pair_windows_strand_w(const DevZPair *rs, uint32_t n, in
 			}
 			if(p_off1 == 0x1FFFFFu) break;
 			while(p_off1 > p0_off1 + kwin){
-				zmo_ring_get(rs, n, G, ++j, lane, key, len);
+				zmo_chunk_get(rs, n, Cj, ++j, lane, key, len);
 				const uint32_t p1_off1 = key & 0x7FFFFFFFu;
 				s = p0_off1 > p1_off1? p0_off1 : p1_off1;
 				t = (p0_off1 + p0_len1) < (p1_off1 + len)? (p0_off1 + p0_len1) : (p1_off1 + len);
@@ -275,11 +262,12 @@ __device__ uint32_t zmo_pair_windows_strand_w(const DevZPair *rs, uint32_t n, in
 }
 
 /* strand driver: windows (cooperative) + chain (lane 0); all lanes return the same values */
-__device__ int zmo_pair_seed_strand_w(const DevZPair *rs, uint32_t n, int dir, const SeedPar &par, PairScratch &P, ZRing &G, uint32_t *nwin, int *overflow, int lane){
+__device__ int zmo_pair_seed_strand_w(const DevZPair *rs, uint32_t n, int dir, const SeedPar &par, PairScratch &P, uint32_t *nwin, int *overflow, int lane){
 	WinOut O; O.wins = P.w2; O.nwin = 0; O.capwin = P.capw2; O.anc = P.a2; O.nanc = 0; O.capanc = P.cap; O.overflow = 0; O.stage = P.stage; O.capstage = P.capstage; O.capwin_ovf = P.w2_ovf;
 	int ovl = 0;
-	const uint32_t got = zmo_pair_windows_strand_w(rs, n, dir, O, P.ws, par, G, lane);
+	const uint32_t got = zmo_pair_windows_strand_w(rs, n, dir, O, P.ws, par, lane);
 	__syncwarp();
+	if(got && !O.overflow && O.nwin > P.ws.capt) O.overflow = 2;      /* chain nodes (2 ints per window) live in ts */
 	if(got && !O.overflow){
 		if(lane == 0) ovl = zmo_chain_windows(P.w2, O.nwin, par.W, (int*)P.ws.ts);
 		ovl = __shfl_sync(0xffffffffu, ovl, 0);
