@@ -116,8 +116,8 @@ def main():
     os.makedirs(tmpdir, exist_ok=True)
     metric = "aligned Gbp/sec (all-vs-all overlap)"
     config = {"workload": "%s: %d synthetic %s reads x %d bp, genome %d bp, wtzmo %s; step = one `-P %d -p i` query shard incl. index build" % (
-        args.workload, wl["n"], wl["model"], wl["L"], wl["G"], " ".join(wl["flags"]), wl["shards"] * max(1, world)),
-        "n_reads": wl["n"], "read_len": wl["L"], "genome": wl["G"], "shards": wl["shards"] * max(1, world),
+        args.workload, wl["n"], wl["model"], wl["L"], wl["G"], " ".join(wl["flags"]), max(wl["shards"], world)),
+        "n_reads": wl["n"], "read_len": wl["L"], "genome": wl["G"], "shards": max(wl["shards"], world),
         "l2": "inputs larger than L2 per step (every step streams a different shard: new candidates, match lists and traceback)"}
 
     import __graft_entry__ as ge
@@ -173,7 +173,7 @@ def main():
     S = host.wz_open(len(argv), arr, C.byref(rc))
     if not S:
         raise RuntimeError("wz_open failed rc=%d (no GPU / build missing: there is no CPU fallback)" % rc.value)
-    n_job = wl["shards"] * world
+    n_job = max(wl["shards"], world)      # the shard size (work per GPU per step) does not depend on the number of GPUs: weak scaling
 
     def stats():
         a = (C.c_double * 32)()
@@ -208,8 +208,7 @@ def main():
             rec += st[0]
         gathered = None
         if world > 1:
-            parts = zdist.gather_records(open(out_path, "rb").read(), device="cuda")     # one NCCL all-gather of sizes + one of records
-            gathered = sum(len(p) for p in parts)
+            gathered, _blob = zdist.gather_record_file(out_path, device="cuda")     # one NCCL all-gather of sizes + one of records, to rank 0
         e1.record()
         torch.cuda.synchronize()
         if world > 1:

@@ -16,8 +16,10 @@
 
 int zmo_launch_ext(zmo_ctx *c, int mode, int cls, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells);
 int zmo_launch_glb(zmo_ctx *c, bool wide, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells);
-int zmo_launch_ext_on(zmo_ctx *c, cudaStream_t st, int wk, int mode, int cls, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells);
-int zmo_launch_glb_on(zmo_ctx *c, cudaStream_t st, int wk, bool wide, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells);
+int zmo_launch_ext_on(zmo_ctx *c, cudaStream_t st, int wk, int mode, int cls, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, DPSlab SB, uint32_t *cig, DPRes *d_res, int ctr_cells);
+int zmo_ext_grid(const zmo_ctx *c, int cls, uint32_t n, uint32_t *n_exec);
+int zmo_glb_grid(const zmo_ctx *c, bool wide, uint32_t n, uint32_t *n_exec);
+int zmo_launch_glb_on(zmo_ctx *c, cudaStream_t st, int wk, bool wide, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, DPSlab SB, uint32_t *cig, DPRes *d_res, int ctr_cells);
 
 #define CUB_CALL(c, call_expr) do { size_t _tb = 0; void *_tp = nullptr; { auto d_temp = _tp; size_t &temp_bytes = _tb; CUDA_TRY(call_expr); } \
 	if((c)->cubtmp.reserve(_tb + 256)) return ZMO_ERR_CUDA; { void *d_temp = (c)->cubtmp.p; size_t &temp_bytes = _tb; CUDA_TRY(call_expr); } (c)->launches++; } while(0)
@@ -174,20 +176,21 @@ __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *ite
 
 __global__ void k_job_keys(const DPJob *jobs, uint32_t n, uint32_t *keys, uint32_t *idx){
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if(i < n){ keys[i] = jobs[i].est; idx[i] = i; }
+	if(i < n){ keys[i] = jobs[i].sw32; idx[i] = i; }      /* longest scratch first (~ longest job first): see DPSlab */
 }
 
 /* per-task bookkeeping shared by the plan/finish kernels */
 struct TaskState { int ok; int first, last; int left_job, right_job; int gap0, ngap; int score, tb, te, qb, qe, aln, mat, mis, ins, del; unsigned long long cig_need; };
 /* six job lists: extension classes 0..3 (warp, CTA 64/128/256), gap-fill warp (4) and CTA (5); a job's index in the
  * concatenated array equals its result index */
-struct JobLists { DPJob *list[6]; unsigned long long *cnt[6]; uint32_t res_base[6]; uint32_t cap; unsigned long long *arena_cur, arena_cap, *cig_cur, cig_cap, *overflow; };
+struct JobLists { DPJob *list[6]; unsigned long long *cnt[6]; uint32_t res_base[6]; uint32_t cap; unsigned long long *cig_cur, cig_cap, *overflow; };
 
-__device__ inline int push_job(DPJob *list, unsigned long long *cnt, uint32_t cap, uint32_t res_base, DPJob &J, unsigned long long scratch_words, JobLists &L){
-	const unsigned long long s0 = atomicAdd(L.arena_cur, scratch_words), c0 = atomicAdd(L.cig_cur, (unsigned long long)J.cig_cap);
+__device__ inline int push_job(int cls, JobLists &L, DPJob &J, unsigned long long scratch_words){
+	DPJob *list = L.list[cls]; unsigned long long *cnt = L.cnt[cls]; const uint32_t cap = L.cap, res_base = L.res_base[cls];
+	const unsigned long long c0 = atomicAdd(L.cig_cur, (unsigned long long)J.cig_cap);
 	const unsigned long long k = atomicAdd(cnt, 1ULL);
-	if(s0 + scratch_words > L.arena_cap || c0 + J.cig_cap > L.cig_cap || k >= cap){ atomicAdd(L.overflow, 1ULL); return -1; }
-	J.scratch = s0; J.cig_off = c0; J.out_idx = res_base + (uint32_t)k;
+	if(c0 + J.cig_cap > L.cig_cap || k >= cap){ atomicAdd(L.overflow, 1ULL); return -1; }
+	J.scratch = 0; J.sw32 = (uint32_t)((scratch_words + 31) >> 5); J.cig_off = c0; J.out_idx = res_base + (uint32_t)k;
 	list[k] = J;
 	return (int)J.out_idx;
 }
@@ -216,8 +219,8 @@ __global__ void k_plan(const AlnTask *tasks, uint32_t nt, const zmo_pair_t *pair
 			const int bw = gq < 2 * w + 1? gq : 2 * w + 1;
 			const bool wide = bw > 32 * 7 * 2;
 			int id;
-			if(wide) id = push_job(L.list[5], L.cnt[5], L.cap, L.res_base[5], J, glb_scratch_words<256, 7>(gq, gt, 2048), L);
-			else id = push_job(L.list[4], L.cnt[4], L.cap, L.res_base[4], J, glb_scratch_words<32, 7>(gq, gt, 256), L);
+			if(wide) id = push_job(5, L, J, glb_scratch_words<256, 7>(gq, gt, 2048));
+			else id = push_job(4, L, J, glb_scratch_words<32, 7>(gq, gt, 256));
 			/* gap job ids of one task are not contiguous across classes: remember them in the region record slot */
 			((DevReg*)regs)[T.item_off + k].kept = 2u + (uint32_t)(id < 0? 0 : id);
 			S.ngap++;
@@ -236,7 +239,7 @@ __global__ void k_plan(const AlnTask *tasks, uint32_t nt, const zmo_pair_t *pair
 			const int init = J.init < 0? 0 : J.init;
 			const BandDims d = band_dims(J.qlen, J.tlen, init, J.Wp, A.P);
 			{ const unsigned long long e = ((unsigned long long)d.ql * (unsigned long long)d.ncol) >> 8; J.est = e > 0xFFFFFFFFull? 0xFFFFFFFFu : (uint32_t)e; }
-			{ const int cls = ext_class(d.ncol); S.left_job = push_job(L.list[cls], L.cnt[cls], L.cap, L.res_base[cls], J, ext_scratch_words_cls(d, cls), L); }
+			{ const int cls = ext_class(d.ncol); S.left_job = push_job(cls, L, J, ext_scratch_words_cls(d, cls)); }
 		}
 	}
 	ts[t] = S;
@@ -286,7 +289,7 @@ __global__ void k_plan2(const AlnTask *tasks, uint32_t nt, const zmo_pair_t *pai
 		const int init = J.init < 0? 0 : J.init;
 		const BandDims d = band_dims(J.qlen, J.tlen, init, J.Wp, A.P);
 		{ const unsigned long long e = ((unsigned long long)d.ql * (unsigned long long)d.ncol) >> 8; J.est = e > 0xFFFFFFFFull? 0xFFFFFFFFu : (uint32_t)e; }
-		{ const int cls = ext_class(d.ncol); S.right_job = push_job(L.list[cls], L.cnt[cls], L.cap, L.res_base[cls], J, ext_scratch_words_cls(d, cls), L); }
+		{ const int cls = ext_class(d.ncol); S.right_job = push_job(cls, L, J, ext_scratch_words_cls(d, cls)); }
 	}
 	ts[t] = S;
 }
@@ -373,22 +376,42 @@ __global__ void k_cig_text(zmo_record_t *recs, uint32_t nt, const uint32_t *ops,
 
 /* Run the job lists [first[k], n[k]) of all six executor classes CONCURRENTLY (one auxiliary stream per class, forked from
  * and joined back to the context stream), each work queue ordered longest-job-first to cut the tail. */
-static int run_dp_lists(zmo_ctx *c, const JobLists &L, const uint32_t *n, const uint32_t *first, uint32_t *arena, uint32_t *cig_arena, DPRes *d_res){
-	uint32_t tot = 0, cnt[6], off[6];
-	for(int k = 0; k < 6; k++){ off[k] = first? first[k] : 0; cnt[k] = n[k] - off[k]; tot += cnt[k]; }
-	if(tot == 0) return 0;
-	/* order arrays: keys | idx | sorted keys | sorted idx per class, in s0's tail is not safe -> dedicated buffer h-less: reuse cubtmp after sizing */
-	DevBuf &ob = c->s5;      /* s5 is free until k_finish */
-	if(ob.reserve((size_t)tot * 16 + 256)) return ZMO_ERR_CUDA;
-	uint32_t *base = ob.as<uint32_t>(); uint32_t *order[6]; size_t pos = 0;
+/* One DP phase: the six job lists run concurrently, each on its own stream.  Every list is ordered by scratch size
+ * (descending) and its executors work in private slabs: executor e starts with job e, so its slab is as large as job e's
+ * scratch and the arena holds the prefix sum over the first #executors jobs of every class (DPSlab) -- not the scratch
+ * of every job of the wave.  Nothing in the arena is live between phases, so it may grow here. */
+struct SlabWords { const uint32_t *k; uint32_t m; __host__ __device__ unsigned long long operator()(uint32_t i) const { return i < m? (unsigned long long)k[i] << 5 : 0ull; } };
+static int run_dp_lists(zmo_ctx *c, const JobLists &L, const uint32_t *n, const uint32_t *first, uint32_t *cig_arena, DPRes *d_res){
+	uint32_t tot = 0, cnt[6], off[6], nex[6]; size_t nexs = 0;
 	for(int k = 0; k < 6; k++){
-		order[k] = nullptr;
-		if(cnt[k] < 2){ continue; }
+		off[k] = first? first[k] : 0; cnt[k] = n[k] - off[k]; tot += cnt[k]; nex[k] = 0;
+		if(cnt[k]){ if(k < 4) zmo_ext_grid(c, k, cnt[k], &nex[k]); else zmo_glb_grid(c, k == 5, cnt[k], &nex[k]); }
+		nexs += nex[k] + 2;
+	}
+	if(tot == 0) return 0;
+	DevBuf &ob = c->s5;      /* s5 is free until k_finish: keys | idx | sorted keys | sorted idx per class, then the slab offsets */
+	if(ob.reserve((size_t)tot * 16 + nexs * 8 + 512)) return ZMO_ERR_CUDA;
+	uint32_t *base = ob.as<uint32_t>(); uint32_t *order[6]; size_t pos = 0;
+	unsigned long long *soff[6], *sbase = (unsigned long long*)(((uintptr_t)(base + (size_t)tot * 4) + 63) & ~(uintptr_t)63), htot[6] = {0, 0, 0, 0, 0, 0};
+	for(int k = 0; k < 6; k++){
+		order[k] = nullptr; soff[k] = sbase; sbase += nex[k] + 2;
+		if(cnt[k] == 0) continue;
 		uint32_t *keys = base + pos, *idx = keys + cnt[k], *skeys = idx + cnt[k], *sidx = skeys + cnt[k]; pos += (size_t)cnt[k] * 4;
 		k_job_keys<<<(cnt[k] + 255) / 256, 256, 0, c->stream>>>(L.list[k] + off[k], cnt[k], keys, idx); c->launches++;
-		CUB_CALL(c, cub::DeviceRadixSort::SortPairsDescending(d_temp, temp_bytes, keys, skeys, idx, sidx, (int)cnt[k], 0, 32, c->stream));
-		order[k] = sidx;
+		if(cnt[k] >= 2){
+			CUB_CALL(c, cub::DeviceRadixSort::SortPairsDescending(d_temp, temp_bytes, keys, skeys, idx, sidx, (int)cnt[k], 0, 32, c->stream));
+			order[k] = sidx;
+		} else skeys = keys;
+		SlabWords f; f.k = skeys; f.m = std::min(nex[k], cnt[k]);
+		cub::TransformInputIterator<unsigned long long, SlabWords, cub::CountingInputIterator<uint32_t>> it(cub::CountingInputIterator<uint32_t>(0), f);
+		CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, it, soff[k], (int)nex[k] + 1, c->stream));
+		CUDA_TRY(cudaMemcpyAsync(&htot[k], soff[k] + nex[k], 8, cudaMemcpyDeviceToHost, c->stream));
 	}
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	DPSlab SB[6]; unsigned long long need = 0;
+	for(int k = 0; k < 6; k++){ SB[k].base = need; SB[k].off = soff[k]; need += htot[k] + 32; }
+	if(c->arena.reserve((need + 64) * 4)) return ZMO_ERR_CUDA;
+	uint32_t *arena = c->arena.as<uint32_t>();
 	CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
 	CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
 	for(int k = 0; k < 6; k++){
@@ -396,8 +419,8 @@ static int run_dp_lists(zmo_ctx *c, const JobLists &L, const uint32_t *n, const 
 		CUDA_TRY(cudaStreamWaitEvent(c->aux[k], c->ev_fork, 0));
 		CUDA_TRY(cudaEventRecord(c->ev_a0[k], c->aux[k]));
 		int rc;
-		if(k < 4) rc = zmo_launch_ext_on(c, c->aux[k], CTR_WORKK + k, 1, k, L.list[k] + off[k], order[k], cnt[k], arena, cig_arena, d_res, CTR_CELLS_EXT);
-		else rc = zmo_launch_glb_on(c, c->aux[k], CTR_WORKK + k, k == 5, L.list[k] + off[k], order[k], cnt[k], arena, cig_arena, d_res, CTR_CELLS_GAP);
+		if(k < 4) rc = zmo_launch_ext_on(c, c->aux[k], CTR_WORKK + k, 1, k, L.list[k] + off[k], order[k], cnt[k], arena, SB[k], cig_arena, d_res, CTR_CELLS_EXT);
+		else rc = zmo_launch_glb_on(c, c->aux[k], CTR_WORKK + k, k == 5, L.list[k] + off[k], order[k], cnt[k], arena, SB[k], cig_arena, d_res, CTR_CELLS_GAP);
 		if(rc) return rc;
 		CUDA_TRY(cudaEventRecord(c->ev_a1[k], c->aux[k]));
 		CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_a1[k], 0));
@@ -470,11 +493,10 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 		CUDA_TRY(cudaMemcpyAsync(d_icig, icig.data(), (size_t)nitems * 8, cudaMemcpyHostToDevice, c->stream));
 	}
 	c->counters[5] += (size_t)nt * sizeof(AlnTask) + (size_t)nitems * 16;
-	unsigned long long arena_words = std::max<unsigned long long>(c->arena.cap / 4, slabs_total + (64ull << 20));
 	unsigned long long cig_cap_words = cig_words + (unsigned long long)nt * 4096 + (1ull << 20);
 	for(int attempt = 0; ; attempt++){
-		if(c->arena.reserve(arena_words * 4) || c->s6.reserve(cig_cap_words * 4)) return ZMO_ERR_CUDA;
-		arena_words = c->arena.cap / 4; cig_cap_words = c->s6.cap / 4;
+		if(c->arena.reserve((slabs_total + 64) * 4) || c->s6.reserve(cig_cap_words * 4)) return ZMO_ERR_CUDA;
+		cig_cap_words = c->s6.cap / 4;
 		uint32_t *arena = c->arena.as<uint32_t>(), *cig_arena = c->s6.as<uint32_t>();
 		if(nitems){
 			StageTimer tm(c, ST_WINALN);
@@ -487,36 +509,35 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 		/* plan: left extensions + gaps */
 		JobLists L; L.cap = jcap;
 		for(int k = 0; k < 6; k++){ L.list[k] = d_jobs + (size_t)k * jcap; L.cnt[k] = ctr + CTR_JOBS + k; L.res_base[k] = (uint32_t)k * jcap; }
-		L.arena_cur = ctr + CTR_ARENA; L.arena_cap = arena_words; L.cig_cur = ctr + CTR_CIG; L.cig_cap = cig_cap_words; L.overflow = ctr + CTR_OVERFLOW;
-		unsigned long long init_ctr[2] = {slabs_total, cig_words};
+		L.cig_cur = ctr + CTR_CIG; L.cig_cap = cig_cap_words; L.overflow = ctr + CTR_OVERFLOW;
+		unsigned long long init_ctr[2] = {0, cig_words};
 		CUDA_TRY(cudaMemsetAsync(ctr + CTR_JOBS, 0, 6 * 8, c->stream));
 		CUDA_TRY(cudaMemsetAsync(ctr + CTR_OVERFLOW, 0, 8, c->stream));
-		CUDA_TRY(cudaMemcpyAsync(ctr + CTR_ARENA, &init_ctr[0], 8, cudaMemcpyHostToDevice, c->stream));
 		CUDA_TRY(cudaMemcpyAsync(ctr + CTR_CIG, &init_ctr[1], 8, cudaMemcpyHostToDevice, c->stream));
 		k_plan<<<(nt + 63) / 64, 64, 0, c->stream>>>(d_tasks, nt, SL.pairs.as<zmo_pair_t>(), d_regs, R, A, L, d_ts, 0); c->launches++;
 		unsigned long long h[CTR_TOTAL];
 		CUDA_TRY(cudaMemcpyAsync(h, ctr, CTR_TOTAL * 8, cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
 		if(h[CTR_OVERFLOW]){
-			if(attempt >= 6) return zmo_set_err(ZMO_ERR_CAPACITY, "DP arena overflow after %d attempts", attempt);
-			arena_words = std::max(arena_words * 2, h[CTR_ARENA] + (64ull << 20)); cig_cap_words = std::max(cig_cap_words * 2, h[CTR_CIG] + (1ull << 20));
+			if(attempt >= 6) return zmo_set_err(ZMO_ERR_CAPACITY, "cigar arena overflow after %d attempts", attempt);
+			cig_cap_words = std::max(cig_cap_words * 2, h[CTR_CIG] + (1ull << 20));
 			continue;
 		}
 		uint32_t n1[6]; for(int k = 0; k < 6; k++) n1[k] = (uint32_t)h[CTR_JOBS + k];
-		if(int rc = run_dp_lists(c, L, n1, nullptr, arena, cig_arena, d_res)) return rc;
+		if(int rc = run_dp_lists(c, L, n1, nullptr, cig_arena, d_res)) return rc;      /* the window slabs are dead by now: the DP slabs reuse the arena from 0 */
 		/* plan2: right extensions appended to the same extension lists */
 		k_plan2<<<(nt + 63) / 64, 64, 0, c->stream>>>(d_tasks, nt, SL.pairs.as<zmo_pair_t>(), d_regs, d_res, R, A, L, d_ts); c->launches++;
 		CUDA_TRY(cudaMemcpyAsync(h, ctr, CTR_TOTAL * 8, cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
 		if(h[CTR_OVERFLOW]){
-			if(attempt >= 6) return zmo_set_err(ZMO_ERR_CAPACITY, "DP arena overflow after %d attempts", attempt);
-			arena_words = std::max(arena_words * 2, h[CTR_ARENA] + (64ull << 20)); cig_cap_words = std::max(cig_cap_words * 2, h[CTR_CIG] + (1ull << 20));
+			if(attempt >= 6) return zmo_set_err(ZMO_ERR_CAPACITY, "cigar arena overflow after %d attempts", attempt);
+			cig_cap_words = std::max(cig_cap_words * 2, h[CTR_CIG] + (1ull << 20));
 			continue;
 		}
 		{
 			uint32_t n2[6]; for(int k = 0; k < 6; k++) n2[k] = (uint32_t)h[CTR_JOBS + k];
 			n2[4] = n1[4]; n2[5] = n1[5];      /* no new gap jobs in the second phase */
-			if(int rc = run_dp_lists(c, L, n2, n1, arena, cig_arena, d_res)) return rc;
+			if(int rc = run_dp_lists(c, L, n2, n1, cig_arena, d_res)) return rc;
 		}
 		/* final sizes, offsets, stitched CIGARs */
 		unsigned long long *d_need = c->s7.as<unsigned long long>(), *d_ooff = d_need + nt + 1;

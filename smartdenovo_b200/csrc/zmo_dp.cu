@@ -19,7 +19,7 @@
  * bands beyond that (chunked sweep with rows in global memory). */
 template<int NT, int C, int MODE>
 __global__ void __launch_bounds__(NT, (NT == 256? 2 : (NT == 128? (C > 7? 3 : 5) : 8))) k_ext_cta(const DPJob *jobs, const uint32_t *order, uint32_t njobs, DevReads R, DPPar P,
-		uint32_t *arena, uint32_t *cig_arena, DPRes *res, unsigned long long *ctr, int ctr_work, int ctr_cells){
+		uint32_t *arena, DPSlab SB, uint32_t *cig_arena, DPRes *res, unsigned long long *ctr, int ctr_work, int ctr_cells){
 	constexpr int SEQW = (NT == 256 || C > 7)? 4096 : 2048;
 	__shared__ uint32_t s_seq[SEQW];
 	__shared__ int s_red[2 * (NT / 32)];
@@ -28,13 +28,14 @@ __global__ void __launch_bounds__(NT, (NT == 256? 2 : (NT == 128? (C > 7? 3 : 5)
 	__shared__ uint32_t s_job;
 	ExecSmem<NT> X; X.carve(nullptr, 0, s_seq, SEQW, s_red, s_redk, s_misc);
 	const int tid = threadIdx.x;
-	while(1){
-		if(tid == 0) s_job = (uint32_t)atomicAdd(ctr + ctr_work, 1ULL);
+	uint32_t *slab = SB.off? arena + SB.base + SB.off[blockIdx.x] : nullptr;
+	for(bool first = true; ; first = false){
+		if(tid == 0) s_job = first? blockIdx.x : gridDim.x + (uint32_t)atomicAdd(ctr + ctr_work, 1ULL);
 		__syncthreads();
 		const uint32_t jn = s_job;
 		__syncthreads();
 		if(jn >= njobs) break;
-		run_ext_job<NT, C, MODE>(jobs[order? order[jn] : jn], R, P, X, arena, cig_arena, res, ctr + ctr_cells, tid);
+		run_ext_job<NT, C, MODE>(jobs[order? order[jn] : jn], R, P, X, arena, slab, cig_arena, res, ctr + ctr_cells, tid);
 		__syncthreads();
 	}
 }
@@ -42,41 +43,43 @@ __global__ void __launch_bounds__(NT, (NT == 256? 2 : (NT == 128? (C > 7? 3 : 5)
 /* warp-per-job extension kernel (bands up to 211 columns) */
 template<int MODE>
 __global__ void __launch_bounds__(32 * WRP_PER_CTA) k_ext_warp(const DPJob *jobs, const uint32_t *order, uint32_t njobs, DevReads R, DPPar P,
-		uint32_t *arena, uint32_t *cig_arena, DPRes *res, unsigned long long *ctr, int ctr_work, int ctr_cells){
+		uint32_t *arena, DPSlab SB, uint32_t *cig_arena, DPRes *res, unsigned long long *ctr, int ctr_work, int ctr_cells){
 	__shared__ uint32_t s_seq[WRP_PER_CTA][WRP_SEQW];
 	__shared__ int s_misc[WRP_PER_CTA][16];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	ExecSmem<32> X; X.carve(nullptr, 0, s_seq[warp], WRP_SEQW, nullptr, nullptr, s_misc[warp]);
-	while(1){
-		uint32_t jn = 0;
-		if(lane == 0) jn = (uint32_t)atomicAdd(ctr + ctr_work, 1ULL);
-		jn = __shfl_sync(0xffffffffu, jn, 0);
+	const uint32_t ex = blockIdx.x * WRP_PER_CTA + warp;
+	uint32_t *slab = SB.off? arena + SB.base + SB.off[ex] : nullptr;
+	for(bool first = true; ; first = false){
+		uint32_t jn = ex;
+		if(!first){ if(lane == 0) jn = gridDim.x * WRP_PER_CTA + (uint32_t)atomicAdd(ctr + ctr_work, 1ULL); jn = __shfl_sync(0xffffffffu, jn, 0); }
 		if(jn >= njobs) break;
-		run_ext_job<32, WRP_C, MODE>(jobs[order? order[jn] : jn], R, P, X, arena, cig_arena, res, ctr + ctr_cells, lane);
+		run_ext_job<32, WRP_C, MODE>(jobs[order? order[jn] : jn], R, P, X, arena, slab, cig_arena, res, ctr + ctr_cells, lane);
 		__syncwarp();
 	}
 }
 
 __global__ void __launch_bounds__(32 * WRP_PER_CTA) k_glb_warp(const DPJob *jobs, const uint32_t *order, uint32_t njobs, DevReads R, DPPar P,
-		uint32_t *arena, uint32_t *cig_arena, DPRes *res, unsigned long long *ctr, int ctr_work, int ctr_cells){
+		uint32_t *arena, DPSlab SB, uint32_t *cig_arena, DPRes *res, unsigned long long *ctr, int ctr_work, int ctr_cells){
 	__shared__ int s_h[WRP_PER_CTA][3 * WRP_CAP];
 	__shared__ uint32_t s_seq[WRP_PER_CTA][WRP_SEQW];
 	__shared__ int s_misc[WRP_PER_CTA][16];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	ExecSmem<32> X; X.carve(s_h[warp], WRP_CAP, s_seq[warp], WRP_SEQW, nullptr, nullptr, s_misc[warp]);
-	while(1){
-		uint32_t jn = 0;
-		if(lane == 0) jn = (uint32_t)atomicAdd(ctr + ctr_work, 1ULL);
-		jn = __shfl_sync(0xffffffffu, jn, 0);
+	const uint32_t ex = blockIdx.x * WRP_PER_CTA + warp;
+	uint32_t *slab = SB.off? arena + SB.base + SB.off[ex] : nullptr;
+	for(bool first = true; ; first = false){
+		uint32_t jn = ex;
+		if(!first){ if(lane == 0) jn = gridDim.x * WRP_PER_CTA + (uint32_t)atomicAdd(ctr + ctr_work, 1ULL); jn = __shfl_sync(0xffffffffu, jn, 0); }
 		if(jn >= njobs) break;
-		run_glb_job<32, WRP_C>(jobs[order? order[jn] : jn], R, P, X, arena, cig_arena, res, ctr + ctr_cells, lane);
+		run_glb_job<32, WRP_C>(jobs[order? order[jn] : jn], R, P, X, arena, slab, cig_arena, res, ctr + ctr_cells, lane);
 		__syncwarp();
 	}
 }
 
 /* CTA-per-job global kernel for gaps whose band does not fit a warp executor comfortably */
 __global__ void __launch_bounds__(EXT_NT) k_glb_cta(const DPJob *jobs, const uint32_t *order, uint32_t njobs, DevReads R, DPPar P,
-		uint32_t *arena, uint32_t *cig_arena, DPRes *res, unsigned long long *ctr, int ctr_work, int ctr_cells){
+		uint32_t *arena, DPSlab SB, uint32_t *cig_arena, DPRes *res, unsigned long long *ctr, int ctr_work, int ctr_cells){
 	__shared__ int s_h[3 * EXT_CAP];
 	__shared__ uint32_t s_seq[EXT_SEQW];
 	__shared__ int s_red[2 * (EXT_NT / 32)];
@@ -85,13 +88,14 @@ __global__ void __launch_bounds__(EXT_NT) k_glb_cta(const DPJob *jobs, const uin
 	__shared__ uint32_t s_job;
 	ExecSmem<EXT_NT> X; X.carve(s_h, EXT_CAP, s_seq, EXT_SEQW, s_red, s_redk, s_misc);
 	const int tid = threadIdx.x;
-	while(1){
-		if(tid == 0) s_job = (uint32_t)atomicAdd(ctr + ctr_work, 1ULL);
+	uint32_t *slab = SB.off? arena + SB.base + SB.off[blockIdx.x] : nullptr;
+	for(bool first = true; ; first = false){
+		if(tid == 0) s_job = first? blockIdx.x : gridDim.x + (uint32_t)atomicAdd(ctr + ctr_work, 1ULL);
 		__syncthreads();
 		const uint32_t jn = s_job;
 		__syncthreads();
 		if(jn >= njobs) break;
-		run_glb_job<EXT_NT, EXT_C>(jobs[order? order[jn] : jn], R, P, X, arena, cig_arena, res, ctr + ctr_cells, tid);
+		run_glb_job<EXT_NT, EXT_C>(jobs[order? order[jn] : jn], R, P, X, arena, slab, cig_arena, res, ctr + ctr_cells, tid);
 		__syncthreads();
 	}
 }
@@ -99,48 +103,59 @@ __global__ void __launch_bounds__(EXT_NT) k_glb_cta(const DPJob *jobs, const uin
 static DPPar dp_par(const zmo_ctx *c){ DPPar P; P.M = c->par.M; P.X = c->par.X; P.I = c->par.O; P.D = c->par.O; P.E = c->par.E; P.T = c->par.T; return P; }
 
 /* ---- launch helpers used by the API and the pipeline --------------------------------------- */
-template<int NT, int C> static void launch_ext_cta(cudaStream_t st, int wk, int mode, int grid, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, DevReads R, DPPar P, uint32_t *arena, uint32_t *cig, DPRes *d_res, unsigned long long *ctr, int ctr_cells){
-	if(mode == 1) k_ext_cta<NT, C, 1><<<grid, NT, 0, st>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, wk, ctr_cells);
-	else k_ext_cta<NT, C, 0><<<grid, NT, 0, st>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, wk, ctr_cells);
+template<int NT, int C> static void launch_ext_cta(cudaStream_t st, int wk, int mode, int grid, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, DevReads R, DPPar P, uint32_t *arena, DPSlab SB, uint32_t *cig, DPRes *d_res, unsigned long long *ctr, int ctr_cells){
+	if(mode == 1) k_ext_cta<NT, C, 1><<<grid, NT, 0, st>>>(d_jobs, d_order, n, R, P, arena, SB, cig, d_res, ctr, wk, ctr_cells);
+	else k_ext_cta<NT, C, 0><<<grid, NT, 0, st>>>(d_jobs, d_order, n, R, P, arena, SB, cig, d_res, ctr, wk, ctr_cells);
+}
+/* grid (CTAs) and executor count of a DP launch: the pipeline sizes the executor slabs with the same numbers */
+int zmo_ext_grid(const zmo_ctx *c, int cls, uint32_t n, uint32_t *n_exec){
+	int grid;
+	if(cls == 0){ grid = (int)std::min<uint64_t>((n + WRP_PER_CTA - 1) / WRP_PER_CTA, (uint64_t)c->n_sm * 8); *n_exec = (uint32_t)grid * WRP_PER_CTA; }
+	else { grid = (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * (cls == 1? 8 : (cls == 2? 5 : (CL3_NT == 256? 2 : 3)))); *n_exec = (uint32_t)grid; }
+	return grid;
+}
+int zmo_glb_grid(const zmo_ctx *c, bool wide, uint32_t n, uint32_t *n_exec){
+	int grid;
+	if(wide){ grid = (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 4); *n_exec = (uint32_t)grid; }
+	else { grid = (int)std::min<uint64_t>((n + WRP_PER_CTA - 1) / WRP_PER_CTA, (uint64_t)c->n_sm * 8); *n_exec = (uint32_t)grid * WRP_PER_CTA; }
+	return grid;
 }
 /* cls: 0 = warp executor, 1/2/3 = CTA executors (see ext_class) */
-int zmo_launch_ext_on(zmo_ctx *c, cudaStream_t st, int wk, int mode, int cls, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells){
+int zmo_launch_ext_on(zmo_ctx *c, cudaStream_t st, int wk, int mode, int cls, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, DPSlab SB, uint32_t *cig, DPRes *d_res, int ctr_cells){
 	if(n == 0) return 0;
 	unsigned long long *ctr = c->d_ctr.as<unsigned long long>();
 	CUDA_TRY(cudaMemsetAsync(ctr + wk, 0, 8, st));
 	DevReads R = dev_reads(c); DPPar P = dp_par(c);
+	uint32_t nex = 0; const int grid = zmo_ext_grid(c, cls, n, &nex);
 	if(cls == 0){
-		int grid = (int)std::min<uint64_t>((n + WRP_PER_CTA - 1) / WRP_PER_CTA, (uint64_t)c->n_sm * 8);
-		if(mode == 1) k_ext_warp<1><<<grid, 32 * WRP_PER_CTA, 0, st>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, wk, ctr_cells);
-		else k_ext_warp<0><<<grid, 32 * WRP_PER_CTA, 0, st>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, wk, ctr_cells);
-	} else if(cls == 1) launch_ext_cta<64, 7>(st, wk, mode, (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 8), d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, ctr_cells);
-	else if(cls == 2) launch_ext_cta<128, 7>(st, wk, mode, (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 5), d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, ctr_cells);
-	else launch_ext_cta<CL3_NT, CL3_C>(st, wk, mode, (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * (CL3_NT == 256? 2 : 3)), d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, ctr_cells);
+		if(mode == 1) k_ext_warp<1><<<grid, 32 * WRP_PER_CTA, 0, st>>>(d_jobs, d_order, n, R, P, arena, SB, cig, d_res, ctr, wk, ctr_cells);
+		else k_ext_warp<0><<<grid, 32 * WRP_PER_CTA, 0, st>>>(d_jobs, d_order, n, R, P, arena, SB, cig, d_res, ctr, wk, ctr_cells);
+	} else if(cls == 1) launch_ext_cta<64, 7>(st, wk, mode, grid, d_jobs, d_order, n, R, P, arena, SB, cig, d_res, ctr, ctr_cells);
+	else if(cls == 2) launch_ext_cta<128, 7>(st, wk, mode, grid, d_jobs, d_order, n, R, P, arena, SB, cig, d_res, ctr, ctr_cells);
+	else launch_ext_cta<CL3_NT, CL3_C>(st, wk, mode, grid, d_jobs, d_order, n, R, P, arena, SB, cig, d_res, ctr, ctr_cells);
 	c->launches++;
 	CUDA_TRY(cudaGetLastError());
 	return 0;
 }
 int zmo_launch_ext(zmo_ctx *c, int mode, int cls, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells){
-	return zmo_launch_ext_on(c, c->stream, CTR_WORK, mode, cls, d_jobs, d_order, n, arena, cig, d_res, ctr_cells);
+	DPSlab SB; SB.base = 0; SB.off = nullptr;
+	return zmo_launch_ext_on(c, c->stream, CTR_WORK, mode, cls, d_jobs, d_order, n, arena, SB, cig, d_res, ctr_cells);
 }
-int zmo_launch_glb_on(zmo_ctx *c, cudaStream_t st, int wk, bool wide, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells){
+int zmo_launch_glb_on(zmo_ctx *c, cudaStream_t st, int wk, bool wide, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, DPSlab SB, uint32_t *cig, DPRes *d_res, int ctr_cells){
 	if(n == 0) return 0;
 	unsigned long long *ctr = c->d_ctr.as<unsigned long long>();
 	CUDA_TRY(cudaMemsetAsync(ctr + wk, 0, 8, st));
 	DevReads R = dev_reads(c); DPPar P = dp_par(c);
-	if(wide){
-		int grid = (int)std::min<uint64_t>(n, (uint64_t)c->n_sm * 4);
-		k_glb_cta<<<grid, EXT_NT, 0, st>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, wk, ctr_cells);
-	} else {
-		int grid = (int)std::min<uint64_t>((n + WRP_PER_CTA - 1) / WRP_PER_CTA, (uint64_t)c->n_sm * 8);
-		k_glb_warp<<<grid, 32 * WRP_PER_CTA, 0, st>>>(d_jobs, d_order, n, R, P, arena, cig, d_res, ctr, wk, ctr_cells);
-	}
+	uint32_t nex = 0; const int grid = zmo_glb_grid(c, wide, n, &nex);
+	if(wide) k_glb_cta<<<grid, EXT_NT, 0, st>>>(d_jobs, d_order, n, R, P, arena, SB, cig, d_res, ctr, wk, ctr_cells);
+	else k_glb_warp<<<grid, 32 * WRP_PER_CTA, 0, st>>>(d_jobs, d_order, n, R, P, arena, SB, cig, d_res, ctr, wk, ctr_cells);
 	c->launches++;
 	CUDA_TRY(cudaGetLastError());
 	return 0;
 }
 int zmo_launch_glb(zmo_ctx *c, bool wide, const DPJob *d_jobs, const uint32_t *d_order, uint32_t n, uint32_t *arena, uint32_t *cig, DPRes *d_res, int ctr_cells){
-	return zmo_launch_glb_on(c, c->stream, CTR_WORK, wide, d_jobs, d_order, n, arena, cig, d_res, ctr_cells);
+	DPSlab SB; SB.base = 0; SB.off = nullptr;
+	return zmo_launch_glb_on(c, c->stream, CTR_WORK, wide, d_jobs, d_order, n, arena, SB, cig, d_res, ctr_cells);
 }
 
 /* ---- stand-alone operators ------------------------------------------------------------------ */

@@ -13,12 +13,16 @@ struct DPJob {
 	int t_start, t_step, t_comp, tlen;
 	int init, Wp;                 /* extension: init score and W as the reference passes it; global: Wp = first band w */
 	int Wmax;                     /* global only: -W cap for band doubling (hzm_aln.h:1411) */
-	unsigned long long scratch;   /* word offset of this job's scratch in the arena */
+	unsigned long long scratch;   /* word offset of this job's scratch in the arena (stand-alone operators; the pipeline uses executor slabs) */
 	unsigned long long cig_off;   /* word offset in the cigar arena */
 	uint32_t cig_cap;
 	uint32_t out_idx;
-	uint32_t est, pad;            /* estimated DP cells / 256 (saturating): longest-job-first ordering of the work queue */
+	uint32_t est, sw32;           /* estimated DP cells / 256 (saturating); scratch words / 32 (rounded up): the work-queue order and the slab sizes */
 };
+/* executor-private scratch of a DP kernel launch.  Jobs are handed out longest-scratch-first: executor e starts with job e
+ * and then pulls from the shared counter, so everything it will ever run fits the scratch of job e.  off[e] (words, relative
+ * to base) is the prefix sum of those sizes; off == nullptr: per-job scratch at J.scratch (stand-alone operators). */
+struct DPSlab { unsigned long long base; const unsigned long long *off; };
 struct DPRes { int score, qe, te, mat, mis, ins, del, ncig, w_used, pad; };
 
 /* scratch words needed by an extension job (host + device agree through this one function) */
@@ -68,13 +72,13 @@ template<int NT> struct ExecSmem {
 };
 
 template<int NT, int C, int MODE>
-__device__ void run_ext_job(const DPJob &J, const DevReads &R, const DPPar &P, ExecSmem<NT> &X, uint32_t *arena, uint32_t *cig_arena,
+__device__ void run_ext_job(const DPJob &J, const DevReads &R, const DPPar &P, ExecSmem<NT> &X, uint32_t *arena, uint32_t *slab, uint32_t *cig_arena,
 		DPRes *res, unsigned long long *cells, int tid){
 	int init = J.init < 0? 0 : J.init;
 	DPOut o; o.score = init; o.qe = o.te = o.mat = o.mis = o.ins = o.del = o.ncig = 0;
 	if(J.qlen > 0 && J.tlen > 0){
 		BandDims d = band_dims(J.qlen, J.tlen, init, J.Wp, P);
-		uint32_t *scr = arena + J.scratch;
+		uint32_t *scr = slab? slab : arena + J.scratch;      /* executor-private slab (pipeline) or per-job scratch (stand-alone operators) */
 		const bool reg = d.ncol <= RegCap<NT, C>::ncol;
 		const int rw = reg? NT * RegCap<NT, C>::WPT : band_row_words<NT, 7>(d.ncol);
 		uint32_t *z = scr; scr += (size_t)d.ql * rw;
@@ -101,10 +105,10 @@ __device__ void run_ext_job(const DPJob &J, const DevReads &R, const DPPar &P, E
 
 /* gap filling with the reference's band-doubling retry (hzm_aln.h:1400-1418) */
 template<int NT, int C>
-__device__ void run_glb_job(const DPJob &J, const DevReads &R, const DPPar &P, ExecSmem<NT> &X, uint32_t *arena, uint32_t *cig_arena,
+__device__ void run_glb_job(const DPJob &J, const DevReads &R, const DPPar &P, ExecSmem<NT> &X, uint32_t *arena, uint32_t *slab, uint32_t *cig_arena,
 		DPRes *res, unsigned long long *cells, int tid){
 	const int qlen = J.qlen, tlen = J.tlen;
-	uint32_t *scr = arena + J.scratch;
+	uint32_t *scr = slab? slab : arena + J.scratch;
 	const int rwmax = band_row_words<NT, C>(qlen > 0? qlen : 0);
 	uint32_t *z = scr; scr += (size_t)(tlen > 0? tlen : 0) * rwmax;
 	const int qw = (qlen + 15) >> 4, tw = (tlen + 15) >> 4;

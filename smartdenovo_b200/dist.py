@@ -3,6 +3,8 @@
 so there is NO collective during compute.  The only exchange is the final gather of the variable-length record
 text to rank 0 (one all-gather of sizes + one all-gather of padded byte tensors), equivalent to `cat part*.ovl`.
 Works with any torch.distributed backend (NCCL on GPUs, gloo in the CPU tests)."""
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -27,6 +29,41 @@ def gather_records(payload: bytes, device="cpu"):
     outs = [torch.empty(mx, dtype=torch.uint8, device=device) for _ in range(world)]
     dist.all_gather(outs, buf)
     return [bytes(o[: int(s.item())].cpu().numpy().tobytes()) for o, s in zip(outs, sizes)]
+
+
+def gather_record_file(path, device="cpu", dst_rank=0):
+    """Gather the record files of all ranks on `dst_rank` (`cat part*.ovl` in rank order) with ONE all-gather of sizes and
+    ONE all-gather of the padded byte buffers.  The file is read straight into a page-locked staging tensor, the
+    gathered buffer is copied back to the host on dst_rank only.  Returns (total bytes over all ranks, bytes object on
+    dst_rank or None elsewhere)."""
+    n = os.path.getsize(path)
+    on_gpu = str(device).startswith("cuda")
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return n, open(path, "rb").read()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    sizes = torch.zeros(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(sizes, torch.tensor([n], dtype=torch.int64, device=device))
+    sizes = [int(x) for x in sizes.cpu()]
+    mx = max(1, max(sizes))
+    stage = torch.empty(mx, dtype=torch.uint8, pin_memory=on_gpu)
+    if n:
+        with open(path, "rb", buffering=0) as f:
+            mv = memoryview(stage.numpy())[:n]
+            got = 0
+            while got < n:
+                r = f.readinto(mv[got:])
+                if not r:
+                    raise IOError("short read of %s" % path)
+                got += r
+    buf = stage.to(device, non_blocking=True)
+    out = torch.empty(world * mx, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(out, buf)
+    if rank != dst_rank:
+        return sum(sizes), None
+    host = torch.empty(world * mx, dtype=torch.uint8, pin_memory=on_gpu)
+    host.copy_(out)
+    a = host.numpy()
+    return sum(sizes), b"".join(a[r * mx: r * mx + sizes[r]].tobytes() for r in range(world))
 
 
 def max_over_ranks(values, device="cpu"):
