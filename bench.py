@@ -222,6 +222,8 @@ def main():
 
     for w in range(args.warmup):
         step(w, False)
+    if world > 1:
+        zdist.gather_record_file(out_path, device="cuda")      # warm-up of the gather path too (NCCL channels, pinned staging)
     sampler = ClockSampler(local_rank)
     sampler.start()
     r_val = timed(args.steps, args.warmup, False)

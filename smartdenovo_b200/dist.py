@@ -34,12 +34,14 @@ def gather_records(payload: bytes, device="cpu"):
 def gather_record_file(path, device="cpu", dst_rank=0):
     """Gather the record files of all ranks on `dst_rank` (`cat part*.ovl` in rank order) with ONE all-gather of sizes and
     ONE all-gather of the padded byte buffers.  The file is read straight into a page-locked staging tensor, the
-    gathered buffer is copied back to the host on dst_rank only.  Returns (total bytes over all ranks, bytes object on
-    dst_rank or None elsewhere)."""
+    gathered buffer is copied back to the host on dst_rank only.  Returns (total bytes over all ranks, list of per-rank
+    uint8 numpy views of the host copy on dst_rank or None elsewhere); the staging tensors come from torch's caching
+    pinned allocator, so repeated gathers do not pay cudaHostAlloc again."""
     n = os.path.getsize(path)
     on_gpu = str(device).startswith("cuda")
     if not dist.is_initialized() or dist.get_world_size() == 1:
-        return n, open(path, "rb").read()
+        import numpy as np
+        return n, [np.fromfile(path, dtype=np.uint8)]
     world, rank = dist.get_world_size(), dist.get_rank()
     sizes = torch.zeros(world, dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(sizes, torch.tensor([n], dtype=torch.int64, device=device))
@@ -63,7 +65,7 @@ def gather_record_file(path, device="cpu", dst_rank=0):
     host = torch.empty(world * mx, dtype=torch.uint8, pin_memory=on_gpu)
     host.copy_(out)
     a = host.numpy()
-    return sum(sizes), b"".join(a[r * mx: r * mx + sizes[r]].tobytes() for r in range(world))
+    return sum(sizes), [a[r * mx: r * mx + sizes[r]] for r in range(world)]
 
 
 def max_over_ranks(values, device="cpu"):

@@ -26,7 +26,7 @@ mx = zd.max_over_ranks([float(rank + 1), 5.0])
 sm = zd.sum_over_ranks([float(rank + 1)])
 assert mx == [float(world), 5.0] and sm == [world * (world + 1) / 2.0]
 tot, blob = zd.gather_record_file(out)
-assert tot == sum(len(x) for x in parts) and (blob == b"".join(parts) if rank == 0 else blob is None)
+assert tot == sum(len(x) for x in parts) and (b"".join(v.tobytes() for v in blob) == b"".join(parts) if rank == 0 else blob is None)
 if rank == 0:
     open(os.path.join(outdir, "gathered.ovl"), "wb").write(b"".join(parts))
 # an empty payload on one rank must not break the gather
