@@ -132,8 +132,11 @@ __device__ __forceinline__ void reg_sweep(const BandSmem &S, const uint32_t *row
 	int best = init, bi = -1, bj = -1, gbest = 0, gi = -1, gj = -1;
 	int c = 0;
 	unsigned long long cells = 0;
-	for(int i = 0; i < nrow; i++){
+	uint32_t rwd = 0;                /* sixteen row bases, reloaded every 16 rows (keeps the shared-memory load off the per-row critical path) */
+	uint32_t *zp = z + (size_t)tid * WPT;
+	for(int i = 0; i < nrow; i++, zp += NT * WPT){
 		int jb, je;
+		if((i & 15) == 0) rwd = rowpk[i >> 4];
 		if(KIND == 1){ jb = c - W; je = c + W + 1; } else { jb = i - W; je = i + W + 1; }
 		if(jb < 0) jb = 0;
 		if(je > tl) je = tl;
@@ -154,7 +157,7 @@ __device__ __forceinline__ void reg_sweep(const BandSmem &S, const uint32_t *row
 		if(j0 == 0) left = i == 0? init : init + P.I + E * i;
 		const bool act = j0 < je;
 		const int lo = jb - j0, hi = je - j0;
-		const unsigned long long x = xw ^ (0x5555555555555555ull * (unsigned long long)pk_base(rowpk, i));
+		const unsigned long long x = xw ^ (0x5555555555555555ull * (unsigned long long)((rwd >> (((~i) & 15) << 1)) & 3u));
 		/* m = diagonal move; g[k] = best F value reaching cell k from gaps opened INSIDE this thread's block (no dependence on
 		 * what enters from the left), so that after the scan every cell's F is max(entry + k*E, g[k]) with no serial chain */
 		int m[C], g[C]; int b = ZMO_BIGNEG;
@@ -209,10 +212,17 @@ __device__ __forceinline__ void reg_sweep(const BandSmem &S, const uint32_t *row
 				if(fk + E > mm + DE) d |= 8u;
 				H[k] = hn; Ev[k] = inb? ee : NEGV;
 				zw[k >> 3] |= d << ((k & 7) << 2);
-				if(j == je - 1) S.smisc[0] = h;
 			}
 			#pragma unroll
-			for(int wd = 0; wd < WPT; wd++) z[((size_t)i * NT + tid) * WPT + wd] = zw[wd];
+			for(int wd = 0; wd < WPT; wd++) zp[wd] = zw[wd];
+			/* H of the row's last column, read by the end-point rules below / by reg_global after the last row */
+			const int kq = je - 1 - j0;
+			if((unsigned)kq < (unsigned)C){
+				int hv = H[0];
+				#pragma unroll
+				for(int k = 1; k < C; k++) if(kq == k) hv = H[k];
+				S.smisc[0] = hv;
+			}
 		}
 		if(KIND == 2){
 			if(NW > 1){ if(lane == 31) S.sred[NW + warp] = H[C - 1]; __syncthreads(); } else __syncwarp();
