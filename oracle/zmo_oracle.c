@@ -990,6 +990,95 @@ static aln_t stitch_regs(int len1, int len2, const alnreg_t *regs, u32 nreg, con
 	return x;
 }
 
+/* ------------------------------------------------------------------ -n: refinement of the stitched alignment
+ * Restates kswx_refine_alignment (kswx.h:483-659) as wtzmo calls it (wtzmo.c:1031-1034): a global affine re-alignment of
+ * query[qb, qe) (= c on its strand) against target[tb, te) (= q) inside a per-row band around the path of the input CIGAR.
+ *   half width of row r: W, or W + L on the rows of an insertion run of length L; rows within L-1 of an indel run of length
+ *   L get (L - distance) more (a deletion run sits between two rows); a deletion's own "+= len" is overwritten and has no
+ *   effect (kswx.h:529-543).  Band of row r around the path column tx: [tx - zw, tx + 1 + zw) clipped to [0, tl), then the
+ *   starts are made non-decreasing from the top and the ends non-increasing from the bottom (kswx.h:590-601).
+ *   DP: H(-1,-1) = 0, every other out-of-band H / E and the row-initial F read as -10000, e/f opened from the diagonal move,
+ *   same precedence and traceback flags as the extension DP; score = H(ql-1, tl-1); the walk starts there in state M. */
+static aln_t refine_alignment(const u8 *query, int qb, const u8 *target, int tb, int W, const zparams_t *par, u32v *cigar){
+	const int M = par->M, X = par->X, I = par->O, D = par->O, E = par->E;     /* wtzmo passes O for both gap opens */
+	aln_t y = ALN_NULL; u32v in; size_t k; int ql = 0, tl = 0, qx, tx, i, j, wmax = 1;
+	int *zw, *zb, *ze, *hrow, *erow; u8 *z;
+	vec_init(in); vec_reserve(in, cigar->n + 1); memcpy(in.a, cigar->a, cigar->n * sizeof(u32)); in.n = cigar->n;
+	cigar->n = 0;
+	for(k=0;k<in.n;k++){ const u32 op = in.a[k] & 0xF, len = in.a[k] >> 4; if(op == 0){ ql += len; tl += len; } else if(op == 1) ql += len; else tl += len; }
+	if(ql == 0 || tl == 0){ vec_free(in); return ALN_NULL; }
+	zw = calloc((size_t)ql + 2, sizeof(int)); zb = calloc((size_t)ql + 2, sizeof(int)); ze = calloc((size_t)ql + 2, sizeof(int));
+	for(qx=0,k=0;k<in.n;k++){
+		const u32 op = in.a[k] & 0xF; const int len = (int)(in.a[k] >> 4);
+		if(op == 0) for(j=0;j<len;j++) zw[qx++] = W;
+		else if(op == 1) for(j=0;j<len;j++) zw[qx++] = W + len;
+	}
+	for(qx=0,k=0;k<in.n;k++){
+		const u32 op = in.a[k] & 0xF; const int len = (int)(in.a[k] >> 4);
+		if(op == 0) qx += len;
+		else if(op == 1){
+			for(j=1;j<len&&j<qx;j++) zw[qx-j] += len - j;
+			qx += len - 1;
+			for(j=1;j<len&&j+qx<ql;j++) zw[qx+j] += len - j;
+			qx ++;
+		} else {
+			for(j=1;j<len&&j<qx;j++) zw[qx-j] += len - j;
+			for(j=1;j<len&&j+qx<ql;j++) zw[qx+j] += len - j;
+		}
+	}
+	for(qx=tx=0,k=0;k<in.n;k++){
+		const u32 op = in.a[k] & 0xF; const int len = (int)(in.a[k] >> 4);
+		if(op == 0 || op == 1){
+			for(j=0;j<len;j++){
+				int b = tx - zw[qx], e = tx + 1 + zw[qx];
+				zb[qx] = b < 0? 0 : b; ze[qx] = e > tl? tl : e;
+				if(op == 0) tx ++;
+				qx ++;
+			}
+		} else tx += len;
+	}
+	{ int lim = 0; for(i=0;i<ql;i++){ if(zb[i] < lim) zb[i] = lim; else lim = zb[i]; } }
+	{ int lim = tl; for(i=ql-1;i>=0;i--){ if(ze[i] > lim) ze[i] = lim; else lim = ze[i]; } }
+	for(i=0;i<ql;i++) if(ze[i] - zb[i] > wmax) wmax = ze[i] - zb[i];
+	hrow = malloc(((size_t)tl + 2) * sizeof(int)); erow = malloc(((size_t)tl + 2) * sizeof(int));
+	z = calloc((size_t)ql * wmax, 1);
+	hrow[0] = 0; for(j=1;j<=tl;j++) hrow[j] = NEG_SENT;
+	for(j=0;j<=tl;j++) erow[j] = NEG_SENT;
+	for(i=0;i<ql;i++){
+		const u8 qc = query[qb + i]; int hleft = NEG_SENT, f = NEG_SENT; u8 *zi = z + (size_t)i * wmax;
+		for(j=zb[i];j<ze[i];j++){
+			const int m = hrow[j] + (qc == target[tb + j]? M : X); int e = erow[j], h, t; u8 d;
+			hrow[j] = hleft;
+			if(m >= e){ d = 0; h = m; } else { d = 1; h = e; }
+			if(h < f){ d = 2; h = f; }
+			hleft = h;
+			t = m + I + E; e += E; if(e > t) d |= 1 << 2; else e = t;
+			erow[j] = e;
+			t = m + D + E; f += E; if(f > t) d |= 2 << 4; else f = t;
+			zi[j - zb[i]] = d;
+		}
+		hrow[j] = hleft; erow[j] = NEG_SENT;
+	}
+	y.qb = qb; y.qe = qb + ql; y.tb = tb; y.te = tb + tl; y.score = hrow[tl];
+	{
+		u8 d = 0; i = ql - 1; j = tl - 1;
+		while(i >= 0 && j >= 0){
+			if(j < zb[i] || j >= ze[i]){ fprintf(stderr, "zmo_oracle: refine walk left the band (row %d col %d): undefined in the reference\n", i, j); exit(5); }
+			d = (z[(size_t)i * wmax + (j - zb[i])] >> (d << 1)) & 3;
+			if(d == 0){ if(query[qb + i] == target[tb + j]) y.mat ++; else y.mis ++; i --; j --; }
+			else if(d == 1){ i --; y.ins ++; }
+			else { j --; y.del ++; }
+			cig_push(cigar, d, 1);
+		}
+		if(i >= 0){ y.ins += i + 1; cig_push(cigar, 1, (u32)(i + 1)); }
+		if(j >= 0){ y.del += j + 1; cig_push(cigar, 2, (u32)(j + 1)); }
+		cig_reverse(cigar);
+	}
+	y.aln = y.mat + y.mis + y.ins + y.del;
+	free(zw); free(zb); free(ze); free(hrow); free(erow); free(z); vec_free(in);
+	return y;
+}
+
 /* Pure per-pair alignment (wtzmo.c:1017-1030): windows of the chosen strand -> regions -> stitched
  * alignment.  Returns 0 if no region survived the per-window filter (wtzmo.c:1026,1029). */
 static int pair_align(const u8 *pb1, int alen, const u8 *pb2, int blen, const win_t *wins, u32 nwin, const zpair_t *anchors, const zparams_t *par, aln_t *out, u32v *cigar){
@@ -1007,6 +1096,7 @@ static int pair_align(const u8 *pb1, int alen, const u8 *pb2, int blen, const wi
 	}
 	ok = regs.n != 0;
 	if(ok) *out = stitch_regs(alen, blen, regs.a, (u32)regs.n, pb1, pb2, cache.a, cigar, par);
+	if(ok && par->refine) *out = refine_alignment(pb2, out->qb, pb1, out->tb, par->w, par, cigar);     /* wtzmo.c:1031-1034 */
 	vec_free(regs); vec_free(cache);
 	return ok;
 }
@@ -1571,7 +1661,6 @@ int main(int argc, char **argv){
 	if(par->ksize > 32 || par->ksize < 5) return usage();
 	if(par->zsize > 16 || par->zsize < 5) return usage();
 	if(par->ksave < 1) return usage();
-	if(par->refine){ fprintf(stderr, "zmo_oracle: -n (refine) is not restated\n"); return 2; }
 	par->max_overhang = 2 * par->xvar;
 	par->kstep = par->kwin / 2;
 	rs_load(&z->rs, pbs.a, (int)pbs.n, par->min_rdlen, 0);
