@@ -55,6 +55,9 @@ int  zmo_ctx_create(zmo_ctx **ctx, int device, const zmo_params_t *par);
  * the index is built through the root, while no clone is executing; clones are destroyed before the root. */
 int  zmo_ctx_clone(zmo_ctx *root, zmo_ctx **clone);
 void zmo_ctx_destroy(zmo_ctx *ctx);
+/* -n (wtzmo.c:1648,1031-1034): re-align every stitched alignment with kswx_refine_alignment (kswx.h:483-659) inside the
+ * band around its CIGAR before the record is judged.  Set on the root before cloning; clones inherit it. */
+int  zmo_set_refine(zmo_ctx *ctx, int on);
 const char *zmo_last_error(void);
 /* number of kernels launched by this context so far (bench.py's gpu_launches claim) */
 uint64_t zmo_kernel_launches(const zmo_ctx *ctx);

@@ -96,6 +96,7 @@ def load_lib(path=None):
     lib.zmo_pair_align.argtypes = [vp, C.c_int, vp, C.c_uint32, vp, vp, C.c_uint64, u64p]
     lib.zmo_pair_align_text.argtypes = [vp, C.c_int, vp, C.c_uint32, vp, vp, C.c_uint64, u64p]
     lib.zmo_ctx_clone.argtypes = [vp, C.POINTER(vp)]
+    lib.zmo_set_refine.argtypes = [vp, C.c_int]
     lib.zmo_pair_dotmatrix.argtypes = [vp, vp, C.c_uint32, vp]
     lib.zmo_dp_extend.argtypes = [vp, C.c_int, vp, C.c_uint32, vp, vp, C.c_uint64, u64p]
     lib.zmo_dp_global.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, u64p]
@@ -148,6 +149,10 @@ class Zmo:
     def clone(self):
         """zmo_ctx_clone: a context with its own streams / scratch that shares this one's reads and index."""
         return Zmo(lib=self.lib, _clone_of=self)
+
+    def set_refine(self, on=True):
+        """zmo_set_refine: -n, re-align stitched alignments with kswx_refine_alignment (set before cloning)."""
+        self._chk(self.lib.zmo_set_refine(self._h, 1 if on else 0))
 
     def _chk(self, rc):
         if rc != 0:

@@ -897,7 +897,7 @@ static int usage(void){
 	" -e <int>    Maximum bandwidth at ending extension, [800]\n"
 	" -s <int>    Minimum alignment score, [200]\n"
 	" -m <float>  Minimum alignment identity, [0.5]\n"
-	" -n          Refine the alignment (not available in the B200 build)\n"
+	" -n          Refine the alignment\n"
 	" -v          Verbose (accepted, ignored)\n"
 	"Environment: ZMO_DEVICE (GPU ordinal, default 0; under torchrun LOCAL_RANK), ZMO_BATCH_READS, ZMO_BATCH_PAIRS, ZMO_STATS=file\n"
 	"\n");
@@ -983,7 +983,6 @@ wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	if(S->output == NULL){ *rc_out = usage(); return NULL; }
 	if(!par->overwrite && strcmp(S->output, "-") && file_exists(S->output)){ fprintf(stderr, "File exists! '%s'\n\n", S->output); *rc_out = usage(); return NULL; }
 	if(pbs.n == 0 || par->ksize > 32 || par->ksize < 5 || par->zsize > 16 || par->zsize < 5 || par->ksave < 1){ *rc_out = usage(); return NULL; }
-	if(par->refine){ fprintf(stderr, "wtzmo(b200): -n (kswx_refine_alignment) is not available in this build\n"); *rc_out = 2; return NULL; }
 	if(par->n_job < 1 || par->n_idx < 1){ fprintf(stderr, "wtzmo(b200): -P and -G must be >= 1\n"); *rc_out = 2; return NULL; }
 	par->max_overhang = 2 * par->xvar;
 	par->kstep = par->kwin / 2;
@@ -1059,6 +1058,7 @@ wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	zp.M = par->M; zp.X = par->X; zp.O = par->O; zp.E = par->E; zp.T = par->T; zp.min_id = par->min_id;
 	zp.xvar = par->xvar; zp.yvar = par->yvar; zp.min_block_len = par->min_block_len; zp.max_overhang = par->max_overhang; zp.deviation_penalty = par->deviation_penalty; zp.gap_penalty = par->gap_penalty;
 	if(zmo_ctx_create(&z->ctx, S->device, &zp)){ fprintf(stderr, "wtzmo(b200): zmo_ctx_create: %s\n", zmo_last_error()); *rc_out = 3; return NULL; }
+	if(par->refine && zmo_set_refine(z->ctx, 1)){ fprintf(stderr, "wtzmo(b200): zmo_set_refine: %s\n", zmo_last_error()); *rc_out = 3; return NULL; }
 	/* one context per queued batch: those in flight + the one being replayed (which may still ask for on-demand waves) */
 	z->ctxs[0] = z->ctx; z->n_ctx = 1;
 	{ int q; for(q=1;q<z->depth;q++){ if(zmo_ctx_clone(z->ctx, &z->ctxs[z->n_ctx])){ fprintf(stderr, "wtzmo(b200): zmo_ctx_clone: %s\n", zmo_last_error()); *rc_out = 3; return NULL; } z->n_ctx ++; } }

@@ -47,11 +47,13 @@ extern "C" int zmo_ctx_clone(zmo_ctx *root, zmo_ctx **out){
 	if(root->is_clone) return zmo_set_err(ZMO_ERR_ARG, "clone of a clone");
 	CUDA_TRY(cudaSetDevice(root->device));
 	zmo_ctx *c = new zmo_ctx();
-	c->st = root->st; c->is_clone = true;
+	c->st = root->st; c->is_clone = true; c->refine = root->refine;
 	if(int rc = ctx_init(c, root->device, &root->par)){ zmo_ctx_destroy(c); return rc; }
 	*out = c;
 	return ZMO_OK;
 }
+
+extern "C" int zmo_set_refine(zmo_ctx *c, int on){ if(!c) return zmo_set_err(ZMO_ERR_ARG, "null context"); c->refine = on != 0; return ZMO_OK; }
 
 extern "C" void zmo_ctx_destroy(zmo_ctx *c){
 	if(!c) return;

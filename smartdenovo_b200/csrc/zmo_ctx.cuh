@@ -94,6 +94,7 @@ struct zmo_ctx {
 	ZStore *st = nullptr;  /* read store + k-mer index: own (root context) or the root's (clone) */
 	ZStore own;
 	bool is_clone = false;
+	bool refine = false;      /* -n: kswx_refine_alignment after the stitch (zmo_set_refine) */
 	/* scratch */
 	DevBuf s0, s1, s2, s3, s4, s5, s6, s7, cubtmp;
 	DevBuf arena;        /* bump-allocated DP scratch (traceback, staged sequences) */

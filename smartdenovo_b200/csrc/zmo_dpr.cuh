@@ -97,7 +97,10 @@ __device__ __forceinline__ int reg_walk(const uint32_t *z, const uint32_t *rowpk
 
 /*
  * The sweep.  KIND 0: extension, fixed band (kswx_extend_align_core); 1: extension, band follows the row arg-max
- * (kswx_extend_align_shift_core); 2: global (ksw_global2; rows = target, columns = query, init = 0).
+ * (kswx_extend_align_shift_core); 2: global (ksw_global2; rows = target, columns = query, init = 0); 3: global inside the
+ * per-row band [zb[i], ze[i]) of kswx_refine_alignment (kswx.h:602-633: both arrays monotone, H(-1,-1) = 0, every other
+ * out-of-band neighbour -10000; the band may jump by whole blocks between rows, so the value handed over from the left
+ * neighbour is only taken if that thread really held the adjacent block in the previous row).
  * nrow rows are swept over tl columns with half band W; full_rows / full_cols are the unclamped lengths the end-point
  * rules test against.  Requires min(tl, 2W+1) <= RegCap<NT,C>::ncol.  S.sred holds 2*NW ints (NW scan totals | NW
  * edge values), S.sredk NW keys, S.smisc >= 16 ints.  Returns through o_*: extension = chosen end point (0-based),
@@ -105,11 +108,13 @@ __device__ __forceinline__ int reg_walk(const uint32_t *z, const uint32_t *rowpk
  */
 template<int NT, int C, int KIND>
 __device__ __forceinline__ void reg_sweep(const BandSmem &S, const uint32_t *rowpk, const uint32_t *colpk, int nrow, int tl, int full_rows, int full_cols,
-		int W, int init, const DPPar &P, uint32_t *z, int &o_score, int &o_i, int &o_j, unsigned long long &o_cells, int tid){
+		int W, int init, const DPPar &P, uint32_t *z, int &o_score, int &o_i, int &o_j, unsigned long long &o_cells, int tid,
+		const int *zb = nullptr, const int *ze = nullptr){
 	static_assert(KIND != 1 || C >= 2, "the shifting band may advance two columns per row");
 	static_assert((NT & (NT - 1)) == 0 && NT >= 32, "NT must be a power of two");
 	constexpr int NW = NT / 32, WPT = (C + 7) / 8;
 	constexpr int NEGV = KIND == 2? ZMO_GNEG : ZMO_NEG;
+	static_assert(KIND >= 0 && KIND <= 3, "unknown sweep kind");
 	constexpr unsigned FULL = 0xffffffffu;
 	const int lane = tid & 31, warp = tid >> 5;
 	const int IE = P.I + P.E, DE = P.D + P.E, E = P.E, CE = C * P.E;
@@ -125,9 +130,9 @@ __device__ __forceinline__ void reg_sweep(const BandSmem &S, const uint32_t *row
 		/* "row -1": H(-1, j) = boundary value read by cell (0, j+1) (kswx.h:140-146 / ksw.c:527-531); nothing right of row 0's band is ever read */
 		const int je0 = tl < W + 1? tl : W + 1;
 		#pragma unroll
-		for(int k = 0; k < C; k++){ const int j = tid * C + k; H[k] = j < je0? init + P.D + E * (j + 1) : NEGV; Ev[k] = NEGV; }
+		for(int k = 0; k < C; k++){ const int j = tid * C + k; H[k] = (KIND != 3 && j < je0)? init + P.D + E * (j + 1) : NEGV; Ev[k] = NEGV; }
 		xw = load_cols(tid * C);
-		if(NW > 1){ if(lane == 31) S.sred[NW + warp] = H[C - 1]; __syncthreads(); }
+		if(NW > 1){ if(lane == 31){ S.sred[NW + warp] = H[C - 1]; if(KIND == 3) S.sredk[warp] = tid; } __syncthreads(); }
 	}
 	int best = init, bi = -1, bj = -1, gbest = 0, gi = -1, gj = -1;
 	int c = 0;
@@ -137,7 +142,8 @@ __device__ __forceinline__ void reg_sweep(const BandSmem &S, const uint32_t *row
 	for(int i = 0; i < nrow; i++, zp += NT * WPT){
 		int jb, je;
 		if((i & 15) == 0) rwd = rowpk[i >> 4];
-		if(KIND == 1){ jb = c - W; je = c + W + 1; } else { jb = i - W; je = i + W + 1; }
+		if(KIND == 3){ jb = zb[i]; je = ze[i]; }
+		else if(KIND == 1){ jb = c - W; je = c + W + 1; } else { jb = i - W; je = i + W + 1; }
 		if(jb < 0) jb = 0;
 		if(je > tl) je = tl;
 		cells += (unsigned long long)(je > jb? je - jb : 0);
@@ -148,13 +154,19 @@ __device__ __forceinline__ void reg_sweep(const BandSmem &S, const uint32_t *row
 		int left;
 		if(NW == 1) left = __shfl_sync(FULL, H[C - 1], (lane + 31) & 31);
 		else { left = __shfl_up_sync(FULL, H[C - 1], 1); if(lane == 0) left = S.sred[NW + ((warp + NW - 1) & (NW - 1))]; }
+		if(KIND == 3){
+			int lblk;
+			if(NW == 1) lblk = __shfl_sync(FULL, myblk, (lane + 31) & 31);
+			else { lblk = __shfl_up_sync(FULL, myblk, 1); if(lane == 0) lblk = (int)S.sredk[(warp + NW - 1) & (NW - 1)]; }
+			if(lblk != blk - 1) left = NEGV;
+		}
 		if(blk != myblk){
 			myblk = blk;
 			#pragma unroll
 			for(int k = 0; k < C; k++){ H[k] = NEGV; Ev[k] = NEGV; }
 			xw = load_cols(j0);
 		}
-		if(j0 == 0) left = i == 0? init : init + P.I + E * i;
+		if(j0 == 0) left = KIND == 3? (i == 0? 0 : NEGV) : (i == 0? init : init + P.I + E * i);
 		const bool act = j0 < je;
 		const int lo = jb - j0, hi = je - j0;
 		const unsigned long long x = xw ^ (0x5555555555555555ull * (unsigned long long)((rwd >> (((~i) & 15) << 1)) & 3u));
@@ -224,8 +236,8 @@ __device__ __forceinline__ void reg_sweep(const BandSmem &S, const uint32_t *row
 				S.smisc[0] = hv;
 			}
 		}
-		if(KIND == 2){
-			if(NW > 1){ if(lane == 31) S.sred[NW + warp] = H[C - 1]; __syncthreads(); } else __syncwarp();
+		if(KIND == 2 || KIND == 3){
+			if(NW > 1){ if(lane == 31){ S.sred[NW + warp] = H[C - 1]; if(KIND == 3) S.sredk[warp] = myblk; } __syncthreads(); } else __syncwarp();
 			continue;
 		}
 		/* row arg-max: max h over the row, then the first (shifting band) / last (fixed band) column reaching it */
@@ -312,5 +324,31 @@ __device__ void reg_global(const BandSmem &S, const uint32_t *colpk /*query*/, i
 	ex_sync<NT>();
 	out.mat = S.smisc[4]; out.mis = S.smisc[5]; out.ins = S.smisc[6]; out.del = S.smisc[7]; out.ncig = S.smisc[8];
 	out.qe = qlen; out.te = tlen;
+	ex_sync<NT>();
+}
+
+
+/* kswx_refine_alignment's DP + walk (kswx.h:602-655) for a band that fits the executor: max_i (ze[i] - zb[i]) <= RegCap<NT,C>::ncol.
+ * rowpk = query (c on its strand from qb), colpk = target (q from tb); z needs ql * NT * WPT words.  cig receives the ops in
+ * WALK order.  out.score = H(ql-1, tl-1). */
+template<int NT, int C>
+__device__ void reg_refine(const BandSmem &S, const uint32_t *rowpk, int ql, const uint32_t *colpk, int tl, const int *zb, const int *ze,
+		const DPPar &P, uint32_t *z, uint32_t *cig, int cig_cap, DPOut &out, unsigned long long *cells_acc, int tid){
+	unsigned long long cells = 0; int d0 = 0, d1 = 0, d2 = 0;
+	reg_sweep<NT, C, 3>(S, rowpk, colpk, ql, tl, ql, tl, 0, 0, P, z, d0, d1, d2, cells, tid, zb, ze);
+	ex_sync<NT>();
+	out.score = (ze[ql - 1] == tl && ze[ql - 1] > zb[ql - 1])? S.smisc[0] : ZMO_NEG;
+	ex_sync<NT>();
+	if(tid < 32){
+		int cnt[4];
+		const int n = reg_walk<NT, C>(z, rowpk, colpk, ql - 1, tl - 1, 1u, 2u, cig, cig_cap, tid, cnt);
+		if(tid == 0){
+			S.smisc[4] = cnt[0]; S.smisc[5] = cnt[1]; S.smisc[6] = cnt[2]; S.smisc[7] = cnt[3]; S.smisc[8] = n;
+			if(cells_acc) atomicAdd(cells_acc, cells);
+		}
+	}
+	ex_sync<NT>();
+	out.mat = S.smisc[4]; out.mis = S.smisc[5]; out.ins = S.smisc[6]; out.del = S.smisc[7]; out.ncig = S.smisc[8];
+	out.qe = ql; out.te = tl;
 	ex_sync<NT>();
 }

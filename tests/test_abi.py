@@ -64,7 +64,7 @@ def test_usage_exit_codes(built, tmp_path):
     assert run("-i", str(fa), "-o", str(tmp_path / "x.ovl"), "-S", "0") == 1
     (tmp_path / "exists.ovl").write_text("x")
     assert run("-i", str(fa), "-o", str(tmp_path / "exists.ovl")) == 1     # exists without -f (wtzmo.c:1654)
-    assert run("-i", str(fa), "-fo", str(tmp_path / "x.ovl"), "-n") == 2   # refine not available
+    assert run("-i", str(fa), "-fo", str(tmp_path / "x.ovl"), "-n") == 3   # -n is accepted; without a GPU the run then fails loudly (no CPU fallback)
 
 
 def test_pack_reads_layout():

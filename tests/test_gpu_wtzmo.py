@@ -56,6 +56,15 @@ def test_sw_small_batches(tmp_path, gen_reads, oracle_bin):
         _compare(tmp_path, gen_reads, oracle_bin, ["-n", "120", "-L", "5000", "-G", "50000", "-s", "3"], ["-k", "16", "-s", "200", "-m", "0.6"], env=env)
 
 
+def test_refine_n(tmp_path, gen_reads, oracle_bin):
+    """-n: kswx_refine_alignment after the stitch (wtzmo.c:1031-1034), PacBio-like and ONT-like error models, narrow -w too"""
+    n = _compare(tmp_path, gen_reads, oracle_bin, ["-n", "200", "-L", "6000", "-G", "60000", "-s", "1"], ["-k", "16", "-s", "200", "-m", "0.6", "-n"])
+    assert n > 100
+    _compare(tmp_path, gen_reads, oracle_bin, ["-n", "150", "-L", "4000", "-G", "60000", "-s", "17", "-m", "ont"], ["-k", "16", "-n", "-w", "20"])
+    env = dict(os.environ, ZMO_BATCH_READS="5")
+    _compare(tmp_path, gen_reads, oracle_bin, ["-n", "100", "-L", "5000", "-G", "50000", "-s", "23"], ["-k", "16", "-s", "100", "-m", "0.5", "-n", "-w", "120"], env=env)
+
+
 def test_sw_ont_repeats(tmp_path, gen_reads, oracle_bin):
     n = _compare(tmp_path, gen_reads, oracle_bin, ["-n", "400", "-L", "5000", "-G", "80000", "-s", "7", "-m", "ont"], ["-k", "16", "-s", "200", "-m", "0.6"])
     assert n > 300
