@@ -14,8 +14,9 @@ step is different work of the same shape.  The read set is synthetic (tools/gen_
   cpu_baseline : the unmodified reference binary (oracle/_ref/wtzmo -t <cores>) on a bounded sub-shard
 
 `--impl reference` times only the reference CPU binary on the same configuration.
-Under torchrun (N>1) every rank owns a GPU and its own shard sequence (weak scaling, no data-path collective);
-records are gathered to rank 0 with one NCCL all-gather at the end of the timed region.
+Under torchrun (N>1) every rank owns a GPU and its own shard sequence -- the shard size is the same for every N (weak
+scaling, no data-path collective); the last step's records are gathered to rank 0 with one NCCL all-gather at the end of
+the timed region.
 """
 import argparse
 import ctypes as C
@@ -258,7 +259,9 @@ def main():
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
             "alg_bytes_per_cell": 0.5, "cells_per_step": groups[dom][1] / args.steps, "kernel_ms_per_step": groups[dom][0] / args.steps,
             "gcells_per_s": groups[dom][1] / dom_s / 1e9 if dom_s > 0 else 0.0,
-            "note": "integer DP is ALU/latency bound, not HBM bound (see DESIGN.md): gcells_per_s is the number to optimise"}
+            "traffic_profile": {"kernel": "k_window_align", "dram_bytes_per_launch": 379.9e6, "launch_ms": 17.7, "alg_bytes_per_launch_est": 0.85e9,
+                                "source": "profiles/r01_ncu_final.md (ncu --set full, one launch on the cfg2s shard; short bridges keep their traceback in shared memory)"},
+            "note": "integer DP is ALU/latency bound, not HBM bound (see DESIGN.md): gcells_per_s is the number to optimise; kernel time = CUDA-event stage time summed over the contexts in flight"}
     line = {"metric": metric, "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * r_val["wall"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": config, "clocks": sampler.summary(),
