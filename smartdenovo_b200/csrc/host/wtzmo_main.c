@@ -143,11 +143,21 @@ static void rs_add_read(readset_t *rs, const char *name, int name_len, const cha
 	u64 need = (rs->nbases + len + 31) / 32 + 2;
 	if(need > rs->cap_words){ u64 m = rs->cap_words? rs->cap_words : 1024; while(m < need) m <<= 1; rs->bits = realloc(rs->bits, m * 8); memset(rs->bits + rs->cap_words, 0, (m - rs->cap_words) * 8); rs->cap_words = m; }
 	r.off = rs->nbases; r.len = len; r.name = malloc(name_len + 1); memcpy(r.name, name, name_len); r.name[name_len] = 0;
-	for(i=0;i<len;i++){
-		u64 c;
-		switch(seq[i]){ case 'A': case 'a': c = 0; break; case 'C': case 'c': c = 1; break; case 'G': case 'g': c = 2; break; case 'T': case 't': c = 3; break;
-			default: c = lrand48() & 3; }                    /* dna.h:405: unseeded lrand48 on non-ACGT */
-		bank_put(rs->bits, rs->nbases, c); rs->nbases ++;
+	{
+		/* sequential append in the BaseBank layout (dna.h:78,263: base i in word i>>5, MSB first): one shift-or per base
+		 * into an accumulator, one store per 32 bases; non-ACGT -> lrand48() & 3 in file order like dna.h:405 */
+		static u8 tab[256]; static int tab_ok = 0;
+		u64 w = rs->nbases >> 5, acc; int fill = (int)(rs->nbases & 31);
+		if(!tab_ok){ memset(tab, 4, 256); tab['A'] = tab['a'] = 0; tab['C'] = tab['c'] = 1; tab['G'] = tab['g'] = 2; tab['T'] = tab['t'] = 3; tab_ok = 1; }
+		acc = fill? rs->bits[w] >> (64 - 2 * fill) : 0;
+		for(i=0;i<len;i++){
+			u64 c = tab[(u8)seq[i]];
+			if(c > 3) c = lrand48() & 3;
+			acc = (acc << 2) | c;
+			if(++fill == 32){ rs->bits[w++] = acc; acc = 0; fill = 0; }
+		}
+		if(fill) rs->bits[w] = acc << (64 - 2 * fill);
+		rs->nbases += len;
 	}
 	vec_push(rs->reads, r);
 }
@@ -160,7 +170,7 @@ static int sr_open_next(seqreader_t *sr){
 		if(!strcmp(fn, "-")){ sr->fp = stdin; sr->is_proc = 0; return 1; }
 		if(l > 3 && !strcmp(fn + l - 3, ".gz")){ char *cmd = malloc(l + 20); sprintf(cmd, "gzip -dc %s", fn); sr->fp = popen(cmd, "r"); free(cmd); sr->is_proc = 1; if(sr->fp) return 1; continue; }
 		sr->fp = fopen(fn, "r"); sr->is_proc = 0;
-		if(sr->fp) return 1;
+		if(sr->fp){ setvbuf(sr->fp, NULL, _IOFBF, 4u << 20); return 1; }
 		fprintf(stderr, " -- Cannot open %s --\n", fn); exit(1);
 	}
 	return 0;
