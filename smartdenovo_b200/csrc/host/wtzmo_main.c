@@ -331,6 +331,7 @@ typedef VEC(seed_t) seedv;
 #define WZ_PIN_WAVES 6
 typedef struct {
 	readset_t rs; zparams_t par; zmo_ctx *ctx;      /* ctx = root context (reads + index); ctxs[0] == ctx, ctxs[1..] = clones */
+	int call_pairs;
 	zmo_ctx *ctxs[WZ_MAX_CTX]; int n_ctx, depth; u8 ctx_busy[WZ_MAX_CTX];
 	u8 *masked; u32 *rdcovs; u64set_t closed; u32 avg_rdlen; u32 kcut;
 	u64v *rdhits;                       /* per-read candidate carry-over, only with -G > 1 */
@@ -830,6 +831,24 @@ static void run_overlap(wz_t *z){
 				t0 = now_s();
 				batch_candidates(z, nxt);
 				batch_pairs(z, nxt);
+				{
+					/* a device call takes at most 65,536 pairs (32,768 in dot-matrix mode): give the tail of an over-full batch
+					 * back to the read cursor (only reached with large -A / very deep coverage) */
+					const size_t lim = z->call_pairs? (size_t)z->call_pairs : (par->dot_matrix? 32768 : 65536);
+					if(nxt->pairs.n > lim){
+						size_t k, cum = 0, keep = 0, kr = 0;
+						for(k=0;k<nxt->reads.n;k++){
+							bread_t *r = &nxt->reads.a[k]; size_t c = 0, q;
+							for(q=0;q<r->cand_pair.n;q++) if(r->cand_pair.a[q] != 0xFFFFFFFFU) c ++;
+							if(cum + c > lim && k > 0) break;
+							cum += c; keep = cum; kr = k + 1;
+						}
+						if(keep > lim){ fprintf(stderr, "wtzmo(b200): read with %zu candidate pairs exceeds the per-call limit of %zu (lower -A)\n", keep, lim); exit(1); }
+						j = nxt->reads.a[kr].rd_id;
+						for(k=kr;k<nxt->reads.n;k++){ vec_free(nxt->reads.a[k].cands_raw); vec_free(nxt->reads.a[k].cand_pair); }
+						nxt->reads.n = kr; nxt->pairs.n = keep;
+					}
+				}
 				if(z->depth > 1){
 					wk_arg_t *wa = malloc(sizeof(wk_arg_t)); wa->z = z; wa->b = nxt;
 					if(pthread_create(&nxt->th, NULL, batch_compute_thread, wa) != 0){ free(wa); batch_compute(z, nxt); } else nxt->have_thread = 1;
@@ -1003,6 +1022,7 @@ wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	if((env = getenv("ZMO_PIPELINE")) && atoi(env) == 0) z->depth = 1;  /* no pipeline: one batch at a time, one context */
 	if(z->depth < 1) z->depth = 1;
 	if(z->depth > WZ_MAX_CTX) z->depth = WZ_MAX_CTX;
+	z->call_pairs = (env = getenv("ZMO_CALL_PAIRS"))? atoi(env) : 0;     /* test hook: pairs per device call (0 = the library's limits) */
 	z->wave_margin = (env = getenv("ZMO_WAVE0"))? atoi(env) : 8;       /* seeds per read in the first DP wave (doubles per wave); < 0: align every seed up front */
 	z->wave_growth = (env = getenv("ZMO_WAVE_GROWTH"))? atoi(env) : 4; if(z->wave_growth < 2) z->wave_growth = 2;
 	{ int q; for(q=0;q<WZ_MAX_CTX;q++) pthread_mutex_init(&z->dev_mu[q], NULL); pthread_mutex_init(&z->stat_mu, NULL); }

@@ -56,6 +56,13 @@ def test_sw_small_batches(tmp_path, gen_reads, oracle_bin):
         _compare(tmp_path, gen_reads, oracle_bin, ["-n", "120", "-L", "5000", "-G", "50000", "-s", "3"], ["-k", "16", "-s", "200", "-m", "0.6"], env=env)
 
 
+def test_overfull_batches_are_split(tmp_path, gen_reads, oracle_bin):
+    """a batch whose pair list exceeds the per-call limit hands its tail back to the read cursor (SW and dot-matrix mode)"""
+    env = dict(os.environ, ZMO_CALL_PAIRS="300")
+    _compare(tmp_path, gen_reads, oracle_bin, ["-n", "200", "-L", "5000", "-G", "50000", "-s", "29"], ["-k", "16", "-s", "200", "-m", "0.6"], env=env)
+    _compare(tmp_path, gen_reads, oracle_bin, ["-n", "200", "-L", "4000", "-G", "60000", "-s", "7", "-m", "ont"], ["-k", "16", "-z", "10", "-Z", "16", "-U", "-1", "-m", "0.1", "-A", "1000"], env=env)
+
+
 def test_refine_n(tmp_path, gen_reads, oracle_bin):
     """-n: kswx_refine_alignment after the stitch (wtzmo.c:1031-1034), PacBio-like and ONT-like error models, narrow -w too"""
     n = _compare(tmp_path, gen_reads, oracle_bin, ["-n", "200", "-L", "6000", "-G", "60000", "-s", "1"], ["-k", "16", "-s", "200", "-m", "0.6", "-n"])
