@@ -33,6 +33,8 @@ ZMO_HD DotScratch zmo_dot_scratch_carve(uint8_t *base, uint32_t n){
 struct GtZPairDiag { ZMO_HDM bool operator()(const DevZPair &a, const DevZPair &b) const {
 	return ((((int64_t)a.off1 - (int64_t)a.off2) << 32) | (int64_t)a.off1) > ((((int64_t)b.off1 - (int64_t)b.off2) << 32) | (int64_t)b.off1); } };
 struct GtIdxOff1 { const DevZPair *rs; ZMO_HDM bool operator()(uint32_t a, uint32_t b) const { return rs[a].off1 > rs[b].off1; } };
+struct DotKey { uint64_t key; uint32_t idx, pad; };
+struct GtDotKey { ZMO_HDM bool operator()(const DotKey &a, const DotKey &b) const { return a.key > b.key; } };
 struct GtZPairGidOff1 { ZMO_HDM bool operator()(const DevZPairG &a, const DevZPairG &b) const { return (a.gid > b.gid)? true : ((a.gid < b.gid)? false : (a.p.off1 > b.p.off1)); } };
 struct GtWinDiag { ZMO_HDM bool operator()(const DevWin &a, const DevWin &b) const {
 	return ((((int64_t)(a.beg[0] - a.beg[1])) << 32) | (int64_t)a.beg[0]) > ((((int64_t)(b.beg[0] - b.beg[1])) << 32) | (int64_t)b.beg[0]); } };
@@ -56,6 +58,8 @@ ZMO_HDN void zmo_tidy_groups(uint32_t *g, uint32_t n){          /* hzm_aln.h:836
 ZMO_HDN uint32_t zmo_denoise_strand(const DevZPair *rs, uint32_t n, int dir, const DotPar &par, DotScratch &S){
 	const int xvar = par.xvar, yvar = par.yvar, min_len = par.min_block_len;
 	uint32_t i, j, k, doff, dcnt, gid, ndiag = 0, ngrp = 0, nblock, ndst = 0, nreg = 0; int lst_offset, end_offset, len;
+	/* packed sort keys of a diagonal bucket live in the (still unused) block region; those of the group sort in the node region */
+	uint64_t *blk = (uint64_t*)(((uintptr_t)S.regs + 7) & ~(uintptr_t)7); DotKey *gk = (DotKey*)(((uintptr_t)S.nodes + 7) & ~(uintptr_t)7);
 	for(i = 0; i < n; i++){
 		if(rs[i].dir1 ^ rs[i].dir2 ^ dir) continue;
 		const int dg = (int)rs[i].off1 - (int)rs[i].off2;
@@ -79,25 +83,26 @@ ZMO_HDN uint32_t zmo_denoise_strand(const DevZPair *rs, uint32_t n, int dir, con
 			const DevDiag d = S.diags[i + doff];
 			for(j = 0; j < d.cnt; j++){
 				if(d.off + j >= n) break;
-				if(rs[d.off + j].dir1 ^ rs[d.off + j].dir2 ^ dir) continue;
-				S.block[nblock++] = d.off + j;
+				const DevZPair &q = rs[d.off + j];
+				if(q.dir1 ^ q.dir2 ^ dir) continue;
+				blk[nblock++] = ((uint64_t)q.off1 << 32) | (d.off + j);      /* sort key | index: the comparator reads no other memory */
 			}
 		}
-		{ GtIdxOff1 g; g.rs = rs; zmo_ref_sort(S.block, (size_t)nblock, g); }
+		zmo_ref_sort(blk, (size_t)nblock, GtHi32());
 		if(nblock){
-			int p0_off1 = (int)rs[S.block[0]].off1, p0_len1 = (int)rs[S.block[0]].len1;
+			int p0_off1 = (int)(blk[0] >> 32), p0_len1 = (int)rs[(uint32_t)blk[0]].len1;
 			len = p0_len1; j = 0;
 			for(i = 1; i <= nblock; i++){
-				const int p_off1 = (i == nblock)? 0x7FFFFFFF : (int)rs[S.block[i]].off1, p_len1 = (i == nblock)? 0 : (int)rs[S.block[i]].len1;
+				const int p_off1 = (i == nblock)? 0x7FFFFFFF : (int)(blk[i] >> 32), p_len1 = (i == nblock)? 0 : (int)rs[(uint32_t)blk[i]].len1;
 				if(p_off1 <= p0_off1 + p0_len1 || p_off1 <= p0_off1 + p0_len1 + xvar){
 					len += (int)((uint32_t)p_off1 + (uint32_t)p_len1) - (p0_off1 + p0_len1);
 				} else {
 					if(len >= min_len){
 						gid = 0;
-						for(k = j; k < i; k++){ const uint32_t g = S.gid[S.block[k]]; if(g){ if(gid == 0) gid = S.grps[g]; else if(gid > S.grps[g]) gid = S.grps[g]; } }
+						for(k = j; k < i; k++){ const uint32_t g = S.gid[(uint32_t)blk[k]]; if(g){ if(gid == 0) gid = S.grps[g]; else if(gid > S.grps[g]) gid = S.grps[g]; } }
 						if(gid == 0){ gid = ngrp; S.grps[ngrp++] = gid; }
-						else { for(k = j; k < i; k++){ const uint32_t g = S.gid[S.block[k]]; if(g) S.grps[g] = gid; } }
-						for(; j < i; j++) S.gid[S.block[j]] = gid;
+						else { for(k = j; k < i; k++){ const uint32_t g = S.gid[(uint32_t)blk[k]]; if(g) S.grps[g] = gid; } }
+						for(; j < i; j++) S.gid[(uint32_t)blk[j]] = gid;
 					}
 					j = i;
 					len = p0_len1;
@@ -113,9 +118,11 @@ ZMO_HDN uint32_t zmo_denoise_strand(const DevZPair *rs, uint32_t n, int dir, con
 		if(rs[i].dir1 ^ rs[i].dir2 ^ dir) continue;
 		if(S.gid[i] == 0) continue;
 		S.gid[i] = S.grps[S.gid[i]];
-		S.dst[ndst].p = rs[i]; S.dst[ndst].gid = S.gid[i]; ndst++;
+		gk[ndst].key = ((uint64_t)S.gid[i] << 32) | rs[i].off1; gk[ndst].idx = i; gk[ndst].pad = 0; ndst++;
 	}
-	zmo_ref_sort(S.dst, (size_t)ndst, GtZPairGidOff1());
+	/* (gid, off1) as one 64-bit key: the same comparison outcomes as the two-level comparator, hence the same permutation */
+	zmo_ref_sort(gk, (size_t)ndst, GtDotKey());
+	for(i = 0; i < ndst; i++){ S.dst[i].p = rs[gk[i].idx]; S.dst[i].gid = (uint32_t)(gk[i].key >> 32); }
 	j = 0;
 	for(i = 1; i <= ndst; i++){
 		DevWin s; uint32_t lst = 0;
