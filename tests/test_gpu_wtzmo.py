@@ -170,3 +170,26 @@ def test_edge_reads(tmp_path, oracle_bin):
         ref = open(tmp_path / "ref.ovl", "rb").read()
         assert ref == open(tmp_path / "gpu.ovl", "rb").read() and ref.count(b"\n") > 200
         assert open(tmp_path / "ref.ovl.contained", "rb").read() == open(tmp_path / "gpu.ovl.contained", "rb").read()
+
+
+def test_scale_200k_reads_shard_matches_reference_golden(tmp_path, gen_reads):
+    """2.09 Gbp read set (200,000 x 10 kb): one query shard against the full index; the golden digest is the unmodified
+    reference binary's `-t 1` output for the same seeded input (tests/golden/make_scale_golden.sh, ~8 min of CPU there)"""
+    import hashlib
+    import json
+    gold = json.load(open(os.path.join(REPO, "tests", "golden", "scale_digests.json")))["big200k_P400_p0"]
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else str(tmp_path)
+    fa = os.path.join(base, "zmo_scale_test.fa")
+    out = os.path.join(base, "zmo_scale_test.ovl")
+    try:
+        subprocess.run([gen_reads] + gold["gen"] + ["-o", fa], check=True)
+        r = subprocess.run([EXE, "-t", "1", "-i", fa, "-f", "-o", out] + gold["args"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        data = open(out, "rb").read()
+        assert data.count(b"\n") == gold["lines"]
+        assert hashlib.md5(data).hexdigest() == gold["md5"]
+        assert hashlib.md5(open(out + ".contained", "rb").read()).hexdigest() == gold["contained_md5"]
+    finally:
+        for f in (fa, out, out + ".contained"):
+            if os.path.exists(f):
+                os.remove(f)
