@@ -44,19 +44,26 @@ __global__ void k_z_heads(const unsigned long long *keys, const unsigned long lo
 	for(unsigned long long j = i + 1; j < n && keys[j] == key && c <= zcut; j++) c++;
 	flag[i] = c < zcut; runlen[i] = c;
 }
-__global__ void k_z_slots(const unsigned long long *keys, const uint32_t *flag, const uint32_t *pos, const uint32_t *runlen, unsigned long long n, const unsigned long long *zoff, DevSlot *slots){
+/* Per-query membership filter over the slot z-mers: ZF_BITS bits per query read, one hashed bit per slot.  A c z-mer whose
+ * bit is clear cannot hit a slot (>= 97% of all look-ups at ~8,000 slots per read), so k_hit pays one L2-resident load
+ * instead of a 13-step binary search for it; the reference's 4^z bit vector (hzm_aln.h:107-114,152) plays the same role. */
+#define ZF_LOG 18
+#define ZF_WORDS (1u << (ZF_LOG - 5))
+__device__ __forceinline__ uint32_t zf_hash(uint32_t mer){ return (mer * 2654435761u) >> (32 - ZF_LOG); }
+__global__ void k_z_slots(const unsigned long long *keys, const uint32_t *flag, const uint32_t *pos, const uint32_t *runlen, unsigned long long n, const unsigned long long *zoff, DevSlot *slots, uint32_t *filt){
 	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= n || !flag[i]) return;
 	const uint32_t u = (uint32_t)(keys[i] >> 32);
 	DevSlot s; s.mer = (uint32_t)keys[i]; s.off = (uint32_t)(i - zoff[u]); s.cnt = runlen[i];
 	slots[pos[i]] = s;
+	{ const uint32_t h = zf_hash(s.mer); atomicOr(filt + (size_t)u * ZF_WORDS + (h >> 5), 1u << (h & 31)); }
 }
 __global__ void k_z_ranges(const unsigned long long *zoff, const uint32_t *pos, uint32_t nuq, unsigned long long Z, uint32_t NS, uint32_t *slot_beg){
 	uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
 	if(u > nuq) return;
 	slot_beg[u] = (u < nuq && zoff[u] < Z)? pos[zoff[u]] : NS;
 }
-struct ZIdxView { const DevSlot *slots; const uint32_t *slot_beg; const DevZSeed *zs; const unsigned long long *zoff; };
+struct ZIdxView { const DevSlot *slots; const uint32_t *slot_beg; const DevZSeed *zs; const unsigned long long *zoff; const uint32_t *filt; };
 #define SEED_CH 128
 /* chunk table of the candidate reads: one thread per pair */
 __global__ void k_c_nchunks(DevReads R, const uint32_t *pc, uint32_t np, unsigned long long *nch){
@@ -75,9 +82,11 @@ __global__ void k_hit(DevReads R, ZIdxView Z, const uint32_t *pq, const uint32_t
 	while(lo + 1 < hi){ uint32_t mid = (lo + hi) >> 1; if(choff[mid] <= c) lo = mid; else hi = mid; }
 	const uint32_t p = lo, u = pq[p], cid = pc[p], s = (uint32_t)(c - choff[p]) * SEED_CH;
 	const uint32_t sb = Z.slot_beg[u], ns = Z.slot_beg[u + 1] - sb; const DevSlot *slots = Z.slots + sb;
+	const uint32_t *fl = Z.filt + (size_t)u * ZF_WORDS;
 	unsigned long long n = PASS? cnt_or_off[c] : 0;
 	zmo_scan_kmers_chunk(R.words + R.woff[cid], R.len[cid], zsize, hz, s, s + SEED_CH, [&](uint64_t mer64, uint32_t dir, uint32_t off, uint32_t ln){
 		const uint32_t mer = (uint32_t)mer64;
+		{ const uint32_t h = zf_hash(mer); if(!((__ldg(fl + (h >> 5)) >> (h & 31)) & 1u)) return; }
 		uint32_t a = 0, b = ns;
 		while(a < b){ uint32_t mid = (a + b) >> 1; if(slots[mid].mer < mer) a = mid + 1; else b = mid; }
 		if(a >= ns || slots[a].mer != mer) return;
@@ -256,6 +265,8 @@ int seed_prepare(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, int mode, See
 	uint32_t *d_flag = c->s6.as<uint32_t>(), *d_pos = d_flag + Zp, *d_run = d_pos + Zp;
 	DevZSeed *d_zs = c->s7.as<DevZSeed>(); DevSlot *d_slots = (DevSlot*)(d_zs + Zp);
 	uint32_t NS = 0;
+	if(c->zfilt.reserve((size_t)(nuq + 1) * ZF_WORDS * 4)) return ZMO_ERR_CUDA;
+	CUDA_TRY(cudaMemsetAsync(c->zfilt.p, 0, (size_t)(nuq + 1) * ZF_WORDS * 4, c->stream));
 	if(Z){
 		k_z_scan<1><<<(nuq + bs - 1) / bs, bs, 0, c->stream>>>(R, d_uq, nuq, c->par.zsize, c->par.hz, d_zoff, k_in, v_in); c->launches++;
 		int qbits = 1; while((1ull << qbits) < nuq) qbits++;
@@ -267,7 +278,7 @@ int seed_prepare(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, int mode, See
 		CUDA_TRY(cudaMemcpyAsync(&lf, d_flag + (Z - 1), 4, cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
 		NS = lp + lf;
-		k_z_slots<<<(unsigned)((Z + 255) / 256), 256, 0, c->stream>>>(k_out, d_flag, d_pos, d_run, Z, d_zoff, d_slots); c->launches++;
+		k_z_slots<<<(unsigned)((Z + 255) / 256), 256, 0, c->stream>>>(k_out, d_flag, d_pos, d_run, Z, d_zoff, d_slots, c->zfilt.as<uint32_t>()); c->launches++;
 	}
 	k_z_ranges<<<(nuq + 1 + 127) / 128, 128, 0, c->stream>>>(d_zoff, d_pos, nuq, Z, NS, d_slot_beg); c->launches++;
 	/* ---- match lists, fully parallel: hits per (pair, c-chunk) -> stable sort by (pair, slot) -> rank cap + expansion
@@ -277,7 +288,7 @@ int seed_prepare(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, int mode, See
 	if(c->st->max_rdlen >= (1u << 24)) return zmo_set_err(ZMO_ERR_ARG, "reads of 2^24 bases or more are not supported (reference limit rdlen:24, wtzmo.c:88)");
 	if(c->s2.reserve(((size_t)np + 2) * 24 + np + 64)) return ZMO_ERR_CUDA;
 	unsigned long long *d_pnch = c->s2.as<unsigned long long>(), *d_pchoff = d_pnch + np + 1, *d_coff = d_pchoff + np + 1; uint8_t *d_tie = (uint8_t*)(d_coff + np + 2);
-	ZIdxView ZV; ZV.slots = d_slots; ZV.slot_beg = d_slot_beg; ZV.zs = d_zs; ZV.zoff = d_zoff;
+	ZIdxView ZV; ZV.slots = d_slots; ZV.slot_beg = d_slot_beg; ZV.zs = d_zs; ZV.zoff = d_zoff; ZV.filt = c->zfilt.as<uint32_t>();
 	k_c_nchunks<<<(np + 127) / 128, 128, 0, c->stream>>>(R, d_pc, np, d_pnch); c->launches++;
 	CUDA_TRY(cudaMemsetAsync(d_pnch + np, 0, 8, c->stream));
 	CUDA_TRY(cudaMemsetAsync(d_tie, 0, np, c->stream));
