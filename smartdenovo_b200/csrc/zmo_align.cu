@@ -195,7 +195,7 @@ __device__ inline int push_job(int cls, JobLists &L, DPJob &J, unsigned long lon
 	return (int)J.out_idx;
 }
 
-__global__ void k_plan(const AlnTask *tasks, uint32_t nt, const zmo_pair_t *pairs, const DevReg *regs, DevReads R, AlnPar A, JobLists L, TaskState *ts, unsigned long long arena_base){
+__global__ void k_plan(const AlnTask *tasks, uint32_t nt, const zmo_pair_t *pairs, const DevReg *regs, DevReads R, AlnPar A, JobLists L, TaskState *ts){
 	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if(t >= nt) return;
 	const AlnTask T = tasks[t]; const zmo_pair_t pr = pairs[T.pair_idx];
@@ -686,7 +686,7 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 		CUDA_TRY(cudaMemsetAsync(ctr + CTR_JOBS, 0, 6 * 8, c->stream));
 		CUDA_TRY(cudaMemsetAsync(ctr + CTR_OVERFLOW, 0, 8, c->stream));
 		CUDA_TRY(cudaMemcpyAsync(ctr + CTR_CIG, &init_ctr[1], 8, cudaMemcpyHostToDevice, c->stream));
-		k_plan<<<(nt + 63) / 64, 64, 0, c->stream>>>(d_tasks, nt, SL.pairs.as<zmo_pair_t>(), d_regs, R, A, L, d_ts, 0); c->launches++;
+		k_plan<<<(nt + 63) / 64, 64, 0, c->stream>>>(d_tasks, nt, SL.pairs.as<zmo_pair_t>(), d_regs, R, A, L, d_ts); c->launches++;
 		unsigned long long h[CTR_TOTAL];
 		CUDA_TRY(cudaMemcpyAsync(h, ctr, CTR_TOTAL * 8, cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));

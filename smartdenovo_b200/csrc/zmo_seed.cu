@@ -153,16 +153,17 @@ __global__ void k_pair_offsets(const unsigned long long *zkey, unsigned long lon
 }
 
 struct SeedOut { DevWin *wins; DevZPair *anc; unsigned long long cap_wins, cap_anc; unsigned long long *cur_wins, *cur_anc, *overflow; };
-/* Window finding + chaining, one WARP per pair: the lanes stage the pair's match list in shared memory, lane 0 runs the
- * order-exact serial logic of zmo_seed_core.cuh on it (shared-memory latency instead of global), the lanes copy the
- * kept windows/anchors out.  Lists that do not fit the shared-memory budget run from global memory. */
+/* Window finding + chaining, one WARP per pair (zmo_seed_warp.cuh): the sliding scan runs on all lanes over register
+ * chunks of the match list, span searches are warp-cooperative with their sort keys / anchors staged in shared memory, the
+ * chain runs on lane 0, the lanes copy the kept windows/anchors out.  A span, window or strand that does not fit the
+ * shared-memory scratch is redone by lane 0 with the serial code of zmo_seed_core.cuh on global scratch. */
 #define PS_WARPS 22
 #define PS_MAXT 512       /* strand entries of one sliding span */
 #define PS_MAXW 96       /* sub-windows of one span */
 #define PS_STAGE 192      /* anchors of one window */
-#define PS_MAXWIN 64      /* windows of one strand */
-/* per-warp scratch in shared memory (~14.6 KB, 14 warps per SM: the serial lane is latency bound, so occupancy is what
- * buys throughput); larger spans / windows fall back to the global-memory scratch; the read-only match list is read through L1 */
+/* per-warp scratch in shared memory (~10 KB, 22 warps per SM at 80 registers: the scalar parts are latency bound, so occupancy
+ * is what buys throughput); larger spans / windows fall back to the global-memory scratch; the strand's windows live in the
+ * pair's global scratch; the read-only match list is read through register chunks (zmo_seed_warp.cuh) */
 struct PSSmem { uint64_t ts[PS_MAXT]; uint64_t ak[256]; DevZPair stage[PS_STAGE]; uint32_t wb[PS_MAXW], we[PS_MAXW], wo[PS_MAXW]; int bc[8]; };     /* as (median scratch) aliases ak: it is dead before the anchors are gathered */
 __global__ void __launch_bounds__(32 * PS_WARPS) k_p_seed(const unsigned long long *cache_off, uint32_t np, DevZPair *cache, const uint8_t *tie, const uint32_t *pc, DevReads R,
 		uint8_t *scratch, size_t per, uint32_t F, SeedPar par, SeedOut O, zmo_pairseed_t *seeds, unsigned long long *work){
@@ -182,7 +183,6 @@ __global__ void __launch_bounds__(32 * PS_WARPS) k_p_seed(const unsigned long lo
 			if(tie[p] && lane == 0){ GtZPairEmit g; g.clen = R.len[pc[p]]; zmo_ref_sort(rs, (size_t)n, g); zmo_ref_sort(rs, (size_t)n, GtZPairOff12()); }
 			__syncwarp();
 			uint8_t *scr = scratch + c0 * per + (size_t)64 * p;
-			const bool in_smem = true;
 			for(int d = 0; d < 2; d++){
 				PairScratch P = zmo_pair_scratch_carve(scr, n, F);
 				uint32_t nwin = 0; int ovf = 0, ovl = 0;
@@ -374,7 +374,7 @@ extern "C" int zmo_pair_windows(zmo_ctx *c, int slot, const zmo_pair_t *pairs, u
 		{
 			static bool attr_set = false;
 			if(!attr_set){ CUDA_TRY(cudaFuncSetAttribute(k_p_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PS_WARPS * sizeof(PSSmem)))); attr_set = true; }
-			const int grid = (int)std::min<uint64_t>((np + PS_WARPS - 1) / PS_WARPS, (uint64_t)c->n_sm);      /* one CTA of 8 warps per SM (shared-memory bound) */
+			const int grid = (int)std::min<uint64_t>((np + PS_WARPS - 1) / PS_WARPS, (uint64_t)c->n_sm);      /* one CTA of PS_WARPS warps per SM (shared-memory bound) */
 			k_p_seed<<<grid, 32 * PS_WARPS, PS_WARPS * sizeof(PSSmem), c->stream>>>(W.cache_off, np, W.cache, W.tie, W.pc, dev_reads(c), c->s6.as<uint8_t>(), per, F, par, O, SL.seeds.as<zmo_pairseed_t>(), ctr + CTR_WORK); c->launches++;
 		}
 		CUDA_TRY(cudaGetLastError());
