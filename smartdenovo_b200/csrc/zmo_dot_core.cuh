@@ -43,6 +43,10 @@ struct GtWinGrpBeg0 { ZMO_HDM bool operator()(const DevWin &a, const DevWin &b) 
 struct GtWinClosed { ZMO_HDM bool operator()(const DevWin &a, const DevWin &b) const { return a.closed > b.closed; } };
 struct GtWinBeg0 { ZMO_HDM bool operator()(const DevWin &a, const DevWin &b) const { return a.beg[0] > b.beg[0]; } };
 
+/* how the exact sort_array emulation is run: SerialSort = in place by the calling thread (host tests); the device kernel
+ * substitutes a sorter that stages the array in shared memory with the help of the other lanes of the warp */
+struct SerialSort { template<class T, class GT> ZMO_HDM void operator()(T *a, size_t n, GT gt) const { zmo_ref_sort(a, n, gt); } };
+
 ZMO_HDN void zmo_tidy_groups(uint32_t *g, uint32_t n){          /* hzm_aln.h:836-846 / 1016-1026 */
 	for(uint32_t i = 1; i < n; i++){
 		if(g[i] < i) continue;
@@ -55,7 +59,7 @@ ZMO_HDN void zmo_tidy_groups(uint32_t *g, uint32_t n){          /* hzm_aln.h:836
 
 /* hzm_aln.h:721-889 for one strand; rs is the (diagonal,off1)-sorted match list, gid[] its group ids
  * (zero on entry for this strand's entries).  Returns the number of blocks written to S.regs. */
-ZMO_HDN uint32_t zmo_denoise_strand(const DevZPair *rs, uint32_t n, int dir, const DotPar &par, DotScratch &S){
+template<class SORT> ZMO_HDN uint32_t zmo_denoise_strand(const DevZPair *rs, uint32_t n, int dir, const DotPar &par, DotScratch &S, const SORT &sorter){
 	const int xvar = par.xvar, yvar = par.yvar, min_len = par.min_block_len;
 	uint32_t i, j, k, doff, dcnt, gid, ndiag = 0, ngrp = 0, nblock, ndst = 0, nreg = 0; int lst_offset, end_offset, len;
 	/* packed sort keys of a diagonal bucket live in the (still unused) block region; those of the group sort in the node region */
@@ -88,7 +92,7 @@ ZMO_HDN uint32_t zmo_denoise_strand(const DevZPair *rs, uint32_t n, int dir, con
 				blk[nblock++] = ((uint64_t)q.off1 << 32) | (d.off + j);      /* sort key | index: the comparator reads no other memory */
 			}
 		}
-		zmo_ref_sort(blk, (size_t)nblock, GtHi32());
+		sorter(blk, (size_t)nblock, GtHi32());
 		if(nblock){
 			int p0_off1 = (int)(blk[0] >> 32), p0_len1 = (int)rs[(uint32_t)blk[0]].len1;
 			len = p0_len1; j = 0;
@@ -121,7 +125,7 @@ ZMO_HDN uint32_t zmo_denoise_strand(const DevZPair *rs, uint32_t n, int dir, con
 		gk[ndst].key = ((uint64_t)S.gid[i] << 32) | rs[i].off1; gk[ndst].idx = i; gk[ndst].pad = 0; ndst++;
 	}
 	/* (gid, off1) as one 64-bit key: the same comparison outcomes as the two-level comparator, hence the same permutation */
-	zmo_ref_sort(gk, (size_t)ndst, GtDotKey());
+	sorter(gk, (size_t)ndst, GtDotKey());
 	for(i = 0; i < ndst; i++){ S.dst[i].p = rs[gk[i].idx]; S.dst[i].gid = (uint32_t)(gk[i].key >> 32); }
 	j = 0;
 	for(i = 1; i <= ndst; i++){
@@ -245,14 +249,14 @@ ZMO_HDN int zmo_chain_blocks(int len1, int len2, DevWin *r, uint32_t n, int tail
 /* hzm_aln.h:1134-1181 for one pair.  presorted: 0 = cache is in the reference emission order (sort it here),
  * 1 = already sorted by (diagonal, off1) with no tied keys, 2 = sorted but with tied keys: rebuild the emission order
  * and run the exact sort so that the tie permutation equals the reference's */
-ZMO_HDN DotRes zmo_dot_pair(DevZPair *cache, uint32_t n, int alen, int blen, const DotPar &par, uint8_t *scratch, int presorted){
+template<class SORT> ZMO_HDN DotRes zmo_dot_pair(DevZPair *cache, uint32_t n, int alen, int blen, const DotPar &par, uint8_t *scratch, int presorted, const SORT &sorter){
 	DotScratch S = zmo_dot_scratch_carve(scratch, n);
 	DotRes best[2]; int weight[2];
-	if(presorted == 2){ GtZPairEmit g; g.clen = (uint32_t)blen; zmo_ref_sort(cache, (size_t)n, g); }
-	if(presorted != 1) zmo_ref_sort(cache, (size_t)n, GtZPairDiag());
+	if(presorted == 2){ GtZPairEmit g; g.clen = (uint32_t)blen; sorter(cache, (size_t)n, g); }
+	if(presorted != 1) sorter(cache, (size_t)n, GtZPairDiag());
 	for(uint32_t i = 0; i < n; i++) S.gid[i] = 0;
 	for(int d = 0; d < 2; d++){
-		uint32_t nreg = zmo_denoise_strand(cache, n, d, par, S);
+		uint32_t nreg = zmo_denoise_strand(cache, n, d, par, S, sorter);
 		nreg = zmo_merge_blocks(S.regs, nreg, par.xvar, 2 * par.yvar, S);
 		weight[d] = zmo_chain_blocks(alen, blen, S.regs, nreg, par.xvar, par.max_overhang, par.deviation_penalty, par.gap_penalty, S.nodes);
 		DotRes r; r.score = weight[d]; r.qb = r.tb = 0x7FFFFFFF; r.qe = r.te = 0; r.strand = d;
@@ -267,4 +271,7 @@ ZMO_HDN DotRes zmo_dot_pair(DevZPair *cache, uint32_t n, int alen, int blen, con
 		best[d] = r;
 	}
 	return best[weight[0] < weight[1]];
+}
+ZMO_HDN DotRes zmo_dot_pair(DevZPair *cache, uint32_t n, int alen, int blen, const DotPar &par, uint8_t *scratch, int presorted){
+	return zmo_dot_pair(cache, n, alen, blen, par, scratch, presorted, SerialSort());
 }
