@@ -61,7 +61,7 @@ class ClockSampler(threading.Thread):
         self.gpu, self.rows, self.stop_flag = gpu, [], False
 
     def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu"
         while not self.stop_flag:
             try:
                 r = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"], stdout=subprocess.PIPE, text=True, timeout=5)
@@ -75,7 +75,9 @@ class ClockSampler(threading.Thread):
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+        ut = sorted(int(r[6]) for r in self.rows if len(r) > 6 and r[6].isdigit())
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows),
+                "gpu_util_pct_median": ut[len(ut) // 2] if ut else None}
 
 
 def run_reference(fa, flags, n_job, i_job, threads, outdir, tag):
