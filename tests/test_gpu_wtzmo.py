@@ -163,8 +163,17 @@ def test_edge_reads(tmp_path, oracle_bin):
     with open(fq, "w") as f:
         for n, s in enumerate(recs):
             f.write("@t%d x\n%s\n+\n%s\n" % (n, s, "I" * len(s)))
+    # lower case, non-ACGT bases (lrand48() & 3 in file order, dna.h:405) and gzip input (file_reader.c:66-72)
+    fn = tmp_path / "mixed.fa"
+    with open(fn, "w") as f:
+        for n, s in enumerate(recs):
+            t = list(s.lower() if n % 3 == 0 else s)
+            for k in range(7, len(t), 401):
+                t[k] = "N" if n % 2 else "n"
+            f.write(">t%d\n%s\n" % (n, "".join(t)))
+    subprocess.run(["gzip", "-kf", str(fn)], check=True)
     extra = ["-k", "16", "-s", "100", "-m", "0.5", "-r", "200", "-R", "100", "-d", "100"]
-    for src in (fa, fq):
+    for src in (fa, fq, fn, str(fn) + ".gz"):
         _run(_checker(oracle_bin), str(src), str(tmp_path / "ref.ovl"), extra)
         _run(EXE, str(src), str(tmp_path / "gpu.ovl"), extra)
         ref = open(tmp_path / "ref.ovl", "rb").read()
