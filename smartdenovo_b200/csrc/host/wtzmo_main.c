@@ -364,7 +364,7 @@ typedef struct { hitv hits; u32v masks; u64v closed; seedv seeds; u32 rd_id; } r
  * batch boundary, because the reference tests masked[next read] BEFORE merging the previous read's
  * masks (wtzmo.c:1315 vs 1322) */
 static void flush_read(wz_t *z, readout_t *ro, int defer_masks){
-	size_t i, k; const readset_t *rs = &z->rs;
+	size_t i; const readset_t *rs = &z->rs;
 	if(!z->par.do_align){   /* -N: seed lines only (wtzmo.c:1176-1181) */
 		for(i=0;i<ro->seeds.n;i++){
 			seed_t *s = &ro->seeds.a[i];
