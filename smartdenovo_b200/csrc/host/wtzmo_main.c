@@ -373,7 +373,8 @@ static void flush_read(wz_t *z, readout_t *ro, int defer_masks){
 			z->obuf_n += sprintf(z->obuf + z->obuf_n, "# %s\t%c\t%d\t%s\t%c\t%d\t%d\n", rs->reads.a[ro->rd_id].name, '+', rs->reads.a[ro->rd_id].len, rs->reads.a[s->pb2].name, "+-"[s->dir], rs->reads.a[s->pb2].len, s->ovl);
 		}
 	}
-	for(i=0;i<ro->hits.n;i++){
+	/* with -N the reference prints hits only in step with the seed list (wtzmo.c:1176-1186): no seeds (dot-matrix mode) = no output, no rdcovs */
+	for(i=0;z->par.do_align&&i<ro->hits.n;i++){
 		hit_t *h = &ro->hits.a[i]; u32 x1, x2; int l1 = rs->reads.a[h->pb1].len, l2 = rs->reads.a[h->pb2].len; char *p;
 		if(h->aln == 0) h->aln = 1;
 		x1 = imin(h->tb, h->qb); x2 = imin(l1 - h->te, l2 - h->qe);

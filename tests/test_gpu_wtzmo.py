@@ -82,6 +82,16 @@ def test_sw_job_shard_and_partitioned_index(tmp_path, gen_reads, oracle_bin):
     _compare(tmp_path, gen_reads, oracle_bin, ["-n", "300", "-L", "5000", "-G", "70000", "-s", "11"], ["-k", "16", "-G", "2"])
 
 
+def test_dot_matrix_with_seed_only_flag_prints_nothing(tmp_path, gen_reads, oracle_bin):
+    """-U with -N: the reference prints hits only in step with the (empty) seed list (wtzmo.c:1176-1186)"""
+    fa = str(tmp_path / "reads.fa")
+    subprocess.run([gen_reads, "-n", "200", "-L", "4000", "-G", "60000", "-s", "7", "-m", "ont", "-o", fa], check=True)
+    extra = ["-k", "16", "-z", "10", "-Z", "16", "-U", "-1", "-m", "0.1", "-N"]
+    _run(_checker(oracle_bin), fa, str(tmp_path / "ref.ovl"), extra)
+    _run(EXE, fa, str(tmp_path / "gpu.ovl"), extra)
+    assert open(tmp_path / "ref.ovl", "rb").read() == open(tmp_path / "gpu.ovl", "rb").read() == b""
+
+
 def test_seed_only_mode(tmp_path, gen_reads, oracle_bin):
     _compare(tmp_path, gen_reads, oracle_bin, ["-n", "200", "-L", "5000", "-G", "60000", "-s", "5"], ["-N", "-k", "16"])
 

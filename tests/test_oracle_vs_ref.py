@@ -21,6 +21,7 @@ CASES = {
     "seeds": (["-n", "150", "-L", "4000", "-G", "50000", "-s", "5"], ["-N", "-k", "16"]),
     "refine": (["-n", "150", "-L", "5000", "-G", "50000", "-s", "3"], ["-k", "16", "-s", "200", "-m", "0.6", "-n"]),
     "refine_ont": (["-n", "150", "-L", "4000", "-G", "60000", "-s", "17", "-m", "ont"], ["-k", "16", "-n", "-w", "20"]),
+    "dot_seeds_only": (["-n", "200", "-L", "4000", "-G", "60000", "-s", "7", "-m", "ont"], ["-k", "16", "-z", "10", "-Z", "16", "-U", "-1", "-m", "0.1", "-N"]),
     "params": (["-n", "150", "-L", "4000", "-G", "50000", "-s", "11"], ["-k", "15", "-S", "2", "-z", "12", "-Z", "32", "-y", "600", "-R", "150", "-r", "250", "-w", "30", "-e", "300", "-W", "800", "-m", "0.55", "-s", "150", "-A", "50", "-B", "20"]),
 }
 
