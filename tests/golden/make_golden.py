@@ -25,5 +25,12 @@ with tempfile.TemporaryDirectory() as d:
         subprocess.run([gen] + gen_args + ["-o", fa], check=True)
         t._run(ref, fa, os.path.join(d, case + ".ovl"), extra)
         out[case] = t._digest(os.path.join(d, case + ".ovl"))
+    import pathlib
+    for case in t.SIDE_CASES:
+        sub = pathlib.Path(d) / case
+        sub.mkdir()
+        fa, extra = t._side_inputs(sub, gen, case)
+        t._run(ref, fa, str(sub / "ref.ovl"), extra)
+        out[case] = t._digest(str(sub / "ref.ovl"))
 json.dump(out, open(os.path.join(HERE, "ovl_digests.json"), "w"), indent=1, sort_keys=True)
 print(json.dumps(out, indent=1))

@@ -26,6 +26,42 @@ CASES = {
 }
 
 
+# side inputs of wtzmo.c:1732-1769: -L tried pairs, -F excluded reads, -b clip table (applied after the length sort), -I query-only reads,
+# -J minimum length, -C (only suppresses the .contained file, wtzmo.c:1781)
+SIDE_GEN = ["-n", "250", "-L", "5000", "-G", "70000", "-s", "21"]
+SIDE_CASES = ["side_L", "side_F", "side_b", "side_I", "side_J", "side_C"]
+
+
+def _side_inputs(tmp_path, gen_reads, case):
+    """writes the read set and the side file of one case; returns (fasta, extra wtzmo arguments)"""
+    fa = str(tmp_path / "base.fa")
+    subprocess.run([gen_reads] + SIDE_GEN + ["-o", fa], check=True)
+    names = [l[1:].strip() for l in open(fa) if l.startswith(">")]
+    seqs = [l.strip() for l in open(fa) if not l.startswith(">")]
+    base = ["-k", "16", "-s", "200", "-m", "0.6"]
+    if case == "side_L":
+        with open(tmp_path / "L.pairs", "w") as f:
+            for i in range(0, 60, 2):
+                f.write("%s\t%s\n" % (names[i], names[i + 1]))
+        return fa, base + ["-L", str(tmp_path / "L.pairs")]
+    if case == "side_F":
+        with open(tmp_path / "F.names", "w") as f:
+            f.write("# comment\n" + "\n".join(names[5:25]) + "\n")
+        return fa, base + ["-F", str(tmp_path / "F.names")]
+    if case == "side_b":
+        with open(tmp_path / "B.clip", "w") as f:
+            for i in range(0, 250, 9):
+                f.write("%s\t%d\t%d\t%d\n" % (names[i], 100, len(seqs[i]) - 300, len(seqs[i])))
+        return fa, base + ["-b", str(tmp_path / "B.clip")]
+    if case == "side_I":
+        q = str(tmp_path / "q.fa")
+        subprocess.run([gen_reads, "-n", "30", "-L", "4000", "-G", "70000", "-s", "21", "-o", q], check=True)
+        return fa, base + ["-I", q]
+    if case == "side_J":
+        return fa, base + ["-J", "4500"]
+    return fa, base + ["-C"]
+
+
 def _run(exe, fa, out, extra):
     r = subprocess.run([exe, "-t", "1", "-i", fa, "-f", "-o", out, "-9", out + ".pairs"] + extra, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 0, r.stderr[-1000:]
@@ -57,5 +93,24 @@ def test_oracle_matches_golden_digest(case, tmp_path, gen_reads, oracle_bin):
     gen_args, extra = CASES[case]
     fa = str(tmp_path / "r.fa")
     subprocess.run([gen_reads] + gen_args + ["-o", fa], check=True)
+    _run(oracle_bin, fa, str(tmp_path / "orc.ovl"), extra)
+    assert _digest(str(tmp_path / "orc.ovl")) == gold[case]
+
+
+@pytest.mark.parametrize("case", SIDE_CASES)
+def test_oracle_side_inputs_match_reference_binary(case, tmp_path, gen_reads, oracle_bin, ref_bin):
+    fa, extra = _side_inputs(tmp_path, gen_reads, case)
+    _run(ref_bin, fa, str(tmp_path / "ref.ovl"), extra)
+    _run(oracle_bin, fa, str(tmp_path / "orc.ovl"), extra)
+    assert open(tmp_path / "ref.ovl", "rb").read() == open(tmp_path / "orc.ovl", "rb").read()
+    assert os.path.exists(tmp_path / "ref.ovl.contained") == os.path.exists(tmp_path / "orc.ovl.contained") == (case != "side_C")
+    assert _digest(str(tmp_path / "ref.ovl")) == _digest(str(tmp_path / "orc.ovl"))
+
+
+@pytest.mark.parametrize("case", SIDE_CASES)
+def test_oracle_side_inputs_match_golden_digest(case, tmp_path, gen_reads, oracle_bin):
+    """golden digests were produced by the reference binary (tests/golden/make_golden.py)"""
+    gold = json.load(open(GOLDEN))
+    fa, extra = _side_inputs(tmp_path, gen_reads, case)
     _run(oracle_bin, fa, str(tmp_path / "orc.ovl"), extra)
     assert _digest(str(tmp_path / "orc.ovl")) == gold[case]
