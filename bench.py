@@ -257,11 +257,14 @@ def main():
     alg_bytes = 0.5 * groups[dom][1]
     achieved = alg_bytes / dom_s / 1e9 if dom_s > 0 else 0.0
     roof = {"bound": "hbm", "kernel": groups[dom][2],
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+            # DRAM bytes (read + write) of ONE captured launch of the group's kernel: ncu --set full, profiles/r01_ncu_final.md
+            # (k_window_align launch id 0: 144.5 + 233.3 MB; k_ext_cta<128,13,1>: 26.2 + 207.4 MB); see traffic_profile for its algorithmic bytes
+            "traffic": {"window_align": 377.8e6, "dp_phase": 233.6e6}[dom],
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
             "alg_bytes_per_cell": 0.5, "cells_per_step": groups[dom][1] / args.steps, "kernel_ms_per_step": groups[dom][0] / args.steps,
             "gcells_per_s": groups[dom][1] / dom_s / 1e9 if dom_s > 0 else 0.0,
-            "traffic_profile": {"kernel": "k_window_align", "dram_bytes_per_launch": 379.9e6, "launch_ms": 17.7, "alg_bytes_per_launch_est": 0.85e9,
+            "traffic_profile": {"kernel": "k_window_align", "dram_bytes_per_launch": 377.8e6, "launch_ms": 17.7, "alg_bytes_per_launch_est": 0.85e9,
                                 "source": "profiles/r01_ncu_final.md (ncu --set full, one launch on the cfg2s shard; short bridges keep their traceback in shared memory)"},
             "note": "integer DP is ALU/latency bound, not HBM bound (see DESIGN.md): gcells_per_s is the number to optimise; kernel time = CUDA-event stage time summed over the contexts in flight"}
     line = {"metric": metric, "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
