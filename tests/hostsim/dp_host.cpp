@@ -1,0 +1,108 @@
+/*
+ * TEST-ONLY host simulation of the DP executor kernels (smartdenovo_b200/csrc/zmo_dp_kernels.cuh with zmo_jobs.cuh,
+ * zmo_dpr.cuh, zmo_dp.cuh underneath): the kernels are compiled for the host against tests/hostsim/emu/cuda_runtime.h and
+ * every thread block runs as cooperative fibers, so the CPU-only test-suite executes the source the sm_100a kernels
+ * are built from -- register-resident sweeps, warp shuffles, reductions, barriers, traceback walk -- and compares it with
+ * the oracle.  Never linked into libzmo_b200.so or wtzmo.
+ *
+ * build: g++ -O1 -std=c++17 -Itests/hostsim/emu -fPIC -shared tests/hostsim/dp_host.cpp
+ */
+#include "cuda_runtime.h"
+#include <string>
+thread_local std::string g_zmo_err;
+int zmo_set_err(int code, const char *, ...){ return code; }
+namespace emu { Block *g_blk = nullptr; }
+#include "../../smartdenovo_b200/csrc/zmo_dp_kernels.cuh"
+
+/* two reads in the device layout: 16 bases per uint32, MSB first, per read 16-byte aligned, spare words behind */
+struct SimReads {
+	std::vector<uint32_t> words; uint64_t woff[2]; uint32_t len[2];
+	SimReads(const uint8_t *a, int na, const uint8_t *b, int nb){
+		const uint8_t *s[2] = {a, b}; const int n[2] = {na, nb};
+		for(int r = 0; r < 2; r++){
+			woff[r] = words.size(); len[r] = (uint32_t)n[r];
+			size_t nw = ((size_t)(n[r] + 15) / 16 + 4 + 3) & ~(size_t)3;
+			words.resize(words.size() + nw, 0u);
+			for(int i = 0; i < n[r]; i++) words[woff[r] + (i >> 4)] |= (uint32_t)(s[r][i] & 3) << (((~i) & 15) << 1);
+		}
+	}
+	DevReads dev() const { DevReads R; R.words = words.data(); R.woff = woff; R.len = len; R.n = 2; return R; }
+};
+
+static void fill_out(const DPRes &r, std::vector<uint32_t> &cg, int *out10, uint32_t *cig, int cig_cap){
+	out10[0] = r.score; out10[1] = 0; out10[2] = r.te; out10[3] = 0; out10[4] = r.qe; out10[5] = r.mat + r.mis + r.ins + r.del;
+	out10[6] = r.mat; out10[7] = r.mis; out10[8] = r.ins; out10[9] = r.del;
+	/* kernels emit the CIGAR in walk order (end -> start); flip it like zmo_dp.cu's dp_batch does */
+	for(int k = 0; k < r.ncig && k < cig_cap; k++) cig[k] = cg[r.ncig - 1 - k];
+}
+
+/*
+ * One extension problem (q = rows, t = columns; both given as 0..3 codes in logical order) through the kernel of executor
+ * class `cls` (-1: the class ext_class() picks, as the product does; a larger class than needed is legal, a smaller one is
+ * not).  copies > 1 queues the same job several times on a 2-CTA grid so that the work-counter loop of the persistent
+ * executors runs as well.  Returns the number of CIGAR ops; out10 mirrors ref_shim's layout (conftest.call_ext).
+ */
+extern "C" int sim_dp_extend(int mode, int cls, int copies, const uint8_t *q, int qlen, const uint8_t *t, int tlen, int init, int Wp,
+		int M, int X, int O, int E, int T, int *out10, uint32_t *cig, int cig_cap){
+	DPPar P; P.M = M; P.X = X; P.I = O; P.D = O; P.E = E; P.T = T;
+	SimReads rd(q, qlen, t, tlen); DevReads R = rd.dev();
+	BandDims d; d.W = 0; d.ql = d.tl = d.ncol = 0;
+	const int init0 = init < 0? 0 : init;
+	if(qlen > 0 && tlen > 0) d = band_dims(qlen, tlen, init0, Wp, P);
+	const int need = ext_class(d.ncol);
+	if(cls < 0) cls = need;
+	if(cls < need) return -1;
+	if(copies < 1) copies = 1;
+	std::vector<DPJob> jobs(copies); std::vector<DPRes> res(copies); unsigned long long scratch = 0, cigw = 0;
+	for(int k = 0; k < copies; k++){
+		DPJob J; memset(&J, 0, sizeof(J));
+		J.q_rid = 0; J.t_rid = 1; J.q_start = 0; J.q_step = 1; J.q_comp = 0; J.qlen = qlen; J.t_start = 0; J.t_step = 1; J.t_comp = 0; J.tlen = tlen;
+		J.init = init; J.Wp = Wp; J.out_idx = (uint32_t)k; J.cig_off = cigw; J.cig_cap = (uint32_t)(qlen + tlen + 4); cigw += J.cig_cap;
+		J.scratch = scratch;
+		/* the widest layout any class may use for this band, so that forcing a larger class stays inside the job's scratch */
+		unsigned long long sw = 0; for(int c2 = need; c2 <= 3; c2++) sw = std::max(sw, ext_scratch_words_cls(d, c2));
+		scratch += sw + 64;
+		jobs[k] = J;
+	}
+	std::vector<uint32_t> arena(scratch + 64, 0xDEADBEEFu), cg(cigw + 16, 0u);
+	unsigned long long ctr[4] = {0, 0, 0, 0};
+	DPSlab SB; SB.base = 0; SB.off = nullptr;
+	const uint32_t n = (uint32_t)copies;
+	const DPJob *dj = jobs.data(); DPRes *dr = res.data(); uint32_t *ar = arena.data(), *cgp = cg.data(); unsigned long long *cp = ctr;
+	const unsigned grid = copies > 1? 2u : 1u;
+#define EXT_LAUNCH(KERNEL, NT) emu::launch(grid, NT, [=](){ KERNEL(dj, nullptr, n, R, P, ar, SB, cgp, dr, cp, 0, 1); })
+	if(cls == 0){ if(mode) EXT_LAUNCH((k_ext_warp<1>), 32 * WRP_PER_CTA); else EXT_LAUNCH((k_ext_warp<0>), 32 * WRP_PER_CTA); }
+	else if(cls == 1){ if(mode) EXT_LAUNCH((k_ext_cta<64, 7, 1>), 64); else EXT_LAUNCH((k_ext_cta<64, 7, 0>), 64); }
+	else if(cls == 2){ if(mode) EXT_LAUNCH((k_ext_cta<128, 7, 1>), 128); else EXT_LAUNCH((k_ext_cta<128, 7, 0>), 128); }
+	else { if(mode) EXT_LAUNCH((k_ext_cta<CL3_NT, CL3_C, 1>), CL3_NT); else EXT_LAUNCH((k_ext_cta<CL3_NT, CL3_C, 0>), CL3_NT); }
+#undef EXT_LAUNCH
+	for(int k = 1; k < copies; k++){
+		if(memcmp(&res[k], &res[0], sizeof(DPRes))) return -2;
+		if(memcmp(cg.data() + jobs[k].cig_off, cg.data(), sizeof(uint32_t) * (size_t)std::max(res[0].ncig, 0))) return -3;
+	}
+	fill_out(res[0], cg, out10, cig, cig_cap);
+	out10[1] = (int)(ctr[1] / (unsigned long long)copies);      /* DP cells of one job, as the kernels count them */
+	return res[0].ncig;
+}
+
+/* ksw_global2 with first band w (the kernels run the reference's `w < |qlen - tlen|` doubling; wmax > 0 also the score < 0 retry):
+ * wide = 0: k_glb_warp, 1: k_glb_cta.  Returns the number of CIGAR ops, *score and *w_used. */
+extern "C" int sim_dp_global(int wide, const uint8_t *q, int qlen, const uint8_t *t, int tlen, int M, int X, int O, int E, int w, int wmax,
+		int *score, int *w_used, int *cnt4, uint32_t *cig, int cig_cap){
+	DPPar P; P.M = M; P.X = X; P.I = O; P.D = O; P.E = E; P.T = 0;
+	SimReads rd(q, qlen, t, tlen); DevReads R = rd.dev();
+	DPJob J; memset(&J, 0, sizeof(J));
+	J.q_rid = 0; J.t_rid = 1; J.q_step = 1; J.t_step = 1; J.qlen = qlen; J.tlen = tlen; J.Wp = w; J.Wmax = wmax; J.cig_cap = (uint32_t)(qlen + tlen + 4);
+	const unsigned long long sw = wide? glb_scratch_words<EXT_NT, EXT_C>(qlen, tlen, EXT_CAP) : glb_scratch_words<32, WRP_C>(qlen, tlen, WRP_CAP);
+	std::vector<uint32_t> arena(sw + 64, 0xDEADBEEFu), cg(J.cig_cap + 16, 0u);
+	DPRes res; memset(&res, 0, sizeof(res));
+	unsigned long long ctr[4] = {0, 0, 0, 0};
+	DPSlab SB; SB.base = 0; SB.off = nullptr;
+	const DPJob *dj = &J; DPRes *dr = &res; uint32_t *ar = arena.data(), *cgp = cg.data(); unsigned long long *cp = ctr;
+	if(wide) emu::launch(1, EXT_NT, [=](){ k_glb_cta(dj, nullptr, 1u, R, P, ar, SB, cgp, dr, cp, 0, 1); });
+	else emu::launch(1, 32 * WRP_PER_CTA, [=](){ k_glb_warp(dj, nullptr, 1u, R, P, ar, SB, cgp, dr, cp, 0, 1); });
+	*score = res.score; *w_used = res.w_used;
+	cnt4[0] = res.mat; cnt4[1] = res.mis; cnt4[2] = res.ins; cnt4[3] = res.del;
+	for(int k = 0; k < res.ncig && k < cig_cap; k++) cig[k] = cg[res.ncig - 1 - k];
+	return res.ncig;
+}

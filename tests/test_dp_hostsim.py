@@ -1,0 +1,173 @@
+"""CPU: the product's DP executor KERNELS (smartdenovo_b200/csrc/zmo_dp_kernels.cuh: k_ext_warp, k_ext_cta<64|128,7>,
+k_ext_cta<128,13>, k_glb_warp, k_glb_cta, with the register-resident sweeps of zmo_dpr.cuh and the shared/global-row
+fallback of zmo_dp.cuh underneath) compiled for the host by tests/hostsim (test-only; thread blocks run as cooperative
+fibers, warp collectives and barriers emulated) against the oracle: score, end point, counts and CIGAR bit-exact.
+The same comparisons run on the real device in tests/test_gpu_dp.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import REPO, call_ext, call_global, mutate
+
+SC = (2, -5, -3, -1, -50)   # -M -X -O -E -T defaults (wtzmo.c:1574-1578)
+
+
+@pytest.fixture(scope="module")
+def dp_sim():
+    out = os.path.join(REPO, "tests", "_build", "libdp_host.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I" + os.path.join(REPO, "tests", "hostsim", "emu"), "-fPIC", "-shared", "-o", out,
+                    os.path.join(REPO, "tests", "hostsim", "dp_host.cpp")], check=True)
+    return C.CDLL(out)
+
+
+def sim_ext(sim, mode, cls, copies, q, t, init, W, sc=SC):
+    q = np.ascontiguousarray(q, np.uint8)
+    t = np.ascontiguousarray(t, np.uint8)
+    out = (C.c_int * 10)()
+    cap = len(q) + len(t) + 8
+    cig = (C.c_uint32 * cap)()
+    M, X, O, E, T = sc
+    n = sim.sim_dp_extend(mode, cls, copies, q.ctypes.data_as(C.c_void_p), len(q), t.ctypes.data_as(C.c_void_p), len(t), init, W, M, X, O, E, T, out, cig, cap)
+    assert n >= 0, "simulation refused the problem (%d)" % n
+    out = list(out)
+    cells, out[1] = out[1], 0
+    return out, list(cig[:n]), cells
+
+
+def check_ext(sim, orc, mode, cls, q, t, init, W, sc=SC, copies=1):
+    got, gcig, cells = sim_ext(sim, mode, cls, copies, q, t, init, W, sc)
+    M, X, O, E, T = sc
+    exp, ecig = call_ext(orc, "orc_extend", mode, q, t, init, W, sc=(M, X, O, O, E, T))
+    assert got == exp, (mode, cls, len(q), len(t), init, W, got, exp)
+    assert gcig == ecig, (mode, cls, len(q), len(t), init, W)
+    return cells
+
+
+def related(rng, n, err=1.0, shift=0):
+    """a noisy copy pair: q = genome slice, t = mutated copy (PacBio-like profile scaled by err)"""
+    g = rng.integers(0, 4, n + abs(shift) + 50).astype(np.uint8)
+    q = g[:n]
+    t = mutate(rng, g[max(shift, 0): max(shift, 0) + n], ins=0.0825 * err, dele=0.045 * err, sub=0.0225 * err)
+    return q, t
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_kernels_by_executor_class(dp_sim, oracle_lib, mode):
+    """every executor class on bands it serves: warp x 7 (<= 211 columns), 64 x 7 (<= 435), 128 x 7 (<= 883), 128 x 13 (<= 1639)"""
+    rng = np.random.default_rng(10 + mode)
+    total = 0
+    for cls, Ws, nmax in ((0, [-3, -20, -50, -105, 50], 500), (1, [-120, -217], 420), (2, [-250, -441], 380), (3, [-500, -819], 330)):
+        for W in Ws:
+            for rep in range(2):
+                n = int(rng.integers(nmax // 2, nmax))
+                q, t = related(rng, n, err=float(rng.choice([0.3, 1.0])))
+                total += check_ext(dp_sim, oracle_lib, mode, -1, q, t, int(rng.choice([0, 0, 150])), W)
+    assert total > 10 ** 6
+
+
+def test_band_wider_than_the_register_executors(dp_sim, oracle_lib):
+    """> 1639 columns: the class-3 kernel falls back to the chunked sweep with H/E rows in shared (2W+3 <= 4096... per kernel) or global memory"""
+    rng = np.random.default_rng(5)
+    q, t = related(rng, 2100, err=0.5)
+    for mode in (0, 1):
+        check_ext(dp_sim, oracle_lib, mode, -1, q[:260], t, 0, -900)
+        check_ext(dp_sim, oracle_lib, mode, -1, q[:200], t, 0, -1500)
+
+
+def test_larger_class_gives_the_same_bytes(dp_sim, oracle_lib):
+    """a band may run on any executor class that holds it (the pipeline's class choice is a performance decision only)"""
+    rng = np.random.default_rng(6)
+    q, t = related(rng, 300)
+    for mode in (0, 1):
+        for cls in (0, 1, 2, 3):
+            check_ext(dp_sim, oracle_lib, mode, cls, q, t, 0, -40)
+
+
+def test_persistent_executor_loop(dp_sim, oracle_lib):
+    """several jobs on a 2-CTA grid: the first job of an executor is its own index, the rest come from the work counter"""
+    rng = np.random.default_rng(7)
+    q, t = related(rng, 200)
+    for cls, copies in ((0, 11), (1, 5), (3, 4)):
+        check_ext(dp_sim, oracle_lib, 1, cls, q, t, 0, -30, copies=copies)
+
+
+def test_end_rules_and_degenerate_shapes(dp_sim, oracle_lib):
+    """early termination (row maximum <= 0), the T rule (kswx.h:200-204), W > 0 clamped by max_gap (kswx.h:115-121), length
+    truncation, negative init, 1 x n and n x 1, unrelated sequences, other scoring parameters"""
+    rng = np.random.default_rng(8)
+    q, t = related(rng, 400)
+    u = rng.integers(0, 4, 400).astype(np.uint8)
+    for mode in (0, 1):
+        check_ext(dp_sim, oracle_lib, mode, -1, q, u, 0, -50)                 # unrelated: stops after a few rows
+        check_ext(dp_sim, oracle_lib, mode, -1, q, u, 300, -50)
+        check_ext(dp_sim, oracle_lib, mode, -1, q, t, -9, 50)                 # negative init clamps to 0; W > 0
+        check_ext(dp_sim, oracle_lib, mode, -1, q, t, 3000, 800)
+        check_ext(dp_sim, oracle_lib, mode, -1, q[:1], t, 0, -800)
+        check_ext(dp_sim, oracle_lib, mode, -1, q, t[:1], 100, -800)
+        check_ext(dp_sim, oracle_lib, mode, -1, q[:1], t[:1], 0, -1)
+        check_ext(dp_sim, oracle_lib, mode, -1, q[:120], t, 0, -30)           # tl truncated to ql + W
+        check_ext(dp_sim, oracle_lib, mode, -1, q, t[:120], 0, -30)           # ql truncated to tl + W
+        check_ext(dp_sim, oracle_lib, mode, -1, q, np.concatenate([t[:200], u[:150]]), 0, -60)   # good prefix, then noise
+        for sc in ((1, -2, -2, -1, -20), (3, -7, -6, -2, -100), (2, -5, -3, -1, 0)):
+            check_ext(dp_sim, oracle_lib, mode, -1, q, t, 0, -45, sc=sc)
+    lowc = np.repeat(rng.integers(0, 4, 150), 3).astype(np.uint8)             # homopolymer triples: many score ties
+    for mode in (0, 1):
+        check_ext(dp_sim, oracle_lib, mode, -1, lowc, lowc[3:], 0, 50)
+        check_ext(dp_sim, oracle_lib, mode, -1, lowc, mutate(rng, lowc), 0, -25)
+
+
+def sim_glb(sim, wide, q, t, w, wmax=0, sc=(2, -5, -3, -1)):
+    q = np.ascontiguousarray(q, np.uint8)
+    t = np.ascontiguousarray(t, np.uint8)
+    score, wused = C.c_int(0), C.c_int(0)
+    cnt = (C.c_int * 4)()
+    cap = len(q) + len(t) + 8
+    cig = (C.c_uint32 * cap)()
+    M, X, O, E = sc
+    n = sim.sim_dp_global(wide, q.ctypes.data_as(C.c_void_p), len(q), t.ctypes.data_as(C.c_void_p), len(t), M, X, O, E, w, wmax, C.byref(score), C.byref(wused), cnt, cig, cap)
+    return score.value, wused.value, list(cnt), list(cig[:n])
+
+
+def check_glb(sim, orc, wide, q, t, w, wmax=0):
+    score, wused, cnt, cig = sim_glb(sim, wide, q, t, w, wmax)
+    ww = w
+    while True:       # hzm_aln.h:1400-1418: widen until the band holds the length difference, then while the score is negative
+        while ww < abs(len(q) - len(t)):
+            ww <<= 1
+        escore, ecig = call_global(orc, "orc_global2", q, t, ww, sc=(2, -5, 3, 1, 3, 1))
+        if wmax > 0 and escore < 0 and ww < wmax and ww < max(len(q), len(t)):
+            ww <<= 1
+        else:
+            break
+    assert (score, wused) == (escore, ww), (wide, len(q), len(t), w, wmax)
+    assert cig == ecig, (wide, len(q), len(t), w)
+    x1 = x2 = mat = mis = ins = dele = 0
+    for op in ecig:
+        ln, o = op >> 4, op & 15
+        if o == 0:
+            same = int((q[x1:x1 + ln] == t[x2:x2 + ln]).sum())
+            mat += same; mis += ln - same; x1 += ln; x2 += ln
+        elif o == 1:
+            ins += ln; x1 += ln
+        else:
+            dele += ln; x2 += ln
+    assert cnt == [mat, mis, ins, dele]
+
+
+def test_gap_kernels(dp_sim, oracle_lib):
+    """ksw_global2 through k_glb_warp (1/2/4/7 columns per lane by band width) and k_glb_cta, with the reference's band doubling"""
+    rng = np.random.default_rng(9)
+    for n, w in ((30, 50), (60, 7), (150, 50), (250, 100), (400, 50), (420, 400)):
+        q, t = related(rng, n)
+        check_glb(dp_sim, oracle_lib, 0, q, t, w)
+    q, t = related(rng, 300)
+    check_glb(dp_sim, oracle_lib, 0, q[:200], t, 7)                 # band doubles until it holds the length difference
+    check_glb(dp_sim, oracle_lib, 0, q, rng.integers(0, 4, 280).astype(np.uint8), 8, wmax=3200)   # negative score: retry with 2w
+    for n, w in ((500, 300), (700, 400)):
+        q, t = related(rng, n, err=0.5)
+        check_glb(dp_sim, oracle_lib, 1, q, t, w)
+    check_glb(dp_sim, oracle_lib, 1, q[:40], t[:60], 50)            # small problem on the wide kernel
