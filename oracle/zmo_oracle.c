@@ -1815,5 +1815,20 @@ int orc_pair_dotmatrix(u8 *pb1, int alen, u8 *pb2, int blen, int zsize, int hz, 
 	vec_free(cache); vec_free(zi.seeds); vec_free(zi.slots);
 	return n;
 }
-/* full pair alignment on explicit windows/anchors is exercised through the whole-program runs */
+/* one window of orc_pair_windows' output through the per-window anchored alignment (fast_seeds_align_hzmo, hzm_aln.h:1247-1302):
+ * pb2 is c on the window's strand (reverse-complemented by the caller for strand 1), anc = n_anc x {off1, off2, len1, len2, dir1, dir2}.
+ * out = score, tb, te, qb, qe, aln, mat, mis, ins, del; returns the number of CIGAR ops. */
+int orc_window_align(u8 *pb1, u8 *pb2, const int *anc, int n_anc, int w, int M, int X, int O, int E, int T, int *out, u32 *cigar_out, int cigar_cap){
+	zparams_t par = orc_par(10, 1, 64, 2, 800, 400, 200, 300, 3200);
+	win_t win; zpair_t *a = malloc(sizeof(zpair_t) * (size_t)(n_anc > 0? n_anc : 1)); u32v cg; aln_t x; int i, n;
+	par.w = w; par.M = M; par.X = X; par.O = O; par.E = E; par.T = T;
+	memset(&win, 0, sizeof(win)); win.anc[0] = 0; win.anc[1] = (u32)n_anc;
+	for(i=0;i<n_anc;i++){ zpair_t *p = &a[i]; const int *o = anc + 6 * i; memset(p, 0, sizeof(*p)); p->off1 = o[0]; p->off2 = o[1]; p->len1 = o[2]; p->len2 = o[3]; p->dir1 = o[4]; p->dir2 = o[5]; }
+	vec_init(cg);
+	x = window_align(pb1, pb2, &win, a, &cg, &par);
+	out[0]=x.score; out[1]=x.tb; out[2]=x.te; out[3]=x.qb; out[4]=x.qe; out[5]=x.aln; out[6]=x.mat; out[7]=x.mis; out[8]=x.ins; out[9]=x.del;
+	n = (int)cg.n; for(i=0;i<n&&i<cigar_cap;i++) cigar_out[i] = cg.a[i];
+	vec_free(cg); free(a); return n;
+}
+/* full pair alignment (stitching, gaps, end extensions) is exercised through the whole-program runs */
 #endif

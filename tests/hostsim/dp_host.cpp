@@ -1,6 +1,6 @@
 /*
- * TEST-ONLY host simulation of the DP executor kernels (smartdenovo_b200/csrc/zmo_dp_kernels.cuh with zmo_jobs.cuh,
- * zmo_dpr.cuh, zmo_dp.cuh underneath): the kernels are compiled for the host against tests/hostsim/emu/cuda_runtime.h and
+ * TEST-ONLY host simulation of the DP executor kernels (smartdenovo_b200/csrc/zmo_dp_kernels.cuh and zmo_winalign.cuh with
+ * zmo_jobs.cuh, zmo_dpr.cuh, zmo_dp.cuh underneath): the kernels are compiled for the host against tests/hostsim/emu/cuda_runtime.h and
  * every thread block runs as cooperative fibers, so the CPU-only test-suite executes the source the sm_100a kernels
  * are built from -- register-resident sweeps, warp shuffles, reductions, barriers, traceback walk -- and compares it with
  * the oracle.  Never linked into libzmo_b200.so or wtzmo.
@@ -13,6 +13,7 @@ thread_local std::string g_zmo_err;
 int zmo_set_err(int code, const char *, ...){ return code; }
 namespace emu { Block *g_blk = nullptr; }
 #include "../../smartdenovo_b200/csrc/zmo_dp_kernels.cuh"
+#include "../../smartdenovo_b200/csrc/zmo_winalign.cuh"
 
 /* two reads in the device layout: 16 bases per uint32, MSB first, per read 16-byte aligned, spare words behind */
 struct SimReads {
@@ -105,4 +106,55 @@ extern "C" int sim_dp_global(int wide, const uint8_t *q, int qlen, const uint8_t
 	cnt4[0] = res.mat; cnt4[1] = res.mis; cnt4[2] = res.ins; cnt4[3] = res.del;
 	for(int k = 0; k < res.ncig && k < cig_cap; k++) cig[k] = cg[res.ncig - 1 - k];
 	return res.ncig;
+}
+
+/*
+ * n_win windows of one (q, c, strand) task through k_window_align: q = pb1 forward, c given FORWARD (the kernel addresses the
+ * reverse complement itself for dir = 1, view_pb2).  win = n_win x {q span, c span, n_anchors} (what the pipeline keeps in
+ * SeedSlot::h_wspan), anc = the windows' anchors back to back, 6 ints each {off1, off2, len1, len2, dir1, dir2}.  Slab and CIGAR
+ * region sizes follow pair_align_impl (zmo_align.cu).  out = n_win x 11 {score, tb, te, qb, qe, aln, mat, mis, ins, del, kept};
+ * cig_out = the windows' CIGARs back to back, cig_n[i] ops each.
+ */
+extern "C" int sim_window_align(const uint8_t *q, int qlen, const uint8_t *c, int clen, int dir, const int *win, int n_win, const int *anc,
+		int w, int M, int X, int O, int E, int T, int zovl, float min_id, int *out, uint32_t *cig_out, int cig_cap, int *cig_n){
+	SimReads rd(q, qlen, c, clen); DevReads R = rd.dev();
+	AlnPar A; A.w = w; A.ew = 800; A.W = 3200; A.zovl = zovl; A.min_id = min_id; A.P.M = M; A.P.X = X; A.P.I = O; A.P.D = O; A.P.E = E; A.P.T = T;
+	std::vector<WItem> items(n_win); std::vector<DevWin> wins(n_win); std::vector<DevZPair> an; std::vector<unsigned long long> icig(n_win);
+	AlnTask task; task.pair_idx = 0; task.dir = (uint32_t)dir; task.item_off = 0; task.n_item = (uint32_t)n_win;
+	zmo_pair_t pair; pair.qid = 0; pair.cid = 1;
+	unsigned long long cig_words = 0; int max_rows = 16, a0 = 0;
+	for(int i = 0; i < n_win; i++){
+		const int s0 = win[3 * i], s1 = win[3 * i + 1], na = win[3 * i + 2];
+		items[i].task = 0; items[i].win = (uint32_t)i;
+		DevWin W; memset(&W, 0, sizeof(W)); W.anc0 = (uint32_t)a0; W.anc1 = (uint32_t)(a0 + na); W.dir = (uint8_t)dir; wins[i] = W;
+		for(int k = 0; k < na; k++){
+			const int *o = anc + 6 * (a0 + k); DevZPair p; memset(&p, 0, sizeof(p));
+			p.off1 = (uint32_t)o[0]; p.off2 = (uint32_t)o[1]; p.len1 = (uint16_t)o[2]; p.len2 = (uint16_t)o[3]; p.dir1 = (uint8_t)o[4]; p.dir2 = (uint8_t)o[5]; an.push_back(p);
+		}
+		a0 += na;
+		icig[i] = cig_words; cig_words += (unsigned long long)(s0 + s1 + 16 + 2 * na);
+		if(s1 + 8 > max_rows) max_rows = s1 + 8;
+		if(s0 + 8 > max_rows) max_rows = s0 + 8;
+	}
+	const int wgrid = (n_win + WA_WARPS - 1) / WA_WARPS + 1;
+	const int wcol = std::min(max_rows + w, 2 * w + 1);
+	unsigned long long slab = (unsigned long long)max_rows * band_row_words<32, WA_C>(wcol) + max_rows + (2ull * max_rows + 2ull * w + 16) + ((unsigned long long)max_rows >> 3) + (w >> 3) + 8;
+	if(2 * w + 3 > WA_CAP){ unsigned long long cap = 1; while(cap < (unsigned long long)(2 * w + 3)) cap <<= 1; slab += 3 * cap; }
+	slab = (slab + 63) & ~63ull;
+	std::vector<uint32_t> arena(slab * (unsigned long long)wgrid * WA_WARPS + 64, 0xDEADBEEFu), cg(cig_words + 64, 0u);
+	std::vector<DevReg> regs(n_win);
+	unsigned long long ctr[4] = {0, 0, 0, 0};
+	const WItem *di = items.data(); const AlnTask *dt = &task; const zmo_pair_t *dp = &pair; const DevWin *dw = wins.data(); const DevZPair *da = an.data();
+	uint32_t *ar = arena.data(), *cgp = cg.data(); const unsigned long long *dic = icig.data(); DevReg *dr = regs.data(); unsigned long long *cp = ctr;
+	const uint32_t nitems = (uint32_t)n_win;
+	emu::launch((unsigned)wgrid, 32 * WA_WARPS, [=](){ k_window_align(di, nitems, dt, dp, dw, da, R, A, ar, slab, max_rows, cgp, dic, dr, cp, 0, 1); });
+	int total = 0;
+	for(int i = 0; i < n_win; i++){
+		const DevReg &r = regs[i]; int *o = out + 11 * i;
+		o[0] = r.score; o[1] = r.tb; o[2] = r.te; o[3] = r.qb; o[4] = r.qe; o[5] = r.aln; o[6] = r.mat; o[7] = r.mis; o[8] = r.ins; o[9] = r.del; o[10] = (int)r.kept;
+		cig_n[i] = (int)r.cig_len;
+		if(r.cig_off != icig[i] || r.cig_len > (unsigned long long)(win[3 * i] + win[3 * i + 1] + 16 + 2 * win[3 * i + 2])) return -1;     /* CIGAR region overrun */
+		for(uint32_t k = 0; k < r.cig_len && total < cig_cap; k++) cig_out[total++] = cg[r.cig_off + k];
+	}
+	return total;
 }

@@ -1,5 +1,5 @@
 """CPU: the product's DP executor KERNELS (smartdenovo_b200/csrc/zmo_dp_kernels.cuh: k_ext_warp, k_ext_cta<64|128,7>,
-k_ext_cta<128,13>, k_glb_warp, k_glb_cta, with the register-resident sweeps of zmo_dpr.cuh and the shared/global-row
+k_ext_cta<128,13>, k_glb_warp, k_glb_cta; zmo_winalign.cuh: k_window_align; with the register-resident sweeps of zmo_dpr.cuh and the shared/global-row
 fallback of zmo_dp.cuh underneath) compiled for the host by tests/hostsim (test-only; thread blocks run as cooperative
 fibers, warp collectives and barriers emulated) against the oracle: score, end point, counts and CIGAR bit-exact.
 The same comparisons run on the real device in tests/test_gpu_dp.py."""
@@ -171,3 +171,59 @@ def test_gap_kernels(dp_sim, oracle_lib):
         q, t = related(rng, n, err=0.5)
         check_glb(dp_sim, oracle_lib, 1, q, t, w)
     check_glb(dp_sim, oracle_lib, 1, q[:40], t[:60], 50)            # small problem on the wide kernel
+
+
+def _windows(orc, a, b):
+    """kept windows + anchors of the pair (a = q, b = c) from the oracle's seeding stage"""
+    from test_seed_core import run_pw
+    nh, ovl, wins, anc = run_pw(orc, "orc_pair_windows", a, b)
+    out, k = [], 0
+    for i in range(len(wins) // 7):
+        d, b0, e0, b1, e1, _, na = wins[7 * i: 7 * i + 7]
+        out.append((d, e0 - b0, e1 - b1, anc[6 * k: 6 * (k + na)]))
+        k += na
+    return out
+
+
+@pytest.mark.parametrize("w", [50, 20, 120])
+def test_window_align_kernel(dp_sim, oracle_lib, w):
+    """k_window_align (zmo_winalign.cuh: anchor walk, fixed-band bridges with 1/2/4/7 columns per lane, traceback in shared memory
+    for short bridges, D/I padding, run-length anchor alignment, CIGAR splicing, region filter) against the oracle's restatement of
+    fast_seeds_align_hzmo (hzm_aln.h:1247-1302) on the windows and anchors of real read pairs, both strands"""
+    from test_seed_core import pairs
+    n_win = 0
+    for a, b in pairs(40 + w, 6):
+        wl = _windows(oracle_lib, a, b)
+        for d in (0, 1):
+            ws = [x for x in wl if x[0] == d]
+            if not ws:
+                continue
+            c_strand = b if d == 0 else (3 - b[::-1]).astype(np.uint8)
+            win = (C.c_int * (3 * len(ws)))(*[v for x in ws for v in (x[1], x[2], len(x[3]) // 6)])
+            flat = [v for x in ws for v in x[3]]
+            anc = (C.c_int * max(len(flat), 1))(*flat)
+            out = (C.c_int * (11 * len(ws)))()
+            cap = sum(x[1] + x[2] + 16 + len(x[3]) // 3 for x in ws)
+            cig = (C.c_uint32 * cap)()
+            cn = (C.c_int * len(ws))()
+            qa = np.ascontiguousarray(a, np.uint8)
+            cb = np.ascontiguousarray(b, np.uint8)
+            tot = dp_sim.sim_window_align(qa.ctypes.data_as(C.c_void_p), len(qa), cb.ctypes.data_as(C.c_void_p), len(cb), d, win, len(ws), anc,
+                                          w, 2, -5, -3, -1, -50, 200, C.c_float(0.6), out, cig, cap, cn)
+            assert tot >= 0
+            pos = 0
+            for i, x in enumerate(ws):
+                eo = (C.c_int * 10)()
+                ecap = x[1] + x[2] + 16 + len(x[3]) // 3
+                ec = (C.c_uint32 * ecap)()
+                ea = (C.c_int * len(x[3]))(*x[3])
+                cs = np.ascontiguousarray(c_strand, np.uint8)
+                en = oracle_lib.orc_window_align(qa.ctypes.data_as(C.c_void_p), cs.ctypes.data_as(C.c_void_p), ea, len(x[3]) // 6, w, 2, -5, -3, -1, -50, eo, ec, ecap)
+                got = list(out[11 * i: 11 * i + 10])
+                assert got == list(eo), (d, i, got, list(eo))
+                assert list(cig[pos: pos + cn[i]]) == list(ec[:en]), (d, i)
+                kept = not (eo[5] * 2 < 200 or np.float32(eo[6]) < np.float32(eo[5]) * np.float32(0.6))
+                assert out[11 * i + 10] == int(kept)
+                pos += cn[i]
+                n_win += 1
+    assert n_win >= 8
