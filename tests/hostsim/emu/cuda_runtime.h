@@ -64,9 +64,11 @@ struct Block {
 	std::vector<Fiber> f; std::vector<Warp> w; ucontext_t sched; int cur = 0;
 	int bar_expected = 0, bar_count = 0; unsigned bar_gen = 0;
 	std::function<void()> body;
+	std::vector<unsigned long long> dyn;      /* dynamic shared memory of the block (ZMO_DYN_SMEM) */
 };
 extern Block *g_blk;       /* defined by the one translation unit that includes this header */
 static inline Fiber &cur(){ return g_blk->f[g_blk->cur]; }
+static inline uint8_t *dyn_smem(){ return (uint8_t*)g_blk->dyn.data(); }
 static inline void yield(){ Block *b = g_blk; swapcontext(&b->f[b->cur].ctx, &b->sched); }
 
 /* warp-level rendezvous of all 32 lanes (every collective in the product uses the full mask) */
@@ -103,8 +105,8 @@ static void trampoline(){
 }
 
 /* run `grid` blocks of `block` threads; kernel() is the __global__ function call with its arguments bound */
-static inline void launch(unsigned grid, unsigned block, const std::function<void()> &kernel, size_t stack_bytes = 512u << 10){
-	Block B; B.body = kernel;
+static inline void launch(unsigned grid, unsigned block, const std::function<void()> &kernel, size_t dyn_smem_bytes = 0, size_t stack_bytes = 512u << 10){
+	Block B; B.body = kernel; B.dyn.assign(dyn_smem_bytes / 8 + 2, 0xA5A5A5A5A5A5A5A5ull);
 	B.f.resize(block); B.w.resize((block + 31) / 32);
 	for(unsigned t = 0; t < block; t++) B.f[t].stack = malloc(stack_bytes);
 	for(unsigned bx = 0; bx < grid; bx++){
@@ -139,6 +141,7 @@ static inline void launch(unsigned grid, unsigned block, const std::function<voi
 
 }  // namespace emu
 
+#define ZMO_DYN_SMEM(name) uint8_t *name = emu::dyn_smem()
 #define threadIdx (emu::cur().tid)
 #define blockIdx  (emu::cur().bid)
 #define blockDim  (emu::cur().bdim)
