@@ -1,5 +1,6 @@
 /*
- * TEST-ONLY host simulation of the pair-seeding KERNEL k_p_seed (smartdenovo_b200/csrc/zmo_seed_kernels.cuh with the
+ * TEST-ONLY host simulation of the pair-seeding KERNEL k_p_seed and the dot-matrix KERNEL k_p_dot (smartdenovo_b200/csrc/
+ * zmo_seed_kernels.cuh, zmo_dot_kernels.cuh with the
  * warp-cooperative span searches of zmo_seed_warp.cuh and the serial core of zmo_seed_core.cuh underneath), compiled for the
  * host against tests/hostsim/emu/cuda_runtime.h: one warp per pair runs as 32 cooperative fibers.  The front end (z-index,
  * z-match, sort by (off1, off2)) is done here on the host the way tests/hostsim/seed_host.cpp does it.
@@ -13,6 +14,7 @@ thread_local std::string g_zmo_err;
 int zmo_set_err(int code, const char *, ...){ return code; }
 namespace emu { Block *g_blk = nullptr; }
 #include "../../smartdenovo_b200/csrc/zmo_seed_kernels.cuh"
+#include "../../smartdenovo_b200/csrc/zmo_dot_kernels.cuh"
 
 static std::vector<uint32_t> pack(const uint8_t *s, int n){
 	std::vector<uint32_t> w((n + 15) / 16 + 4, 0);
@@ -109,4 +111,41 @@ extern "C" int simk_pair_windows(const uint8_t *pb1, int alen, const uint8_t *pb
 	for(int i = 0; i < na && i < anc_cap; i++) std::copy(a0.begin() + 6 * i, a0.begin() + 6 * i + 6, anc_out + 6 * i);
 	*n_anc_out = na;
 	return nw;
+}
+
+/*
+ * Dot-matrix mode (-U) for one pair through k_p_dot: same contract as seed_host.cpp's sim_pair_dotmatrix / the oracle's
+ * orc_pair_dotmatrix.  The match list is delivered the way the device front end does in this mode: sorted by
+ * (off1 - off2, off1), runs of equal keys in adversarial order and flagged as ties.  copies / force_tie as above.
+ */
+extern "C" int simk_pair_dotmatrix(const uint8_t *pb1, int alen, const uint8_t *pb2, int blen, int zsize, int hz, int zcut, int kvar,
+		int xvar, int yvar, int min_block_len, int max_overhang, float dev_pen, float gap_pen, int ztot, int copies, int force_tie, int *out){
+	std::vector<DevZPair> srt = match_list(pb1, alen, pb2, blen, zsize, hz, zcut, kvar);
+	const uint32_t n = (uint32_t)srt.size();
+	auto key = [](const DevZPair &z){ return (int64_t)((((int64_t)z.off1 - (int64_t)z.off2) << 32) | (int64_t)z.off1); };
+	std::stable_sort(srt.begin(), srt.end(), [&](const DevZPair &a, const DevZPair &b){ return key(a) < key(b); });
+	bool tie = false;
+	for(size_t i = 0, j; i < srt.size(); i = j){
+		for(j = i + 1; j < srt.size() && key(srt[j]) == key(srt[i]); j++);
+		if(j - i > 1){ tie = true; std::reverse(srt.begin() + i, srt.begin() + j); }
+	}
+	if(copies < 1) copies = 1;
+	const uint32_t np = (uint32_t)copies;
+	const size_t per = 4 + sizeof(DevDiag) + 4 + 4 + sizeof(DevZPairG) + sizeof(DevWin) + 16;      /* zmo_dot.cu: zmo_dot_scratch_bytes(n) = (n+2)*per + 64 */
+	std::vector<unsigned long long> coff(np + 1); std::vector<DevZPair> cache((size_t)n * np + 1);
+	std::vector<uint8_t> tieflag(np, (uint8_t)((tie || force_tie)? 1 : 0)); std::vector<zmo_pair_t> pairs(np);
+	for(uint32_t p = 0; p < np; p++){ coff[p] = (unsigned long long)p * n; std::copy(srt.begin(), srt.end(), cache.begin() + (size_t)p * n); pairs[p].qid = 0; pairs[p].cid = 1; }
+	coff[np] = (unsigned long long)np * n;
+	std::vector<uint8_t> scratch((size_t)n * np * per + (size_t)(2 * per + 64) * np + 256, 0xEE);
+	std::vector<zmo_dotres_t> res(np);
+	unsigned long long work = 0;
+	uint64_t woff[2] = {0, 0}; uint32_t len[2] = {(uint32_t)alen, (uint32_t)blen};
+	DevReads R; R.words = nullptr; R.woff = woff; R.len = len; R.n = 2;
+	DotPar par; par.xvar = xvar; par.yvar = yvar; par.min_block_len = min_block_len; par.max_overhang = max_overhang; par.deviation_penalty = dev_pen; par.gap_penalty = gap_pen;
+	const unsigned long long *dco = coff.data(); const zmo_pair_t *dp = pairs.data(); DevZPair *dc = cache.data(); const uint8_t *dt = tieflag.data();
+	uint8_t *ds = scratch.data(); zmo_dotres_t *dr = res.data(); unsigned long long *dw = &work;
+	emu::launch(np > 1? 2u : 1u, 32 * DOT_WARPS, [=](){ k_p_dot(dco, dp, np, dc, dt, ds, per, R, par, (uint32_t)zsize, (uint32_t)ztot, dr, dw); });
+	for(uint32_t p = 1; p < np; p++) if(memcmp(&res[p], &res[0], sizeof(zmo_dotres_t))) return -2;
+	out[0] = res[0].score; out[1] = res[0].qb; out[2] = res[0].qe; out[3] = res[0].tb; out[4] = res[0].te; out[5] = res[0].strand;
+	return (int)res[0].n_zpair;
 }

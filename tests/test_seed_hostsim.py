@@ -101,3 +101,36 @@ def test_seed_kernel_tie_path_and_work_loop(seedk_sim, oracle_lib):
         g[k: k + 80] = pal
     check(seedk_sim, oracle_lib, g, g.copy())
     check(seedk_sim, oracle_lib, g, (3 - g[::-1]).astype(np.uint8))
+
+
+def run_dot_kernel(lib, a, b, copies=1, force_tie=0, ztot=0, zcut=16, xvar=128, yvar=64, mbl=160, dev=1.0, gap=0.05):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    out = (C.c_int * 6)()
+    n = lib.simk_pair_dotmatrix(a.ctypes.data_as(C.c_void_p), len(a), b.ctypes.data_as(C.c_void_p), len(b), 10, 1, zcut, 2, xvar, yvar, mbl, 2 * xvar,
+                                C.c_float(dev), C.c_float(gap), ztot, copies, force_tie, out)
+    assert n != -2, "copies of the same pair disagree"
+    return n, list(out)
+
+
+def test_dot_kernel_matches_oracle(seedk_sim, oracle_lib):
+    """k_p_dot (zmo_dot_kernels.cuh): lane 0 runs the serial dot-matrix logic of zmo_dot_core.cuh, its sort_array emulations are staged
+    through shared memory by the helper lanes (mailbox + paired __syncwarp()s); input sorted by diagonal like the device front end"""
+    from test_seed_core import run_dot
+    hits = 0
+    for i, (a, b) in enumerate(pairs(600, 30)):
+        exp = run_dot(oracle_lib, "orc_pair_dotmatrix", a, b)
+        assert exp == run_dot_kernel(seedk_sim, a, b)
+        if i % 6 == 0:
+            assert exp == run_dot_kernel(seedk_sim, a, b, force_tie=1)
+        if i % 10 == 0:
+            assert exp == run_dot_kernel(seedk_sim, a, b, copies=20)
+        hits += exp[1][0] > 0
+    assert hits > 8
+    for a, b in pairs(601, 6):
+        kw = dict(zcut=64, xvar=256, yvar=32, mbl=300, dev=0.1, gap=0.01)
+        assert run_dot(oracle_lib, "orc_pair_dotmatrix", a, b, **kw) == run_dot_kernel(seedk_sim, a, b, **kw)
+    # below the -r threshold the kernel reports an empty hit without looking at the list (hzm_aln.h:1184)
+    a, b = next(pairs(602, 1))
+    n, out = run_dot_kernel(seedk_sim, a, b[:300], ztot=10 ** 6)
+    assert out[0] == 0 and out[5] == 0
