@@ -1830,5 +1830,19 @@ int orc_window_align(u8 *pb1, u8 *pb2, const int *anc, int n_anc, int w, int M, 
 	n = (int)cg.n; for(i=0;i<n&&i<cigar_cap;i++) cigar_out[i] = cg.a[i];
 	vec_free(cg); free(a); return n;
 }
+/* -n: kswx_refine_alignment (kswx.h:483-659) of an alignment given by its start (qb on `query` = c on the strand shown, tb on `target` = q)
+ * and CIGAR inside half band W (wtzmo passes -w).  out as in orc_window_align (tb/te/qb/qe relative to the start, as the restatement
+ * returns them); returns the number of new CIGAR ops. */
+int orc_refine(u8 *query, int qb, u8 *target, int tb, int W, int M, int X, int O, int E, const u32 *cigar_in, int n_in, int *out, u32 *cigar_out, int cigar_cap){
+	zparams_t par = orc_par(10, 1, 64, 2, 800, 400, 200, 300, 3200);
+	u32v cg; aln_t x; int i, n;
+	par.M = M; par.X = X; par.O = O; par.E = E;
+	if(n_in < 0) n_in = 0;
+	vec_init(cg); vec_reserve(cg, (size_t)n_in + 1); memcpy(cg.a, cigar_in, (size_t)n_in * sizeof(u32)); cg.n = (size_t)n_in;
+	x = refine_alignment(query, qb, target, tb, W, &par, &cg);
+	orc_export(x, out);
+	n = (int)cg.n; for(i=0;i<n&&i<cigar_cap;i++) cigar_out[i] = cg.a[i];
+	vec_free(cg); return n;
+}
 /* full pair alignment (stitching, gaps, end extensions) is exercised through the whole-program runs */
 #endif

@@ -227,3 +227,58 @@ def test_window_align_kernel(dp_sim, oracle_lib, w):
                 pos += cn[i]
                 n_win += 1
     assert n_win >= 8
+
+
+def _refine_both(sim, orc, q, c, d, tb, qb, cig, W=50):
+    """refine the alignment (start tb on q, qb on c's strand d, CIGAR cig) with the simulated kernels and with the oracle"""
+    q = np.ascontiguousarray(q, np.uint8)
+    c = np.ascontiguousarray(c, np.uint8)
+    cs = np.ascontiguousarray(c if d == 0 else (3 - c[::-1]), np.uint8)
+    ql = sum(op >> 4 for op in cig if (op & 15) in (0, 1))
+    tl = sum(op >> 4 for op in cig if (op & 15) in (0, 2))
+    cin = (C.c_uint32 * max(len(cig), 1))(*cig)
+    cap = ql + tl + 8
+    eo, go = (C.c_int * 10)(), (C.c_int * 10)()
+    ec, gc = (C.c_uint32 * cap)(), (C.c_uint32 * cap)()
+    cls = C.c_int(-1)
+    gn = sim.sim_refine(q.ctypes.data_as(C.c_void_p), len(q), c.ctypes.data_as(C.c_void_p), len(c), d, tb, tb + tl, qb, qb + ql, cin, len(cig),
+                        W, 2, -5, -3, -1, go, gc, cap, C.byref(cls))
+    if gn == -1:
+        return None
+    assert gn >= 0, gn
+    en = orc.orc_refine(cs.ctypes.data_as(C.c_void_p), qb, q.ctypes.data_as(C.c_void_p), tb, W, 2, -5, -3, -1, cin, len(cig), eo, ec, cap)
+    assert list(go) == list(eo), (list(go), list(eo))
+    assert list(gc[:gn]) == list(ec[:en])
+    return cls.value
+
+
+def test_refine_kernels(dp_sim, oracle_lib):
+    """-n: k_refine_size / k_refine_band (per-row band from the CIGAR, widened around indel runs, made monotone) and the warp / CTA
+    executors of the variable-band sweep (reg_refine) against the oracle's restatement of kswx_refine_alignment (kswx.h:483-659)"""
+    rng = np.random.default_rng(21)
+    seen = set()
+    for trial in range(10):
+        n = int(rng.integers(150, 700))
+        g = rng.integers(0, 4, n + 400).astype(np.uint8)
+        tb, qb = int(rng.integers(0, 100)), int(rng.integers(0, 100))
+        q = g.copy()                                                  # pb1
+        body = mutate(rng, g[tb: tb + n])
+        c_strand = np.concatenate([rng.integers(0, 4, qb).astype(np.uint8), body, rng.integers(0, 4, 50).astype(np.uint8)])
+        d = trial & 1
+        c = c_strand if d == 0 else (3 - c_strand[::-1]).astype(np.uint8)
+        # a banded global alignment of the two segments supplies a realistic CIGAR (I = base of c only, D = base of q only)
+        score, cig = call_global(oracle_lib, "orc_global2", body, g[tb: tb + n], 60)
+        seen.add(_refine_both(dp_sim, oracle_lib, q, c, d, tb, qb, cig, W=int(rng.choice([50, 20, 5]))))
+        # a crude CIGAR (what a stitch with long pads looks like): the band widens around the long runs
+        ql, tl = len(body), n
+        k = min(ql, tl) - 40
+        run = int(rng.integers(60, 260))
+        crude = [(k // 2) << 4, (run << 4) | 1, (run << 4) | 2, ((k - k // 2 - run) << 4)] if k - k // 2 - run > 0 else [(k << 4)]
+        used_q = sum(op >> 4 for op in crude if (op & 15) in (0, 1))
+        used_t = sum(op >> 4 for op in crude if (op & 15) in (0, 2))
+        crude += [((ql - used_q) << 4) | 1, ((tl - used_t) << 4) | 2]
+        seen.add(_refine_both(dp_sim, oracle_lib, q, c, d, tb, qb, crude, W=50))
+    assert {0, 1} <= seen          # both executor classes ran
+    # a run of > ~800 inserted bases needs a band beyond the CTA executor: the product rejects the run instead of differing
+    g = rng.integers(0, 4, 3000).astype(np.uint8)
+    assert _refine_both(dp_sim, oracle_lib, g, g, 0, 0, 0, [(100 << 4), (900 << 4) | 1, (900 << 4) | 2, (1100 << 4)]) is None
