@@ -14,6 +14,7 @@ int zmo_set_err(int code, const char *, ...){ return code; }
 namespace emu { Block *g_blk = nullptr; }
 #include "../../smartdenovo_b200/csrc/zmo_dp_kernels.cuh"
 #include "../../smartdenovo_b200/csrc/zmo_winalign.cuh"
+#include "../../smartdenovo_b200/csrc/zmo_stitch_kernels.cuh"
 #include "../../smartdenovo_b200/csrc/zmo_refine_kernels.cuh"
 
 /* two reads in the device layout: 16 bases per uint32, MSB first, per read 16-byte aligned, spare words behind */
@@ -196,4 +197,39 @@ extern "C" int sim_refine(const uint8_t *q, int qlen, const uint8_t *c, int clen
 	out[0] = rec.score; out[1] = rec.tb; out[2] = rec.te; out[3] = rec.qb; out[4] = rec.qe; out[5] = rec.aln; out[6] = rec.mat; out[7] = rec.mis; out[8] = rec.ins; out[9] = rec.del;
 	for(uint32_t k = 0; k < rec.n_cigar && (int)k < cigar_cap; k++) cigar_out[k] = out_ops[rec.cigar_off + k];
 	return (int)rec.n_cigar;
+}
+
+/*
+ * k_finish (warp = 0) / k_finish_warp (warp = 1) on caller-built stitch inputs.  Flat arrays: per task item_off, n_item and
+ * ts = {ok, first, left_job, right_job, score, tb, te, qb, qe, aln, mat, mis, ins, del}; per region kept, cig_off, cig_len; per job
+ * cig_off and jv = {score, qe, te, mat, mis, ins, del, ncig}.  recs_out = nt x {ok, score, tb, te, qb, qe, aln, mat, mis, ins, del, n_cigar}.
+ */
+extern "C" int sim_finish(int warp, int nt, const int *item_off, const int *n_item, const int *tsv, int nreg, const int *reg_kept, const int *reg_cig_off,
+		const int *reg_cig_len, int njob, const int *job_cig_off, const int *jv, const uint32_t *cig_arena, const int *out_off, uint32_t *out_cig, int *recs_out){
+	std::vector<AlnTask> tasks(nt); std::vector<TaskState> ts(nt); std::vector<DevReg> regs(nreg + 1); std::vector<DPRes> res(njob + 1); std::vector<DPJob> jobs(njob + 1);
+	std::vector<unsigned long long> ooff(nt + 1); std::vector<zmo_record_t> recs(nt);
+	for(int t = 0; t < nt; t++){
+		tasks[t].pair_idx = 0; tasks[t].dir = 0; tasks[t].item_off = (uint32_t)item_off[t]; tasks[t].n_item = (uint32_t)n_item[t];
+		const int *v = tsv + 14 * t; TaskState S; memset(&S, 0, sizeof(S));
+		S.ok = v[0]; S.first = v[1]; S.last = -1; S.left_job = v[2]; S.right_job = v[3]; S.score = v[4]; S.tb = v[5]; S.te = v[6]; S.qb = v[7]; S.qe = v[8];
+		S.aln = v[9]; S.mat = v[10]; S.mis = v[11]; S.ins = v[12]; S.del = v[13]; ts[t] = S;
+		ooff[t] = (unsigned long long)out_off[t];
+		memset(&recs[t], 0xCC, sizeof(zmo_record_t));
+	}
+	for(int i = 0; i < nreg; i++){ DevReg r; memset(&r, 0, sizeof(r)); r.kept = (uint32_t)reg_kept[i]; r.cig_off = (unsigned long long)reg_cig_off[i]; r.cig_len = (uint32_t)reg_cig_len[i]; regs[i] = r; }
+	for(int j = 0; j < njob; j++){
+		DPJob J; memset(&J, 0, sizeof(J)); J.cig_off = (unsigned long long)job_cig_off[j]; jobs[j] = J;
+		const int *v = jv + 8 * j; DPRes r; memset(&r, 0, sizeof(r)); r.score = v[0]; r.qe = v[1]; r.te = v[2]; r.mat = v[3]; r.mis = v[4]; r.ins = v[5]; r.del = v[6]; r.ncig = v[7]; res[j] = r;
+	}
+	AlnPar A; memset(&A, 0, sizeof(A));
+	const AlnTask *dt = tasks.data(); const DevReg *dr = regs.data(); const DPRes *ds = res.data(); const DPJob *dj = jobs.data(); const TaskState *dts = ts.data();
+	const unsigned long long *doo = ooff.data(); zmo_record_t *drec = recs.data(); const uint32_t n = (uint32_t)nt;
+	if(warp) emu::launch((unsigned)(((unsigned long long)n * 32 + 255) / 256), 256, [=](){ k_finish_warp(dt, n, dr, ds, dj, cig_arena, A, dts, doo, out_cig, drec); });
+	else emu::launch((n + 63) / 64, 64, [=](){ k_finish(dt, n, dr, ds, dj, cig_arena, A, dts, doo, out_cig, drec); });
+	for(int t = 0; t < nt; t++){
+		const zmo_record_t &r = recs[t]; int *o = recs_out + 12 * t;
+		o[0] = r.ok; o[1] = r.score; o[2] = r.tb; o[3] = r.te; o[4] = r.qb; o[5] = r.qe; o[6] = r.aln; o[7] = r.mat; o[8] = r.mis; o[9] = r.ins; o[10] = r.del; o[11] = (int)r.n_cigar;
+		if(r.ok && r.cigar_off != ooff[t]) return -1;
+	}
+	return 0;
 }

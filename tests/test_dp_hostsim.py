@@ -282,3 +282,98 @@ def test_refine_kernels(dp_sim, oracle_lib):
     # a run of > ~800 inserted bases needs a band beyond the CTA executor: the product rejects the run instead of differing
     g = rng.integers(0, 4, 3000).astype(np.uint8)
     assert _refine_both(dp_sim, oracle_lib, g, g, 0, 0, 0, [(100 << 4), (900 << 4) | 1, (900 << 4) | 2, (1100 << 4)]) is None
+
+
+def _rand_ops(rng, n, first_op=None):
+    """n run-length ops with alternating types (a valid CIGAR never repeats an op), optionally starting with first_op"""
+    ops, prev = [], None
+    for i in range(n):
+        op = first_op if (i == 0 and first_op is not None) else int(rng.choice([o for o in (0, 1, 2) if o != prev]))
+        ops.append((int(rng.integers(1, 300)) << 4) | op)
+        prev = op
+    return ops
+
+
+def _cat(dst, block):
+    """kswx_push_cigars (kswx.h:46-52): only the first op of an appended block may merge with the previous last op"""
+    if not block:
+        return
+    if dst and (dst[-1] & 15) == (block[0] & 15):
+        dst[-1] += block[0] & 0xFFFFFFF0
+        dst.extend(block[1:])
+    else:
+        dst.extend(block)
+
+
+@pytest.mark.parametrize("warp", [0, 1])
+def test_finish_kernels(dp_sim, warp):
+    """k_finish and its opt-in warp-per-task variant k_finish_warp (zmo_stitch_kernels.cuh) against an independent restatement of the
+    stitch of global_align_regs_hzmo (hzm_aln.h:1345-1486): [left extension] + region 0 + sum([gap] + region i) + [right extension],
+    gap and right-extension CIGARs stored in walk order (reversed), block-wise merging at every seam, counts from the right job"""
+    rng = np.random.default_rng(33 + warp)
+    nt = 70
+    arena, regs, jobs, tasks, tsv, exp_recs, exp_cigs, out_off = [], [], [], [], [], [], [], []
+
+    def put(ops):
+        off = len(arena)
+        arena.extend(ops)
+        arena.extend([0xABCDEF] * int(rng.integers(0, 3)))      # slack between segments
+        return off
+
+    def job(ops_walk_order, vals):
+        jobs.append((put(ops_walk_order), vals + [len(ops_walk_order)]))
+        return len(jobs) - 1
+
+    total = 0
+    for t in range(nt):
+        item_off, n_item = len(regs), int(rng.integers(1, 7))
+        base = [int(x) for x in rng.integers(0, 5000, 10)]          # score tb te qb qe aln mat mis ins del
+        if t % 9 == 8:                                              # a task whose windows were all filtered out
+            for _ in range(n_item):
+                regs.append((0, 0, 0))
+            tasks.append((item_off, n_item)); tsv.append([0, -1, -1, -1] + base); exp_recs.append([0] * 12); exp_cigs.append([]); out_off.append(total)
+            continue
+        cig, first, prev_last = [], -1, None
+        left = -1
+        if rng.random() < 0.6:
+            ops = _rand_ops(rng, int(rng.integers(0, 40)))
+            left = job(ops, [int(x) for x in rng.integers(0, 900, 7)])      # stored in alignment order (already flipped by the walk of a backward extension)
+            _cat(cig, ops)
+        for k in range(n_item):
+            if k and rng.random() < 0.3:
+                regs.append((0, 0, 0))                              # a region dropped by the per-window filter
+                continue
+            force = (cig[-1] & 15) if (cig and rng.random() < 0.5) else None     # make seams that merge
+            rops = _rand_ops(rng, int(rng.integers(1, 120)), force)
+            if first < 0:
+                first = len(regs)
+                regs.append((1, put(rops), len(rops)))
+                _cat(cig, rops)
+            else:
+                gops = _rand_ops(rng, int(rng.integers(0, 30)), (cig[-1] & 15) if rng.random() < 0.5 else None)
+                gid = job(gops[::-1], [int(x) for x in rng.integers(0, 900, 7)])
+                regs.append((2 + gid, put(rops), len(rops)))
+                _cat(cig, gops)
+                _cat(cig, rops)
+        rec = [1] + base + [0]
+        right = -1
+        if rng.random() < 0.6:
+            ops = _rand_ops(rng, int(rng.integers(0, 60)), (cig[-1] & 15) if rng.random() < 0.5 else None)
+            vals = [int(x) for x in rng.integers(0, 900, 7)]        # score qe te mat mis ins del
+            right = job(ops[::-1], vals)
+            _cat(cig, ops)
+            rec[1] = vals[0]; rec[5] += vals[1]; rec[3] += vals[2]  # score replaced; qe, te advanced
+            rec[6] += sum(vals[3:7]); rec[7] += vals[3]; rec[8] += vals[4]; rec[9] += vals[5]; rec[10] += vals[6]
+        rec[11] = len(cig)
+        tasks.append((item_off, n_item)); tsv.append([1, first, left, right] + base); exp_recs.append(rec); exp_cigs.append(cig); out_off.append(total)
+        total += len(cig) + int(rng.integers(0, 4))
+    ia = lambda xs: (C.c_int * max(len(xs), 1))(*xs)
+    out_cig = (C.c_uint32 * (total + 8))()
+    recs = (C.c_int * (12 * nt))()
+    rc = dp_sim.sim_finish(warp, nt, ia([x[0] for x in tasks]), ia([x[1] for x in tasks]), ia([v for x in tsv for v in x]), len(regs), ia([x[0] for x in regs]),
+                           ia([x[1] for x in regs]), ia([x[2] for x in regs]), len(jobs), ia([x[0] for x in jobs]), ia([v for x in jobs for v in x[1]]),
+                           (C.c_uint32 * max(len(arena), 1))(*arena), ia(out_off), out_cig, recs)
+    assert rc == 0
+    for t in range(nt):
+        assert list(recs[12 * t: 12 * t + 12]) == exp_recs[t], t
+        assert list(out_cig[out_off[t]: out_off[t] + len(exp_cigs[t])]) == exp_cigs[t], t
