@@ -220,3 +220,28 @@ def test_scale_200k_reads_shard_matches_reference_golden(tmp_path, gen_reads):
         for f in (fa, out, out + ".contained"):
             if os.path.exists(f):
                 os.remove(f)
+
+
+def test_cfg2_full_size_shard_properties(tmp_path, gen_reads):
+    """BASELINE.json configs[1] at full size (50,000 PacBio-like reads x 10 kb, the bench workload): one `-P 10 -p 3` query shard, too
+    large for a CPU run inside the suite, checked through the size-independent properties of tests/ovl_props.py -- every record inside its
+    reads, counts consistent with the spans, thresholds honoured, pairs unique, and for every 16th record the CIGAR walked over the actual
+    bases must reproduce mat / mis / ins / del and the reported coordinates on the strand shown"""
+    from ovl_props import check_ovl, load_fasta
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else str(tmp_path)
+    fa = os.path.join(base, "zmo_cfg2_props.fa")
+    out = os.path.join(base, "zmo_cfg2_props.ovl")
+    try:
+        subprocess.run([gen_reads, "-n", "50000", "-L", "10000", "-G", "4600000", "-m", "pacbio", "-s", "20240603", "-o", fa], check=True)
+        r = subprocess.run([EXE, "-t", "1", "-i", fa, "-f", "-o", out, "-k", "16", "-s", "200", "-m", "0.6", "-P", "10", "-p", "3"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        reads = load_fasta(fa)
+        assert len(reads) == 50000
+        n, walked, cols = check_ovl(reads, out, min_score=200, min_id=0.6, walk_every=16)
+        assert n > 30000 and walked >= n // 16 and cols > 3 * 10 ** 8
+        contained = open(out + ".contained", "rb").read().split()
+        assert len(contained) == len(set(contained)) > 100 and all(x in reads for x in contained)
+    finally:
+        for f in (fa, out, out + ".contained"):
+            if os.path.exists(f):
+                os.remove(f)
