@@ -1003,7 +1003,7 @@ static aln_t refine_alignment(const u8 *query, int qb, const u8 *target, int tb,
 	const int M = par->M, X = par->X, I = par->O, D = par->O, E = par->E;     /* wtzmo passes O for both gap opens */
 	aln_t y = ALN_NULL; u32v in; size_t k; int ql = 0, tl = 0, qx, tx, i, j, wmax = 1;
 	int *zw, *zb, *ze, *hrow, *erow; u8 *z;
-	vec_init(in); vec_reserve(in, cigar->n + 1); memcpy(in.a, cigar->a, cigar->n * sizeof(u32)); in.n = cigar->n;
+	vec_init(in); vec_reserve(in, cigar->n + 1); for(k=0;k<cigar->n;k++) in.a[k] = cigar->a[k]; in.n = cigar->n;
 	cigar->n = 0;
 	for(k=0;k<in.n;k++){ const u32 op = in.a[k] & 0xF, len = in.a[k] >> 4; if(op == 0){ ql += len; tl += len; } else if(op == 1) ql += len; else tl += len; }
 	if(ql == 0 || tl == 0){ vec_free(in); return ALN_NULL; }
@@ -1837,12 +1837,31 @@ int orc_refine(u8 *query, int qb, u8 *target, int tb, int W, int M, int X, int O
 	zparams_t par = orc_par(10, 1, 64, 2, 800, 400, 200, 300, 3200);
 	u32v cg; aln_t x; int i, n;
 	par.M = M; par.X = X; par.O = O; par.E = E;
-	if(n_in < 0) n_in = 0;
-	vec_init(cg); vec_reserve(cg, (size_t)n_in + 1); memcpy(cg.a, cigar_in, (size_t)n_in * sizeof(u32)); cg.n = (size_t)n_in;
+	vec_init(cg); vec_reserve(cg, (size_t)(n_in > 0? n_in : 0) + 1);
+	for(i=0;i<n_in;i++) cg.a[i] = cigar_in[i];
+	cg.n = (size_t)(n_in > 0? n_in : 0);
 	x = refine_alignment(query, qb, target, tb, W, &par, &cg);
 	orc_export(x, out);
 	n = (int)cg.n; for(i=0;i<n&&i<cigar_cap;i++) cigar_out[i] = cg.a[i];
 	vec_free(cg); return n;
 }
-/* full pair alignment (stitching, gaps, end extensions) is exercised through the whole-program runs */
+/* pure per-pair alignment of one strand (wtzmo.c:1017-1034): windows -> per-window regions -> region filter -> stitched alignment
+ * (left extension, gaps, right extension) -> optional -n refinement.  pb2 = c on the strand of the windows; win = n_win x
+ * {n_anchors}, anc as in orc_window_align (windows' anchors back to back).  Returns -1 if no region survived, else the number of
+ * CIGAR ops. */
+int orc_pair_align(u8 *pb1, int alen, u8 *pb2, int blen, const int *win, int n_win, const int *anc, int w, int ew, int W, int zovl, float min_id,
+		int M, int X, int O, int E, int T, int refine, int *out, u32 *cigar_out, int cigar_cap){
+	zparams_t par = orc_par(10, 1, 64, 2, 800, 400, zovl, 300, W);
+	win_t *wins = calloc((size_t)(n_win > 0? n_win : 1), sizeof(win_t)); zpair_t *a; u32v cg; aln_t x = ALN_NULL; int i, n, na = 0, ok;
+	par.w = w; par.ew = ew; par.min_id = min_id; par.M = M; par.X = X; par.O = O; par.E = E; par.T = T; par.refine = refine;
+	for(i=0;i<n_win;i++){ wins[i].anc[0] = (u32)na; na += win[i]; wins[i].anc[1] = (u32)na; }
+	a = calloc((size_t)(na > 0? na : 1), sizeof(zpair_t));
+	for(i=0;i<na;i++){ zpair_t *p = &a[i]; const int *o = anc + 6 * i; p->off1 = o[0]; p->off2 = o[1]; p->len1 = o[2]; p->len2 = o[3]; p->dir1 = o[4]; p->dir2 = o[5]; }
+	vec_init(cg);
+	ok = pair_align(pb1, alen, pb2, blen, wins, (u32)n_win, a, &par, &x, &cg);
+	orc_export(x, out);
+	n = (int)cg.n; for(i=0;i<n&&i<cigar_cap;i++) cigar_out[i] = cg.a[i];
+	vec_free(cg); free(a); free(wins);
+	return ok? n : -1;
+}
 #endif

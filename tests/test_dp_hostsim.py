@@ -377,3 +377,61 @@ def test_finish_kernels(dp_sim, warp):
     for t in range(nt):
         assert list(recs[12 * t: 12 * t + 12]) == exp_recs[t], t
         assert list(out_cig[out_off[t]: out_off[t] + len(exp_cigs[t])]) == exp_cigs[t], t
+
+
+@pytest.fixture(scope="module")
+def align_sim():
+    out = os.path.join(REPO, "tests", "_build", "libalign_host.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I" + os.path.join(REPO, "tests", "hostsim", "emu"), "-fPIC", "-shared", "-o", out,
+                    os.path.join(REPO, "tests", "hostsim", "align_host.cpp")], check=True)
+    return C.CDLL(out)
+
+
+def _pair_align_both(sim, orc, a, b, refine=0, finish_warp=0, w=50, ew=800):
+    """every strand with kept windows of the pair (a = q, b = c): the simulated alignment stage against the oracle's pair_align"""
+    results = []
+    wl = _windows(orc, a, b)
+    qa = np.ascontiguousarray(a, np.uint8)
+    cb = np.ascontiguousarray(b, np.uint8)
+    for d in (0, 1):
+        ws = [x for x in wl if x[0] == d]
+        if not ws:
+            continue
+        cs = np.ascontiguousarray(b if d == 0 else (3 - b[::-1]), np.uint8)
+        flat = [v for x in ws for v in x[3]]
+        anc = (C.c_int * max(len(flat), 1))(*flat)
+        win3 = (C.c_int * (3 * len(ws)))(*[v for x in ws for v in (x[1], x[2], len(x[3]) // 6)])
+        win1 = (C.c_int * len(ws))(*[len(x[3]) // 6 for x in ws])
+        cap = len(a) + len(b) + 64
+        go, eo = (C.c_int * 10)(), (C.c_int * 10)()
+        gc, ec = (C.c_uint32 * cap)(), (C.c_uint32 * cap)()
+        stats = (C.c_int * 7)()
+        gn = sim.sim_pair_align(qa.ctypes.data_as(C.c_void_p), len(qa), cb.ctypes.data_as(C.c_void_p), len(cb), d, win3, len(ws), anc,
+                                w, ew, 3200, 200, C.c_float(0.6), 2, -5, -3, -1, -50, refine, finish_warp, go, gc, cap, stats)
+        en = orc.orc_pair_align(qa.ctypes.data_as(C.c_void_p), len(qa), cs.ctypes.data_as(C.c_void_p), len(cs), win1, len(ws), anc,
+                                w, ew, 3200, 200, C.c_float(0.6), 2, -5, -3, -1, -50, refine, eo, ec, cap)
+        assert gn > -2, gn
+        assert gn == en, (d, gn, en)
+        if en >= 0:
+            assert list(go) == list(eo), (d, list(go), list(eo))
+            assert list(gc[:gn]) == list(ec[:en]), d
+        results.append((en, list(stats)))
+    return results
+
+
+def test_alignment_stage_end_to_end(align_sim, oracle_lib):
+    """zmo_pair_align's device side for real read pairs: window alignment, job planning, the six DP job lists run from sorted orders with
+    executor slabs, right extensions, stitch -- and the same with -n refinement and with the opt-in warp stitch"""
+    from test_seed_core import pairs
+    done, jobs = 0, np.zeros(6, int)
+    for i, (a, b) in enumerate(pairs(700, 8)):
+        for en, stats in _pair_align_both(align_sim, oracle_lib, a, b, refine=int(i % 3 == 2), finish_warp=int(i % 2)):
+            done += en >= 0
+            jobs += np.array(stats[:6])
+    assert done >= 5
+    assert jobs[:4].sum() >= 8 and jobs[4:].sum() >= 3, jobs          # end extensions and gap fills really ran
+    # a narrow end-extension band (-e 60) sends the extensions to the warp class, a wide one (-e 800) to the CTA classes
+    a, b = next(pairs(701, 1))
+    narrow = _pair_align_both(align_sim, oracle_lib, a, b, ew=60)
+    assert any(st[0] > 0 for en, st in narrow)
