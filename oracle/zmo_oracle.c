@@ -1141,7 +1141,7 @@ typedef struct {
 	readset_t rs; zparams_t par; kindex_t ix;
 	u8 *masked; u32 *rdcovs; u64set_t closed; u32 avg_rdlen; u32 kcut;
 	u64v *rdhits;              /* per-read candidate carry-over, only with -G > 1 */
-	u64 n_records, aln_cols, n_pairs, n_zpairs;
+	u64 n_records, aln_cols, n_pairs, n_zpairs, n_seeded;
 } zmo_t;
 
 static int gt_cand_ol_desc(const void *a, const void *b, void *ctx){ (void)ctx; return (u32)(*(const u64*)b) > (u32)(*(const u64*)a); }
@@ -1216,7 +1216,7 @@ static void process_read(zmo_t *z, u32 pbid, u32 bcov, readout_t *ro){
 		u32 id2 = (u32)(cands->a[i] >> 32), blen = rs->reads.a[id2].len; pair_seed_t ps; int dir;
 		rs_unpack(rs, id2, 0, pb2);
 		zmatch(&zi, pb2, blen, par, &cache);
-		z->n_zpairs += cache.n;
+		z->n_zpairs += cache.n; z->n_seeded ++;
 		if(cache.n * par->zsize < (u32)par->ztot) continue;
 		if(par->dot_matrix){
 			dotres_t r; u32 ol;
@@ -1730,7 +1730,7 @@ int main(int argc, char **argv){
 		}
 		fclose(pf);
 	}
-	fprintf(stderr, "[oracle] records=%llu aligned_cols=%llu pairs_aligned=%llu zpairs=%llu\n", (unsigned long long)z->n_records, (unsigned long long)z->aln_cols, (unsigned long long)z->n_pairs, (unsigned long long)z->n_zpairs);
+	fprintf(stderr, "[oracle] records=%llu aligned_cols=%llu pairs_seeded=%llu pairs_aligned=%llu zpairs=%llu\n", (unsigned long long)z->n_records, (unsigned long long)z->aln_cols, (unsigned long long)z->n_seeded, (unsigned long long)z->n_pairs, (unsigned long long)z->n_zpairs);
 	return 0;
 }
 #endif
