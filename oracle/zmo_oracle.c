@@ -1142,6 +1142,8 @@ typedef struct {
 	u8 *masked; u32 *rdcovs; u64set_t closed; u32 avg_rdlen; u32 kcut;
 	u64v *rdhits;              /* per-read candidate carry-over, only with -G > 1 */
 	u64 n_records, aln_cols, n_pairs, n_zpairs, n_seeded;
+	/* ZMO_ORACLE_LAG=n (analysis aid): what a speculative batch pipeline that learns of a mask n query reads late would have to seed */
+	u32 *mask_k, cur_k; int lag; u64 lag_reads, lag_pairs, n_reads_done;
 } zmo_t;
 
 static int gt_cand_ol_desc(const void *a, const void *b, void *ctx){ (void)ctx; return (u32)(*(const u64*)b) > (u32)(*(const u64*)a); }
@@ -1172,7 +1174,7 @@ static void flush_read(zmo_t *z, readout_t *ro, FILE *out){
 		z->aln_cols += z->par.dot_matrix? (u64)h->aln : (u64)(h->mat + h->mis + h->ins + h->del);
 	}
 	vec_clear(ro->hits); vec_clear(ro->seeds);
-	if(z->par.skip_contained) for(i=0;i<ro->masks.n;i++) z->masked[ro->masks.a[i]] = 1;
+	if(z->par.skip_contained) for(i=0;i<ro->masks.n;i++){ if(z->mask_k && !z->masked[ro->masks.a[i]]) z->mask_k[ro->masks.a[i]] = z->cur_k; z->masked[ro->masks.a[i]] = 1; }
 	vec_clear(ro->masks);
 	for(i=0;i<ro->closed.n;i++) u64set_add(&z->closed, ro->closed.a[i]);
 	vec_clear(ro->closed);
@@ -1325,9 +1327,17 @@ static void run_overlap(zmo_t *z, FILE *out){
 		}
 	}
 	if(rs->n_qr == 0){ beg = 0; end = rs->n_rd; } else { beg = rs->n_rd; end = beg + rs->n_qr; }
+	if(getenv("ZMO_ORACLE_LAG")){ z->lag = atoi(getenv("ZMO_ORACLE_LAG")); z->mask_k = calloc(rs->n_rd + rs->n_qr + 1, sizeof(u32)); }
 	for(j=beg;j<end;j++){
 		if((j % par->n_job) != (u32)par->i_job) continue;
+		z->cur_k ++;
+		if(z->mask_k && (!z->masked[j] || z->mask_k[j] + (u32)z->lag > z->cur_k)){      /* not known to be masked n reads ago: a lagging pipeline seeds it */
+			u64v cl; vec_init(cl); if(z->masked[j]) read_candidates(z, j, &cl);
+			z->lag_reads ++; if(z->masked[j]) z->lag_pairs += cl.n;
+			vec_free(cl);
+		}
 		if(z->masked[j]) continue;            /* checked BEFORE the previous read's masks are merged (wtzmo.c:1315 vs 1322) */
+		z->n_reads_done ++;
 		flush_read(z, &ro, out);
 		process_read(z, j, z->rdcovs[j], &ro);
 	}
@@ -1730,6 +1740,7 @@ int main(int argc, char **argv){
 		}
 		fclose(pf);
 	}
+	if(z->mask_k) fprintf(stderr, "[oracle] lag=%d: reads processed=%llu, reads a lagging pipeline seeds=%llu (+%llu pairs of reads that were already masked)\n", z->lag, (unsigned long long)z->n_reads_done, (unsigned long long)z->lag_reads, (unsigned long long)z->lag_pairs);
 	fprintf(stderr, "[oracle] records=%llu aligned_cols=%llu pairs_seeded=%llu pairs_aligned=%llu zpairs=%llu\n", (unsigned long long)z->n_records, (unsigned long long)z->aln_cols, (unsigned long long)z->n_seeded, (unsigned long long)z->n_pairs, (unsigned long long)z->n_zpairs);
 	return 0;
 }
