@@ -55,16 +55,15 @@ static int refine_records(zmo_ctx *c, SeedSlot &SL, const AlnTask *d_tasks, uint
 	CUDA_TRY(cudaMemcpyAsync(&tot[1], d_ooff + nt, 8, cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	*out_words = tot[1];
-	if(c->s1.reserve((tot[0] * 3 + 16) * 4) || c->s3.reserve(((size_t)nt * 2 + 2) * sizeof(RefJob)) || c->s6.reserve((tot[1] + 16) * 4)) return ZMO_ERR_CUDA;
+	if(c->s1.reserve((tot[0] * 3 + 16) * 4) || c->s3.reserve(((size_t)nt * 3 + 2) * sizeof(RefJob)) || c->s6.reserve((tot[1] + 16) * 4)) return ZMO_ERR_CUDA;
 	CUDA_TRY(cudaMemsetAsync(ctr + CTR_N1, 0, 24, c->stream));
-	k_refine_band<<<(nt + 63) / 64, 64, 0, c->stream>>>(d_recs, nt, d_ops, d_roff, d_ooff, A.w, c->s1.as<int>(), c->s3.as<RefJob>(), ctr + CTR_N1, d_scr, ctr + CTR_N3); c->launches++;
+	k_refine_band<<<(nt + 63) / 64, 64, 0, c->stream>>>(d_recs, nt, d_ops, d_roff, d_ooff, A.w, c->s1.as<int>(), c->s3.as<RefJob>(), ctr + CTR_N1, d_scr); c->launches++;
 	CUDA_TRY(cudaMemsetAsync(d_scr + nt, 0, 8, c->stream));
 	CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->s2.p, tb, d_scr, d_soff, nt + 1, c->stream)); c->launches++;
 	unsigned long long h[3] = {0, 0, 0}, stot = 0;
 	CUDA_TRY(cudaMemcpyAsync(h, ctr + CTR_N1, 24, cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaMemcpyAsync(&stot, d_soff + nt, 8, cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
-	if(h[2]) return zmo_set_err(ZMO_ERR_CAPACITY, "-n: %llu alignment(s) need a refinement band wider than %d columns (not supported)", h[2], RegCap<CL3_NT, CL3_C>::ncol);
 	if(c->arena.reserve((stot + 64) * 4)) return ZMO_ERR_CUDA;
 	StageTimer tm(c, ST_GAP);
 	if(h[0]){
@@ -76,6 +75,12 @@ static int refine_records(zmo_ctx *c, SeedSlot &SL, const AlnTask *d_tasks, uint
 		CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORKK, 0, 8, c->stream));
 		const int grid = (int)std::min<uint64_t>(h[1], (uint64_t)c->n_sm * 3);
 		k_refine_cta<<<grid, CL3_NT, 0, c->stream>>>(c->s3.as<RefJob>() + nt, (uint32_t)h[1], d_soff, SL.pairs.as<zmo_pair_t>(), d_tasks, dev_reads(c), A.P, c->s1.as<int>(), c->arena.as<uint32_t>(), c->s6.as<uint32_t>(), d_recs, ctr, CTR_WORKK, CTR_CELLS_GAP); c->launches++;
+	}
+	if(h[2]){
+		/* bands beyond the register executors: chunked sweep, one CTA per job (rare: an indel run of several hundred bases) */
+		CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORKK + 1, 0, 8, c->stream));
+		const int grid = (int)std::min<uint64_t>(h[2], (uint64_t)c->n_sm * 2);
+		k_refine_wide<<<grid, REFW_NT, 0, c->stream>>>(c->s3.as<RefJob>() + 2 * (size_t)nt, (uint32_t)h[2], d_soff, SL.pairs.as<zmo_pair_t>(), d_tasks, dev_reads(c), A.P, c->s1.as<int>(), c->arena.as<uint32_t>(), c->s6.as<uint32_t>(), d_recs, ctr, CTR_WORKK + 1, CTR_CELLS_GAP); c->launches++;
 	}
 	CUDA_TRY(cudaGetLastError());
 	return 0;

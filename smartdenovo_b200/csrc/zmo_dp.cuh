@@ -373,3 +373,124 @@ __device__ void band_global(const BandSmem &S, const uint32_t *colpk /*query*/, 
 	out.qe = qlen; out.te = tlen;
 	ex_sync<NT>();
 }
+
+/*
+ * kswx_refine_alignment's sweep + walk (kswx.h:602-655) for bands wider than the register executors: global alignment of the
+ * query (rows, rowpk, ql) against the target (columns, colpk, tl) inside the per-row band [zb[i], ze[i]) (both arrays monotone).
+ * H(-1,-1) = 0, every other neighbour outside the previous row's band reads as -10000 (the reference's rolling rows are only ever
+ * written inside the bands, and the bands never move left).  Columns are swept in chunks of NT*C with the H / E rows in global
+ * memory (H0, H1, Ev: tl + 2 ints each, indexed by absolute column); the F chain is the same max-plus scan as in band_extend with a
+ * carry between chunks.  z: ql * band_row_words<NT,C>(wmax) words, one nibble per cell at column offset j - zb[i].  The walk runs
+ * on thread 0 (this path serves the rare alignment with an indel run of several hundred bases).  Ops are emitted in walk order.
+ */
+template<int NT, int C>
+__device__ void band_refine(const BandSmem &S, const uint32_t *rowpk, int ql, const uint32_t *colpk, int tl, const int *zb, const int *ze, int wmax,
+		const DPPar &P, uint32_t *z, uint32_t *cig, int cig_cap, DPOut &out, unsigned long long *cells_acc, int tid){
+	constexpr int NW = NT / 32;
+	constexpr int PC = NT * C;
+	const int lane = tid & 31, warp = tid >> 5;
+	const int IE = P.I + P.E, DE = P.D + P.E, E = P.E, CE = C * P.E;
+	const int rw = band_row_words<NT, C>(wmax);
+	int *Hp = S.H0, *Hc = S.H1;
+	unsigned long long cells = 0;
+	int pbeg = 0, pend = 0;
+	for(int i = 0; i < ql; i++){
+		const int beg = zb[i], end = ze[i];
+		const uint32_t qb = pk_base(rowpk, i);
+		int chunk = 0;
+		cells += (unsigned long long)(end > beg? end - beg : 0);
+		for(int cb = beg; cb < end; cb += PC, chunk++){
+			const int j0 = cb + tid * C;
+			int m[C], e[C];
+			unsigned long long xw = 0; const int xs = 62 - ((j0 & 15) << 1);
+			if(j0 < end){ const int w0 = j0 >> 4; xw = (((unsigned long long)colpk[w0] << 32) | colpk[w0 + 1]) ^ (0x5555555555555555ull * qb); }
+			#pragma unroll
+			for(int k = 0; k < C; k++){
+				const int j = j0 + k;
+				if(j < end){
+					int hd, ee;
+					if(i == 0){ hd = j == 0? 0 : ZMO_NEG; ee = ZMO_NEG; }
+					else {
+						hd = (j - 1 >= pbeg && j - 1 < pend)? Hp[j - 1] : ZMO_NEG;
+						ee = (j >= pbeg && j < pend)? S.Ev[j] : ZMO_NEG;
+					}
+					m[k] = hd + (((xw >> (xs - 2 * k)) & 3ull)? P.X : P.M);
+					e[k] = ee;
+				} else { m[k] = ZMO_BIGNEG; e[k] = ZMO_BIGNEG; }
+			}
+			int b = ZMO_BIGNEG;
+			#pragma unroll
+			for(int k = 0; k < C; k++){ const int t2 = m[k] + DE; b += E; if(b < t2) b = t2; }
+			int incl = b - tid * CE;
+			#pragma unroll
+			for(int d = 1; d < 32; d <<= 1){ const int o = __shfl_up_sync(0xffffffffu, incl, d); if(lane >= d && o > incl) incl = o; }
+			int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+			if(lane == 0) excl = ZMO_BIGNEG;
+			if(NW > 1){
+				int *sr = S.sred + (chunk & 1) * NW;
+				if(lane == 31) sr[warp] = incl;
+				__syncthreads();
+				for(int w2 = 0; w2 < warp; w2++){ const int o = sr[w2]; if(o > excl) excl = o; }
+			}
+			if(NW == 1) __syncwarp();
+			const int fcarry = (cb == beg)? ZMO_NEG : S.smisc[1 + (chunk & 1)];
+			int f = fcarry + tid * CE;
+			if(tid > 0){ const int o = (tid - 1) * CE + excl; if(o > f) f = o; }
+			uint32_t zw = 0;
+			#pragma unroll
+			for(int k = 0; k < C; k++){
+				const int j = j0 + k;
+				if(j < end){
+					const int mm = m[k]; int ee = e[k]; int h; uint32_t d;
+					if(mm >= ee){ d = 0; h = mm; } else { d = 1; h = ee; }
+					if(h < f){ d = 2; h = f; }
+					Hc[j] = h;
+					const int t1 = mm + IE; ee += E; if(ee > t1) d |= 4u; else ee = t1;
+					S.Ev[j] = ee;
+					const int t2 = mm + DE; f += E; if(f > t2) d |= 8u; else f = t2;
+					zw |= d << (k << 2);
+					if(j == end - 1) S.smisc[0] = h;
+				} else f += E;
+			}
+			z[(size_t)i * rw + chunk * NT + tid] = zw;
+			if(tid == NT - 1) S.smisc[1 + ((chunk + 1) & 1)] = f;
+		}
+		ex_sync<NT>();
+		{ int *sw = Hp; Hp = Hc; Hc = sw; }
+		pbeg = beg; pend = end;
+	}
+	out.score = (ql > 0 && ze[ql - 1] == tl && ze[ql - 1] > zb[ql - 1])? S.smisc[0] : ZMO_NEG;
+	ex_sync<NT>();
+	if(tid == 0){
+		int ii = ql - 1, jj = tl - 1, st = 0, mat = 0, mis = 0, ins = 0, del = 0, n = 0;
+		uint32_t cur_op = 0xF, cur_len = 0;
+		while(ii >= 0 && jj >= 0){
+			if(jj < zb[ii] || jj >= ze[ii]) break;        /* the reference reads outside its traceback here (undefined); stop instead */
+			const int rel = jj - zb[ii];
+			const int ch = rel / PC, r2 = rel - ch * PC;
+			const uint32_t nib = (z[(size_t)ii * rw + ch * NT + r2 / C] >> ((r2 % C) << 2)) & 0xFu;
+			uint32_t op;
+			if(st == 0) st = nib & 3u; else if(st == 1) st = (nib & 4u)? 1 : 0; else st = (nib & 8u)? 2 : 0;
+			if(st == 0){ if(pk_base(rowpk, ii) == pk_base(colpk, jj)) mat++; else mis++; ii--; jj--; op = 0; }
+			else if(st == 1){ ii--; ins++; op = 1; }
+			else { jj--; del++; op = 2; }
+			if(op == cur_op) cur_len++;
+			else { if(cur_len){ if(n < cig_cap) cig[n] = (cur_len << 4) | cur_op; n++; } cur_op = op; cur_len = 1; }
+		}
+		if(ii >= 0){
+			ins += ii + 1;
+			if(cur_op == 1u) cur_len += ii + 1; else { if(cur_len){ if(n < cig_cap) cig[n] = (cur_len << 4) | cur_op; n++; } cur_op = 1; cur_len = ii + 1; }
+		}
+		if(jj >= 0){
+			del += jj + 1;
+			if(cur_op == 2u) cur_len += jj + 1; else { if(cur_len){ if(n < cig_cap) cig[n] = (cur_len << 4) | cur_op; n++; } cur_op = 2; cur_len = jj + 1; }
+		}
+		if(cur_len){ if(n < cig_cap) cig[n] = (cur_len << 4) | cur_op; n++; }
+		S.smisc[4] = mat; S.smisc[5] = mis; S.smisc[6] = ins; S.smisc[7] = del; S.smisc[8] = n;
+		if(cells_acc) atomicAdd(cells_acc, cells);
+	}
+	ex_sync<NT>();
+	out.mat = S.smisc[4]; out.mis = S.smisc[5]; out.ins = S.smisc[6]; out.del = S.smisc[7]; out.ncig = S.smisc[8];
+	out.qe = ql; out.te = tl;
+	ex_sync<NT>();
+}

@@ -7,6 +7,8 @@
 #include "zmo_winalign.cuh"
 
 struct RefJob { uint32_t task; int ql, tl; unsigned long long band, scratch, out; uint32_t out_cap, pad; };
+#define REFW_NT 256            /* executor of the wide-band fallback: 256 threads x 7 columns per chunk */
+#define REFW_C 7
 #define REF_SEQW 1280          /* staged sequence words kept in shared memory by a refine executor (<= ~10 kb per side) */
 __global__ void k_refine_size(const zmo_record_t *recs, uint32_t nt, unsigned long long *rows, unsigned long long *outw){
 	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -16,7 +18,7 @@ __global__ void k_refine_size(const zmo_record_t *recs, uint32_t nt, unsigned lo
 	rows[t] = v? (unsigned long long)ql + 2 : 0; outw[t] = v? (unsigned long long)(ql + tl + 4) : 0;
 }
 __global__ void k_refine_band(zmo_record_t *recs, uint32_t nt, const uint32_t *ops, const unsigned long long *row_off, const unsigned long long *out_off, int W,
-		int *bands, RefJob *jobs, unsigned long long *njobs, unsigned long long *scr_words, unsigned long long *too_wide){
+		int *bands, RefJob *jobs, unsigned long long *njobs, unsigned long long *scr_words){
 	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if(t >= nt) return;
 	scr_words[t] = 0;
@@ -66,11 +68,12 @@ __global__ void k_refine_band(zmo_record_t *recs, uint32_t nt, const uint32_t *o
 	int wmax = 1;
 	{ int lim = tl; for(int i = ql - 1; i >= 0; i--){ if(ze[i] > lim) ze[i] = lim; else lim = ze[i]; if(ze[i] - zb[i] > wmax) wmax = ze[i] - zb[i]; } }
 	const int cls = wmax <= RegCap<32, 7>::ncol? 0 : (wmax <= RegCap<CL3_NT, CL3_C>::ncol? 1 : 2);
-	if(cls == 2){ atomicAdd(too_wide, 1ULL); return; }
-	const unsigned long long zwords = (unsigned long long)ql * (cls == 0? 32 : CL3_NT * RegCap<CL3_NT, CL3_C>::WPT);
+	/* class 2: band beyond the register executors (an indel run of several hundred bases): chunked sweep with its rows in the job's scratch */
+	const unsigned long long zwords = cls == 2? (unsigned long long)ql * band_row_words<REFW_NT, REFW_C>(wmax) + 3ull * (unsigned long long)(tl + 2)
+		: (unsigned long long)ql * (cls == 0? 32 : CL3_NT * RegCap<CL3_NT, CL3_C>::WPT);
 	const unsigned long long seq = (unsigned long long)((ql + 15) >> 4) + ((tl + 15) >> 4) + 4;
 	scr_words[t] = (zwords + seq + 31) & ~31ull;
-	RefJob J; J.task = t; J.ql = ql; J.tl = tl; J.band = 3 * R + (unsigned long long)(ql + 2); J.scratch = 0; J.out = out_off[t]; J.out_cap = (uint32_t)(ql + tl + 4); J.pad = (uint32_t)cls;
+	RefJob J; J.task = t; J.ql = ql; J.tl = tl; J.band = 3 * R + (unsigned long long)(ql + 2); J.scratch = (unsigned long long)wmax;      /* widest row */ J.out = out_off[t]; J.out_cap = (uint32_t)(ql + tl + 4); J.pad = (uint32_t)cls;
 	jobs[cls * (size_t)nt + atomicAdd(njobs + cls, 1ULL)] = J;
 }
 template<int NT, int C>
@@ -127,6 +130,42 @@ __global__ void __launch_bounds__(CL3_NT, 3) k_refine_cta(const RefJob *jobs, ui
 		__syncthreads();
 		if(jn >= njobs) break;
 		run_refine_job<CL3_NT, CL3_C>(jobs[jn], scr_off, pairs, tasks, R, P, bands, arena, out_ops, recs, S, s_seq, ctr + ctr_cells, tid);
+		__syncthreads();
+	}
+}
+/* wide-band fallback (class 2 of k_refine_band): one CTA per job, band_refine (zmo_dp.cuh) with H / E rows and sequences in the job's scratch */
+__global__ void __launch_bounds__(REFW_NT) k_refine_wide(const RefJob *jobs, uint32_t njobs, const unsigned long long *scr_off, const zmo_pair_t *pairs, const AlnTask *tasks, DevReads R, DPPar P,
+		const int *bands, uint32_t *arena, uint32_t *out_ops, zmo_record_t *recs, unsigned long long *ctr, int ctr_work, int ctr_cells){
+	__shared__ int s_red[2 * (REFW_NT / 32)];
+	__shared__ int s_misc[16];
+	__shared__ uint32_t s_job;
+	const int tid = threadIdx.x;
+	while(1){
+		if(tid == 0) s_job = (uint32_t)atomicAdd(ctr + ctr_work, 1ULL);
+		__syncthreads();
+		const uint32_t jn = s_job;
+		__syncthreads();
+		if(jn >= njobs) break;
+		const RefJob J = jobs[jn];
+		const AlnTask T = tasks[J.task]; const zmo_pair_t pr = pairs[T.pair_idx]; zmo_record_t r = recs[J.task];
+		const int wmax = (int)J.scratch;
+		uint32_t *scr = arena + scr_off[J.task];
+		uint32_t *z = scr; scr += (size_t)J.ql * band_row_words<REFW_NT, REFW_C>(wmax);
+		BandSmem S; S.H0 = (int*)scr; S.H1 = S.H0 + (J.tl + 2); S.Ev = S.H1 + (J.tl + 2); S.cap_mask = 0; S.sred = s_red; S.sredk = nullptr; S.smisc = s_misc;
+		scr += 3 * (size_t)(J.tl + 2);
+		const int qw = (J.ql + 15) >> 4;
+		uint32_t *qpk = scr, *tpk = scr + qw + 1;
+		stage_packed<REFW_NT>(view_pb2(R, pr.cid, T.dir, r.qb, 1), J.ql, qpk, tid);
+		stage_packed<REFW_NT>(view_pb1(R, pr.qid, r.tb, 1), J.tl, tpk, tid);
+		__syncthreads();
+		uint32_t *cig = out_ops + J.out; DPOut o;
+		band_refine<REFW_NT, REFW_C>(S, qpk, J.ql, tpk, J.tl, bands + J.band, bands + J.band + (J.ql + 2), wmax, P, z, cig, (int)J.out_cap, o, ctr + ctr_cells, tid);
+		for(int a = tid; a < o.ncig / 2; a += REFW_NT){ const uint32_t x = cig[a]; cig[a] = cig[o.ncig - 1 - a]; cig[o.ncig - 1 - a] = x; }
+		if(tid == 0){
+			r.score = o.score; r.mat = o.mat; r.mis = o.mis; r.ins = o.ins; r.del = o.del; r.aln = o.mat + o.mis + o.ins + o.del;
+			r.cigar_off = J.out; r.n_cigar = (uint32_t)o.ncig;
+			recs[J.task] = r;
+		}
 		__syncthreads();
 	}
 }

@@ -104,3 +104,26 @@ def call_global(lib, fn_name, q, t, w, sc=(2, -5, 3, 1, 3, 1)):
     M, X, od, ed, oi, ei = sc
     n = getattr(lib, fn_name)(len(q), q.ctypes.data_as(C.c_void_p), len(t), t.ctypes.data_as(C.c_void_p), M, X, od, ed, oi, ei, w, C.byref(score), cig, cap)
     return score.value, list(cig[:n])
+
+
+def write_long_indel_reads(path, seed=5):
+    """five reads over one 12 kb genome, 4% noise; read w1 carries a 1,000-base insertion and w2 a 900-base deletion, so that alignments
+    against them hold indel runs of ~800-1,000 bases (with -n: refinement bands beyond the 1,639 columns of the register executors)"""
+    rng = np.random.default_rng(seed)
+
+    def mut(s, r=0.04):
+        o = []
+        for ch in s:
+            u = rng.random()
+            if u < r / 3:
+                continue
+            o.append("ACGT"[rng.integers(0, 4)] if u < 2 * r / 3 else ch)
+            if rng.random() < r / 3:
+                o.append("ACGT"[rng.integers(0, 4)])
+        return "".join(o)
+    g = "".join("ACGT"[i] for i in rng.integers(0, 4, 12000))
+    ins = "".join("ACGT"[i] for i in rng.integers(0, 4, 1000))
+    reads = [mut(g[0:9000]), mut(g[500:4500] + ins + g[4500:9500]), mut(g[1000:5000] + g[5900:10900]), mut(g[2000:11000]), mut(g[0:8000])]
+    with open(path, "w") as f:
+        for i, s in enumerate(reads):
+            f.write(">w%d\n%s\n" % (i, s))

@@ -32,5 +32,11 @@ with tempfile.TemporaryDirectory() as d:
         fa, extra = t._side_inputs(sub, gen, case)
         t._run(ref, fa, str(sub / "ref.ovl"), extra)
         out[case] = t._digest(str(sub / "ref.ovl"))
+    sub = pathlib.Path(d) / "long_indel"
+    sub.mkdir()
+    from conftest import write_long_indel_reads
+    write_long_indel_reads(str(sub / "w.fa"))
+    t._run(ref, str(sub / "w.fa"), str(sub / "ref.ovl"), t.LONG_INDEL_ARGS)
+    out["refine_long_indel"] = t._digest(str(sub / "ref.ovl"))
 json.dump(out, open(os.path.join(HERE, "ovl_digests.json"), "w"), indent=1, sort_keys=True)
 print(json.dumps(out, indent=1))

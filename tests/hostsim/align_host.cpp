@@ -64,7 +64,7 @@ static void run_lists(const JobLists &L, const uint32_t *n, const uint32_t *firs
 /*
  * q = pb1 forward, c FORWARD with strand dir; win = n_win x {q span, c span, n_anchors}, anc = the windows' anchors back to back
  * (6 ints each).  out = {score, tb, te, qb, qe, aln, mat, mis, ins, del}; stats = {jobs per class x 6, windows kept}.  Returns the number
- * of CIGAR ops, -1 if no window region survived (record not ok), -2 on a capacity overflow, -4 if -n needs a band beyond the executors.
+ * of CIGAR ops, -1 if no window region survived (record not ok), -2 on a capacity overflow.
  */
 extern "C" int sim_pair_align(const uint8_t *q, int qlen, const uint8_t *c, int clen, int dir, const int *win, int n_win, const int *anc,
 		int w, int ew, int Wcap, int zovl, float min_id, int M, int X, int O, int E, int T, int refine, int finish_warp,
@@ -134,11 +134,10 @@ extern "C" int sim_pair_align(const uint8_t *q, int qlen, const uint8_t *c, int 
 		/* refine_records (zmo_align.cu) for one task */
 		unsigned long long rows = 0, outw = 0; unsigned long long *prow = &rows, *pout = &outw;
 		emu::launch(1, 128, [=](){ k_refine_size(drec, nt, prow, pout); });
-		std::vector<int> bands(rows * 3 + 16, 0x7EEEEEEE); std::vector<RefJob> rj(2 * nt + 2);
+		std::vector<int> bands(rows * 3 + 16, 0x7EEEEEEE); std::vector<RefJob> rj(3 * nt + 2);
 		unsigned long long rc[4] = {0, 0, 0, 0}, row_off[2] = {0, rows}, out_off[2] = {0, outw}, scr_words[2] = {0, 0};
 		int *db = bands.data(); RefJob *drj = rj.data(); unsigned long long *prc = rc, *dsw = scr_words; const unsigned long long *dro = row_off, *doo2 = out_off;
-		emu::launch(1, 64, [=](){ k_refine_band(drec, nt, ops, dro, doo2, A.w, db, drj, prc, dsw, prc + 2); });
-		if(rc[2]) return -4;
+		emu::launch(1, 64, [=](){ k_refine_band(drec, nt, ops, dro, doo2, A.w, db, drj, prc, dsw); });
 		unsigned long long scr_off[2] = {0, scr_words[0]}; const unsigned long long *dso = scr_off;
 		std::vector<uint32_t> rarena(scr_words[0] + 64, 0xDEADBEEFu); ref_ops.assign(outw + 16, 0u);
 		uint32_t *ra = rarena.data(), *ro = ref_ops.data();
@@ -146,6 +145,8 @@ extern "C" int sim_pair_align(const uint8_t *q, int qlen, const uint8_t *c, int 
 		ctr[0] = 0; ctr[3] = 0;
 		if(rc[0]) emu::launch(1, 128, [=](){ k_refine_warp(drj, (uint32_t)prc[0], dso, dp, dt, R, P, db, ra, ro, drec, cp, 0, 2); });
 		if(rc[1]) emu::launch(1, CL3_NT, [=](){ k_refine_cta(drj + nt, (uint32_t)prc[1], dso, dp, dt, R, P, db, ra, ro, drec, cp, 3, 2); });
+		ctr[4] = 0;
+		if(rc[2]) emu::launch(1, REFW_NT, [=](){ k_refine_wide(drj + 2 * nt, (uint32_t)prc[2], dso, dp, dt, R, P, db, ra, ro, drec, cp, 4, 2); });
 		ops = ro;
 	}
 	out[0] = rec.score; out[1] = rec.tb; out[2] = rec.te; out[3] = rec.qb; out[4] = rec.qe; out[5] = rec.aln; out[6] = rec.mat; out[7] = rec.mis; out[8] = rec.ins; out[9] = rec.del;

@@ -165,8 +165,7 @@ extern "C" int sim_window_align(const uint8_t *q, int qlen, const uint8_t *c, in
  * -n refinement of one stitched alignment through k_refine_size / k_refine_band / k_refine_warp|k_refine_cta: q = pb1 forward, c given
  * FORWARD with strand dir, the alignment by its start (tb on q, qb on c's strand), ends and CIGAR (alignment order).  The exclusive
  * scans the product does with CUB between the kernels are trivial for one task.  out = score, tb, te, qb, qe, aln, mat, mis, ins, del;
- * *cls_out = executor class (0 warp, 1 CTA); returns the number of new CIGAR ops, -1 if the band is wider than the CTA executor
- * (the product rejects such a run), -3 if the record came back not ok.
+ * *cls_out = executor class (0 warp, 1 CTA, 2 wide-band fallback); returns the number of new CIGAR ops, -3 if the record came back not ok.
  */
 extern "C" int sim_refine(const uint8_t *q, int qlen, const uint8_t *c, int clen, int dir, int tb, int te, int qb, int qe, const uint32_t *cigar_in, int n_in,
 		int W, int M, int X, int O, int E, int *out, uint32_t *cigar_out, int cigar_cap, int *cls_out){
@@ -180,19 +179,19 @@ extern "C" int sim_refine(const uint8_t *q, int qlen, const uint8_t *c, int clen
 	unsigned long long rows = 0, outw = 0;
 	zmo_record_t *dr = &rec; unsigned long long *prow = &rows, *pout = &outw;
 	emu::launch(1, 64, [=](){ k_refine_size(dr, 1u, prow, pout); });
-	std::vector<int> bands(rows * 3 + 16, 0x7EEEEEEE); std::vector<RefJob> jobs(2 * 1 + 2);
-	unsigned long long ctr[8] = {0, 0, 0, 0, 0, 0, 0, 0};      /* [0] work warp, [1] work cta, [2] cells, [4..5] njobs per class, [6] too wide */
+	std::vector<int> bands(rows * 3 + 16, 0x7EEEEEEE); std::vector<RefJob> jobs(3 * 1 + 2);
+	unsigned long long ctr[8] = {0, 0, 0, 0, 0, 0, 0, 0};      /* [0] work warp, [1] work cta, [2] cells, [3] work wide, [4..6] njobs per class */
 	unsigned long long row_off[2] = {0, rows}, out_off[2] = {0, outw}, scr_words[2] = {0, 0};
 	const uint32_t *dops = ops.data(); int *db = bands.data(); RefJob *dj = jobs.data(); unsigned long long *cp = ctr;
 	const unsigned long long *dro = row_off, *doo = out_off; unsigned long long *dsw = scr_words;
-	emu::launch(1, 64, [=](){ k_refine_band(dr, 1u, dops, dro, doo, W, db, dj, cp + 4, dsw, cp + 6); });
-	if(ctr[6]) return -1;
+	emu::launch(1, 64, [=](){ k_refine_band(dr, 1u, dops, dro, doo, W, db, dj, cp + 4, dsw); });
 	unsigned long long scr_off[2] = {0, scr_words[0]};
 	std::vector<uint32_t> arena(scr_words[0] + 64, 0xDEADBEEFu), out_ops(outw + 16, 0u);
 	const unsigned long long *dso = scr_off; uint32_t *ar = arena.data(), *oo = out_ops.data(); const AlnTask *dt = &task; const zmo_pair_t *dp = &pair;
-	*cls_out = ctr[5]? 1 : 0;
+	*cls_out = ctr[6]? 2 : (ctr[5]? 1 : 0);
 	if(ctr[4]) emu::launch(1, 128, [=](){ k_refine_warp(dj, (uint32_t)cp[4], dso, dp, dt, R, P, db, ar, oo, dr, cp, 0, 2); });
 	if(ctr[5]) emu::launch(1, CL3_NT, [=](){ k_refine_cta(dj + 1, (uint32_t)cp[5], dso, dp, dt, R, P, db, ar, oo, dr, cp, 1, 2); });
+	if(ctr[6]) emu::launch(1, REFW_NT, [=](){ k_refine_wide(dj + 2, (uint32_t)cp[6], dso, dp, dt, R, P, db, ar, oo, dr, cp, 3, 2); });
 	if(!rec.ok) return -3;
 	out[0] = rec.score; out[1] = rec.tb; out[2] = rec.te; out[3] = rec.qb; out[4] = rec.qe; out[5] = rec.aln; out[6] = rec.mat; out[7] = rec.mis; out[8] = rec.ins; out[9] = rec.del;
 	for(uint32_t k = 0; k < rec.n_cigar && (int)k < cigar_cap; k++) cigar_out[k] = out_ops[rec.cigar_off + k];

@@ -243,8 +243,6 @@ def _refine_both(sim, orc, q, c, d, tb, qb, cig, W=50):
     cls = C.c_int(-1)
     gn = sim.sim_refine(q.ctypes.data_as(C.c_void_p), len(q), c.ctypes.data_as(C.c_void_p), len(c), d, tb, tb + tl, qb, qb + ql, cin, len(cig),
                         W, 2, -5, -3, -1, go, gc, cap, C.byref(cls))
-    if gn == -1:
-        return None
     assert gn >= 0, gn
     en = orc.orc_refine(cs.ctypes.data_as(C.c_void_p), qb, q.ctypes.data_as(C.c_void_p), tb, W, 2, -5, -3, -1, cin, len(cig), eo, ec, cap)
     assert list(go) == list(eo), (list(go), list(eo))
@@ -253,8 +251,8 @@ def _refine_both(sim, orc, q, c, d, tb, qb, cig, W=50):
 
 
 def test_refine_kernels(dp_sim, oracle_lib):
-    """-n: k_refine_size / k_refine_band (per-row band from the CIGAR, widened around indel runs, made monotone) and the warp / CTA
-    executors of the variable-band sweep (reg_refine) against the oracle's restatement of kswx_refine_alignment (kswx.h:483-659)"""
+    """-n: k_refine_size / k_refine_band (per-row band from the CIGAR, widened around indel runs, made monotone), the warp / CTA
+    executors of the variable-band sweep (reg_refine) and the wide-band fallback k_refine_wide against the oracle's restatement of kswx_refine_alignment (kswx.h:483-659)"""
     rng = np.random.default_rng(21)
     seen = set()
     for trial in range(10):
@@ -278,10 +276,15 @@ def test_refine_kernels(dp_sim, oracle_lib):
         used_t = sum(op >> 4 for op in crude if (op & 15) in (0, 2))
         crude += [((ql - used_q) << 4) | 1, ((tl - used_t) << 4) | 2]
         seen.add(_refine_both(dp_sim, oracle_lib, q, c, d, tb, qb, crude, W=50))
-    assert {0, 1} <= seen          # both executor classes ran
-    # a run of > ~800 inserted bases needs a band beyond the CTA executor: the product rejects the run instead of differing
-    g = rng.integers(0, 4, 3000).astype(np.uint8)
-    assert _refine_both(dp_sim, oracle_lib, g, g, 0, 0, 0, [(100 << 4), (900 << 4) | 1, (900 << 4) | 2, (1100 << 4)]) is None
+    assert {0, 1} <= seen          # both register executor classes ran
+    # indel runs of ~800+ bases need a band beyond the 1,639 columns of the CTA executor: wide-band fallback (band_refine, zmo_dp.cuh),
+    # including bands of more than one 1,792-column chunk
+    g = rng.integers(0, 4, 6000).astype(np.uint8)
+    h = mutate(rng, g)
+    for d in (0, 1):
+        c = h if d == 0 else (3 - h[::-1]).astype(np.uint8)
+        assert _refine_both(dp_sim, oracle_lib, g, c, d, 0, 0, [(100 << 4), (900 << 4) | 1, (900 << 4) | 2, (1100 << 4)]) == 2
+        assert _refine_both(dp_sim, oracle_lib, g, c, d, 30, 10, [(300 << 4), (1500 << 4) | 2, (200 << 4), (1400 << 4) | 1, (500 << 4)], W=20) == 2
 
 
 def _rand_ops(rng, n, first_op=None):

@@ -7,7 +7,7 @@ import subprocess
 
 import pytest
 
-from conftest import REF_DIR, REPO
+from conftest import REF_DIR, REPO, write_long_indel_reads
 
 pytestmark = pytest.mark.gpu
 EXE = os.path.join(REPO, "smartdenovo_b200", "bin", "wtzmo")
@@ -62,6 +62,19 @@ def test_experimental_warp_stitch_gives_the_same_bytes(tmp_path, gen_reads, orac
     env = dict(os.environ, ZMO_FINISH_WARP="1")
     _compare(tmp_path, gen_reads, oracle_bin, ["-n", "200", "-L", "6000", "-G", "60000", "-s", "1"], ["-k", "16", "-s", "200", "-m", "0.6"], env=env)
     _compare(tmp_path, gen_reads, oracle_bin, ["-n", "150", "-L", "5000", "-G", "50000", "-s", "3"], ["-k", "16", "-s", "200", "-m", "0.6", "-n"], env=env)
+
+
+@pytest.mark.skipif(os.environ.get("ZMO_TEST_EXPERIMENTAL", "0") == "0", reason="wide-band -n fallback not yet run on the device (set ZMO_TEST_EXPERIMENTAL=1)")
+def test_refine_n_long_indel_runs(tmp_path, oracle_bin):
+    """-n with refinement bands beyond the register executors (indel runs of 800-1,000 bases): k_refine_wide / band_refine, bit-exact in
+    the host simulation (tests/test_dp_hostsim.py::test_refine_kernels); before this fallback existed such a run was rejected with an error"""
+    fa = str(tmp_path / "w.fa")
+    write_long_indel_reads(fa)
+    extra = ["-k", "16", "-s", "200", "-m", "0.5", "-n"]
+    _run(_checker(oracle_bin), fa, str(tmp_path / "ref.ovl"), extra)
+    _run(EXE, fa, str(tmp_path / "gpu.ovl"), extra)
+    ref = open(tmp_path / "ref.ovl", "rb").read()
+    assert ref == open(tmp_path / "gpu.ovl", "rb").read() and ref.count(b"\n") >= 8
 
 
 def test_overfull_batches_are_split(tmp_path, gen_reads, oracle_bin):

@@ -9,7 +9,7 @@ import subprocess
 
 import pytest
 
-from conftest import REPO
+from conftest import REPO, write_long_indel_reads
 
 GOLDEN = os.path.join(REPO, "tests", "golden", "ovl_digests.json")
 CASES = {
@@ -114,3 +114,26 @@ def test_oracle_side_inputs_match_golden_digest(case, tmp_path, gen_reads, oracl
     fa, extra = _side_inputs(tmp_path, gen_reads, case)
     _run(oracle_bin, fa, str(tmp_path / "orc.ovl"), extra)
     assert _digest(str(tmp_path / "orc.ovl")) == gold[case]
+
+
+LONG_INDEL_ARGS = ["-k", "16", "-s", "200", "-m", "0.5", "-n"]
+
+
+def test_oracle_refine_with_long_indel_runs(tmp_path, oracle_bin, ref_bin):
+    """-n on alignments holding indel runs of 800-1,000 bases (kswx_refine_alignment widens its band by the run length, kswx.h:524-560)"""
+    import re
+    fa = str(tmp_path / "w.fa")
+    write_long_indel_reads(fa)
+    _run(ref_bin, fa, str(tmp_path / "ref.ovl"), LONG_INDEL_ARGS)
+    _run(oracle_bin, fa, str(tmp_path / "orc.ovl"), LONG_INDEL_ARGS)
+    ref = open(tmp_path / "ref.ovl", "rb").read()
+    assert ref == open(tmp_path / "orc.ovl", "rb").read()
+    assert sum(1 for l in ref.split(b"\n") if l and max(int(n) for n in re.findall(rb"(\d+)[ID]", l.split(b"\t")[16])) >= 800) >= 4
+    assert _digest(str(tmp_path / "ref.ovl")) == json.load(open(GOLDEN))["refine_long_indel"]
+
+
+def test_oracle_refine_with_long_indel_runs_golden(tmp_path, oracle_bin):
+    fa = str(tmp_path / "w.fa")
+    write_long_indel_reads(fa)
+    _run(oracle_bin, fa, str(tmp_path / "orc.ovl"), LONG_INDEL_ARGS)
+    assert _digest(str(tmp_path / "orc.ovl")) == json.load(open(GOLDEN))["refine_long_indel"]
