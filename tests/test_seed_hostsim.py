@@ -134,3 +134,42 @@ def test_dot_kernel_matches_oracle(seedk_sim, oracle_lib):
     a, b = next(pairs(602, 1))
     n, out = run_dot_kernel(seedk_sim, a, b[:300], ztot=10 ** 6)
     assert out[0] == 0 and out[5] == 0
+
+
+def test_seeding_stage_batch(seedk_sim, oracle_lib):
+    """the whole device side of zmo_pair_windows for a batch of pairs sharing query reads: z-index of the batch (k_z_scan, k_z_heads,
+    k_z_slots with the hashed slot filter, k_z_ranges), chunk-parallel hits (k_hit), rank cap + expansion (k_expand), unpacking with tie
+    flags (k_unpack, k_pair_offsets) -- zmo_seedfront_kernels.cuh, with std:: sorts / scans where seed_prepare calls CUB -- then k_p_seed;
+    every pair must give the oracle's match count, chain weights, windows and anchors"""
+    reads = []
+    for a, b in pairs(800, 3):
+        reads += [a, b]
+    rng = np.random.default_rng(9)
+    reads.append(rng.integers(0, 4, 7).astype(np.uint8))          # shorter than z: no z-mers at all
+    plist = [(0, 1), (2, 3), (4, 5), (0, 3), (1, 0), (2, 1), (0, 6), (6, 0), (5, 4), (0, 0)]
+    seqs = np.ascontiguousarray(np.concatenate(reads), np.uint8)
+    lens = (C.c_int * len(reads))(*[len(r) for r in reads])
+    flat = (C.c_int * (2 * len(plist)))(*[v for p in plist for v in p])
+    nwin = 0
+    for zcut in (64, 3):          # -Z 3: the per-slot rank cap cuts most repeated z-mers
+        for which, (q, c) in enumerate(plist):
+            exp = expected(oracle_lib, reads[q], reads[c], zcut=zcut)
+            got = None
+            for F in (2, 8, 32):
+                nh, na = C.c_int(0), C.c_int(0)
+                ovl = (C.c_int * 2)()
+                wcap, acap = 4096, 1 << 18
+                wins = (C.c_int * (7 * wcap))()
+                anc = (C.c_int * (6 * acap))()
+                tie = (C.c_int * len(plist))()
+                nz = (C.c_int * len(plist))()
+                nw = seedk_sim.simk_batch_windows(seqs.ctypes.data_as(C.c_void_p), lens, len(reads), flat, len(plist), 10, 1, zcut, 2, 800, 400, 200, 300, 3200,
+                                                  F, which, tie, nz, C.byref(nh), ovl, wins, wcap, anc, acap, C.byref(na))
+                if nw >= 0:
+                    got = (nh.value, list(ovl), list(wins[: 7 * nw]), list(anc[: 6 * na.value]))
+                    assert nz[which] == nh.value
+                    break
+            assert got is not None
+            assert got == exp, (zcut, which, q, c)
+            nwin += len(exp[2]) // 7
+    assert nwin > 10
