@@ -1856,6 +1856,32 @@ int orc_refine(u8 *query, int qb, u8 *target, int tb, int W, int M, int X, int O
 	n = (int)cg.n; for(i=0;i<n&&i<cigar_cap;i++) cigar_out[i] = cg.a[i];
 	vec_free(cg); return n;
 }
+/* global k-mer index over reads [beg, end) of a read set given as 0..3 codes back to back (index_wtzmo, wtzmo.c:349-430) and the candidate
+ * event stream of query read qid against it (query_wtzmo, wtzmo.c:433-562): events with union length >= kovl in ascending
+ * (target<<1|strand) order as tkey/ol pairs.  *kcut_io < 2: automatic K, written back.  idx_stats = {distinct k-mers, postings kept}. */
+int orc_candidates(const u8 *seqs, const int *lens, int nreads, int beg, int end, int qid, int ksize, int hk, int ksave, int kovl, u32 *kcut_io,
+		u64 *idx_stats, u32 *ev_out, int ev_cap){
+	static const char L[4] = {'A', 'C', 'G', 'T'};
+	zparams_t par = orc_par(10, 1, 64, 2, 800, 400, 200, 300, 3200);
+	readset_t rs; kindex_t ix; eventv ev; size_t o = 0, i; int r, n = 0; char *tmp;
+	memset(&rs, 0, sizeof(rs)); memset(&ix, 0, sizeof(ix)); vec_init(ev);
+	par.ksize = ksize; par.hk = hk; par.ksave = ksave; par.kovl = kovl;
+	for(r=0;r<nreads;r++){
+		char name[32]; int nl = sprintf(name, "s%d", r);
+		tmp = malloc((size_t)lens[r] + 1);
+		for(i=0;i<(size_t)lens[r];i++) tmp[i] = L[seqs[o + i] & 3];
+		rs_add_read(&rs, name, nl, tmp, (u32)lens[r]); free(tmp); o += (size_t)lens[r];
+	}
+	rs.n_rd = (u32)nreads;
+	kindex_build(&ix, &rs, (u32)beg, (u32)end, &par, kcut_io);
+	idx_stats[0] = ix.n_ent; idx_stats[1] = ix.n_post;
+	candidate_events(&rs, &ix, (u32)qid, &par, &ev);
+	for(i=0;i<ev.n;i++) if(ev.a[i].ol >= (u32)kovl){ if(n < ev_cap){ ev_out[2 * n] = ev.a[i].tkey; ev_out[2 * n + 1] = ev.a[i].ol; } n ++; }
+	vec_free(ev); kindex_free(&ix);
+	for(r=0;r<nreads;r++) free(rs.reads.a[r].name);
+	vec_free(rs.reads); free(rs.bits);
+	return n;
+}
 /* pure per-pair alignment of one strand (wtzmo.c:1017-1034): windows -> per-window regions -> region filter -> stitched alignment
  * (left extension, gaps, right extension) -> optional -n refinement.  pb2 = c on the strand of the windows; win = n_win x
  * {n_anchors}, anc as in orc_window_align (windows' anchors back to back).  Returns -1 if no region survived, else the number of
