@@ -73,7 +73,7 @@ __global__ void k_refine_band(zmo_record_t *recs, uint32_t nt, const uint32_t *o
 		: (unsigned long long)ql * (cls == 0? 32 : CL3_NT * RegCap<CL3_NT, CL3_C>::WPT);
 	const unsigned long long seq = (unsigned long long)((ql + 15) >> 4) + ((tl + 15) >> 4) + 4;
 	scr_words[t] = (zwords + seq + 31) & ~31ull;
-	RefJob J; J.task = t; J.ql = ql; J.tl = tl; J.band = 3 * R + (unsigned long long)(ql + 2); J.scratch = (unsigned long long)wmax;      /* widest row */ J.out = out_off[t]; J.out_cap = (uint32_t)(ql + tl + 4); J.pad = (uint32_t)cls;
+	RefJob J; J.task = t; J.ql = ql; J.tl = tl; J.band = 3 * R + (unsigned long long)(ql + 2); J.scratch = (unsigned long long)wmax /* widest row: sizes the traceback of the wide-band fallback */; J.out = out_off[t]; J.out_cap = (uint32_t)(ql + tl + 4); J.pad = (uint32_t)cls;
 	jobs[cls * (size_t)nt + atomicAdd(njobs + cls, 1ULL)] = J;
 }
 template<int NT, int C>
