@@ -13,13 +13,15 @@ import pytest
 from conftest import REPO, call_ext, call_global, mutate
 
 SC = (2, -5, -3, -1, -50)   # -M -X -O -E -T defaults (wtzmo.c:1574-1578)
+# compile-time experiments of the kernels (e.g. ZMO_SIM_DEFINES="-DZMO_EXP_WALK_RUNS") are checked with the same tests
+SIM_DEFINES = os.environ.get("ZMO_SIM_DEFINES", "").split()
 
 
 @pytest.fixture(scope="module")
 def dp_sim():
     out = os.path.join(REPO, "tests", "_build", "libdp_host.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    subprocess.run(["g++", "-O1", "-std=c++17", "-I" + os.path.join(REPO, "tests", "hostsim", "emu"), "-fPIC", "-shared", "-o", out,
+    subprocess.run(["g++", "-O1", "-std=c++17"] + SIM_DEFINES + ["-I" + os.path.join(REPO, "tests", "hostsim", "emu"), "-fPIC", "-shared", "-o", out,
                     os.path.join(REPO, "tests", "hostsim", "dp_host.cpp")], check=True)
     return C.CDLL(out)
 
@@ -386,7 +388,7 @@ def test_finish_kernels(dp_sim, warp):
 def align_sim():
     out = os.path.join(REPO, "tests", "_build", "libalign_host.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    subprocess.run(["g++", "-O1", "-std=c++17", "-I" + os.path.join(REPO, "tests", "hostsim", "emu"), "-fPIC", "-shared", "-o", out,
+    subprocess.run(["g++", "-O1", "-std=c++17"] + SIM_DEFINES + ["-I" + os.path.join(REPO, "tests", "hostsim", "emu"), "-fPIC", "-shared", "-o", out,
                     os.path.join(REPO, "tests", "hostsim", "align_host.cpp")], check=True)
     return C.CDLL(out)
 
