@@ -38,6 +38,20 @@ __device__ __forceinline__ void cig_cat(uint32_t *c, uint32_t &n, const uint32_t
 	else for(; i < len; i++) c[n++] = src[i];
 }
 
+#ifdef ZMO_EXP_ANCHOR_REGS
+/* EXPERIMENT (compile with -DZMO_EXP_ANCHOR_REGS, off by default): the first n <= 32 logical bases of a view as one 64-bit word, base k at
+ * bits 63-2k..62-2k, cut out of at most three packed words (only words that hold requested bases are touched) */
+__device__ __forceinline__ unsigned long long view_load64(const SeqView &s, int n){
+	const int p0 = s.step == 1? s.start : s.start - 31;            /* first position of the forward 32-base chunk */
+	const int lo = s.step == 1? s.start : s.start - (n - 1), hi = s.step == 1? s.start + n - 1 : s.start;      /* positions really needed */
+	const int i0 = p0 >> 4, sh = (p0 & 15) << 1, wl = lo >> 4, wh = hi >> 4;
+	const unsigned long long w0 = (i0 >= wl && i0 <= wh)? __ldg(s.w + i0) : 0u, w1 = (i0 + 1 >= wl && i0 + 1 <= wh)? __ldg(s.w + i0 + 1) : 0u, w2 = (i0 + 2 >= wl && i0 + 2 <= wh)? __ldg(s.w + i0 + 2) : 0u;
+	unsigned long long v = (w0 << 32) | w1;
+	if(sh) v = (v << sh) | (w2 >> (32 - sh));
+	if(s.step != 1){ const unsigned long long u = __brevll(v); v = ((u >> 1) & 0x5555555555555555ull) | ((u & 0x5555555555555555ull) << 1); }
+	return s.comp? ~v : v;
+}
+#endif
 /* warp-per-window executor */
 __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *items, uint32_t nitems, const AlnTask *tasks, const zmo_pair_t *pairs,
 		const DevWin *wins, const DevZPair *anchors, DevReads R, AlnPar A, uint32_t *arena, unsigned long long slab_words, int max_rows,
@@ -123,17 +137,29 @@ __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *ite
 				const uint32_t la = p.len1, lb = p.len2; uint32_t sa = 0, sb = 0;
 				int y_score = 0, y_aln = 0, y_mat = 0, y_ins = 0, y_del = 0;
 				uint32_t blk2[96]; uint32_t n2 = 0; bool bad = false;
+#ifdef ZMO_EXP_ANCHOR_REGS
+				/* anchors are z-mer spans (a few tens of bases): keep both in registers instead of one cached global load per base */
+				const bool inreg = la <= 32u && lb <= 32u;
+				const unsigned long long RA = inreg? view_load64(a, (int)la) : 0ull, RB = inreg? view_load64(b, (int)lb) : 0ull;
+				#define ANC_A(k) (inreg? (uint32_t)(RA >> (62 - 2 * (int)(k))) & 3u : sv_base(a, (int)(k)))
+				#define ANC_B(k) (inreg? (uint32_t)(RB >> (62 - 2 * (int)(k))) & 3u : sv_base(b, (int)(k)))
+#else
+				#define ANC_A(k) sv_base(a, (int)(k))
+				#define ANC_B(k) sv_base(b, (int)(k))
+#endif
 				while(sa < la || sb < lb){
-					const uint32_t ca = sa < la? sv_base(a, sa) : 4u, cb = sb < lb? sv_base(b, sb) : 5u;
+					const uint32_t ca = sa < la? ANC_A(sa) : 4u, cb = sb < lb? ANC_B(sb) : 5u;
 					if(ca != cb){ bad = true; break; }
-					uint32_t ea = sa + 1; while(ea < la && sv_base(a, ea) == ca) ea++;
-					uint32_t eb = sb + 1; while(eb < lb && sv_base(b, eb) == cb) eb++;
+					uint32_t ea = sa + 1; while(ea < la && ANC_A(ea) == ca) ea++;
+					uint32_t eb = sb + 1; while(eb < lb && ANC_B(eb) == cb) eb++;
 					const uint32_t na = ea - sa, nbb = eb - sb;
 					if(na < nbb){ y_aln += nbb; y_mat += na; y_ins += nbb - na; y_score += na * P.M + P.I + (int)(nbb - na) * P.E; if(n2 < 94){ cig_put(blk2, n2, 0, na); cig_put(blk2, n2, 1, nbb - na); } }
 					else if(na == nbb){ y_aln += na; y_mat += na; y_score += na * P.M; if(n2 < 94) cig_put(blk2, n2, 0, na); }
 					else { y_aln += na; y_mat += nbb; y_del += na - nbb; y_score += nbb * P.M + P.D + (int)(na - nbb) * P.E; if(n2 < 94){ cig_put(blk2, n2, 0, nbb); cig_put(blk2, n2, 2, na - nbb); } }
 					sa = ea; sb = eb;
 				}
+				#undef ANC_A
+				#undef ANC_B
 				if(bad || y_aln == 0) ok = 0;
 				else {
 					s_misc[warp][9] = y_score; s_misc[warp][10] = y_aln; s_misc[warp][11] = y_mat; s_misc[warp][12] = y_ins; s_misc[warp][13] = y_del;

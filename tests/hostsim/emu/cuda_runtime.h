@@ -198,6 +198,7 @@ static inline int __clzll(long long v){ return v? __builtin_clzll((unsigned long
 static inline int __ffs(int v){ return __builtin_ffs(v); }
 static inline int __ffsll(long long v){ return __builtin_ffsll(v); }
 static inline unsigned __brev(unsigned v){ unsigned r = 0; for(int i = 0; i < 32; i++) if(v & (1u << i)) r |= 1u << (31 - i); return r; }
+static inline unsigned long long __brevll(unsigned long long v){ unsigned long long r = 0; for(int i = 0; i < 64; i++) if(v & (1ull << i)) r |= 1ull << (63 - i); return r; }
 static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh){ sh &= 31; return sh? (hi << sh) | (lo >> (32 - sh)) : hi; }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh){ sh &= 31; return sh? (lo >> sh) | (hi << (32 - sh)) : lo; }
 static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s){

@@ -18,5 +18,12 @@ timeout 1500 bash tools/dbg/sweep.sh "ZMO_BATCH_READS=384" "ZMO_BATCH_READS=256"
 ZMO_NVCC_DEFINES="-DZMO_EXP_WALK_RUNS" python -c 'import __graft_entry__ as g; g.build()' > "$out/build_walk_runs.log" 2>&1
 timeout 900 python -m pytest tests/test_gpu_dp.py tests/test_gpu_wtzmo.py -q -m gpu -x -k "not scale and not cfg2" > "$out/pytest_walk_runs.log" 2>&1; echo "pytest rc=$?" >> "$out/pytest_walk_runs.log"
 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > "$out/bench_walk_runs.json" 2> "$out/bench_walk_runs.err"
+# 5. second compile-time experiment: window anchors aligned from registers (zmo_winalign.cuh), alone and together with the first
+for defs in "-DZMO_EXP_ANCHOR_REGS" "-DZMO_EXP_ANCHOR_REGS -DZMO_EXP_WALK_RUNS"; do
+  tag=$(echo "$defs" | tr -d ' ' | tr -c 'A-Za-z0-9_\n' '_')
+  ZMO_NVCC_DEFINES="$defs" python -c 'import __graft_entry__ as g; g.build()' > "$out/build$tag.log" 2>&1
+  timeout 900 python -m pytest tests/test_gpu_wtzmo.py -q -m gpu -x -k "not scale and not cfg2" > "$out/pytest$tag.log" 2>&1; echo "pytest rc=$?" >> "$out/pytest$tag.log"
+  timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > "$out/bench$tag.json" 2> "$out/bench$tag.err"
+done
 python -c 'import __graft_entry__ as g; g.build()' >> "$out/build_walk_runs.log" 2>&1
 tail -3 "$out/pytest_gpu.log" "$out/pytest_walk_runs.log"; cat "$out/sweep.log"
