@@ -343,7 +343,7 @@ typedef struct {
 	zmo_record_t *pin_recs[WZ_MAX_CTX][WZ_PIN_WAVES]; size_t pin_recs_cap[WZ_MAX_CTX][WZ_PIN_WAVES]; u32 *pin_cig[WZ_MAX_CTX][WZ_PIN_WAVES]; size_t pin_cig_cap[WZ_MAX_CTX][WZ_PIN_WAVES];
 	pthread_mutex_t dev_mu[WZ_MAX_CTX];  /* one device call at a time per context */
 	pthread_mutex_t stat_mu;
-	u64 n_waves, n_wave_tasks; int wave_margin, wave_growth;
+	u64 n_waves, n_wave_tasks; int wave_margin, wave_growth, wave_maskcheck;
 } wz_t;
 
 static double now_s(void){ struct timeval tv; gettimeofday(&tv, NULL); return tv.tv_sec + 1e-6 * tv.tv_usec; }
@@ -708,6 +708,9 @@ static void batch_compute(wz_t *z, batch_t *b){
 			for(i=0;i<nr;i++){
 				size_t got = 0;
 				if(pos[i] < 0) continue;
+				/* ZMO_WAVE_MASKCHECK=1 (experiment, off by default): a read that the replay of the batches ahead has masked in the meantime
+				 * will be skipped at its turn (masks only grow), so its remaining waves are dropped; a stale read of masked[] only skips less */
+				if(z->wave_maskcheck && z->masked[b->reads.a[i].rd_id]){ pos[i] = -1; continue; }
 				for(k=(size_t)pos[i];k<sv[i].n&&got<chunk;k++){
 					const seed_t *sd = &sv[i].a[k]; zmo_task_t t;
 					if(sd->closed || b->pres[sd->cand_idx]) continue;
@@ -1026,6 +1029,7 @@ wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	z->call_pairs = (env = getenv("ZMO_CALL_PAIRS"))? atoi(env) : 0;     /* test hook: pairs per device call (0 = the library's limits) */
 	z->wave_margin = (env = getenv("ZMO_WAVE0"))? atoi(env) : 8;       /* seeds per read in the first DP wave (doubles per wave); < 0: align every seed up front */
 	z->wave_growth = (env = getenv("ZMO_WAVE_GROWTH"))? atoi(env) : 4; if(z->wave_growth < 2) z->wave_growth = 2;
+	z->wave_maskcheck = (env = getenv("ZMO_WAVE_MASKCHECK"))? atoi(env) : 0;
 	{ int q; for(q=0;q<WZ_MAX_CTX;q++) pthread_mutex_init(&z->dev_mu[q], NULL); pthread_mutex_init(&z->stat_mu, NULL); }
 	if(z->batch_reads < 1) z->batch_reads = 1;
 	fprintf(stderr, "[wtzmo-b200] loading long reads\n");

@@ -59,8 +59,9 @@ def test_sw_small_batches(tmp_path, gen_reads, oracle_bin):
 @pytest.mark.skipif(os.environ.get("ZMO_TEST_EXPERIMENTAL", "0") == "0", reason="opt-in kernel variants not yet measured on the device (set ZMO_TEST_EXPERIMENTAL=1)")
 def test_experimental_warp_stitch_gives_the_same_bytes(tmp_path, gen_reads, oracle_bin):
     """ZMO_FINISH_WARP=1: warp-per-task k_finish_warp instead of k_finish (bit-exact in the host simulation, tests/test_dp_hostsim.py)"""
-    env = dict(os.environ, ZMO_FINISH_WARP="1")
+    env = dict(os.environ, ZMO_FINISH_WARP="1", ZMO_WAVE_MASKCHECK="1")      # + the waves re-check masked[] (host experiment)
     _compare(tmp_path, gen_reads, oracle_bin, ["-n", "200", "-L", "6000", "-G", "60000", "-s", "1"], ["-k", "16", "-s", "200", "-m", "0.6"], env=env)
+    _compare(tmp_path, gen_reads, oracle_bin, ["-n", "300", "-L", "5000", "-G", "50000", "-s", "2"], ["-k", "16", "-s", "200", "-m", "0.6"], env=dict(env, ZMO_BATCH_READS="16"))
     _compare(tmp_path, gen_reads, oracle_bin, ["-n", "150", "-L", "5000", "-G", "50000", "-s", "3"], ["-k", "16", "-s", "200", "-m", "0.6", "-n"], env=env)
 
 

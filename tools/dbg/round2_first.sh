@@ -12,7 +12,7 @@ timeout 600 python bench.py --steps 3 --warmup 3 > "$out/bench_default.json" 2> 
 ZMO_FINISH_WARP=1 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > "$out/bench_finish_warp.json" 2> "$out/bench_finish_warp.err"
 # 3. speculation lag (+36% seeding at batch 384 x depth 2): smaller batches / different depth, with and without the warp stitch
 timeout 1500 bash tools/dbg/sweep.sh "ZMO_BATCH_READS=384" "ZMO_BATCH_READS=256" "ZMO_BATCH_READS=192" "ZMO_BATCH_READS=128" \
-  "ZMO_BATCH_READS=192 ZMO_DEPTH=3" "ZMO_BATCH_READS=256 ZMO_DEPTH=1" "ZMO_BATCH_READS=256 ZMO_FINISH_WARP=1" > "$out/sweep.log" 2>&1
+  "ZMO_BATCH_READS=192 ZMO_DEPTH=3" "ZMO_BATCH_READS=256 ZMO_DEPTH=1" "ZMO_BATCH_READS=256 ZMO_FINISH_WARP=1" "ZMO_WAVE_MASKCHECK=1" "ZMO_WAVE_MASKCHECK=1 ZMO_BATCH_READS=256" > "$out/sweep.log" 2>&1
 # 4. compile-time experiment: diagonal runs of the traceback walk taken in one go (reg_walk, zmo_dpr.cuh; bit-exact in the host simulation
 #    with ZMO_SIM_DEFINES=-DZMO_EXP_WALK_RUNS): parity on the device first, then the bench; the plain build() at the end restores the default
 ZMO_NVCC_DEFINES="-DZMO_EXP_WALK_RUNS" python -c 'import __graft_entry__ as g; g.build()' > "$out/build_walk_runs.log" 2>&1
