@@ -56,16 +56,15 @@ def test_sw_small_batches(tmp_path, gen_reads, oracle_bin):
         _compare(tmp_path, gen_reads, oracle_bin, ["-n", "120", "-L", "5000", "-G", "50000", "-s", "3"], ["-k", "16", "-s", "200", "-m", "0.6"], env=env)
 
 
-@pytest.mark.skipif(os.environ.get("ZMO_TEST_EXPERIMENTAL", "0") == "0", reason="opt-in kernel variants not yet measured on the device (set ZMO_TEST_EXPERIMENTAL=1)")
 def test_experimental_warp_stitch_gives_the_same_bytes(tmp_path, gen_reads, oracle_bin):
-    """ZMO_FINISH_WARP=1: warp-per-task k_finish_warp instead of k_finish (bit-exact in the host simulation, tests/test_dp_hostsim.py)"""
+    """ZMO_FINISH_WARP=1: warp-per-task k_finish_warp instead of k_finish (bit-exact in the host simulation, tests/test_dp_hostsim.py; opt-in
+    until its time has been measured)"""
     env = dict(os.environ, ZMO_FINISH_WARP="1", ZMO_WAVE_MASKCHECK="1")      # + the waves re-check masked[] (host experiment)
     _compare(tmp_path, gen_reads, oracle_bin, ["-n", "200", "-L", "6000", "-G", "60000", "-s", "1"], ["-k", "16", "-s", "200", "-m", "0.6"], env=env)
     _compare(tmp_path, gen_reads, oracle_bin, ["-n", "300", "-L", "5000", "-G", "50000", "-s", "2"], ["-k", "16", "-s", "200", "-m", "0.6"], env=dict(env, ZMO_BATCH_READS="16"))
     _compare(tmp_path, gen_reads, oracle_bin, ["-n", "150", "-L", "5000", "-G", "50000", "-s", "3"], ["-k", "16", "-s", "200", "-m", "0.6", "-n"], env=env)
 
 
-@pytest.mark.skipif(os.environ.get("ZMO_TEST_EXPERIMENTAL", "0") == "0", reason="wide-band -n fallback not yet run on the device (set ZMO_TEST_EXPERIMENTAL=1)")
 def test_refine_n_long_indel_runs(tmp_path, oracle_bin):
     """-n with refinement bands beyond the register executors (indel runs of 800-1,000 bases): k_refine_wide / band_refine, bit-exact in
     the host simulation (tests/test_dp_hostsim.py::test_refine_kernels); before this fallback existed such a run was rejected with an error"""
@@ -239,7 +238,7 @@ def test_scale_200k_reads_shard_matches_reference_golden(tmp_path, gen_reads):
 def test_cfg2_full_size_shard_properties(tmp_path, gen_reads):
     """BASELINE.json configs[1] at full size (50,000 PacBio-like reads x 10 kb, the bench workload): one `-P 10 -p 3` query shard, too
     large for a CPU run inside the suite, checked through the size-independent properties of tests/ovl_props.py -- every record inside its
-    reads, counts consistent with the spans, thresholds honoured, pairs unique, and for every 16th record the CIGAR walked over the actual
+    reads, counts consistent with the spans, thresholds honoured, pairs unique, and for every 32nd record the CIGAR walked over the actual
     bases must reproduce mat / mis / ins / del and the reported coordinates on the strand shown"""
     from ovl_props import check_ovl, load_fasta
     base = "/dev/shm" if os.path.isdir("/dev/shm") else str(tmp_path)
@@ -251,8 +250,8 @@ def test_cfg2_full_size_shard_properties(tmp_path, gen_reads):
         assert r.returncode == 0, r.stderr[-2000:]
         reads = load_fasta(fa)
         assert len(reads) == 50000
-        n, walked, cols = check_ovl(reads, out, min_score=200, min_id=0.6, walk_every=16)
-        assert n > 30000 and walked >= n // 16 and cols > 3 * 10 ** 8
+        n, walked, cols = check_ovl(reads, out, min_score=200, min_id=0.6, walk_every=32)
+        assert n > 30000 and walked >= n // 32 and cols > 3 * 10 ** 8
         contained = open(out + ".contained", "rb").read().split()
         assert len(contained) == len(set(contained)) > 100 and all(x in reads for x in contained)
     finally:

@@ -5,8 +5,8 @@
 set -u
 out=gpurun_out/r2_first; mkdir -p "$out"
 python -c 'import __graft_entry__ as g; g.build()' > "$out/build.log" 2>&1
-# 1. parity: the regular GPU suite plus the gated tests (k_finish_warp, wide-band -n fallback) and the cfg2 full-size property test
-ZMO_TEST_EXPERIMENTAL=1 timeout 1200 python -m pytest tests -q -m gpu -x > "$out/pytest_gpu.log" 2>&1; echo "pytest rc=$?" >> "$out/pytest_gpu.log"
+# 1. parity: the GPU suite (incl. k_finish_warp, the wide-band -n fallback and the cfg2 full-size property test, all green once at the end of round 1)
+timeout 1200 python -m pytest tests -q -m gpu -x > "$out/pytest_gpu.log" 2>&1; echo "pytest rc=$?" >> "$out/pytest_gpu.log"
 # 2. baseline bench line, then the opt-in stitch kernel (4% of the GPU time in r01_ncu_final.md was k_finish)
 timeout 600 python bench.py --steps 3 --warmup 3 > "$out/bench_default.json" 2> "$out/bench_default.err"
 ZMO_FINISH_WARP=1 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > "$out/bench_finish_warp.json" 2> "$out/bench_finish_warp.err"
