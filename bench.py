@@ -179,7 +179,7 @@ def main():
     n_job = max(wl["shards"], world)      # the shard size (work per GPU per step) does not depend on the number of GPUs: weak scaling
 
     def stats():
-        a = (C.c_double * 32)()
+        a = (C.c_double * 40)()      # wz_stats writes 35 values
         host.wz_stats(S, a)
         return list(a)
 
@@ -275,7 +275,9 @@ def main():
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
             "last_step_host_ms": {"device_calls": 1e3 * st1[3], "replay_format": 1e3 * st1[4]},
             "records_per_step": r_val["rec"] / args.steps, "aligned_bp_per_step": r_val["bp"] / args.steps,
-            "last_step_work": {"batches": st1[5], "pairs_seeded": st1[6], "pairs_aligned": st1[7], "alignments_consumed": st1[8], "demand_waves": st1[29], "demand_wave_tasks": st1[30]}}
+            "last_step_work": {"batches": st1[5], "pairs_seeded": st1[6], "pairs_aligned": st1[7], "alignments_consumed": st1[8], "demand_waves": st1[29], "demand_wave_tasks": st1[30],
+                               # speculation of the batch pipeline: reads put into batches, reads masked by the time of their turn, candidates of those reads (seeded for nothing)
+                               "reads_batched": st1[32], "reads_late_masked": st1[33], "cands_late_masked": st1[34]}}
     if world > 1:
         line["gathered_bytes"] = r_e2e["gathered"]
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(REPO, "oracle", "_ref", "wtzmo")):

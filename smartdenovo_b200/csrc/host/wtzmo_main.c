@@ -1145,6 +1145,7 @@ void wz_stats(wz_session_t *S, double *out){
 	for(i=0;i<7;i++) out[18 + i] = (double)ct[i];
 	out[25] = (double)(z->rs.n_rd + z->rs.n_qr); out[26] = (double)z->rs.nbases; out[27] = S->last_upload_s; out[28] = (double)S->upload_bytes;
 	out[29] = (double)z->n_waves; out[30] = (double)z->n_wave_tasks; out[31] = ms[8];
+	out[32] = (double)z->n_reads_batched; out[33] = (double)z->n_reads_late_masked; out[34] = (double)z->n_pairs_late_masked;      /* speculation: reads batched / masked by the time of their turn / their candidates */
 }
 
 void wz_close(wz_session_t *S){ if(S){ int q; for(q=S->z.n_ctx-1;q>=0;q--) if(S->z.ctxs[q]) zmo_ctx_destroy(S->z.ctxs[q]); free(S); } }
