@@ -179,7 +179,7 @@ def main():
     n_job = max(wl["shards"], world)      # the shard size (work per GPU per step) does not depend on the number of GPUs: weak scaling
 
     def stats():
-        a = (C.c_double * 40)()      # wz_stats writes 35 values
+        a = (C.c_double * host.wz_stats_n())()
         host.wz_stats(S, a)
         return list(a)
 

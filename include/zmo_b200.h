@@ -133,6 +133,8 @@ typedef struct {
 	int32_t  t_start, t_step, t_comp, tlen;
 	int32_t  init_score, W;                 /* W as passed to the reference (negative = exact band) */
 } zmo_dp_problem_t;
+/* cells: zmo_dp_global = the band width the doubling loop ended with (hzm_aln.h:1402-1417), extensions = 0; DP cell totals are in zmo_counters().
+ * Slices outside their reads, steps other than +-1 and bands <= 0 are rejected with ZMO_ERR_ARG. */
 typedef struct { int32_t score, qe, te, aln, mat, mis, ins, del; uint64_t cigar_off; uint32_t n_cigar; uint64_t cells; } zmo_dp_result_t;
 int zmo_dp_extend(zmo_ctx *ctx, int mode, const zmo_dp_problem_t *probs, uint32_t n,
                   zmo_dp_result_t *res, uint32_t *cigars, uint64_t cigar_cap, uint64_t *cigar_needed);

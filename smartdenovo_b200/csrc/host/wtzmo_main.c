@@ -1135,9 +1135,11 @@ int wz_run(wz_session_t *S, int n_job, int i_job, const char *out_path){
 /* out[0]=records [1]=aligned columns [2]=overlap wall s [3]=device-call s [4]=replay+format s [5]=batches [6]=pairs seeded
  * [7]=tasks aligned [8]=tasks consumed [9]=kernel launches (cumulative) [10..17]=stage ms (cumulative) [18..24]=counters (cumulative)
  * [25]=reads [26]=bases [27]=last upload s [28]=upload bytes */
+#define WZ_STATS_N 40   /* doubles written by wz_stats (callers size their buffer with wz_stats_n()) */
+int wz_stats_n(void){ return WZ_STATS_N; }
 void wz_stats(wz_session_t *S, double *out){
 	wz_t *z = &S->z; double ms[12], m1[12]; uint64_t ct[8], c1[8]; int i, q; u64 nl = 0;
-	memset(ms, 0, sizeof(ms)); memset(ct, 0, sizeof(ct));
+	memset(ms, 0, sizeof(ms)); memset(ct, 0, sizeof(ct)); for(i=0;i<WZ_STATS_N;i++) out[i] = 0;
 	for(q=0;q<z->n_ctx;q++){ zmo_stage_ms(z->ctxs[q], m1); zmo_counters(z->ctxs[q], c1); for(i=0;i<12;i++) ms[i] += m1[i]; for(i=0;i<8;i++) ct[i] += c1[i]; nl += zmo_kernel_launches(z->ctxs[q]); }
 	out[0] = (double)z->n_records; out[1] = (double)z->aln_cols; out[2] = S->last_overlap_s; out[3] = z->t_dev; out[4] = z->t_replay; out[5] = (double)z->n_batches;
 	out[6] = (double)z->n_pairs_seeded; out[7] = (double)z->n_tasks; out[8] = (double)z->n_tasks_used; out[9] = (double)nl;
@@ -1178,7 +1180,7 @@ int main(int argc, char **argv){
 		fclose(pf);
 	}
 	if((env = getenv("ZMO_STATS"))){
-		FILE *sf = fopen(env, "w"); double st[32]; const char *nm[8] = {"index", "candidates", "pair_windows", "window_align", "gap_global", "end_extend", "dotmatrix", "copy"};
+		FILE *sf = fopen(env, "w"); double st[WZ_STATS_N]; const char *nm[8] = {"index", "candidates", "pair_windows", "window_align", "gap_global", "end_extend", "dotmatrix", "copy"};
 		const char *cn[7] = {"cells_ext", "cells_win", "cells_gap", "zpairs", "postings", "h2d_bytes", "d2h_bytes"}; int k;
 		wz_stats(S, st);
 		if(sf){

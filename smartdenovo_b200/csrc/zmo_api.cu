@@ -11,7 +11,10 @@ int zmo_set_err(int code, const char *fmt, ...){
 }
 extern "C" const char *zmo_last_error(void){ return g_zmo_err.c_str(); }
 
+int zmo_seed_init_device(void);     /* zmo_seed.cu */
+
 static int ctx_init(zmo_ctx *c, int device, const zmo_params_t *par){
+	CUDA_TRY(cudaSetDevice(device));
 	cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, device));
 	if(prop.major < 10) return zmo_set_err(ZMO_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
 	c->device = device; c->n_sm = prop.multiProcessorCount; c->par = *par;
@@ -21,6 +24,7 @@ static int ctx_init(zmo_ctx *c, int device, const zmo_params_t *par){
 	if(c->d_ctr.reserve(CTR_TOTAL * 8)) return ZMO_ERR_CUDA;
 	CUDA_TRY(cudaMemsetAsync(c->d_ctr.p, 0, CTR_TOTAL * 8, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	if(int rc = zmo_seed_init_device()) return rc;
 	return ZMO_OK;
 }
 

@@ -68,12 +68,22 @@ static int dp_batch(zmo_ctx *c, int kind /*0 ext mode0, 1 ext mode1, 2 global*/,
 		zmo_dp_result_t *res, uint32_t *cigars, uint64_t cigar_cap, uint64_t *cigar_needed){
 	if(!c || (n && (!probs || !res))) return zmo_set_err(ZMO_ERR_ARG, "null argument");
 	if(n == 0){ if(cigar_needed) *cigar_needed = 0; return 0; }
+	CUDA_TRY(cudaSetDevice(c->device));
 	DPPar P = dp_par(c);
 	std::vector<DPJob> jl[4];       /* per executor class (global: class 3 = CTA, class 0 = warp) */
 	uint64_t scratch = 0, cig = 0;
 	for(uint32_t i = 0; i < n; i++){
 		const zmo_dp_problem_t &p = probs[i]; DPJob J; memset(&J, 0, sizeof(J));
 		if(p.q_rid >= c->st->n_reads || p.t_rid >= c->st->n_reads) return zmo_set_err(ZMO_ERR_ARG, "problem %u: read id out of range", i);
+		{
+			/* both slices must lie inside their reads: element k is base start + k*step */
+			const long long ql = c->st->h_rdlen[p.q_rid], tl = c->st->h_rdlen[p.t_rid];
+			const long long qa = p.q_start, qz = (long long)p.q_start + (long long)(p.qlen > 0? p.qlen - 1 : 0) * p.q_step;
+			const long long ta = p.t_start, tz = (long long)p.t_start + (long long)(p.tlen > 0? p.tlen - 1 : 0) * p.t_step;
+			if(p.qlen < 0 || p.tlen < 0 || (p.q_step != 1 && p.q_step != -1) || (p.t_step != 1 && p.t_step != -1)) return zmo_set_err(ZMO_ERR_ARG, "problem %u: negative length or step not +-1", i);
+			if((p.qlen > 0 && (qa < 0 || qa >= ql || qz < 0 || qz >= ql)) || (p.tlen > 0 && (ta < 0 || ta >= tl || tz < 0 || tz >= tl))) return zmo_set_err(ZMO_ERR_ARG, "problem %u: slice outside its read", i);
+			if(kind == 2 && wv[i] <= 0) return zmo_set_err(ZMO_ERR_ARG, "problem %u: band must be positive", i);
+		}
 		J.q_rid = p.q_rid; J.t_rid = p.t_rid; J.q_start = p.q_start; J.q_step = p.q_step; J.q_comp = p.q_comp; J.qlen = p.qlen;
 		J.t_start = p.t_start; J.t_step = p.t_step; J.t_comp = p.t_comp; J.tlen = p.tlen; J.init = p.init_score; J.Wp = p.W; J.Wmax = 0;
 		J.out_idx = i; J.cig_off = cig; J.cig_cap = (uint32_t)((p.qlen > 0? p.qlen : 0) + (p.tlen > 0? p.tlen : 0) + 4);

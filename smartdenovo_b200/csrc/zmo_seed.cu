@@ -141,6 +141,12 @@ int seed_prepare(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, int mode, See
 	return 0;
 }
 
+/* function attributes are per device: called by ctx_init for every context, with that context's device current */
+int zmo_seed_init_device(void){
+	CUDA_TRY(cudaFuncSetAttribute(k_p_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PS_WARPS * sizeof(PSSmem))));
+	return 0;
+}
+
 extern "C" int zmo_pair_windows(zmo_ctx *c, int slot, const zmo_pair_t *pairs, uint32_t np, zmo_pairseed_t *seeds, zmo_window_t *wins, uint64_t win_cap, uint64_t *win_needed){
 	if(!c || (np && (!pairs || !seeds))) return zmo_set_err(ZMO_ERR_ARG, "null argument");
 	if(slot < 0 || slot > 1) return zmo_set_err(ZMO_ERR_ARG, "slot must be 0 or 1");
@@ -164,8 +170,6 @@ extern "C" int zmo_pair_windows(zmo_ctx *c, int slot, const zmo_pair_t *pairs, u
 		SeedOut O; O.wins = SL.wins.as<DevWin>(); O.anc = SL.anchors.as<DevZPair>(); O.cap_wins = cap_w; O.cap_anc = cap_a; O.cur_wins = ctr + CTR_N1; O.cur_anc = ctr + CTR_N2; O.overflow = ctr + CTR_N3;
 		CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORK, 0, 8, c->stream));
 		{
-			static bool attr_set = false;
-			if(!attr_set){ CUDA_TRY(cudaFuncSetAttribute(k_p_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PS_WARPS * sizeof(PSSmem)))); attr_set = true; }
 			const int grid = (int)std::min<uint64_t>((np + PS_WARPS - 1) / PS_WARPS, (uint64_t)c->n_sm);      /* one CTA of PS_WARPS warps per SM (shared-memory bound) */
 			k_p_seed<<<grid, 32 * PS_WARPS, PS_WARPS * sizeof(PSSmem), c->stream>>>(W.cache_off, np, W.cache, W.tie, W.pc, dev_reads(c), c->s6.as<uint8_t>(), per, F, par, O, SL.seeds.as<zmo_pairseed_t>(), ctr + CTR_WORK); c->launches++;
 		}

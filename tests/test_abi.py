@@ -26,8 +26,21 @@ def test_exports_every_declared_symbol(built):
     for n in sorted(names):
         assert hasattr(lib, n), n
     host = C.CDLL(os.path.join(REPO, "smartdenovo_b200", "lib", "libwtzmo_host.so"))
-    for n in ("wz_open", "wz_upload", "wz_run", "wz_stats", "wz_close"):
+    for n in ("wz_open", "wz_upload", "wz_run", "wz_stats", "wz_stats_n", "wz_close"):
         assert hasattr(host, n), n
+
+
+def test_stats_buffer_contract(built):
+    """wz_stats writes exactly wz_stats_n() doubles; every buffer handed to it (main()'s ZMO_STATS path, bench.py) is sized from that
+    constant (round-1 advisor finding: a 32-element stack array under a 35-value writer)"""
+    host = C.CDLL(os.path.join(REPO, "smartdenovo_b200", "lib", "libwtzmo_host.so"))
+    n = host.wz_stats_n()
+    src = open(os.path.join(REPO, "smartdenovo_b200", "csrc", "host", "wtzmo_main.c")).read()
+    assert "#define WZ_STATS_N %d" % n in src
+    used = [int(x) for x in re.findall(r"out\[(\d+)\]", src)] + [int(x) + 7 for x in re.findall(r"out\[(\d+) \+ i\]", src)]      # out[b + i]: i < 8
+    assert used and max(used) < n
+    assert re.search(r"double st\[WZ_STATS_N\]", src) and not re.search(r"double st\[\d+\]", src)
+    assert "wz_stats_n()" in open(os.path.join(REPO, "bench.py")).read()
 
 
 def test_struct_layouts_match_header(built):
