@@ -2,27 +2,33 @@
 """bench.py -- aligned Gbp/s of the all-vs-all overlap hot path (BASELINE.json metric).
 
 A *step* is one complete overlap job `wtzmo -P n -p i` (the reference's own query sharding, wtzmo.c:1291,1314)
-over the resident read set: k-mer index build + candidate query + z-mer seeding + banded DP + state replay +
-.ovl text, for the 1/n of the query reads with rd_id % n == i.  Steps use consecutive shard indices, so every
-step is different work of the same shape.  The read set is synthetic (tools/gen_reads.c, seed 20240601+cfg).
+over the resident read set: k-mer index build + candidate query + z-mer seeding + banded DP (or dot-matrix blocks)
++ state replay + .ovl text, for the 1/n of the query reads with rd_id % n == i.  Steps use consecutive shard
+indices, so every step is different work of the same shape.  Read sets are synthetic (tools/gen_reads.c,
+seed 20240601+cfg).
 
-  value : whole-job aligned bp / time, reads already resident in HBM when the timed region starts
-  e2e   : same, but the timed region of every step also re-uploads the packed reads from host memory and, like
-          `value`, brings every record + CIGAR back to the host and formats the 17-column .ovl text
-  roofline : dominant kernel (banded end-extension DP): algorithmic bytes = 0.5 B per DP cell (4 traceback bits)
-          + packed sequence bytes, over the CUDA-event time of that kernel inside the timed steps
+  value    : whole-job aligned bp / time, reads already resident in HBM when the timed region starts
+  e2e      : same, but the timed region of every step also re-uploads the packed reads from host memory and, like
+             `value`, brings every record + CIGAR back to the host and formats the 17-column .ovl text
+  roofline : the stage with the largest CUDA-event time inside the timed steps, whatever it is (seeding, window
+             alignment, end extension + gap fill, dot-matrix): algorithmic bytes of SURVEY 8d over that time
+  parity   : after the timed regions the same session runs the query shard whose reference `-t 1` digest is committed
+             (tests/golden/scale_digests.json) and compares the bytes; under torchrun rank g checks job `-p g`
   cpu_baseline : the unmodified reference binary (oracle/_ref/wtzmo -t <cores>) on a bounded sub-shard
+  sub      : (N=1) short measurements of the other single-GPU configurations: cfg1 (configs[0]) and cfg3s (configs[2]
+             shape, dot-matrix mode), each with its own roofline entry and golden parity check
+  cli_whole_job : (N=1) wall time of the product binary on the whole workload (`-P 1`), process start to exit
 
-`--impl reference` times only the reference CPU binary on the same configuration.
+`--impl reference` times only the reference CPU binary on the same configuration: every step is the SAME shard
+(`-P shards -p i`) a step of our arm processes.
 Under torchrun (N>1) every rank owns a GPU and its own shard sequence -- the shard size is the same for every N (weak
-scaling, no data-path collective); the last step's records are gathered to rank 0 with one NCCL all-gather at the end of
-the timed region.
+scaling, no data-path collective); the last step's records are gathered to rank 0 at the end of the timed region.
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
-import shutil
 import subprocess
 import sys
 import tempfile
@@ -32,11 +38,21 @@ import time
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
-# configs[1] of BASELINE.json: 50k PacBio-like reads x 10 kb over a 4.6 Mb genome (108x), -k 16 -s 200 -m 0.6
+SW = ["-k", "16", "-s", "200", "-m", "0.6"]
+DOT = ["-k", "16", "-z", "10", "-Z", "16", "-U", "-1", "-m", "0.1", "-A", "1000"]
+# configs[0..2] of BASELINE.json (cfg3s = configs[2]'s shape at 1/10 of the reads, what one GPU step of a few seconds holds)
 WORKLOADS = {
-    "cfg1": dict(n=2000, L=8000, G=500000, model="pacbio", seed=20240602, flags=["-k", "16", "-s", "200", "-m", "0.6"], shards=1),
-    "cfg2": dict(n=50000, L=10000, G=4600000, model="pacbio", seed=20240603, flags=["-k", "16", "-s", "200", "-m", "0.6"], shards=int(os.environ.get("ZMO_BENCH_SHARDS", "10"))),
-    "cfg2s": dict(n=5000, L=10000, G=460000, model="pacbio", seed=20240603, flags=["-k", "16", "-s", "200", "-m", "0.6"], shards=5),
+    "cfg1": dict(n=2000, L=8000, G=500000, model="pacbio", seed=20240602, flags=SW, shards=1, dot=False, golden=("cfg1_full", 1)),
+    "cfg2": dict(n=50000, L=10000, G=4600000, model="pacbio", seed=20240603, flags=SW, shards=int(os.environ.get("ZMO_BENCH_SHARDS", "10")), dot=False, golden=("cfg2_P160_p%d", 160)),
+    "cfg2s": dict(n=5000, L=10000, G=460000, model="pacbio", seed=20240603, flags=SW, shards=5, dot=False, golden=None),
+    "cfg3s": dict(n=20000, L=15000, G=10000000, model="ont", seed=20240604, flags=DOT, shards=4, dot=True, golden=("cfg3s_dot_P4_p%d", 4)),
+}
+STAGES = ["index", "candidates", "pair_windows", "window_align", "gap_global", "end_extend", "dotmatrix", "copy"]
+# DRAM bytes (read + write) of ONE captured launch of a stage's dominant kernel, `ncu --set full`, keyed by the workload the capture was
+# taken on; absent = no capture of that kernel on that workload is committed.  alg_bytes = algorithmic bytes of the same launch.
+TRAFFIC = {
+    ("cfg2s", "window_align"): dict(kernel="k_window_align", dram_bytes=377.8e6, alg_bytes=0.85e9, source="profiles/r01_ncu_final.md"),
+    ("cfg2s", "dp_phase"): dict(kernel="k_ext_cta<128,13,1>", dram_bytes=233.6e6, alg_bytes=None, source="profiles/r01_ncu_final.md"),
 }
 
 
@@ -48,9 +64,14 @@ def ensure_reads(wl, tmpdir):
     gen = os.path.join(REPO, "tools", "_build", "gen_reads")
     fa = os.path.join(tmpdir, "reads_%d_%d_%d_%s_%d.fa" % (wl["n"], wl["L"], wl["G"], wl["model"], wl["seed"]))
     if not os.path.exists(fa):
-        sh([gen, "-n", str(wl["n"]), "-L", str(wl["L"]), "-G", str(wl["G"]), "-m", wl["model"], "-s", str(wl["seed"]), "-o", fa + ".tmp"])
-        os.replace(fa + ".tmp", fa)
+        sh([gen, "-n", str(wl["n"]), "-L", str(wl["L"]), "-G", str(wl["G"]), "-m", wl["model"], "-s", str(wl["seed"]), "-o", fa + ".tmp%d" % os.getpid()])
+        os.replace(fa + ".tmp%d" % os.getpid(), fa)
     return fa
+
+
+def workload_text(name, wl, n_job):
+    return "%s: %d synthetic %s reads x %d bp, genome %d bp, wtzmo %s; step = one `-P %d -p i` query shard incl. index build" % (
+        name, wl["n"], wl["model"], wl["L"], wl["G"], " ".join(wl["flags"]), n_job)
 
 
 class ClockSampler(threading.Thread):
@@ -80,24 +101,198 @@ class ClockSampler(threading.Thread):
                 "gpu_util_pct_median": ut[len(ut) // 2] if ut else None}
 
 
-def run_reference(fa, flags, n_job, i_job, threads, outdir, tag):
-    """unmodified reference binary on one shard; returns (aligned bp, overlap seconds)"""
-    ref = os.path.join(REPO, "oracle", "_ref", "wtzmo")
-    out = os.path.join(outdir, "ref_%s.ovl" % tag)
-    t0 = time.time()
-    r = subprocess.run([ref, "-t", str(threads), "-i", fa, "-f", "-o", out, "-P", str(n_job), "-p", str(i_job)] + flags, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
-    wall = time.time() - t0
-    if r.returncode != 0:
-        raise RuntimeError("reference wtzmo failed: " + r.stderr[-500:])
+def aligned_cols(path, dot):
     cols = 0
-    with open(out) as f:
+    with open(path) as f:
         for line in f:
             c = line.split("\t")
-            cols += int(c[12]) + int(c[13]) + int(c[14]) + int(c[15])
-    # overlap phase = "calculating overlaps" -> "Done" (wtzmo.c:1777-1780); the stamps have 1 s resolution, so
-    # subtract the measured load phase instead: time from start to the "calculating overlaps" line is not
-    # recoverable exactly, so report whole-process wall for small samples (load is < 2% of it)
-    return cols, wall
+            cols += max(int(c[4]) - int(c[3]), int(c[9]) - int(c[8])) if dot else int(c[12]) + int(c[13]) + int(c[14]) + int(c[15])
+    return cols
+
+
+def run_reference(fa, flags, n_job, i_job, threads, outdir, tag, dot=False):
+    """unmodified reference binary on one shard.  Returns (aligned bp, process wall s, overlap-phase s, load s): the phases are split at the
+    reference's own stderr stamps "calculating overlaps" / "Done" (wtzmo.c:1777-1780), timed here as the lines arrive (its date() has 1 s
+    resolution).  The overlap phase = index build + query + align + write, i.e. what a step of our arm does; load = FASTA parse + sort."""
+    ref = os.path.join(REPO, "oracle", "_ref", "wtzmo")
+    out = os.path.join(outdir, "ref_%s.ovl" % tag)
+    t0 = time.perf_counter()
+    p = subprocess.Popen([ref, "-t", str(threads), "-i", fa, "-f", "-o", out, "-P", str(n_job), "-p", str(i_job)] + flags, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    t_calc = t_done = None
+    tail = b""
+    while True:
+        ch = p.stderr.read1(65536)
+        if not ch:
+            break
+        now = time.perf_counter()
+        tail = (tail + ch)[-8192:]
+        if t_calc is None and b"calculating overlaps" in tail:
+            t_calc = now
+            tail = tail[tail.index(b"calculating overlaps") + 20:]
+        if t_calc is not None and b"] Done\n" in tail:       # the index build prints a "Done" of its own: the LAST one closes the overlap phase
+            t_done = now
+            tail = tail[tail.rindex(b"] Done\n") + 7:]
+    p.wait()
+    wall = time.perf_counter() - t0
+    if p.returncode != 0:
+        raise RuntimeError("reference wtzmo failed: " + tail[-500:].decode(errors="replace"))
+    cols = aligned_cols(out, dot)
+    t_calc = t_calc if t_calc is not None else t0
+    t_done = t_done if t_done is not None else t0 + wall
+    return cols, wall, t_done - t_calc, t_calc - t0
+
+
+def open_host():
+    host = C.CDLL(os.path.join(REPO, "smartdenovo_b200", "lib", "libwtzmo_host.so"))
+    host.wz_open.restype = C.c_void_p
+    host.wz_open.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int)]
+    host.wz_upload.argtypes = [C.c_void_p]
+    host.wz_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+    host.wz_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    host.wz_stats_n.restype = C.c_int
+    host.wz_close.argtypes = [C.c_void_p]
+    return host
+
+
+class Session:
+    """one `wtzmo` session through libwtzmo_host.so (the C host of the product binary as a library): reads parsed once, every run() is a
+    complete `-P n -p i` job from a clean state"""
+
+    def __init__(self, host, fa, flags, out_path):
+        self.host, self.out_path = host, out_path
+        argv = [b"wtzmo", b"-t", b"1", b"-i", fa.encode(), b"-f", b"-o", out_path.encode()] + [x.encode() for x in flags]
+        arr = (C.c_char_p * len(argv))(*argv)
+        rc = C.c_int(0)
+        self.S = host.wz_open(len(argv), arr, C.byref(rc))
+        if not self.S:
+            raise RuntimeError("wz_open failed rc=%d (no GPU / build missing: there is no CPU fallback)" % rc.value)
+
+    def upload(self):
+        if self.host.wz_upload(self.S):
+            raise RuntimeError("upload failed")
+
+    def run(self, n_job, i_job, out_path=None):
+        if self.host.wz_run(self.S, n_job, i_job, (out_path or self.out_path).encode()):
+            raise RuntimeError("wz_run failed")
+        return self.stats()
+
+    def stats(self):
+        a = (C.c_double * self.host.wz_stats_n())()
+        self.host.wz_stats(self.S, a)
+        return list(a)
+
+    def close(self):
+        self.host.wz_close(self.S)
+        self.S = None
+
+
+def load_golden():
+    try:
+        return json.load(open(os.path.join(REPO, "tests", "golden", "scale_digests.json")))
+    except Exception:
+        return {}
+
+
+def parity_check(sess, wl, job, tmp_out):
+    """run the golden query shard `-P n -p job` in this session and compare with the committed reference `-t 1` digest"""
+    if not wl.get("golden"):
+        return {"checked": False, "why": "no golden digest for this workload"}
+    pat, n_job = wl["golden"]
+    name = pat % (job % n_job) if "%d" in pat else pat
+    gold = load_golden().get(name)
+    if gold is None:
+        return {"checked": False, "why": "golden %s missing" % name}
+    sess.run(n_job, job % n_job, tmp_out)
+    data = open(tmp_out, "rb").read()
+    ok = hashlib.md5(data).hexdigest() == gold["md5"] and data.count(b"\n") == gold["lines"]
+    return {"checked": True, "ok": bool(ok), "golden": name, "job": "-P %d -p %d" % (n_job, job % n_job), "records": data.count(b"\n"),
+            "reference_t1_wall_s_where_made": gold.get("ref_wall_s")}
+
+
+def stage_roofline(wl_name, st0, st1, steps, peak, peaks_found):
+    """roofline entry of the stage with the largest CUDA-event time between two stats snapshots (SURVEY 8d's byte model:
+    DP = 0.5 B per cell (4 traceback bits); seeding / dot-matrix = 2 x 16 B per z-mer match (list written, then re-read sorted))"""
+    stage_ms = {n: st1[10 + i] - st0[10 + i] for i, n in enumerate(STAGES)}
+    stage_ms["dp_phase_wall"] = st1[31] - st0[31]
+    cells = {"end_extend": st1[18] - st0[18], "window_align": st1[19] - st0[19], "gap_global": st1[20] - st0[20]}
+    matches = st1[21] - st0[21]
+    # the end-extension + gap-fill executors run CONCURRENTLY (one stream per executor class): their cost is the wall time of that phase
+    groups = {
+        "dp_phase": (stage_ms["dp_phase_wall"], 0.5 * (cells["end_extend"] + cells["gap_global"]), cells["end_extend"] + cells["gap_global"], "k_ext_cta<64|128,7|13,1> + k_ext_warp<1> + k_glb_warp/k_glb_cta (concurrent)", "0.5 B x DP cells"),
+        "window_align": (stage_ms["window_align"], 0.5 * cells["window_align"], cells["window_align"], "window alignment (k_wa_lane / k_window_align)", "0.5 B x DP cells"),
+        "pair_windows": (stage_ms["pair_windows"], 32.0 * matches, matches, "k_p_seed + k_hit + k_expand + radix sorts (z-mer seeding)", "2 x 16 B x z-mer matches"),
+        "dotmatrix": (stage_ms["dotmatrix"], 32.0 * matches, matches, "k_p_dot + k_hit + k_expand + radix sorts (dot-matrix)", "2 x 16 B x z-mer matches"),
+    }
+    dom = max(groups, key=lambda k: groups[k][0])
+    ms, alg, units, kern, model = groups[dom]
+    s = ms / 1e3
+    ach = alg / s / 1e9 if s > 0 else 0.0
+    tr = TRAFFIC.get((wl_name, dom))
+    roof = {"bound": "hbm", "stage": dom, "kernel": kern, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
+            "traffic": tr["dram_bytes"] if tr else None,
+            "traffic_capture": tr if tr else "no ncu --set full capture of this stage's kernel on this workload is committed (profiles/ holds the captures that exist, taken on cfg2s)",
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks_found else "fallback 6650 (of fallback)",
+            "alg_bytes_model": model, "units_per_step": units / steps, "kernel_ms_per_step": ms / steps,
+            "units_per_s": units / s if s > 0 else 0.0,
+            "note": "kernel time = CUDA-event stage time summed over the contexts in flight (they overlap, so the sum can exceed the step wall); integer DP and the seeding scans are instruction/latency bound, not HBM bound (DESIGN.md)"}
+    if dom in ("dp_phase", "window_align"):
+        roof["gcells_per_s"] = roof["units_per_s"] / 1e9
+    fr = {}
+    for k, g in groups.items():
+        if g[0] > 0 and peak:
+            fr[k] = {"ms_per_step": g[0] / steps, "hbm_frac": g[1] / (g[0] / 1e3) / 1e9 / peak, "units_per_s": g[2] / (g[0] / 1e3)}
+    return roof, {k: v / steps for k, v in stage_ms.items()}, fr
+
+
+def sub_record(host, name, tmpdir, peak, peaks_found, steps=2):
+    """short measurement of another single-GPU configuration in its own session: 1 warm-up + `steps` timed steps, stage roofline, golden parity"""
+    import torch
+    wl = WORKLOADS[name]
+    fa = ensure_reads(wl, tmpdir)
+    out = os.path.join(tmpdir, "bench_sub_%s.ovl" % name)
+    t0 = time.perf_counter()
+    sess = Session(host, fa, wl["flags"], out)
+    t_open = time.perf_counter() - t0
+    sess.upload()
+    n_job = wl["shards"]
+    sess.run(n_job, 0)
+    torch.cuda.synchronize()
+    st0 = sess.stats()
+    t0 = time.perf_counter()
+    bp = rec = 0
+    for k in range(steps):
+        st = sess.run(n_job, (1 + k) % n_job)
+        bp += st[1]
+        rec += st[0]
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    st1 = sess.stats()
+    roof, stage_ms, _ = stage_roofline(name, st0, st1, steps, peak, peaks_found)
+    par = parity_check(sess, wl, 0, os.path.join(tmpdir, "parity_sub_%s.ovl" % name))
+    sess.close()
+    return {"workload": workload_text(name, wl, n_job), "value": bp / wall / 1e9, "unit": "Gbp/s", "steps": steps, "ms_per_step": 1e3 * wall / steps,
+            "records_per_step": rec / steps, "aligned_bp_per_step": bp / steps, "gpu_launches": int(st1[9] - st0[9]), "roofline": roof, "stage_ms_per_step": stage_ms,
+            "parity_checked": bool(par.get("checked") and par.get("ok")), "parity": par, "fasta_load_sort_s": t_open}
+
+
+def cli_whole_job(fa, wl, tmpdir):
+    """the product binary as a user runs it: one process, the whole job (`-P 1`), cold start (context creation, first-batch allocations) included"""
+    exe = os.path.join(REPO, "smartdenovo_b200", "bin", "wtzmo")
+    out = os.path.join(tmpdir, "cli_job.ovl")
+    stats = os.path.join(tmpdir, "cli_job.stats.json")
+    env = dict(os.environ, ZMO_STATS=stats)
+    t0 = time.perf_counter()
+    r = subprocess.run([exe, "-t", "1", "-i", fa, "-f", "-o", out] + wl["flags"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+    wall = time.perf_counter() - t0
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr[-300:])
+    s = json.load(open(stats))
+    for f in (out, out + ".contained", stats):
+        if os.path.exists(f):
+            os.remove(f)
+    return {"command": "wtzmo -t 1 -i reads.fa -fo out.ovl %s" % " ".join(wl["flags"]), "process_wall_s": wall, "overlap_phase_s": s["overlap_s"], "records": s["records"],
+            "aligned_bp": s["aligned_cols"], "gbp_per_s_over_process_wall": s["aligned_cols"] / wall / 1e9, "gbp_per_s_over_overlap_phase": s["aligned_cols"] / s["overlap_s"] / 1e9,
+            "note": "one job: fewer records than the sum of the -P 10 shards by design (a pair is found from one side only)"}
 
 
 def main():
@@ -106,8 +301,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("ZMO_BENCH_WORKLOAD", "cfg2"))
+    ap.add_argument("--workload", default=os.environ.get("ZMO_BENCH_WORKLOAD", "cfg2"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the cfg1 / cfg3s sub-records and the whole-job CLI run")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -118,37 +314,47 @@ def main():
     tmpdir = os.path.join(tmpdir, "zmo_bench")
     os.makedirs(tmpdir, exist_ok=True)
     metric = "aligned Gbp/sec (all-vs-all overlap)"
-    config = {"workload": "%s: %d synthetic %s reads x %d bp, genome %d bp, wtzmo %s; step = one `-P %d -p i` query shard incl. index build" % (
-        args.workload, wl["n"], wl["model"], wl["L"], wl["G"], " ".join(wl["flags"]), max(wl["shards"], world)),
-        "n_reads": wl["n"], "read_len": wl["L"], "genome": wl["G"], "shards": max(wl["shards"], world),
-        "l2": "inputs larger than L2 per step (every step streams a different shard: new candidates, match lists and traceback)"}
+    n_job = max(wl["shards"], world)      # the shard size (work per GPU per step) does not depend on the number of GPUs: weak scaling
+    config = {"workload": workload_text(args.workload, wl, n_job),
+              "n_reads": wl["n"], "read_len": wl["L"], "genome": wl["G"], "shards": n_job,
+              "l2": "inputs larger than L2 per step (every step streams a different shard: new candidates, match lists and traceback)"}
 
     import __graft_entry__ as ge
-    if rank == 0:
-        ge.build()
     if args.impl == "reference":
         if rank != 0:
             return 0
+        ge.build_checker()
         fa = ensure_reads(wl, tmpdir)
-        # bounded sample: a sub-shard of one step's shard so that K+W steps finish within minutes
-        sub = int(os.environ.get("ZMO_REF_SUBSHARD", "2"))       # 1 = exactly the shard a step of our arm processes
-        n_job = wl["shards"] * sub
-        times, bp = [], 0
+        # every step is exactly the shard a step of our arm processes (ZMO_REF_SUBSHARD > 1 would time 1/sub of it; not the default)
+        sub = int(os.environ.get("ZMO_REF_SUBSHARD", "1"))
+        nj = n_job * sub
+        walls, ovls, loads, bp = [], [], [], 0
         for s in range(args.warmup + args.steps):
-            cols, wall = run_reference(fa, wl["flags"], n_job, s % n_job, cores, tmpdir, "r%d" % s)
+            cols, wall, ovl_s, load_s = run_reference(fa, wl["flags"], nj, s % nj, cores, tmpdir, "r%d" % s, wl["dot"])
             if s >= args.warmup:
-                times.append(wall)
+                walls.append(wall)
+                ovls.append(ovl_s)
+                loads.append(load_s)
                 bp += cols
-        total = sum(times)
+        # the metric is defined over the overlap phase ("calculating overlaps" -> "Done", FASTA parse excluded), which is also
+        # what a step of our arm contains (index build + overlap on resident reads)
+        total = sum(ovls)
         val = bp / total / 1e9 if total > 0 else 0.0
         line = {"impl": "reference", "metric": metric, "value": val, "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * total / max(1, len(times)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "ms_per_step": 1e3 * total / max(1, len(ovls)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
                 "config": config,
-                "cpu_baseline": {"value": val, "unit": "Gbp/s", "cores": cores, "kind": "reference", "sample": "each step = `oracle/_ref/wtzmo -t %d -P %d -p i`: 1/%d of the query shard of one step of our arm, full index rebuilt per step like ours" % (cores, n_job, sub)},
+                "cpu_baseline": {"value": val, "unit": "Gbp/s", "cores": cores, "kind": "reference",
+                                 "sample": "each step = `oracle/_ref/wtzmo -t %d -P %d -p i`: %s, full index rebuilt per step like ours; timed over the reference's own overlap phase (stderr stamps \"calculating overlaps\" -> \"Done\", wtzmo.c:1777-1780)" % (
+                                     cores, nj, "the same query shard as one step of our arm" if sub == 1 else "1/%d of the query shard of one step of our arm" % sub)},
+                "reference_phases_s_per_step": {"overlap_phase": total / max(1, len(ovls)), "fasta_load_sort": sum(loads) / max(1, len(loads)), "process_wall": sum(walls) / max(1, len(walls))},
+                "value_over_process_wall": bp / sum(walls) / 1e9 if walls else None,
+                "equal_work": sub == 1,
                 "e2e": {"value": val, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
 
+    if rank == 0:
+        ge.build()
     import torch
     import torch.distributed as dist
     from smartdenovo_b200 import dist as zdist
@@ -162,44 +368,23 @@ def main():
         dist.barrier()
     fa = ensure_reads(wl, tmpdir)
 
-    host = C.CDLL(os.path.join(REPO, "smartdenovo_b200", "lib", "libwtzmo_host.so"))
-    host.wz_open.restype = C.c_void_p
-    host.wz_open.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int)]
-    host.wz_upload.argtypes = [C.c_void_p]
-    host.wz_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
-    host.wz_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
-    host.wz_close.argtypes = [C.c_void_p]
+    host = open_host()
     out_path = os.path.join(tmpdir, "bench_rank%d.ovl" % rank)
-    argv = [b"wtzmo", b"-t", b"1", b"-i", fa.encode(), b"-f", b"-o", out_path.encode()] + [x.encode() for x in wl["flags"]]
-    arr = (C.c_char_p * len(argv))(*argv)
-    rc = C.c_int(0)
-    S = host.wz_open(len(argv), arr, C.byref(rc))
-    if not S:
-        raise RuntimeError("wz_open failed rc=%d (no GPU / build missing: there is no CPU fallback)" % rc.value)
-    n_job = max(wl["shards"], world)      # the shard size (work per GPU per step) does not depend on the number of GPUs: weak scaling
-
-    def stats():
-        a = (C.c_double * host.wz_stats_n())()
-        host.wz_stats(S, a)
-        return list(a)
+    sess = Session(host, fa, wl["flags"], out_path)
 
     def step(idx, reupload):
-        if reupload and host.wz_upload(S):
-            raise RuntimeError("upload failed")
-        shard = zdist.shard_of(idx, rank, world, n_job)
-        if host.wz_run(S, n_job, shard, out_path.encode()):
-            raise RuntimeError("wz_run failed")
-        return stats()
+        if reupload:
+            sess.upload()
+        return sess.run(n_job, zdist.shard_of(idx, rank, world, n_job))
 
-    if host.wz_upload(S):
-        raise RuntimeError("upload failed")
+    sess.upload()
 
     def timed(nsteps, first_idx, reupload):
         """K steps bracketed by barrier + synchronize; device-side wall via CUDA events on the default stream + host wall"""
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        st0 = stats()
+        st0 = sess.stats()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t0 = time.perf_counter()
@@ -211,13 +396,13 @@ def main():
             rec += st[0]
         gathered = None
         if world > 1:
-            gathered, _blob = zdist.gather_record_file(out_path, device="cuda")     # one NCCL all-gather of sizes + one of records, to rank 0
+            gathered, _blob = zdist.gather_record_file(out_path, device="cuda")     # sizes + records to rank 0 over NCCL
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         wall = time.perf_counter() - t0
-        st1 = stats()
+        st1 = sess.stats()
         if world > 1:
             wall = zdist.max_over_ranks([wall], device="cuda")[0]
             bp, rec = zdist.sum_over_ranks([float(bp), float(rec)], device="cuda")
@@ -235,44 +420,27 @@ def main():
     sampler.join(timeout=2)
     value = r_val["bp"] / r_val["wall"] / 1e9
     e2e = r_e2e["bp"] / r_e2e["wall"] / 1e9
-    # roofline of the dominant kernel over the `value` region (stage timers are CUDA events on the library stream)
-    names = ["index", "candidates", "pair_windows", "window_align", "gap_global", "end_extend", "dotmatrix", "copy"]
-    st0, st1 = r_val["st0"], r_val["st1"]
-    stage_ms = {n: st1[10 + i] - st0[10 + i] for i, n in enumerate(names)}
-    stage_ms["dp_phase_wall"] = st1[31] - st0[31]
-    cells = {"end_extend": st1[18] - st0[18], "window_align": st1[19] - st0[19], "gap_global": st1[20] - st0[20]}
-    # dominant DP kernel group: the end-extension + gap-fill executors run CONCURRENTLY (one stream per executor class), so
-    # their cost is the wall time of that phase (CUDA events on the library stream), not the sum of overlapping kernels
-    groups = {"dp_phase": (stage_ms["dp_phase_wall"], cells["end_extend"] + cells["gap_global"], "k_ext_cta<64|128|256,1> + k_ext_warp<1> + k_glb_warp/k_glb_cta (concurrent)"),
-              "window_align": (stage_ms["window_align"], cells["window_align"], "k_window_align")}
-    dom = max(groups, key=lambda k: groups[k][0])
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    st0, st1 = r_val["st0"], r_val["st1"]
     launches = st1[9] - st0[9]
-    dom_s = groups[dom][0] / 1e3
-    alg_bytes = 0.5 * groups[dom][1]
-    achieved = alg_bytes / dom_s / 1e9 if dom_s > 0 else 0.0
-    roof = {"bound": "hbm", "kernel": groups[dom][2],
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-            # DRAM bytes (read + write) of ONE captured launch of the group's kernel: ncu --set full, profiles/r01_ncu_final.md
-            # (k_window_align launch id 0: 144.5 + 233.3 MB; k_ext_cta<128,13,1>: 26.2 + 207.4 MB); see traffic_profile for its algorithmic bytes
-            "traffic": {"window_align": 377.8e6, "dp_phase": 233.6e6}[dom],
-            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-            "alg_bytes_per_cell": 0.5, "cells_per_step": groups[dom][1] / args.steps, "kernel_ms_per_step": groups[dom][0] / args.steps,
-            "gcells_per_s": groups[dom][1] / dom_s / 1e9 if dom_s > 0 else 0.0,
-            "traffic_profile": {"kernel": "k_window_align", "dram_bytes_per_launch": 377.8e6, "launch_ms": 17.7, "alg_bytes_per_launch_est": 0.85e9,
-                                "source": "profiles/r01_ncu_final.md (ncu --set full, one launch on the cfg2s shard; short bridges keep their traceback in shared memory)"},
-            "note": "integer DP is ALU/latency bound, not HBM bound (see DESIGN.md): gcells_per_s is the number to optimise; kernel time = CUDA-event stage time summed over the contexts in flight"}
+    roof, stage_ms, stage_roofs = stage_roofline(args.workload, st0, st1, args.steps, peak, bool(peaks))
+    # parity of the timed workload: rank g runs the golden job `-p g` (untimed) and compares the bytes with the reference `-t 1` digest
+    par = parity_check(sess, wl, rank, os.path.join(tmpdir, "parity_rank%d.ovl" % rank))
+    par_all = bool(par.get("checked", False) and par.get("ok", False))
+    if world > 1:
+        par_all = zdist.sum_over_ranks([1.0 if par_all else 0.0], device="cuda")[0] == world
     line = {"metric": metric, "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * r_val["wall"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": config, "clocks": sampler.summary(),
             "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": r_e2e["h2d"], "d2h_bytes_per_step": r_e2e["d2h"], "ms_per_step": 1e3 * r_e2e["wall"] / args.steps},
             "gpu_launches": int(launches), "roofline": roof,
-            "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+            "parity_checked": bool(par_all), "parity": dict(par, ranks_checked=world),
+            "stage_ms_per_step": stage_ms, "stage_rooflines": stage_roofs,
             "last_step_host_ms": {"device_calls": 1e3 * st1[3], "replay_format": 1e3 * st1[4]},
             "records_per_step": r_val["rec"] / args.steps, "aligned_bp_per_step": r_val["bp"] / args.steps,
             "last_step_work": {"batches": st1[5], "pairs_seeded": st1[6], "pairs_aligned": st1[7], "alignments_consumed": st1[8], "demand_waves": st1[29], "demand_wave_tasks": st1[30],
@@ -280,15 +448,28 @@ def main():
                                "reads_batched": st1[32], "reads_late_masked": st1[33], "cands_late_masked": st1[34]}}
     if world > 1:
         line["gathered_bytes"] = r_e2e["gathered"]
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(REPO, "oracle", "_ref", "wtzmo")):
-        sub = int(os.environ.get("ZMO_REF_SUBSHARD", "16"))
+    sess.close()
+    if rank == 0 and world == 1 and not args.no_sub:
+        line["sub"] = {}
+        for name in ("cfg1", "cfg3s"):
+            if name == args.workload:
+                continue
+            try:
+                line["sub"][name] = sub_record(host, name, tmpdir, peak, bool(peaks))
+            except Exception as e:   # noqa: BLE001
+                line["sub"][name] = {"error": str(e)[:300]}
         try:
-            cols, wall = run_reference(fa, wl["flags"], n_job * sub, 0, cores, tmpdir, "cpu")
-            line["cpu_baseline"] = {"value": cols / wall / 1e9, "unit": "Gbp/s", "cores": cores, "kind": "reference",
-                                    "sample": "`oracle/_ref/wtzmo -t %d -P %d -p 0` = 1/%d of one bench step's shard, full index build included, %.1f s" % (cores, n_job * sub, sub, wall)}
+            line["cli_whole_job"] = cli_whole_job(fa, wl, tmpdir)
+        except Exception as e:   # noqa: BLE001
+            line["cli_whole_job"] = {"error": str(e)[:300]}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(REPO, "oracle", "_ref", "wtzmo")):
+        sub = int(os.environ.get("ZMO_CPU_SUBSHARD", "16"))
+        try:
+            cols, wall, ovl_s, load_s = run_reference(fa, wl["flags"], n_job * sub, 0, cores, tmpdir, "cpu", wl["dot"])
+            line["cpu_baseline"] = {"value": cols / ovl_s / 1e9, "unit": "Gbp/s", "cores": cores, "kind": "reference",
+                                    "sample": "`oracle/_ref/wtzmo -t %d -P %d -p 0` = 1/%d of one bench step's shard; overlap phase %.1f s (full index build included, as in our step) + %.1f s FASTA load; the fixed index cost is amortised over 1/%d of the work, so this bounded sample UNDER-states the reference -- `--impl reference` times whole equal shards" % (cores, n_job * sub, sub, ovl_s, load_s, sub)}
         except Exception as e:   # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "Gbp/s", "cores": cores, "kind": "reference", "sample": "failed: %s" % e}
-    host.wz_close(S)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

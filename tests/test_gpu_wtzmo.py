@@ -212,27 +212,90 @@ def test_edge_reads(tmp_path, oracle_bin):
         assert open(tmp_path / "ref.ovl.contained", "rb").read() == open(tmp_path / "gpu.ovl.contained", "rb").read()
 
 
-def test_scale_200k_reads_shard_matches_reference_golden(tmp_path, gen_reads):
-    """2.09 Gbp read set (200,000 x 10 kb): one query shard against the full index; the golden digest is the unmodified
-    reference binary's `-t 1` output for the same seeded input (tests/golden/make_scale_golden.sh, ~8 min of CPU there)"""
+def _golden_run(tmp_path, gen_reads, name, env=None, keep=None):
+    """product binary on the seeded read set of tests/golden/scale_digests.json[name] (digests of the UNMODIFIED reference `-t 1`, made by
+    tests/golden/make_scale_golden.py where /root/reference exists): .ovl and .contained must be md5-identical"""
     import hashlib
     import json
-    gold = json.load(open(os.path.join(REPO, "tests", "golden", "scale_digests.json")))["big200k_P400_p0"]
+    gold = json.load(open(os.path.join(REPO, "tests", "golden", "scale_digests.json")))[name]
     base = "/dev/shm" if os.path.isdir("/dev/shm") else str(tmp_path)
-    fa = os.path.join(base, "zmo_scale_test.fa")
-    out = os.path.join(base, "zmo_scale_test.ovl")
+    fa = os.path.join(base, "zmo_gold_%s.fa" % hashlib.md5(" ".join(gold["gen"]).encode()).hexdigest()[:10])
+    out = os.path.join(base, "zmo_gold_%s_%d.ovl" % (name, os.getpid()))
     try:
-        subprocess.run([gen_reads] + gold["gen"] + ["-o", fa], check=True)
-        r = subprocess.run([EXE, "-t", "1", "-i", fa, "-f", "-o", out] + gold["args"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        if not os.path.exists(fa):
+            subprocess.run([gen_reads] + gold["gen"] + ["-o", fa + ".tmp"], check=True)
+            os.replace(fa + ".tmp", fa)
+        r = subprocess.run([EXE, "-t", "1", "-i", fa, "-f", "-o", out] + gold["args"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
         assert r.returncode == 0, r.stderr[-2000:]
         data = open(out, "rb").read()
-        assert data.count(b"\n") == gold["lines"]
-        assert hashlib.md5(data).hexdigest() == gold["md5"]
-        assert hashlib.md5(open(out + ".contained", "rb").read()).hexdigest() == gold["contained_md5"]
+        assert data.count(b"\n") == gold["lines"], (name, data.count(b"\n"), gold["lines"])
+        assert hashlib.md5(data).hexdigest() == gold["md5"], name
+        assert hashlib.md5(open(out + ".contained", "rb").read()).hexdigest() == gold["contained_md5"], name
+        return r.stderr
     finally:
-        for f in (fa, out, out + ".contained"):
+        for f in (out, out + ".contained") + (() if keep else (fa,)):
             if os.path.exists(f):
                 os.remove(f)
+
+
+def test_scale_200k_reads_shard_matches_reference_golden(tmp_path, gen_reads):
+    """2.09 Gbp read set (200,000 x 10 kb): one query shard against the full index (~8 min of CPU for the reference)"""
+    _golden_run(tmp_path, gen_reads, "big200k_P400_p0")
+
+
+def test_cfg1_full_run_matches_reference_golden(tmp_path, gen_reads):
+    """BASELINE.json configs[0], the whole job: 2,000 PacBio-like reads x 8 kb, 7,443 records incl. every CIGAR; and the same reads in
+    dot-matrix mode (smartdenovo.pl:48 flags), 11,921 records"""
+    _golden_run(tmp_path, gen_reads, "cfg1_full", keep=True)
+    _golden_run(tmp_path, gen_reads, "cfg1_dot")
+
+
+def test_cfg2_bench_workload_shards_match_reference_golden(tmp_path, gen_reads):
+    """BASELINE.json configs[1] = the workload bench.py times (50,000 reads x 10 kb): query shards `-P 160 -p 0` and `-p 7` against the
+    full index, byte-identical to the reference `-t 1` (SURVEY 8d's sub-shard recipe); one of them again with the batch pipeline off"""
+    _golden_run(tmp_path, gen_reads, "cfg2_P160_p0", keep=True)
+    _golden_run(tmp_path, gen_reads, "cfg2_P160_p7", keep=True)
+    _golden_run(tmp_path, gen_reads, "cfg2_P160_p0", env=dict(os.environ, ZMO_PIPELINE="0"))
+
+
+def test_cfg2_full_bench_step_matches_reference_golden(tmp_path, gen_reads):
+    """one complete bench step (`-P 10 -p 0`: 5,000 query reads of cfg2) against the reference `-t 1` digest"""
+    import json
+    if "cfg2_P10_p0" not in json.load(open(os.path.join(REPO, "tests", "golden", "scale_digests.json"))):
+        pytest.skip("golden not generated (tests/golden/make_scale_golden.py cfg2_P10_p0: ~1 h of CPU)")
+    _golden_run(tmp_path, gen_reads, "cfg2_P10_p0")
+
+
+def test_cfg3_shaped_dot_matrix_shards_match_reference_golden(tmp_path, gen_reads):
+    """BASELINE.json configs[2] shape at 1/10 of the reads (20,000 ONT-like reads x 15 kb, 30x, `-U -1 -m 0.1 -A 1000`): two `-P 4` query
+    shards, ~147,000 records each"""
+    _golden_run(tmp_path, gen_reads, "cfg3s_dot_P4_p0", keep=True)
+    _golden_run(tmp_path, gen_reads, "cfg3s_dot_P4_p1")
+
+
+def test_partitioned_index_G4_matches_reference_golden(tmp_path, gen_reads):
+    """-G 4 (index built in four read-range partitions, candidates carried between them, wtzmo.c:1276-1303): 1,370 records"""
+    _golden_run(tmp_path, gen_reads, "g4_2000")
+
+
+def test_two_jobs_concurrently_on_one_gpu_match_their_shards(tmp_path, gen_reads, oracle_bin):
+    """GPU g of n == reference job `-P n -p g`: both jobs of a -P 2 split run AT THE SAME TIME as two processes sharing the
+    device (separate contexts, streams and arenas), each byte-identical to the checker's `-P 2 -p g`"""
+    fa = str(tmp_path / "reads.fa")
+    subprocess.run([gen_reads, "-n", "400", "-L", "6000", "-G", "80000", "-s", "31", "-o", fa], check=True)
+    base = ["-k", "16", "-s", "200", "-m", "0.6", "-P", "2"]
+    procs = [subprocess.Popen([EXE, "-t", "1", "-i", fa, "-f", "-o", str(tmp_path / ("gpu%d.ovl" % g))] + base + ["-p", str(g)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for g in range(2)]
+    for g, p in enumerate(procs):
+        _, err = p.communicate(timeout=600)
+        assert p.returncode == 0, err[-2000:]
+    total = 0
+    for g in range(2):
+        _run(_checker(oracle_bin), fa, str(tmp_path / ("ref%d.ovl" % g)), base + ["-p", str(g)])
+        ref = open(tmp_path / ("ref%d.ovl" % g), "rb").read()
+        assert ref == open(tmp_path / ("gpu%d.ovl" % g), "rb").read(), g
+        assert open(tmp_path / ("ref%d.ovl.contained" % g), "rb").read() == open(tmp_path / ("gpu%d.ovl.contained" % g), "rb").read()
+        total += ref.count(b"\n")
+    assert total > 300
 
 
 def test_cfg2_full_size_shard_properties(tmp_path, gen_reads):

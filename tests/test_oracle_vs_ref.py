@@ -137,3 +137,18 @@ def test_oracle_refine_with_long_indel_runs_golden(tmp_path, oracle_bin):
     write_long_indel_reads(fa)
     _run(oracle_bin, fa, str(tmp_path / "orc.ovl"), LONG_INDEL_ARGS)
     assert _digest(str(tmp_path / "orc.ovl")) == json.load(open(GOLDEN))["refine_long_indel"]
+
+
+@pytest.mark.parametrize("name", ["g4_2000", "cfg1_dot"])
+def test_oracle_matches_scale_golden(name, tmp_path, gen_reads, oracle_bin):
+    """the larger reference digests of tests/golden/scale_digests.json that the oracle reproduces in well under a minute: -G 4 with 1,370
+    records (candidate carry-over between four index partitions) and BASELINE configs[0]'s reads in dot-matrix mode (11,921 records)"""
+    gold = json.load(open(os.path.join(REPO, "tests", "golden", "scale_digests.json")))[name]
+    fa = str(tmp_path / "r.fa")
+    subprocess.run([gen_reads] + gold["gen"] + ["-o", fa], check=True)
+    out = str(tmp_path / "orc.ovl")
+    r = subprocess.run([oracle_bin, "-t", "1", "-i", fa, "-f", "-o", out] + gold["args"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-1000:]
+    data = open(out, "rb").read()
+    assert data.count(b"\n") == gold["lines"] and hashlib.md5(data).hexdigest() == gold["md5"]
+    assert hashlib.md5(open(out + ".contained", "rb").read()).hexdigest() == gold["contained_md5"]
