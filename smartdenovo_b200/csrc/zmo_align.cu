@@ -14,7 +14,6 @@
 #include "zmo_jobs.cuh"
 #include "zmo_seed_core.cuh"
 #include "zmo_winalign.cuh"
-#include "zmo_winlane.cuh"
 #include "zmo_stitch_kernels.cuh"
 #include "zmo_refine_kernels.cuh"
 
@@ -191,12 +190,6 @@ static int run_dp_lists(zmo_ctx *c, const JobLists &L, const uint32_t *n, const 
 	return 0;
 }
 
-/* function attributes are per device: called by ctx_init for every context, with that context's device current */
-int zmo_align_init_device(void){
-	CUDA_TRY(cudaFuncSetAttribute(k_wa_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-	return 0;
-}
-
 /* res index -> position in the concatenated job array [ext_w | ext_n | glb_w | glb_n] is the identity by construction */
 static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32_t nt, zmo_record_t *recs, uint32_t *cigars, uint64_t cigar_cap, uint64_t *cigar_needed, bool as_text);
 extern "C" int zmo_pair_align(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32_t nt, zmo_record_t *recs, uint32_t *cigars, uint64_t cigar_cap, uint64_t *cigar_needed){
@@ -234,28 +227,13 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 	A.P.M = c->par.M; A.P.X = c->par.X; A.P.I = c->par.O; A.P.D = c->par.O; A.P.E = c->par.E; A.P.T = c->par.T;
 	DevReads R = dev_reads(c);
 	unsigned long long *ctr = c->d_ctr.as<unsigned long long>();
-	/* window-align executors and their slabs: one lane per window (k_wa_lane, zmo_winlane.cuh) whenever its per-lane H/E ring fits in shared
-	 * memory (-w up to 220); a warp per window (k_window_align) beyond that, or with ZMO_WA_WARP=1 (A/B timing of the two kernels) */
-	static const bool force_warp = getenv("ZMO_WA_WARP") && atoi(getenv("ZMO_WA_WARP")) > 0;
-	static const int epi_min = getenv("ZMO_WL_EPI")? std::max(1, std::min(32, atoi(getenv("ZMO_WL_EPI")))) : WL_EPI_MIN;
-	static const int ctas_max = getenv("ZMO_WL_CTAS")? std::max(1, atoi(getenv("ZMO_WL_CTAS"))) : 8;
-	const int lcap = wl_cap(c->par.w), lrw = wl_row_words(c->par.w);
-	const size_t lsmem = (size_t)lcap * WL_NT * sizeof(int2);
-	const bool use_lane = !force_warp && c->par.w >= 1 && lsmem <= 200u * 1024u;
-	int wgrid; unsigned long long slab, slabs_total;
-	if(use_lane){
-		const int per_sm = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctas_max, (220u * 1024u) / (lsmem + 1024)));
-		wgrid = (int)std::min<uint64_t>((nitems + WL_NT - 1) / WL_NT + 1, (uint64_t)c->n_sm * per_sm);
-		slab = ((unsigned long long)max_rows * lrw + 63) & ~63ull;
-		slabs_total = slab * (unsigned long long)wgrid * WL_NT;
-	} else {
-		wgrid = (int)std::min<uint64_t>((nitems + WA_WARPS - 1) / WA_WARPS + 1, (uint64_t)c->n_sm * 8);
-		const int wcol = std::min(max_rows + c->par.w, 2 * c->par.w + 1);
-		slab = (unsigned long long)max_rows * band_row_words<32, WA_C>(wcol) + max_rows + (2ull * max_rows + 2ull * c->par.w + 16) + ((unsigned long long)max_rows >> 3) + (c->par.w >> 3) + 8;
-		if(2 * c->par.w + 3 > WA_CAP){ unsigned long long cap = 1; while(cap < (unsigned long long)(2 * c->par.w + 3)) cap <<= 1; slab += 3 * cap; }
-		slab = (slab + 63) & ~63ull;
-		slabs_total = slab * (unsigned long long)wgrid * WA_WARPS;
-	}
+	/* window-align executors and their slabs */
+	const int wgrid = (int)std::min<uint64_t>((nitems + WA_WARPS - 1) / WA_WARPS + 1, (uint64_t)c->n_sm * 8);
+	const int wcol = std::min(max_rows + c->par.w, 2 * c->par.w + 1);
+	unsigned long long slab = (unsigned long long)max_rows * band_row_words<32, WA_C>(wcol) + max_rows + (2ull * max_rows + 2ull * c->par.w + 16) + ((unsigned long long)max_rows >> 3) + (c->par.w >> 3) + 8;
+	if(2 * c->par.w + 3 > WA_CAP){ unsigned long long cap = 1; while(cap < (unsigned long long)(2 * c->par.w + 3)) cap <<= 1; slab += 3 * cap; }
+	slab = (slab + 63) & ~63ull;
+	const unsigned long long slabs_total = slab * (unsigned long long)wgrid * WA_WARPS;
 	const uint32_t jcap = nitems + 2 * nt + 8;
 	/* device buffers: s0 tasks|items|icig, s1 regs, s2 task state, s3 jobs (4 lists), s4 results, s6 cig arena, s7 out offsets */
 	if(c->s0.reserve((size_t)nt * sizeof(AlnTask) + (size_t)nitems * (sizeof(WItem) + 8) + 64) || c->s1.reserve(((size_t)nitems + 1) * sizeof(DevReg)) || c->s2.reserve(((size_t)nt + 1) * sizeof(TaskState))
@@ -277,9 +255,7 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 		if(nitems){
 			StageTimer tm(c, ST_WINALN);
 			CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORK, 0, 8, c->stream));
-			if(use_lane) k_wa_lane<<<wgrid, WL_NT, lsmem, c->stream>>>(d_items, nitems, d_tasks, SL.pairs.as<zmo_pair_t>(), SL.wins.as<DevWin>(), SL.anchors.as<DevZPair>(), R, A,
-				arena, slab, lcap, lrw, epi_min, cig_arena, d_icig, d_regs, ctr, CTR_WORK, CTR_CELLS_WIN);
-			else k_window_align<<<wgrid, 32 * WA_WARPS, 0, c->stream>>>(d_items, nitems, d_tasks, SL.pairs.as<zmo_pair_t>(), SL.wins.as<DevWin>(), SL.anchors.as<DevZPair>(), R, A,
+			k_window_align<<<wgrid, 32 * WA_WARPS, 0, c->stream>>>(d_items, nitems, d_tasks, SL.pairs.as<zmo_pair_t>(), SL.wins.as<DevWin>(), SL.anchors.as<DevZPair>(), R, A,
 				arena, slab, max_rows, cig_arena, d_icig, d_regs, ctr, CTR_WORK, CTR_CELLS_WIN);
 			c->launches++;
 			CUDA_TRY(cudaGetLastError());

@@ -12,7 +12,6 @@ int zmo_set_err(int code, const char *fmt, ...){
 extern "C" const char *zmo_last_error(void){ return g_zmo_err.c_str(); }
 
 int zmo_seed_init_device(void);     /* zmo_seed.cu */
-int zmo_align_init_device(void);    /* zmo_align.cu */
 
 static int ctx_init(zmo_ctx *c, int device, const zmo_params_t *par){
 	CUDA_TRY(cudaSetDevice(device));
@@ -26,7 +25,6 @@ static int ctx_init(zmo_ctx *c, int device, const zmo_params_t *par){
 	CUDA_TRY(cudaMemsetAsync(c->d_ctr.p, 0, CTR_TOTAL * 8, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	if(int rc = zmo_seed_init_device()) return rc;
-	if(int rc = zmo_align_init_device()) return rc;
 	return ZMO_OK;
 }
 

@@ -16,7 +16,6 @@ int zmo_set_err(int code, const char *, ...){ return code; }
 namespace emu { Block *g_blk = nullptr; }
 #include "../../smartdenovo_b200/csrc/zmo_dp_kernels.cuh"
 #include "../../smartdenovo_b200/csrc/zmo_winalign.cuh"
-#include "../../smartdenovo_b200/csrc/zmo_winlane.cuh"
 #include "../../smartdenovo_b200/csrc/zmo_stitch_kernels.cuh"
 #include "../../smartdenovo_b200/csrc/zmo_refine_kernels.cuh"
 
@@ -104,13 +103,7 @@ extern "C" int sim_pair_align(const uint8_t *q, int qlen, const uint8_t *c, int 
 	const WItem *di = items.data(); const AlnTask *dt = &task; const zmo_pair_t *dp = &pair; const DevWin *dw = wins.data(); const DevZPair *da = an.data();
 	uint32_t *ar = arena.data(), *cgp = cig_arena.data(); const unsigned long long *dic = icig.data(); DevReg *dr = regs.data(); unsigned long long *cp = ctr;
 	TaskState *dts = ts.data(); DPJob *dj = jobs.data(); DPRes *dres = res.data();
-	if(nitems && w >= 1 && (size_t)wl_cap(w) * WL_NT * sizeof(int2) <= 200u * 1024u){
-		/* the product's default: one lane per window (k_wa_lane), own traceback slabs */
-		const int lcap = wl_cap(w), lrw = wl_row_words(w); const size_t lsmem = (size_t)lcap * WL_NT * sizeof(int2);
-		const unsigned lgrid = (nitems + WL_NT - 1) / WL_NT; const unsigned long long lslab = ((unsigned long long)max_rows * lrw + 63) & ~63ull;
-		std::vector<uint32_t> larena(lslab * (unsigned long long)lgrid * WL_NT + 64, 0xDEADBEEFu); uint32_t *lar = larena.data();
-		emu::launch(lgrid, WL_NT, [=](){ k_wa_lane(di, nitems, dt, dp, dw, da, R, A, lar, lslab, lcap, lrw, WL_EPI_MIN, cgp, dic, dr, cp, 0, 1); }, lsmem);
-	} else if(nitems) emu::launch((unsigned)wgrid, 32 * WA_WARPS, [=](){ k_window_align(di, nitems, dt, dp, dw, da, R, A, ar, slab, max_rows, cgp, dic, dr, cp, 0, 1); });
+	if(nitems) emu::launch((unsigned)wgrid, 32 * WA_WARPS, [=](){ k_window_align(di, nitems, dt, dp, dw, da, R, A, ar, slab, max_rows, cgp, dic, dr, cp, 0, 1); });
 	stats[6] = 0; for(uint32_t i = 0; i < nitems; i++) stats[6] += regs[i].kept? 1 : 0;
 	JobLists L; L.cap = jcap;
 	for(int k = 0; k < 6; k++){ L.list[k] = dj + (size_t)k * jcap; L.cnt[k] = ctr + 10 + k; L.res_base[k] = (uint32_t)k * jcap; }

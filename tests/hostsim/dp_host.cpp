@@ -14,7 +14,6 @@ int zmo_set_err(int code, const char *, ...){ return code; }
 namespace emu { Block *g_blk = nullptr; }
 #include "../../smartdenovo_b200/csrc/zmo_dp_kernels.cuh"
 #include "../../smartdenovo_b200/csrc/zmo_winalign.cuh"
-#include "../../smartdenovo_b200/csrc/zmo_winlane.cuh"
 #include "../../smartdenovo_b200/csrc/zmo_stitch_kernels.cuh"
 #include "../../smartdenovo_b200/csrc/zmo_refine_kernels.cuh"
 
@@ -118,14 +117,7 @@ extern "C" int sim_dp_global(int wide, const uint8_t *q, int qlen, const uint8_t
  * region sizes follow pair_align_impl (zmo_align.cu).  out = n_win x 11 {score, tb, te, qb, qe, aln, mat, mis, ins, del, kept};
  * cig_out = the windows' CIGARs back to back, cig_n[i] ops each.
  */
-extern "C" int sim_window_align_k(int kernel, const uint8_t *q, int qlen, const uint8_t *c, int clen, int dir, const int *win, int n_win, const int *anc,
-		int w, int M, int X, int O, int E, int T, int zovl, float min_id, int *out, uint32_t *cig_out, int cig_cap, int *cig_n);
 extern "C" int sim_window_align(const uint8_t *q, int qlen, const uint8_t *c, int clen, int dir, const int *win, int n_win, const int *anc,
-		int w, int M, int X, int O, int E, int T, int zovl, float min_id, int *out, uint32_t *cig_out, int cig_cap, int *cig_n){
-	return sim_window_align_k(0, q, qlen, c, clen, dir, win, n_win, anc, w, M, X, O, E, T, zovl, min_id, out, cig_out, cig_cap, cig_n);
-}
-/* kernel: 0 = k_window_align (a warp per window), 1 / 2 = k_wa_lane (a lane per window, zmo_winlane.cuh), launched as pair_align_impl does */
-extern "C" int sim_window_align_k(int kernel, const uint8_t *q, int qlen, const uint8_t *c, int clen, int dir, const int *win, int n_win, const int *anc,
 		int w, int M, int X, int O, int E, int T, int zovl, float min_id, int *out, uint32_t *cig_out, int cig_cap, int *cig_n){
 	SimReads rd(q, qlen, c, clen); DevReads R = rd.dev();
 	AlnPar A; A.w = w; A.ew = 800; A.W = 3200; A.zovl = zovl; A.min_id = min_id; A.P.M = M; A.P.X = X; A.P.I = O; A.P.D = O; A.P.E = E; A.P.T = T;
@@ -146,44 +138,14 @@ extern "C" int sim_window_align_k(int kernel, const uint8_t *q, int qlen, const 
 		if(s1 + 8 > max_rows) max_rows = s1 + 8;
 		if(s0 + 8 > max_rows) max_rows = s0 + 8;
 	}
-	std::vector<DevReg> regs(n_win);
-	unsigned long long ctr[4] = {0, 0, 0, 0};
-	if(kernel >= 1){
-		/* kernel 2: every window queued 24 times on ONE CTA, so that each lane pulls several windows from the work counter one after another
-		 * (re-use of its H/E ring, traceback slab and state) and the replicas must all agree */
-		const int reps = kernel == 2? 24 : 1;
-		const int lcap = wl_cap(w), lrw = wl_row_words(w);
-		const size_t lsmem = (size_t)lcap * WL_NT * sizeof(int2);
-		const uint32_t nitems = (uint32_t)(n_win * reps);
-		const int lgrid = kernel == 2? 1 : (n_win + WL_NT - 1) / WL_NT;
-		const unsigned long long lslab = ((unsigned long long)max_rows * lrw + 63) & ~63ull;
-		std::vector<WItem> it2(nitems); std::vector<unsigned long long> ic2(nitems); std::vector<DevReg> rg2(nitems);
-		for(uint32_t k = 0; k < nitems; k++){ it2[k] = items[k % n_win]; ic2[k] = (unsigned long long)(k / n_win) * cig_words + icig[k % n_win]; }
-		std::vector<uint32_t> arena(lslab * (unsigned long long)lgrid * WL_NT + 64, 0xDEADBEEFu), cg(cig_words * reps + 64, 0u);
-		const WItem *di = it2.data(); const AlnTask *dt = &task; const zmo_pair_t *dp = &pair; const DevWin *dw = wins.data(); const DevZPair *da = an.data();
-		uint32_t *ar = arena.data(), *cgp = cg.data(); const unsigned long long *dic = ic2.data(); DevReg *dr = rg2.data(); unsigned long long *cp = ctr;
-		emu::launch((unsigned)lgrid, WL_NT, [=](){ k_wa_lane(di, nitems, dt, dp, dw, da, R, A, ar, lslab, lcap, lrw, kernel == 2? 5 : WL_EPI_MIN, cgp, dic, dr, cp, 0, 1); }, lsmem);
-		for(uint32_t k = (uint32_t)n_win; k < nitems; k++){
-			const DevReg &a = rg2[k], &b = rg2[k % n_win];
-			if(a.score != b.score || a.tb != b.tb || a.te != b.te || a.qb != b.qb || a.qe != b.qe || a.aln != b.aln || a.mat != b.mat || a.mis != b.mis || a.ins != b.ins || a.del != b.del || a.cig_len != b.cig_len || a.kept != b.kept) return -2;
-			if(a.cig_off != ic2[k] || memcmp(&cg[a.cig_off], &cg[b.cig_off], (size_t)a.cig_len * 4)) return -2;
-		}
-		int total = 0;
-		for(int i = 0; i < n_win; i++){
-			const DevReg &r = rg2[i]; int *o = out + 11 * i;
-			o[0] = r.score; o[1] = r.tb; o[2] = r.te; o[3] = r.qb; o[4] = r.qe; o[5] = r.aln; o[6] = r.mat; o[7] = r.mis; o[8] = r.ins; o[9] = r.del; o[10] = (int)r.kept;
-			cig_n[i] = (int)r.cig_len;
-			if(r.cig_off != icig[i] || r.cig_len > (unsigned long long)(win[3 * i] + win[3 * i + 1] + 16 + 2 * win[3 * i + 2])) return -1;     /* CIGAR region overrun */
-			for(uint32_t k = 0; k < r.cig_len && total < cig_cap; k++) cig_out[total++] = cg[r.cig_off + k];
-		}
-		return total;
-	}
 	const int wgrid = (n_win + WA_WARPS - 1) / WA_WARPS + 1;
 	const int wcol = std::min(max_rows + w, 2 * w + 1);
 	unsigned long long slab = (unsigned long long)max_rows * band_row_words<32, WA_C>(wcol) + max_rows + (2ull * max_rows + 2ull * w + 16) + ((unsigned long long)max_rows >> 3) + (w >> 3) + 8;
 	if(2 * w + 3 > WA_CAP){ unsigned long long cap = 1; while(cap < (unsigned long long)(2 * w + 3)) cap <<= 1; slab += 3 * cap; }
 	slab = (slab + 63) & ~63ull;
 	std::vector<uint32_t> arena(slab * (unsigned long long)wgrid * WA_WARPS + 64, 0xDEADBEEFu), cg(cig_words + 64, 0u);
+	std::vector<DevReg> regs(n_win);
+	unsigned long long ctr[4] = {0, 0, 0, 0};
 	const WItem *di = items.data(); const AlnTask *dt = &task; const zmo_pair_t *dp = &pair; const DevWin *dw = wins.data(); const DevZPair *da = an.data();
 	uint32_t *ar = arena.data(), *cgp = cg.data(); const unsigned long long *dic = icig.data(); DevReg *dr = regs.data(); unsigned long long *cp = ctr;
 	const uint32_t nitems = (uint32_t)n_win;

@@ -187,12 +187,9 @@ def _windows(orc, a, b):
     return out
 
 
-@pytest.mark.parametrize("kernel", [0, 1, 2])
-@pytest.mark.parametrize("w", [50, 20, 120, 7])
-def test_window_align_kernel(dp_sim, oracle_lib, w, kernel):
-    """kernel 1 = k_wa_lane (zmo_winlane.cuh: one lane per window -- serial recurrence per lane, H/E ring in shared memory, flat main loop
-    with batched "advance" steps, look-ahead traceback walk; 64-lane CTAs pulling windows from the work counter; kernel 2 = the same with every window queued 24 times on one CTA), kernel 0 =
-    k_window_align (zmo_winalign.cuh: anchor walk, fixed-band bridges with 1/2/4/7 columns per lane, traceback in shared memory
+@pytest.mark.parametrize("w", [50, 20, 120])
+def test_window_align_kernel(dp_sim, oracle_lib, w):
+    """k_window_align (zmo_winalign.cuh: anchor walk, fixed-band bridges with 1/2/4/7 columns per lane, traceback in shared memory
     for short bridges, D/I padding, run-length anchor alignment, CIGAR splicing, region filter) against the oracle's restatement of
     fast_seeds_align_hzmo (hzm_aln.h:1247-1302) on the windows and anchors of real read pairs, both strands"""
     from test_seed_core import pairs
@@ -213,7 +210,7 @@ def test_window_align_kernel(dp_sim, oracle_lib, w, kernel):
             cn = (C.c_int * len(ws))()
             qa = np.ascontiguousarray(a, np.uint8)
             cb = np.ascontiguousarray(b, np.uint8)
-            tot = dp_sim.sim_window_align_k(kernel, qa.ctypes.data_as(C.c_void_p), len(qa), cb.ctypes.data_as(C.c_void_p), len(cb), d, win, len(ws), anc,
+            tot = dp_sim.sim_window_align(qa.ctypes.data_as(C.c_void_p), len(qa), cb.ctypes.data_as(C.c_void_p), len(cb), d, win, len(ws), anc,
                                           w, 2, -5, -3, -1, -50, 200, C.c_float(0.6), out, cig, cap, cn)
             assert tot >= 0
             pos = 0
