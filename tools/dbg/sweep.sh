@@ -2,7 +2,7 @@
 # usage: tools/dbg/sweep.sh "ENV1=a ENV2=b" "ENV1=c" ...   (one bench run per argument)
 for cfg in "$@"; do
   ( for kv in $cfg; do export "$kv"; done
-    python bench.py --steps 3 --warmup 2 --no-cpu-baseline 2>/dev/null | python -c "
+    python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-sub 2>/dev/null | python -c "
 import json,sys
 t=sys.stdin.read().strip().splitlines()
 if not t: print('$cfg', 'FAILED'); sys.exit()
