@@ -123,6 +123,15 @@ int zmo_pair_align_text(zmo_ctx *ctx, int slot, const zmo_task_t *tasks, uint32_
 typedef struct { uint32_t n_zpair; int32_t score, qb, qe, tb, te, strand; } zmo_dotres_t;
 int zmo_pair_dotmatrix(zmo_ctx *ctx, const zmo_pair_t *pairs, uint32_t np, zmo_dotres_t *out);
 
+/* ---- multi-GPU: the one exchange step of the path ---------------------------------------------------- */
+/* Every GPU runs its own query shard = the reference's job `-P n -p g` (wtzmo.c:1291,1314) without communication; at the end the
+ * record text of all jobs is gathered on the GPU of ctxs[0] over NVLink (NCCL: one all-gather of the sizes, one grouped send/receive
+ * of the payloads) and copied to `out` in job order, i.e. `cat part*.ovl` (usage, wtzmo.c:1431-1433).  parts[g] / sizes[g]: job g's text
+ * in host memory; ctxs on n DISTINCT devices; one caller thread.  NCCL is loaded at run time (libnccl.so.2); no fallback. */
+int zmo_gather_records(zmo_ctx **ctxs, int n, const void *const *parts, const uint64_t *sizes,
+                       void *out, uint64_t out_cap, uint64_t *total, double *device_ms);
+int zmo_device_count(void);
+
 /* ---- stand-alone DP operators (unit-testable; same kernels the pipeline uses) ---------------- */
 /* One problem = kswx_extend_align_core (mode 0, kswx.h:234) or kswx_extend_align_shift_core
  * (mode 1, kswx.h:101) on slices of uploaded reads.  Element k of the DP "query" is base

@@ -932,7 +932,8 @@ static int usage(void){
 	" -m <float>  Minimum alignment identity, [0.5]\n"
 	" -n          Refine the alignment\n"
 	" -v          Verbose (accepted, ignored)\n"
-	"Environment: ZMO_DEVICE (GPU ordinal, default 0; under torchrun LOCAL_RANK), ZMO_BATCH_READS, ZMO_BATCH_PAIRS, ZMO_STATS=file\n"
+	"Environment: ZMO_DEVICE (GPU ordinal, default 0; under torchrun LOCAL_RANK), ZMO_GPUS=n|all (GPU g runs job -P P*n -p p*n+g, records gathered\n"
+	"             over NCCL and written in job order), ZMO_DEVICES=a,b,.. (their ordinals), ZMO_BATCH_READS, ZMO_BATCH_PAIRS, ZMO_STATS=file\n"
 	"\n");
 	return 1;
 }
@@ -943,7 +944,7 @@ static int usage(void){
  * wz_run    one complete overlap job `-P n_job -p i_job` from a clean state (index build included), .ovl to out_path
  * wz_stats  numbers of the last wz_run */
 typedef struct {
-	wz_t z; char *output, *pairoutf; int device, uploaded; u8 *masked0; u64v closed0;
+	wz_t z; char *output, *pairoutf; int device, uploaded, is_fork; u8 *masked0; u64v closed0;
 	double t_open, last_overlap_s, last_upload_s; u64 upload_bytes;
 } wz_session_t;
 
@@ -1112,7 +1113,8 @@ int wz_upload(wz_session_t *S){
 	return 0;
 }
 
-int wz_run(wz_session_t *S, int n_job, int i_job, const char *out_path){
+/* one complete overlap job `-P n_job -p i_job` from a clean state, records written to fp */
+int wz_run_fp(wz_session_t *S, int n_job, int i_job, FILE *fp){
 	wz_t *z = &S->z; size_t k, n = z->rs.n_rd + z->rs.n_qr; double t0;
 	if(!S->uploaded){ int rc = wz_upload(S); if(rc) return rc; }
 	if(n_job < 1 || i_job < 0 || i_job >= n_job) return 2;
@@ -1122,19 +1124,46 @@ int wz_run(wz_session_t *S, int n_job, int i_job, const char *out_path){
 	for(k=0;k<S->closed0.n;k++) u64set_add(&z->closed, S->closed0.a[k]);
 	if(z->rdhits){ for(k=0;k<n;k++) vec_free(z->rdhits[k]); free(z->rdhits); z->rdhits = NULL; }
 	z->n_records = z->aln_cols = z->n_tasks = z->n_tasks_used = z->n_pairs_seeded = z->n_batches = z->n_reads_batched = z->n_reads_late_masked = z->n_pairs_late_masked = z->n_waves = z->n_wave_tasks = 0; z->t_dev = z->t_replay = 0;
-	z->out = strcmp(out_path, "-")? fopen(out_path, "w") : stdout;
-	if(z->out == NULL){ fprintf(stderr, "wtzmo(b200): cannot open %s\n", out_path); return 1; }
+	z->out = fp;
 	if(z->obuf == NULL){ z->obuf_cap = 8u << 20; z->obuf = malloc(z->obuf_cap); }
 	t0 = now_s();
 	run_overlap(z);
-	if(strcmp(out_path, "-")) fclose(z->out); else fflush(stdout);
+	fflush(fp);
 	S->last_overlap_s = now_s() - t0;
 	return 0;
 }
+int wz_run(wz_session_t *S, int n_job, int i_job, const char *out_path){
+	FILE *fp = strcmp(out_path, "-")? fopen(out_path, "w") : stdout; int rc;
+	if(fp == NULL){ fprintf(stderr, "wtzmo(b200): cannot open %s\n", out_path); return 1; }
+	rc = wz_run_fp(S, n_job, i_job, fp);
+	if(fp != stdout) fclose(fp);
+	return rc;
+}
 
-/* out[0]=records [1]=aligned columns [2]=overlap wall s [3]=device-call s [4]=replay+format s [5]=batches [6]=pairs seeded
- * [7]=tasks aligned [8]=tasks consumed [9]=kernel launches (cumulative) [10..17]=stage ms (cumulative) [18..24]=counters (cumulative)
- * [25]=reads [26]=bases [27]=last upload s [28]=upload bytes */
+/* a second session on another GPU over the SAME parsed read set (shared, read-only) and the same initial state: own device
+ * context(s), own replay state.  Multi-GPU runs: GPU g of n is the reference's job `-P n -p g` (wtzmo.c:1291,1314). */
+wz_session_t* wz_fork(const wz_session_t *S0, int device, int *rc_out){
+	wz_session_t *S = calloc(1, sizeof(wz_session_t)); wz_t *z = &S->z; const wz_t *z0 = &S0->z; zmo_params_t zp; const zparams_t *par = &z0->par; size_t n = z0->rs.n_rd + z0->rs.n_qr; int q;
+	*rc_out = 0;
+	z->rs = z0->rs; z->par = z0->par;      /* reads: shared pointers, never written after wz_open */
+	z->batch_reads = z0->batch_reads; z->batch_pairs = z0->batch_pairs; z->depth = z0->depth; z->call_pairs = z0->call_pairs;
+	z->wave_margin = z0->wave_margin; z->wave_growth = z0->wave_growth; z->wave_maskcheck = z0->wave_maskcheck;
+	for(q=0;q<WZ_MAX_CTX;q++) pthread_mutex_init(&z->dev_mu[q], NULL);
+	pthread_mutex_init(&z->stat_mu, NULL);
+	z->masked = calloc(n + 1, 1); z->rdcovs = calloc(n + 1, sizeof(u32)); u64set_init(&z->closed);
+	S->masked0 = S0->masked0; S->closed0 = S0->closed0; S->output = S0->output; S->pairoutf = S0->pairoutf; S->device = device; S->is_fork = 1;
+	memset(&zp, 0, sizeof(zp));
+	zp.hk = par->hk; zp.hz = par->hz; zp.ksize = par->ksize; zp.zsize = par->zsize; zp.ksave = par->ksave; zp.kovl = par->kovl; zp.zcut = par->zcut; zp.kvar = par->kvar;
+	zp.kwin = par->kwin; zp.kstep = par->kstep; zp.zovl = par->zovl; zp.ztot = par->ztot; zp.w = par->w; zp.ew = par->ew; zp.W = par->W;
+	zp.M = par->M; zp.X = par->X; zp.O = par->O; zp.E = par->E; zp.T = par->T; zp.min_id = par->min_id;
+	zp.xvar = par->xvar; zp.yvar = par->yvar; zp.min_block_len = par->min_block_len; zp.max_overhang = par->max_overhang; zp.deviation_penalty = par->deviation_penalty; zp.gap_penalty = par->gap_penalty;
+	if(zmo_ctx_create(&z->ctx, device, &zp)){ fprintf(stderr, "wtzmo(b200): zmo_ctx_create(device %d): %s\n", device, zmo_last_error()); *rc_out = 3; return NULL; }
+	if(par->refine && zmo_set_refine(z->ctx, 1)){ *rc_out = 3; return NULL; }
+	z->ctxs[0] = z->ctx; z->n_ctx = 1;
+	for(q=1;q<z->depth;q++){ if(zmo_ctx_clone(z->ctx, &z->ctxs[z->n_ctx])){ fprintf(stderr, "wtzmo(b200): zmo_ctx_clone: %s\n", zmo_last_error()); *rc_out = 3; return NULL; } z->n_ctx ++; }
+	return S;
+}
+
 #define WZ_STATS_N 40   /* doubles written by wz_stats (callers size their buffer with wz_stats_n()) */
 int wz_stats_n(void){ return WZ_STATS_N; }
 void wz_stats(wz_session_t *S, double *out){
@@ -1152,48 +1181,112 @@ void wz_stats(wz_session_t *S, double *out){
 
 void wz_close(wz_session_t *S){ if(S){ int q; for(q=S->z.n_ctx-1;q>=0;q--) if(S->z.ctxs[q]) zmo_ctx_destroy(S->z.ctxs[q]); free(S); } }
 
+/* ------------------------------------------------------------------ multi-GPU job: ZMO_GPUS=n
+ * One process, one host thread per GPU.  GPU g runs the reference's job `-P (P*n) -p (p*n+g)` (query reads with rd_id % (P*n) == p*n+g
+ * against the full index, private masked / tried-pair / counter state, wtzmo.c:1291,1314) into a memory stream; no communication during
+ * compute.  At the end the record text of all jobs is gathered on GPU 0 over NVLink with NCCL (zmo_gather_records) and written in job
+ * order, which is what `cat` of the per-job files gives (usage, wtzmo.c:1431-1433).  <out>.contained = union of the jobs' masked reads in
+ * read-id order; -9 = union of the jobs' tried pairs. */
+typedef struct { wz_session_t *S; int n_job, i_job, rc; char *buf; size_t len; } mg_arg_t;
+static void* mg_thread(void *arg){
+	mg_arg_t *a = arg; FILE *fp = open_memstream(&a->buf, &a->len);
+	if(fp == NULL){ a->rc = 1; return NULL; }
+	a->rc = wz_upload(a->S);
+	if(!a->rc) a->rc = wz_run_fp(a->S, a->n_job, a->i_job, fp);
+	fclose(fp);
+	return NULL;
+}
+#define WZ_MAX_GPU 16
+typedef struct { wz_session_t *S[WZ_MAX_GPU]; int n; double gather_ms, gather_wall_s; u64 gathered_bytes; } wz_multi_t;
+static int run_multi(wz_session_t *S0, int ngpu, const int *devs, wz_multi_t *M){
+	mg_arg_t a[WZ_MAX_GPU]; pthread_t th[WZ_MAX_GPU]; int g, rc = 0; zmo_ctx *ctxs[WZ_MAX_GPU]; const void *parts[WZ_MAX_GPU]; uint64_t sizes[WZ_MAX_GPU], total = 0; char *out; double t0;
+	FILE *fp;
+	memset(M, 0, sizeof(*M)); M->n = ngpu; M->S[0] = S0;
+	for(g=0;g<ngpu;g++){ int h; if(devs[g] < 0 || devs[g] >= zmo_device_count()){ fprintf(stderr, "wtzmo(b200): ZMO_GPUS=%d: no GPU %d (%d visible)\n", ngpu, devs[g], zmo_device_count()); return 3; }
+		for(h=0;h<g;h++) if(devs[h] == devs[g]){ fprintf(stderr, "wtzmo(b200): ZMO_DEVICES names GPU %d twice: one job per GPU\n", devs[g]); return 2; } }
+	for(g=1;g<ngpu;g++){ M->S[g] = wz_fork(S0, devs[g], &rc); if(M->S[g] == NULL) return rc; }
+	for(g=0;g<ngpu;g++){ memset(&a[g], 0, sizeof(a[g])); a[g].S = M->S[g]; a[g].n_job = S0->z.par.n_job * ngpu; a[g].i_job = S0->z.par.i_job * ngpu + g; }
+	for(g=0;g<ngpu;g++) if(pthread_create(&th[g], NULL, mg_thread, &a[g]) != 0){ fprintf(stderr, "wtzmo(b200): cannot start the thread of GPU %d\n", devs[g]); return 3; }
+	for(g=0;g<ngpu;g++){ pthread_join(th[g], NULL); if(a[g].rc) rc = a[g].rc; }
+	if(rc) return rc;
+	for(g=0;g<ngpu;g++){ ctxs[g] = M->S[g]->z.ctx; parts[g] = a[g].buf; sizes[g] = a[g].len; total += a[g].len; }
+	out = malloc(total + 1);
+	t0 = now_s();
+	if(zmo_gather_records(ctxs, ngpu, parts, sizes, out, total, &total, &M->gather_ms)){ fprintf(stderr, "wtzmo(b200): zmo_gather_records: %s\n", zmo_last_error()); return 3; }
+	M->gather_wall_s = now_s() - t0; M->gathered_bytes = total;
+	fp = strcmp(S0->output, "-")? fopen(S0->output, "w") : stdout;
+	if(fp == NULL){ fprintf(stderr, "wtzmo(b200): cannot open %s\n", S0->output); return 1; }
+	fwrite(out, 1, total, fp);
+	if(fp != stdout) fclose(fp); else fflush(stdout);
+	free(out);
+	for(g=0;g<ngpu;g++) free(a[g].buf);
+	return 0;
+}
+
 #ifndef WTZMO_LIB
 int main(int argc, char **argv){
-	int rc = 0; double t_start = now_s(); char *env; u32 i;
-	wz_session_t *S = wz_open(argc, argv, &rc); wz_t *z;
+	int rc = 0, ngpu = 1, devs[WZ_MAX_GPU], g; double t_start = now_s(); char *env; u32 i;
+	wz_session_t *S = wz_open(argc, argv, &rc); wz_t *z; wz_multi_t M;
 	if(S == NULL) return rc;
 	z = &S->z;
-	if((rc = wz_upload(S))) return rc;
-	fprintf(stderr, "[wtzmo-b200] calculating overlaps on GPU %d\n", S->device);
-	if((rc = wz_run(S, z->par.n_job, z->par.i_job, S->output))) return rc;
-	fprintf(stderr, "[wtzmo-b200] Done, %llu records, %llu aligned columns, %.3f s (device calls %.3f s, replay+format %.3f s, %llu batches, %llu pairs seeded, %llu aligned, %llu consumed)\n",
-		(unsigned long long)z->n_records, (unsigned long long)z->aln_cols, S->last_overlap_s, z->t_dev, z->t_replay, (unsigned long long)z->n_batches,
-		(unsigned long long)z->n_pairs_seeded, (unsigned long long)z->n_tasks, (unsigned long long)z->n_tasks_used);
+	memset(&M, 0, sizeof(M)); M.n = 1; M.S[0] = S;
+	if((env = getenv("ZMO_GPUS"))){ ngpu = !strcmp(env, "all")? zmo_device_count() : atoi(env); if(ngpu < 1) ngpu = 1; if(ngpu > WZ_MAX_GPU) ngpu = WZ_MAX_GPU; }
+	for(g=0;g<ngpu;g++) devs[g] = S->device + g;
+	if((env = getenv("ZMO_DEVICES"))){ char *cp = strdup(env), *sv, *tok; for(g=0,tok=strtok_r(cp, ",", &sv);tok&&g<ngpu;tok=strtok_r(NULL, ",", &sv)) devs[g++] = atoi(tok); free(cp); }
+	if(ngpu > 1){
+		fprintf(stderr, "[wtzmo-b200] calculating overlaps on %d GPUs: GPU g runs job -P %d -p %d+g\n", ngpu, z->par.n_job * ngpu, z->par.i_job * ngpu);
+		if((rc = run_multi(S, ngpu, devs, &M))) return rc;
+	} else {
+		if((rc = wz_upload(S))) return rc;
+		fprintf(stderr, "[wtzmo-b200] calculating overlaps on GPU %d\n", S->device);
+		if((rc = wz_run(S, z->par.n_job, z->par.i_job, S->output))) return rc;
+	}
+	for(g=0;g<M.n;g++){
+		wz_session_t *Sg = M.S[g]; wz_t *zg = &Sg->z;
+		fprintf(stderr, "[wtzmo-b200] %sDone, %llu records, %llu aligned columns, %.3f s (device calls %.3f s, replay+format %.3f s, %llu batches, %llu pairs seeded, %llu aligned, %llu consumed)\n", M.n > 1? "job " : "",
+			(unsigned long long)zg->n_records, (unsigned long long)zg->aln_cols, Sg->last_overlap_s, zg->t_dev, zg->t_replay, (unsigned long long)zg->n_batches,
+			(unsigned long long)zg->n_pairs_seeded, (unsigned long long)zg->n_tasks, (unsigned long long)zg->n_tasks_used);
+	}
+	if(M.n > 1) fprintf(stderr, "[wtzmo-b200] gathered %llu bytes of records on GPU %d over NCCL: %.3f ms on the device, %.3f s incl. staging\n", (unsigned long long)M.gathered_bytes, devs[0], M.gather_ms, M.gather_wall_s);
 	if(z->par.write_contained && strcmp(S->output, "-")){
 		char *maskf = malloc(strlen(S->output) + 16); FILE *mf;
 		sprintf(maskf, "%s.contained", S->output); mf = fopen(maskf, "w");
-		for(i=0;i<z->rs.n_rd;i++) if(z->masked[i]) fprintf(mf, "%s\n", z->rs.reads.a[i].name);
+		for(i=0;i<z->rs.n_rd;i++){ int m = 0; for(g=0;g<M.n;g++) m |= M.S[g]->z.masked[i]; if(m) fprintf(mf, "%s\n", z->rs.reads.a[i].name); }
 		fclose(mf); free(maskf);
 	}
 	if(S->pairoutf){
-		FILE *pf = fopen(S->pairoutf, "w"); size_t k;
-		for(k=0;k<z->closed.cap;k++){
-			u64 v = z->closed.tab[k];
-			if(v == ~0ULL) continue;
-			fprintf(pf, "%s\t%s\n", z->rs.reads.a[v >> 33].name, z->rs.reads.a[(v & 0xFFFFFFFFU) >> 1].name);
+		FILE *pf = fopen(S->pairoutf, "w"); size_t k; u64set_t seen; u64set_init(&seen);
+		for(g=0;g<M.n;g++){
+			const u64set_t *cl = &M.S[g]->z.closed;
+			for(k=0;k<cl->cap;k++){
+				u64 v = cl->tab[k];
+				if(v == ~0ULL || (M.n > 1 && u64set_has(&seen, v))) continue;
+				if(M.n > 1) u64set_add(&seen, v);
+				fprintf(pf, "%s\t%s\n", z->rs.reads.a[v >> 33].name, z->rs.reads.a[(v & 0xFFFFFFFFU) >> 1].name);
+			}
 		}
-		fclose(pf);
+		fclose(pf); free(seen.tab);
 	}
 	if((env = getenv("ZMO_STATS"))){
-		FILE *sf = fopen(env, "w"); double st[WZ_STATS_N]; const char *nm[8] = {"index", "candidates", "pair_windows", "window_align", "gap_global", "end_extend", "dotmatrix", "copy"};
-		const char *cn[7] = {"cells_ext", "cells_win", "cells_gap", "zpairs", "postings", "h2d_bytes", "d2h_bytes"}; int k;
-		wz_stats(S, st);
+		FILE *sf = fopen(env, "w"); double st[WZ_STATS_N], s1[WZ_STATS_N]; const char *nm[8] = {"index", "candidates", "pair_windows", "window_align", "gap_global", "end_extend", "dotmatrix", "copy"};
+		const char *cn[7] = {"cells_ext", "cells_win", "cells_gap", "zpairs", "postings", "h2d_bytes", "d2h_bytes"}; int k; double ovl_max = 0;
+		u64 rb = 0, rl = 0, cl = 0;
+		memset(st, 0, sizeof(st));
+		for(g=0;g<M.n;g++){ wz_stats(M.S[g], s1); for(k=0;k<WZ_STATS_N;k++) if(k != 2 && k != 25 && k != 26) st[k] += s1[k]; if(s1[2] > ovl_max) ovl_max = s1[2]; st[25] = s1[25]; st[26] = s1[26];
+			rb += M.S[g]->z.n_reads_batched; rl += M.S[g]->z.n_reads_late_masked; cl += M.S[g]->z.n_pairs_late_masked; }
+		st[2] = ovl_max;
 		if(sf){
 			fprintf(sf, "{\"records\": %.0f, \"aligned_cols\": %.0f, \"overlap_s\": %.6f, \"total_s\": %.6f, \"device_call_s\": %.6f, \"replay_s\": %.6f, \"batches\": %.0f, \"pairs_seeded\": %.0f, \"tasks\": %.0f, \"tasks_used\": %.0f, \"launches\": %.0f, \"stage_ms\": {",
 				st[0], st[1], st[2], now_s() - t_start, st[3], st[4], st[5], st[6], st[7], st[8], st[9]);
 			for(k=0;k<8;k++) fprintf(sf, "%s\"%s\": %.3f", k? ", " : "", nm[k], st[10 + k]);
 			fprintf(sf, "}, \"counters\": {");
 			for(k=0;k<7;k++) fprintf(sf, "%s\"%s\": %.0f", k? ", " : "", cn[k], st[18 + k]);
-			fprintf(sf, "}, \"n_reads\": %.0f, \"n_bases\": %.0f, \"reads_batched\": %llu, \"reads_late_masked\": %llu, \"cands_late_masked\": %llu}\n", st[25], st[26], (unsigned long long)S->z.n_reads_batched, (unsigned long long)S->z.n_reads_late_masked, (unsigned long long)S->z.n_pairs_late_masked);
+			fprintf(sf, "}, \"n_reads\": %.0f, \"n_bases\": %.0f, \"reads_batched\": %llu, \"reads_late_masked\": %llu, \"cands_late_masked\": %llu, \"n_gpus\": %d, \"gather_device_ms\": %.3f, \"gather_wall_s\": %.6f, \"gathered_bytes\": %llu, \"load_s\": %.3f}\n", st[25], st[26],
+				(unsigned long long)rb, (unsigned long long)rl, (unsigned long long)cl, M.n, M.gather_ms, M.gather_wall_s, (unsigned long long)M.gathered_bytes, S->t_open);
 			fclose(sf);
 		}
 	}
-	wz_close(S);
+	for(g=M.n-1;g>=0;g--) wz_close(M.S[g]);
 	return 0;
 }
 #endif

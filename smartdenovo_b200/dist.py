@@ -1,7 +1,7 @@
 """Multi-GPU plumbing for the overlap path: query reads shard across ranks exactly like the reference's
 `-P n -p i` jobs (wtzmo.c:1291,1314, usage :1431-1433) -- rank r of N is job r -- with the k-mer index replicated,
 so there is NO collective during compute.  The only exchange is the final gather of the variable-length record
-text to rank 0 (one all-gather of sizes + one all-gather of padded byte tensors), equivalent to `cat part*.ovl`.
+text to rank 0 (one all-gather of sizes + one gather of padded byte tensors to the root), equivalent to `cat part*.ovl`.
 Works with any torch.distributed backend (NCCL on GPUs, gloo in the CPU tests)."""
 import os
 
@@ -33,7 +33,7 @@ def gather_records(payload: bytes, device="cpu"):
 
 def gather_record_file(path, device="cpu", dst_rank=0):
     """Gather the record files of all ranks on `dst_rank` (`cat part*.ovl` in rank order) with ONE all-gather of sizes and
-    ONE all-gather of the padded byte buffers.  The file is read straight into a page-locked staging tensor, the
+    ONE gather of the padded byte buffers to dst_rank.  The file is read straight into a page-locked staging tensor, the
     gathered buffer is copied back to the host on dst_rank only.  Returns (total bytes over all ranks, list of per-rank
     uint8 numpy views of the host copy on dst_rank or None elsewhere); the staging tensors come from torch's caching
     pinned allocator, so repeated gathers do not pay cudaHostAlloc again."""
@@ -58,12 +58,16 @@ def gather_record_file(path, device="cpu", dst_rank=0):
                     raise IOError("short read of %s" % path)
                 got += r
     buf = stage.to(device, non_blocking=True)
-    out = torch.empty(world * mx, dtype=torch.uint8, device=device)
-    dist.all_gather_into_tensor(out, buf)
+    # gather to dst_rank only (the other ranks send and receive nothing): 1/world of the traffic of an all-gather
+    outs = [torch.empty(mx, dtype=torch.uint8, device=device) for _ in range(world)] if rank == dst_rank else None
+    dist.gather(buf, gather_list=outs, dst=dst_rank)
     if rank != dst_rank:
         return sum(sizes), None
     host = torch.empty(world * mx, dtype=torch.uint8, pin_memory=on_gpu)
-    host.copy_(out)
+    for r in range(world):
+        host[r * mx: r * mx + sizes[r]].copy_(outs[r][: sizes[r]], non_blocking=True)
+    if on_gpu:
+        torch.cuda.current_stream().synchronize()
     a = host.numpy()
     return sum(sizes), [a[r * mx: r * mx + sizes[r]] for r in range(world)]
 

@@ -298,6 +298,39 @@ def test_two_jobs_concurrently_on_one_gpu_match_their_shards(tmp_path, gen_reads
     assert total > 300
 
 
+def test_multi_gpu_job_needs_distinct_gpus(tmp_path, gen_reads):
+    """ZMO_GPUS=2 on a box with one GPU (or the same ordinal twice) stops before any work is done"""
+    fa = str(tmp_path / "reads.fa")
+    subprocess.run([gen_reads, "-n", "50", "-L", "3000", "-G", "30000", "-s", "2", "-o", fa], check=True)
+    r = subprocess.run([EXE, "-t", "1", "-i", fa, "-f", "-o", str(tmp_path / "x.ovl"), "-k", "16"], env=dict(os.environ, ZMO_GPUS="2", ZMO_DEVICES="0,0"), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 2 and "twice" in r.stderr
+
+
+def test_multi_gpu_job_equals_cat_of_reference_jobs(tmp_path, gen_reads, oracle_bin):
+    """product-level multi-GPU (ZMO_GPUS=n, one process, one host thread per GPU, records gathered on GPU 0 over NCCL): the output is
+    `cat` of the checker's jobs `-P n -p 0..n-1`, .contained their union in read-id order, -9 the union of their pairs"""
+    import torch
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs at least two GPUs (run under `gpurun --gpus 2`)")
+    fa = str(tmp_path / "reads.fa")
+    subprocess.run([gen_reads, "-n", "600", "-L", "6000", "-G", "100000", "-s", "37", "-o", fa], check=True)
+    base = ["-k", "16", "-s", "200", "-m", "0.6"]
+    _run(EXE, fa, str(tmp_path / "gpu.ovl"), base, env=dict(os.environ, ZMO_GPUS=str(n)))
+    cat, contained, pairs = b"", set(), set()
+    for g in range(n):
+        _run(_checker(oracle_bin), fa, str(tmp_path / ("ref%d.ovl" % g)), base + ["-P", str(n), "-p", str(g)])
+        cat += open(tmp_path / ("ref%d.ovl" % g), "rb").read()
+        contained |= set(open(tmp_path / ("ref%d.ovl.contained" % g)).read().split())
+        pairs |= set(open(tmp_path / ("ref%d.ovl.pairs" % g)).read().split("\n"))
+    assert open(tmp_path / "gpu.ovl", "rb").read() == cat and cat.count(b"\n") > 500
+    got = open(tmp_path / "gpu.ovl.contained").read().split()
+    assert set(got) == contained and len(got) == len(contained)
+    lens = {l[1:].strip(): len(s.strip()) for l, s in zip(*[iter(open(fa))] * 2)}
+    assert all(lens[a] >= lens[b] for a, b in zip(got, got[1:]))          # read-id order = length descending
+    assert set(open(tmp_path / "gpu.ovl.pairs").read().split("\n")) == pairs
+
+
 def test_cfg2_full_size_shard_properties(tmp_path, gen_reads):
     """BASELINE.json configs[1] at full size (50,000 PacBio-like reads x 10 kb, the bench workload): one `-P 10 -p 3` query shard, too
     large for a CPU run inside the suite, checked through the size-independent properties of tests/ovl_props.py -- every record inside its
