@@ -31,6 +31,24 @@ __device__ __forceinline__ void zmo_warp_bitonic_u64(uint64_t *a, uint32_t n2, i
 }
 __device__ __forceinline__ uint32_t zmo_pow2_ge(uint32_t n){ uint32_t p = 1; while(p < n) p <<= 1; return p; }
 
+/* k-th smallest (0-based) of n int32 values in shared memory, |value| < 2^24 (diagonals off1 - off2 of reads shorter than 2^24), by all
+ * 32 lanes: radix select, one vote per bit.  calculate_median_value (hzm_aln.h:316-343) is a quickselect that returns element size/2 of
+ * the sorted order -- a VALUE, so any selection algorithm gives the same result (its in-place permutation of the scratch array is never
+ * looked at again). */
+__device__ __forceinline__ int32_t zmo_warp_kth_i32(const int32_t *a, uint32_t n, uint32_t k, int lane){
+	uint32_t prefix = 0, mask = 0;
+	#pragma unroll 1
+	for(int bit = 24; bit >= 0; bit--){
+		const uint32_t m2 = mask | (1u << bit);
+		uint32_t c = 0;
+		for(uint32_t i = lane; i < n; i += 32) c += (((uint32_t)(a[i] + (1 << 24)) & m2) == prefix)? 1u : 0u;
+		c = __reduce_add_sync(0xffffffffu, c);
+		if(k >= c){ k -= c; prefix |= 1u << bit; }
+		mask = m2;
+	}
+	return (int32_t)prefix - (1 << 24);
+}
+
 /* warp-cooperative windows_in_span; S arrays must live in shared memory with capt a power of two >= the span's strand
  * entries and S.ak holding at least pow2(capstage) keys.  Returns like the serial version; O.overflow == 2 asks the
  * caller to redo the strand with the serial global-memory path. */
@@ -118,9 +136,7 @@ __device__ uint32_t zmo_windows_in_span_w(const DevZPair *rs, int dir, uint32_t 
 		int32_t offset;
 		for(uint32_t j = wb + lane; j <= we; j += 32){ const DevZPair p = rs[beg + ZMO_TS_IDX(S.ts[j])]; S.as[j - wb] = (int32_t)p.off1 - (int32_t)p.off2; }
 		__syncwarp();
-		offset = 0;
-		if(lane == 0) offset = zmo_median_select(S.as, (int32_t)offn);
-		offset = __shfl_sync(0xffffffffu, offset, 0);
+		offset = zmo_warp_kth_i32(S.as, offn, offn / 2, lane);
 		/* anchors within +-50 of the median diagonal, gathered in span order */
 		uint32_t na = 0;
 		for(int pass = 0; pass < 2; pass++){

@@ -101,9 +101,12 @@ __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *ite
 				/* columns per lane chosen by band width: narrow bridges (the common case, ~50 columns) run 1-2 cells per lane
 				 * instead of 7 mostly idle ones, which cuts the per-row instruction count several-fold */
 				const int ccap = 2 * max_rows + 2 * A.w + 16;
+#ifndef ZMO_EXP_WA_C4      /* EXPERIMENT -DZMO_EXP_WA_C4: two sweep instances (4 and 7 columns per lane) instead of four, to see what the instruction-cache misses cost */
 				if(d.ncol <= RegCap<32, 1>::ncol) reg_extend<32, 1, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, tmpc, ccap, o, ctr + ctr_cells, lane);
 				else if(d.ncol <= RegCap<32, 2>::ncol) reg_extend<32, 2, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, tmpc, ccap, o, ctr + ctr_cells, lane);
-				else if(d.ncol <= RegCap<32, 4>::ncol) reg_extend<32, 4, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, tmpc, ccap, o, ctr + ctr_cells, lane);
+				else
+#endif
+				if(d.ncol <= RegCap<32, 4>::ncol) reg_extend<32, 4, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, tmpc, ccap, o, ctr + ctr_cells, lane);
 				else if(d.ncol <= RegCap<32, WA_C>::ncol) reg_extend<32, WA_C, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, tmpc, ccap, o, ctr + ctr_cells, lane);
 				else band_extend<32, WA_C, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, zb, tmpc, ccap, o, ctr + ctr_cells, lane);
 			}
