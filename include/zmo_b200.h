@@ -70,6 +70,10 @@ void zmo_stage_ms(const zmo_ctx *ctx, double out[12]);
  * [2]=cells gap global, [3]=z-mer match pairs, [4]=postings visited, [5]=bytes H2D, [6]=bytes D2H */
 void zmo_counters(const zmo_ctx *ctx, uint64_t out[8]);
 
+/* process-wide wall time spent growing buffers: out[0..2] = seconds, calls, bytes of device-buffer growth, out[3..5] = the same for
+ * page-locked host buffers (what a cold start pays on top of the steady state) */
+void zmo_alloc_stats(double out[6]);
+
 /* page-locked host memory for result buffers (records, CIGARs): lets the D2H copies run at PCIe speed */
 void *zmo_host_alloc(size_t bytes);
 void  zmo_host_free(void *p);

@@ -343,7 +343,7 @@ typedef struct {
 	zmo_record_t *pin_recs[WZ_MAX_CTX][WZ_PIN_WAVES]; size_t pin_recs_cap[WZ_MAX_CTX][WZ_PIN_WAVES]; u32 *pin_cig[WZ_MAX_CTX][WZ_PIN_WAVES]; size_t pin_cig_cap[WZ_MAX_CTX][WZ_PIN_WAVES];
 	pthread_mutex_t dev_mu[WZ_MAX_CTX];  /* one device call at a time per context */
 	pthread_mutex_t stat_mu;
-	u64 n_waves, n_wave_tasks; int wave_margin, wave_growth, wave_maskcheck;
+	u64 n_waves, n_wave_tasks; int wave_margin, wave_growth;
 } wz_t;
 
 static double now_s(void){ struct timeval tv; gettimeofday(&tv, NULL); return tv.tv_sec + 1e-6 * tv.tv_usec; }
@@ -708,9 +708,6 @@ static void batch_compute(wz_t *z, batch_t *b){
 			for(i=0;i<nr;i++){
 				size_t got = 0;
 				if(pos[i] < 0) continue;
-				/* ZMO_WAVE_MASKCHECK=1 (experiment, off by default): a read that the replay of the batches ahead has masked in the meantime
-				 * will be skipped at its turn (masks only grow), so its remaining waves are dropped; a stale read of masked[] only skips less */
-				if(z->wave_maskcheck && z->masked[b->reads.a[i].rd_id]){ pos[i] = -1; continue; }
 				for(k=(size_t)pos[i];k<sv[i].n&&got<chunk;k++){
 					const seed_t *sd = &sv[i].a[k]; zmo_task_t t;
 					if(sd->closed || b->pres[sd->cand_idx]) continue;
@@ -1030,7 +1027,6 @@ wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	z->call_pairs = (env = getenv("ZMO_CALL_PAIRS"))? atoi(env) : 0;     /* test hook: pairs per device call (0 = the library's limits) */
 	z->wave_margin = (env = getenv("ZMO_WAVE0"))? atoi(env) : 8;       /* seeds per read in the first DP wave (doubles per wave); < 0: align every seed up front */
 	z->wave_growth = (env = getenv("ZMO_WAVE_GROWTH"))? atoi(env) : 4; if(z->wave_growth < 2) z->wave_growth = 2;
-	z->wave_maskcheck = (env = getenv("ZMO_WAVE_MASKCHECK"))? atoi(env) : 0;
 	{ int q; for(q=0;q<WZ_MAX_CTX;q++) pthread_mutex_init(&z->dev_mu[q], NULL); pthread_mutex_init(&z->stat_mu, NULL); }
 	if(z->batch_reads < 1) z->batch_reads = 1;
 	fprintf(stderr, "[wtzmo-b200] loading long reads\n");
@@ -1147,7 +1143,7 @@ wz_session_t* wz_fork(const wz_session_t *S0, int device, int *rc_out){
 	*rc_out = 0;
 	z->rs = z0->rs; z->par = z0->par;      /* reads: shared pointers, never written after wz_open */
 	z->batch_reads = z0->batch_reads; z->batch_pairs = z0->batch_pairs; z->depth = z0->depth; z->call_pairs = z0->call_pairs;
-	z->wave_margin = z0->wave_margin; z->wave_growth = z0->wave_growth; z->wave_maskcheck = z0->wave_maskcheck;
+	z->wave_margin = z0->wave_margin; z->wave_growth = z0->wave_growth;
 	for(q=0;q<WZ_MAX_CTX;q++) pthread_mutex_init(&z->dev_mu[q], NULL);
 	pthread_mutex_init(&z->stat_mu, NULL);
 	z->masked = calloc(n + 1, 1); z->rdcovs = calloc(n + 1, sizeof(u32)); u64set_init(&z->closed);
@@ -1270,7 +1266,8 @@ int main(int argc, char **argv){
 	if((env = getenv("ZMO_STATS"))){
 		FILE *sf = fopen(env, "w"); double st[WZ_STATS_N], s1[WZ_STATS_N]; const char *nm[8] = {"index", "candidates", "pair_windows", "window_align", "gap_global", "end_extend", "dotmatrix", "copy"};
 		const char *cn[7] = {"cells_ext", "cells_win", "cells_gap", "zpairs", "postings", "h2d_bytes", "d2h_bytes"}; int k; double ovl_max = 0;
-		u64 rb = 0, rl = 0, cl = 0;
+		u64 rb = 0, rl = 0, cl = 0; double al[6];
+		zmo_alloc_stats(al);
 		memset(st, 0, sizeof(st));
 		for(g=0;g<M.n;g++){ wz_stats(M.S[g], s1); for(k=0;k<WZ_STATS_N;k++) if(k != 2 && k != 25 && k != 26) st[k] += s1[k]; if(s1[2] > ovl_max) ovl_max = s1[2]; st[25] = s1[25]; st[26] = s1[26];
 			rb += M.S[g]->z.n_reads_batched; rl += M.S[g]->z.n_reads_late_masked; cl += M.S[g]->z.n_pairs_late_masked; }
@@ -1281,8 +1278,8 @@ int main(int argc, char **argv){
 			for(k=0;k<8;k++) fprintf(sf, "%s\"%s\": %.3f", k? ", " : "", nm[k], st[10 + k]);
 			fprintf(sf, "}, \"counters\": {");
 			for(k=0;k<7;k++) fprintf(sf, "%s\"%s\": %.0f", k? ", " : "", cn[k], st[18 + k]);
-			fprintf(sf, "}, \"n_reads\": %.0f, \"n_bases\": %.0f, \"reads_batched\": %llu, \"reads_late_masked\": %llu, \"cands_late_masked\": %llu, \"n_gpus\": %d, \"gather_device_ms\": %.3f, \"gather_wall_s\": %.6f, \"gathered_bytes\": %llu, \"load_s\": %.3f}\n", st[25], st[26],
-				(unsigned long long)rb, (unsigned long long)rl, (unsigned long long)cl, M.n, M.gather_ms, M.gather_wall_s, (unsigned long long)M.gathered_bytes, S->t_open);
+			fprintf(sf, "}, \"n_reads\": %.0f, \"n_bases\": %.0f, \"reads_batched\": %llu, \"reads_late_masked\": %llu, \"cands_late_masked\": %llu, \"n_gpus\": %d, \"gather_device_ms\": %.3f, \"gather_wall_s\": %.6f, \"gathered_bytes\": %llu, \"load_s\": %.3f, \"alloc\": {\"device_s\": %.3f, \"device_calls\": %.0f, \"device_bytes\": %.0f, \"pinned_s\": %.3f, \"pinned_calls\": %.0f, \"pinned_bytes\": %.0f}}\n", st[25], st[26],
+				(unsigned long long)rb, (unsigned long long)rl, (unsigned long long)cl, M.n, M.gather_ms, M.gather_wall_s, (unsigned long long)M.gathered_bytes, S->t_open, al[0], al[1], al[2], al[3], al[4], al[5]);
 			fclose(sf);
 		}
 	}

@@ -5,6 +5,9 @@
 #include "zmo_ctx.cuh"
 
 thread_local std::string g_zmo_err;
+std::atomic<unsigned long long> g_zmo_alloc_ns[2], g_zmo_alloc_calls[2], g_zmo_alloc_bytes[2];
+/* out[0..2] = seconds, calls, bytes of device-buffer growth (cudaFree + cudaMalloc); out[3..5] = the same for page-locked host buffers */
+extern "C" void zmo_alloc_stats(double out[6]){ for(int k = 0; k < 2; k++){ out[3 * k] = 1e-9 * (double)g_zmo_alloc_ns[k].load(); out[3 * k + 1] = (double)g_zmo_alloc_calls[k].load(); out[3 * k + 2] = (double)g_zmo_alloc_bytes[k].load(); } }
 int zmo_set_err(int code, const char *fmt, ...){
 	char buf[1024]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
 	g_zmo_err = buf; return code;
@@ -73,7 +76,7 @@ extern "C" void zmo_ctx_destroy(zmo_ctx *c){
 	delete c;
 }
 
-extern "C" void *zmo_host_alloc(size_t bytes){ void *p = nullptr; if(cudaHostAlloc(&p, bytes? bytes : 1, cudaHostAllocDefault) != cudaSuccess){ zmo_set_err(ZMO_ERR_CUDA, "cudaHostAlloc(%zu) failed", bytes); return nullptr; } return p; }
+extern "C" void *zmo_host_alloc(size_t bytes){ void *p = nullptr; AllocTimer at(1, bytes); if(cudaHostAlloc(&p, bytes? bytes : 1, cudaHostAllocDefault) != cudaSuccess){ zmo_set_err(ZMO_ERR_CUDA, "cudaHostAlloc(%zu) failed", bytes); return nullptr; } return p; }
 extern "C" void zmo_host_free(void *p){ if(p) cudaFreeHost(p); }
 
 extern "C" uint64_t zmo_kernel_launches(const zmo_ctx *c){ return c? c->launches : 0; }

@@ -16,6 +16,13 @@ int zmo_set_err(int code, const char *fmt, ...);
 
 #define CUDA_TRY(expr) do { cudaError_t _e = (expr); if(_e != cudaSuccess){ return zmo_set_err(ZMO_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); } } while(0)
 
+/* wall time spent growing device / pinned buffers (process-wide; zmo_alloc_stats): what a cold start pays */
+#include <chrono>
+#include <atomic>
+extern std::atomic<unsigned long long> g_zmo_alloc_ns[2], g_zmo_alloc_calls[2], g_zmo_alloc_bytes[2];
+struct AllocTimer { int k; size_t b; std::chrono::steady_clock::time_point t0; AllocTimer(int k_, size_t b_) : k(k_), b(b_), t0(std::chrono::steady_clock::now()) {}
+	~AllocTimer(){ g_zmo_alloc_ns[k] += (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); g_zmo_alloc_calls[k]++; g_zmo_alloc_bytes[k] += b; } };
+
 /* growable device buffer */
 struct DevBuf {
 	void *p = nullptr; size_t cap = 0;
@@ -23,6 +30,7 @@ struct DevBuf {
 		if(bytes <= cap) return 0;
 		size_t want = cap? cap : (1u << 20);
 		while(want < bytes) want = want + want / 2 + (1u << 20);
+		AllocTimer at(0, want);
 		if(p) cudaFree(p);
 		p = nullptr; cap = 0;
 		cudaError_t e = cudaMalloc(&p, want);
@@ -40,6 +48,7 @@ struct PinBuf {
 		if(bytes <= cap) return 0;
 		size_t want = cap? cap : (1u << 20);
 		while(want < bytes) want = want + want / 2 + (1u << 20);
+		AllocTimer at(1, want);
 		if(p) cudaFreeHost(p);
 		p = nullptr; cap = 0;
 		cudaError_t e = cudaMallocHost(&p, want);

@@ -42,24 +42,6 @@ template<int NT, int C> struct ZWin {
 			for(int wd = 0; wd < WPT; wd++) pw[s][wd] = (r >= 0 && b >= 0)? z[((size_t)r * NT + (b & (NT - 1))) * WPT + wd] : 0u;
 		}
 	}
-#ifdef ZMO_EXP_WALK_RUNS
-	/* EXPERIMENT (compile with -DZMO_EXP_WALK_RUNS, off by default): lane `lane` looks at the cell k = lane - (iw - ii) steps down the
-	 * diagonal from (ii, jj), which it holds itself if the walk is still near the diagonal the window was filled on.  Returns true if
-	 * that cell is held and its H source is the diagonal; *same = its two bases are equal. */
-	__device__ __forceinline__ bool diag_probe(const uint32_t *rowpk, const uint32_t *colpk, int ii, int jj, int lane, bool *same) const {
-		const int k = lane - (iw - ii), r = ii - k, c = jj - k;
-		*same = false;
-		if(k < 0 || r < 0 || c < 0) return false;
-		const int bcur = c / C, s = bcur - gblk(jw - lane) + 1;
-		if((unsigned)s > 2u) return false;
-		const int kk = c - bcur * C;
-		uint32_t w;
-		if(WPT == 1) w = s == 0? pw[0][0] : (s == 1? pw[1][0] : pw[2][0]);
-		else { const int wd = kk >> 3; w = s == 0? (wd? pw[0][WPT - 1] : pw[0][0]) : (s == 1? (wd? pw[1][WPT - 1] : pw[1][0]) : (wd? pw[2][WPT - 1] : pw[2][0])); }
-		*same = pk_base(rowpk, r) == pk_base(colpk, c);
-		return ((w >> ((kk & 7) << 2)) & 3u) == 0u;
-	}
-#endif
 	/* traceback nibble of cell (ii, jj); uniform arguments, all 32 lanes call */
 	__device__ __forceinline__ uint32_t get(const uint32_t *z, int ii, int jj, int lane){
 		int L = iw - ii;
@@ -90,24 +72,6 @@ __device__ __forceinline__ int reg_walk(const uint32_t *z, const uint32_t *rowpk
 	int st = 0, n = 0, mat = 0, mis = 0, c1 = 0, c2 = 0;
 	uint32_t cur_op = 0xF, cur_len = 0;
 	while(ii >= 0 && jj >= 0){
-#ifdef ZMO_EXP_WALK_RUNS
-		/* a run of diagonal moves in state H is taken in one go: every lane tests its own cell down the diagonal, two ballots give the
-		 * run length and its matches (with ~15% error a run is 5-6 cells long on average) */
-		if(st == 0 && (unsigned)(win.iw - ii) < 32u){
-			bool same; const bool dg = win.diag_probe(rowpk, colpk, ii, jj, lane, &same);
-			const unsigned L0 = (unsigned)(win.iw - ii);
-			const unsigned md = __ballot_sync(0xffffffffu, dg) >> L0, ms = __ballot_sync(0xffffffffu, same) >> L0;
-			const int run = (~md)? __ffs((int)~md) - 1 : 32;      /* consecutive diagonal cells starting at (ii, jj); 32 - L0 at most since the shifted-in bits are 0 */
-			if(run > 1){
-				const unsigned take = run >= 32? 0xffffffffu : ((1u << run) - 1u);
-				const int eq = __popc(ms & take);
-				mat += eq; mis += run - eq; ii -= run; jj -= run;
-				if(cur_op == 0u) cur_len += (uint32_t)run;
-				else { if(cur_len){ if(lane == 0 && n < cig_cap) cig[n] = (cur_len << 4) | cur_op; n++; } cur_op = 0; cur_len = (uint32_t)run; }
-				continue;
-			}
-		}
-#endif
 		const uint32_t nib = win.get(z, ii, jj, lane);
 		uint32_t op;
 		if(st == 0) st = nib & 3u; else if(st == 1) st = (nib & 4u)? 1 : 0; else st = (nib & 8u)? 2 : 0;

@@ -38,20 +38,6 @@ __device__ __forceinline__ void cig_cat(uint32_t *c, uint32_t &n, const uint32_t
 	else for(; i < len; i++) c[n++] = src[i];
 }
 
-#ifdef ZMO_EXP_ANCHOR_REGS
-/* EXPERIMENT (compile with -DZMO_EXP_ANCHOR_REGS, off by default): the first n <= 32 logical bases of a view as one 64-bit word, base k at
- * bits 63-2k..62-2k, cut out of at most three packed words (only words that hold requested bases are touched) */
-__device__ __forceinline__ unsigned long long view_load64(const SeqView &s, int n){
-	const int p0 = s.step == 1? s.start : s.start - 31;            /* first position of the forward 32-base chunk */
-	const int lo = s.step == 1? s.start : s.start - (n - 1), hi = s.step == 1? s.start + n - 1 : s.start;      /* positions really needed */
-	const int i0 = p0 >> 4, sh = (p0 & 15) << 1, wl = lo >> 4, wh = hi >> 4;
-	const unsigned long long w0 = (i0 >= wl && i0 <= wh)? __ldg(s.w + i0) : 0u, w1 = (i0 + 1 >= wl && i0 + 1 <= wh)? __ldg(s.w + i0 + 1) : 0u, w2 = (i0 + 2 >= wl && i0 + 2 <= wh)? __ldg(s.w + i0 + 2) : 0u;
-	unsigned long long v = (w0 << 32) | w1;
-	if(sh) v = (v << sh) | (w2 >> (32 - sh));
-	if(s.step != 1){ const unsigned long long u = __brevll(v); v = ((u >> 1) & 0x5555555555555555ull) | ((u & 0x5555555555555555ull) << 1); }
-	return s.comp? ~v : v;
-}
-#endif
 /* warp-per-window executor */
 __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *items, uint32_t nitems, const AlnTask *tasks, const zmo_pair_t *pairs,
 		const DevWin *wins, const DevZPair *anchors, DevReads R, AlnPar A, uint32_t *arena, unsigned long long slab_words, int max_rows,
@@ -101,12 +87,9 @@ __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *ite
 				/* columns per lane chosen by band width: narrow bridges (the common case, ~50 columns) run 1-2 cells per lane
 				 * instead of 7 mostly idle ones, which cuts the per-row instruction count several-fold */
 				const int ccap = 2 * max_rows + 2 * A.w + 16;
-#ifndef ZMO_EXP_WA_C4      /* EXPERIMENT -DZMO_EXP_WA_C4: two sweep instances (4 and 7 columns per lane) instead of four, to see what the instruction-cache misses cost */
 				if(d.ncol <= RegCap<32, 1>::ncol) reg_extend<32, 1, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, tmpc, ccap, o, ctr + ctr_cells, lane);
 				else if(d.ncol <= RegCap<32, 2>::ncol) reg_extend<32, 2, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, tmpc, ccap, o, ctr + ctr_cells, lane);
-				else
-#endif
-				if(d.ncol <= RegCap<32, 4>::ncol) reg_extend<32, 4, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, tmpc, ccap, o, ctr + ctr_cells, lane);
+				else if(d.ncol <= RegCap<32, 4>::ncol) reg_extend<32, 4, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, tmpc, ccap, o, ctr + ctr_cells, lane);
 				else if(d.ncol <= RegCap<32, WA_C>::ncol) reg_extend<32, WA_C, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, tmpc, ccap, o, ctr + ctr_cells, lane);
 				else band_extend<32, WA_C, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, zb, tmpc, ccap, o, ctr + ctr_cells, lane);
 			}
@@ -140,16 +123,8 @@ __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *ite
 				const uint32_t la = p.len1, lb = p.len2; uint32_t sa = 0, sb = 0;
 				int y_score = 0, y_aln = 0, y_mat = 0, y_ins = 0, y_del = 0;
 				uint32_t blk2[96]; uint32_t n2 = 0; bool bad = false;
-#ifdef ZMO_EXP_ANCHOR_REGS
-				/* anchors are z-mer spans (a few tens of bases): keep both in registers instead of one cached global load per base */
-				const bool inreg = la <= 32u && lb <= 32u;
-				const unsigned long long RA = inreg? view_load64(a, (int)la) : 0ull, RB = inreg? view_load64(b, (int)lb) : 0ull;
-				#define ANC_A(k) (inreg? (uint32_t)(RA >> (62 - 2 * (int)(k))) & 3u : sv_base(a, (int)(k)))
-				#define ANC_B(k) (inreg? (uint32_t)(RB >> (62 - 2 * (int)(k))) & 3u : sv_base(b, (int)(k)))
-#else
 				#define ANC_A(k) sv_base(a, (int)(k))
 				#define ANC_B(k) sv_base(b, (int)(k))
-#endif
 				while(sa < la || sb < lb){
 					const uint32_t ca = sa < la? ANC_A(sa) : 4u, cb = sb < lb? ANC_B(sb) : 5u;
 					if(ca != cb){ bad = true; break; }

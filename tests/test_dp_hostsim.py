@@ -13,7 +13,7 @@ import pytest
 from conftest import REPO, call_ext, call_global, mutate
 
 SC = (2, -5, -3, -1, -50)   # -M -X -O -E -T defaults (wtzmo.c:1574-1578)
-# compile-time experiments of the kernels (e.g. ZMO_SIM_DEFINES="-DZMO_EXP_WALK_RUNS") are checked with the same tests
+# compile-time variants of the kernels (ZMO_SIM_DEFINES="-D...") are checked with the same tests
 SIM_DEFINES = os.environ.get("ZMO_SIM_DEFINES", "").split()
 
 

@@ -56,12 +56,11 @@ def test_sw_small_batches(tmp_path, gen_reads, oracle_bin):
         _compare(tmp_path, gen_reads, oracle_bin, ["-n", "120", "-L", "5000", "-G", "50000", "-s", "3"], ["-k", "16", "-s", "200", "-m", "0.6"], env=env)
 
 
-def test_experimental_warp_stitch_gives_the_same_bytes(tmp_path, gen_reads, oracle_bin):
-    """ZMO_FINISH_WARP=1: warp-per-task k_finish_warp instead of k_finish (bit-exact in the host simulation, tests/test_dp_hostsim.py; opt-in
-    until its time has been measured)"""
-    env = dict(os.environ, ZMO_FINISH_WARP="1", ZMO_WAVE_MASKCHECK="1")      # + the waves re-check masked[] (host experiment)
+def test_thread_per_task_stitch_gives_the_same_bytes(tmp_path, gen_reads, oracle_bin):
+    """ZMO_FINISH_WARP=0: one-thread-per-task k_finish instead of the default warp-per-task k_finish_warp (both bit-exact against an
+    independent restatement in the host simulation, tests/test_dp_hostsim.py::test_finish_kernels)"""
+    env = dict(os.environ, ZMO_FINISH_WARP="0")
     _compare(tmp_path, gen_reads, oracle_bin, ["-n", "200", "-L", "6000", "-G", "60000", "-s", "1"], ["-k", "16", "-s", "200", "-m", "0.6"], env=env)
-    _compare(tmp_path, gen_reads, oracle_bin, ["-n", "300", "-L", "5000", "-G", "50000", "-s", "2"], ["-k", "16", "-s", "200", "-m", "0.6"], env=dict(env, ZMO_BATCH_READS="16"))
     _compare(tmp_path, gen_reads, oracle_bin, ["-n", "150", "-L", "5000", "-G", "50000", "-s", "3"], ["-k", "16", "-s", "200", "-m", "0.6", "-n"], env=env)
 
 
