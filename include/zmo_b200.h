@@ -134,6 +134,8 @@ int zmo_pair_dotmatrix(zmo_ctx *ctx, const zmo_pair_t *pairs, uint32_t np, zmo_d
  * in host memory; ctxs on n DISTINCT devices; one caller thread.  NCCL is loaded at run time (libnccl.so.2); no fallback. */
 int zmo_gather_records(zmo_ctx **ctxs, int n, const void *const *parts, const uint64_t *sizes,
                        void *out, uint64_t out_cap, uint64_t *total, double *device_ms);
+/* optional: create the NCCL communicators of the device set ahead of time (about a second; safe to call from a helper thread while the jobs run) */
+int zmo_gather_prepare(zmo_ctx **ctxs, int n);
 int zmo_device_count(void);
 
 /* ---- stand-alone DP operators (unit-testable; same kernels the pipeline uses) ---------------- */

@@ -945,9 +945,28 @@ typedef struct {
 	double t_open, last_overlap_s, last_upload_s; u64 upload_bytes;
 } wz_session_t;
 
+/* device context(s) of a session, created on a helper thread while the main thread parses the reads: CUDA start-up (context creation,
+ * module load) costs about as much as loading a 0.5 GB FASTA */
+typedef struct { wz_t *z; int device, refine, rc; zmo_params_t zp; char err[600]; pthread_t th; int started; } ctx_boot_t;
+static void* ctx_boot_thread(void *arg){
+	ctx_boot_t *b = arg; wz_t *z = b->z; int q;
+	b->rc = 0; b->err[0] = 0;
+	if(zmo_ctx_create(&z->ctx, b->device, &b->zp)){ snprintf(b->err, sizeof(b->err), "zmo_ctx_create: %s", zmo_last_error()); b->rc = 3; return NULL; }
+	if(b->refine && zmo_set_refine(z->ctx, 1)){ snprintf(b->err, sizeof(b->err), "zmo_set_refine: %s", zmo_last_error()); b->rc = 3; return NULL; }
+	/* one context per queued batch: those in flight + the one being replayed (which may still ask for on-demand waves) */
+	z->ctxs[0] = z->ctx; z->n_ctx = 1;
+	for(q=1;q<z->depth;q++){ if(zmo_ctx_clone(z->ctx, &z->ctxs[z->n_ctx])){ snprintf(b->err, sizeof(b->err), "zmo_ctx_clone: %s", zmo_last_error()); b->rc = 3; return NULL; } z->n_ctx ++; }
+	return NULL;
+}
+static int ctx_boot_join(ctx_boot_t *b){
+	if(b->started){ pthread_join(b->th, NULL); b->started = 0; }
+	if(b->rc) fprintf(stderr, "wtzmo(b200): %s\n", b->err);
+	return b->rc;
+}
+
 wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	wz_session_t *S = calloc(1, sizeof(wz_session_t)); wz_t *z = &S->z; zparams_t *par = &z->par; int c; float optval; zmo_params_t zp;
-	char *env; double t_start = now_s();
+	char *env; double t_start = now_s(); ctx_boot_t boot;
 	VEC(char*) pbs, flts, ovls, obts, tbas; u32 i; size_t k;
 	zparams_default(par);
 	vec_init(pbs); vec_init(flts); vec_init(ovls); vec_init(obts); vec_init(tbas);
@@ -1029,12 +1048,19 @@ wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	z->wave_growth = (env = getenv("ZMO_WAVE_GROWTH"))? atoi(env) : 4; if(z->wave_growth < 2) z->wave_growth = 2;
 	{ int q; for(q=0;q<WZ_MAX_CTX;q++) pthread_mutex_init(&z->dev_mu[q], NULL); pthread_mutex_init(&z->stat_mu, NULL); }
 	if(z->batch_reads < 1) z->batch_reads = 1;
+	memset(&zp, 0, sizeof(zp));
+	zp.hk = par->hk; zp.hz = par->hz; zp.ksize = par->ksize; zp.zsize = par->zsize; zp.ksave = par->ksave; zp.kovl = par->kovl; zp.zcut = par->zcut; zp.kvar = par->kvar;
+	zp.kwin = par->kwin; zp.kstep = par->kstep; zp.zovl = par->zovl; zp.ztot = par->ztot; zp.w = par->w; zp.ew = par->ew; zp.W = par->W;
+	zp.M = par->M; zp.X = par->X; zp.O = par->O; zp.E = par->E; zp.T = par->T; zp.min_id = par->min_id;
+	zp.xvar = par->xvar; zp.yvar = par->yvar; zp.min_block_len = par->min_block_len; zp.max_overhang = par->max_overhang; zp.deviation_penalty = par->deviation_penalty; zp.gap_penalty = par->gap_penalty;
+	memset(&boot, 0, sizeof(boot)); boot.z = z; boot.device = S->device; boot.refine = par->refine; boot.zp = zp;
+	if(pthread_create(&boot.th, NULL, ctx_boot_thread, &boot) == 0) boot.started = 1; else ctx_boot_thread(&boot);
 	fprintf(stderr, "[wtzmo-b200] loading long reads\n");
 	rs_load(&z->rs, pbs.a, (int)pbs.n, par->min_rdlen, 0);
 	ref_sort(z->rs.reads.a, z->rs.reads.n, sizeof(read_t), gt_read_len_desc, NULL);      /* wtzmo.c:1708 */
 	if(tbas.n) rs_load(&z->rs, tbas.a, (int)tbas.n, par->min_rdlen, 1);
 	fprintf(stderr, "[wtzmo-b200] Done, %u reads (+%u query-only), %.3f s\n", z->rs.n_rd, z->rs.n_qr, now_s() - t_start);
-	if(z->rs.n_rd == 0){ fprintf(stderr, "wtzmo(b200): no reads\n"); *rc_out = 1; return NULL; }
+	if(z->rs.n_rd == 0){ fprintf(stderr, "wtzmo(b200): no reads\n"); ctx_boot_join(&boot); *rc_out = 1; return NULL; }
 	z->masked = calloc(z->rs.n_rd + z->rs.n_qr + 1, 1);
 	z->rdcovs = calloc(z->rs.n_rd + z->rs.n_qr + 1, sizeof(u32));
 	u64set_init(&z->closed);
@@ -1084,16 +1110,7 @@ wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	S->masked0 = malloc(z->rs.n_rd + z->rs.n_qr + 1); memcpy(S->masked0, z->masked, z->rs.n_rd + z->rs.n_qr + 1);
 	vec_init(S->closed0);
 	for(k=0;k<z->closed.cap;k++) if(z->closed.tab[k] != ~0ULL) vec_push(S->closed0, z->closed.tab[k]);
-	memset(&zp, 0, sizeof(zp));
-	zp.hk = par->hk; zp.hz = par->hz; zp.ksize = par->ksize; zp.zsize = par->zsize; zp.ksave = par->ksave; zp.kovl = par->kovl; zp.zcut = par->zcut; zp.kvar = par->kvar;
-	zp.kwin = par->kwin; zp.kstep = par->kstep; zp.zovl = par->zovl; zp.ztot = par->ztot; zp.w = par->w; zp.ew = par->ew; zp.W = par->W;
-	zp.M = par->M; zp.X = par->X; zp.O = par->O; zp.E = par->E; zp.T = par->T; zp.min_id = par->min_id;
-	zp.xvar = par->xvar; zp.yvar = par->yvar; zp.min_block_len = par->min_block_len; zp.max_overhang = par->max_overhang; zp.deviation_penalty = par->deviation_penalty; zp.gap_penalty = par->gap_penalty;
-	if(zmo_ctx_create(&z->ctx, S->device, &zp)){ fprintf(stderr, "wtzmo(b200): zmo_ctx_create: %s\n", zmo_last_error()); *rc_out = 3; return NULL; }
-	if(par->refine && zmo_set_refine(z->ctx, 1)){ fprintf(stderr, "wtzmo(b200): zmo_set_refine: %s\n", zmo_last_error()); *rc_out = 3; return NULL; }
-	/* one context per queued batch: those in flight + the one being replayed (which may still ask for on-demand waves) */
-	z->ctxs[0] = z->ctx; z->n_ctx = 1;
-	{ int q; for(q=1;q<z->depth;q++){ if(zmo_ctx_clone(z->ctx, &z->ctxs[z->n_ctx])){ fprintf(stderr, "wtzmo(b200): zmo_ctx_clone: %s\n", zmo_last_error()); *rc_out = 3; return NULL; } z->n_ctx ++; } }
+	if((*rc_out = ctx_boot_join(&boot))) return NULL;
 	S->t_open = now_s() - t_start;
 	vec_free(pbs); vec_free(flts); vec_free(ovls); vec_free(obts); vec_free(tbas);
 	return S;
@@ -1184,6 +1201,8 @@ void wz_close(wz_session_t *S){ if(S){ int q; for(q=S->z.n_ctx-1;q>=0;q--) if(S-
  * order, which is what `cat` of the per-job files gives (usage, wtzmo.c:1431-1433).  <out>.contained = union of the jobs' masked reads in
  * read-id order; -9 = union of the jobs' tried pairs. */
 typedef struct { wz_session_t *S; int n_job, i_job, rc; char *buf; size_t len; } mg_arg_t;
+typedef struct { zmo_ctx *ctxs[16]; int n, rc; } mg_prep_t;
+static void* mg_prepare_thread(void *arg){ mg_prep_t *p = arg; p->rc = zmo_gather_prepare(p->ctxs, p->n); return NULL; }
 static void* mg_thread(void *arg){
 	mg_arg_t *a = arg; FILE *fp = open_memstream(&a->buf, &a->len);
 	if(fp == NULL){ a->rc = 1; return NULL; }
@@ -1203,7 +1222,13 @@ static int run_multi(wz_session_t *S0, int ngpu, const int *devs, wz_multi_t *M)
 	for(g=1;g<ngpu;g++){ M->S[g] = wz_fork(S0, devs[g], &rc); if(M->S[g] == NULL) return rc; }
 	for(g=0;g<ngpu;g++){ memset(&a[g], 0, sizeof(a[g])); a[g].S = M->S[g]; a[g].n_job = S0->z.par.n_job * ngpu; a[g].i_job = S0->z.par.i_job * ngpu + g; }
 	for(g=0;g<ngpu;g++) if(pthread_create(&th[g], NULL, mg_thread, &a[g]) != 0){ fprintf(stderr, "wtzmo(b200): cannot start the thread of GPU %d\n", devs[g]); return 3; }
-	for(g=0;g<ngpu;g++){ pthread_join(th[g], NULL); if(a[g].rc) rc = a[g].rc; }
+	{	/* NCCL communicators while the jobs compute */
+		mg_prep_t prep; pthread_t pt; int have;
+		prep.n = ngpu; prep.rc = 0; for(g=0;g<ngpu;g++) prep.ctxs[g] = M->S[g]->z.ctx;
+		have = pthread_create(&pt, NULL, mg_prepare_thread, &prep) == 0;
+		for(g=0;g<ngpu;g++){ pthread_join(th[g], NULL); if(a[g].rc) rc = a[g].rc; }
+		if(have) pthread_join(pt, NULL);
+	}
 	if(rc) return rc;
 	for(g=0;g<ngpu;g++){ ctxs[g] = M->S[g]->z.ctx; parts[g] = a[g].buf; sizes[g] = a[g].len; total += a[g].len; }
 	out = malloc(total + 1);

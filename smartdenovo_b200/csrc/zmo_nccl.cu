@@ -42,6 +42,33 @@ static int nccl_load(){
 }
 #define NCCL_TRY(expr) do { ncclResult_t _r = (expr); if(_r != 0) return zmo_set_err(ZMO_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, g_nccl.GetErrorString(_r)); } while(0)
 
+/* communicators of the process, created once per device set (ncclCommInitAll costs about a second: zmo_gather_prepare lets the host do it on a
+ * helper thread while the jobs are still computing) */
+#include <mutex>
+static std::mutex g_comm_mu;
+static std::vector<int> g_comm_devs;
+static std::vector<ncclComm_t> g_comms;
+static int nccl_comms(const std::vector<int> &devs, std::vector<ncclComm_t> &out){
+	std::lock_guard<std::mutex> lk(g_comm_mu);
+	if(g_comm_devs != devs){
+		for(ncclComm_t c : g_comms) g_nccl.CommDestroy(c);
+		g_comms.assign(devs.size(), nullptr); g_comm_devs.clear();
+		NCCL_TRY(g_nccl.CommInitAll(g_comms.data(), (int)devs.size(), devs.data()));
+		g_comm_devs = devs;
+	}
+	out = g_comms;
+	return 0;
+}
+extern "C" int zmo_gather_prepare(zmo_ctx **ctxs, int n){
+	if(!ctxs || n < 1) return zmo_set_err(ZMO_ERR_ARG, "null argument");
+	if(n == 1) return 0;
+	if(int rc = nccl_load()) return rc;
+	std::vector<int> devs(n); for(int g = 0; g < n; g++){ if(!ctxs[g]) return zmo_set_err(ZMO_ERR_ARG, "null context"); devs[g] = ctxs[g]->device; }
+	for(int a = 0; a < n; a++) for(int b = a + 1; b < n; b++) if(devs[a] == devs[b]) return zmo_set_err(ZMO_ERR_ARG, "contexts %d and %d share device %d: one job per GPU", a, b, devs[a]);
+	std::vector<ncclComm_t> comm;
+	return nccl_comms(devs, comm);
+}
+
 /* Gather n byte strings (part g = parts[g], sizes[g] bytes, produced by the job of ctxs[g]'s GPU and sitting in host memory) on the
  * GPU of ctxs[0] and copy them, in order, to out (capacity out_cap).  Every part travels host -> its own GPU -> NVLink -> root GPU ->
  * host, so that the exchange is the device-to-device gather the path defines; *total = sum of sizes.  ctxs must sit on n DISTINCT
@@ -56,8 +83,8 @@ extern "C" int zmo_gather_records(zmo_ctx **ctxs, int n, const void *const *part
 	if(n == 1){ if(tot) memcpy(out, parts[0], tot); if(ms_out) *ms_out = 0; return 0; }
 	if(int rc = nccl_load()) return rc;
 	std::vector<int> devs(n); for(int g = 0; g < n; g++) devs[g] = ctxs[g]->device;
-	std::vector<ncclComm_t> comm(n);
-	NCCL_TRY(g_nccl.CommInitAll(comm.data(), n, devs.data()));
+	std::vector<ncclComm_t> comm;
+	if(int rc0 = nccl_comms(devs, comm)) return rc0;
 	int rc = 0;
 	std::vector<void*> dsend(n, nullptr); std::vector<uint64_t*> dsz(n, nullptr); void *droot = nullptr;
 	cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -66,7 +93,7 @@ extern "C" int zmo_gather_records(zmo_ctx **ctxs, int n, const void *const *part
 		for(int g = 0; g < n && !rc; g++){
 			if(cudaSetDevice(devs[g]) != cudaSuccess || cudaMalloc(&dsend[g], sizes[g] + 16) != cudaSuccess || cudaMalloc((void**)&dsz[g], ((size_t)n + 1) * 8) != cudaSuccess){ rc = zmo_set_err(ZMO_ERR_CUDA, "cudaMalloc for the gather failed on device %d", devs[g]); break; }
 			if(cudaMemcpyAsync(dsz[g] + n, &sizes[g], 8, cudaMemcpyHostToDevice, ctxs[g]->stream) != cudaSuccess) rc = zmo_set_err(ZMO_ERR_CUDA, "H2D failed");
-			if(sizes[g] && cudaMemcpyAsync(dsend[g], parts[g], sizes[g], cudaMemcpyHostToDevice, ctxs[g]->stream) != cudaSuccess) rc = zmo_set_err(ZMO_ERR_CUDA, "H2D failed");
+			if(sizes[g] && cudaMemcpyAsync(dsend[g], parts[g], sizes[g], cudaMemcpyHostToDevice, ctxs[g]->stream) != cudaSuccess) rc = zmo_set_err(ZMO_ERR_CUDA, "H2D failed");      /* pageable source: staged by the driver */
 			ctxs[g]->counters[5] += sizes[g];
 		}
 		if(rc) break;
@@ -113,7 +140,6 @@ extern "C" int zmo_gather_records(zmo_ctx **ctxs, int n, const void *const *part
 	if(droot) cudaFree(droot);
 	if(e0) cudaEventDestroy(e0);
 	if(e1) cudaEventDestroy(e1);
-	for(int g = 0; g < n; g++) g_nccl.CommDestroy(comm[g]);
 	return rc;
 }
 
