@@ -309,10 +309,7 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 		/* a job's index in [ext_w | ext_n | glb_w | glb_n] equals its result index by construction */
 		zmo_record_t *d_recs = c->cubtmp.as<zmo_record_t>();
 		{
-			/* warp-per-task stitch (k_finish_warp: coalesced segment copies); ZMO_FINISH_WARP=0 = the one-thread-per-task k_finish, same bytes */
-			static const bool finish_warp = !(getenv("ZMO_FINISH_WARP") && atoi(getenv("ZMO_FINISH_WARP")) == 0);
-			if(finish_warp) k_finish_warp<<<(unsigned)(((unsigned long long)nt * 32 + 255) / 256), 256, 0, c->stream>>>(d_tasks, nt, d_regs, d_res, d_jobs, cig_arena, A, d_ts, d_ooff, c->s5.as<uint32_t>(), d_recs);
-			else k_finish<<<(nt + 63) / 64, 64, 0, c->stream>>>(d_tasks, nt, d_regs, d_res, d_jobs, cig_arena, A, d_ts, d_ooff, c->s5.as<uint32_t>(), d_recs);
+			k_finish_warp<<<(unsigned)(((unsigned long long)nt * 32 + 255) / 256), 256, 0, c->stream>>>(d_tasks, nt, d_regs, d_res, d_jobs, cig_arena, A, d_ts, d_ooff, c->s5.as<uint32_t>(), d_recs);
 			c->launches++;
 		}
 		CUDA_TRY(cudaGetLastError());

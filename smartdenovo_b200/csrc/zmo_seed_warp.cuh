@@ -107,27 +107,60 @@ __device__ uint32_t zmo_windows_in_span_w(const DevZPair *rs, int dir, uint32_t 
 			__syncwarp();
 		}
 	}
-	/* sub-windows along c (serial two-pointer scan, lane 0), hzm_aln.h:450-481 */
-	if(lane == 0){
-		uint32_t i, j, ol = 0, ol2, lst = 0; int ovf = 0;
-		for(i = j = 0; i < n; i++){
-			const uint64_t pk = S.ts[i]; const uint32_t p_off2 = ZMO_TS_OFF2(pk), p_len2 = ZMO_TS_LEN2(pk);
-			while(p_off2 + p_len2 > ZMO_TS_OFF2(S.ts[j]) + kwin && j + 1 < n){
-				const uint64_t k0 = S.ts[j++], k1 = S.ts[j];
-				const uint32_t s = ZMO_TS_OFF2(k1), t = ZMO_TS_OFF2(k0) + ZMO_TS_LEN2(k0);
-				ol2 = s < t? t - s : 0;
-				ol = ol + ol2 - ZMO_TS_LEN2(k0);
-			}
-			ol += (p_off2 > lst)? p_len2 : p_off2 + p_len2 - lst;
-			lst = p_off2 + p_len2;
-			if(ol >= zovl){
-				if(n2 && ( p_off2 <= ZMO_TS_OFF2(S.ts[S.we[n2-1]]) + kwin / 3 || ZMO_TS_OFF2(S.ts[j]) <= ZMO_TS_OFF2(S.ts[S.wb[n2-1]]) + kwin / 3 )){
-					if(ol > S.wo[n2-1]){ S.wb[n2-1] = j; S.we[n2-1] = i; S.wo[n2-1] = ol; }
-				} else { if(n2 >= S.capw){ ovf = 1; break; } S.wb[n2] = j; S.we[n2] = i; S.wo[n2] = ol; n2++; }
-			}
+	/* sub-windows along c (hzm_aln.h:450-481).  The reference slides two cursors over the off2-sorted entries and keeps a running covered length
+	 *   ol(i) = sum_{k<=i} inc(k) - sum_{k<J(i)} dec(k)   (uint32, wraps like the reference's)
+	 * with inc(k) = len_k or end_k - end_{k-1} (one look at the predecessor), dec(k) = len_k - overlap(k, k+1) (one look at the successor), and the
+	 * trailing cursor J(i) = min(n-1, max_{i'<=i} #{j : off_j + kwin < end_i'}).  All three are scans / searches every lane can take part in; only the
+	 * merge rule of neighbouring sub-windows is order dependent and stays on lane 0, reading ol(i) and J(i) from shared memory. */
+	const bool par_scan = (size_t)n * 4 <= (size_t)zmo_pow2_ge(O.capstage) * 8 && (size_t)n * 6 <= (size_t)O.capstage * sizeof(DevZPair) && O.stage != nullptr;
+	if(par_scan){
+		uint32_t *dsum = (uint32_t*)S.ak, *olv = (uint32_t*)O.stage; uint16_t *jv = (uint16_t*)(olv + n);
+		uint32_t carry = 0;
+		for(uint32_t base = 0; base < n; base += 32){          /* dsum[k] = sum_{k'<k} dec(k') */
+			const uint32_t k = base + lane; uint32_t v = 0;
+			if(k + 1 < n){ const uint64_t k0 = S.ts[k], k1 = S.ts[k + 1]; const uint32_t s_ = ZMO_TS_OFF2(k1), t_ = ZMO_TS_OFF2(k0) + ZMO_TS_LEN2(k0); v = ZMO_TS_LEN2(k0) - (s_ < t_? t_ - s_ : 0u); }
+			uint32_t inc = v;
+			#pragma unroll
+			for(int d = 1; d < 32; d <<= 1){ const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if(lane >= d) inc += o; }
+			if(k < n) dsum[k] = carry + inc - v;
+			carry += __shfl_sync(0xffffffffu, inc, 31);
 		}
-		if(ovf) n2 = 0xFFFFFFFFu;
-	}
+		__syncwarp();
+		uint32_t csum = 0, cmax = 0;
+		for(uint32_t base = 0; base < n; base += 32){
+			const uint32_t i = base + lane; uint32_t v = 0, T = 0;
+			if(i < n){
+				const uint64_t pk = S.ts[i]; const uint32_t off = ZMO_TS_OFF2(pk), len = ZMO_TS_LEN2(pk), lst = i? ZMO_TS_OFF2(S.ts[i - 1]) + ZMO_TS_LEN2(S.ts[i - 1]) : 0u;
+				v = (off > lst)? len : off + len - lst;
+				uint32_t lo = 0, hi = n;                           /* T = #{j : off_j + kwin < off + len} (off_j ascending) */
+				while(lo < hi){ const uint32_t mid = (lo + hi) >> 1; if(ZMO_TS_OFF2(S.ts[mid]) + kwin < off + len) lo = mid + 1; else hi = mid; }
+				T = lo;
+			}
+			uint32_t inc = v, mx = T;
+			#pragma unroll
+			for(int d = 1; d < 32; d <<= 1){
+				const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d), m_ = __shfl_up_sync(0xffffffffu, mx, d);
+				if(lane >= d){ inc += o; if(m_ > mx) mx = m_; }
+			}
+			if(cmax > mx) mx = cmax;
+			if(i < n){ const uint32_t J = mx < n - 1? mx : n - 1; olv[i] = csum + inc - dsum[J]; jv[i] = (uint16_t)J; }
+			csum += __shfl_sync(0xffffffffu, inc, 31); cmax = __shfl_sync(0xffffffffu, mx, 31);
+		}
+		__syncwarp();
+		if(lane == 0){
+			int ovf = 0;
+			for(uint32_t i = 0; i < n; i++){
+				const uint32_t ol = olv[i];
+				if(ol >= zovl){
+					const uint32_t j = jv[i], p_off2 = ZMO_TS_OFF2(S.ts[i]);
+					if(n2 && ( p_off2 <= ZMO_TS_OFF2(S.ts[S.we[n2-1]]) + kwin / 3 || ZMO_TS_OFF2(S.ts[j]) <= ZMO_TS_OFF2(S.ts[S.wb[n2-1]]) + kwin / 3 )){
+						if(ol > S.wo[n2-1]){ S.wb[n2-1] = j; S.we[n2-1] = i; S.wo[n2-1] = ol; }
+					} else { if(n2 >= S.capw){ ovf = 1; break; } S.wb[n2] = j; S.we[n2] = i; S.wo[n2] = ol; n2++; }
+				}
+			}
+			if(ovf) n2 = 0xFFFFFFFFu;
+		}
+	} else { O.overflow = 2; return 0; }      /* scratch too small for the scan arrays: the strand is redone by the serial path */
 	n2 = __shfl_sync(0xffffffffu, n2, 0);
 	__syncwarp();
 	if(n2 == 0xFFFFFFFFu){ O.overflow = 2; return 0; }

@@ -130,38 +130,11 @@ __global__ void k_finish_size(uint32_t nt, const DPRes *res, TaskState *ts, unsi
 	need[t] = n;
 }
 
-__global__ void k_finish(const AlnTask *tasks, uint32_t nt, const DevReg *regs, const DPRes *res, const DPJob *jobs_all,
-		const uint32_t *cig_arena, AlnPar A, const TaskState *ts, const unsigned long long *out_off, uint32_t *out_cig, zmo_record_t *recs){
-	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	if(t >= nt) return;
-	TaskState S = ts[t]; zmo_record_t rec; memset(&rec, 0, sizeof(rec));
-	if(!S.ok){ recs[t] = rec; return; }
-	const AlnTask T = tasks[t];
-	uint32_t *dst = out_cig + out_off[t]; uint32_t n = 0;
-	if(S.left_job >= 0){ const DPRes &y = res[S.left_job]; const DPJob &J = jobs_all[S.left_job]; cig_cat(dst, n, cig_arena + J.cig_off, (uint32_t)y.ncig, false); }
-	{ const DevReg &r0 = regs[S.first]; cig_cat(dst, n, cig_arena + r0.cig_off, r0.cig_len, false); }
-	for(uint32_t k = (uint32_t)S.first + 1 - T.item_off; k < T.n_item; k++){
-		const DevReg &r = regs[T.item_off + k];
-		if(r.kept < 2u) continue;
-		const DPRes &g = res[r.kept - 2u]; const DPJob &J = jobs_all[r.kept - 2u];
-		cig_cat(dst, n, cig_arena + J.cig_off, (uint32_t)g.ncig, true);
-		cig_cat(dst, n, cig_arena + r.cig_off, r.cig_len, false);
-	}
-	if(S.right_job >= 0){
-		const DPRes &y = res[S.right_job]; const DPJob &J = jobs_all[S.right_job];
-		S.score = y.score;
-		S.aln += y.mat + y.mis + y.ins + y.del; S.mat += y.mat; S.mis += y.mis; S.ins += y.ins; S.del += y.del;
-		S.qe += y.qe; S.te += y.te;
-		cig_cat(dst, n, cig_arena + J.cig_off, (uint32_t)y.ncig, true);
-	}
-	rec.ok = 1; rec.score = S.score; rec.tb = S.tb; rec.te = S.te; rec.qb = S.qb; rec.qe = S.qe; rec.aln = S.aln; rec.mat = S.mat; rec.mis = S.mis; rec.ins = S.ins; rec.del = S.del;
-	rec.cigar_off = out_off[t]; rec.n_cigar = n;
-	recs[t] = rec;
-}
-
-/* Warp-per-task variant of k_finish (opt-in: ZMO_FINISH_WARP=1, see pair_align_impl): the CIGAR segments of a task are copied by all
+/* Final record and stitched CIGAR of a task (global_align_regs_hzmo's bookkeeping, hzm_aln.h:1345-1486), one WARP per task: [left extension] +
+ * region 0 + sum([gap] + region i) + [right extension]; gap and extension CIGARs are stored in walk order.  The CIGAR segments of a task are copied by all
  * 32 lanes (coalesced) instead of one thread walking thousands of ops; the block-merge rule of kswx_push_cigars (kswx.h:46-52: only the
- * first op of an appended block may merge with the previous last op) is applied by lane 0 between the copies.  Same bytes as k_finish. */
+ * first op of an appended block may merge with the previous last op) is applied by lane 0 between the copies.  (A one-thread-per-task version
+ * took 15.2 ms per quarter shard of cfg2 against 0.93 ms for this one: profiles/r02_experiments_decided.md.) */
 __device__ __forceinline__ void cig_cat_warp(uint32_t *c, uint32_t &n, const uint32_t *src, uint32_t len, bool reversed, int lane){
 	if(len == 0) return;                                 /* uniform: every lane sees the same arguments */
 	const uint32_t first = reversed? src[len - 1] : src[0];

@@ -1,7 +1,7 @@
 /*
  * TEST-ONLY host simulation of the whole pair-alignment stage (zmo_pair_align) for one (q, c, strand) task: k_window_align ->
  * k_plan -> DP executor kernels (four extension classes, two gap classes, run from sorted job lists with executor slabs) -> k_plan2 ->
- * right-extension jobs -> k_finish_size -> k_finish | k_finish_warp -> optional -n refinement kernels.  The kernels are the
+ * right-extension jobs -> k_finish_size -> k_finish_warp -> optional -n refinement kernels.  The kernels are the
  * product's own source (smartdenovo_b200/csrc/zmo_*_kernels.cuh, zmo_winalign.cuh) compiled against tests/hostsim/emu/cuda_runtime.h;
  * only the host orchestration between them (buffer sizing, radix sort of the job keys, prefix sums: pair_align_impl / run_dp_lists
  * in zmo_align.cu, which call CUB and the CUDA runtime) is restated here with std:: algorithms.  Never linked into the product.
@@ -125,8 +125,8 @@ extern "C" int sim_pair_align(const uint8_t *q, int qlen, const uint8_t *c, int 
 	ooff[1] = need[0];
 	std::vector<uint32_t> final_ops(need[0] + 16, 0u); zmo_record_t rec; memset(&rec, 0xCC, sizeof(rec));
 	uint32_t *fo = final_ops.data(); zmo_record_t *drec = &rec; const unsigned long long *doo = ooff;
-	if(finish_warp) emu::launch((unsigned)(((unsigned long long)nt * 32 + 255) / 256), 256, [=](){ k_finish_warp(dt, nt, dr, dres, dj, cgp, A, dts, doo, fo, drec); });
-	else emu::launch((nt + 63) / 64, 64, [=](){ k_finish(dt, nt, dr, dres, dj, cgp, A, dts, doo, fo, drec); });
+	(void)finish_warp;
+	emu::launch((unsigned)(((unsigned long long)nt * 32 + 255) / 256), 256, [=](){ k_finish_warp(dt, nt, dr, dres, dj, cgp, A, dts, doo, fo, drec); });
 	if(!rec.ok) return -1;
 	const uint32_t *ops = fo;
 	std::vector<uint32_t> ref_ops;

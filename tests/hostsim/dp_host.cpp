@@ -199,7 +199,7 @@ extern "C" int sim_refine(const uint8_t *q, int qlen, const uint8_t *c, int clen
 }
 
 /*
- * k_finish (warp = 0) / k_finish_warp (warp = 1) on caller-built stitch inputs.  Flat arrays: per task item_off, n_item and
+ * k_finish_warp on caller-built stitch inputs.  Flat arrays: per task item_off, n_item and
  * ts = {ok, first, left_job, right_job, score, tb, te, qb, qe, aln, mat, mis, ins, del}; per region kept, cig_off, cig_len; per job
  * cig_off and jv = {score, qe, te, mat, mis, ins, del, ncig}.  recs_out = nt x {ok, score, tb, te, qb, qe, aln, mat, mis, ins, del, n_cigar}.
  */
@@ -223,8 +223,8 @@ extern "C" int sim_finish(int warp, int nt, const int *item_off, const int *n_it
 	AlnPar A; memset(&A, 0, sizeof(A));
 	const AlnTask *dt = tasks.data(); const DevReg *dr = regs.data(); const DPRes *ds = res.data(); const DPJob *dj = jobs.data(); const TaskState *dts = ts.data();
 	const unsigned long long *doo = ooff.data(); zmo_record_t *drec = recs.data(); const uint32_t n = (uint32_t)nt;
-	if(warp) emu::launch((unsigned)(((unsigned long long)n * 32 + 255) / 256), 256, [=](){ k_finish_warp(dt, n, dr, ds, dj, cig_arena, A, dts, doo, out_cig, drec); });
-	else emu::launch((n + 63) / 64, 64, [=](){ k_finish(dt, n, dr, ds, dj, cig_arena, A, dts, doo, out_cig, drec); });
+	(void)warp;
+	emu::launch((unsigned)(((unsigned long long)n * 32 + 255) / 256), 256, [=](){ k_finish_warp(dt, n, dr, ds, dj, cig_arena, A, dts, doo, out_cig, drec); });
 	for(int t = 0; t < nt; t++){
 		const zmo_record_t &r = recs[t]; int *o = recs_out + 12 * t;
 		o[0] = r.ok; o[1] = r.score; o[2] = r.tb; o[3] = r.te; o[4] = r.qb; o[5] = r.qe; o[6] = r.aln; o[7] = r.mat; o[8] = r.mis; o[9] = r.ins; o[10] = r.del; o[11] = (int)r.n_cigar;

@@ -310,9 +310,9 @@ def _cat(dst, block):
         dst.extend(block)
 
 
-@pytest.mark.parametrize("warp", [0, 1])
+@pytest.mark.parametrize("warp", [1])
 def test_finish_kernels(dp_sim, warp):
-    """k_finish and its opt-in warp-per-task variant k_finish_warp (zmo_stitch_kernels.cuh) against an independent restatement of the
+    """k_finish_warp (zmo_stitch_kernels.cuh, one warp per task) against an independent restatement of the
     stitch of global_align_regs_hzmo (hzm_aln.h:1345-1486): [left extension] + region 0 + sum([gap] + region i) + [right extension],
     gap and right-extension CIGARs stored in walk order (reversed), block-wise merging at every seam, counts from the right job"""
     rng = np.random.default_rng(33 + warp)

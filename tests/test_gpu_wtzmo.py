@@ -56,14 +56,6 @@ def test_sw_small_batches(tmp_path, gen_reads, oracle_bin):
         _compare(tmp_path, gen_reads, oracle_bin, ["-n", "120", "-L", "5000", "-G", "50000", "-s", "3"], ["-k", "16", "-s", "200", "-m", "0.6"], env=env)
 
 
-def test_thread_per_task_stitch_gives_the_same_bytes(tmp_path, gen_reads, oracle_bin):
-    """ZMO_FINISH_WARP=0: one-thread-per-task k_finish instead of the default warp-per-task k_finish_warp (both bit-exact against an
-    independent restatement in the host simulation, tests/test_dp_hostsim.py::test_finish_kernels)"""
-    env = dict(os.environ, ZMO_FINISH_WARP="0")
-    _compare(tmp_path, gen_reads, oracle_bin, ["-n", "200", "-L", "6000", "-G", "60000", "-s", "1"], ["-k", "16", "-s", "200", "-m", "0.6"], env=env)
-    _compare(tmp_path, gen_reads, oracle_bin, ["-n", "150", "-L", "5000", "-G", "50000", "-s", "3"], ["-k", "16", "-s", "200", "-m", "0.6", "-n"], env=env)
-
-
 def test_refine_n_long_indel_runs(tmp_path, oracle_bin):
     """-n with refinement bands beyond the register executors (indel runs of 800-1,000 bases): k_refine_wide / band_refine, bit-exact in
     the host simulation (tests/test_dp_hostsim.py::test_refine_kernels); before this fallback existed such a run was rejected with an error"""
