@@ -97,6 +97,8 @@ static void ref_sort(void *base, size_t n, size_t es, gt_fn gt, void *ctx){
 
 /* ------------------------------------------------------------------ 2-bit read store (dna.h:78,263,397-471) */
 static inline u32 bank_get(const u64 *bits, u64 off){ return (bits[off >> 5] >> (((~off) & 31) << 1)) & 3; }
+static inline void bank_or(u64 *bits, u64 off, u64 b){ bits[off >> 5] |= b << (((~off) & 31) << 1); }
+static inline int b_is_header(const char *buf, size_t p){ return buf[p] == '>' && (p == 0 || buf[p - 1] == '\n'); }
 static inline void bank_put(u64 *bits, u64 off, u64 b){ if((off & 31) == 0) bits[off >> 5] = 0; bits[off >> 5] |= b << (((~off) & 31) << 1); }
 
 
@@ -232,8 +234,121 @@ static int sr_next(seqreader_t *sr, u8v *name, u8v *seq){
 
 static int gt_read_len_desc(const void *a, const void *b, void *ctx){ (void)ctx; return ((const read_t*)b)->len > ((const read_t*)a)->len; }
 
+/* ------------------------------------------------------------------ parallel FASTA loader (the step right before the path)
+ * Plain FASTA files are mapped and cut into one piece per thread at header lines; every thread parses and 2-bit-packs its records into a bank
+ * of its own, the banks are then shifted into the global BaseBank in parallel.  Same result as the serial reader below, including the one
+ * order-dependent detail: non-ACGT bases become lrand48() & 3 in FILE order (dna.h:405) -- the threads only note their positions, the
+ * values are drawn afterwards in one sequential pass.  FASTQ, gzip and stdin inputs take the serial reader. */
+#include <sys/mman.h>
+#include <fcntl.h>
+#include <unistd.h>
+static u8 g_base_tab[256];
+typedef struct {
+	const char *buf; size_t beg, end, fend; int min_rdlen;
+	u64 *bits; u64 nbases, cap_words; VEC(read_t) reads; u64v bad; pthread_t th;
+} pchunk_t;
+static void* pchunk_run(void *arg){
+	pchunk_t *c = arg; const char *b = c->buf; size_t p = c->beg; const u8 *tab = g_base_tab;
+	while(p < c->end){
+		size_t nb, q, ls, len = 0; read_t r; u64 acc; int fill;
+		/* header: name = up to the first blank (file_reader.c:319-329) */
+		for(nb = p + 1; nb < c->fend; nb++){ char ch = b[nb]; if(ch == ' ' || ch == '\t' || ch == '\r' || ch == '\n') break; }
+		r.name = malloc(nb - p); memcpy(r.name, b + p + 1, nb - p - 1); r.name[nb - p - 1] = 0;
+		{ const char *e = memchr(b + p, '\n', c->fend - p); q = e? (size_t)(e - b) + 1 : c->fend; }
+		/* sequence lines up to the next header at a line start: first their total length, then the packing */
+		for(ls = q; ls < c->fend && b[ls] != '>'; ){ const char *e = memchr(b + ls, '\n', c->fend - ls); size_t le = e? (size_t)(e - b) : c->fend; len += le - ls; ls = e? le + 1 : c->fend; }
+		p = ls;
+		if((long long)len < (long long)c->min_rdlen || len > 0xFFFFFFFFULL){ free(r.name); continue; }
+		{ u64 need = (c->nbases + len + 31) / 32 + 2; if(need > c->cap_words){ u64 m = c->cap_words? c->cap_words : 4096; while(m < need) m <<= 1; c->bits = realloc(c->bits, m * 8); c->cap_words = m; } }
+		r.off = c->nbases; r.len = (u32)len;
+		{
+			u64 w = c->nbases >> 5, pos = c->nbases; fill = (int)(c->nbases & 31);
+			acc = fill? c->bits[w] >> (64 - 2 * fill) : 0;
+			for(ls = q; ls < p; ){
+				const char *e = memchr(b + ls, '\n', p - ls); size_t le = e? (size_t)(e - b) : p, k;
+				for(k = ls; k < le; k++, pos++){
+					u64 v = tab[(u8)b[k]];
+					if(v > 3){ vec_push(c->bad, pos); v = 0; }
+					acc = (acc << 2) | v;
+					if(++fill == 32){ c->bits[w++] = acc; acc = 0; fill = 0; }
+				}
+				ls = e? le + 1 : p;
+			}
+			if(fill) c->bits[w] = acc << (64 - 2 * fill);
+			c->nbases += len;
+		}
+		vec_push(c->reads, r);
+	}
+	return NULL;
+}
+typedef struct { pchunk_t *c; u64 *dst; u64 g0; pthread_t th; } pmerge_t;
+static void* pmerge_run(void *arg){
+	pmerge_t *m = arg; const pchunk_t *c = m->c; u64 nw = (c->nbases + 31) / 32, k, w0 = m->g0 >> 5; int r = (int)(m->g0 & 31);
+	for(k=0;k<nw;k++){
+		u64 v = c->bits[k];
+		if(k == nw - 1 && (c->nbases & 31)) v &= ~0ULL << (64 - 2 * (c->nbases & 31));      /* bases past the end of the piece */
+		if(r == 0) __sync_fetch_and_or(&m->dst[w0 + k], v);
+		else { __sync_fetch_and_or(&m->dst[w0 + k], v >> (2 * r)); __sync_fetch_and_or(&m->dst[w0 + k + 1], v << (64 - 2 * r)); }
+	}
+	return NULL;
+}
+/* returns 1 if the files were loaded, 0 if the serial reader has to do it (nothing touched then) */
+static int rs_load_parallel(readset_t *rs, char **files, int nfiles, int min_rdlen, int as_query, int nth){
+	int f, t; size_t i;
+	if(nth < 2) return 0;
+	memset(g_base_tab, 4, 256); g_base_tab['A'] = g_base_tab['a'] = 0; g_base_tab['C'] = g_base_tab['c'] = 1; g_base_tab['G'] = g_base_tab['g'] = 2; g_base_tab['T'] = g_base_tab['t'] = 3;
+	for(f=0;f<nfiles;f++){
+		size_t l = strlen(files[f]); int fd; char ch = 0; struct stat st;
+		if(!strcmp(files[f], "-") || (l > 3 && !strcmp(files[f] + l - 3, ".gz"))) return 0;
+		if((fd = open(files[f], O_RDONLY)) < 0) return 0;
+		if(fstat(fd, &st) || !S_ISREG(st.st_mode) || st.st_size < 2 || read(fd, &ch, 1) != 1 || ch != '>'){ close(fd); return 0; }
+		close(fd);
+	}
+	for(f=0;f<nfiles;f++){
+		int fd = open(files[f], O_RDONLY); struct stat st; const char *buf; pchunk_t *ch; pmerge_t *mg; u64 g0, tot = 0; size_t fend; int n;
+		fstat(fd, &st); fend = (size_t)st.st_size;
+		buf = mmap(NULL, fend, PROT_READ, MAP_PRIVATE, fd, 0);
+		close(fd);
+		if(buf == MAP_FAILED){ fprintf(stderr, " -- Cannot map %s --\n", files[f]); exit(1); }
+		madvise((void*)buf, fend, MADV_SEQUENTIAL);
+		n = nth; if((size_t)n > fend / 4096 + 1) n = (int)(fend / 4096 + 1);
+		ch = calloc(n + 1, sizeof(pchunk_t)); mg = calloc(n + 1, sizeof(pmerge_t));
+		for(t=0;t<=n;t++){
+			/* piece t starts at the first header line at or after its share of the file */
+			size_t p = t == n? fend : (size_t)((unsigned __int128)fend * t / n);
+			if(t == 0) p = 0;
+			else while(p < fend){ const char *e; if(b_is_header(buf, p)) break; e = memchr(buf + p, '\n', fend - p); p = e? (size_t)(e - buf) + 1 : fend; }
+			ch[t].beg = p;
+		}
+		for(t=0;t<n;t++){ ch[t].buf = buf; ch[t].end = ch[t + 1].beg; ch[t].fend = fend; ch[t].min_rdlen = min_rdlen; if(ch[t].end < ch[t].beg) ch[t].end = ch[t].beg; }
+		for(t=0;t<n;t++) if(pthread_create(&ch[t].th, NULL, pchunk_run, &ch[t]) != 0){ pchunk_run(&ch[t]); ch[t].th = 0; }
+		for(t=0;t<n;t++){ if(ch[t].th) pthread_join(ch[t].th, NULL); tot += ch[t].nbases; }
+		{	/* grow the global bank (zero-filled), then shift the pieces in */
+			u64 need = (rs->nbases + tot + 31) / 32 + 2;
+			if(need > rs->cap_words){ u64 m = rs->cap_words? rs->cap_words : 1024; while(m < need) m <<= 1; rs->bits = realloc(rs->bits, m * 8); memset(rs->bits + rs->cap_words, 0, (m - rs->cap_words) * 8); rs->cap_words = m; }
+			/* words past the current end must be zero: the serial appender leaves garbage-free words (it zeroes on growth and writes whole words) */
+			{ u64 w = (rs->nbases + 31) / 32; memset(rs->bits + w, 0, (rs->cap_words - w) * 8); if(rs->nbases & 31) rs->bits[rs->nbases >> 5] &= ~0ULL << (64 - 2 * (rs->nbases & 31)); }
+		}
+		g0 = rs->nbases;
+		for(t=0;t<n;t++){ mg[t].c = &ch[t]; mg[t].dst = rs->bits; mg[t].g0 = g0; g0 += ch[t].nbases; }
+		for(t=0;t<n;t++) if(pthread_create(&mg[t].th, NULL, pmerge_run, &mg[t]) != 0){ pmerge_run(&mg[t]); mg[t].th = 0; }
+		for(t=0;t<n;t++) if(mg[t].th) pthread_join(mg[t].th, NULL);
+		for(t=0;t<n;t++){
+			/* reads in file order; non-ACGT bases drawn in file order (dna.h:405) */
+			for(i=0;i<ch[t].reads.n;i++){ read_t r = ch[t].reads.a[i]; r.off += mg[t].g0; vec_push(rs->reads, r); if(as_query) rs->n_qr ++; else rs->n_rd ++; }
+			for(i=0;i<ch[t].bad.n;i++) bank_or(rs->bits, mg[t].g0 + ch[t].bad.a[i], (u64)(lrand48() & 3));
+			free(ch[t].bits); vec_free(ch[t].reads); vec_free(ch[t].bad);
+		}
+		rs->nbases = g0;
+		free(ch); free(mg);
+		munmap((void*)buf, fend);
+	}
+	return 1;
+}
+
 static void rs_load(readset_t *rs, char **files, int nfiles, int min_rdlen, int as_query){
 	seqreader_t sr; u8v name, seq;
+	{ char *env = getenv("ZMO_LOAD_THREADS"); long nc = sysconf(_SC_NPROCESSORS_ONLN); int nth = env? atoi(env) : (int)(nc > 16? 16 : nc); if(rs_load_parallel(rs, files, nfiles, min_rdlen, as_query, nth)) return; }
 	memset(&sr, 0, sizeof(sr)); sr.files = files; sr.nfiles = nfiles;
 	vec_init(name); vec_init(seq);
 	while(sr_next(&sr, &name, &seq)){
@@ -257,6 +372,25 @@ static u32 rs_find(const readset_t *rs, u32 n, const char *name){   /* linear/bs
 }
 
 
+
+/* test hook (CPU suite): load the files with `threads` loader threads (0 / 1 = the serial reader) from the process-start state of lrand48 and
+ * return {reads, bases, FNV-1a over (lengths, names, bank words)}: the parallel loader must reproduce the serial one bit for bit */
+int wz_load_digest(int nfiles, char **files, int min_rdlen, int threads, uint64_t out[3]){
+	readset_t rs; char tbuf[32]; u64 h = 1469598103934665603ULL; size_t i, k; const char *old = getenv("ZMO_LOAD_THREADS"); char *keep = old? strdup(old) : NULL;
+	memset(&rs, 0, sizeof(rs));
+	srand48(0x1234ABCD);      /* = the initial state of lrand48() in a fresh process */
+	snprintf(tbuf, sizeof(tbuf), "%d", threads); setenv("ZMO_LOAD_THREADS", tbuf, 1);
+	rs_load(&rs, files, nfiles, min_rdlen, 0);
+	if(keep){ setenv("ZMO_LOAD_THREADS", keep, 1); free(keep); } else unsetenv("ZMO_LOAD_THREADS");
+#define FNV(b) do { h ^= (u64)(b); h *= 1099511628211ULL; } while(0)
+	for(i=0;i<rs.reads.n;i++){ const read_t *r = &rs.reads.a[i]; const char *s = r->name; FNV(r->len); FNV(r->off); while(*s) FNV((u8)*s++); FNV(0xFF); }
+	for(k=0;k<(rs.nbases+31)/32;k++){ u64 w = rs.bits[k]; if(k == (rs.nbases >> 5) && (rs.nbases & 31)) w &= ~0ULL << (64 - 2 * (rs.nbases & 31)); FNV(w & 0xFFFFFFFFULL); FNV(w >> 32); }
+#undef FNV
+	out[0] = rs.reads.n; out[1] = rs.nbases; out[2] = h;
+	for(i=0;i<rs.reads.n;i++) free(rs.reads.a[i].name);
+	vec_free(rs.reads); free(rs.bits);
+	return 0;
+}
 
 /* ------------------------------------------------------------------ heap macros behaviour (list.h:78-144) on u64 keyed by low 32 bits */
 static inline int cand_cmp(u64 a, u64 b){ u32 x = (u32)a, y = (u32)b; return x > y? 1 : (x < y? -1 : 0); }

@@ -53,7 +53,7 @@ extern "C" int zmo_index_build(zmo_ctx *c, uint32_t beg, uint32_t end, uint32_t 
 	/* run-length encode (hand-rolled, 64-bit safe): head flags -> exclusive scan -> scatter of
 	 * distinct k-mers (ix_mer) and run starts; counts = difference of consecutive run starts */
 	if(N >= 0xFFFFFFF0ull) return zmo_set_err(ZMO_ERR_CAPACITY, "index partition too large (%llu sampled k-mers); split it with -G", N);
-	if(c->st->ix_mer.reserve(N * 8) || c->s0.reserve((N + 2) * 8) || c->s6.reserve(N * 4 + 16) || c->s7.reserve(N * 4 + 16)) return ZMO_ERR_CUDA;
+	if(c->s0.reserve((N + 2) * 8) || c->s6.reserve(N * 4 + 16) || c->s7.reserve(N * 4 + 16)) return ZMO_ERR_CUDA;
 	unsigned long long *ctr = c->d_ctr.as<unsigned long long>();
 	uint32_t *d_hflag = c->s6.as<uint32_t>(), *d_hpos = c->s7.as<uint32_t>();
 	unsigned long long *run_start = c->s0.as<unsigned long long>();
@@ -64,6 +64,7 @@ extern "C" int zmo_index_build(zmo_ctx *c, uint32_t beg, uint32_t end, uint32_t 
 	CUDA_TRY(cudaMemcpyAsync(&lf, d_hflag + (N - 1), 4, cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	const unsigned long long ne = (unsigned long long)lp + lf;
+	if(c->st->ix_mer.reserve((ne + 2) * 8)) return ZMO_ERR_CUDA;      /* distinct k-mers only (cfg4: 7 M of 2.3 G sampled) */
 	k_idx_runs<<<(unsigned)((N + 255) / 256), 256, 0, c->stream>>>(k_out, d_hflag, d_hpos, N, c->st->ix_mer.as<unsigned long long>(), run_start); c->launches++;
 	uint32_t *d_rc = v_in;       /* v_in is free after the sort */
 	k_idx_counts<<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(run_start, ne, N, d_rc); c->launches++;
@@ -95,6 +96,9 @@ extern "C" int zmo_index_build(zmo_ctx *c, uint32_t beg, uint32_t end, uint32_t 
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	c->st->n_ent = ne; c->st->n_post = np; c->st->have_index = true;
+	/* the sort buffers of a large partition (cfg4: 120 GB for 2.3 G sampled k-mers) are not needed by the batches: give them back, the
+	 * per-batch stages re-grow what they use (a few GB); small builds keep theirs so that a rebuilt index costs no allocation */
+	{ DevBuf *tmp[] = { &c->s0, &c->s1, &c->s2, &c->s3, &c->s4, &c->s5, &c->s6, &c->s7, &c->cubtmp }; for(DevBuf *b : tmp) if(b->cap > (2ull << 30)) b->release(); }
 	if(stats){ stats->n_kmers = ne; stats->n_postings = np; stats->n_filtered_high = st2[0]; stats->n_indexed = st2[1]; stats->kcut = K; stats->kavg = kavg; }
 	return 0;
 }
