@@ -37,17 +37,30 @@ int seed_prepare(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, int mode, See
 	/* layout of small per-batch arrays in s0: uq | pq | pc | slot_beg ; s1: zcnt/zoff ; */
 	if(c->s0.reserve(((size_t)nuq + 2 + 2 * (size_t)np + nuq + 4) * 4) || c->s1.reserve(((size_t)nuq + 2) * 16)) return ZMO_ERR_CUDA;
 	uint32_t *d_uq = c->s0.as<uint32_t>(), *d_pq = d_uq + nuq + 1, *d_pc = d_pq + np, *d_slot_beg = d_pc + np;
-	unsigned long long *d_zcnt = c->s1.as<unsigned long long>(), *d_zoff = d_zcnt + nuq + 1;
+	unsigned long long *d_zoff = c->s1.as<unsigned long long>() + nuq + 1;
 	CUDA_TRY(cudaMemcpyAsync(d_uq, uq.data(), (size_t)nuq * 4, cudaMemcpyHostToDevice, c->stream));
 	CUDA_TRY(cudaMemcpyAsync(d_pq, pq.data(), (size_t)np * 4, cudaMemcpyHostToDevice, c->stream));
 	CUDA_TRY(cudaMemcpyAsync(d_pc, pc.data(), (size_t)np * 4, cudaMemcpyHostToDevice, c->stream));
 	c->counters[5] += ((size_t)nuq + 2 * (size_t)np) * 4;
-	const int bs = 32;
-	k_z_scan<0><<<(nuq + bs - 1) / bs, bs, 0, c->stream>>>(R, d_uq, nuq, c->par.zsize, c->par.hz, d_zcnt, nullptr, nullptr); c->launches++;
-	CUDA_TRY(cudaMemsetAsync(d_zcnt + nuq, 0, 8, c->stream));
-	CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_zcnt, d_zoff, nuq + 1, c->stream));
+	/* z-mer scan, chunk-parallel: chunk table from the host copy of the read lengths (no device round trip), per-chunk counts and offsets
+	 * behind the slot filters in zfilt */
+	std::vector<unsigned long long> h_choff(nuq + 1);
+	unsigned long long NCz = 0;
+	for(uint32_t u = 0; u < nuq; u++){ h_choff[u] = NCz; NCz += (c->st->h_rdlen[uq[u]] + ZSCAN_CH - 1) / ZSCAN_CH; }
+	h_choff[nuq] = NCz;
+	const size_t filt_bytes = (size_t)(nuq + 1) * ZF_WORDS * 4;
+	if(c->zfilt.reserve(filt_bytes + (NCz + 2) * 16 + ((size_t)nuq + 2) * 8 + 64)) return ZMO_ERR_CUDA;
+	unsigned long long *d_ccnt = (unsigned long long*)((uint8_t*)c->zfilt.p + filt_bytes), *d_ccoff = d_ccnt + NCz + 1, *d_zchoff = d_ccoff + NCz + 1;
+	CUDA_TRY(cudaMemcpyAsync(d_zchoff, h_choff.data(), ((size_t)nuq + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+	c->counters[5] += ((size_t)nuq + 1) * 8;
 	unsigned long long Z = 0;
-	CUDA_TRY(cudaMemcpyAsync(&Z, d_zoff + nuq, 8, cudaMemcpyDeviceToHost, c->stream));
+	if(NCz){
+		k_z_scan<0><<<(unsigned)((NCz + 127) / 128), 128, 0, c->stream>>>(R, d_uq, nuq, d_zchoff, NCz, c->par.zsize, c->par.hz, d_ccnt, nullptr, nullptr); c->launches++;
+		CUDA_TRY(cudaMemsetAsync(d_ccnt + NCz, 0, 8, c->stream));
+		CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_ccnt, d_ccoff, (uint64_t)NCz + 1, c->stream));
+		k_z_readoff<<<(nuq + 1 + 127) / 128, 128, 0, c->stream>>>(d_zchoff, d_ccoff, nuq, d_zoff); c->launches++;
+		CUDA_TRY(cudaMemcpyAsync(&Z, d_ccoff + NCz, 8, cudaMemcpyDeviceToHost, c->stream));
+	} else CUDA_TRY(cudaMemsetAsync(d_zoff, 0, ((size_t)nuq + 1) * 8, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	if(Z >= 0xFFFFFFF0ull) return zmo_set_err(ZMO_ERR_CAPACITY, "pair batch too large (%llu z-mers)", Z);
 	/* s2 keys_in, s3 keys_out, s4 vals_in, s5 vals_out, s6 flag|pos|runlen, s7 zs|slots */
@@ -57,10 +70,9 @@ int seed_prepare(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, int mode, See
 	uint32_t *d_flag = c->s6.as<uint32_t>(), *d_pos = d_flag + Zp, *d_run = d_pos + Zp;
 	DevZSeed *d_zs = c->s7.as<DevZSeed>(); DevSlot *d_slots = (DevSlot*)(d_zs + Zp);
 	uint32_t NS = 0;
-	if(c->zfilt.reserve((size_t)(nuq + 1) * ZF_WORDS * 4)) return ZMO_ERR_CUDA;
-	CUDA_TRY(cudaMemsetAsync(c->zfilt.p, 0, (size_t)(nuq + 1) * ZF_WORDS * 4, c->stream));
+	CUDA_TRY(cudaMemsetAsync(c->zfilt.p, 0, filt_bytes, c->stream));
 	if(Z){
-		k_z_scan<1><<<(nuq + bs - 1) / bs, bs, 0, c->stream>>>(R, d_uq, nuq, c->par.zsize, c->par.hz, d_zoff, k_in, v_in); c->launches++;
+		k_z_scan<1><<<(unsigned)((NCz + 127) / 128), 128, 0, c->stream>>>(R, d_uq, nuq, d_zchoff, NCz, c->par.zsize, c->par.hz, d_ccoff, k_in, v_in); c->launches++;
 		int qbits = 1; while((1ull << qbits) < nuq) qbits++;
 		CUB_CALL(c, cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, k_in, k_out, v_in, v_out, (uint64_t)Z, 0, 32 + qbits, c->stream));
 		k_z_heads<<<(unsigned)((Z + 255) / 256), 256, 0, c->stream>>>(k_out, v_out, Z, (uint32_t)c->par.zcut, d_flag, d_run, d_zs); c->launches++;

@@ -9,17 +9,29 @@
 #include "zmo_ctx.cuh"
 #include "zmo_seed_core.cuh"
 
+#define ZSCAN_CH 128
+/* z-mers of the batch's query reads, one thread per (read, 128-base chunk): chunk c of read u emits the z-mers whose last kept base lies in the
+ * chunk (zmo_scan_kmers_chunk), in offset order; the chunk table choff (nuq + 1 entries, built on the host from the read lengths) maps chunks to
+ * reads.  PASS 0 counts per chunk, PASS 1 writes key = u << 32 | mer, value = off << 17 | len << 1 | dir at the chunk's offset. */
 template<int PASS>
-__global__ void k_z_scan(DevReads R, const uint32_t *uq, uint32_t nuq, int zsize, int hz, unsigned long long *cnt_or_off, unsigned long long *keys, unsigned long long *vals){
-	uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-	if(u >= nuq) return;
-	const uint32_t rid = uq[u];
-	unsigned long long n = PASS? cnt_or_off[u] : 0;
-	zmo_scan_kmers(R.words + R.woff[rid], R.len[rid], zsize, hz, [&](uint64_t mer, uint32_t dir, uint32_t off, uint32_t ln){
+__global__ void k_z_scan(DevReads R, const uint32_t *uq, uint32_t nuq, const unsigned long long *choff, unsigned long long NC, int zsize, int hz,
+		unsigned long long *cnt_or_off, unsigned long long *keys, unsigned long long *vals){
+	unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if(c >= NC) return;
+	uint32_t lo = 0, hi = nuq;
+	while(lo + 1 < hi){ uint32_t mid = (lo + hi) >> 1; if(choff[mid] <= c) lo = mid; else hi = mid; }
+	const uint32_t u = lo, rid = uq[u], s0 = (uint32_t)(c - choff[u]) * ZSCAN_CH;
+	unsigned long long n = PASS? cnt_or_off[c] : 0;
+	zmo_scan_kmers_chunk(R.words + R.woff[rid], R.len[rid], zsize, hz, s0, s0 + ZSCAN_CH, [&](uint64_t mer, uint32_t dir, uint32_t off, uint32_t ln){
 		if(PASS){ keys[n] = ((unsigned long long)u << 32) | (uint32_t)mer; vals[n] = ((unsigned long long)off << 17) | ((unsigned long long)ln << 1) | dir; }
 		n++;
 	});
-	if(!PASS) cnt_or_off[u] = n;
+	if(!PASS) cnt_or_off[c] = n;
+}
+/* first z-mer of every read = offset of its first chunk (zoff[nuq] = total) */
+__global__ void k_z_readoff(const unsigned long long *choff, const unsigned long long *coff, uint32_t nuq, unsigned long long *zoff){
+	uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+	if(u <= nuq) zoff[u] = coff[choff[u]];
 }
 /* per sorted z-seed: unpack payload; run heads count their run and flag it as a slot if shorter than zcut */
 __global__ void k_z_heads(const unsigned long long *keys, const unsigned long long *vals, unsigned long long n, uint32_t zcut, uint32_t *flag, uint32_t *runlen, DevZSeed *zs){

@@ -189,8 +189,17 @@ extern "C" int simk_batch_windows(const uint8_t *seqs, const int *lens, int nrea
 	const uint32_t *d_uq = uq.data(), *d_pq = pq.data(), *d_pc = pc.data();
 	unsigned long long *d_zcnt = zcnt.data(), *d_zoff = zoff.data();
 	const int bs = 32;
-	emu::launch((nuq + bs - 1) / bs, bs, [=](){ k_z_scan<0>(R, d_uq, nuq, zsize, hz, d_zcnt, nullptr, nullptr); });
-	zcnt[nuq] = 0; excl_scan(zcnt.data(), zoff.data(), (size_t)nuq + 1);
+	/* chunk table from the read lengths, per-chunk counts -> offsets, read offsets (what seed_prepare does with a CUB scan) */
+	std::vector<unsigned long long> zchoff(nuq + 1, 0);
+	unsigned long long NCz = 0;
+	for(uint32_t u = 0; u < nuq; u++){ zchoff[u] = NCz; NCz += (R.len[d_uq[u]] + ZSCAN_CH - 1) / ZSCAN_CH; }
+	zchoff[nuq] = NCz;
+	std::vector<unsigned long long> zccnt(NCz + 2, 0), zccoff(NCz + 2, 0);
+	const unsigned long long *d_zchoff = zchoff.data(); unsigned long long *d_zccnt = zccnt.data(), *d_zccoff = zccoff.data();
+	(void)bs; (void)d_zcnt;
+	emu::launch((unsigned)((NCz + 127) / 128), 128, [=](){ k_z_scan<0>(R, d_uq, nuq, d_zchoff, NCz, zsize, hz, d_zccnt, nullptr, nullptr); });
+	zccnt[NCz] = 0; excl_scan(zccnt.data(), zccoff.data(), (size_t)NCz + 1);
+	emu::launch((nuq + 1 + 127) / 128, 128, [=](){ k_z_readoff(d_zchoff, d_zccoff, nuq, d_zoff); });
 	const unsigned long long Z = zoff[nuq], Zp = Z + 4;
 	std::vector<unsigned long long> zk(Zp), zv(Zp); std::vector<uint32_t> flag(Zp, 0), pos(Zp, 0), run(Zp, 0); std::vector<DevZSeed> zs(Zp); std::vector<DevSlot> slots(Zp);
 	std::vector<uint32_t> filt((size_t)(nuq + 1) * ZF_WORDS, 0u), slot_beg(nuq + 2, 0);
@@ -198,7 +207,7 @@ extern "C" int simk_batch_windows(const uint8_t *seqs, const int *lens, int nrea
 	unsigned long long *d_zk = zk.data(), *d_zv = zv.data(); uint32_t *d_flag = flag.data(), *d_pos = pos.data(), *d_run = run.data(); DevZSeed *d_zs = zs.data(); DevSlot *d_slots = slots.data();
 	uint32_t *d_filt = filt.data(), *d_sb = slot_beg.data();
 	if(Z){
-		emu::launch((nuq + bs - 1) / bs, bs, [=](){ k_z_scan<1>(R, d_uq, nuq, zsize, hz, d_zoff, d_zk, d_zv); });
+		emu::launch((unsigned)((NCz + 127) / 128), 128, [=](){ k_z_scan<1>(R, d_uq, nuq, d_zchoff, NCz, zsize, hz, d_zccoff, d_zk, d_zv); });
 		sort_pairs(zk, zv, (size_t)Z);
 		emu::launch((unsigned)((Z + 255) / 256), 256, [=](){ k_z_heads(d_zk, d_zv, Z, (uint32_t)zcut, d_flag, d_run, d_zs); });
 		excl_scan(flag.data(), pos.data(), (size_t)Z);
