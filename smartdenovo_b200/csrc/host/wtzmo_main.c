@@ -474,7 +474,9 @@ typedef struct {
 	double t_dev, t_replay, t_write;
 	int batch_reads, batch_pairs;
 	/* page-locked result buffers reused across batches */
-	zmo_record_t *pin_recs[WZ_MAX_CTX][WZ_PIN_WAVES]; size_t pin_recs_cap[WZ_MAX_CTX][WZ_PIN_WAVES]; u32 *pin_cig[WZ_MAX_CTX][WZ_PIN_WAVES]; size_t pin_cig_cap[WZ_MAX_CTX][WZ_PIN_WAVES];
+	/* one page-locked arena per device context: the result buffers of a batch's DP waves are carved from it (bump allocation, reset when the next
+	 * batch starts on that context); allocated once on the start-up thread -- cudaHostAlloc costs ~45 ms per CALL next to running kernels */
+	struct { u8 *base; size_t cap, used, want; } pin[WZ_MAX_CTX];
 	pthread_mutex_t dev_mu[WZ_MAX_CTX];  /* one device call at a time per context */
 	pthread_mutex_t stat_mu;
 	u64 n_waves, n_wave_tasks; int wave_margin, wave_growth;
@@ -793,6 +795,18 @@ static void batch_pairs(wz_t *z, batch_t *b){
 	}
 }
 
+/* the context's previous batch has been replayed: its result buffers are dead; grow the arena if the last batch spilled */
+#define WZ_PIN_ARENA0 ((size_t)160 << 20)
+static void pin_arena_reset(wz_t *z, int ci){
+	z->pin[ci].used = 0;
+	if(z->pin[ci].base == NULL || z->pin[ci].want > z->pin[ci].cap){
+		size_t cap = z->pin[ci].want > WZ_PIN_ARENA0? z->pin[ci].want : WZ_PIN_ARENA0;
+		if(z->pin[ci].base) zmo_host_free(z->pin[ci].base);
+		z->pin[ci].base = zmo_host_alloc(cap); if(!z->pin[ci].base) die_zmo("zmo_host_alloc");
+		z->pin[ci].cap = cap; z->pin[ci].want = cap;
+	}
+}
+
 /* first guess of the CIGAR text of a wave, in 4-byte words: an alignment has at most min(len q, len c) + end overhangs columns and its text
  * measured 0.77 bytes per column on 15%-error reads; 1.1 bytes per base of the shorter read + slack covers it (a too small buffer costs a
  * re-run of the wave: ZMO_ERR_CAPACITY) */
@@ -826,6 +840,7 @@ static void batch_compute(wz_t *z, batch_t *b){
 	if(rc) die_zmo("zmo_pair_windows");
 	if(!par->do_align) return;
 	b->pres = calloc(b->pairs.n, sizeof(*b->pres)); b->pcig = calloc(b->pairs.n, sizeof(*b->pcig)); b->pdir = calloc(b->pairs.n, 1);
+	pin_arena_reset(z, b->ci);
 	/* DP waves: every read's seeds in the order the replay is predicted to walk them (build_seeds on the candidate list
 	 * as it was at batch build time); wave k aligns the next chunk (16, 32, 64, ... seeds) of every read whose DRY walk
 	 * over the results so far still stops at a missing alignment.  Most reads finish early (the first containing
@@ -860,27 +875,28 @@ static void batch_compute(wz_t *z, batch_t *b){
 			if(tk.n == 0){ vec_free(tk); break; }
 			pthread_mutex_lock(&z->stat_mu); z->n_tasks += tk.n; pthread_mutex_unlock(&z->stat_mu);
 			{
-				/* results land in page-locked buffers owned by (context, wave): they stay valid until the batch has been replayed */
-				const int ps = b->ci, pinned = wave < WZ_PIN_WAVES;
-				if(pinned){
-					if(tk.n > z->pin_recs_cap[ps][wave]){ zmo_host_free(z->pin_recs[ps][wave]); z->pin_recs_cap[ps][wave] = tk.n * 2 + 1024; z->pin_recs[ps][wave] = zmo_host_alloc(z->pin_recs_cap[ps][wave] * sizeof(zmo_record_t)); if(!z->pin_recs[ps][wave]) die_zmo("zmo_host_alloc"); }
-					const size_t want = wave_text_words(z, b, tk.a, tk.n);
-					if(z->pin_cig_cap[ps][wave] < want){ zmo_host_free(z->pin_cig[ps][wave]); z->pin_cig_cap[ps][wave] = want * 5 / 4 + (1u << 18); z->pin_cig[ps][wave] = zmo_host_alloc(z->pin_cig_cap[ps][wave] * 4); if(!z->pin_cig[ps][wave]) die_zmo("zmo_host_alloc"); }
-					recs = z->pin_recs[ps][wave]; cig = z->pin_cig[ps][wave]; cap = z->pin_cig_cap[ps][wave];
-				} else { recs = malloc(tk.n * sizeof(zmo_record_t)); cap = wave_text_words(z, b, tk.a, tk.n); cig = malloc(cap * 4); }
+				/* results land in the context's page-locked arena (or, if it is full, in pageable memory until the next batch has grown it): they
+				 * stay valid until the batch has been replayed */
+				const int ps = b->ci; const size_t want = wave_text_words(z, b, tk.a, tk.n), rbytes = (tk.n * sizeof(zmo_record_t) + 63) & ~(size_t)63;
+				int pinned = z->pin[ps].used + rbytes + want * 4 <= z->pin[ps].cap;
+				if(pinned){ recs = (zmo_record_t*)(z->pin[ps].base + z->pin[ps].used); cig = (u32*)(z->pin[ps].base + z->pin[ps].used + rbytes); cap = want; z->pin[ps].used += (rbytes + want * 4 + 63) & ~(size_t)63; }
+				else {
+					recs = malloc(tk.n * sizeof(zmo_record_t)); cap = want; cig = malloc(cap * 4); vec_push(b->extra, (void*)recs); vec_push(b->extra, (void*)cig);
+					if(z->pin[ps].want < 2 * (z->pin[ps].used + rbytes + want * 4)) z->pin[ps].want = 2 * (z->pin[ps].used + rbytes + want * 4);
+				}
 				pthread_mutex_lock(mu);
 				rc = zmo_pair_align_text(ctx, b->slot, tk.a, (u32)tk.n, recs, (char*)cig, cap * 4, &need);
 				if(rc == ZMO_ERR_CAPACITY && need > cap * 4){
+					/* the guess was too small: the text of this wave goes to pageable memory, the wave is run again */
 					cap = (need + need / 4) / 4 + 16;
-					if(pinned){ zmo_host_free(z->pin_cig[ps][wave]); z->pin_cig_cap[ps][wave] = cap; z->pin_cig[ps][wave] = zmo_host_alloc(cap * 4); if(!z->pin_cig[ps][wave]) die_zmo("zmo_host_alloc"); cig = z->pin_cig[ps][wave]; }
-					else cig = realloc(cig, cap * 4);
+					cig = malloc(cap * 4); vec_push(b->extra, (void*)cig);
+					if(z->pin[ps].want < z->pin[ps].cap + 2 * cap * 4) z->pin[ps].want = z->pin[ps].cap + 2 * cap * 4;
 					rc = zmo_pair_align_text(ctx, b->slot, tk.a, (u32)tk.n, recs, (char*)cig, cap * 4, &need);
 				}
 				pthread_mutex_unlock(mu);
 			}
 			if(rc) die_zmo("zmo_pair_align");
 			for(i=0;i<tk.n;i++){ b->pres[tk.a[i].pair_idx] = &recs[i]; b->pcig[tk.a[i].pair_idx] = cig; b->pdir[tk.a[i].pair_idx] = (u8)tk.a[i].dir; }
-			if(wave >= WZ_PIN_WAVES){ vec_push(b->extra, (void*)recs); vec_push(b->extra, (void*)cig); }
 			vec_free(tk);
 			for(i=0;i<nr;i++) if(pos[i] >= 0) pos[i] = dry_walk(z, b, &b->reads.a[i], &sv[i]);
 			wave ++; if(chunk < ((size_t)1 << 20)) chunk *= (size_t)z->wave_growth;
@@ -1100,6 +1116,7 @@ static void* ctx_boot_thread(void *arg){
 	/* one context per queued batch: those in flight + the one being replayed (which may still ask for on-demand waves) */
 	z->ctxs[0] = z->ctx; z->n_ctx = 1;
 	for(q=1;q<z->depth;q++){ if(zmo_ctx_clone(z->ctx, &z->ctxs[z->n_ctx])){ snprintf(b->err, sizeof(b->err), "zmo_ctx_clone: %s", zmo_last_error()); b->rc = 3; return NULL; } z->n_ctx ++; }
+	if(z->par.do_align && !z->par.dot_matrix) for(q=0;q<z->n_ctx;q++) pin_arena_reset(z, q);      /* page-locked result arenas, behind the FASTA parse */
 	return NULL;
 }
 static int ctx_boot_join(ctx_boot_t *b){
@@ -1337,7 +1354,7 @@ void wz_stats(wz_session_t *S, double *out){
 	out[32] = (double)z->n_reads_batched; out[33] = (double)z->n_reads_late_masked; out[34] = (double)z->n_pairs_late_masked;      /* speculation: reads batched / masked by the time of their turn / their candidates */
 }
 
-void wz_close(wz_session_t *S){ if(S){ int q; for(q=S->z.n_ctx-1;q>=0;q--) if(S->z.ctxs[q]) zmo_ctx_destroy(S->z.ctxs[q]); free(S); } }
+void wz_close(wz_session_t *S){ if(S){ int q; for(q=0;q<WZ_MAX_CTX;q++) if(S->z.pin[q].base) zmo_host_free(S->z.pin[q].base); for(q=S->z.n_ctx-1;q>=0;q--) if(S->z.ctxs[q]) zmo_ctx_destroy(S->z.ctxs[q]); free(S); } }
 
 /* ------------------------------------------------------------------ multi-GPU job: ZMO_GPUS=n
  * One process, one host thread per GPU.  GPU g runs the reference's job `-P (P*n) -p (p*n+g)` (query reads with rd_id % (P*n) == p*n+g

@@ -50,16 +50,16 @@ int seed_prepare(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, int mode, See
 	h_choff[nuq] = NCz;
 	const size_t filt_bytes = (size_t)(nuq + 1) * ZF_WORDS * 4;
 	if(c->zfilt.reserve(filt_bytes + (NCz + 2) * 16 + ((size_t)nuq + 2) * 8 + 64)) return ZMO_ERR_CUDA;
-	unsigned long long *d_ccnt = (unsigned long long*)((uint8_t*)c->zfilt.p + filt_bytes), *d_ccoff = d_ccnt + NCz + 1, *d_zchoff = d_ccoff + NCz + 1;
+	unsigned long long *d_zccnt = (unsigned long long*)((uint8_t*)c->zfilt.p + filt_bytes), *d_zccoff = d_zccnt + NCz + 1, *d_zchoff = d_zccoff + NCz + 1;
 	CUDA_TRY(cudaMemcpyAsync(d_zchoff, h_choff.data(), ((size_t)nuq + 1) * 8, cudaMemcpyHostToDevice, c->stream));
 	c->counters[5] += ((size_t)nuq + 1) * 8;
 	unsigned long long Z = 0;
 	if(NCz){
-		k_z_scan<0><<<(unsigned)((NCz + 127) / 128), 128, 0, c->stream>>>(R, d_uq, nuq, d_zchoff, NCz, c->par.zsize, c->par.hz, d_ccnt, nullptr, nullptr); c->launches++;
-		CUDA_TRY(cudaMemsetAsync(d_ccnt + NCz, 0, 8, c->stream));
-		CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_ccnt, d_ccoff, (uint64_t)NCz + 1, c->stream));
-		k_z_readoff<<<(nuq + 1 + 127) / 128, 128, 0, c->stream>>>(d_zchoff, d_ccoff, nuq, d_zoff); c->launches++;
-		CUDA_TRY(cudaMemcpyAsync(&Z, d_ccoff + NCz, 8, cudaMemcpyDeviceToHost, c->stream));
+		k_z_scan<0><<<(unsigned)((NCz + 127) / 128), 128, 0, c->stream>>>(R, d_uq, nuq, d_zchoff, NCz, c->par.zsize, c->par.hz, d_zccnt, nullptr, nullptr); c->launches++;
+		CUDA_TRY(cudaMemsetAsync(d_zccnt + NCz, 0, 8, c->stream));
+		CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_zccnt, d_zccoff, (uint64_t)NCz + 1, c->stream));
+		k_z_readoff<<<(nuq + 1 + 127) / 128, 128, 0, c->stream>>>(d_zchoff, d_zccoff, nuq, d_zoff); c->launches++;
+		CUDA_TRY(cudaMemcpyAsync(&Z, d_zccoff + NCz, 8, cudaMemcpyDeviceToHost, c->stream));
 	} else CUDA_TRY(cudaMemsetAsync(d_zoff, 0, ((size_t)nuq + 1) * 8, c->stream));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	if(Z >= 0xFFFFFFF0ull) return zmo_set_err(ZMO_ERR_CAPACITY, "pair batch too large (%llu z-mers)", Z);
@@ -72,7 +72,7 @@ int seed_prepare(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, int mode, See
 	uint32_t NS = 0;
 	CUDA_TRY(cudaMemsetAsync(c->zfilt.p, 0, filt_bytes, c->stream));
 	if(Z){
-		k_z_scan<1><<<(unsigned)((NCz + 127) / 128), 128, 0, c->stream>>>(R, d_uq, nuq, d_zchoff, NCz, c->par.zsize, c->par.hz, d_ccoff, k_in, v_in); c->launches++;
+		k_z_scan<1><<<(unsigned)((NCz + 127) / 128), 128, 0, c->stream>>>(R, d_uq, nuq, d_zchoff, NCz, c->par.zsize, c->par.hz, d_zccoff, k_in, v_in); c->launches++;
 		int qbits = 1; while((1ull << qbits) < nuq) qbits++;
 		CUB_CALL(c, cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, k_in, k_out, v_in, v_out, (uint64_t)Z, 0, 32 + qbits, c->stream));
 		k_z_heads<<<(unsigned)((Z + 255) / 256), 256, 0, c->stream>>>(k_out, v_out, Z, (uint32_t)c->par.zcut, d_flag, d_run, d_zs); c->launches++;
