@@ -479,7 +479,7 @@ typedef struct {
 	struct { u8 *base; size_t cap, used, want; } pin[WZ_MAX_CTX];
 	pthread_mutex_t dev_mu[WZ_MAX_CTX];  /* one device call at a time per context */
 	pthread_mutex_t stat_mu;
-	u64 n_waves, n_wave_tasks; int wave_margin, wave_growth;
+	u64 n_waves, n_wave_tasks; int wave_margin, wave_growth, ramp;
 } wz_t;
 
 static double now_s(void){ struct timeval tv; gettimeofday(&tv, NULL); return tv.tv_sec + 1e-6 * tv.tv_usec; }
@@ -969,7 +969,7 @@ static void run_overlap(wz_t *z){
 		/* software pipeline: up to `depth` batches are in flight on their own device contexts (one worker thread each)
 		 * while the host replays the oldest one.  A batch is built from the state as of its build time, i.e. batch k+depth
 		 * from the state at the end of batch k-1, which only makes the speculation set larger (results are pure). */
-		batch_t *q[WZ_MAX_CTX]; int qh = 0, qn = 0, ci; double t0, t1;
+		batch_t *q[WZ_MAX_CTX]; int qh = 0, qn = 0, ci; double t0, t1; unsigned n_built = 0;
 		memset(z->ctx_busy, 0, sizeof(z->ctx_busy));
 		j = beg;
 		while(1){
@@ -979,7 +979,16 @@ static void run_overlap(wz_t *z){
 				for(ci=0;ci<z->n_ctx;ci++) if(!z->ctx_busy[ci]) break;
 				if(ci == z->n_ctx){ fprintf(stderr, "wtzmo(b200): internal error: no free device context\n"); exit(4); }
 				nxt->ci = ci; nxt->slot = 0;
-				for(;j<end&&nxt->reads.n<(size_t)z->batch_reads&&est_pairs<(size_t)z->batch_pairs;j++){
+				/* batch size: full batches in the steady state, smaller ones while the pipeline fills (the first replay can start sooner) and
+				 * drains (the last reads are spread over all contexts instead of leaving the GPU to one of them) */
+				size_t target = (size_t)z->batch_reads;
+				if(z->ramp){
+					size_t left = (size_t)(end - j) / (size_t)par->n_job + 1, up = (size_t)z->ramp << (n_built < 8? n_built : 8);
+					if(up < target) target = up;
+					if(left < target * (size_t)z->depth){ size_t t2 = left / (size_t)z->depth; if(t2 < 48) t2 = 48; if(t2 < target) target = t2; }
+				}
+				n_built ++;
+				for(;j<end&&nxt->reads.n<target&&est_pairs<(size_t)z->batch_pairs;j++){
 					bread_t r; memset(&r, 0, sizeof(r));
 					if((j % par->n_job) != (u32)par->i_job) continue;
 					if(z->masked[j]) continue;
@@ -1208,6 +1217,7 @@ wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	z->call_pairs = (env = getenv("ZMO_CALL_PAIRS"))? atoi(env) : 0;     /* test hook: pairs per device call (0 = the library's limits) */
 	z->wave_margin = (env = getenv("ZMO_WAVE0"))? atoi(env) : 8;       /* seeds per read in the first DP wave (doubles per wave); < 0: align every seed up front */
 	z->wave_growth = (env = getenv("ZMO_WAVE_GROWTH"))? atoi(env) : 4; if(z->wave_growth < 2) z->wave_growth = 2;
+	z->ramp = (env = getenv("ZMO_RAMP"))? atoi(env) : 0;      /* first batch size of the pipeline ramp (doubles per batch up to ZMO_BATCH_READS); 0 = off */
 	{ int q; for(q=0;q<WZ_MAX_CTX;q++) pthread_mutex_init(&z->dev_mu[q], NULL); pthread_mutex_init(&z->stat_mu, NULL); }
 	if(z->batch_reads < 1) z->batch_reads = 1;
 	memset(&zp, 0, sizeof(zp));
@@ -1322,7 +1332,7 @@ wz_session_t* wz_fork(const wz_session_t *S0, int device, int *rc_out){
 	*rc_out = 0;
 	z->rs = z0->rs; z->par = z0->par;      /* reads: shared pointers, never written after wz_open */
 	z->batch_reads = z0->batch_reads; z->batch_pairs = z0->batch_pairs; z->depth = z0->depth; z->call_pairs = z0->call_pairs;
-	z->wave_margin = z0->wave_margin; z->wave_growth = z0->wave_growth;
+	z->wave_margin = z0->wave_margin; z->wave_growth = z0->wave_growth; z->ramp = z0->ramp;
 	for(q=0;q<WZ_MAX_CTX;q++) pthread_mutex_init(&z->dev_mu[q], NULL);
 	pthread_mutex_init(&z->stat_mu, NULL);
 	z->masked = calloc(n + 1, 1); z->rdcovs = calloc(n + 1, sizeof(u32)); u64set_init(&z->closed);

@@ -36,6 +36,8 @@ extern "C" int zmo_index_build(zmo_ctx *c, uint32_t beg, uint32_t end, uint32_t 
 	CUDA_TRY(cudaSetDevice(c->device));
 	StageTimer tm(c, ST_INDEX);
 	const uint32_t nr = end - beg; const int bs = 64; DevReads R = dev_reads(c);
+	DevBuf *const tmpbuf[9] = { &c->s0, &c->s1, &c->s2, &c->s3, &c->s4, &c->s5, &c->s6, &c->s7, &c->cubtmp }; size_t cap0[9];
+	for(int k = 0; k < 9; k++) cap0[k] = tmpbuf[k]->cap;
 	if(c->s0.reserve(((size_t)nr + 1) * 8) || c->s1.reserve(((size_t)nr + 1) * 8)) return ZMO_ERR_CUDA;
 	unsigned long long *d_cnt = c->s0.as<unsigned long long>(), *d_off = c->s1.as<unsigned long long>();
 	k_idx_count<<<(nr + bs - 1) / bs, bs, 0, c->stream>>>(R, beg, end, c->par.ksize, c->par.hk, (uint32_t)c->par.ksave, d_cnt); c->launches++;
@@ -97,8 +99,9 @@ extern "C" int zmo_index_build(zmo_ctx *c, uint32_t beg, uint32_t end, uint32_t 
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	c->st->n_ent = ne; c->st->n_post = np; c->st->have_index = true;
 	/* the sort buffers of a large partition (cfg4: 120 GB for 2.3 G sampled k-mers) are not needed by the batches: give them back, the
-	 * per-batch stages re-grow what they use (a few GB); small builds keep theirs so that a rebuilt index costs no allocation */
-	{ DevBuf *tmp[] = { &c->s0, &c->s1, &c->s2, &c->s3, &c->s4, &c->s5, &c->s6, &c->s7, &c->cubtmp }; for(DevBuf *b : tmp) if(b->cap > (2ull << 30)) b->release(); }
+	 * per-batch stages re-grow what they use (a few GB); buffers that were already that large (the batches' own scratch) and small builds
+	 * keep theirs, so that rebuilding the index in a warm session costs no allocation */
+	for(int k = 0; k < 9; k++) if(tmpbuf[k]->cap > cap0[k] && tmpbuf[k]->cap > (2ull << 30)) tmpbuf[k]->release();      /* only what THIS build grew */
 	if(stats){ stats->n_kmers = ne; stats->n_postings = np; stats->n_filtered_high = st2[0]; stats->n_indexed = st2[1]; stats->kcut = K; stats->kavg = kavg; }
 	return 0;
 }

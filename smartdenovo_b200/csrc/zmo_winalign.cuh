@@ -38,6 +38,33 @@ __device__ __forceinline__ void cig_cat(uint32_t *c, uint32_t &n, const uint32_t
 	else for(; i < len; i++) c[n++] = src[i];
 }
 
+/* run-length alignment of one anchor pair (hz_align_hzmo, hzm_aln.h:278-314): equal base runs -> M, length difference -> I or D.  Up to cap
+ * ops go to ops[] (cap + 1 slots; the reference's CIGAR list has no limit, the pipeline keeps 94 ops, far beyond any z-mer span).
+ * res = {score, aln, mat, ins, del, flags (1 = run bases differ, 2 = more than cap ops), number of ops} */
+#ifdef __CUDACC__
+#define ZMO_NOINLINE __noinline__
+#else
+#define ZMO_NOINLINE __attribute__((noinline))
+#endif
+__device__ ZMO_NOINLINE void anchor_runlen(const SeqView a, uint32_t la, const SeqView b, uint32_t lb, const DPPar P, uint32_t *ops, uint32_t cap, int *res){
+	uint32_t sa = 0, sb = 0, n2 = 0; int y_score = 0, y_aln = 0, y_mat = 0, y_ins = 0, y_del = 0, flags = 0;
+	while(sa < la || sb < lb){
+		const uint32_t ca = sa < la? sv_base(a, (int)sa) : 4u, cb = sb < lb? sv_base(b, (int)sb) : 5u;
+		if(ca != cb){ flags |= 1; break; }
+		uint32_t ea = sa + 1; while(ea < la && sv_base(a, (int)ea) == ca) ea++;
+		uint32_t eb = sb + 1; while(eb < lb && sv_base(b, (int)eb) == cb) eb++;
+		const uint32_t na = ea - sa, nbb = eb - sb;
+		if(n2 >= cap) flags |= 2;
+		if(na < nbb){ y_aln += nbb; y_mat += na; y_ins += nbb - na; y_score += na * P.M + P.I + (int)(nbb - na) * P.E; if(n2 < cap){ cig_put(ops, n2, 0, na); cig_put(ops, n2, 1, nbb - na); } }
+		else if(na == nbb){ y_aln += na; y_mat += na; y_score += na * P.M; if(n2 < cap) cig_put(ops, n2, 0, na); }
+		else { y_aln += na; y_mat += nbb; y_del += na - nbb; y_score += nbb * P.M + P.D + (int)(na - nbb) * P.E; if(n2 < cap){ cig_put(ops, n2, 0, nbb); cig_put(ops, n2, 2, na - nbb); } }
+		sa = ea; sb = eb;
+	}
+	res[0] = y_score; res[1] = y_aln; res[2] = y_mat; res[3] = y_ins; res[4] = y_del; res[5] = flags; res[6] = (int)n2;
+}
+#define WA_ANC_OPS 8        /* ops per anchor kept in the per-warp anchor cache (an anchor with more is redone by lane 0) */
+#define WA_ANC_INTS 16      /* ints per cache entry: 7 results + WA_ANC_OPS + 1 ops */
+
 /* warp-per-window executor */
 __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *items, uint32_t nitems, const AlnTask *tasks, const zmo_pair_t *pairs,
 		const DevWin *wins, const DevZPair *anchors, DevReads R, AlnPar A, uint32_t *arena, unsigned long long slab_words, int max_rows,
@@ -59,6 +86,9 @@ __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *ite
 		const WItem I = items[it]; const AlnTask T = tasks[I.task]; const zmo_pair_t pr = pairs[T.pair_idx]; const DevWin W = wins[I.win];
 		uint32_t *cig = cig_arena + item_cig_off[it]; uint32_t ncig = 0;
 		int x_score = 0, x_tb = 0, x_te = 0, x_qb = 0, x_qe = 0, x_aln = 0, x_mat = 0, x_mis = 0, x_ins = 0, x_del = 0;
+		/* anchor cache: the run-length alignments of the next 32 anchors of the window, one per lane, in the (otherwise idle) H/E rows of the
+		 * shared-memory fallback sweep; the anchors of a window are known up front, only WHICH of them are used depends on the bridges */
+		uint32_t cbase = 0; bool cvalid = false; int *const acache = s_h[warp];
 		for(uint32_t ai = W.anc0; ai < W.anc1; ai++){
 			const DevZPair p = anchors[ai];
 			if(x_aln == 0){ x_tb = x_te = (int)p.off1; x_qb = x_qe = (int)p.off2; }
@@ -91,7 +121,7 @@ __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *ite
 				else if(d.ncol <= RegCap<32, 2>::ncol) reg_extend<32, 2, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, tmpc, ccap, o, ctr + ctr_cells, lane);
 				else if(d.ncol <= RegCap<32, 4>::ncol) reg_extend<32, 4, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, tmpc, ccap, o, ctr + ctr_cells, lane);
 				else if(d.ncol <= RegCap<32, WA_C>::ncol) reg_extend<32, WA_C, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, tmpc, ccap, o, ctr + ctr_cells, lane);
-				else band_extend<32, WA_C, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, zb, tmpc, ccap, o, ctr + ctr_cells, lane);
+				else { band_extend<32, WA_C, 0>(S2, qpk, qlen, tpk, tlen, init, d, P, z, zb, tmpc, ccap, o, ctr + ctr_cells, lane); cvalid = false; }      /* may have used the rows the anchor cache lives in */
 			}
 			x_score = o.score;
 			x_aln += o.mat + o.mis + o.ins + o.del; x_mat += o.mat; x_mis += o.mis; x_ins += o.ins; x_del += o.del;
@@ -102,6 +132,17 @@ __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *ite
 			if(x_te < (int)p.off1){ padD = p.off1 - x_te; x_del += padD; x_aln += padD; x_te = p.off1; }
 			if(x_qe < (int)p.off2){ padI = p.off2 - x_qe; x_ins += padI; x_aln += padI; x_qe = p.off2; }
 			int ok = 1;
+			if(!cvalid || ai - cbase >= 32u){
+				/* refill: lane l aligns anchor ai + l */
+				__syncwarp();
+				cbase = ai; cvalid = true;
+				const uint32_t aj = ai + (uint32_t)lane;
+				if(aj < W.anc1){
+					const DevZPair pj = anchors[aj];
+					anchor_runlen(view_pb1(R, pr.qid, (int)pj.off1, 1), pj.len1, view_pb2(R, pr.cid, T.dir, (int)pj.off2, 1), pj.len2, P, (uint32_t*)(acache + lane * WA_ANC_INTS + 7), WA_ANC_OPS, acache + lane * WA_ANC_INTS);
+				}
+				__syncwarp();
+			}
 			if(lane == 0){
 				/* block = reverse(walk-order ops) ++ D pad ++ I pad with run merging inside the block */
 				const uint32_t base = ncig; uint32_t nb = ncig;   /* build the block in place after position base, merging only within the block */
@@ -118,30 +159,16 @@ __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *ite
 					} else nb = base + bn;
 				}
 				ncig = nb;
-				/* run-length alignment of the anchor itself (hzm_aln.h:278-314) */
-				const SeqView a = view_pb1(R, pr.qid, (int)p.off1, 1), b = view_pb2(R, pr.cid, T.dir, (int)p.off2, 1);
-				const uint32_t la = p.len1, lb = p.len2; uint32_t sa = 0, sb = 0;
-				int y_score = 0, y_aln = 0, y_mat = 0, y_ins = 0, y_del = 0;
-				uint32_t blk2[96]; uint32_t n2 = 0; bool bad = false;
-				#define ANC_A(k) sv_base(a, (int)(k))
-				#define ANC_B(k) sv_base(b, (int)(k))
-				while(sa < la || sb < lb){
-					const uint32_t ca = sa < la? ANC_A(sa) : 4u, cb = sb < lb? ANC_B(sb) : 5u;
-					if(ca != cb){ bad = true; break; }
-					uint32_t ea = sa + 1; while(ea < la && ANC_A(ea) == ca) ea++;
-					uint32_t eb = sb + 1; while(eb < lb && ANC_B(eb) == cb) eb++;
-					const uint32_t na = ea - sa, nbb = eb - sb;
-					if(na < nbb){ y_aln += nbb; y_mat += na; y_ins += nbb - na; y_score += na * P.M + P.I + (int)(nbb - na) * P.E; if(n2 < 94){ cig_put(blk2, n2, 0, na); cig_put(blk2, n2, 1, nbb - na); } }
-					else if(na == nbb){ y_aln += na; y_mat += na; y_score += na * P.M; if(n2 < 94) cig_put(blk2, n2, 0, na); }
-					else { y_aln += na; y_mat += nbb; y_del += na - nbb; y_score += nbb * P.M + P.D + (int)(na - nbb) * P.E; if(n2 < 94){ cig_put(blk2, n2, 0, nbb); cig_put(blk2, n2, 2, na - nbb); } }
-					sa = ea; sb = eb;
+				/* run-length alignment of the anchor itself (hzm_aln.h:278-314): from the cache, or (more than WA_ANC_OPS ops) redone here */
+				const int *e = acache + (ai - cbase) * WA_ANC_INTS; int big[8]; uint32_t blk2[96]; const uint32_t *ops2 = (const uint32_t*)(e + 7);
+				if(e[5] & 2){
+					anchor_runlen(view_pb1(R, pr.qid, (int)p.off1, 1), p.len1, view_pb2(R, pr.cid, T.dir, (int)p.off2, 1), p.len2, P, blk2, 94u, big);
+					e = big; ops2 = blk2;
 				}
-				#undef ANC_A
-				#undef ANC_B
-				if(bad || y_aln == 0) ok = 0;
+				if((e[5] & 1) || e[1] == 0) ok = 0;
 				else {
-					s_misc[warp][9] = y_score; s_misc[warp][10] = y_aln; s_misc[warp][11] = y_mat; s_misc[warp][12] = y_ins; s_misc[warp][13] = y_del;
-					cig_cat(cig, ncig, blk2, n2, false);
+					s_misc[warp][9] = e[0]; s_misc[warp][10] = e[1]; s_misc[warp][11] = e[2]; s_misc[warp][12] = e[3]; s_misc[warp][13] = e[4];
+					cig_cat(cig, ncig, ops2, (uint32_t)e[6], false);
 				}
 			}
 			ok = __shfl_sync(0xffffffffu, ok, 0);
