@@ -442,6 +442,8 @@ def main():
             "parity_checked": bool(par_all), "parity": dict(par, ranks_checked=world),
             "stage_ms_per_step": stage_ms, "stage_rooflines": stage_roofs,
             "last_step_host_ms": {"device_calls": 1e3 * st1[3], "replay_format": 1e3 * st1[4]},
+            # where a step's wall goes: seconds since the start of the last job; the GPU is under-used before `first_replay` and after `last_batch_built`
+            "last_step_timeline_s": {"first_batch_built": st1[35], "first_replay": st1[36], "last_batch_built": st1[37], "last_compute_joined": st1[38], "end": st1[39]},
             "records_per_step": r_val["rec"] / args.steps, "aligned_bp_per_step": r_val["bp"] / args.steps,
             "last_step_work": {"batches": st1[5], "pairs_seeded": st1[6], "pairs_aligned": st1[7], "alignments_consumed": st1[8], "demand_waves": st1[29], "demand_wave_tasks": st1[30],
                                # speculation of the batch pipeline: reads put into batches, reads masked by the time of their turn, candidates of those reads (seeded for nothing)

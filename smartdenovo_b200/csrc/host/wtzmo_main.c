@@ -472,6 +472,7 @@ typedef struct {
 	u64 n_records, aln_cols, n_tasks, n_tasks_used, n_pairs_seeded, n_batches, n_reads_batched, n_reads_late_masked, n_pairs_late_masked;
 	FILE *out; char *obuf; size_t obuf_n, obuf_cap;
 	double t_dev, t_replay, t_write;
+	double tl[6];      /* timeline of the last job, seconds since its start: index done, first batch built, first replay starts, last batch built, last compute joined, end */
 	int batch_reads, batch_pairs;
 	/* page-locked result buffers reused across batches */
 	/* one page-locked arena per device context: the result buffers of a batch's DP waves are carved from it (bump allocation, reset when the next
@@ -479,7 +480,7 @@ typedef struct {
 	struct { u8 *base; size_t cap, used, want; } pin[WZ_MAX_CTX];
 	pthread_mutex_t dev_mu[WZ_MAX_CTX];  /* one device call at a time per context */
 	pthread_mutex_t stat_mu;
-	u64 n_waves, n_wave_tasks; int wave_margin, wave_growth, ramp;
+	u64 n_waves, n_wave_tasks; int wave_margin, wave_growth, ramp, drain_div, drain_min;
 } wz_t;
 
 static double now_s(void){ struct timeval tv; gettimeofday(&tv, NULL); return tv.tv_sec + 1e-6 * tv.tv_usec; }
@@ -943,6 +944,8 @@ static void run_overlap(wz_t *z){
 	if(par->n_idx > 1) z->rdhits = calloc(rs->n_rd + rs->n_qr, sizeof(u64v));
 	z->kcut = par->kcut;
 	if(rs->n_qr == 0){ beg = 0; end = rs->n_rd; } else { beg = rs->n_rd; end = beg + rs->n_qr; }
+	const double tl0 = now_s(); int tl_first = 1;
+	memset(z->tl, 0, sizeof(z->tl));
 	for(i_idx=0;i_idx<(u32)par->n_idx;i_idx++){
 		double t0 = now_s();
 		pbbeg = pbend; pbend = pbbeg + (rs->n_rd + par->n_idx - 1) / par->n_idx;
@@ -971,7 +974,7 @@ static void run_overlap(wz_t *z){
 		 * from the state at the end of batch k-1, which only makes the speculation set larger (results are pure). */
 		batch_t *q[WZ_MAX_CTX]; int qh = 0, qn = 0, ci; double t0, t1; unsigned n_built = 0;
 		memset(z->ctx_busy, 0, sizeof(z->ctx_busy));
-		j = beg;
+		j = beg; z->tl[0] = now_s() - tl0;
 		while(1){
 			size_t i; batch_t *cur;
 			while(qn < z->depth && j < end){
@@ -985,7 +988,7 @@ static void run_overlap(wz_t *z){
 				if(z->ramp){
 					size_t left = (size_t)(end - j) / (size_t)par->n_job + 1, up = (size_t)z->ramp << (n_built < 8? n_built : 8);
 					if(up < target) target = up;
-					if(left < target * (size_t)z->depth){ size_t t2 = left / (size_t)z->depth; if(t2 < 48) t2 = 48; if(t2 < target) target = t2; }
+					{ size_t t2 = left / (size_t)z->drain_div; if(t2 < (size_t)z->drain_min) t2 = (size_t)z->drain_min; if(t2 < target) target = t2; }      /* geometric drain: every batch takes 1/drain_div of what is left */
 				}
 				n_built ++;
 				for(;j<end&&nxt->reads.n<target&&est_pairs<(size_t)z->batch_pairs;j++){
@@ -1025,11 +1028,15 @@ static void run_overlap(wz_t *z){
 				} else batch_compute(z, nxt);
 				z->t_dev += now_s() - t0;
 				q[(qh + qn) % WZ_MAX_CTX] = nxt; qn ++;
+				if(z->tl[1] == 0) z->tl[1] = now_s() - tl0;
+				z->tl[3] = now_s() - tl0;
 			}
 			if(qn == 0) break;
 			cur = q[qh]; qh = (qh + 1) % WZ_MAX_CTX; qn --;
 			if(cur->have_thread){ double tj = now_s(); pthread_join(cur->th, NULL); z->t_dev += now_s() - tj; }
 			t1 = now_s();
+			if(tl_first){ z->tl[2] = t1 - tl0; tl_first = 0; }
+			z->tl[4] = t1 - tl0;
 			z->n_reads_batched += cur->reads.n;
 			for(i=0;i<cur->reads.n;i++){
 				bread_t *br = &cur->reads.a[i];
@@ -1045,6 +1052,7 @@ static void run_overlap(wz_t *z){
 	}
 	flush_read(z, &ro, 0);
 	ob_flush(z);
+	z->tl[5] = now_s() - tl0;
 	vec_free(ro.hits); vec_free(ro.masks); vec_free(ro.closed); vec_free(ro.seeds);
 }
 
@@ -1217,7 +1225,9 @@ wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	z->call_pairs = (env = getenv("ZMO_CALL_PAIRS"))? atoi(env) : 0;     /* test hook: pairs per device call (0 = the library's limits) */
 	z->wave_margin = (env = getenv("ZMO_WAVE0"))? atoi(env) : 8;       /* seeds per read in the first DP wave (doubles per wave); < 0: align every seed up front */
 	z->wave_growth = (env = getenv("ZMO_WAVE_GROWTH"))? atoi(env) : 4; if(z->wave_growth < 2) z->wave_growth = 2;
-	z->ramp = (env = getenv("ZMO_RAMP"))? atoi(env) : 0;      /* first batch size of the pipeline ramp (doubles per batch up to ZMO_BATCH_READS); 0 = off */
+	z->drain_div = (env = getenv("ZMO_DRAIN_DIV"))? atoi(env) : z->depth; if(z->drain_div < 1) z->drain_div = 1;
+	z->drain_min = (env = getenv("ZMO_DRAIN_MIN"))? atoi(env) : 48; if(z->drain_min < 1) z->drain_min = 1;
+	z->ramp = (env = getenv("ZMO_RAMP"))? atoi(env) : 96;     /* first batch size of the pipeline ramp (doubles per batch up to ZMO_BATCH_READS); 0 = off.  cfg2: 1,025 -> 938 ms per shard */
 	{ int q; for(q=0;q<WZ_MAX_CTX;q++) pthread_mutex_init(&z->dev_mu[q], NULL); pthread_mutex_init(&z->stat_mu, NULL); }
 	if(z->batch_reads < 1) z->batch_reads = 1;
 	memset(&zp, 0, sizeof(zp));
@@ -1332,7 +1342,7 @@ wz_session_t* wz_fork(const wz_session_t *S0, int device, int *rc_out){
 	*rc_out = 0;
 	z->rs = z0->rs; z->par = z0->par;      /* reads: shared pointers, never written after wz_open */
 	z->batch_reads = z0->batch_reads; z->batch_pairs = z0->batch_pairs; z->depth = z0->depth; z->call_pairs = z0->call_pairs;
-	z->wave_margin = z0->wave_margin; z->wave_growth = z0->wave_growth; z->ramp = z0->ramp;
+	z->wave_margin = z0->wave_margin; z->wave_growth = z0->wave_growth; z->ramp = z0->ramp; z->drain_div = z0->drain_div; z->drain_min = z0->drain_min;
 	for(q=0;q<WZ_MAX_CTX;q++) pthread_mutex_init(&z->dev_mu[q], NULL);
 	pthread_mutex_init(&z->stat_mu, NULL);
 	z->masked = calloc(n + 1, 1); z->rdcovs = calloc(n + 1, sizeof(u32)); u64set_init(&z->closed);
@@ -1361,7 +1371,8 @@ void wz_stats(wz_session_t *S, double *out){
 	for(i=0;i<7;i++) out[18 + i] = (double)ct[i];
 	out[25] = (double)(z->rs.n_rd + z->rs.n_qr); out[26] = (double)z->rs.nbases; out[27] = S->last_upload_s; out[28] = (double)S->upload_bytes;
 	out[29] = (double)z->n_waves; out[30] = (double)z->n_wave_tasks; out[31] = ms[8];
-	out[32] = (double)z->n_reads_batched; out[33] = (double)z->n_reads_late_masked; out[34] = (double)z->n_pairs_late_masked;      /* speculation: reads batched / masked by the time of their turn / their candidates */
+	out[32] = (double)z->n_reads_batched; out[33] = (double)z->n_reads_late_masked; out[34] = (double)z->n_pairs_late_masked;
+	{ int k; for(k=0;k<5;k++) out[35 + k] = z->tl[k + (k >= 0)]; }      /* timeline [1..5] of the last job (s): first batch built, first replay, last batch built, last compute joined, end */      /* speculation: reads batched / masked by the time of their turn / their candidates */
 }
 
 void wz_close(wz_session_t *S){ if(S){ int q; for(q=0;q<WZ_MAX_CTX;q++) if(S->z.pin[q].base) zmo_host_free(S->z.pin[q].base); for(q=S->z.n_ctx-1;q>=0;q--) if(S->z.ctxs[q]) zmo_ctx_destroy(S->z.ctxs[q]); free(S); } }
