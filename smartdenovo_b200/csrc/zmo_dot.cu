@@ -27,15 +27,8 @@ extern "C" int zmo_pair_dotmatrix(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t 
 	{
 		unsigned long long *ctr = c->d_ctr.as<unsigned long long>();
 		CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORK, 0, 8, c->stream));
-		/* ZMO_DOT_LANE=1: one lane per pair (k_p_dot_lane) instead of one warp per pair (k_p_dot); same results */
-		static const bool dot_lane = getenv("ZMO_DOT_LANE") && atoi(getenv("ZMO_DOT_LANE")) > 0;
-		if(dot_lane){
-			const int grid = (int)std::min<uint64_t>((np + DOTL_NT - 1) / DOTL_NT, (uint64_t)c->n_sm * 16);
-			k_p_dot_lane<<<grid, DOTL_NT, 0, c->stream>>>(W.cache_off, d_pairs, np, W.cache, W.tie, c->s6.as<uint8_t>(), per, dev_reads(c), par, (uint32_t)c->par.zsize, (uint32_t)c->par.ztot, d_out, ctr + CTR_WORK);
-		} else {
-			const int grid = (int)std::min<uint64_t>((np + DOT_WARPS - 1) / DOT_WARPS, (uint64_t)c->n_sm * 4);
-			k_p_dot<<<grid, 32 * DOT_WARPS, 0, c->stream>>>(W.cache_off, d_pairs, np, W.cache, W.tie, c->s6.as<uint8_t>(), per, dev_reads(c), par, (uint32_t)c->par.zsize, (uint32_t)c->par.ztot, d_out, ctr + CTR_WORK);
-		}
+		const int grid = (int)std::min<uint64_t>((np + DOT_WARPS - 1) / DOT_WARPS, (uint64_t)c->n_sm * 4);
+		k_p_dot<<<grid, 32 * DOT_WARPS, 0, c->stream>>>(W.cache_off, d_pairs, np, W.cache, W.tie, c->s6.as<uint8_t>(), per, dev_reads(c), par, (uint32_t)c->par.zsize, (uint32_t)c->par.ztot, d_out, ctr + CTR_WORK);
 		c->launches++;
 	}
 	CUDA_TRY(cudaGetLastError());

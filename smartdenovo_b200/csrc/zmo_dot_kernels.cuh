@@ -73,20 +73,3 @@ __global__ void __launch_bounds__(32 * DOT_WARPS) k_p_dot(const unsigned long lo
 	}
 }
 
-/* One LANE per pair (persistent lanes pulling pairs from the work counter): every lane runs the serial logic of zmo_dot_core.cuh on its own pair with
- * its own global scratch, the exact sort_array emulations in place.  32 pairs share the instruction stream of a warp; they diverge (the logic is
- * data dependent) and their memory accesses do not coalesce, but a warp of k_p_dot issues for ONE lane (1.01 threads per instruction, ncu). */
-#define DOTL_NT 64
-__global__ void __launch_bounds__(DOTL_NT) k_p_dot_lane(const unsigned long long *cache_off, const zmo_pair_t *pairs, uint32_t np, DevZPair *cache, const uint8_t *tie, uint8_t *scratch, size_t per, DevReads R, DotPar par, uint32_t zsize, uint32_t ztot, zmo_dotres_t *out, unsigned long long *work){
-	while(1){
-		const uint32_t p = (uint32_t)atomicAdd(work, 1ULL);
-		if(p >= np) break;
-		const unsigned long long c0 = cache_off[p]; const uint32_t n = (uint32_t)(cache_off[p + 1] - c0);
-		zmo_dotres_t o; o.n_zpair = n; o.score = 0; o.qb = o.tb = 0x7FFFFFFF; o.qe = o.te = 0; o.strand = 0;
-		if((unsigned long long)n * zsize >= ztot){
-			const DotRes r = zmo_dot_pair(cache + c0, n, (int)R.len[pairs[p].qid], (int)R.len[pairs[p].cid], par, scratch + c0 * per + (size_t)(2 * per + 64) * p, tie[p]? 2 : 1);
-			o.score = r.score; o.qb = r.qb; o.qe = r.qe; o.tb = r.tb; o.te = r.te; o.strand = r.strand;
-		}
-		out[p] = o;
-	}
-}

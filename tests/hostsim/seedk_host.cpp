@@ -121,8 +121,6 @@ extern "C" int simk_pair_windows(const uint8_t *pb1, int alen, const uint8_t *pb
  * orc_pair_dotmatrix.  The match list is delivered the way the device front end does in this mode: sorted by
  * (off1 - off2, off1), runs of equal keys in adversarial order and flagged as ties.  copies / force_tie as above.
  */
-static int g_dot_lane = 0;
-extern "C" void simk_set_dot_lane(int on){ g_dot_lane = on; }      /* 1: k_p_dot_lane (one lane per pair) instead of k_p_dot */
 extern "C" int simk_pair_dotmatrix(const uint8_t *pb1, int alen, const uint8_t *pb2, int blen, int zsize, int hz, int zcut, int kvar,
 		int xvar, int yvar, int min_block_len, int max_overhang, float dev_pen, float gap_pen, int ztot, int copies, int force_tie, int *out){
 	std::vector<DevZPair> srt = match_list(pb1, alen, pb2, blen, zsize, hz, zcut, kvar);
@@ -149,8 +147,7 @@ extern "C" int simk_pair_dotmatrix(const uint8_t *pb1, int alen, const uint8_t *
 	DotPar par; par.xvar = xvar; par.yvar = yvar; par.min_block_len = min_block_len; par.max_overhang = max_overhang; par.deviation_penalty = dev_pen; par.gap_penalty = gap_pen;
 	const unsigned long long *dco = coff.data(); const zmo_pair_t *dp = pairs.data(); DevZPair *dc = cache.data(); const uint8_t *dt = tieflag.data();
 	uint8_t *ds = scratch.data(); zmo_dotres_t *dr = res.data(); unsigned long long *dw = &work;
-	if(g_dot_lane) emu::launch(np > 40? 2u : 1u, DOTL_NT, [=](){ k_p_dot_lane(dco, dp, np, dc, dt, ds, per, R, par, (uint32_t)zsize, (uint32_t)ztot, dr, dw); });
-	else emu::launch(np > 1? 2u : 1u, 32 * DOT_WARPS, [=](){ k_p_dot(dco, dp, np, dc, dt, ds, per, R, par, (uint32_t)zsize, (uint32_t)ztot, dr, dw); });
+	emu::launch(np > 1? 2u : 1u, 32 * DOT_WARPS, [=](){ k_p_dot(dco, dp, np, dc, dt, ds, per, R, par, (uint32_t)zsize, (uint32_t)ztot, dr, dw); });
 	for(uint32_t p = 1; p < np; p++) if(memcmp(&res[p], &res[0], sizeof(zmo_dotres_t))) return -2;
 	out[0] = res[0].score; out[1] = res[0].qb; out[2] = res[0].qe; out[3] = res[0].tb; out[4] = res[0].te; out[5] = res[0].strand;
 	return (int)res[0].n_zpair;

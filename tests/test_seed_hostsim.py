@@ -113,13 +113,10 @@ def run_dot_kernel(lib, a, b, copies=1, force_tie=0, ztot=0, zcut=16, xvar=128, 
     return n, list(out)
 
 
-@pytest.mark.parametrize("lane", [0, 1])
-def test_dot_kernel_matches_oracle(seedk_sim, oracle_lib, lane):
+def test_dot_kernel_matches_oracle(seedk_sim, oracle_lib):
     """k_p_dot (zmo_dot_kernels.cuh): lane 0 runs the serial dot-matrix logic of zmo_dot_core.cuh, its sort_array emulations are staged
-    through shared memory by the helper lanes (mailbox + paired __syncwarp()s); input sorted by diagonal like the device front end.
-    lane = 1: k_p_dot_lane, one lane per pair (64-lane CTAs pulling pairs from the work counter)"""
+    through shared memory by the helper lanes (mailbox + paired __syncwarp()s); input sorted by diagonal like the device front end"""
     from test_seed_core import run_dot
-    seedk_sim.simk_set_dot_lane(lane)
     hits = 0
     for i, (a, b) in enumerate(pairs(600, 30)):
         exp = run_dot(oracle_lib, "orc_pair_dotmatrix", a, b)
@@ -137,7 +134,6 @@ def test_dot_kernel_matches_oracle(seedk_sim, oracle_lib, lane):
     a, b = next(pairs(602, 1))
     n, out = run_dot_kernel(seedk_sim, a, b[:300], ztot=10 ** 6)
     assert out[0] == 0 and out[5] == 0
-    seedk_sim.simk_set_dot_lane(0)
 
 
 def test_seeding_stage_batch(seedk_sim, oracle_lib):
