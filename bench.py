@@ -51,8 +51,13 @@ STAGES = ["index", "candidates", "pair_windows", "window_align", "gap_global", "
 # DRAM bytes (read + write) of ONE captured launch of a stage's dominant kernel, `ncu --set full`, keyed by the workload the capture was
 # taken on; absent = no capture of that kernel on that workload is committed.  alg_bytes = algorithmic bytes of the same launch.
 TRAFFIC = {
-    ("cfg2s", "window_align"): dict(kernel="k_window_align", dram_bytes=377.8e6, alg_bytes=0.85e9, source="profiles/r01_ncu_final.md"),
-    ("cfg2s", "dp_phase"): dict(kernel="k_ext_cta<128,13,1>", dram_bytes=233.6e6, alg_bytes=None, source="profiles/r01_ncu_final.md"),
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (one 384-read batch of the cfg2 `-P 40 -p 0` shard = the batch size of the bench)
+    ("cfg2", "pair_windows"): dict(kernel="k_p_seed", dram_bytes=2.109e9, launch="largest of the 5 batches of the shard", source="profiles/r02_ncu_final.md"),
+    ("cfg2", "window_align"): dict(kernel="k_window_align", dram_bytes=268.2e6, launch="first wave of the shard", source="profiles/r02_ncu_final.md"),
+    ("cfg2", "dp_phase"): dict(kernel="k_ext_cta<128,13,1>", dram_bytes=239.3e6, launch="first wave of the shard", source="profiles/r02_ncu_final.md"),
+    ("cfg3s", "dotmatrix"): dict(kernel="k_p_dot", dram_bytes=5.219e9, launch="first batch of the cfg3s `-P 16 -p 0` shard", source="profiles/r02_ncu_final.md"),
+    ("cfg2s", "window_align"): dict(kernel="k_window_align", dram_bytes=377.8e6, source="profiles/r01_ncu_final.md"),
+    ("cfg2s", "dp_phase"): dict(kernel="k_ext_cta<128,13,1>", dram_bytes=233.6e6, source="profiles/r01_ncu_final.md"),
 }
 
 
@@ -219,7 +224,7 @@ def stage_roofline(wl_name, st0, st1, steps, peak, peaks_found):
     # the end-extension + gap-fill executors run CONCURRENTLY (one stream per executor class): their cost is the wall time of that phase
     groups = {
         "dp_phase": (stage_ms["dp_phase_wall"], 0.5 * (cells["end_extend"] + cells["gap_global"]), cells["end_extend"] + cells["gap_global"], "k_ext_cta<64|128,7|13,1> + k_ext_warp<1> + k_glb_warp/k_glb_cta (concurrent)", "0.5 B x DP cells"),
-        "window_align": (stage_ms["window_align"], 0.5 * cells["window_align"], cells["window_align"], "window alignment (k_wa_lane / k_window_align)", "0.5 B x DP cells"),
+        "window_align": (stage_ms["window_align"], 0.5 * cells["window_align"], cells["window_align"], "k_window_align", "0.5 B x DP cells"),
         "pair_windows": (stage_ms["pair_windows"], 32.0 * matches, matches, "k_p_seed + k_hit + k_expand + radix sorts (z-mer seeding)", "2 x 16 B x z-mer matches"),
         "dotmatrix": (stage_ms["dotmatrix"], 32.0 * matches, matches, "k_p_dot + k_hit + k_expand + radix sorts (dot-matrix)", "2 x 16 B x z-mer matches"),
     }
@@ -230,7 +235,7 @@ def stage_roofline(wl_name, st0, st1, steps, peak, peaks_found):
     tr = TRAFFIC.get((wl_name, dom))
     roof = {"bound": "hbm", "stage": dom, "kernel": kern, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
             "traffic": tr["dram_bytes"] if tr else None,
-            "traffic_capture": tr if tr else "no ncu --set full capture of this stage's kernel on this workload is committed (profiles/ holds the captures that exist, taken on cfg2s)",
+            "traffic_capture": tr if tr else "no ncu --set full capture of this stage's kernel on this workload is committed (profiles/r02_ncu_final.md holds the captures that exist)",
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks_found else "fallback 6650 (of fallback)",
             "alg_bytes_model": model, "units_per_step": units / steps, "kernel_ms_per_step": ms / steps,
             "units_per_s": units / s if s > 0 else 0.0,
