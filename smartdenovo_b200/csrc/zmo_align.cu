@@ -14,6 +14,7 @@
 #include "zmo_jobs.cuh"
 #include "zmo_seed_core.cuh"
 #include "zmo_winalign.cuh"
+#include "zmo_winbridge.cuh"
 #include "zmo_stitch_kernels.cuh"
 #include "zmo_refine_kernels.cuh"
 
@@ -208,8 +209,8 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 	if(SL.np == 0) return zmo_set_err(ZMO_ERR_STATE, "zmo_pair_windows has not filled slot %d", slot);
 	CUDA_TRY(cudaSetDevice(c->device));
 	/* host: items and per-item cigar regions */
-	std::vector<AlnTask> ht(nt); std::vector<WItem> items; std::vector<unsigned long long> icig;
-	unsigned long long cig_words = 0; int max_rows = 16;
+	std::vector<AlnTask> ht(nt); std::vector<WItem> items; std::vector<unsigned long long> icig, istep;
+	unsigned long long cig_words = 0, nsteps64 = 0, wb_rows = 0, wb_cols = 0; int max_rows = 16;
 	for(uint32_t t = 0; t < nt; t++){
 		if(tasks[t].pair_idx >= SL.np || tasks[t].dir > 1) return zmo_set_err(ZMO_ERR_ARG, "task %u out of range", t);
 		const zmo_pairseed_t &ps = SL.h_seeds[tasks[t].pair_idx]; const uint32_t d = tasks[t].dir;
@@ -218,6 +219,7 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 			WItem it; it.task = t; it.win = ps.win_off[d] + k; items.push_back(it);
 			const int s0 = SL.h_wspan[3 * (size_t)it.win], s1 = SL.h_wspan[3 * (size_t)it.win + 1], na = SL.h_wspan[3 * (size_t)it.win + 2];
 			icig.push_back(cig_words); cig_words += (unsigned long long)(s0 + s1 + 16 + 2 * na);
+			istep.push_back(nsteps64); nsteps64 += (unsigned long long)na; wb_rows += (unsigned long long)(s1 + 16); wb_cols += (unsigned long long)(s0 + 16) + 8ull * (unsigned long long)na;
 			if(s1 + 8 > max_rows) max_rows = s1 + 8;
 			if(s0 + 8 > max_rows) max_rows = s0 + 8;
 		}
@@ -228,7 +230,13 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 	DevReads R = dev_reads(c);
 	unsigned long long *ctr = c->d_ctr.as<unsigned long long>();
 	/* window-align executors and their slabs */
-	const int wgrid = (int)std::min<uint64_t>((nitems + WA_WARPS - 1) / WA_WARPS + 1, (uint64_t)c->n_sm * 8);
+	static const bool wb_env = [](){ const char *e = getenv("ZMO_WA_BRIDGE"); return !(e && e[0] == '0'); }();      /* ZMO_WA_BRIDGE=0: every window through k_window_align (A/B runs) */
+	const bool use_wb = wb_env && c->par.w >= 1 && c->par.w <= WB_MAX_W && nitems > 0 && nsteps64 < 0xFFFFFFF0ull;
+	const int wb_ring = wb_cap(c->par.w), wb_rw = wb_row_words(c->par.w), wb_acap = 2 * (int)c->par.zsize + 2;      /* an anchor is a z-mer: zsize runs, at most M + I|D each */
+	/* scratch of the swept bridges, bounded from the window spans: rows of all bridges of a window <= its span on c, columns <= its span on q + w per bridge */
+	const unsigned long long wb_scr_cap = use_wb? wb_rows * (unsigned long long)(wb_rw + 5) + wb_cols + 8ull * nsteps64 + 1024 : 0;
+	/* with the bridge pipeline k_window_align only sees the windows that pipeline leaves out: a quarter of the executors (all of them are used if needed, just in more rounds) */
+	const int wgrid = (int)std::min<uint64_t>((nitems + WA_WARPS - 1) / WA_WARPS + 1, (uint64_t)c->n_sm * (use_wb? 2 : 8));
 	const int wcol = std::min(max_rows + c->par.w, 2 * c->par.w + 1);
 	unsigned long long slab = (unsigned long long)max_rows * band_row_words<32, WA_C>(wcol) + max_rows + (2ull * max_rows + 2ull * c->par.w + 16) + ((unsigned long long)max_rows >> 3) + (c->par.w >> 3) + 8;
 	if(2 * c->par.w + 3 > WA_CAP){ unsigned long long cap = 1; while(cap < (unsigned long long)(2 * c->par.w + 3)) cap <<= 1; slab += 3 * cap; }
@@ -249,14 +257,45 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 	c->counters[5] += (size_t)nt * sizeof(AlnTask) + (size_t)nitems * 16;
 	unsigned long long cig_cap_words = cig_words + (unsigned long long)nt * 4096 + (1ull << 20);
 	for(int attempt = 0; ; attempt++){
-		if(c->arena.reserve((slabs_total + 64) * 4) || c->s6.reserve(cig_cap_words * 4)) return ZMO_ERR_CUDA;
+		if(c->arena.reserve((std::max(slabs_total, wb_scr_cap) + 64) * 4) || c->s6.reserve(cig_cap_words * 4)) return ZMO_ERR_CUDA;
+		if(use_wb && (c->wb0.reserve((size_t)(nsteps64 + 1) * (sizeof(WBStep) + 4 * (size_t)(wb_acap + 1))) || c->wb1.reserve(((size_t)nitems + 1) * 8 + ((size_t)nsteps64 + 2) * 16 + 16 + (size_t)nsteps64 * 16 + (size_t)nitems * 5 + 64))) return ZMO_ERR_CUDA;
 		cig_cap_words = c->s6.cap / 4;
 		uint32_t *arena = c->arena.as<uint32_t>(), *cig_arena = c->s6.as<uint32_t>();
-		if(nitems){
+		if(nitems && use_wb){
+			/* bridge-level pipeline (zmo_winbridge.cuh); the windows it leaves out go through k_window_align below */
 			StageTimer tm(c, ST_WINALN);
+			const uint32_t nsteps = (uint32_t)nsteps64;
+			WBStep *d_steps = c->wb0.as<WBStep>(); uint32_t *d_aops = (uint32_t*)(d_steps + nsteps + 1);
+			unsigned long long *d_istep = c->wb1.as<unsigned long long>(), *d_scrw = d_istep + nitems + 1, *d_scro = d_scrw + nsteps + 1;
+			uint32_t *d_keys = (uint32_t*)(d_scro + nsteps + 2), *d_ord = d_keys + nsteps, *d_skeys = d_ord + nsteps, *d_sord = d_skeys + nsteps, *d_fb = d_sord + nsteps;
+			uint8_t *d_iseq = (uint8_t*)(d_fb + nitems);
+			CUDA_TRY(cudaMemcpyAsync(d_istep, istep.data(), (size_t)nitems * 8, cudaMemcpyHostToDevice, c->stream));
+			CUDA_TRY(cudaMemsetAsync(ctr + CTR_N4, 0, 16, c->stream));            /* CTR_N4 = windows left to k_window_align, CTR_N5 = scratch bound violated */
+			CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORK, 0, 8, c->stream));
+			CUDA_TRY(cudaMemsetAsync(d_scrw + nsteps, 0, 8, c->stream));
+			k_wb_prep<<<(unsigned)(((unsigned long long)nitems * 32 + 127) / 128), 128, 0, c->stream>>>(d_items, nitems, d_tasks, SL.pairs.as<zmo_pair_t>(), SL.wins.as<DevWin>(), SL.anchors.as<DevZPair>(), R, A,
+				d_istep, wb_rw, d_steps, d_aops, wb_acap, d_scrw, d_keys, d_ord, d_iseq, d_fb, ctr + CTR_N4); c->launches++;
+			if(nsteps){
+				CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_scrw, d_scro, (int)nsteps + 1, c->stream));
+				const uint32_t *sk = d_keys, *so = d_ord;
+				if(nsteps >= 2){ CUB_CALL(c, cub::DeviceRadixSort::SortPairsDescending(d_temp, temp_bytes, d_keys, d_skeys, d_ord, d_sord, (int)nsteps, 0, 32, c->stream)); sk = d_skeys; so = d_sord; }
+				const int sgrid = (int)std::min<uint64_t>(((uint64_t)nsteps + WB_NT - 1) / WB_NT, (uint64_t)c->n_sm * 8);
+				k_wb_sweep<<<sgrid, WB_NT, (size_t)wb_ring * 4 * WB_NT, c->stream>>>(d_steps, so, sk, nsteps, d_scro, wb_scr_cap, R.words, A.P, arena, wb_ring, wb_rw, ctr + CTR_WORK, ctr + CTR_N5); c->launches++;
+				k_wb_ends<<<(nitems + 63) / 64, 64, 0, c->stream>>>(nitems, d_items, SL.wins.as<DevWin>(), A, d_istep, d_iseq, d_steps, d_scro, arena, wb_rw, ctr + CTR_N5, ctr, CTR_CELLS_WIN); c->launches++;
+				k_wb_walk<<<(nsteps + 127) / 128, 128, 0, c->stream>>>(d_steps, nsteps, d_scro, R.words, A.P, arena, wb_rw, ctr + CTR_N5); c->launches++;
+			}
+			k_wb_stitch<<<(nitems + 63) / 64, 64, 0, c->stream>>>(d_items, nitems, SL.wins.as<DevWin>(), A, d_istep, d_iseq, d_steps, d_aops, wb_acap, d_scro, arena, wb_rw, ctr + CTR_N5, cig_arena, d_icig, d_regs); c->launches++;
 			CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORK, 0, 8, c->stream));
 			k_window_align<<<wgrid, 32 * WA_WARPS, 0, c->stream>>>(d_items, nitems, d_tasks, SL.pairs.as<zmo_pair_t>(), SL.wins.as<DevWin>(), SL.anchors.as<DevZPair>(), R, A,
-				arena, slab, max_rows, cig_arena, d_icig, d_regs, ctr, CTR_WORK, CTR_CELLS_WIN);
+				arena, slab, max_rows, cig_arena, d_icig, d_regs, ctr, CTR_WORK, CTR_CELLS_WIN, d_fb, ctr + CTR_N4);
+			c->launches++;
+			CUDA_TRY(cudaGetLastError());
+		} else if(nitems){
+			StageTimer tm(c, ST_WINALN);
+			CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORK, 0, 8, c->stream));
+			CUDA_TRY(cudaMemsetAsync(ctr + CTR_N4, 0, 16, c->stream));
+			k_window_align<<<wgrid, 32 * WA_WARPS, 0, c->stream>>>(d_items, nitems, d_tasks, SL.pairs.as<zmo_pair_t>(), SL.wins.as<DevWin>(), SL.anchors.as<DevZPair>(), R, A,
+				arena, slab, max_rows, cig_arena, d_icig, d_regs, ctr, CTR_WORK, CTR_CELLS_WIN, nullptr, nullptr);
 			c->launches++;
 			CUDA_TRY(cudaGetLastError());
 		}
@@ -272,6 +311,8 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 		unsigned long long h[CTR_TOTAL];
 		CUDA_TRY(cudaMemcpyAsync(h, ctr, CTR_TOTAL * 8, cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		if(use_wb && h[CTR_N5]) return zmo_set_err(ZMO_ERR_STATE, "window alignment: bridge scratch bound violated (%llu bridges)", h[CTR_N5]);
+		c->counters[7] += use_wb? h[CTR_N4] : 0;      /* windows that took the sequential path */
 		if(h[CTR_OVERFLOW]){
 			if(attempt >= 6) return zmo_set_err(ZMO_ERR_CAPACITY, "cigar arena overflow after %d attempts", attempt);
 			cig_cap_words = std::max(cig_cap_words * 2, h[CTR_CIG] + (1ull << 20));

@@ -67,7 +67,7 @@ extern "C" void zmo_ctx_destroy(zmo_ctx *c){
 	cudaSetDevice(c->device);
 	if(c->stream) cudaStreamSynchronize(c->stream);
 	if(!c->is_clone){ DevBuf *sb[] = { &c->own.rd_words, &c->own.rd_woff, &c->own.rd_len, &c->own.ix_mer, &c->own.ix_off, &c->own.ix_flt, &c->own.ix_post }; for(DevBuf *b : sb) b->release(); }
-	DevBuf *bufs[] = { &c->s0, &c->s1, &c->s2, &c->s3, &c->s4, &c->s5, &c->s6, &c->s7, &c->cubtmp, &c->arena, &c->d_ctr, &c->zfilt };
+	DevBuf *bufs[] = { &c->s0, &c->s1, &c->s2, &c->s3, &c->s4, &c->s5, &c->s6, &c->s7, &c->cubtmp, &c->arena, &c->d_ctr, &c->zfilt, &c->wb0, &c->wb1 };
 	for(DevBuf *b : bufs) b->release();
 	for(int s = 0; s < 2; s++){ c->slot[s].pairs.release(); c->slot[s].seeds.release(); c->slot[s].wins.release(); c->slot[s].anchors.release(); }
 	c->h0.release(); c->h1.release(); c->h2.release();

@@ -107,6 +107,7 @@ struct zmo_ctx {
 	/* scratch */
 	DevBuf s0, s1, s2, s3, s4, s5, s6, s7, cubtmp;
 	DevBuf zfilt;        /* per-query slot filter of the batch z-index (zmo_seed.cu) */
+	DevBuf wb0, wb1;     /* bridge-level window alignment (zmo_winbridge.cuh): step records; offsets / sort keys / lists */
 	DevBuf arena;        /* bump-allocated DP scratch (traceback, staged sequences) */
 	DevBuf d_ctr;        /* device counters / cursors (uint64[64]) */
 	PinBuf h0, h1, h2;

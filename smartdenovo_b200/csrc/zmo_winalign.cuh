@@ -68,7 +68,8 @@ __device__ ZMO_NOINLINE void anchor_runlen(const SeqView a, uint32_t la, const S
 /* warp-per-window executor */
 __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *items, uint32_t nitems, const AlnTask *tasks, const zmo_pair_t *pairs,
 		const DevWin *wins, const DevZPair *anchors, DevReads R, AlnPar A, uint32_t *arena, unsigned long long slab_words, int max_rows,
-		uint32_t *cig_arena, const unsigned long long *item_cig_off, DevReg *regs, unsigned long long *ctr, int ctr_work, int ctr_cells){
+		uint32_t *cig_arena, const unsigned long long *item_cig_off, DevReg *regs, unsigned long long *ctr, int ctr_work, int ctr_cells,
+		const uint32_t *sel, const unsigned long long *nsel){      /* sel != null: only the items sel[0 .. *nsel) (the windows k_wb_prep left to this kernel) */
 	__shared__ int s_h[WA_WARPS][3 * WA_CAP];
 	__shared__ uint32_t s_seq[WA_WARPS][WA_SEQW];
 	__shared__ int s_misc[WA_WARPS][16];
@@ -82,7 +83,8 @@ __global__ void __launch_bounds__(32 * WA_WARPS) k_window_align(const WItem *ite
 		uint32_t it = 0;
 		if(lane == 0) it = (uint32_t)atomicAdd(ctr + ctr_work, 1ULL);
 		it = __shfl_sync(0xffffffffu, it, 0);
-		if(it >= nitems) break;
+		if(sel){ if(it >= *nsel) break; it = sel[it]; }
+		else if(it >= nitems) break;
 		const WItem I = items[it]; const AlnTask T = tasks[I.task]; const zmo_pair_t pr = pairs[T.pair_idx]; const DevWin W = wins[I.win];
 		uint32_t *cig = cig_arena + item_cig_off[it]; uint32_t ncig = 0;
 		int x_score = 0, x_tb = 0, x_te = 0, x_qb = 0, x_qe = 0, x_aln = 0, x_mat = 0, x_mis = 0, x_ins = 0, x_del = 0;

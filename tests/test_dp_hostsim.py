@@ -231,6 +231,61 @@ def test_window_align_kernel(dp_sim, oracle_lib, w):
     assert n_win >= 8
 
 
+@pytest.mark.parametrize("w,sc,copies,acap", [(50, (2, -5, -3, -1, -50), 1, 22), (20, (2, -5, -3, -1, -50), 9, 22), (91, (2, -5, -3, -1, -50), 1, 22), (50, (1, -3, -2, -2, -10), 1, 22), (50, (2, -5, -3, -1, -20), 1, 22), (50, (2, -5, -3, -1, -50), 1, 6),
+                                                    (50, (2, -5, -3, -1, -50), -12, 22), (20, (2, -5, -3, -1, -50), -7, 22), (91, (2, -5, -3, -1, -50), -30, 22)])
+def test_window_align_bridge_pipeline(dp_sim, oracle_lib, w, sc, copies, acap):
+    """bridge-level window alignment (zmo_winbridge.cuh: k_wb_prep / k_wb_sweep / k_wb_ends / k_wb_walk / k_wb_stitch + k_window_align for the
+    windows left out) against the oracle's fast_seeds_align_hzmo on the windows and anchors of real read pairs, both strands.  The sweep runs
+    every bridge with init = 0; the test is the claim that this shift changes nothing.  -T -20: max_gap(0) < w for short bridges, so those
+    windows must take the sequential kernel (likewise anchors with more CIGAR ops than acap); copies < 0: anchors thinned out so that bridges are longer than the band is wide; copies = 9: more than 32 bridges per warp and several rounds"""
+    from test_seed_core import pairs
+    M, X, O, E, T = sc
+    n_win = n_fb = 0
+    thin, copies = (-copies, 1) if copies < 0 else (1, copies)
+    for a, b in pairs(40 + w, 6):
+        wl = _windows(oracle_lib, a, b)
+        if thin > 1:
+            # keep every thin-th anchor: bridges several hundred bases long, wider than the band (the sweep's column ring wraps)
+            wl = [(x[0], x[1], x[2], [v for k in range(0, len(x[3]) // 6, thin) for v in x[3][6 * k: 6 * k + 6]]) for x in wl]
+        for d in (0, 1):
+            ws = [x for x in wl if x[0] == d]
+            if not ws:
+                continue
+            c_strand = b if d == 0 else (3 - b[::-1]).astype(np.uint8)
+            win = (C.c_int * (3 * len(ws)))(*[v for x in ws for v in (x[1], x[2], len(x[3]) // 6)])
+            flat = [v for x in ws for v in x[3]]
+            anc = (C.c_int * max(len(flat), 1))(*flat)
+            out = (C.c_int * (11 * len(ws)))()
+            cap = sum(x[1] + x[2] + 16 + len(x[3]) // 3 for x in ws)
+            cig = (C.c_uint32 * cap)()
+            cn = (C.c_int * len(ws))()
+            nfb = C.c_int(0)
+            qa = np.ascontiguousarray(a, np.uint8)
+            cb = np.ascontiguousarray(b, np.uint8)
+            tot = dp_sim.sim_window_align_bridge(qa.ctypes.data_as(C.c_void_p), len(qa), cb.ctypes.data_as(C.c_void_p), len(cb), d, win, len(ws), anc,
+                                                 w, M, X, O, E, T, 200, C.c_float(0.6), copies, acap, out, cig, cap, cn, C.byref(nfb))
+            assert tot >= 0, tot
+            n_fb += nfb.value
+            pos = 0
+            for i, x in enumerate(ws):
+                eo = (C.c_int * 10)()
+                ecap = x[1] + x[2] + 16 + len(x[3]) // 3
+                ec = (C.c_uint32 * ecap)()
+                ea = (C.c_int * len(x[3]))(*x[3])
+                cs = np.ascontiguousarray(c_strand, np.uint8)
+                en = oracle_lib.orc_window_align(qa.ctypes.data_as(C.c_void_p), cs.ctypes.data_as(C.c_void_p), ea, len(x[3]) // 6, w, M, X, O, E, T, eo, ec, ecap)
+                got = list(out[11 * i: 11 * i + 10])
+                assert got == list(eo), (d, i, got, list(eo))
+                assert list(cig[pos: pos + cn[i]]) == list(ec[:en]), (d, i)
+                pos += cn[i]
+                n_win += 1
+    assert n_win >= 8
+    if T == -20 or acap == 6:
+        assert n_fb > 0          # the guards send them to the sequential kernel
+    elif sc == SC and w <= 50:
+        assert n_fb == 0         # default scores: every window takes the bridge pipeline
+
+
 def _refine_both(sim, orc, q, c, d, tb, qb, cig, W=50):
     """refine the alignment (start tb on q, qb on c's strand d, CIGAR cig) with the simulated kernels and with the oracle"""
     q = np.ascontiguousarray(q, np.uint8)
