@@ -279,7 +279,9 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 				CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_scrw, d_scro, (int)nsteps + 1, c->stream));
 				const uint32_t *sk = d_keys, *so = d_ord;
 				if(nsteps >= 2){ CUB_CALL(c, cub::DeviceRadixSort::SortPairsDescending(d_temp, temp_bytes, d_keys, d_skeys, d_ord, d_sord, (int)nsteps, 0, 32, c->stream)); sk = d_skeys; so = d_sord; }
-				const int sgrid = (int)std::min<uint64_t>(((uint64_t)nsteps + WB_NT - 1) / WB_NT, (uint64_t)c->n_sm * 8);
+				int per_sm = 0;      /* resident CTAs per SM with this ring: one wave of persistent CTAs, longest bridges first */
+				CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wb_sweep, WB_NT, (size_t)wb_ring * 4 * WB_NT));
+				const int sgrid = (int)std::min<uint64_t>(((uint64_t)nsteps + WB_NT - 1) / WB_NT, (uint64_t)c->n_sm * (uint64_t)std::max(per_sm, 1));
 				k_wb_sweep<<<sgrid, WB_NT, (size_t)wb_ring * 4 * WB_NT, c->stream>>>(d_steps, so, sk, nsteps, d_scro, wb_scr_cap, R.words, A.P, arena, wb_ring, wb_rw, ctr + CTR_WORK, ctr + CTR_N5); c->launches++;
 				k_wb_ends<<<(nitems + 63) / 64, 64, 0, c->stream>>>(nitems, d_items, SL.wins.as<DevWin>(), A, d_istep, d_iseq, d_steps, d_scro, arena, wb_rw, ctr + CTR_N5, ctr, CTR_CELLS_WIN); c->launches++;
 				k_wb_walk<<<(nsteps + 127) / 128, 128, 0, c->stream>>>(d_steps, nsteps, d_scro, R.words, A.P, arena, wb_rw, ctr + CTR_N5); c->launches++;

@@ -45,6 +45,9 @@ struct WBStep {
 	int32_t a_score; uint32_t a_nops; uint16_t a_aln, a_mat, a_ins, a_del;      /* run-length alignment of the anchor */
 	int32_t o_score, end_i, end_j;      /* k_wb_ends */
 	int32_t o_mat, o_mis, o_ins, o_del; uint32_t o_ncig;      /* k_wb_walk */
+	/* k_wb_sweep: outcome of the row rules relative to init, valid when no row stops the sweep, i.e. s_low + init > 0 (kswx.h:281-305):
+	 * best cell (value s_best + init), end-of-sequence cell (value s_g + init), lowest maximum of a row that did not improve, cells swept */
+	int32_t s_best, s_bi, s_bj, s_g, s_gi, s_gj, s_low; uint32_t s_cells;
 	uint32_t pad_[2];
 };
 
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(128) k_wb_prep(const WItem *items, uint32_t ni
 }
 
 /* ---- 2. a lane per bridge: row sweep for init = 0 --------------------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(WB_NT) k_wb_sweep(const WBStep *steps, const uint32_t *order, const uint32_t *skeys, uint32_t nsteps, const unsigned long long *scr_off,
+__global__ void __launch_bounds__(WB_NT) k_wb_sweep(WBStep *steps, const uint32_t *order, const uint32_t *skeys, uint32_t nsteps, const unsigned long long *scr_off,
 		unsigned long long scr_cap, const uint32_t *words, DPPar P, uint32_t *arena, int cap, int rw, unsigned long long *work, unsigned long long *overflow){
 	ZMO_DYN_SMEM(wb_raw);
 	uint4 *const ring4 = (uint4*)wb_raw; uint32_t *const ring = (uint32_t*)wb_raw;     /* slot s of lane t: word ((s >> 2) * WB_NT + t) * 4 + (s & 3) = H (low 16 bits) | E (high 16 bits) */
@@ -144,6 +147,7 @@ __global__ void __launch_bounds__(WB_NT) k_wb_sweep(const WBStep *steps, const u
 		const uint32_t *qwp = words, *cwp = words; int clen = 0; uint32_t dir = 0;
 		int x_te = 0, x_qe = 0, ql = 0, tl = 0, W = 0, i = 0, jb = 0, je = 0, j8 = 0, slot8 = 0, se = 0, hd = 0, f = 0, key = 0, hl = 0, qnext = 0, qvalid = 0;
 		unsigned long long qv = 0; uint32_t rmask = 0; uint32_t *zrow = arena; int4 *stat = nullptr;
+		int tlen = 0, qlen = 0, sb = 0, sbi = -1, sbj = -1, sg = WB_KEY_MIN, sgi = -1, sgj = -1, slow = 0x7FFFFFFF; uint32_t scells = 0; WBStep *Sw = steps;
 #define WB_ROW_BEGIN() do { \
 			jb = i > W? i - W : 0; je = i + W + 1 < tl? i + W + 1 : tl; \
 			j8 = jb & ~7; slot8 = j8 % cap; \
@@ -158,7 +162,7 @@ __global__ void __launch_bounds__(WB_NT) k_wb_sweep(const WBStep *steps, const u
 		} while(0)
 		if(busy){
 			const uint32_t si = order[k];
-			const WBStep *S = steps + si;
+			WBStep *S = steps + si; Sw = S; qlen = S->qlen; tlen = S->tlen;
 			const unsigned long long so = scr_off[si];
 			qwp = words + S->qoff; cwp = words + S->coff; clen = (int)S->clen; dir = S->dir; x_te = (int)S->x_te; x_qe = (int)S->x_qe; W = (int)S->W;
 			const BandDims d = band_dims(S->qlen, S->tlen, 0, -W, P);       /* the clamps of kswx.h:251-258 with the half-width k_wb_prep decided */
@@ -200,7 +204,7 @@ __global__ void __launch_bounds__(WB_NT) k_wb_sweep(const WBStep *steps, const u
 				key = kc > key? kc : key;
 				zw |= dd << (4 * c);
 				wv[c] = ((uint32_t)h & 0xFFFFu) | ((uint32_t)e << 16);
-				hd = ge? hup : hd; f = ge? fn : f; hl = lt? h : hl;
+				hd = ge? hup : hd; f = ge? fn : f;
 			}
 			v0.x = wv[0]; v0.y = wv[1]; v0.z = wv[2]; v0.w = wv[3]; v1.x = wv[4]; v1.y = wv[5]; v1.z = wv[6]; v1.w = wv[7];
 			sp[0] = v0; sp[WB_NT] = v1;
@@ -208,9 +212,19 @@ __global__ void __launch_bounds__(WB_NT) k_wb_sweep(const WBStep *steps, const u
 			j8 += 8; slot8 += 8; if(slot8 == cap) slot8 = 0;
 			if(j8 >= je){
 				/* row statistics for k_wb_ends: maximum (no floor at 0), its LAST column (kswx.h:284-285), value of the row's last column */
-				stat[i] = make_int4(key >> WB_KEY_SH, jb + (key & ((1 << WB_KEY_SH) - 1)) - 1, hl, 0);
+				const int Mx = key >> WB_KEY_SH, arg = jb + (key & ((1 << WB_KEY_SH) - 1)) - 1;
+				{ const int sl = (je - 1) % cap; hl = (int)(short)(WB_SLOT(sl) & 0xFFFFu); }      /* H of the row's last column */
+				stat[i] = make_int4(Mx, arg, hl, 0);
+				/* the row rules relative to init, assuming no row stops the sweep (k_wb_ends checks that with s_low and replays the rows otherwise) */
+				scells += (uint32_t)(je - jb);
+				if(je == tlen && hl > sg){ sg = hl; sgi = i; sgj = je - 1; }
+				if(i + 1 == qlen && Mx > sg){ sg = Mx; sgi = i; sgj = arg; }
+				if(Mx > sb){ sb = Mx; sbi = i; sbj = arg; } else if(Mx < slow) slow = Mx;
 				i++;
-				if(i >= ql) busy = false; else WB_ROW_BEGIN();
+				if(i >= ql){
+					busy = false;
+					Sw->s_best = sb; Sw->s_bi = sbi; Sw->s_bj = sbj; Sw->s_g = sg; Sw->s_gi = sgi; Sw->s_gj = sgj; Sw->s_low = slow; Sw->s_cells = scells;
+				} else WB_ROW_BEGIN();
 			}
 		}
 		__syncwarp();
@@ -236,6 +250,12 @@ __global__ void k_wb_ends(uint32_t nitems, const WItem *items, const DevWin *win
 			const int W = (int)S->W, qlen = S->qlen, tlen = S->tlen; const BandDims d = band_dims(qlen, tlen, 0, -W, P); const int ql = d.ql, tl = d.tl;
 			const int4 *stat = (const int4*)(arena + scr_off[s0 + a] + (size_t)ql * rw);
 			int best = init, bi = -1, bj = -1, gbest = 0, gi = -1, gj = -1;
+			if(S->s_low == 0x7FFFFFFF || S->s_low + init > 0){
+				/* no row stops the sweep: what k_wb_sweep found, shifted by init (an end-of-sequence cell counts only above 0) */
+				best = S->s_best + init; bi = S->s_bi; bj = S->s_bj;
+				if(S->s_gi >= 0 && S->s_g + init > 0){ gbest = S->s_g + init; gi = S->s_gi; gj = S->s_gj; }
+				cells += S->s_cells;
+			} else
 			for(int i = 0; i < ql; i++){
 				const int4 st = stat[i];
 				const int Mx = st.x + init, rowmax = Mx >= 0? Mx : 0, rowarg = Mx >= 0? st.y : -1, hlast = st.z + init;

@@ -286,6 +286,71 @@ def test_window_align_bridge_pipeline(dp_sim, oracle_lib, w, sc, copies, acap):
         assert n_fb == 0         # default scores: every window takes the bridge pipeline
 
 
+def _bridge_vs_oracle(dp_sim, oracle_lib, a, b, ws, w=50, sc=SC):
+    """forward-strand windows ws of (a = q, b = c) through the bridge pipeline and through the oracle; returns the number of windows left to k_window_align"""
+    M, X, O, E, T = sc
+    win = (C.c_int * (3 * len(ws)))(*[v for x in ws for v in (x[1], x[2], len(x[3]) // 6)])
+    flat = [v for x in ws for v in x[3]]
+    anc = (C.c_int * max(len(flat), 1))(*flat)
+    out = (C.c_int * (11 * len(ws)))()
+    cap = sum(x[1] + x[2] + 16 + len(x[3]) // 3 for x in ws)
+    cig = (C.c_uint32 * cap)()
+    cn = (C.c_int * len(ws))()
+    nfb = C.c_int(0)
+    qa = np.ascontiguousarray(a, np.uint8)
+    cb = np.ascontiguousarray(b, np.uint8)
+    tot = dp_sim.sim_window_align_bridge(qa.ctypes.data_as(C.c_void_p), len(qa), cb.ctypes.data_as(C.c_void_p), len(cb), 0, win, len(ws), anc,
+                                         w, M, X, O, E, T, 200, C.c_float(0.6), 1, 22, out, cig, cap, cn, C.byref(nfb))
+    assert tot >= 0, tot
+    pos = 0
+    res = []
+    for i, x in enumerate(ws):
+        eo = (C.c_int * 10)()
+        ecap = x[1] + x[2] + 16 + len(x[3]) // 3
+        ec = (C.c_uint32 * ecap)()
+        ea = (C.c_int * len(x[3]))(*x[3])
+        en = oracle_lib.orc_window_align(qa.ctypes.data_as(C.c_void_p), cb.ctypes.data_as(C.c_void_p), ea, len(x[3]) // 6, w, M, X, O, E, T, eo, ec, ecap)
+        assert list(out[11 * i: 11 * i + 10]) == list(eo), (i, list(out[11 * i: 11 * i + 10]), list(eo))
+        assert list(cig[pos: pos + cn[i]]) == list(ec[:en]), i
+        pos += cn[i]
+        res.append(list(eo))
+    return nfb.value, res
+
+
+def test_window_align_bridge_stopped_sweeps_and_broken_anchors(dp_sim, oracle_lib):
+    """the two rare paths of the bridge pipeline: (1) a bridge whose sweep the reference stops early (row maximum <= 0 without improvement:
+    the sequence between two anchors replaced by noise while the running score is still small), where k_wb_ends must replay the rows with the
+    real init instead of using the sweep's init-free summary; (2) an anchor whose run bases differ (the window is truncated after the bridge
+    in front of it, hzm_aln.h:1288-1291)"""
+    from test_seed_core import pairs
+    rng = np.random.default_rng(77)
+    n1 = n2 = 0
+    for a, b in pairs(90, 6):
+        wl = [x for x in _windows(oracle_lib, a, b) if x[0] == 0 and len(x[3]) // 6 >= 30]
+        if not wl:
+            continue
+        # (1) every 12th anchor; noise between the first two kept anchors
+        ws = [(x[0], x[1], x[2], [v for k in range(0, len(x[3]) // 6, 12) for v in x[3][6 * k: 6 * k + 6]]) for x in wl]
+        b1 = b.copy()
+        for x in ws:
+            a0, a1 = x[3][0:6], x[3][6:12]
+            lo, hi = a0[1] + a0[3] + 2, a1[1] - 2            # on c, strictly between the two anchors
+            if hi - lo > 60:
+                b1[lo:hi] = rng.integers(0, 4, hi - lo).astype(np.uint8)
+        _, res = _bridge_vs_oracle(dp_sim, oracle_lib, a, b1, ws)
+        _, res0 = _bridge_vs_oracle(dp_sim, oracle_lib, a, b, ws)
+        n1 += sum(1 for r, r0 in zip(res, res0) if r != r0)
+        # (2) one base inside the 5th anchor changed
+        b2 = b.copy()
+        for x in wl:
+            p = x[3][24:30]
+            b2[p[1] + p[3] // 2] = (b2[p[1] + p[3] // 2] + 1) & 3
+        _, res2 = _bridge_vs_oracle(dp_sim, oracle_lib, a, b2, wl)
+        _, res3 = _bridge_vs_oracle(dp_sim, oracle_lib, a, b, wl)
+        n2 += sum(1 for r, r0 in zip(res2, res3) if r[5] < r0[5] // 2)      # truncated: far fewer aligned columns
+    assert n1 >= 2 and n2 >= 2, (n1, n2)
+
+
 def _refine_both(sim, orc, q, c, d, tb, qb, cig, W=50):
     """refine the alignment (start tb on q, qb on c's strand d, CIGAR cig) with the simulated kernels and with the oracle"""
     q = np.ascontiguousarray(q, np.uint8)
