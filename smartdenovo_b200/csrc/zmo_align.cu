@@ -284,9 +284,9 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 				const int sgrid = (int)std::min<uint64_t>(((uint64_t)nsteps + WB_NT - 1) / WB_NT, (uint64_t)c->n_sm * (uint64_t)std::max(per_sm, 1));
 				k_wb_sweep<<<sgrid, WB_NT, (size_t)wb_ring * 4 * WB_NT, c->stream>>>(d_steps, so, sk, nsteps, d_scro, wb_scr_cap, R.words, A.P, arena, wb_ring, wb_rw, ctr + CTR_WORK, ctr + CTR_N5); c->launches++;
 				k_wb_ends<<<(nitems + 63) / 64, 64, 0, c->stream>>>(nitems, d_items, SL.wins.as<DevWin>(), A, d_istep, d_iseq, d_steps, d_scro, arena, wb_rw, ctr + CTR_N5, ctr, CTR_CELLS_WIN); c->launches++;
-				k_wb_walk<<<(nsteps + 127) / 128, 128, 0, c->stream>>>(d_steps, nsteps, d_scro, R.words, A.P, arena, wb_rw, ctr + CTR_N5); c->launches++;
+				k_wb_walk<<<(nsteps + 127) / 128, 128, 0, c->stream>>>(d_steps, so, sk, nsteps, d_scro, R.words, A.P, arena, wb_rw, ctr + CTR_N5); c->launches++;
 			}
-			k_wb_stitch<<<(nitems + 63) / 64, 64, 0, c->stream>>>(d_items, nitems, SL.wins.as<DevWin>(), A, d_istep, d_iseq, d_steps, d_aops, wb_acap, d_scro, arena, wb_rw, ctr + CTR_N5, cig_arena, d_icig, d_regs); c->launches++;
+			k_wb_stitch<<<(unsigned)(((unsigned long long)nitems * 32 + 127) / 128), 128, 0, c->stream>>>(d_items, nitems, SL.wins.as<DevWin>(), A, d_istep, d_iseq, d_steps, d_aops, wb_acap, d_scro, arena, wb_rw, ctr + CTR_N5, cig_arena, d_icig, d_regs); c->launches++;
 			CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORK, 0, 8, c->stream));
 			k_window_align<<<wgrid, 32 * WA_WARPS, 0, c->stream>>>(d_items, nitems, d_tasks, SL.pairs.as<zmo_pair_t>(), SL.wins.as<DevWin>(), SL.anchors.as<DevZPair>(), R, A,
 				arena, slab, max_rows, cig_arena, d_icig, d_regs, ctr, CTR_WORK, CTR_CELLS_WIN, d_fb, ctr + CTR_N4);

@@ -17,6 +17,7 @@
 #include "zmo_seed.cuh"
 #include "zmo_seed_warp.cuh"
 #include "zmo_seed_kernels.cuh"
+#include "zmo_seed_lanes.cuh"
 #include "zmo_seedfront_kernels.cuh"
 
 #define CUB_CALL(c, call_expr) do { size_t _tb = 0; void *_tp = nullptr; { auto d_temp = _tp; size_t &temp_bytes = _tb; CUDA_TRY(call_expr); } \
@@ -129,7 +130,7 @@ int seed_prepare(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, int mode, See
 		if(T >= 0xFFFFFFF0ull) return zmo_set_err(ZMO_ERR_CAPACITY, "pair batch too large (%llu z-mer matches)", T);
 		if(T){
 			/* match keys/values: s3 (chunk tables dead) zk_in | zk_out ; s4 zv_in | zv_out */
-			if(c->s3.reserve((T + 2) * 16) || c->s4.reserve((T + 2) * 16) || cache_buf.reserve((T + 4) * sizeof(DevZPair))) return ZMO_ERR_CUDA;
+			if(c->s3.reserve((T + 2) * 16) || c->s4.reserve((T + 2) * 16) || cache_buf.reserve((T + 36) * sizeof(DevZPair))) return ZMO_ERR_CUDA;
 			unsigned long long *zk_in = c->s3.as<unsigned long long>(), *zk_out = zk_in + T + 1, *zv_in = c->s4.as<unsigned long long>(), *zv_out = zv_in + T + 1;
 			if(mode == 0) k_expand<1, 0><<<(unsigned)((NH + 127) / 128), 128, 0, c->stream>>>(R, ZV, d_pq, d_pc, hk_out, hv_out, NH, (uint32_t)c->par.zcut, (uint32_t)c->par.kvar, d_hoff, zk_in, zv_in);
 			else k_expand<1, 1><<<(unsigned)((NH + 127) / 128), 128, 0, c->stream>>>(R, ZV, d_pq, d_pc, hk_out, hv_out, NH, (uint32_t)c->par.zcut, (uint32_t)c->par.kvar, d_hoff, zk_in, zv_in);
@@ -156,6 +157,7 @@ int seed_prepare(zmo_ctx *c, const zmo_pair_t *pairs, uint32_t np, int mode, See
 /* function attributes are per device: called by ctx_init for every context, with that context's device current */
 int zmo_seed_init_device(void){
 	CUDA_TRY(cudaFuncSetAttribute(k_p_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PS_WARPS * sizeof(PSSmem))));
+	CUDA_TRY(cudaFuncSetAttribute(k_p_seed_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PS_WARPS * sizeof(PSSmem))));
 	return 0;
 }
 
@@ -182,8 +184,18 @@ extern "C" int zmo_pair_windows(zmo_ctx *c, int slot, const zmo_pair_t *pairs, u
 		SeedOut O; O.wins = SL.wins.as<DevWin>(); O.anc = SL.anchors.as<DevZPair>(); O.cap_wins = cap_w; O.cap_anc = cap_a; O.cur_wins = ctr + CTR_N1; O.cur_anc = ctr + CTR_N2; O.overflow = ctr + CTR_N3;
 		CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORK, 0, 8, c->stream));
 		{
-			const int grid = (int)std::min<uint64_t>((np + PS_WARPS - 1) / PS_WARPS, (uint64_t)c->n_sm);      /* one CTA of PS_WARPS warps per SM (shared-memory bound) */
-			k_p_seed<<<grid, 32 * PS_WARPS, PS_WARPS * sizeof(PSSmem), c->stream>>>(W.cache_off, np, W.cache, W.tie, W.pc, dev_reads(c), c->s6.as<uint8_t>(), per, F, par, O, SL.seeds.as<zmo_pairseed_t>(), ctr + CTR_WORK); c->launches++;
+			/* ZMO_SEED_LANES = pairs per warp of k_p_seed_lanes (0: k_p_seed, one pair per warp; default: as many as keep every warp of the grid busy, at most 8) */
+			static const int lanes_env = [](){ const char *e = getenv("ZMO_SEED_LANES"); return e? atoi(e) : -1; }();
+			uint32_t G = 0;
+			if(lanes_env > 0) G = (uint32_t)std::min(lanes_env, 32);      /* default: k_p_seed (measured: the lane scan saves 44% of the instructions but not time, profiles/r02_experiments_decided.md) */
+			/* experiment knobs: warps per CTA (<= PS_WARPS) and CTAs per SM of the seeding kernel: a smaller footprint lets the kernels of the other contexts in flight share the SM */
+			static const int warps_env = [](){ const char *e = getenv("ZMO_SEED_WARPS"); const int v = e? atoi(e) : PS_WARPS; return v < 1? 1 : (v > PS_WARPS? PS_WARPS : v); }();
+			static const int ctas_env = [](){ const char *e = getenv("ZMO_SEED_CTAS"); const int v = e? atoi(e) : 1; return v < 1? 1 : v; }();
+			const uint64_t per_cta = (uint64_t)warps_env * (G? G : 1);
+			const int grid = (int)std::min<uint64_t>(((uint64_t)np + per_cta - 1) / per_cta, (uint64_t)c->n_sm * ctas_env);
+			if(G == 0) k_p_seed<<<grid, 32 * warps_env, warps_env * sizeof(PSSmem), c->stream>>>(W.cache_off, np, W.cache, W.tie, W.pc, dev_reads(c), c->s6.as<uint8_t>(), per, F, par, O, SL.seeds.as<zmo_pairseed_t>(), ctr + CTR_WORK);
+			else k_p_seed_lanes<<<grid, 32 * warps_env, warps_env * sizeof(PSSmem), c->stream>>>(W.cache_off, np, W.cache, W.tie, W.pc, dev_reads(c), c->s6.as<uint8_t>(), per, F, par, O, SL.seeds.as<zmo_pairseed_t>(), ctr + CTR_WORK, G);
+			c->launches++;
 		}
 		CUDA_TRY(cudaGetLastError());
 		unsigned long long h[3];

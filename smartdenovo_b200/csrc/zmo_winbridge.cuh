@@ -18,7 +18,7 @@
  *      k_wb_ends   (a lane per window)  the reference's per-row rules with the real init: best cell, end-of-sequence cell, stop at the first
  *                  row that neither improves nor is positive -> score and end cell of every bridge;
  *      k_wb_walk   (a lane per bridge)  traceback walk from the end cell (kswx.h:311-330);
- *      k_wb_stitch (a lane per window)  pads, CIGAR blocks, anchors -> DevReg + window CIGAR, exactly what k_window_align leaves.
+ *      k_wb_stitch (a warp per window)  pads, CIGAR blocks, anchors -> DevReg + window CIGAR, exactly what k_window_align leaves.
  * The sweep is where the cells are.  All lanes of a warp are in the same phase there (an 8-column group of some row of some bridge) --
  * what the lane-per-WINDOW kernel tried earlier in this round lacked (8.5 of 32 lanes active, profiles/r02_rejected_lane_per_window.md).
  * Windows the argument does not cover (band depends on init, int16 range, an anchor with more CIGAR ops than 2 per z-mer base) are listed by
@@ -276,9 +276,12 @@ __global__ void k_wb_ends(uint32_t nitems, const WItem *items, const DevWin *win
 }
 
 /* ---- 4. a lane per bridge: traceback walk (kswx.h:311-330), ops in WALK order ------------------------------------------------------------------ */
-__global__ void k_wb_walk(WBStep *steps, uint32_t nsteps, const unsigned long long *scr_off, const uint32_t *words, DPPar P, uint32_t *arena, int rw, const unsigned long long *overflow){
-	const uint32_t si = blockIdx.x * blockDim.x + threadIdx.x;
-	if(si >= nsteps || *overflow) return;
+__global__ void k_wb_walk(WBStep *steps, const uint32_t *order, const uint32_t *skeys, uint32_t nsteps, const unsigned long long *scr_off, const uint32_t *words, DPPar P, uint32_t *arena, int rw, const unsigned long long *overflow){
+	/* in the order of the sweep (longest first): the lanes of a warp walk bridges of similar length, and the bridges without cells (sort key 0) are a
+	 * contiguous tail that returns at once */
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if(k >= nsteps || *overflow || skeys[k] == 0) return;
+	const uint32_t si = order[k];
 	WBStep *S = steps + si;
 	if((S->flags & 5u) != 5u) return;
 	const int W = (int)S->W; const BandDims d = band_dims(S->qlen, S->tlen, 0, -W, P); const int ql = d.ql;
@@ -300,14 +303,29 @@ __global__ void k_wb_walk(WBStep *steps, uint32_t nsteps, const unsigned long lo
 	S->o_mat = mat; S->o_mis = mis; S->o_ins = ins; S->o_del = del; S->o_ncig = n;
 }
 
-/* ---- 5. a lane per window: pads, CIGAR blocks, anchors (hzm_aln.h:1264-1297) ------------------------------------------------------------------- */
-__global__ void k_wb_stitch(const WItem *items, uint32_t nitems, const DevWin *wins, AlnPar A, const unsigned long long *item_step_off, const uint8_t *item_seq,
+/* ---- 5. a warp per window: pads, CIGAR blocks, anchors (hzm_aln.h:1264-1297) ------------------------------------------------------------------- */
+/* One block joins the window CIGAR the way kswx_push_cigars does it (kswx.h:46-52): only its FIRST op may merge with the op in front of it.  The block is
+ * bulk[0 .. nb) (read backwards when rev) followed by the scalars tail[0 .. nt); lastv mirrors cig[ncig - 1] so that nothing is read back from memory.
+ * All arguments are warp-uniform; the lanes share the copy. */
+__device__ __forceinline__ void wb_push_block(uint32_t *cig, uint32_t &ncig, uint32_t &lastv, const uint32_t *bulk, uint32_t nb, bool rev, const uint32_t *tail, uint32_t nt, int lane){
+	const uint32_t bn = nb + nt;
+	if(bn == 0) return;      /* warp-uniform */
+	const uint32_t f0 = nb? __ldg(bulk + (rev? nb - 1 : 0)) : tail[0];
+	const uint32_t mg = (ncig && (lastv & 0xFu) == (f0 & 0xFu))? 1u : 0u;
+	if(mg){ lastv += f0 & 0xFFFFFFF0u; if(lane == 0) cig[ncig - 1] = lastv; }
+	for(uint32_t k = (uint32_t)lane + mg; k < nb; k += 32u) cig[ncig + k - mg] = __ldg(bulk + (rev? nb - 1 - k : k));
+	if(lane == 0) for(uint32_t k = nb > mg? 0u : mg - nb; k < nt; k++) cig[ncig + nb + k - mg] = tail[k];
+	if(bn > mg) lastv = nt? tail[nt - 1] : __ldg(bulk + (rev? 0 : nb - 1));
+	ncig += bn - mg;
+	__syncwarp();      /* the next block may rewrite this block's last op from another lane */
+}
+__global__ void __launch_bounds__(128) k_wb_stitch(const WItem *items, uint32_t nitems, const DevWin *wins, AlnPar A, const unsigned long long *item_step_off, const uint8_t *item_seq,
 		const WBStep *steps, const uint32_t *aops, int acap, const unsigned long long *scr_off, const uint32_t *arena, int rw, const unsigned long long *overflow,
 		uint32_t *cig_arena, const unsigned long long *item_cig_off, DevReg *regs){
-	const uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; const int lane = threadIdx.x & 31;
 	if(it >= nitems || item_seq[it] || *overflow) return;
 	const DevWin Wn = wins[items[it].win]; const DPPar P = A.P;
-	uint32_t *cig = cig_arena + item_cig_off[it]; uint32_t ncig = 0;
+	uint32_t *cig = cig_arena + item_cig_off[it]; uint32_t ncig = 0, lastv = 0;
 	int x_score = 0, x_tb = 0, x_te = 0, x_qb = 0, x_qe = 0, x_aln = 0, x_mat = 0, x_mis = 0, x_ins = 0, x_del = 0;
 	const unsigned long long s0 = item_step_off[it]; const uint32_t na = Wn.anc1 - Wn.anc0;
 	for(uint32_t a = 0; a < na; a++){
@@ -315,31 +333,27 @@ __global__ void k_wb_stitch(const WItem *items, uint32_t nitems, const DevWin *w
 		if(!(fl & 1u)) continue;
 		const int a_off1 = (int)S->x_te + S->tlen, a_off2 = (int)S->x_qe + S->qlen;          /* the anchor's start */
 		if(x_aln == 0){ x_tb = x_te = (int)S->x_te; x_qb = x_qe = (int)S->x_qe; }               /* = the anchor's start: no bridge in front of the first anchor */
-		uint32_t *blk = cig + ncig; uint32_t bn = 0;
 		x_score = S->o_score;
+		const uint32_t *ops = arena; uint32_t n = 0;
 		if(fl & 4u){
 			const int W = (int)S->W; const BandDims d = band_dims(S->qlen, S->tlen, 0, -W, P);
-			const uint32_t *ops = arena + scr_off[s0 + a] + (size_t)d.ql * (rw + 4); const uint32_t n = S->o_ncig;
-			for(uint32_t k2 = 0; k2 < n; k2++) blk[bn++] = ops[n - 1 - k2];
+			ops = arena + scr_off[s0 + a] + (size_t)d.ql * (rw + 4); n = S->o_ncig;
 			x_aln += S->o_mat + S->o_mis + S->o_ins + S->o_del; x_mat += S->o_mat; x_mis += S->o_mis; x_ins += S->o_ins; x_del += S->o_del;
 			x_te += S->end_j + 1; x_qe += S->end_i + 1;
 		}
-		/* pads count in del / ins / aln, not in the score; [bridge ops + D pad + I pad] join the window CIGAR as ONE block whose first op alone
-		 * may merge with the previous op (kswx_push_cigars, kswx.h:46-52) */
-		if(x_te < a_off1){ const uint32_t pd = (uint32_t)(a_off1 - x_te); x_del += (int)pd; x_aln += (int)pd; x_te = a_off1; if(bn && (blk[bn - 1] & 0xFu) == 2u) blk[bn - 1] += pd << 4; else blk[bn++] = (pd << 4) | 2u; }
-		if(x_qe < a_off2){ const uint32_t pi = (uint32_t)(a_off2 - x_qe); x_ins += (int)pi; x_aln += (int)pi; x_qe = a_off2; if(bn && (blk[bn - 1] & 0xFu) == 1u) blk[bn - 1] += pi << 4; else blk[bn++] = (pi << 4) | 1u; }
-		if(bn){
-			if(ncig && (cig[ncig - 1] & 0xFu) == (blk[0] & 0xFu)){
-				cig[ncig - 1] += blk[0] & 0xFFFFFFF0u;
-				for(uint32_t k2 = 1; k2 < bn; k2++) cig[ncig + k2 - 1] = blk[k2];
-				ncig += bn - 1;
-			} else ncig += bn;
-		}
+		/* pads count in del / ins / aln, not in the score; block = [bridge ops in alignment order (the walk wrote them backwards) + D pad + I pad], pads merging
+		 * with the op in front of them inside the block */
+		uint32_t tail[3], nt = 0;
+		if(n) tail[nt++] = __ldg(ops);                   /* the block's last bridge op = first op of the walk */
+		if(x_te < a_off1){ const uint32_t pd = (uint32_t)(a_off1 - x_te); x_del += (int)pd; x_aln += (int)pd; x_te = a_off1; if(nt && (tail[nt - 1] & 0xFu) == 2u) tail[nt - 1] += pd << 4; else tail[nt++] = (pd << 4) | 2u; }
+		if(x_qe < a_off2){ const uint32_t pi = (uint32_t)(a_off2 - x_qe); x_ins += (int)pi; x_aln += (int)pi; x_qe = a_off2; if(nt && (tail[nt - 1] & 0xFu) == 1u) tail[nt - 1] += pi << 4; else tail[nt++] = (pi << 4) | 1u; }
+		wb_push_block(cig, ncig, lastv, ops + 1, n? n - 1 : 0u, true, tail, nt, lane);
 		if(fl & 2u) break;        /* "should never happen": the anchor's run bases differ, the window is truncated here (hzm_aln.h:1288-1291) */
-		cig_cat(cig, ncig, aops + (s0 + a) * (unsigned long long)(acap + 1), S->a_nops, false);
+		wb_push_block(cig, ncig, lastv, aops + (s0 + a) * (unsigned long long)(acap + 1), S->a_nops, false, tail, 0u, lane);
 		x_score += S->a_score; x_aln += S->a_aln; x_mat += S->a_mat; x_ins += S->a_ins; x_del += S->a_del;
 		x_te += S->a_mat + S->a_del; x_qe += S->a_mat + S->a_ins;
 	}
+	if(lane) return;
 	DevReg r; r.score = x_score; r.tb = x_tb; r.te = x_te; r.qb = x_qb; r.qe = x_qe; r.aln = x_aln; r.mat = x_mat; r.mis = x_mis; r.ins = x_ins; r.del = x_del;
 	r.cig_off = item_cig_off[it]; r.cig_len = ncig;
 	r.kept = !(x_aln * 2 < A.zovl || (float)x_mat < (float)x_aln * A.min_id);       /* wtzmo.c:1026 */

@@ -223,9 +223,9 @@ extern "C" int sim_window_align_bridge(const uint8_t *q, int qlen, const uint8_t
 	if(nsteps){
 		emu::launch(2, WB_NT, [=](){ k_wb_sweep(ds, dsor, dsk, nsteps, dso, wb_scr_cap, wd, A.P, ar, wb_ring, wb_rw, cp, cp + 3); }, (size_t)wb_ring * 4 * WB_NT);
 		emu::launch((nitems + 63) / 64, 64, [=](){ k_wb_ends(nitems, di, dw, A, dis, dq, ds, dso, ar, wb_rw, cp + 3, cp, 1); });
-		emu::launch((nsteps + 127) / 128, 128, [=](){ k_wb_walk(ds, nsteps, dso, wd, A.P, ar, wb_rw, cp + 3); });
+		emu::launch((nsteps + 127) / 128, 128, [=](){ k_wb_walk(ds, dsor, dsk, nsteps, dso, wd, A.P, ar, wb_rw, cp + 3); });
 	}
-	emu::launch((nitems + 63) / 64, 64, [=](){ k_wb_stitch(di, nitems, dw, A, dis, dq, ds, dao, acap, dso, ar, wb_rw, cp + 3, cgp, dic, dr); });
+	emu::launch((unsigned)(((unsigned long long)nitems * 32 + 127) / 128), 128, [=](){ k_wb_stitch(di, nitems, dw, A, dis, dq, ds, dao, acap, dso, ar, wb_rw, cp + 3, cgp, dic, dr); });
 	if(ctr[3]) return -4;       /* scratch bound violated */
 	ctr[0] = 0;
 	emu::launch((unsigned)wgrid, 32 * WA_WARPS, [=](){ k_window_align(di, nitems, dt, dp, dw, da, R, A, ar, slab, max_rows, cgp, dic, dr, cp, 0, 1, dfb, cp + 2); });

@@ -16,6 +16,10 @@ thread_local std::string g_zmo_err;
 int zmo_set_err(int code, const char *, ...){ return code; }
 namespace emu { Block *g_blk = nullptr; }
 #include "../../smartdenovo_b200/csrc/zmo_seed_kernels.cuh"
+#include "../../smartdenovo_b200/csrc/zmo_seed_lanes.cuh"
+/* which pair-seeding kernel the simulations launch: 0 = k_p_seed (one pair per warp), G > 0 = k_p_seed_lanes with G pairs per warp */
+static int g_seed_lanes = 0;
+extern "C" void simk_set_seed_lanes(int g){ g_seed_lanes = g; }
 #include "../../smartdenovo_b200/csrc/zmo_seedfront_kernels.cuh"
 #include "../../smartdenovo_b200/csrc/zmo_dot_kernels.cuh"
 
@@ -89,7 +93,7 @@ extern "C" int simk_pair_windows(const uint8_t *pb1, int alen, const uint8_t *pb
 	const unsigned long long *dco = coff.data(); DevZPair *dc = cache.data(); const uint8_t *dt = tieflag.data(); const uint32_t *dpc = pc.data();
 	uint8_t *ds = scratch.data(); zmo_pairseed_t *dsd = seeds.data(); unsigned long long *work = ctr;
 	const uint32_t FF = (uint32_t)F;
-	emu::launch(np > 1? 2u : 1u, 32 * PS_WARPS, [=](){ k_p_seed(dco, np, dc, dt, dpc, R, ds, per, FF, par, O, dsd, work); }, PS_WARPS * sizeof(PSSmem));
+	{ const int gl = g_seed_lanes; emu::launch(np > 1? 2u : 1u, 32 * PS_WARPS, [=](){ if(gl) k_p_seed_lanes(dco, np, dc, dt, dpc, R, ds, per, FF, par, O, dsd, work, (uint32_t)gl); else k_p_seed(dco, np, dc, dt, dpc, R, ds, per, FF, par, O, dsd, work); }, PS_WARPS * sizeof(PSSmem)); }
 	if(ctr[3]) return -1;
 	*n_hzmp = (int)seeds[0].n_zpair; ovl[0] = seeds[0].ovl[0]; ovl[1] = seeds[0].ovl[1];
 	auto emit = [&](const zmo_pairseed_t &S, std::vector<int> &wv, std::vector<int> &av){
@@ -255,7 +259,7 @@ extern "C" int simk_batch_windows(const uint8_t *seqs, const int *lens, int nrea
 	SeedOut O; O.wins = wins.data(); O.anc = anc.data(); O.cap_wins = cap_w; O.cap_anc = cap_a; O.cur_wins = ctr + 1; O.cur_anc = ctr + 2; O.overflow = ctr + 3;
 	SeedPar par; par.zsize = zsize; par.kwin = kwin; par.kstep = kstep; par.zovl = zovl; par.ztot = ztot; par.W = W;
 	DevZPair *dc = cache.data(); uint8_t *ds = scratch.data(); zmo_pairseed_t *dsd = seeds.data(); unsigned long long *work = ctr; const uint32_t FF = (uint32_t)F;
-	emu::launch(std::min<uint32_t>((np + PS_WARPS - 1) / PS_WARPS, 2u), 32 * PS_WARPS, [=](){ k_p_seed(d_coff, np, dc, d_tie, d_pc, R, ds, per, FF, par, O, dsd, work); }, PS_WARPS * sizeof(PSSmem));
+	{ const int gl = g_seed_lanes; emu::launch(std::min<uint32_t>((np + PS_WARPS - 1) / PS_WARPS, 2u), 32 * PS_WARPS, [=](){ if(gl) k_p_seed_lanes(d_coff, np, dc, d_tie, d_pc, R, ds, per, FF, par, O, dsd, work, (uint32_t)gl); else k_p_seed(d_coff, np, dc, d_tie, d_pc, R, ds, per, FF, par, O, dsd, work); }, PS_WARPS * sizeof(PSSmem)); }
 	if(ctr[3]) return -1;
 	const zmo_pairseed_t &S = seeds[which];
 	*n_hzmp = (int)S.n_zpair; ovl[0] = S.ovl[0]; ovl[1] = S.ovl[1];

@@ -68,14 +68,18 @@ def check(lib, orc, a, b, **kw):
     return len(exp[2]) // 7
 
 
-def test_seed_kernel_matches_oracle(seedk_sim, oracle_lib):
+@pytest.mark.parametrize("lanes", [0, 4, 32])
+def test_seed_kernel_matches_oracle(seedk_sim, oracle_lib, lanes):
+    seedk_sim.simk_set_seed_lanes(lanes)      # 0: k_p_seed (a pair per warp); G: k_p_seed_lanes with G pairs per warp (zmo_seed_lanes.cuh)
     nwin = 0
     for a, b in pairs(500, 24):
         nwin += check(seedk_sim, oracle_lib, a, b)
     assert nwin > 30
 
 
-def test_seed_kernel_parameters_and_degenerate_inputs(seedk_sim, oracle_lib):
+@pytest.mark.parametrize("lanes", [0, 4, 32])
+def test_seed_kernel_parameters_and_degenerate_inputs(seedk_sim, oracle_lib, lanes):
+    seedk_sim.simk_set_seed_lanes(lanes)      # 0: k_p_seed (a pair per warp); G: k_p_seed_lanes with G pairs per warp (zmo_seed_lanes.cuh)
     for a, b in pairs(501, 5):
         for kw in (dict(zsize=12, zcut=16, kvar=1, kwin=500, kstep=250, zovl=100, ztot=200, W=1000), dict(zsize=8, hz=0, zcut=255, kvar=0), dict(zsize=16)):
             check(seedk_sim, oracle_lib, a, b, **kw)
@@ -85,9 +89,11 @@ def test_seed_kernel_parameters_and_degenerate_inputs(seedk_sim, oracle_lib):
         check(seedk_sim, oracle_lib, x, y)
 
 
-def test_seed_kernel_tie_path_and_work_loop(seedk_sim, oracle_lib):
+@pytest.mark.parametrize("lanes", [0, 4, 32])
+def test_seed_kernel_tie_path_and_work_loop(seedk_sim, oracle_lib, lanes):
     """force_tie: the kernel first rebuilds the reference's emission order, then runs the exact sort_array emulation -- the same
     bytes as the radix-sorted fast path; 50 copies of a pair on 2 CTAs x 22 warps run the work-counter loop"""
+    seedk_sim.simk_set_seed_lanes(lanes)      # 0: k_p_seed (a pair per warp); G: k_p_seed_lanes with G pairs per warp (zmo_seed_lanes.cuh)
     for i, (a, b) in enumerate(pairs(502, 6)):
         check(seedk_sim, oracle_lib, a, b, force_tie=1)
         if i < 2:
@@ -136,11 +142,13 @@ def test_dot_kernel_matches_oracle(seedk_sim, oracle_lib):
     assert out[0] == 0 and out[5] == 0
 
 
-def test_seeding_stage_batch(seedk_sim, oracle_lib):
+@pytest.mark.parametrize("lanes", [0, 4, 32])
+def test_seeding_stage_batch(seedk_sim, oracle_lib, lanes):
     """the whole device side of zmo_pair_windows for a batch of pairs sharing query reads: z-index of the batch (k_z_scan, k_z_heads,
     k_z_slots with the hashed slot filter, k_z_ranges), chunk-parallel hits (k_hit), rank cap + expansion (k_expand), unpacking with tie
     flags (k_unpack, k_pair_offsets) -- zmo_seedfront_kernels.cuh, with std:: sorts / scans where seed_prepare calls CUB -- then k_p_seed;
     every pair must give the oracle's match count, chain weights, windows and anchors"""
+    seedk_sim.simk_set_seed_lanes(lanes)      # 0: k_p_seed (a pair per warp); G: k_p_seed_lanes with G pairs per warp (zmo_seed_lanes.cuh)
     reads = []
     for a, b in pairs(800, 3):
         reads += [a, b]
