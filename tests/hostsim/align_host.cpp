@@ -103,7 +103,7 @@ extern "C" int sim_pair_align(const uint8_t *q, int qlen, const uint8_t *c, int 
 	const WItem *di = items.data(); const AlnTask *dt = &task; const zmo_pair_t *dp = &pair; const DevWin *dw = wins.data(); const DevZPair *da = an.data();
 	uint32_t *ar = arena.data(), *cgp = cig_arena.data(); const unsigned long long *dic = icig.data(); DevReg *dr = regs.data(); unsigned long long *cp = ctr;
 	TaskState *dts = ts.data(); DPJob *dj = jobs.data(); DPRes *dres = res.data();
-	if(nitems) emu::launch((unsigned)wgrid, 32 * WA_WARPS, [=](){ k_window_align(di, nitems, dt, dp, dw, da, R, A, ar, slab, max_rows, cgp, dic, dr, cp, 0, 1); });
+	if(nitems) emu::launch((unsigned)wgrid, 32 * WA_WARPS, [=](){ k_window_align(di, nitems, dt, dp, dw, da, R, A, ar, slab, max_rows, cgp, dic, dr, cp, 0, 1, nullptr, nullptr); });      /* the bridge pipeline (zmo_winbridge.cuh) leaves the same DevReg + CIGAR per window: tests/test_dp_hostsim.py::test_window_align_bridge_pipeline */
 	stats[6] = 0; for(uint32_t i = 0; i < nitems; i++) stats[6] += regs[i].kept? 1 : 0;
 	JobLists L; L.cap = jcap;
 	for(int k = 0; k < 6; k++){ L.list[k] = dj + (size_t)k * jcap; L.cnt[k] = ctr + 10 + k; L.res_base[k] = (uint32_t)k * jcap; }
