@@ -1218,7 +1218,7 @@ wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	if((env = getenv("ZMO_DEVICE"))) S->device = atoi(env); else if((env = getenv("LOCAL_RANK"))) S->device = atoi(env);
 	z->batch_reads = (env = getenv("ZMO_BATCH_READS"))? atoi(env) : 384;
 	z->batch_pairs = (env = getenv("ZMO_BATCH_PAIRS"))? atoi(env) : 40000;
-	z->depth = 1 + ((env = getenv("ZMO_DEPTH"))? atoi(env) : 3);      /* ZMO_DEPTH = batches in flight on the device while the host replays the oldest */
+	z->depth = 1 + ((env = getenv("ZMO_DEPTH"))? atoi(env) : 2);      /* ZMO_DEPTH = batches in flight on the device while the host replays the oldest */
 	if((env = getenv("ZMO_PIPELINE")) && atoi(env) == 0) z->depth = 1;  /* no pipeline: one batch at a time, one context */
 	if(z->depth < 1) z->depth = 1;
 	if(z->depth > WZ_MAX_CTX) z->depth = WZ_MAX_CTX;

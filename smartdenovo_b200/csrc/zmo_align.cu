@@ -209,7 +209,7 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 	if(SL.np == 0) return zmo_set_err(ZMO_ERR_STATE, "zmo_pair_windows has not filled slot %d", slot);
 	CUDA_TRY(cudaSetDevice(c->device));
 	/* host: items and per-item cigar regions */
-	std::vector<AlnTask> ht(nt); std::vector<WItem> items; std::vector<unsigned long long> icig, istep;
+	std::vector<AlnTask> ht(nt); std::vector<WItem> items; std::vector<unsigned long long> icig, istep, ibound;
 	unsigned long long cig_words = 0, nsteps64 = 0, wb_rows = 0, wb_cols = 0; int max_rows = 16;
 	for(uint32_t t = 0; t < nt; t++){
 		if(tasks[t].pair_idx >= SL.np || tasks[t].dir > 1) return zmo_set_err(ZMO_ERR_ARG, "task %u out of range", t);
@@ -219,7 +219,7 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 			WItem it; it.task = t; it.win = ps.win_off[d] + k; items.push_back(it);
 			const int s0 = SL.h_wspan[3 * (size_t)it.win], s1 = SL.h_wspan[3 * (size_t)it.win + 1], na = SL.h_wspan[3 * (size_t)it.win + 2];
 			icig.push_back(cig_words); cig_words += (unsigned long long)(s0 + s1 + 16 + 2 * na);
-			istep.push_back(nsteps64); nsteps64 += (unsigned long long)na; wb_rows += (unsigned long long)(s1 + 16); wb_cols += (unsigned long long)(s0 + 16) + 8ull * (unsigned long long)na;
+			istep.push_back(nsteps64); nsteps64 += (unsigned long long)na; ibound.push_back((unsigned long long)(s1 + 16)); wb_cols += (unsigned long long)(s0 + 16) + 16ull * (unsigned long long)na;      /* rows of all bridges of a window <= its span on c; columns <= its span on q (+ w per bridge, below) */
 			if(s1 + 8 > max_rows) max_rows = s1 + 8;
 			if(s0 + 8 > max_rows) max_rows = s0 + 8;
 		}
@@ -233,8 +233,23 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 	static const bool wb_env = [](){ const char *e = getenv("ZMO_WA_BRIDGE"); return !(e && e[0] == '0'); }();      /* ZMO_WA_BRIDGE=0: every window through k_window_align (A/B runs) */
 	const bool use_wb = wb_env && c->par.w >= 1 && c->par.w <= WB_MAX_W && nitems > 0 && nsteps64 < 0xFFFFFFF0ull;
 	const int wb_ring = wb_cap(c->par.w), wb_rw = wb_row_words(c->par.w), wb_acap = 2 * (int)c->par.zsize + 2;      /* an anchor is a z-mer: zsize runs, at most M + I|D each */
-	/* scratch of the swept bridges, bounded from the window spans: rows of all bridges of a window <= its span on c, columns <= its span on q + w per bridge */
-	const unsigned long long wb_scr_cap = use_wb? wb_rows * (unsigned long long)(wb_rw + 5) + wb_cols + 8ull * nsteps64 + 1024 : 0;
+	/* scratch of the swept bridges, bounded from the window spans (wb_scr_words per bridge); a wave whose bound exceeds the budget is swept in several
+	 * passes over item ranges, so the arena stays bounded whatever the wave size (ZMO_WB_CHUNK_MB, default 2048) */
+	static const unsigned long long wb_budget = [](){ const char *e = getenv("ZMO_WB_CHUNK_MB"); const long long mb = e? atoll(e) : 2048; return (unsigned long long)(mb < 1? 1 : mb) * (1ull << 18); }();     /* words */
+	std::vector<uint32_t> wb_chunk;      /* first item of every pass, then nitems */
+	unsigned long long wb_scr_cap = 0;
+	if(use_wb){
+		unsigned long long acc = 0; wb_chunk.push_back(0);
+		for(uint32_t i = 0; i < nitems; i++){
+			const unsigned long long na_i = (i + 1 < nitems? istep[i + 1] : nsteps64) - istep[i];
+			const unsigned long long b = ibound[i] * (unsigned long long)(wb_rw + 5) + ibound[i] + na_i * (unsigned long long)(c->par.w + 24) + 64;      /* sum of wb_scr_words: rows <= span on c, columns of a bridge <= its rows + w */
+			if(acc && acc + b > wb_budget){ wb_chunk.push_back(i); if(acc > wb_scr_cap) wb_scr_cap = acc; acc = 0; }
+			acc += b;
+		}
+		wb_chunk.push_back(nitems); if(acc > wb_scr_cap) wb_scr_cap = acc;
+		wb_scr_cap += 1024;
+	}
+	(void)wb_rows; (void)wb_cols;
 	/* with the bridge pipeline k_window_align only sees the windows that pipeline leaves out: a quarter of the executors (all of them are used if needed, just in more rounds) */
 	const int wgrid = (int)std::min<uint64_t>((nitems + WA_WARPS - 1) / WA_WARPS + 1, (uint64_t)c->n_sm * (use_wb? 2 : 8));
 	const int wcol = std::min(max_rows + c->par.w, 2 * c->par.w + 1);
@@ -271,26 +286,32 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 			uint8_t *d_iseq = (uint8_t*)(d_fb + nitems);
 			CUDA_TRY(cudaMemcpyAsync(d_istep, istep.data(), (size_t)nitems * 8, cudaMemcpyHostToDevice, c->stream));
 			CUDA_TRY(cudaMemsetAsync(ctr + CTR_N4, 0, 16, c->stream));            /* CTR_N4 = windows left to k_window_align, CTR_N5 = scratch bound violated */
-			CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORK, 0, 8, c->stream));
-			CUDA_TRY(cudaMemsetAsync(d_scrw + nsteps, 0, 8, c->stream));
-			k_wb_prep<<<(unsigned)(((unsigned long long)nitems * 32 + 127) / 128), 128, 0, c->stream>>>(d_items, nitems, d_tasks, SL.pairs.as<zmo_pair_t>(), SL.wins.as<DevWin>(), SL.anchors.as<DevZPair>(), R, A,
-				d_istep, wb_rw, d_steps, d_aops, wb_acap, d_scrw, d_keys, d_ord, d_iseq, d_fb, ctr + CTR_N4); c->launches++;
-			if(nsteps){
-				CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_scrw, d_scro, (int)nsteps + 1, c->stream));
-				const uint32_t *sk = d_keys, *so = d_ord;
-				if(nsteps >= 2){ CUB_CALL(c, cub::DeviceRadixSort::SortPairsDescending(d_temp, temp_bytes, d_keys, d_skeys, d_ord, d_sord, (int)nsteps, 0, 32, c->stream)); sk = d_skeys; so = d_sord; }
-				int per_sm = 0;      /* resident CTAs per SM with this ring: one wave of persistent CTAs, longest bridges first */
-				CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wb_sweep, WB_NT, (size_t)wb_ring * 4 * WB_NT));
-				const int sgrid = (int)std::min<uint64_t>(((uint64_t)nsteps + WB_NT - 1) / WB_NT, (uint64_t)c->n_sm * (uint64_t)std::max(per_sm, 1));
-				k_wb_sweep<<<sgrid, WB_NT, (size_t)wb_ring * 4 * WB_NT, c->stream>>>(d_steps, so, sk, nsteps, d_scro, wb_scr_cap, R.words, A.P, arena, wb_ring, wb_rw, ctr + CTR_WORK, ctr + CTR_N5); c->launches++;
-				k_wb_ends<<<(nitems + 63) / 64, 64, 0, c->stream>>>(nitems, d_items, SL.wins.as<DevWin>(), A, d_istep, d_iseq, d_steps, d_scro, arena, wb_rw, ctr + CTR_N5, ctr, CTR_CELLS_WIN); c->launches++;
-				k_wb_walk<<<(nsteps + 127) / 128, 128, 0, c->stream>>>(d_steps, so, sk, nsteps, d_scro, R.words, A.P, arena, wb_rw, ctr + CTR_N5); c->launches++;
+			int per_sm = 0;      /* resident CTAs per SM with this ring: one wave of persistent CTAs, longest bridges first */
+			CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wb_sweep, WB_NT, (size_t)wb_ring * 4 * WB_NT));
+			for(size_t ch = 0; ch + 1 < wb_chunk.size(); ch++){
+				/* one pass: items [i0, i1), their steps [st0, st1); every per-item / per-step array is addressed from its global base, the per-pass views below only
+				 * shift the item-indexed ones (k_wb_prep lists the windows it leaves out by their index inside the pass) */
+				const uint32_t i0 = wb_chunk[ch], i1 = wb_chunk[ch + 1], ni = i1 - i0;
+				const unsigned long long st0 = istep[i0], st1 = i1 < nitems? istep[i1] : nsteps64; const uint32_t ns = (uint32_t)(st1 - st0);
+				if(ch) CUDA_TRY(cudaMemsetAsync(ctr + CTR_N4, 0, 8, c->stream));
+				CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORK, 0, 8, c->stream));
+				k_wb_prep<<<(unsigned)(((unsigned long long)ni * 32 + 127) / 128), 128, 0, c->stream>>>(d_items + i0, ni, d_tasks, SL.pairs.as<zmo_pair_t>(), SL.wins.as<DevWin>(), SL.anchors.as<DevZPair>(), R, A,
+					d_istep + i0, wb_rw, d_steps, d_aops, wb_acap, d_scrw, d_keys, d_ord, d_iseq + i0, d_fb, ctr + CTR_N4); c->launches++;
+				if(ns){
+					CUB_CALL(c, cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_scrw + st0, d_scro + st0, (int)ns + 1, c->stream));      /* offsets from 0 in every pass; the input behind the last step is not used */
+					const uint32_t *sk = d_keys + st0, *so = d_ord + st0;
+					if(ns >= 2){ CUB_CALL(c, cub::DeviceRadixSort::SortPairsDescending(d_temp, temp_bytes, d_keys + st0, d_skeys + st0, d_ord + st0, d_sord + st0, (int)ns, 0, 32, c->stream)); sk = d_skeys + st0; so = d_sord + st0; }
+					const int sgrid = (int)std::min<uint64_t>(((uint64_t)ns + WB_NT - 1) / WB_NT, (uint64_t)c->n_sm * (uint64_t)std::max(per_sm, 1));
+					k_wb_sweep<<<sgrid, WB_NT, (size_t)wb_ring * 4 * WB_NT, c->stream>>>(d_steps, so, sk, ns, d_scro, wb_scr_cap, R.words, A.P, arena, wb_ring, wb_rw, ctr + CTR_WORK, ctr + CTR_N5); c->launches++;
+					k_wb_ends<<<(ni + 63) / 64, 64, 0, c->stream>>>(ni, d_items + i0, SL.wins.as<DevWin>(), A, d_istep + i0, d_iseq + i0, d_steps, d_scro, arena, wb_rw, ctr + CTR_N5, ctr, CTR_CELLS_WIN); c->launches++;
+					k_wb_walk<<<(ns + 127) / 128, 128, 0, c->stream>>>(d_steps, so, sk, ns, d_scro, R.words, A.P, arena, wb_rw, ctr + CTR_N5); c->launches++;
+				}
+				k_wb_stitch<<<(unsigned)(((unsigned long long)ni * 32 + 127) / 128), 128, 0, c->stream>>>(d_items + i0, ni, SL.wins.as<DevWin>(), A, d_istep + i0, d_iseq + i0, d_steps, d_aops, wb_acap, d_scro, arena, wb_rw, ctr + CTR_N5, cig_arena, d_icig + i0, d_regs + i0); c->launches++;
+				CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORK, 0, 8, c->stream));
+				k_window_align<<<wgrid, 32 * WA_WARPS, 0, c->stream>>>(d_items + i0, ni, d_tasks, SL.pairs.as<zmo_pair_t>(), SL.wins.as<DevWin>(), SL.anchors.as<DevZPair>(), R, A,
+					arena, slab, max_rows, cig_arena, d_icig + i0, d_regs + i0, ctr, CTR_WORK, CTR_CELLS_WIN, d_fb, ctr + CTR_N4);
+				c->launches++;
 			}
-			k_wb_stitch<<<(unsigned)(((unsigned long long)nitems * 32 + 127) / 128), 128, 0, c->stream>>>(d_items, nitems, SL.wins.as<DevWin>(), A, d_istep, d_iseq, d_steps, d_aops, wb_acap, d_scro, arena, wb_rw, ctr + CTR_N5, cig_arena, d_icig, d_regs); c->launches++;
-			CUDA_TRY(cudaMemsetAsync(ctr + CTR_WORK, 0, 8, c->stream));
-			k_window_align<<<wgrid, 32 * WA_WARPS, 0, c->stream>>>(d_items, nitems, d_tasks, SL.pairs.as<zmo_pair_t>(), SL.wins.as<DevWin>(), SL.anchors.as<DevZPair>(), R, A,
-				arena, slab, max_rows, cig_arena, d_icig, d_regs, ctr, CTR_WORK, CTR_CELLS_WIN, d_fb, ctr + CTR_N4);
-			c->launches++;
 			CUDA_TRY(cudaGetLastError());
 		} else if(nitems){
 			StageTimer tm(c, ST_WINALN);

@@ -238,6 +238,10 @@ def test_cfg1_full_run_matches_reference_golden(tmp_path, gen_reads):
     """BASELINE.json configs[0], the whole job: 2,000 PacBio-like reads x 8 kb, 7,443 records incl. every CIGAR; and the same reads in
     dot-matrix mode (smartdenovo.pl:48 flags), 11,921 records"""
     _golden_run(tmp_path, gen_reads, "cfg1_full", keep=True)
+    # window alignment: the bridge-level pipeline in passes of 1 MB of scratch (a large wave is swept in several passes over item ranges), and
+    # the sequential warp-per-window kernel alone -- the same bytes
+    _golden_run(tmp_path, gen_reads, "cfg1_full", env=dict(os.environ, ZMO_WB_CHUNK_MB="1"), keep=True)
+    _golden_run(tmp_path, gen_reads, "cfg1_full", env=dict(os.environ, ZMO_WA_BRIDGE="0"), keep=True)
     _golden_run(tmp_path, gen_reads, "cfg1_dot")
 
 
