@@ -53,7 +53,7 @@ STAGES = ["index", "candidates", "pair_windows", "window_align", "gap_global", "
 TRAFFIC = {
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (one 384-read batch of the cfg2 `-P 40 -p 0` shard = the batch size of the bench)
     ("cfg2", "pair_windows"): dict(kernel="k_p_seed", dram_bytes=2.109e9, launch="largest of the 5 batches of the shard", source="profiles/r02_ncu_final.md"),
-    ("cfg2", "window_align"): dict(kernel="k_window_align", dram_bytes=268.2e6, launch="first wave of the shard", source="profiles/r02_ncu_final.md"),
+    ("cfg2", "window_align"): dict(kernel="k_wb_sweep", dram_bytes=1.906e9, launch="second wave of the shard: 4-bit traceback + 16 B per row of every bridge of the wave", source="profiles/r02_ncu_bridge.md"),
     ("cfg2", "dp_phase"): dict(kernel="k_ext_cta<128,13,1>", dram_bytes=239.3e6, launch="first wave of the shard", source="profiles/r02_ncu_final.md"),
     ("cfg3s", "dotmatrix"): dict(kernel="k_p_dot", dram_bytes=5.219e9, launch="first batch of the cfg3s `-P 16 -p 0` shard", source="profiles/r02_ncu_final.md"),
     ("cfg2s", "window_align"): dict(kernel="k_window_align", dram_bytes=377.8e6, source="profiles/r01_ncu_final.md"),
@@ -224,7 +224,7 @@ def stage_roofline(wl_name, st0, st1, steps, peak, peaks_found):
     # the end-extension + gap-fill executors run CONCURRENTLY (one stream per executor class): their cost is the wall time of that phase
     groups = {
         "dp_phase": (stage_ms["dp_phase_wall"], 0.5 * (cells["end_extend"] + cells["gap_global"]), cells["end_extend"] + cells["gap_global"], "k_ext_cta<64|128,7|13,1> + k_ext_warp<1> + k_glb_warp/k_glb_cta (concurrent)", "0.5 B x DP cells"),
-        "window_align": (stage_ms["window_align"], 0.5 * cells["window_align"], cells["window_align"], "k_window_align", "0.5 B x DP cells"),
+        "window_align": (stage_ms["window_align"], 0.5 * cells["window_align"], cells["window_align"], "k_wb_prep + k_wb_sweep + k_wb_ends + k_wb_walk + k_wb_stitch (bridge-level window alignment; k_window_align for the windows it leaves out)", "0.5 B x DP cells"),
         "pair_windows": (stage_ms["pair_windows"], 32.0 * matches, matches, "k_p_seed + k_hit + k_expand + radix sorts (z-mer seeding)", "2 x 16 B x z-mer matches"),
         "dotmatrix": (stage_ms["dotmatrix"], 32.0 * matches, matches, "k_p_dot + k_hit + k_expand + radix sorts (dot-matrix)", "2 x 16 B x z-mer matches"),
     }

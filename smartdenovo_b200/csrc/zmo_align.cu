@@ -234,8 +234,8 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 	const bool use_wb = wb_env && c->par.w >= 1 && c->par.w <= WB_MAX_W && nitems > 0 && nsteps64 < 0xFFFFFFF0ull;
 	const int wb_ring = wb_cap(c->par.w), wb_rw = wb_row_words(c->par.w), wb_acap = 2 * (int)c->par.zsize + 2;      /* an anchor is a z-mer: zsize runs, at most M + I|D each */
 	/* scratch of the swept bridges, bounded from the window spans (wb_scr_words per bridge); a wave whose bound exceeds the budget is swept in several
-	 * passes over item ranges, so the arena stays bounded whatever the wave size (ZMO_WB_CHUNK_MB, default 2048) */
-	static const unsigned long long wb_budget = [](){ const char *e = getenv("ZMO_WB_CHUNK_MB"); const long long mb = e? atoll(e) : 2048; return (unsigned long long)(mb < 1? 1 : mb) * (1ull << 18); }();     /* words */
+	 * passes over item ranges, so the arena stays bounded whatever the wave size (ZMO_WB_CHUNK_MB, default 6144) */
+	static const unsigned long long wb_budget = [](){ const char *e = getenv("ZMO_WB_CHUNK_MB"); const long long mb = e? atoll(e) : 6144; return (unsigned long long)(mb < 1? 1 : mb) * (1ull << 18); }();     /* words */
 	std::vector<uint32_t> wb_chunk;      /* first item of every pass, then nitems */
 	unsigned long long wb_scr_cap = 0;
 	if(use_wb){
