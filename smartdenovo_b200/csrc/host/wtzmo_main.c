@@ -1107,7 +1107,8 @@ static int usage(void){
 	" -n          Refine the alignment\n"
 	" -v          Verbose (accepted, ignored)\n"
 	"Environment: ZMO_DEVICE (GPU ordinal, default 0; under torchrun LOCAL_RANK), ZMO_GPUS=n|all (GPU g runs job -P P*n -p p*n+g, records gathered\n"
-	"             over NCCL and written in job order), ZMO_DEVICES=a,b,.. (their ordinals), ZMO_BATCH_READS, ZMO_BATCH_PAIRS, ZMO_STATS=file\n"
+	"             over NCCL and written in job order), ZMO_DEVICES=a,b,.. (their ordinals), ZMO_BATCH_READS, ZMO_BATCH_PAIRS, ZMO_STATS=file;\n"
+	"             A/B switches: ZMO_WA_BRIDGE=0 (window alignment by the sequential kernel), ZMO_SEED_LANES=G (G pairs per warp in the seeding kernel)\n"
 	"\n");
 	return 1;
 }
