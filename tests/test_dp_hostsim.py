@@ -232,7 +232,8 @@ def test_window_align_kernel(dp_sim, oracle_lib, w):
 
 
 @pytest.mark.parametrize("w,sc,copies,acap", [(50, (2, -5, -3, -1, -50), 1, 22), (20, (2, -5, -3, -1, -50), 9, 22), (91, (2, -5, -3, -1, -50), 1, 22), (50, (1, -3, -2, -2, -10), 1, 22), (50, (2, -5, -3, -1, -20), 1, 22), (50, (2, -5, -3, -1, -50), 1, 6),
-                                                    (50, (2, -5, -3, -1, -50), -12, 22), (20, (2, -5, -3, -1, -50), -7, 22), (91, (2, -5, -3, -1, -50), -30, 22)])
+                                                    (50, (2, -5, -3, -1, -50), -12, 22), (20, (2, -5, -3, -1, -50), -7, 22), (91, (2, -5, -3, -1, -50), -30, 22),
+                                                    (30, (3, -4, -5, -2, -30), -5, 22), (10, (1, -1, -1, -1, -5), -9, 22), (64, (5, -9, -7, -3, -200), -16, 22), (50, (2, -30, -3, -1, -50), -12, 22)])
 def test_window_align_bridge_pipeline(dp_sim, oracle_lib, w, sc, copies, acap):
     """bridge-level window alignment (zmo_winbridge.cuh: k_wb_prep / k_wb_sweep / k_wb_ends / k_wb_walk / k_wb_stitch + k_window_align for the
     windows left out) against the oracle's fast_seeds_align_hzmo on the windows and anchors of real read pairs, both strands.  The sweep runs
