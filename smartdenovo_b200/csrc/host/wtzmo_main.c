@@ -480,7 +480,7 @@ typedef struct {
 	struct { u8 *base; size_t cap, used, want; } pin[WZ_MAX_CTX];
 	pthread_mutex_t dev_mu[WZ_MAX_CTX];  /* one device call at a time per context */
 	pthread_mutex_t stat_mu;
-	u64 n_waves, n_wave_tasks; int wave_margin, wave_growth, ramp, drain_div, drain_min;
+	u64 n_waves, n_wave_tasks; int wave_margin, wave_growth, wave_predict, ramp, drain_div, drain_min;
 } wz_t;
 
 static double now_s(void){ struct timeval tv; gettimeofday(&tv, NULL); return tv.tv_sec + 1e-6 * tv.tv_usec; }
@@ -706,6 +706,39 @@ static long dry_walk(const wz_t *z, const batch_t *b, const bread_t *r, const se
 	return -1;
 }
 
+/* Predicted alignment of a seed that has not been aligned yet, from its kept windows: the bounding box of the chain, extended on both sides to
+ * the nearer read end (what the end extensions reach when the overlap is real).  Only the speculation policy looks at it (how many seeds of a
+ * read the next DP wave aligns); every record the replay uses is a computed one. */
+static void predict_rec(const batch_t *b, const seed_t *s, int l1, int l2, zmo_record_t *x){
+	const zmo_pairseed_t *ps = &b->seeds[s->cand_idx]; int b0 = l1, e0 = 0, b1 = l2, e1 = 0, lo, hi; u32 j;
+	for(j=0;j<ps->n_win[s->dir];j++){
+		const zmo_window_t *w = &b->wins[ps->win_off[s->dir] + j];
+		b0 = imin(b0, w->beg[0]); e0 = imax(e0, w->end[0]); b1 = imin(b1, w->beg[1]); e1 = imax(e1, w->end[1]);
+	}
+	memset(x, 0, sizeof(*x));
+	if(e0 <= b0 || e1 <= b1) return;
+	lo = imin(b0, b1); hi = imin(l1 - e0, l2 - e1); if(hi < 0) hi = 0;
+	x->ok = 1; x->tb = b0 - lo; x->te = e0 + hi; x->qb = b1 - lo; x->qe = e1 + hi;
+}
+/* dry walk in which a missing alignment is replaced by its prediction: index of the seed at which the walk is predicted to stop (the number of
+ * seeds if it is predicted to run through).  The DP wave aligns the missing seeds up to there plus a margin, instead of a fixed number per read. */
+static long predicted_stop(const wz_t *z, const batch_t *b, const bread_t *r, const seedv *sv){
+	const zparams_t *par = &z->par; const readset_t *rs = &z->rs; u32 ncand = par->ncand, bcov = r->bcov0, nbest = read_nbest(z, r->rd_id); size_t i;
+	int alen = rs->reads.a[r->rd_id].len;
+	if(bcov >= nbest) return 0;
+	for(i=0;i<sv->n&&i<ncand;i++){
+		const seed_t *s = &sv->a[i]; const zmo_record_t *x; zmo_record_t px;
+		if(s->closed){ ncand ++; continue; }
+		x = b->pres[s->cand_idx];
+		if(x == NULL){ predict_rec(b, s, alen, rs->reads.a[s->pb2].len, &px); x = &px; }
+		else if(!x->ok){ ncand ++; continue; }
+		else if(x->score < par->min_score || x->mat < x->aln * par->min_id) continue;
+		if(!x->ok) continue;
+		if(hit_rules(par, alen, rs->reads.a[s->pb2].len, r->rd_id, s->pb2, x, &bcov, nbest, &ncand, NULL) == 2) return (long)i;
+	}
+	return (long)i;
+}
+
 /* sort (candidate, pair) records by ol descending with the reference permutation (the payload rides along) */
 static void ref_sort_pairs_desc(u64 *c, u32 *cp, size_t n){
 	typedef struct { u64 v; u32 idx; u32 pad; } rec_t; size_t i;
@@ -865,9 +898,15 @@ static void batch_compute(wz_t *z, batch_t *b){
 			VEC(zmo_task_t) tk; zmo_record_t *recs; u32 *cig; size_t cap;
 			vec_init(tk);
 			for(i=0;i<nr;i++){
-				size_t got = 0;
+				size_t got = 0, lim = sv[i].n;
 				if(pos[i] < 0) continue;
-				for(k=(size_t)pos[i];k<sv[i].n&&got<chunk;k++){
+				if(z->wave_predict >= 0){
+					/* up to the seed at which the walk is predicted to stop, plus a margin for alignments that fail or end short; never fewer than what
+					 * the dry walk is waiting for */
+					const long ps = predicted_stop(z, b, &b->reads.a[i], &sv[i]);
+					lim = (size_t)(ps < pos[i]? pos[i] : ps) + 1 + (size_t)z->wave_predict;
+				}
+				for(k=(size_t)pos[i];k<sv[i].n&&k<lim&&got<chunk;k++){
 					const seed_t *sd = &sv[i].a[k]; zmo_task_t t;
 					if(sd->closed || b->pres[sd->cand_idx]) continue;
 					t.pair_idx = sd->cand_idx; t.dir = sd->dir; vec_push(tk, t); got ++;
@@ -1224,8 +1263,9 @@ wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	if(z->depth < 1) z->depth = 1;
 	if(z->depth > WZ_MAX_CTX) z->depth = WZ_MAX_CTX;
 	z->call_pairs = (env = getenv("ZMO_CALL_PAIRS"))? atoi(env) : 0;     /* test hook: pairs per device call (0 = the library's limits) */
-	z->wave_margin = (env = getenv("ZMO_WAVE0"))? atoi(env) : 8;       /* seeds per read in the first DP wave (doubles per wave); < 0: align every seed up front */
+	z->wave_margin = (env = getenv("ZMO_WAVE0"))? atoi(env) : 32;      /* most seeds of a read in the first DP wave (x ZMO_WAVE_GROWTH per wave); < 0: align every seed up front.  cfg2: 8 without the prediction below */
 	z->wave_growth = (env = getenv("ZMO_WAVE_GROWTH"))? atoi(env) : 4; if(z->wave_growth < 2) z->wave_growth = 2;
+	z->wave_predict = (env = getenv("ZMO_WAVE_PREDICT"))? atoi(env) : 2;      /* >= 0: a wave aligns a read's seeds up to the predicted end of its walk + this margin (predict_rec); -1: fixed chunk per read.  cfg2: 85,432 -> 72,108 alignments issued for 64,797 consumed, 834 -> 761 ms per shard */
 	z->drain_div = (env = getenv("ZMO_DRAIN_DIV"))? atoi(env) : z->depth; if(z->drain_div < 1) z->drain_div = 1;
 	z->drain_min = (env = getenv("ZMO_DRAIN_MIN"))? atoi(env) : 48; if(z->drain_min < 1) z->drain_min = 1;
 	z->ramp = (env = getenv("ZMO_RAMP"))? atoi(env) : 96;     /* first batch size of the pipeline ramp (doubles per batch up to ZMO_BATCH_READS); 0 = off.  cfg2: 1,025 -> 938 ms per shard */
@@ -1343,7 +1383,7 @@ wz_session_t* wz_fork(const wz_session_t *S0, int device, int *rc_out){
 	*rc_out = 0;
 	z->rs = z0->rs; z->par = z0->par;      /* reads: shared pointers, never written after wz_open */
 	z->batch_reads = z0->batch_reads; z->batch_pairs = z0->batch_pairs; z->depth = z0->depth; z->call_pairs = z0->call_pairs;
-	z->wave_margin = z0->wave_margin; z->wave_growth = z0->wave_growth; z->ramp = z0->ramp; z->drain_div = z0->drain_div; z->drain_min = z0->drain_min;
+	z->wave_margin = z0->wave_margin; z->wave_growth = z0->wave_growth; z->wave_predict = z0->wave_predict; z->ramp = z0->ramp; z->drain_div = z0->drain_div; z->drain_min = z0->drain_min;
 	for(q=0;q<WZ_MAX_CTX;q++) pthread_mutex_init(&z->dev_mu[q], NULL);
 	pthread_mutex_init(&z->stat_mu, NULL);
 	z->masked = calloc(n + 1, 1); z->rdcovs = calloc(n + 1, sizeof(u32)); u64set_init(&z->closed);
