@@ -480,7 +480,8 @@ typedef struct {
 	struct { u8 *base; size_t cap, used, want; } pin[WZ_MAX_CTX];
 	pthread_mutex_t dev_mu[WZ_MAX_CTX];  /* one device call at a time per context */
 	pthread_mutex_t stat_mu;
-	u64 n_waves, n_wave_tasks; int wave_margin, wave_growth, wave_predict, ramp, drain_div, drain_min;
+	u64 n_waves, n_wave_tasks; int wave_margin, wave_growth, wave_predict, wave_predict_b, ramp, drain_div, drain_min;
+	u64 wv_tasks[8], wv_reads[8], wv_count[8];      /* ZMO_WAVE_DEBUG: tasks / reads / launches per DP wave index */
 } wz_t;
 
 static double now_s(void){ struct timeval tv; gettimeofday(&tv, NULL); return tv.tv_sec + 1e-6 * tv.tv_usec; }
@@ -722,19 +723,20 @@ static void predict_rec(const batch_t *b, const seed_t *s, int l1, int l2, zmo_r
 }
 /* dry walk in which a missing alignment is replaced by its prediction: index of the seed at which the walk is predicted to stop (the number of
  * seeds if it is predicted to run through).  The DP wave aligns the missing seeds up to there plus a margin, instead of a fixed number per read. */
-static long predicted_stop(const wz_t *z, const batch_t *b, const bread_t *r, const seedv *sv){
+static long predicted_stop(const wz_t *z, const batch_t *b, const bread_t *r, const seedv *sv, int *why){      /* *why: 0 the walk runs through, 1 the read is predicted contained, 2 enough dovetail hits */
 	const zparams_t *par = &z->par; const readset_t *rs = &z->rs; u32 ncand = par->ncand, bcov = r->bcov0, nbest = read_nbest(z, r->rd_id); size_t i;
 	int alen = rs->reads.a[r->rd_id].len;
+	*why = 0;
 	if(bcov >= nbest) return 0;
 	for(i=0;i<sv->n&&i<ncand;i++){
-		const seed_t *s = &sv->a[i]; const zmo_record_t *x; zmo_record_t px;
+		const seed_t *s = &sv->a[i]; const zmo_record_t *x; zmo_record_t px; u32 bc0 = bcov;
 		if(s->closed){ ncand ++; continue; }
 		x = b->pres[s->cand_idx];
 		if(x == NULL){ predict_rec(b, s, alen, rs->reads.a[s->pb2].len, &px); x = &px; }
 		else if(!x->ok){ ncand ++; continue; }
 		else if(x->score < par->min_score || x->mat < x->aln * par->min_id) continue;
 		if(!x->ok) continue;
-		if(hit_rules(par, alen, rs->reads.a[s->pb2].len, r->rd_id, s->pb2, x, &bcov, nbest, &ncand, NULL) == 2) return (long)i;
+		if(hit_rules(par, alen, rs->reads.a[s->pb2].len, r->rd_id, s->pb2, x, &bcov, nbest, &ncand, NULL) == 2){ *why = (bcov > bc0 && bcov >= nbest)? 2 : 1; return (long)i; }
 	}
 	return (long)i;
 }
@@ -903,8 +905,8 @@ static void batch_compute(wz_t *z, batch_t *b){
 				if(z->wave_predict >= 0){
 					/* up to the seed at which the walk is predicted to stop, plus a margin for alignments that fail or end short; never fewer than what
 					 * the dry walk is waiting for */
-					const long ps = predicted_stop(z, b, &b->reads.a[i], &sv[i]);
-					lim = (size_t)(ps < pos[i]? pos[i] : ps) + 1 + (size_t)z->wave_predict;
+					int why = 0; const long ps = predicted_stop(z, b, &b->reads.a[i], &sv[i], &why);
+					lim = (size_t)(ps < pos[i]? pos[i] : ps) + 1 + (size_t)(why == 2? z->wave_predict_b : z->wave_predict);
 				}
 				for(k=(size_t)pos[i];k<sv[i].n&&k<lim&&got<chunk;k++){
 					const seed_t *sd = &sv[i].a[k]; zmo_task_t t;
@@ -913,7 +915,7 @@ static void batch_compute(wz_t *z, batch_t *b){
 				}
 			}
 			if(tk.n == 0){ vec_free(tk); break; }
-			pthread_mutex_lock(&z->stat_mu); z->n_tasks += tk.n; pthread_mutex_unlock(&z->stat_mu);
+			{ size_t nrd = 0; for(i=0;i<nr;i++) if(pos[i] >= 0) nrd ++; pthread_mutex_lock(&z->stat_mu); z->n_tasks += tk.n; { const int wi = wave < 7? wave : 7; z->wv_tasks[wi] += tk.n; z->wv_reads[wi] += nrd; z->wv_count[wi] ++; } pthread_mutex_unlock(&z->stat_mu); }
 			{
 				/* results land in the context's page-locked arena (or, if it is full, in pageable memory until the next batch has grown it): they
 				 * stay valid until the batch has been replayed */
@@ -1265,7 +1267,8 @@ wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	z->call_pairs = (env = getenv("ZMO_CALL_PAIRS"))? atoi(env) : 0;     /* test hook: pairs per device call (0 = the library's limits) */
 	z->wave_margin = (env = getenv("ZMO_WAVE0"))? atoi(env) : 32;      /* most seeds of a read in the first DP wave (x ZMO_WAVE_GROWTH per wave); < 0: align every seed up front.  cfg2: 8 without the prediction below */
 	z->wave_growth = (env = getenv("ZMO_WAVE_GROWTH"))? atoi(env) : 4; if(z->wave_growth < 2) z->wave_growth = 2;
-	z->wave_predict = (env = getenv("ZMO_WAVE_PREDICT"))? atoi(env) : 2;      /* >= 0: a wave aligns a read's seeds up to the predicted end of its walk + this margin (predict_rec); -1: fixed chunk per read.  cfg2: 85,432 -> 72,108 alignments issued for 64,797 consumed, 834 -> 761 ms per shard */
+	z->wave_predict = (env = getenv("ZMO_WAVE_PREDICT"))? atoi(env) : 2;
+	z->wave_predict_b = (env = getenv("ZMO_WAVE_PREDICT_B"))? atoi(env) : z->wave_predict; if(z->wave_predict_b < 0) z->wave_predict_b = 0;      /* margin when the walk is predicted to end on the dovetail count */      /* >= 0: a wave aligns a read's seeds up to the predicted end of its walk + this margin (predict_rec); -1: fixed chunk per read.  cfg2: 85,432 -> 72,108 alignments issued for 64,797 consumed, 834 -> 761 ms per shard */
 	z->drain_div = (env = getenv("ZMO_DRAIN_DIV"))? atoi(env) : z->depth; if(z->drain_div < 1) z->drain_div = 1;
 	z->drain_min = (env = getenv("ZMO_DRAIN_MIN"))? atoi(env) : 48; if(z->drain_min < 1) z->drain_min = 1;
 	z->ramp = (env = getenv("ZMO_RAMP"))? atoi(env) : 96;     /* first batch size of the pipeline ramp (doubles per batch up to ZMO_BATCH_READS); 0 = off.  cfg2: 1,025 -> 938 ms per shard */
@@ -1360,12 +1363,14 @@ int wz_run_fp(wz_session_t *S, int n_job, int i_job, FILE *fp){
 	for(k=0;k<S->closed0.n;k++) u64set_add(&z->closed, S->closed0.a[k]);
 	if(z->rdhits){ for(k=0;k<n;k++) vec_free(z->rdhits[k]); free(z->rdhits); z->rdhits = NULL; }
 	z->n_records = z->aln_cols = z->n_tasks = z->n_tasks_used = z->n_pairs_seeded = z->n_batches = z->n_reads_batched = z->n_reads_late_masked = z->n_pairs_late_masked = z->n_waves = z->n_wave_tasks = 0; z->t_dev = z->t_replay = 0;
+	memset(z->wv_tasks, 0, sizeof(z->wv_tasks)); memset(z->wv_reads, 0, sizeof(z->wv_reads)); memset(z->wv_count, 0, sizeof(z->wv_count));
 	z->out = fp;
 	if(z->obuf == NULL){ z->obuf_cap = 8u << 20; z->obuf = malloc(z->obuf_cap); }
 	t0 = now_s();
 	run_overlap(z);
 	fflush(fp);
 	S->last_overlap_s = now_s() - t0;
+	if(getenv("ZMO_WAVE_DEBUG")){ int w; for(w=0;w<8;w++) if(z->wv_count[w]) fprintf(stderr, "[wtzmo-b200] DP wave %d: %llu launches, %llu reads, %llu alignments\n", w, (unsigned long long)z->wv_count[w], (unsigned long long)z->wv_reads[w], (unsigned long long)z->wv_tasks[w]); }
 	return 0;
 }
 int wz_run(wz_session_t *S, int n_job, int i_job, const char *out_path){
@@ -1383,7 +1388,7 @@ wz_session_t* wz_fork(const wz_session_t *S0, int device, int *rc_out){
 	*rc_out = 0;
 	z->rs = z0->rs; z->par = z0->par;      /* reads: shared pointers, never written after wz_open */
 	z->batch_reads = z0->batch_reads; z->batch_pairs = z0->batch_pairs; z->depth = z0->depth; z->call_pairs = z0->call_pairs;
-	z->wave_margin = z0->wave_margin; z->wave_growth = z0->wave_growth; z->wave_predict = z0->wave_predict; z->ramp = z0->ramp; z->drain_div = z0->drain_div; z->drain_min = z0->drain_min;
+	z->wave_margin = z0->wave_margin; z->wave_growth = z0->wave_growth; z->wave_predict = z0->wave_predict; z->wave_predict_b = z0->wave_predict_b; z->ramp = z0->ramp; z->drain_div = z0->drain_div; z->drain_min = z0->drain_min;
 	for(q=0;q<WZ_MAX_CTX;q++) pthread_mutex_init(&z->dev_mu[q], NULL);
 	pthread_mutex_init(&z->stat_mu, NULL);
 	z->masked = calloc(n + 1, 1); z->rdcovs = calloc(n + 1, sizeof(u32)); u64set_init(&z->closed);
