@@ -210,7 +210,7 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 	CUDA_TRY(cudaSetDevice(c->device));
 	/* host: items and per-item cigar regions */
 	std::vector<AlnTask> ht(nt); std::vector<WItem> items; std::vector<unsigned long long> icig, istep, ibound;
-	unsigned long long cig_words = 0, nsteps64 = 0, wb_rows = 0, wb_cols = 0; int max_rows = 16;
+	unsigned long long cig_words = 0, nsteps64 = 0; int max_rows = 16;
 	for(uint32_t t = 0; t < nt; t++){
 		if(tasks[t].pair_idx >= SL.np || tasks[t].dir > 1) return zmo_set_err(ZMO_ERR_ARG, "task %u out of range", t);
 		const zmo_pairseed_t &ps = SL.h_seeds[tasks[t].pair_idx]; const uint32_t d = tasks[t].dir;
@@ -219,7 +219,7 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 			WItem it; it.task = t; it.win = ps.win_off[d] + k; items.push_back(it);
 			const int s0 = SL.h_wspan[3 * (size_t)it.win], s1 = SL.h_wspan[3 * (size_t)it.win + 1], na = SL.h_wspan[3 * (size_t)it.win + 2];
 			icig.push_back(cig_words); cig_words += (unsigned long long)(s0 + s1 + 16 + 2 * na);
-			istep.push_back(nsteps64); nsteps64 += (unsigned long long)na; ibound.push_back((unsigned long long)(s1 + 16)); wb_cols += (unsigned long long)(s0 + 16) + 16ull * (unsigned long long)na;      /* rows of all bridges of a window <= its span on c; columns <= its span on q (+ w per bridge, below) */
+			istep.push_back(nsteps64); nsteps64 += (unsigned long long)na; ibound.push_back((unsigned long long)(s1 + 16));      /* rows of all bridges of a window <= its span on c */
 			if(s1 + 8 > max_rows) max_rows = s1 + 8;
 			if(s0 + 8 > max_rows) max_rows = s0 + 8;
 		}
@@ -249,7 +249,6 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 		wb_chunk.push_back(nitems); if(acc > wb_scr_cap) wb_scr_cap = acc;
 		wb_scr_cap += 1024;
 	}
-	(void)wb_rows; (void)wb_cols;
 	/* with the bridge pipeline k_window_align only sees the windows that pipeline leaves out: a quarter of the executors (all of them are used if needed, just in more rounds) */
 	const int wgrid = (int)std::min<uint64_t>((nitems + WA_WARPS - 1) / WA_WARPS + 1, (uint64_t)c->n_sm * (use_wb? 2 : 8));
 	const int wcol = std::min(max_rows + c->par.w, 2 * c->par.w + 1);
