@@ -17,7 +17,8 @@ seed 20240601+cfg).
   cpu_baseline : the unmodified reference binary (oracle/_ref/wtzmo -t <cores>) on a bounded sub-shard
   sub      : (N=1) short measurements of the other single-GPU configurations: cfg1 (configs[0]) and cfg3s (configs[2]
              shape, dot-matrix mode), each with its own roofline entry and golden parity check
-  cli_whole_job : (N=1) wall time of the product binary on the whole workload (`-P 1`), process start to exit
+  cli_whole_job : (N=1) wall time of the product binary on the whole workload (`-P 1`), process start to exit (and once more in the
+                  16-column mode that replaces the pipeline's `| cut -f1-16`)
 
 `--impl reference` times only the reference CPU binary on the same configuration: every step is the SAME shard
 (`-P shards -p i`) a step of our arm processes.
@@ -280,12 +281,15 @@ def sub_record(host, name, tmpdir, peak, peaks_found, steps=2):
             "parity_checked": bool(par.get("checked") and par.get("ok")), "parity": par, "fasta_load_sort_s": t_open}
 
 
-def cli_whole_job(fa, wl, tmpdir):
-    """the product binary as a user runs it: one process, the whole job (`-P 1`), cold start (context creation, first-batch allocations) included"""
+def cli_whole_job(fa, wl, tmpdir, cols16=False):
+    """the product binary as a user runs it: one process, the whole job (`-P 1`), cold start (context creation, first-batch allocations) included;
+    cols16: ZMO_OVL_COLS=16, the file the pipeline makes with `| cut -f1-16` (smartdenovo.pl:58) written directly, no CIGAR text formatted or copied"""
     exe = os.path.join(REPO, "smartdenovo_b200", "bin", "wtzmo")
     out = os.path.join(tmpdir, "cli_job.ovl")
     stats = os.path.join(tmpdir, "cli_job.stats.json")
     env = dict(os.environ, ZMO_STATS=stats)
+    if cols16:
+        env["ZMO_OVL_COLS"] = "16"
     t0 = time.perf_counter()
     r = subprocess.run([exe, "-t", "1", "-i", fa, "-f", "-o", out] + wl["flags"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
     wall = time.perf_counter() - t0
@@ -295,7 +299,7 @@ def cli_whole_job(fa, wl, tmpdir):
     for f in (out, out + ".contained", stats):
         if os.path.exists(f):
             os.remove(f)
-    return {"command": "wtzmo -t 1 -i reads.fa -fo out.ovl %s" % " ".join(wl["flags"]), "process_wall_s": wall, "overlap_phase_s": s["overlap_s"], "records": s["records"],
+    return {"command": "%swtzmo -t 1 -i reads.fa -fo out.ovl %s" % ("ZMO_OVL_COLS=16 " if cols16 else "", " ".join(wl["flags"])), "process_wall_s": wall, "overlap_phase_s": s["overlap_s"], "records": s["records"],
             "aligned_bp": s["aligned_cols"], "gbp_per_s_over_process_wall": s["aligned_cols"] / wall / 1e9, "gbp_per_s_over_overlap_phase": s["aligned_cols"] / s["overlap_s"] / 1e9,
             "note": "one job: fewer records than the sum of the -P 10 shards by design (a pair is found from one side only)"}
 
@@ -470,6 +474,7 @@ def main():
                 line["sub"][name] = {"error": str(e)[:300]}
         try:
             line["cli_whole_job"] = cli_whole_job(fa, wl, tmpdir)
+            line["cli_whole_job_16_columns"] = cli_whole_job(fa, wl, tmpdir, cols16=True)
         except Exception as e:   # noqa: BLE001
             line["cli_whole_job"] = {"error": str(e)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(REPO, "oracle", "_ref", "wtzmo")):

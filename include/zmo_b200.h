@@ -122,6 +122,9 @@ int zmo_pair_align(zmo_ctx *ctx, int slot, const zmo_task_t *tasks, uint32_t nt,
  * per op), formatted on the device: recs[i].cigar_off / n_cigar are the byte offset / byte length in cigar_text, sizes in bytes. */
 int zmo_pair_align_text(zmo_ctx *ctx, int slot, const zmo_task_t *tasks, uint32_t nt,
                         zmo_record_t *recs, char *cigar_text, uint64_t text_cap, uint64_t *text_needed);
+/* Same, records only (cigar_off = n_cigar = 0): for consumers that drop the CIGAR column -- the pipeline's `wtzmo ... -fo - | cut -f1-16`
+ * (smartdenovo.pl:58) and the `.ovl` readers of wtclp / wtlay, which parse columns 1-12 / 1-13 (wtclp.c:123-152, wtlay.h:243-268). */
+int zmo_pair_align_records(zmo_ctx *ctx, int slot, const zmo_task_t *tasks, uint32_t nt, zmo_record_t *recs);
 
 /* ---- dot-matrix mode: replaces dot_matrix_align_hzmps for one pair (wtzmo.c:853-863) --------- */
 typedef struct { uint32_t n_zpair; int32_t score, qb, qe, tb, te, strand; } zmo_dotres_t;

@@ -481,6 +481,7 @@ typedef struct {
 	pthread_mutex_t dev_mu[WZ_MAX_CTX];  /* one device call at a time per context */
 	pthread_mutex_t stat_mu;
 	u64 n_waves, n_wave_tasks; int wave_margin, wave_growth, wave_predict, wave_predict_b, ramp, drain_div, drain_min;
+	int no_cigar;      /* ZMO_OVL_COLS=16: the 16 columns `cut -f1-16` keeps (smartdenovo.pl:58); no CIGAR text is formatted, copied or printed */
 	u64 wv_tasks[8], wv_reads[8], wv_count[8];      /* ZMO_WAVE_DEBUG: tasks / reads / launches per DP wave index */
 } wz_t;
 
@@ -518,11 +519,14 @@ static void flush_read(wz_t *z, readout_t *ro, int defer_masks){
 		x1 = imin(h->tb, h->qb); x2 = imin(l1 - h->te, l2 - h->qe);
 		if(x1 + x2 <= z->par.max_unalign_in_dovetail){ z->rdcovs[h->pb1] ++; z->rdcovs[h->pb2] ++; }
 		ob_reserve(z, 512 + strlen(rs->reads.a[h->pb1].name) + strlen(rs->reads.a[h->pb2].name) + (size_t)h->n_cigar + 16);
-		z->obuf_n += sprintf(z->obuf + z->obuf_n, "%s\t%c\t%d\t%d\t%d\t%s\t%c\t%d\t%d\t%d\t%d\t%0.3f\t%d\t%d\t%d\t%d\t", rs->reads.a[h->pb1].name, '+', l1, h->tb, h->te,
+		z->obuf_n += sprintf(z->obuf + z->obuf_n, "%s\t%c\t%d\t%d\t%d\t%s\t%c\t%d\t%d\t%d\t%d\t%0.3f\t%d\t%d\t%d\t%d", rs->reads.a[h->pb1].name, '+', l1, h->tb, h->te,
 			rs->reads.a[h->pb2].name, "+-"[h->dir2], l2, h->qb, h->qe, h->score, 1.0 * h->mat / h->aln, h->mat, h->mis, h->ins, h->del);
 		p = z->obuf + z->obuf_n;
-		if(h->has_cigar){ memcpy(p, h->cigar, h->n_cigar); p += h->n_cigar; }      /* kswx_cigar2string (kswx.h:1093-1120), formatted by k_cig_text */
-		else { *p++ = '0'; *p++ = 'M'; }
+		if(!z->no_cigar){
+			*p++ = '\t';
+			if(h->has_cigar){ memcpy(p, h->cigar, h->n_cigar); p += h->n_cigar; }      /* kswx_cigar2string (kswx.h:1093-1120), formatted by k_cig_text */
+			else { *p++ = '0'; *p++ = 'M'; }
+		}
 		*p++ = '\n';
 		z->obuf_n = p - z->obuf;
 		z->n_records ++;
@@ -919,7 +923,7 @@ static void batch_compute(wz_t *z, batch_t *b){
 			{
 				/* results land in the context's page-locked arena (or, if it is full, in pageable memory until the next batch has grown it): they
 				 * stay valid until the batch has been replayed */
-				const int ps = b->ci; const size_t want = wave_text_words(z, b, tk.a, tk.n), rbytes = (tk.n * sizeof(zmo_record_t) + 63) & ~(size_t)63;
+				const int ps = b->ci; const size_t want = z->no_cigar? 16 : wave_text_words(z, b, tk.a, tk.n), rbytes = (tk.n * sizeof(zmo_record_t) + 63) & ~(size_t)63;
 				int pinned = z->pin[ps].used + rbytes + want * 4 <= z->pin[ps].cap;
 				if(pinned){ recs = (zmo_record_t*)(z->pin[ps].base + z->pin[ps].used); cig = (u32*)(z->pin[ps].base + z->pin[ps].used + rbytes); cap = want; z->pin[ps].used += (rbytes + want * 4 + 63) & ~(size_t)63; }
 				else {
@@ -927,7 +931,8 @@ static void batch_compute(wz_t *z, batch_t *b){
 					if(z->pin[ps].want < 2 * (z->pin[ps].used + rbytes + want * 4)) z->pin[ps].want = 2 * (z->pin[ps].used + rbytes + want * 4);
 				}
 				pthread_mutex_lock(mu);
-				rc = zmo_pair_align_text(ctx, b->slot, tk.a, (u32)tk.n, recs, (char*)cig, cap * 4, &need);
+				if(z->no_cigar) rc = zmo_pair_align_records(ctx, b->slot, tk.a, (u32)tk.n, recs);
+				else rc = zmo_pair_align_text(ctx, b->slot, tk.a, (u32)tk.n, recs, (char*)cig, cap * 4, &need);
 				if(rc == ZMO_ERR_CAPACITY && need > cap * 4){
 					/* the guess was too small: the text of this wave goes to pageable memory, the wave is run again */
 					cap = (need + need / 4) / 4 + 16;
@@ -962,7 +967,8 @@ static void demand_wave(wz_t *z, batch_t *b, bread_t *br, readout_t *ro){
 	if(tk.n == 0){ fprintf(stderr, "wtzmo(b200): internal error: empty demand wave\n"); exit(4); }
 	recs = malloc(tk.n * sizeof(zmo_record_t)); cap = 4096 * tk.n + 65536; cig = malloc(cap * 4);
 	pthread_mutex_lock(&z->dev_mu[b->ci]);
-	rc = zmo_pair_align_text(z->ctxs[b->ci], b->slot, tk.a, (u32)tk.n, recs, (char*)cig, cap * 4, &need);
+	if(z->no_cigar) rc = zmo_pair_align_records(z->ctxs[b->ci], b->slot, tk.a, (u32)tk.n, recs);
+	else rc = zmo_pair_align_text(z->ctxs[b->ci], b->slot, tk.a, (u32)tk.n, recs, (char*)cig, cap * 4, &need);
 	if(rc == ZMO_ERR_CAPACITY && need > cap * 4){ cap = need / 4 + 16; cig = realloc(cig, cap * 4); rc = zmo_pair_align_text(z->ctxs[b->ci], b->slot, tk.a, (u32)tk.n, recs, (char*)cig, cap * 4, &need); }
 	pthread_mutex_unlock(&z->dev_mu[b->ci]);
 	if(rc) die_zmo("zmo_pair_align (demand wave)");
@@ -1149,6 +1155,7 @@ static int usage(void){
 	" -v          Verbose (accepted, ignored)\n"
 	"Environment: ZMO_DEVICE (GPU ordinal, default 0; under torchrun LOCAL_RANK), ZMO_GPUS=n|all (GPU g runs job -P P*n -p p*n+g, records gathered\n"
 	"             over NCCL and written in job order), ZMO_DEVICES=a,b,.. (their ordinals), ZMO_BATCH_READS, ZMO_BATCH_PAIRS, ZMO_STATS=file;\n"
+	"             ZMO_OVL_COLS=16 (print the 16 columns `cut -f1-16` keeps: no CIGAR column);\n"
 	"             A/B switches: ZMO_WA_BRIDGE=0 (window alignment by the sequential kernel), ZMO_SEED_LANES=G (G pairs per warp in the seeding kernel)\n"
 	"\n");
 	return 1;
@@ -1267,6 +1274,7 @@ wz_session_t* wz_open(int argc, char **argv, int *rc_out){
 	z->call_pairs = (env = getenv("ZMO_CALL_PAIRS"))? atoi(env) : 0;     /* test hook: pairs per device call (0 = the library's limits) */
 	z->wave_margin = (env = getenv("ZMO_WAVE0"))? atoi(env) : 32;      /* most seeds of a read in the first DP wave (x ZMO_WAVE_GROWTH per wave); < 0: align every seed up front.  cfg2: 8 without the prediction below */
 	z->wave_growth = (env = getenv("ZMO_WAVE_GROWTH"))? atoi(env) : 4; if(z->wave_growth < 2) z->wave_growth = 2;
+	z->no_cigar = (env = getenv("ZMO_OVL_COLS")) && atoi(env) == 16;
 	z->wave_predict = (env = getenv("ZMO_WAVE_PREDICT"))? atoi(env) : 2;
 	z->wave_predict_b = (env = getenv("ZMO_WAVE_PREDICT_B"))? atoi(env) : z->wave_predict; if(z->wave_predict_b < 0) z->wave_predict_b = 0;      /* margin when the walk is predicted to end on the dovetail count */      /* >= 0: a wave aligns a read's seeds up to the predicted end of its walk + this margin (predict_rec); -1: fixed chunk per read.  cfg2: 85,432 -> 72,108 alignments issued for 64,797 consumed, 834 -> 761 ms per shard */
 	z->drain_div = (env = getenv("ZMO_DRAIN_DIV"))? atoi(env) : z->depth; if(z->drain_div < 1) z->drain_div = 1;
@@ -1388,7 +1396,7 @@ wz_session_t* wz_fork(const wz_session_t *S0, int device, int *rc_out){
 	*rc_out = 0;
 	z->rs = z0->rs; z->par = z0->par;      /* reads: shared pointers, never written after wz_open */
 	z->batch_reads = z0->batch_reads; z->batch_pairs = z0->batch_pairs; z->depth = z0->depth; z->call_pairs = z0->call_pairs;
-	z->wave_margin = z0->wave_margin; z->wave_growth = z0->wave_growth; z->wave_predict = z0->wave_predict; z->wave_predict_b = z0->wave_predict_b; z->ramp = z0->ramp; z->drain_div = z0->drain_div; z->drain_min = z0->drain_min;
+	z->wave_margin = z0->wave_margin; z->wave_growth = z0->wave_growth; z->wave_predict = z0->wave_predict; z->wave_predict_b = z0->wave_predict_b; z->no_cigar = z0->no_cigar; z->ramp = z0->ramp; z->drain_div = z0->drain_div; z->drain_min = z0->drain_min;
 	for(q=0;q<WZ_MAX_CTX;q++) pthread_mutex_init(&z->dev_mu[q], NULL);
 	pthread_mutex_init(&z->stat_mu, NULL);
 	z->masked = calloc(n + 1, 1); z->rdcovs = calloc(n + 1, sizeof(u32)); u64set_init(&z->closed);

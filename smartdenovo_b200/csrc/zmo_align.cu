@@ -192,15 +192,20 @@ static int run_dp_lists(zmo_ctx *c, const JobLists &L, const uint32_t *n, const 
 }
 
 /* res index -> position in the concatenated job array [ext_w | ext_n | glb_w | glb_n] is the identity by construction */
-static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32_t nt, zmo_record_t *recs, uint32_t *cigars, uint64_t cigar_cap, uint64_t *cigar_needed, bool as_text);
+static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32_t nt, zmo_record_t *recs, uint32_t *cigars, uint64_t cigar_cap, uint64_t *cigar_needed, int out_mode);
 extern "C" int zmo_pair_align(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32_t nt, zmo_record_t *recs, uint32_t *cigars, uint64_t cigar_cap, uint64_t *cigar_needed){
-	return pair_align_impl(c, slot, tasks, nt, recs, cigars, cigar_cap, cigar_needed, false);
+	return pair_align_impl(c, slot, tasks, nt, recs, cigars, cigar_cap, cigar_needed, 0);
 }
 extern "C" int zmo_pair_align_text(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32_t nt, zmo_record_t *recs, char *cigar_text, uint64_t text_cap, uint64_t *text_needed){
-	return pair_align_impl(c, slot, tasks, nt, recs, (uint32_t*)cigar_text, text_cap, text_needed, true);
+	return pair_align_impl(c, slot, tasks, nt, recs, (uint32_t*)cigar_text, text_cap, text_needed, 1);
 }
-/* cigar_cap / *cigar_needed count ops (binary) or bytes (text) */
-static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32_t nt, zmo_record_t *recs, uint32_t *cigars, uint64_t cigar_cap, uint64_t *cigar_needed, bool as_text){
+/* records only: what a consumer that drops the CIGAR column needs (`wtzmo ... | cut -f1-16`, smartdenovo.pl:58); no CIGAR text is formatted or copied */
+extern "C" int zmo_pair_align_records(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32_t nt, zmo_record_t *recs){
+	return pair_align_impl(c, slot, tasks, nt, recs, nullptr, 0, nullptr, 2);
+}
+/* out_mode 0: binary ops, 1: text, 2: records only; cigar_cap / *cigar_needed count ops (binary) or bytes (text) */
+static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32_t nt, zmo_record_t *recs, uint32_t *cigars, uint64_t cigar_cap, uint64_t *cigar_needed, int out_mode){
+	const bool as_text = out_mode == 1, no_cigar = out_mode == 2;
 	if(!c || (nt && (!tasks || !recs))) return zmo_set_err(ZMO_ERR_ARG, "null argument");
 	if(slot < 0 || slot > 1) return zmo_set_err(ZMO_ERR_ARG, "slot must be 0 or 1");
 	if(cigar_needed) *cigar_needed = 0;
@@ -364,7 +369,7 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 		unsigned long long total = 0;
 		CUDA_TRY(cudaMemcpyAsync(&total, d_ooff + nt, 8, cudaMemcpyDeviceToHost, c->stream));
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
-		if(!as_text){
+		if(!as_text && !no_cigar){
 			if(cigar_needed) *cigar_needed = total;
 			if(total > cigar_cap) return zmo_set_err(ZMO_ERR_CAPACITY, "cigar buffer too small: need %llu", total);
 		}
@@ -381,7 +386,7 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 			unsigned long long ow = 0;
 			if(int rc = refine_records(c, SL, d_tasks, nt, d_recs, c->s5.as<uint32_t>(), A, &ow)) return rc;
 			d_final_ops = c->s6.as<uint32_t>(); total = ow;
-			if(!as_text){
+			if(!as_text && !no_cigar){
 				if(cigar_needed) *cigar_needed = total;
 				if(total > cigar_cap) return zmo_set_err(ZMO_ERR_CAPACITY, "cigar buffer too small: need %llu", total);
 			}
@@ -413,12 +418,14 @@ static int pair_align_impl(zmo_ctx *c, int slot, const zmo_task_t *tasks, uint32
 			c->counters[6] += (size_t)nt * sizeof(zmo_record_t) + tbytes;
 			return 0;
 		}
+		if(no_cigar) total = 0;
 		{
 			StageTimer tm(c, ST_COPY);
 			CUDA_TRY(cudaMemcpyAsync(recs, d_recs, (size_t)nt * sizeof(zmo_record_t), cudaMemcpyDeviceToHost, c->stream));
 			if(total) CUDA_TRY(cudaMemcpyAsync(cigars, d_final_ops, total * 4, cudaMemcpyDeviceToHost, c->stream));
 		}
 		CUDA_TRY(cudaStreamSynchronize(c->stream));
+		if(no_cigar) for(uint32_t t = 0; t < nt; t++){ recs[t].cigar_off = 0; recs[t].n_cigar = 0; }
 		c->counters[6] += (size_t)nt * sizeof(zmo_record_t) + total * 4;
 		return 0;
 	}

@@ -49,6 +49,20 @@ def test_sw_small(tmp_path, gen_reads, oracle_bin):
     assert n > 100
 
 
+def test_ovl_16_columns_mode(tmp_path, gen_reads, oracle_bin):
+    """ZMO_OVL_COLS=16: the file the pipeline makes with `wtzmo ... -fo - | cut -f1-16` (smartdenovo.pl:58), written directly -- records only
+    through zmo_pair_align_records, no CIGAR text formatted or copied; with and without -n, and in dot-matrix mode (where column 17 is `0M`)"""
+    fa = str(tmp_path / "reads.fa")
+    subprocess.run([gen_reads, "-n", "200", "-L", "6000", "-G", "60000", "-s", "1", "-o", fa], check=True)
+    for extra in (["-k", "16", "-s", "200", "-m", "0.6"], ["-k", "16", "-s", "200", "-m", "0.6", "-n"], ["-k", "16", "-z", "10", "-Z", "16", "-U", "-1", "-m", "0.1", "-A", "1000"]):
+        _run(_checker(oracle_bin), fa, str(tmp_path / "ref.ovl"), extra)
+        _run(EXE, fa, str(tmp_path / "g16.ovl"), extra, env=dict(os.environ, ZMO_OVL_COLS="16"))
+        want = b"".join(b"\t".join(l.split(b"\t")[:16]) + b"\n" for l in open(tmp_path / "ref.ovl", "rb").read().splitlines())
+        got = open(tmp_path / "g16.ovl", "rb").read()
+        assert len(want) > 0 and got == want, extra
+        assert open(tmp_path / "ref.ovl.contained", "rb").read() == open(tmp_path / "g16.ovl.contained", "rb").read()
+
+
 def test_sw_small_batches(tmp_path, gen_reads, oracle_bin):
     """batch size 1 (== the reference's read-by-read order) and odd batch sizes give the same bytes"""
     for br in ("1", "7"):
