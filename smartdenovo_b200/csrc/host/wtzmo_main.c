@@ -882,10 +882,10 @@ static void batch_compute(wz_t *z, batch_t *b){
 	b->pres = calloc(b->pairs.n, sizeof(*b->pres)); b->pcig = calloc(b->pairs.n, sizeof(*b->pcig)); b->pdir = calloc(b->pairs.n, 1);
 	pin_arena_reset(z, b->ci);
 	/* DP waves: every read's seeds in the order the replay is predicted to walk them (build_seeds on the candidate list
-	 * as it was at batch build time); wave k aligns the next chunk (16, 32, 64, ... seeds) of every read whose DRY walk
-	 * over the results so far still stops at a missing alignment.  Most reads finish early (the first containing
-	 * candidate masks them, wtzmo.c:1079-1090), so this skips most of the speculative DP.  Whatever the real replay
-	 * still misses is computed on demand (demand_wave). */
+	 * as it was at batch build time); wave k aligns, for every read whose DRY walk over the results so far still stops at
+	 * a missing alignment, the missing seeds up to the PREDICTED end of the walk plus a margin (predicted_stop; at most
+	 * 32, 128, ... per read).  Most reads finish early (the first containing candidate masks them, wtzmo.c:1079-1090),
+	 * so this skips most of the speculative DP.  Whatever the real replay still misses is computed on demand (demand_wave). */
 	{
 		size_t nr = b->reads.n, k, chunk = z->wave_margin < 0? (size_t)1 << 30 : (size_t)(z->wave_margin > 0? z->wave_margin : 16); int wave = 0;
 		seedv *sv = calloc(nr + 1, sizeof(seedv)); long *pos = calloc(nr + 1, sizeof(long));
