@@ -1,5 +1,6 @@
 /*
- * TEST-ONLY host simulation of the whole pair-alignment stage (zmo_pair_align) for one (q, c, strand) task: k_window_align ->
+ * TEST-ONLY host simulation of the whole pair-alignment stage (zmo_pair_align) for one (q, c, strand) task: window alignment (the bridge-level
+ * pipeline of zmo_winbridge.cuh through tests/hostsim/wb_pipeline.h, k_window_align for -w beyond its ring) ->
  * k_plan -> DP executor kernels (four extension classes, two gap classes, run from sorted job lists with executor slabs) -> k_plan2 ->
  * right-extension jobs -> k_finish_size -> k_finish_warp -> optional -n refinement kernels.  The kernels are the
  * product's own source (smartdenovo_b200/csrc/zmo_*_kernels.cuh, zmo_winalign.cuh) compiled against tests/hostsim/emu/cuda_runtime.h;
@@ -16,6 +17,8 @@ int zmo_set_err(int code, const char *, ...){ return code; }
 namespace emu { Block *g_blk = nullptr; }
 #include "../../smartdenovo_b200/csrc/zmo_dp_kernels.cuh"
 #include "../../smartdenovo_b200/csrc/zmo_winalign.cuh"
+#include "../../smartdenovo_b200/csrc/zmo_winbridge.cuh"
+#include "wb_pipeline.h"
 #include "../../smartdenovo_b200/csrc/zmo_stitch_kernels.cuh"
 #include "../../smartdenovo_b200/csrc/zmo_refine_kernels.cuh"
 
@@ -103,7 +106,12 @@ extern "C" int sim_pair_align(const uint8_t *q, int qlen, const uint8_t *c, int 
 	const WItem *di = items.data(); const AlnTask *dt = &task; const zmo_pair_t *dp = &pair; const DevWin *dw = wins.data(); const DevZPair *da = an.data();
 	uint32_t *ar = arena.data(), *cgp = cig_arena.data(); const unsigned long long *dic = icig.data(); DevReg *dr = regs.data(); unsigned long long *cp = ctr;
 	TaskState *dts = ts.data(); DPJob *dj = jobs.data(); DPRes *dres = res.data();
-	if(nitems) emu::launch((unsigned)wgrid, 32 * WA_WARPS, [=](){ k_window_align(di, nitems, dt, dp, dw, da, R, A, ar, slab, max_rows, cgp, dic, dr, cp, 0, 1, nullptr, nullptr); });      /* the bridge pipeline (zmo_winbridge.cuh) leaves the same DevReg + CIGAR per window: tests/test_dp_hostsim.py::test_window_align_bridge_pipeline */
+	if(nitems && w >= 1 && w <= WB_MAX_W){
+		/* as the product: bridge-level pipeline (zmo_winbridge.cuh), k_window_align for the windows it leaves out */
+		unsigned long long cells = 0;
+		if(sim_wb_pipeline(di, nitems, dt, dp, dw, da, win, R, A, 2 * 10 + 2, dic, cgp, dr, 1ull << 40, &cells) < 0) return -2;
+		ctr[1] += cells;
+	} else if(nitems) emu::launch((unsigned)wgrid, 32 * WA_WARPS, [=](){ k_window_align(di, nitems, dt, dp, dw, da, R, A, ar, slab, max_rows, cgp, dic, dr, cp, 0, 1, nullptr, nullptr); });
 	stats[6] = 0; for(uint32_t i = 0; i < nitems; i++) stats[6] += regs[i].kept? 1 : 0;
 	JobLists L; L.cap = jcap;
 	for(int k = 0; k < 6; k++){ L.list[k] = dj + (size_t)k * jcap; L.cnt[k] = ctr + 10 + k; L.res_base[k] = (uint32_t)k * jcap; }

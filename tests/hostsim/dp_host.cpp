@@ -15,6 +15,7 @@ namespace emu { Block *g_blk = nullptr; }
 #include "../../smartdenovo_b200/csrc/zmo_dp_kernels.cuh"
 #include "../../smartdenovo_b200/csrc/zmo_winalign.cuh"
 #include "../../smartdenovo_b200/csrc/zmo_winbridge.cuh"
+#include "wb_pipeline.h"
 #include "../../smartdenovo_b200/csrc/zmo_stitch_kernels.cuh"
 #include "../../smartdenovo_b200/csrc/zmo_refine_kernels.cuh"
 
@@ -165,18 +166,21 @@ extern "C" int sim_window_align(const uint8_t *q, int qlen, const uint8_t *c, in
 /*
  * The same windows through the bridge-level pipeline (zmo_winbridge.cuh: k_wb_prep -> scan + sort (CUB in the product, std here) -> k_wb_sweep ->
  * k_wb_ends -> k_wb_walk -> k_wb_stitch, then k_window_align on the windows the pipeline left out), sized like pair_align_impl (zmo_align.cu).
- * copies > 1 repeats the window list so that the sweep runs several rounds of 32 bridges per warp.  *n_fallback = windows left to k_window_align.
+ * copies > 1 repeats the window list so that the sweep runs several rounds of 32 bridges per warp; copies = 0 runs one window per pass.  *n_fallback =
+ * windows left to k_window_align.  The orchestration between the kernels is tests/hostsim/wb_pipeline.h.
  */
 extern "C" int sim_window_align_bridge(const uint8_t *q, int qlen, const uint8_t *c, int clen, int dir, const int *win, int n_win0, const int *anc,
 		int w, int M, int X, int O, int E, int T, int zovl, float min_id, int copies, int acap, int *out, uint32_t *cig_out, int cig_cap, int *cig_n, int *n_fallback){
 	SimReads rd(q, qlen, c, clen); DevReads R = rd.dev();
 	AlnPar A; A.w = w; A.ew = 800; A.W = 3200; A.zovl = zovl; A.min_id = min_id; A.P.M = M; A.P.X = X; A.P.I = O; A.P.D = O; A.P.E = E; A.P.T = T;
 	if(w < 1 || w > WB_MAX_W) return -2;
+	unsigned long long budget = 1ull << 40;      /* copies = 0: one window per pass (the product sweeps a wave whose scratch bound exceeds its budget in several passes) */
+	if(copies <= 0){ budget = 1; copies = 1; }
 	const int n_win = n_win0 * copies;
-	std::vector<WItem> items(n_win); std::vector<DevWin> wins(n_win0); std::vector<DevZPair> an; std::vector<unsigned long long> icig(n_win), istep(n_win + 1);
+	std::vector<WItem> items(n_win); std::vector<DevWin> wins(n_win0); std::vector<DevZPair> an; std::vector<unsigned long long> icig(n_win);
 	AlnTask task; task.pair_idx = 0; task.dir = (uint32_t)dir; task.item_off = 0; task.n_item = (uint32_t)n_win;
 	zmo_pair_t pair; pair.qid = 0; pair.cid = 1;
-	unsigned long long cig_words = 0, nsteps64 = 0, wb_rows = 0, wb_cols = 0; int max_rows = 16, a0 = 0;
+	unsigned long long cig_words = 0; int a0 = 0;
 	for(int i = 0; i < n_win0; i++){
 		const int na = win[3 * i + 2];
 		DevWin W; memset(&W, 0, sizeof(W)); W.anc0 = (uint32_t)a0; W.anc1 = (uint32_t)(a0 + na); W.dir = (uint8_t)dir; wins[i] = W;
@@ -186,50 +190,17 @@ extern "C" int sim_window_align_bridge(const uint8_t *q, int qlen, const uint8_t
 		}
 		a0 += na;
 	}
+	an.push_back(DevZPair());
 	for(int i = 0; i < n_win; i++){
 		const int s0 = win[3 * (i % n_win0)], s1 = win[3 * (i % n_win0) + 1], na = win[3 * (i % n_win0) + 2];
 		items[i].task = 0; items[i].win = (uint32_t)(i % n_win0);
 		icig[i] = cig_words; cig_words += (unsigned long long)(s0 + s1 + 16 + 2 * na);
-		istep[i] = nsteps64; nsteps64 += (unsigned long long)na; wb_rows += (unsigned long long)(s1 + 16); wb_cols += (unsigned long long)(s0 + 16) + 8ull * (unsigned long long)na;
-		if(s1 + 8 > max_rows) max_rows = s1 + 8;
-		if(s0 + 8 > max_rows) max_rows = s0 + 8;
 	}
-	const uint32_t nitems = (uint32_t)n_win, nsteps = (uint32_t)nsteps64;
-	const int wb_ring = wb_cap(w), wb_rw = wb_row_words(w);
-	const unsigned long long wb_scr_cap = wb_rows * (unsigned long long)(wb_rw + 5) + wb_cols + 8ull * nsteps64 + 1024;
-	const int wgrid = 2;
-	const int wcol = std::min(max_rows + w, 2 * w + 1);
-	unsigned long long slab = (unsigned long long)max_rows * band_row_words<32, WA_C>(wcol) + max_rows + (2ull * max_rows + 2ull * w + 16) + ((unsigned long long)max_rows >> 3) + (w >> 3) + 8;
-	if(2 * w + 3 > WA_CAP){ unsigned long long cap = 1; while(cap < (unsigned long long)(2 * w + 3)) cap <<= 1; slab += 3 * cap; }
-	slab = (slab + 63) & ~63ull;
-	std::vector<uint32_t> arena(std::max(slab * (unsigned long long)wgrid * WA_WARPS, wb_scr_cap) + 64, 0xDEADBEEFu), cg(cig_words + 64, 0u);
+	std::vector<uint32_t> cg(cig_words + 64, 0u);
 	std::vector<DevReg> regs(n_win);
-	std::vector<WBStep> steps(nsteps + 1); memset(steps.data(), 0xEE, steps.size() * sizeof(WBStep));
-	std::vector<unsigned long long> scrw(nsteps + 1, 0), scro(nsteps + 2, 0); std::vector<uint32_t> aopsv((size_t)(nsteps + 1) * (size_t)(acap + 1), 0xEEEEEEEEu); uint32_t *dao = aopsv.data();
-	std::vector<uint32_t> keys(nsteps + 1), ord(nsteps + 1), skeys(nsteps + 1), sord(nsteps + 1), fb(nitems + 1);
-	std::vector<uint8_t> iseq(nitems + 1);
-	unsigned long long ctr[8] = {0, 0, 0, 0, 0, 0, 0, 0};       /* 0 work, 1 cells, 2 windows left out, 3 scratch overflow */
-	const WItem *di = items.data(); const AlnTask *dt = &task; const zmo_pair_t *dp = &pair; const DevWin *dw = wins.data(); const DevZPair *da = an.data();
-	uint32_t *ar = arena.data(), *cgp = cg.data(); const unsigned long long *dic = icig.data(), *dis = istep.data(); DevReg *dr = regs.data(); unsigned long long *cp = ctr;
-	WBStep *ds = steps.data(); unsigned long long *dsw = scrw.data(), *dso = scro.data(); uint32_t *dk = keys.data(), *dord = ord.data(), *dfb = fb.data(); uint8_t *dq = iseq.data();
-	emu::launch((unsigned)(((unsigned long long)nitems * 32 + 127) / 128), 128, [=](){ k_wb_prep(di, nitems, dt, dp, dw, da, R, A, dis, wb_rw, ds, dao, acap, dsw, dk, dord, dq, dfb, cp + 2); });
-	for(uint32_t k = 0; k < nsteps; k++) scro[k + 1] = scro[k] + scrw[k];
-	{
-		std::vector<uint32_t> idx(nsteps); for(uint32_t k = 0; k < nsteps; k++) idx[k] = k;
-		std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b){ return keys[a] > keys[b]; });
-		for(uint32_t k = 0; k < nsteps; k++){ skeys[k] = keys[idx[k]]; sord[k] = ord[idx[k]]; }
-	}
-	const uint32_t *dsk = skeys.data(), *dsor = sord.data(); const uint32_t *wd = R.words;
-	if(nsteps){
-		emu::launch(2, WB_NT, [=](){ k_wb_sweep(ds, dsor, dsk, nsteps, dso, wb_scr_cap, wd, A.P, ar, wb_ring, wb_rw, cp, cp + 3); }, (size_t)wb_ring * 4 * WB_NT);
-		emu::launch((nitems + 63) / 64, 64, [=](){ k_wb_ends(nitems, di, dw, A, dis, dq, ds, dso, ar, wb_rw, cp + 3, cp, 1); });
-		emu::launch((nsteps + 127) / 128, 128, [=](){ k_wb_walk(ds, dsor, dsk, nsteps, dso, wd, A.P, ar, wb_rw, cp + 3); });
-	}
-	emu::launch((unsigned)(((unsigned long long)nitems * 32 + 127) / 128), 128, [=](){ k_wb_stitch(di, nitems, dw, A, dis, dq, ds, dao, acap, dso, ar, wb_rw, cp + 3, cgp, dic, dr); });
-	if(ctr[3]) return -4;       /* scratch bound violated */
-	ctr[0] = 0;
-	emu::launch((unsigned)wgrid, 32 * WA_WARPS, [=](){ k_window_align(di, nitems, dt, dp, dw, da, R, A, ar, slab, max_rows, cgp, dic, dr, cp, 0, 1, dfb, cp + 2); });
-	*n_fallback = (int)ctr[2];
+	const long nfb = sim_wb_pipeline(items.data(), (uint32_t)n_win, &task, &pair, wins.data(), an.data(), win, R, A, acap, icig.data(), cg.data(), regs.data(), budget, nullptr);
+	if(nfb < 0) return (int)nfb;
+	*n_fallback = (int)nfb;
 	int total = 0;
 	for(int i = 0; i < n_win; i++){
 		const DevReg &r = regs[i]; const int b = i % n_win0;

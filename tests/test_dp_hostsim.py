@@ -231,14 +231,14 @@ def test_window_align_kernel(dp_sim, oracle_lib, w):
     assert n_win >= 8
 
 
-@pytest.mark.parametrize("w,sc,copies,acap", [(50, (2, -5, -3, -1, -50), 1, 22), (20, (2, -5, -3, -1, -50), 9, 22), (91, (2, -5, -3, -1, -50), 1, 22), (50, (1, -3, -2, -2, -10), 1, 22), (50, (2, -5, -3, -1, -20), 1, 22), (50, (2, -5, -3, -1, -50), 1, 6),
+@pytest.mark.parametrize("w,sc,copies,acap", [(50, (2, -5, -3, -1, -50), 1, 22), (20, (2, -5, -3, -1, -50), 9, 22), (91, (2, -5, -3, -1, -50), 1, 22), (50, (1, -3, -2, -2, -10), 1, 22), (50, (2, -5, -3, -1, -20), 1, 22), (50, (2, -5, -3, -1, -50), 1, 6), (50, (2, -5, -3, -1, -50), 0, 22),
                                                     (50, (2, -5, -3, -1, -50), -12, 22), (20, (2, -5, -3, -1, -50), -7, 22), (91, (2, -5, -3, -1, -50), -30, 22),
                                                     (30, (3, -4, -5, -2, -30), -5, 22), (10, (1, -1, -1, -1, -5), -9, 22), (64, (5, -9, -7, -3, -200), -16, 22), (50, (2, -30, -3, -1, -50), -12, 22)])
 def test_window_align_bridge_pipeline(dp_sim, oracle_lib, w, sc, copies, acap):
     """bridge-level window alignment (zmo_winbridge.cuh: k_wb_prep / k_wb_sweep / k_wb_ends / k_wb_walk / k_wb_stitch + k_window_align for the
     windows left out) against the oracle's fast_seeds_align_hzmo on the windows and anchors of real read pairs, both strands.  The sweep runs
     every bridge with init = 0; the test is the claim that this shift changes nothing.  -T -20: max_gap(0) < w for short bridges, so those
-    windows must take the sequential kernel (likewise anchors with more CIGAR ops than acap); copies < 0: anchors thinned out so that bridges are longer than the band is wide; copies = 9: more than 32 bridges per warp and several rounds"""
+    windows must take the sequential kernel (likewise anchors with more CIGAR ops than acap); copies < 0: anchors thinned out so that bridges are longer than the band is wide; copies = 9: more than 32 bridges per warp and several rounds; copies = 0: one window per pass of the pipeline"""
     from test_seed_core import pairs
     M, X, O, E, T = sc
     n_win = n_fb = 0
